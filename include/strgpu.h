@@ -1,0 +1,121 @@
+/*
+ * strgpu.h -- C ABI of libstrgpu.so, the B200 (sm_100a) implementation of STRling's data-parallel hot path.
+ *
+ * STRling (Nim) has no plugin/FFI surface of its own; the boundary is the set of Nim procs a shim replaces.
+ * Every entry point below cites the reference interface it stands in for (paths relative to the reference
+ * checkout).  INTEGRATION.md shows the Nim `importc` binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * strgpu_status; nothing aborts or exits (the reference `quit`s / doAsserts -- the shim maps a non-zero
+ * status to `quit`).  One ctx per host thread and per GPU.  All structs are little-endian PODs with the
+ * exact layouts below (static_asserted in the implementation).
+ */
+#ifndef STRGPU_H
+#define STRGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct strgpu_ctx strgpu_ctx;
+
+typedef enum {
+  STRGPU_OK = 0,
+  STRGPU_ERR_INVALID = -1,       /* bad argument */
+  STRGPU_ERR_CUDA = -2,          /* CUDA runtime error; see strgpu_last_error */
+  STRGPU_ERR_NO_DEVICE = -3,     /* no usable sm_100 device: the library never falls back to the CPU */
+  STRGPU_ERR_TOO_LONG = -4,      /* a segment is longer than STRGPU_MAX_SEGMENT_LEN (or than max_len passed) */
+  STRGPU_ERR_BUSY = -5,          /* no free submit slot: wait on an earlier ticket first */
+  STRGPU_ERR_TICKET = -6,        /* unknown / already consumed ticket */
+  STRGPU_ERR_OVERFLOW = -7       /* an output capacity was too small */
+} strgpu_status;
+
+/* The reference counts k-mers in uint8 tables with overflow checks off (utils.nim:9,113-117,192-195);
+ * beyond 510 bases a count can wrap, so longer segments are rejected instead of reproducing the wrap. */
+#define STRGPU_MAX_SEGMENT_LEN 510
+#define STRGPU_MAX_PCLASS 4
+#define STRGPU_SLOTS 3            /* submit/wait pipeline depth */
+
+/* ---- sequence encoding -------------------------------------------------------------------------
+ * seq2: 2 bits per base, 4 bases per byte, first base in bits 7..6 (byte-wise big-endian, like BAM's
+ * 4-bit packing).  Codes C=0 A=1 T=2 G=3 -- the order of the `kmer` nimble package the reference scans
+ * with (utils.nim:14,19,245).  A non-ACGT base is stored as 1 ('A', as that package encodes it) and is
+ * additionally flagged in nmask: bit (b & 31) of 32-bit word (b >> 5), b = absolute base index.
+ * nmask may be NULL when no segment has STRGPU_SEG_HAS_N set.
+ * The seq2 buffer handed to the library must be readable for 8 bytes past the last base
+ * (strgpu_seq2_bytes() includes that slack); nmask for 8 bytes past its last word likewise.
+ */
+#define STRGPU_SEG_HAS_N 0x01u
+
+/* One scan unit: a read, a soft-clipped end of a read, or a reference window.
+ * Replaces the `read: var string` argument of get_repeat (utils.nim:236). */
+typedef struct {
+  uint32_t base_off;   /* index of the segment's first base in seq2 / nmask */
+  uint16_t len;        /* bases; 0..STRGPU_MAX_SEGMENT_LEN */
+  uint8_t  pclass;     /* which proportion_repeat (strgpu_set_proportions) applies: opts.proportion_repeat */
+  uint8_t  flags;      /* STRGPU_SEG_* */
+} strgpu_segment;      /* 8 bytes */
+
+/* Result of get_repeat (utils.nim:236-271): `result: array[6, char]` zero padded, and `repeat_count`
+ * (already multiplied by reduce_repeat, utils.nim:271). */
+typedef struct {
+  char     unit[6];
+  uint16_t repeat_count;
+} strgpu_repeat;       /* 8 bytes */
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+const char *strgpu_version(void);
+const char *strgpu_error_string(int status);
+/* device: CUDA ordinal.  Fails with STRGPU_ERR_NO_DEVICE unless it is compute capability 10.x. */
+int  strgpu_create(strgpu_ctx **ctx, int device);
+void strgpu_destroy(strgpu_ctx *ctx);
+const char *strgpu_last_error(const strgpu_ctx *ctx);
+/* kernels launched by this ctx since creation (for benchmark accounting) */
+uint64_t strgpu_launch_count(const strgpu_ctx *ctx);
+
+/* Pinned host memory for submit buffers (optional but needed for copy/compute overlap). */
+int  strgpu_host_alloc(void **ptr, size_t bytes);
+void strgpu_host_free(void *ptr);
+
+/* ---- scan: get_repeat(read, counts, repeat_count, opts) -- utils.nim:236, called from
+ * extract.nim:40 (whole read), extract.nim:114 (soft clip), genome_strs.nim:74 (reference window) ---- */
+
+/* The proportion_repeat values in play (extract.nim:204-211,240-244 uses p, p-0.07 and min(p,0.6)).
+ * Thresholds int(len*p/k) and int(len*0.12/k) (utils.nim:251,259) are tabulated on the host in fp64
+ * exactly as the reference computes them. */
+int strgpu_set_proportions(strgpu_ctx *ctx, const double *p, int n);
+
+/* bytes to allocate for n_bases of seq2 / nmask, slack included */
+size_t strgpu_seq2_bytes(uint64_t n_bases);
+size_t strgpu_nmask_bytes(uint64_t n_bases);
+/* Host packers: write `len` bases at base index base_off.  Return the number of non-ACGT bases.
+ * ascii: what hts-nim's aln.sequence() yields (extract.nim:37); bam4: the BAM record's 4-bit SEQ field.
+ * base_off must be a multiple of 4 for the packers (segments themselves may start anywhere). */
+int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint64_t base_off);
+int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint64_t base_off);
+
+/* Asynchronous host API.  Copies the batch to the device on an internal stream, runs the scan, copies the
+ * results back; strgpu_scan_wait blocks until `out` (n_seg records) is filled.  Buffers must stay valid
+ * until the wait returns.  max_len: upper bound of segment lengths in this batch (selects the kernel
+ * variant; a longer segment yields STRGPU_ERR_TOO_LONG at wait). */
+int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask,
+                       const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len,
+                       strgpu_repeat *out, int *ticket);
+int strgpu_scan_wait(strgpu_ctx *ctx, int ticket);
+/* submit + wait */
+int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask,
+                const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len, strgpu_repeat *out);
+/* Device-resident variant: all pointers are device pointers on ctx's device; the kernel is enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream) and the call returns without synchronising.
+ * A too-long segment is reported by the next strgpu_device_status(). */
+int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask, const void *d_segs,
+                       uint32_t n_seg, uint32_t max_len, void *d_out, void *cuda_stream);
+/* synchronises `cuda_stream` and returns the sticky device-side status of launches since the last call */
+int strgpu_device_status(strgpu_ctx *ctx, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRGPU_H */

@@ -1,0 +1,173 @@
+"""ctypes binding of libstrgpu.so (include/strgpu.h).  The names mirror the reference procs they replace:
+`StrGpu.get_repeat` <- get_repeat (utils.nim:236), `StrGpu.cluster` <- cluster/bounds (cluster.nim:364,
+callclusters.nim:52).  Nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstrgpu.so")
+
+SEGMENT_DTYPE = np.dtype([("base_off", "<u4"), ("len", "<u2"), ("pclass", "u1"), ("flags", "u1")])
+REPEAT_DTYPE = np.dtype([("unit", "S6"), ("repeat_count", "<u2")])
+assert SEGMENT_DTYPE.itemsize == 8 and REPEAT_DTYPE.itemsize == 8
+SEG_HAS_N = 1
+MAX_SEGMENT_LEN = 510
+
+_lib = None
+
+
+class StrGpuError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"strgpu status {status}: {msg}")
+        self.status = status
+
+
+def load_library():
+    """Loads the in-tree CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m strling_b200.build` (or __graft_entry__.build()); "
+                          "there is no CPU fallback for the scan / cluster kernels")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.strgpu_version.restype = C.c_char_p
+    L.strgpu_error_string.argtypes = [i32]
+    L.strgpu_error_string.restype = C.c_char_p
+    L.strgpu_create.argtypes = [C.POINTER(vp), i32]
+    L.strgpu_destroy.argtypes = [vp]
+    L.strgpu_destroy.restype = None
+    L.strgpu_last_error.argtypes = [vp]
+    L.strgpu_last_error.restype = C.c_char_p
+    L.strgpu_launch_count.argtypes = [vp]
+    L.strgpu_launch_count.restype = u64
+    L.strgpu_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.strgpu_host_free.argtypes = [vp]
+    L.strgpu_host_free.restype = None
+    L.strgpu_set_proportions.argtypes = [vp, C.POINTER(C.c_double), i32]
+    L.strgpu_seq2_bytes.argtypes = [u64]
+    L.strgpu_seq2_bytes.restype = C.c_size_t
+    L.strgpu_nmask_bytes.argtypes = [u64]
+    L.strgpu_nmask_bytes.restype = C.c_size_t
+    L.strgpu_pack_ascii.argtypes = [vp, u32, vp, vp, u64]
+    L.strgpu_pack_bam4.argtypes = [vp, u32, vp, vp, u64]
+    L.strgpu_scan_submit.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp, C.POINTER(i32)]
+    L.strgpu_scan_wait.argtypes = [vp, i32]
+    L.strgpu_scan.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp]
+    L.strgpu_scan_device.argtypes = [vp, vp, vp, vp, u32, u32, vp, vp]
+    L.strgpu_device_status.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def pack_reads(reads, pclass=0, align_bases: int = 16):
+    """Packs ASCII reads into one seq2 buffer (+ N mask) and one whole-read segment per read.
+    Each read starts at a multiple of `align_bases` (>= 4).  Returns (seq2 u8, nmask u32 or None, segments, n_bases)."""
+    L = load_library()
+    reads = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+    n = len(reads)
+    lens = np.fromiter((len(r) for r in reads), dtype=np.int64, count=n)
+    padded = (lens + align_bases - 1) // align_bases * align_bases
+    offs = np.zeros(n, dtype=np.int64)
+    if n:
+        offs[1:] = np.cumsum(padded)[:-1]
+    n_bases = int(padded.sum())
+    seq2 = np.zeros(L.strgpu_seq2_bytes(n_bases), dtype=np.uint8)
+    nmask = np.zeros(L.strgpu_nmask_bytes(n_bases) // 4, dtype=np.uint32)
+    segs = np.zeros(n, dtype=SEGMENT_DTYPE)
+    segs["base_off"] = offs
+    segs["len"] = lens
+    segs["pclass"] = pclass
+    any_n = False
+    for i, r in enumerate(reads):
+        k = L.strgpu_pack_ascii(r, len(r), seq2.ctypes.data, nmask.ctypes.data, int(offs[i]))
+        if k < 0:
+            raise StrGpuError(k, "pack_ascii")
+        if k:
+            segs["flags"][i] |= SEG_HAS_N
+            any_n = True
+    return seq2, (nmask if any_n else None), segs, n_bases
+
+
+class StrGpu:
+    """One context per process and GPU (include/strgpu.h)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.strgpu_create(C.byref(h), device)
+        if rc != 0:
+            msg = self.L.strgpu_last_error(h).decode() if h else self.L.strgpu_error_string(rc).decode()
+            if h:
+                self.L.strgpu_destroy(h)
+            raise StrGpuError(rc, msg)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.strgpu_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise StrGpuError(rc, self.L.strgpu_last_error(self.h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.strgpu_launch_count(self.h))
+
+    def set_proportions(self, ps):
+        arr = (C.c_double * len(ps))(*ps)
+        self._check(self.L.strgpu_set_proportions(self.h, arr, len(ps)))
+
+    # ---- scan ---------------------------------------------------------------------------------
+    def scan(self, seq2: np.ndarray, n_bases: int, nmask, segs: np.ndarray, max_len: int | None = None) -> np.ndarray:
+        """get_repeat for every segment (host buffers in, host results out)."""
+        segs = np.ascontiguousarray(segs, dtype=SEGMENT_DTYPE)
+        out = np.zeros(len(segs), dtype=REPEAT_DTYPE)
+        if max_len is None:
+            max_len = int(segs["len"].max()) if len(segs) else 0
+        self._check(self.L.strgpu_scan(self.h, seq2.ctypes.data, n_bases, None if nmask is None else nmask.ctypes.data,
+                                       segs.ctypes.data, len(segs), max_len, out.ctypes.data))
+        return out
+
+    def scan_submit(self, seq2, n_bases, nmask, segs, max_len, out) -> int:
+        t = C.c_int(-1)
+        self._check(self.L.strgpu_scan_submit(self.h, seq2.ctypes.data, n_bases, None if nmask is None else nmask.ctypes.data,
+                                              segs.ctypes.data, len(segs), max_len, out.ctypes.data, C.byref(t)))
+        return t.value
+
+    def scan_wait(self, ticket: int):
+        self._check(self.L.strgpu_scan_wait(self.h, ticket))
+
+    def scan_device(self, d_seq2: int, d_nmask: int | None, d_segs: int, n_seg: int, max_len: int, d_out: int, stream: int = 0):
+        self._check(self.L.strgpu_scan_device(self.h, d_seq2, d_nmask, d_segs, n_seg, max_len, d_out, stream or None))
+
+    def device_status(self, stream: int = 0):
+        self._check(self.L.strgpu_device_status(self.h, stream or None))
+
+    def get_repeat(self, reads, p: float = 0.8):
+        """Convenience mirror of get_repeat(read, ..) (utils.nim:236) for a list of ASCII reads.
+        Returns a list of (unit bytes, repeat_count)."""
+        self.set_proportions([p])
+        seq2, nmask, segs, n_bases = pack_reads(reads, 0)
+        res = self.scan(seq2, n_bases, nmask, segs)
+        return [(bytes(r["unit"]).rstrip(b"\0"), int(r["repeat_count"])) for r in res]

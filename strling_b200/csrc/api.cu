@@ -1,0 +1,274 @@
+// C ABI of libstrgpu.so (include/strgpu.h): context, device buffers, streams, the submit/wait pipeline.
+// There is deliberately no CPU code path for the scan or the cluster kernels: without an sm_100 device
+// every compute entry point fails with STRGPU_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "scan_kernels.cuh"
+#include "strgpu.h"
+
+static_assert(sizeof(strgpu_segment) == 8, "strgpu_segment layout");
+static_assert(sizeof(strgpu_repeat) == 8, "strgpu_repeat layout");
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  DevBuf seq, nmask, segs, out;
+  bool busy = false;
+  strgpu_repeat *host_out = nullptr;
+  uint32_t n_seg = 0;
+  int *d_status = nullptr;
+  int *h_status = nullptr;  // pinned
+};
+
+}  // namespace
+
+struct strgpu_ctx {
+  int device = -1;
+  int sm_count = 0;
+  uint16_t *d_thr = nullptr;
+  bool thr_set = false;
+  Slot slots[STRGPU_SLOTS];
+  int *d_status_dev = nullptr;  // sticky status for strgpu_scan_device launches
+  uint64_t launches = 0;
+  char err[512] = {0};
+};
+
+namespace {
+
+int fail(strgpu_ctx *ctx, int status, const char *fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return status;
+}
+
+#define CU(ctx, call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(ctx, STRGPU_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+int ensure(strgpu_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return STRGPU_OK;
+  if (b.p) CU(ctx, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t cap = bytes + bytes / 4 + 256;
+  CU(ctx, cudaMalloc(&b.p, cap));
+  b.cap = cap;
+  return STRGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *strgpu_version(void) { return "strling-b200 0.1.0 (STRling 0.6.0 hot path, sm_100a)"; }
+
+const char *strgpu_error_string(int status) {
+  switch (status) {
+    case STRGPU_OK: return "ok";
+    case STRGPU_ERR_INVALID: return "invalid argument";
+    case STRGPU_ERR_CUDA: return "CUDA error";
+    case STRGPU_ERR_NO_DEVICE: return "no sm_100 CUDA device (no CPU fallback exists)";
+    case STRGPU_ERR_TOO_LONG: return "segment longer than supported";
+    case STRGPU_ERR_BUSY: return "no free submit slot";
+    case STRGPU_ERR_TICKET: return "bad ticket";
+    case STRGPU_ERR_OVERFLOW: return "output capacity too small";
+    default: return "unknown status";
+  }
+}
+
+int strgpu_create(strgpu_ctx **out, int device) {
+  if (!out) return STRGPU_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return STRGPU_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return STRGPU_ERR_NO_DEVICE;
+  if (prop.major != 10) return STRGPU_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  strgpu_ctx *ctx = new (std::nothrow) strgpu_ctx();
+  if (!ctx) return STRGPU_ERR_INVALID;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  CU(ctx, cudaSetDevice(device));
+  CU(ctx, cudaMalloc(&ctx->d_thr, strgpu::kThrEntries * sizeof(uint16_t)));
+  CU(ctx, cudaMalloc(&ctx->d_status_dev, sizeof(int)));
+  CU(ctx, cudaMemset(ctx->d_status_dev, 0, sizeof(int)));
+  for (auto &s : ctx->slots) {
+    CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CU(ctx, cudaMalloc(&s.d_status, sizeof(int)));
+    CU(ctx, cudaMallocHost(&s.h_status, sizeof(int)));
+  }
+  const double dflt[3] = {0.8, 0.8 - 0.07, 0.6};  // extract.nim:255,208,242 defaults
+  return strgpu_set_proportions(ctx, dflt, 3);
+}
+
+void strgpu_destroy(strgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto &s : ctx->slots) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (DevBuf *b : {&s.seq, &s.nmask, &s.segs, &s.out})
+      if (b->p) cudaFree(b->p);
+    if (s.d_status) cudaFree(s.d_status);
+    if (s.h_status) cudaFreeHost(s.h_status);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  if (ctx->d_thr) cudaFree(ctx->d_thr);
+  if (ctx->d_status_dev) cudaFree(ctx->d_status_dev);
+  delete ctx;
+}
+
+const char *strgpu_last_error(const strgpu_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+uint64_t strgpu_launch_count(const strgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int strgpu_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return STRGPU_ERR_INVALID;
+  return cudaMallocHost(ptr, bytes ? bytes : 1) == cudaSuccess ? STRGPU_OK : STRGPU_ERR_CUDA;
+}
+void strgpu_host_free(void *ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+int strgpu_set_proportions(strgpu_ctx *ctx, const double *p, int n) {
+  if (!ctx || !p || n < 1 || n > STRGPU_MAX_PCLASS) return fail(ctx, STRGPU_ERR_INVALID, "set_proportions: n=%d", n);
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint16_t *h = (uint16_t *)malloc(strgpu::kThrEntries * sizeof(uint16_t));
+  if (!h) return fail(ctx, STRGPU_ERR_INVALID, "out of host memory");
+  for (int cls = 0; cls <= STRGPU_MAX_PCLASS; cls++) {
+    // classes past n repeat the last given one; the extra class is the 0.12 give-up bound (utils.nim:251)
+    const double pv = (cls == STRGPU_MAX_PCLASS) ? 0.12 : p[cls < n ? cls : n - 1];
+    for (int k = 2; k <= 6; k++)
+      for (int len = 0; len < strgpu::kThrLen; len++) {
+        // (read.len.float * p / k.float).int : fp64 multiply, fp64 divide, truncate (utils.nim:251,259)
+        volatile double prod = (double)len * pv;
+        volatile double q = prod / (double)k;
+        long v = (long)q;
+        if (v < 0) v = 0;
+        if (v > 65535) v = 65535;
+        h[(cls * 5 + (k - 2)) * strgpu::kThrLen + len] = (uint16_t)v;
+      }
+  }
+  // all slots idle? thresholds are read by in-flight kernels, so drain first
+  for (auto &s : ctx->slots) CU(ctx, cudaStreamSynchronize(s.stream));
+  cudaError_t e = cudaMemcpy(ctx->d_thr, h, strgpu::kThrEntries * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  free(h);
+  if (e != cudaSuccess) return fail(ctx, STRGPU_ERR_CUDA, "thresholds upload: %s", cudaGetErrorString(e));
+  ctx->thr_set = true;
+  return STRGPU_OK;
+}
+
+size_t strgpu_seq2_bytes(uint64_t n_bases) { return (size_t)((n_bases + 3) / 4) + 8; }
+size_t strgpu_nmask_bytes(uint64_t n_bases) { return (size_t)((n_bases + 31) / 32) * 4 + 8; }
+
+int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask,
+                       const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len, strgpu_repeat *out, int *ticket) {
+  if (!ctx || !ticket || (n_seg && (!seq2 || !segs || !out))) return fail(ctx, STRGPU_ERR_INVALID, "scan_submit: null argument");
+  if (max_len > STRGPU_MAX_SEGMENT_LEN) return fail(ctx, STRGPU_ERR_TOO_LONG, "max_len %u > %d", max_len, STRGPU_MAX_SEGMENT_LEN);
+  int si = -1;
+  for (int i = 0; i < STRGPU_SLOTS; i++)
+    if (!ctx->slots[i].busy) { si = i; break; }
+  if (si < 0) return fail(ctx, STRGPU_ERR_BUSY, "all %d submit slots in flight", STRGPU_SLOTS);
+  Slot &s = ctx->slots[si];
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t seq_bytes = (size_t)((n_bases + 3) / 4);
+  const size_t nm_bytes = nmask ? (size_t)((n_bases + 31) / 32) * 4 : 0;
+  int rc;
+  if ((rc = ensure(ctx, s.seq, seq_bytes + 16))) return rc;
+  if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
+  if ((rc = ensure(ctx, s.segs, (size_t)n_seg * sizeof(strgpu_segment) + 16))) return rc;
+  if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
+  s.n_seg = n_seg;
+  s.host_out = out;
+  if (n_seg) {
+    CU(ctx, cudaMemcpyAsync(s.seq.p, seq2, seq_bytes, cudaMemcpyHostToDevice, s.stream));
+    CU(ctx, cudaMemsetAsync((char *)s.seq.p + seq_bytes, 0, 16, s.stream));
+    if (nmask) {
+      CU(ctx, cudaMemcpyAsync(s.nmask.p, nmask, nm_bytes, cudaMemcpyHostToDevice, s.stream));
+      CU(ctx, cudaMemsetAsync((char *)s.nmask.p + nm_bytes, 0, 16, s.stream));
+    }
+    CU(ctx, cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(strgpu_segment), cudaMemcpyHostToDevice, s.stream));
+    CU(ctx, cudaMemsetAsync(s.d_status, 0, sizeof(int), s.stream));
+    CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
+                                       (const strgpu_segment *)s.segs.p, n_seg, max_len, ctx->d_thr,
+                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, s.stream));
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
+    CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  } else {
+    *s.h_status = 0;
+  }
+  CU(ctx, cudaEventRecord(s.done, s.stream));
+  s.busy = true;
+  *ticket = si;
+  return STRGPU_OK;
+}
+
+int strgpu_scan_wait(strgpu_ctx *ctx, int ticket) {
+  if (!ctx || ticket < 0 || ticket >= STRGPU_SLOTS || !ctx->slots[ticket].busy)
+    return fail(ctx, STRGPU_ERR_TICKET, "scan_wait: bad ticket %d", ticket);
+  Slot &s = ctx->slots[ticket];
+  cudaError_t e = cudaEventSynchronize(s.done);
+  s.busy = false;
+  if (e != cudaSuccess) return fail(ctx, STRGPU_ERR_CUDA, "scan_wait: %s", cudaGetErrorString(e));
+  if (*s.h_status != 0) return fail(ctx, *s.h_status, "scan: %s", strgpu_error_string(*s.h_status));
+  return STRGPU_OK;
+}
+
+int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask, const strgpu_segment *segs,
+                uint32_t n_seg, uint32_t max_len, strgpu_repeat *out) {
+  int t = -1;
+  int rc = strgpu_scan_submit(ctx, seq2, n_bases, nmask, segs, n_seg, max_len, out, &t);
+  if (rc) return rc;
+  return strgpu_scan_wait(ctx, t);
+}
+
+int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask, const void *d_segs, uint32_t n_seg,
+                       uint32_t max_len, void *d_out, void *cuda_stream) {
+  if (!ctx || (n_seg && (!d_seq2 || !d_segs || !d_out))) return fail(ctx, STRGPU_ERR_INVALID, "scan_device: null argument");
+  if (max_len > STRGPU_MAX_SEGMENT_LEN) return fail(ctx, STRGPU_ERR_TOO_LONG, "max_len %u > %d", max_len, STRGPU_MAX_SEGMENT_LEN);
+  if (((uintptr_t)d_seq2 & 3) || ((uintptr_t)d_nmask & 3) || ((uintptr_t)d_segs & 7) || ((uintptr_t)d_out & 7))
+    return fail(ctx, STRGPU_ERR_INVALID, "scan_device: misaligned device pointer");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_segs,
+                                     n_seg, max_len, ctx->d_thr, (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count,
+                                     (cudaStream_t)cuda_stream));
+  if (n_seg) ctx->launches++;
+  return STRGPU_OK;
+}
+
+int strgpu_device_status(strgpu_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return STRGPU_ERR_INVALID;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  int st = 0;
+  CU(ctx, cudaMemcpy(&st, ctx->d_status_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st != 0) {
+    CU(ctx, cudaMemset(ctx->d_status_dev, 0, sizeof(int)));
+    return fail(ctx, st, "device: %s", strgpu_error_string(st));
+  }
+  return STRGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,20 @@
+// Launch interface of the repeat-unit scan kernels (K1).  Internal to libstrgpu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "strgpu.h"
+
+namespace strgpu {
+
+constexpr int kThrLen = 512;                    // thresholds tabulated for len 0..511
+constexpr int kThrClasses = STRGPU_MAX_PCLASS + 1;  // + the 0.12 "give up" class (utils.nim:251)
+constexpr int kThrEntries = kThrClasses * 5 * kThrLen;
+constexpr int kShortMaxLen = 160;               // kernel variant with the read in <= 10 words
+
+// thr[(cls * 5 + (k - 2)) * kThrLen + len] = int(len * p_cls / k); cls == STRGPU_MAX_PCLASS holds int(len * 0.12 / k)
+cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
+                               uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, strgpu_repeat *d_out,
+                               int *d_status, int sm_count, cudaStream_t stream);
+
+}  // namespace strgpu

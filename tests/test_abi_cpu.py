@@ -1,0 +1,74 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/strgpu.h
+declares, refuses to compute without a GPU (no CPU fallback), and its host packers agree with numpy."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import strling_b200 as sb
+from strling_b200 import build as sb_build
+from strling_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sb_build.build_lib()
+    return sb.load_library()
+
+
+def test_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "strgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(strgpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"libstrgpu.so does not export {n}"
+
+
+def test_struct_layouts():
+    assert sb.SEGMENT_DTYPE.itemsize == 8 and sb.REPEAT_DTYPE.itemsize == 8
+    assert sb.SEGMENT_DTYPE.fields["len"][1] == 4 and sb.REPEAT_DTYPE.fields["repeat_count"][1] == 6
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sb.StrGpuError) as e:
+        sb.StrGpu(0)
+    assert e.value.status == -3
+
+
+def test_pack_ascii_matches_numpy(lib):
+    reads, _, _, _ = synth.make_reads(300, seed=5, length=150, n_frac=0.2)
+    seq2_np, nmask_np, stride = synth.pack_matrix(reads)
+    seq2, nmask, segs, n_bases = sb.pack_reads([bytes(r) for r in reads])
+    assert n_bases == 300 * stride
+    assert np.array_equal(seq2[: n_bases // 4], seq2_np[: n_bases // 4])
+    assert nmask is not None and np.array_equal(nmask[: n_bases // 32], nmask_np[: n_bases // 32])
+    assert np.array_equal(segs["base_off"], np.arange(300) * stride)
+
+
+def test_pack_bam4_matches_ascii(lib):
+    rng = np.random.default_rng(3)
+    alphabet = b"=ACMGRSVTWYHKDBN"
+    for length in (0, 1, 2, 3, 4, 5, 7, 8, 150, 151):
+        nib = rng.integers(0, 16, size=length).astype(np.uint8)
+        ascii_seq = bytes(alphabet[i] for i in nib)
+        bam = np.zeros((length + 1) // 2 + 1, dtype=np.uint8)
+        for i, v in enumerate(nib):
+            bam[i // 2] |= v << (4 if i % 2 == 0 else 0)
+        nb = 160
+        a2 = np.zeros(lib.strgpu_seq2_bytes(nb), dtype=np.uint8)
+        b2 = np.zeros_like(a2)
+        am = np.zeros(lib.strgpu_nmask_bytes(nb) // 4, dtype=np.uint32)
+        bm = np.zeros_like(am)
+        ka = lib.strgpu_pack_ascii(ascii_seq, length, a2.ctypes.data, am.ctypes.data, 0)
+        kb = lib.strgpu_pack_bam4(bam.ctypes.data, length, b2.ctypes.data, bm.ctypes.data, 0)
+        assert ka == kb == sum(c not in b"ACGT" for c in ascii_seq)
+        assert np.array_equal(a2, b2) and np.array_equal(am, bm)

@@ -80,7 +80,7 @@ def test_scan_examples(read, p, unit, rc):
 
 
 def test_base_order_evidence():  # genome_strs.nim:204 : a get_repeat-produced unit `CACGAT`
-    assert orc.get_repeat("ACGATC" * 16 + "ACGA", 0.8)[0] == b"CACGAT"
+    assert orc.get_repeat("ACGATC" * 16 + "ACGA", 0.8) == (b"CACGAT", 15)
 
 
 def test_scan_edge_cases():

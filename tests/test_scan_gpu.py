@@ -1,0 +1,139 @@
+"""Parity of the CUDA repeat-unit scan (K1, through the C ABI) against the CPU oracle: bit-exact unit and
+repeat_count for every segment.  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+
+import strling_b200 as sb
+from oracle import oracle as orc
+from strling_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+P = [0.8, 0.8 - 0.07, 0.6]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    g = sb.StrGpu(0)
+    g.set_proportions(P)
+    yield g
+    g.close()
+
+
+def oracle_for(reads_ascii_flat, off, lens, pclass):
+    p = np.asarray(P)[pclass]
+    return orc.get_repeat_batch(reads_ascii_flat, off, lens, p)
+
+
+def check(gpu, reads, segs, stride, seq2, nmask):
+    res = gpu.scan(seq2, reads.shape[0] * stride, nmask, segs)
+    flat, off, lens = synth.segment_ascii(reads, segs, stride)
+    units, counts = oracle_for(flat, off, lens, segs["pclass"])
+    bad = np.nonzero((res["unit"] != units) | (res["repeat_count"] != counts))[0]
+    if len(bad):
+        i = int(bad[0])
+        s = bytes(flat[int(off[i]): int(off[i]) + int(lens[i])])
+        raise AssertionError(f"{len(bad)} mismatches; first seg {i} len {lens[i]} pclass {segs['pclass'][i]} "
+                             f"gpu=({res['unit'][i]},{res['repeat_count'][i]}) oracle=({units[i]},{counts[i]}) read={s}")
+    return res
+
+
+def test_reference_known_answers(gpu):
+    # tests/test_strling.nim:46-89 through the GPU path
+    assert gpu.get_repeat(["A" * 150], 0.6) == [(b"A", 150)]
+    assert gpu.get_repeat(["TGC" * 50 + "T"], 0.8) == [(b"CTG", 49)]
+    assert gpu.get_repeat(["CAG" * 50, "ATTCT" * 30, "AC" * 75, "ACGATC" * 16 + "ACGA"], 0.8) == [
+        (b"CAG", 50), (b"CTATT", 29), (b"CA", 74), (b"CACGAT", 15)]
+    gpu.set_proportions(P)
+
+
+def test_config2_mix_150bp(gpu):
+    reads, cls, lclip, rclip = synth.make_reads(200_000, seed=2)
+    seq2, nmask, stride = synth.pack_matrix(reads)
+    segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+    res = check(gpu, reads, segs, stride, seq2, nmask)
+    assert (res["repeat_count"] > 0).sum() > 1000  # the STR classes are actually found
+
+
+def test_reads_with_N(gpu):
+    reads, cls, lclip, rclip = synth.make_reads(50_000, seed=11, n_frac=0.3, mix=(0.5, 0.1, 0.2, 0.2))
+    seq2, nmask, stride = synth.pack_matrix(reads)
+    segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+    assert nmask is not None
+    check(gpu, reads, segs, stride, seq2, nmask)
+
+
+def test_all_p_classes_and_unaligned_segments(gpu):
+    reads, cls, lclip, rclip = synth.make_reads(30_000, seed=4, mix=(0.2, 0.1, 0.3, 0.4), noise=0.03)
+    seq2, nmask, stride = synth.pack_matrix(reads)
+    rng = np.random.default_rng(9)
+    n = reads.shape[0]
+    segs = np.zeros(4 * n, dtype=sb.SEGMENT_DTYPE)
+    start = rng.integers(0, 150, size=4 * n)
+    ln = rng.integers(0, 151, size=4 * n)
+    ln = np.minimum(ln, 150 - start)
+    segs["base_off"] = np.repeat(np.arange(n), 4) * stride + start
+    segs["len"] = ln
+    segs["pclass"] = rng.integers(0, 3, size=4 * n)
+    check(gpu, reads, segs, stride, seq2, nmask)
+
+
+@pytest.mark.parametrize("length", [161, 250, 301, 510])
+def test_long_segments(gpu, length):
+    reads, cls, lclip, rclip = synth.make_reads(20_000, seed=length, length=length, mix=(0.4, 0.1, 0.2, 0.3),
+                                                noise=0.02, n_frac=0.05)
+    seq2, nmask, stride = synth.pack_matrix(reads)
+    segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+    check(gpu, reads, segs, stride, seq2, nmask)
+
+
+def test_adversarial_short_and_periodic(gpu):
+    rng = np.random.default_rng(77)
+    reads = []
+    for L in list(range(0, 40)) + [64, 65, 66, 96, 97, 98, 99, 128, 131, 132, 133, 159, 160]:
+        reads.append("".join(rng.choice(list("ACGT"), size=L)))
+        for unit in ("A", "C", "G", "T", "AC", "CA", "GT", "AAC", "CAG", "GGC", "AAAG", "ACGT", "TTTTA", "AACCC",
+                     "AAAAAT", "ACGATC", "CCCCCG", "ACACAT"):
+            s = (unit * (L // len(unit) + 2))
+            for ph in range(min(len(unit), 3)):
+                reads.append(s[ph: ph + L])
+    # two units competing for the leader (tie-break = first to reach the maximum)
+    for a, b in (("AC", "GT"), ("CAG", "TTG"), ("AAAG", "CCCT")):
+        for na in range(1, 20, 3):
+            reads.append((a * na + b * na)[:160])
+            reads.append((b * na + a * na)[:160])
+            reads.append(((a + b) * na)[:160])
+    reads = [r for r in reads if len(r) <= 160]
+    for pcls, p in enumerate(P):
+        gpu.set_proportions(P)
+        seq2, nmask, segs, n_bases = sb.pack_reads(reads, pcls)
+        res = gpu.scan(seq2, n_bases, nmask, segs)
+        for r, got in zip(reads, res):
+            exp = orc.get_repeat(r, p)
+            assert (bytes(got["unit"]).rstrip(b"\0"), int(got["repeat_count"])) == exp, (r, p, got, exp)
+
+
+def test_too_long_segment_is_reported(gpu):
+    seq2, nmask, segs, n_bases = sb.pack_reads(["A" * 200])
+    with pytest.raises(sb.StrGpuError) as e:
+        gpu.scan(seq2, n_bases, nmask, segs, max_len=160)  # caller lied about max_len
+    assert e.value.status == -4
+    res = gpu.scan(seq2, n_bases, nmask, segs)  # honest max_len picks the long-segment kernel
+    assert (bytes(res[0]["unit"]).rstrip(b"\0"), int(res[0]["repeat_count"])) == (b"A", 200)
+
+
+def test_submit_wait_pipeline(gpu):
+    reads, cls, lclip, rclip = synth.make_reads(60_000, seed=21)
+    seq2, nmask, stride = synth.pack_matrix(reads)
+    segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+    outs = [np.zeros(len(segs), dtype=sb.REPEAT_DTYPE) for _ in range(3)]
+    tickets = [gpu.scan_submit(seq2, reads.shape[0] * stride, nmask, segs, 150, o) for o in outs]
+    with pytest.raises(sb.StrGpuError) as e:  # all slots busy
+        gpu.scan_submit(seq2, reads.shape[0] * stride, nmask, segs, 150, outs[0])
+    assert e.value.status == -5
+    for t in tickets:
+        gpu.scan_wait(t)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    flat, off, lens = synth.segment_ascii(reads, segs, stride)
+    units, counts = oracle_for(flat, off, lens, segs["pclass"])
+    assert np.array_equal(outs[0]["unit"], units) and np.array_equal(outs[0]["repeat_count"], counts)
