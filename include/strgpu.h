@@ -115,6 +115,62 @@ int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask,
 /* synchronises `cuda_stream` and returns the sticky device-side status of launches since the last call */
 int strgpu_device_status(strgpu_ctx *ctx, void *cuda_stream);
 
+/* ---- cluster: the cluster loop of `strling call` (call.nim:118-130,223-235) and `strling merge`
+ * (merge.nim:125-187): group by (tid, repeat), stable sort by position, cluster (cluster.nim:364),
+ * bounds + filters (cluster.nim:175, callclusters.nim:52), has_per_sample_reads (merge.nim:18) ---- */
+
+/* tread (cluster.nim:23-32) as a POD.  `sample` stands in for qname: on this path qname is only read after
+ * merge.nim:121-124 has overwritten it with the sample index. */
+typedef struct {
+  int32_t  tid;
+  uint32_t position;
+  char     repeat[6];
+  uint16_t flag;
+  uint8_t  split;            /* Soft: left=0 right=1 both=2 none=3 none_right=4 none_left=5 (cluster.nim:14-20) */
+  uint8_t  mapping_quality;
+  uint8_t  repeat_count;
+  uint8_t  align_length;
+  int32_t  sample;
+} strgpu_tread;              /* 24 bytes */
+
+/* Bounds (cluster.nim:75-87) as a POD; `name` is always empty for discovered clusters. */
+typedef struct {
+  int32_t  tid;              /* -1: an unplaced bucket (call.nim:226-228): only repeat and n_reads are meaningful */
+  uint32_t left;
+  uint32_t left_most;
+  uint32_t right;
+  uint32_t right_most;
+  uint32_t center_mass;
+  uint16_t n_left;
+  uint16_t n_right;
+  uint16_t n_total;
+  char     repeat[6];
+  uint32_t first_read;       /* index of the cluster's first read in the (tid, repeat, position)-sorted order */
+  uint32_t n_reads;          /* reads in the cluster after trim / split */
+  uint32_t reserved;
+} strgpu_bounds;             /* 48 bytes */
+
+typedef struct {
+  uint32_t window;           /* max_dist: opts.window (call.nim:114, merge.nim:148-152) */
+  int32_t  min_support;      /* -m (call.nim:54, merge.nim:51) */
+  uint16_t min_clip;         /* -c */
+  uint16_t min_clip_total;   /* -t */
+  uint16_t max_clip_dist;    /* uint16(0.5 * frag_dist.median(0.5)) (call.nim:232, merge.nim:181) */
+  uint16_t merge_mode;       /* 1: merge.nim semantics (skip unplaced, has_per_sample_reads); 0: call.nim */
+} strgpu_cluster_params;     /* 16 bytes */
+
+/* treads: n records in `.bin` / concatenation order (host memory).  Writes up to `cap` records to `out`
+ * in ascending (tid, repeat bytes, position) order -- the reference visits buckets in Nim Table hash order,
+ * which only permutes output lines.  Unplaced buckets (tid < 0) come first as tid == -1 records when
+ * merge_mode == 0.  STRGPU_ERR_OVERFLOW if more than `cap` records were produced (*n_out = needed). */
+int strgpu_cluster(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,
+                   strgpu_bounds *out, uint32_t cap, uint32_t *n_out);
+/* Device-resident variant: d_treads / d_out are device pointers, *d_n_out a device uint32; enqueued on
+ * `cuda_stream` after an internal key-range probe (one small synchronising copy).  d_out needs room for
+ * `cap` records; records past cap are dropped and counted in *d_n_out. */
+int strgpu_cluster_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, const strgpu_cluster_params *params,
+                          void *d_out, uint32_t cap, void *d_n_out, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

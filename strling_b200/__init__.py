@@ -3,7 +3,9 @@ scan (`strling extract`, utils.nim:236) and STR-read clustering (`strling call` 
 behind a C ABI (include/strgpu.h, strling_b200/libstrgpu.so).  This package is the thin Python mirror of that
 ABI used by the tests and bench.py; there is no CPU fallback: without the built CUDA library it raises."""
 from .binding import (  # noqa: F401
+    BOUNDS_DTYPE,
     REPEAT_DTYPE,
+    TREAD_DTYPE,
     SEGMENT_DTYPE,
     StrGpu,
     StrGpuError,

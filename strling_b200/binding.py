@@ -13,7 +13,21 @@ LIB_PATH = os.path.join(_HERE, "libstrgpu.so")
 
 SEGMENT_DTYPE = np.dtype([("base_off", "<u4"), ("len", "<u2"), ("pclass", "u1"), ("flags", "u1")])
 REPEAT_DTYPE = np.dtype([("unit", "S6"), ("repeat_count", "<u2")])
+TREAD_DTYPE = np.dtype(
+    [("tid", "<i4"), ("position", "<u4"), ("repeat", "S6"), ("flag", "<u2"), ("split", "u1"),
+     ("mapq", "u1"), ("repeat_count", "u1"), ("align_length", "u1"), ("sample", "<i4")]
+)
+BOUNDS_DTYPE = np.dtype(
+    [("tid", "<i4"), ("left", "<u4"), ("left_most", "<u4"), ("right", "<u4"), ("right_most", "<u4"),
+     ("center_mass", "<u4"), ("n_left", "<u2"), ("n_right", "<u2"), ("n_total", "<u2"), ("repeat", "S6"),
+     ("first_read", "<u4"), ("n_reads", "<u4"), ("reserved", "<u4")]
+)
+CLUSTER_PARAMS_DTYPE = np.dtype(
+    [("window", "<u4"), ("min_support", "<i4"), ("min_clip", "<u2"), ("min_clip_total", "<u2"),
+     ("max_clip_dist", "<u2"), ("merge_mode", "<u2")]
+)
 assert SEGMENT_DTYPE.itemsize == 8 and REPEAT_DTYPE.itemsize == 8
+assert TREAD_DTYPE.itemsize == 24 and BOUNDS_DTYPE.itemsize == 48 and CLUSTER_PARAMS_DTYPE.itemsize == 16
 SEG_HAS_N = 1
 MAX_SEGMENT_LEN = 510
 
@@ -61,6 +75,8 @@ def load_library():
     L.strgpu_scan.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp]
     L.strgpu_scan_device.argtypes = [vp, vp, vp, vp, u32, u32, vp, vp]
     L.strgpu_device_status.argtypes = [vp, vp]
+    L.strgpu_cluster.argtypes = [vp, vp, u32, vp, vp, u32, C.POINTER(u32)]
+    L.strgpu_cluster_device.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp]
     _lib = L
     return L
 
@@ -171,3 +187,30 @@ class StrGpu:
         seq2, nmask, segs, n_bases = pack_reads(reads, 0)
         res = self.scan(seq2, n_bases, nmask, segs)
         return [(bytes(r["unit"]).rstrip(b"\0"), int(r["repeat_count"])) for r in res]
+
+    # ---- cluster ------------------------------------------------------------------------------
+    @staticmethod
+    def cluster_params(window: int, min_support: int, min_clip: int = 0, min_clip_total: int = 0, max_clip_dist: int = 200,
+                       merge_mode: bool = False) -> np.ndarray:
+        p = np.zeros(1, dtype=CLUSTER_PARAMS_DTYPE)
+        p["window"], p["min_support"], p["min_clip"], p["min_clip_total"] = window, min_support, min_clip, min_clip_total
+        p["max_clip_dist"], p["merge_mode"] = max_clip_dist, int(merge_mode)
+        return p
+
+    def cluster(self, treads: np.ndarray, window: int, min_support: int, min_clip: int = 0, min_clip_total: int = 0,
+                max_clip_dist: int = 200, merge_mode: bool = False):
+        """The cluster loop of call.nim:223-235 / merge.nim:172-187 over treads in `.bin` order.
+        Returns (bounds records with tid >= 0, {unit: count} of unplaced buckets)."""
+        treads = np.ascontiguousarray(treads, dtype=TREAD_DTYPE)
+        p = self.cluster_params(window, min_support, min_clip, min_clip_total, max_clip_dist, merge_mode)
+        cap = max(16, len(treads))
+        out = np.zeros(cap, dtype=BOUNDS_DTYPE)
+        n_out = C.c_uint32(0)
+        self._check(self.L.strgpu_cluster(self.h, treads.ctypes.data, len(treads), p.ctypes.data, out.ctypes.data, cap,
+                                          C.byref(n_out)))
+        out = out[: n_out.value]
+        unplaced = {bytes(r["repeat"]).rstrip(b"\0"): int(r["n_reads"]) for r in out[out["tid"] < 0]}
+        return out[out["tid"] >= 0].copy(), unplaced
+
+    def cluster_device(self, d_treads: int, n: int, params: np.ndarray, d_out: int, cap: int, d_n_out: int, stream: int = 0):
+        self._check(self.L.strgpu_cluster_device(self.h, d_treads, n, params.ctypes.data, d_out, cap, d_n_out, stream or None))

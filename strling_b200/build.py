@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstrgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_SOURCES = ["api.cu", "scan_kernels.cu"]
+CUDA_SOURCES = ["api.cu", "scan_kernels.cu", "cluster_kernels.cu"]
 CXX_SOURCES = ["pack.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

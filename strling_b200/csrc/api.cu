@@ -9,11 +9,15 @@
 #include <cstring>
 #include <new>
 
+#include "cluster_kernels.cuh"
 #include "scan_kernels.cuh"
 #include "strgpu.h"
 
 static_assert(sizeof(strgpu_segment) == 8, "strgpu_segment layout");
 static_assert(sizeof(strgpu_repeat) == 8, "strgpu_repeat layout");
+static_assert(sizeof(strgpu_tread) == 24, "strgpu_tread layout");
+static_assert(sizeof(strgpu_bounds) == 48, "strgpu_bounds layout");
+static_assert(sizeof(strgpu_cluster_params) == 16, "strgpu_cluster_params layout");
 
 namespace {
 
@@ -42,6 +46,10 @@ struct strgpu_ctx {
   bool thr_set = false;
   Slot slots[STRGPU_SLOTS];
   int *d_status_dev = nullptr;  // sticky status for strgpu_scan_device launches
+  strgpu::ClusterWorkspace cluster_ws;
+  cudaStream_t cluster_stream = nullptr;
+  DevBuf cl_in, cl_out;
+  uint32_t *d_cl_n = nullptr;
   uint64_t launches = 0;
   char err[512] = {0};
 };
@@ -118,6 +126,8 @@ int strgpu_create(strgpu_ctx **out, int device) {
     CU(ctx, cudaMalloc(&s.d_status, sizeof(int)));
     CU(ctx, cudaMallocHost(&s.h_status, sizeof(int)));
   }
+  CU(ctx, cudaStreamCreateWithFlags(&ctx->cluster_stream, cudaStreamNonBlocking));
+  CU(ctx, cudaMalloc(&ctx->d_cl_n, sizeof(uint32_t)));
   const double dflt[3] = {0.8, 0.8 - 0.07, 0.6};  // extract.nim:255,208,242 defaults
   return strgpu_set_proportions(ctx, dflt, 3);
 }
@@ -134,6 +144,11 @@ void strgpu_destroy(strgpu_ctx *ctx) {
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  strgpu::free_workspace(ctx->cluster_ws);
+  if (ctx->cl_in.p) cudaFree(ctx->cl_in.p);
+  if (ctx->cl_out.p) cudaFree(ctx->cl_out.p);
+  if (ctx->d_cl_n) cudaFree(ctx->d_cl_n);
+  if (ctx->cluster_stream) cudaStreamDestroy(ctx->cluster_stream);
   if (ctx->d_thr) cudaFree(ctx->d_thr);
   if (ctx->d_status_dev) cudaFree(ctx->d_status_dev);
   delete ctx;
@@ -268,6 +283,40 @@ int strgpu_device_status(strgpu_ctx *ctx, void *cuda_stream) {
     CU(ctx, cudaMemset(ctx->d_status_dev, 0, sizeof(int)));
     return fail(ctx, st, "device: %s", strgpu_error_string(st));
   }
+  return STRGPU_OK;
+}
+
+int strgpu_cluster_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, const strgpu_cluster_params *params, void *d_out,
+                          uint32_t cap, void *d_n_out, void *cuda_stream) {
+  if (!ctx || !params || !d_n_out || (n && !d_treads) || (cap && !d_out))
+    return fail(ctx, STRGPU_ERR_INVALID, "cluster_device: null argument");
+  if (((uintptr_t)d_treads & 7) || ((uintptr_t)d_out & 7) || ((uintptr_t)d_n_out & 3))
+    return fail(ctx, STRGPU_ERR_INVALID, "cluster_device: misaligned device pointer");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, strgpu::run_cluster(ctx->cluster_ws, (const strgpu_tread *)d_treads, n, *params, (strgpu_bounds *)d_out, cap,
+                              (uint32_t *)d_n_out, (cudaStream_t)cuda_stream, &ctx->launches));
+  return STRGPU_OK;
+}
+
+int strgpu_cluster(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,
+                   strgpu_bounds *out, uint32_t cap, uint32_t *n_out) {
+  if (!ctx || !params || !n_out || (n && !treads) || (cap && !out)) return fail(ctx, STRGPU_ERR_INVALID, "cluster: null argument");
+  *n_out = 0;
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure(ctx, ctx->cl_in, (size_t)n * sizeof(strgpu_tread) + 16))) return rc;
+  if ((rc = ensure(ctx, ctx->cl_out, (size_t)cap * sizeof(strgpu_bounds) + 16))) return rc;
+  cudaStream_t st = ctx->cluster_stream;
+  if (n) CU(ctx, cudaMemcpyAsync(ctx->cl_in.p, treads, (size_t)n * sizeof(strgpu_tread), cudaMemcpyHostToDevice, st));
+  CU(ctx, strgpu::run_cluster(ctx->cluster_ws, (const strgpu_tread *)ctx->cl_in.p, n, *params, (strgpu_bounds *)ctx->cl_out.p, cap,
+                              ctx->d_cl_n, st, &ctx->launches));
+  uint32_t produced = 0;
+  CU(ctx, cudaMemcpyAsync(&produced, ctx->d_cl_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  *n_out = produced;
+  const uint32_t take = produced < cap ? produced : cap;
+  if (take) CU(ctx, cudaMemcpy(out, ctx->cl_out.p, (size_t)take * sizeof(strgpu_bounds), cudaMemcpyDeviceToHost));
+  if (produced > cap) return fail(ctx, STRGPU_ERR_OVERFLOW, "cluster: %u records produced, capacity %u", produced, cap);
   return STRGPU_OK;
 }
 

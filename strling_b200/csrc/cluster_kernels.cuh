@@ -1,0 +1,31 @@
+// Launch interface of the cluster kernels (K2 tread_sort, K3 cluster_chain, K4 cluster_bounds).  Internal to libstrgpu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "strgpu.h"
+
+namespace strgpu {
+
+struct SortRec {  // 16-byte radix-sort record: key fields + the tread's index in input order
+  uint32_t hi;    // tid with the sign bit flipped (signed order)
+  uint32_t mid;   // repeat unit, 3 bits per char, memcmp order (0 < A < C < G < T)
+  uint32_t pos;
+  uint32_t idx;
+};
+
+// Growable device workspace owned by the ctx; every pointer is device memory.
+struct ClusterWorkspace {
+  void *buf[16] = {nullptr};
+  size_t cap[16] = {0};
+};
+
+// Runs the whole cluster path for n treads already in device memory.  Synchronises `stream` internally
+// (key-range probe, cluster count).  Returns cudaSuccess or the failing call's error; *launches is
+// incremented per kernel launch.  d_n_out receives the number of records produced (may exceed cap).
+cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
+                        strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t stream, uint64_t *launches);
+
+void free_workspace(ClusterWorkspace &ws);
+
+}  // namespace strgpu

@@ -126,3 +126,69 @@ def segment_ascii(reads: np.ndarray, segs: np.ndarray, stride: int):
     col = segs["base_off"].astype(np.int64) % stride
     off = (row * length + col).astype(np.uint64)
     return flat, off, segs["len"].astype(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------------ cluster inputs
+TREAD_DTYPE = np.dtype(
+    [("tid", "<i4"), ("position", "<u4"), ("repeat", "S6"), ("flag", "<u2"), ("split", "u1"),
+     ("mapq", "u1"), ("repeat_count", "u1"), ("align_length", "u1"), ("sample", "<i4")]
+)
+SOFT_LEFT, SOFT_RIGHT, SOFT_BOTH, SOFT_NONE, SOFT_NONE_RIGHT, SOFT_NONE_LEFT = range(6)
+
+
+def make_treads(n_loci: int, seed: int, n_tids: int = 24, n_samples: int = 1, noise_reads: int = 0, unplaced: int = 0,
+                contig_len: int = 100_000_000, dense: bool = False):
+    """STR-read records (`.bin` order, i.e. unsorted) shaped like extract output: per locus a cloud of anchored
+    reads (split none) within a fragment length of the locus, left-clipped reads piling up at the left edge and
+    right-clipped reads at the right edge (with stutter so that clip-position ties occur), plus background reads
+    and unplaced (tid -1) reads.  dense=True packs loci so that clusters chain, trim and split."""
+    rng = np.random.default_rng(seed)
+    units = [b"A", b"AC", b"AG", b"CAG", b"CCG", b"AAG", b"AAAG", b"AAGG", b"ATTCT", b"AAAAG", b"CACGAT", b"AAAAAT", b"T", b"CTG"]
+    parts = []
+    for _ in range(n_loci):
+        tid = int(rng.integers(0, n_tids))
+        unit = units[int(rng.integers(0, len(units)))]
+        left = int(rng.integers(1000, 3000 if dense else contig_len))
+        width = int(rng.integers(1, 120))
+        right = left + width
+        n_anchor = int(rng.integers(0, 30))
+        n_left = int(rng.integers(0, 12))
+        n_right = int(rng.integers(0, 12))
+        m = n_anchor + n_left + n_right
+        if m == 0:
+            continue
+        t = np.zeros(m, dtype=TREAD_DTYPE)
+        t["tid"] = tid
+        t["repeat"] = unit
+        pos = np.concatenate([
+            left + rng.integers(-450, 450, size=n_anchor),
+            left + rng.choice([0, 0, 0, 1, -1, 2, 7], size=n_left),
+            right + rng.choice([0, 0, 0, 1, -1, -2, 5], size=n_right),
+        ])
+        t["position"] = np.maximum(pos, 0).astype(np.uint32)
+        t["split"] = np.concatenate([
+            rng.choice([SOFT_NONE, SOFT_NONE, SOFT_NONE, SOFT_NONE_LEFT, SOFT_NONE_RIGHT], size=n_anchor),
+            np.full(n_left, SOFT_LEFT), np.full(n_right, SOFT_RIGHT)]).astype(np.uint8)
+        t["sample"] = rng.integers(0, n_samples, size=m)
+        parts.append(t)
+    if noise_reads:
+        t = np.zeros(noise_reads, dtype=TREAD_DTYPE)
+        t["tid"] = rng.integers(0, n_tids, size=noise_reads)
+        t["repeat"] = rng.choice(np.array(units, dtype="S6"), size=noise_reads)
+        t["position"] = rng.integers(0, 5000 if dense else contig_len, size=noise_reads)
+        t["split"] = rng.choice([SOFT_NONE, SOFT_LEFT, SOFT_RIGHT, SOFT_NONE_LEFT], size=noise_reads, p=[0.6, 0.15, 0.15, 0.1])
+        t["sample"] = rng.integers(0, n_samples, size=noise_reads)
+        parts.append(t)
+    if unplaced:
+        t = np.zeros(unplaced, dtype=TREAD_DTYPE)
+        t["tid"] = -1
+        t["repeat"] = rng.choice(np.array([b"AAGGG", b"AC", b"AGC", b"A"], dtype="S6"), size=unplaced)
+        t["split"] = SOFT_NONE
+        t["sample"] = rng.integers(0, n_samples, size=unplaced)
+        parts.append(t)
+    out = np.concatenate(parts) if parts else np.zeros(0, dtype=TREAD_DTYPE)
+    out["flag"] = rng.integers(0, 4096, size=len(out))
+    out["mapq"] = rng.integers(0, 61, size=len(out))
+    out["repeat_count"] = rng.integers(1, 75, size=len(out))
+    out["align_length"] = 150
+    return out[rng.permutation(len(out))]
