@@ -58,5 +58,25 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+CLI = os.path.join(HERE, "bin", "strling")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_cli(force: bool = False) -> str:
+    """The `strling` command line (C++ host side: BAM decode, mate pairing, .bin / bounds files) over libstrgpu.so."""
+    build_lib()
+    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + [LIB]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", *srcs, "-I", os.path.join(ROOT, "include"), "-I", HOST,
+           "-L", HERE, "-lstrgpu", "-lz", "-Wl,-rpath,$ORIGIN/..", "-o", CLI]
+    subprocess.check_call(cmd)
+    return CLI
+
+
 if __name__ == "__main__":
+    build_cli(force="--force" in sys.argv)
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

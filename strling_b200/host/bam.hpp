@@ -1,0 +1,285 @@
+// BGZF + BAM reader for the host side of `strling extract` / `strling call` (stands in for htslib, which the
+// reference reaches through hts-nim: extract.nim:275-329).  Blocks are inflated in parallel batches (zlib).
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace strling {
+
+struct Target {
+  std::string name;
+  uint32_t length = 0;
+};
+
+// A view into the reader's decode buffer; valid until the next call to next().
+struct BamRecord {
+  int32_t tid, pos, mate_tid, mate_pos, isize;
+  uint16_t flag, n_cigar;
+  uint8_t mapq;
+  int32_t l_seq;
+  const char *qname;       // NUL terminated
+  uint32_t l_qname;        // without the NUL
+  const uint32_t *cigar;   // len << 4 | op  (may be unaligned: use cigar_at)
+  const uint8_t *seq;      // 4-bit packed
+  uint64_t voffset;        // BGZF virtual offset of the record start (coffset << 16 | uoffset)
+
+  uint32_t cigar_at(int i) const {
+    uint32_t v;
+    std::memcpy(&v, reinterpret_cast<const uint8_t *>(cigar) + 4 * i, 4);
+    return v;
+  }
+  static int op(uint32_t c) { return (int)(c & 15u); }
+  static uint32_t oplen(uint32_t c) { return c >> 4; }
+  // htslib bam_endpos: pos + reference length; unmapped or zero-length alignments count as length 1
+  int32_t stop() const {
+    int64_t rl = 0;
+    if (!(flag & 4))
+      for (int i = 0; i < n_cigar; i++) {
+        const uint32_t c = cigar_at(i);
+        const int o = op(c);
+        if (o == 0 || o == 2 || o == 3 || o == 7 || o == 8) rl += oplen(c);
+      }
+    if (rl == 0) rl = 1;
+    return (int32_t)(pos + rl);
+  }
+};
+
+class BamReader {
+ public:
+  explicit BamReader(const std::string &path, int threads = 0) : path_(path) {
+    fh_ = std::fopen(path.c_str(), "rb");
+    if (!fh_) throw std::runtime_error("couldn't open bam");
+    threads_ = threads > 0 ? threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    read_header();
+  }
+  ~BamReader() {
+    if (fh_) std::fclose(fh_);
+  }
+  BamReader(const BamReader &) = delete;
+  BamReader &operator=(const BamReader &) = delete;
+
+  const std::string &header_text() const { return header_text_; }
+  const std::vector<Target> &targets() const { return targets_; }
+
+  // next record, or false at EOF
+  bool next(BamRecord &r) {
+    if (!ensure(4)) return false;
+    int32_t block_size;
+    std::memcpy(&block_size, data_.data() + cur_, 4);
+    if (block_size < 32) throw std::runtime_error("corrupt BAM record");
+    if (!ensure(4 + (size_t)block_size)) throw std::runtime_error("truncated BAM record");
+    r.voffset = voffset_at(cur_);
+    const uint8_t *p = data_.data() + cur_ + 4;
+    uint8_t l_read_name;
+    uint16_t bin;
+    std::memcpy(&r.tid, p, 4);
+    std::memcpy(&r.pos, p + 4, 4);
+    l_read_name = p[8];
+    r.mapq = p[9];
+    std::memcpy(&bin, p + 10, 2);
+    std::memcpy(&r.n_cigar, p + 12, 2);
+    std::memcpy(&r.flag, p + 14, 2);
+    std::memcpy(&r.l_seq, p + 16, 4);
+    std::memcpy(&r.mate_tid, p + 20, 4);
+    std::memcpy(&r.mate_pos, p + 24, 4);
+    std::memcpy(&r.isize, p + 28, 4);
+    r.qname = reinterpret_cast<const char *>(p + 32);
+    r.l_qname = l_read_name ? (uint32_t)l_read_name - 1 : 0;
+    r.cigar = reinterpret_cast<const uint32_t *>(p + 32 + l_read_name);
+    r.seq = p + 32 + l_read_name + 4 * (size_t)r.n_cigar;
+    if (32 + (size_t)l_read_name + 4 * (size_t)r.n_cigar + (size_t)(r.l_seq + 1) / 2 > (size_t)block_size)
+      throw std::runtime_error("corrupt BAM record (field lengths)");
+    cur_ += 4 + (size_t)block_size;
+    return true;
+  }
+
+  // restart iteration at a BGZF virtual offset previously taken from BamRecord::voffset
+  void seek(uint64_t voffset) {
+    data_.clear();
+    spans_.clear();
+    cur_ = 0;
+    eof_ = false;
+    if (std::fseek(fh_, (long)(voffset >> 16), SEEK_SET) != 0) throw std::runtime_error("seek failed");
+    fpos_ = voffset >> 16;
+    fill();
+    cur_ = (size_t)(voffset & 0xffff);
+  }
+
+ private:
+  struct Span {       // one inflated BGZF block inside data_
+    size_t begin;     // offset in data_
+    uint64_t coffset; // file offset of the compressed block
+  };
+
+  uint64_t voffset_at(size_t pos) const {
+    // binary search the block that holds pos
+    size_t lo = 0, hi = spans_.size();
+    while (hi - lo > 1) {
+      const size_t mid = (lo + hi) / 2;
+      if (spans_[mid].begin <= pos) lo = mid; else hi = mid;
+    }
+    return (spans_[lo].coffset << 16) | (uint64_t)(pos - spans_[lo].begin);
+  }
+
+  bool ensure(size_t need) {
+    while (data_.size() - cur_ < need) {
+      if (eof_) return false;
+      fill();
+    }
+    return true;
+  }
+
+  // read up to kBatch compressed blocks and inflate them in parallel, appending to data_
+  void fill() {
+    // drop consumed bytes
+    if (cur_ > 0) {
+      size_t keep_from = cur_;
+      // keep whole spans so voffsets stay right: find the span containing cur_
+      size_t si = 0;
+      while (si + 1 < spans_.size() && spans_[si + 1].begin <= keep_from) si++;
+      const size_t cut = spans_.empty() ? 0 : spans_[si].begin;
+      if (cut > 0) {
+        data_.erase(data_.begin(), data_.begin() + (long)cut);
+        cur_ -= cut;
+        std::vector<Span> ns;
+        for (size_t i = si; i < spans_.size(); i++) ns.push_back(Span{spans_[i].begin - cut, spans_[i].coffset});
+        spans_.swap(ns);
+      }
+    }
+    struct Blk { size_t coff; uint32_t csize, isize; uint64_t fpos; };
+    std::vector<Blk> blks;
+    comp_.clear();
+    size_t total_out = 0;
+    constexpr size_t kBatch = 1024;
+    while (blks.size() < kBatch) {
+      uint8_t hdr[18];
+      const size_t got = std::fread(hdr, 1, 18, fh_);
+      if (got == 0) { eof_ = true; break; }
+      if (got < 18 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) throw std::runtime_error("not a BGZF file");
+      uint16_t xlen;
+      std::memcpy(&xlen, hdr + 10, 2);
+      // locate the BC subfield (usually first)
+      std::vector<uint8_t> extra(xlen);
+      std::memcpy(extra.data(), hdr + 12, std::min<size_t>(6, xlen));
+      if (xlen > 6 && std::fread(extra.data() + 6, 1, xlen - 6, fh_) != (size_t)xlen - 6) throw std::runtime_error("truncated BGZF header");
+      uint32_t bsize = 0;
+      for (size_t o = 0; o + 4 <= extra.size();) {
+        uint16_t slen;
+        std::memcpy(&slen, extra.data() + o + 2, 2);
+        if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2) {
+          uint16_t bs;
+          std::memcpy(&bs, extra.data() + o + 4, 2);
+          bsize = (uint32_t)bs + 1;
+          break;
+        }
+        o += 4 + slen;
+      }
+      if (!bsize) throw std::runtime_error("BGZF block without BC field");
+      const uint32_t csize = bsize - xlen - 12 - 8;  // deflate payload
+      const size_t coff = comp_.size();
+      comp_.resize(coff + csize + 8);
+      if (std::fread(comp_.data() + coff, 1, csize + 8, fh_) != csize + 8) throw std::runtime_error("truncated BGZF block");
+      uint32_t isize;
+      std::memcpy(&isize, comp_.data() + coff + csize + 4, 4);
+      blks.push_back(Blk{coff, csize, isize, fpos_});
+      fpos_ += bsize;
+      total_out += isize;
+    }
+    if (blks.empty()) return;
+    const size_t base = data_.size();
+    data_.resize(base + total_out);
+    std::vector<size_t> outoff(blks.size());
+    size_t o = base;
+    for (size_t i = 0; i < blks.size(); i++) {
+      outoff[i] = o;
+      if (blks[i].isize) spans_.push_back(Span{o, blks[i].fpos});
+      o += blks[i].isize;
+    }
+    if (spans_.empty()) spans_.push_back(Span{base, blks[0].fpos});
+    auto work = [&](size_t from, size_t to, std::string *err) {
+      z_stream zs;
+      for (size_t i = from; i < to; i++) {
+        if (blks[i].isize == 0) continue;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { *err = "inflateInit2"; return; }
+        zs.next_in = comp_.data() + blks[i].coff;
+        zs.avail_in = blks[i].csize;
+        zs.next_out = data_.data() + outoff[i];
+        zs.avail_out = blks[i].isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) { *err = "inflate failed"; return; }
+      }
+    };
+    const int nt = (int)std::min<size_t>((size_t)threads_, (blks.size() + 15) / 16);
+    std::vector<std::string> errs((size_t)std::max(nt, 1));
+    if (nt <= 1) {
+      work(0, blks.size(), &errs[0]);
+    } else {
+      std::vector<std::thread> th;
+      const size_t per = (blks.size() + (size_t)nt - 1) / (size_t)nt;
+      for (int t = 0; t < nt; t++) {
+        const size_t a = (size_t)t * per, b = std::min(blks.size(), a + per);
+        if (a >= b) break;
+        th.emplace_back(work, a, b, &errs[(size_t)t]);
+      }
+      for (auto &x : th) x.join();
+    }
+    for (auto &e : errs)
+      if (!e.empty()) throw std::runtime_error("BGZF: " + e);
+  }
+
+  void read_raw(void *dst, size_t n) {
+    if (!ensure(n)) throw std::runtime_error("truncated BAM header");
+    std::memcpy(dst, data_.data() + cur_, n);
+    cur_ += n;
+  }
+
+  void read_header() {
+    fpos_ = 0;
+    char magic[4];
+    read_raw(magic, 4);
+    if (std::memcmp(magic, "BAM\1", 4) != 0) throw std::runtime_error("not a BAM file (CRAM/SAM input is not supported)");
+    int32_t l_text;
+    read_raw(&l_text, 4);
+    header_text_.resize((size_t)l_text);
+    if (l_text) read_raw(&header_text_[0], (size_t)l_text);
+    // htslib keeps the text up to its first NUL
+    const size_t z = header_text_.find('\0');
+    if (z != std::string::npos) header_text_.resize(z);
+    int32_t n_ref;
+    read_raw(&n_ref, 4);
+    targets_.resize((size_t)n_ref);
+    for (auto &t : targets_) {
+      int32_t l_name;
+      read_raw(&l_name, 4);
+      std::string nm((size_t)l_name, '\0');
+      read_raw(&nm[0], (size_t)l_name);
+      if (!nm.empty() && nm.back() == '\0') nm.pop_back();
+      t.name = nm;
+      int32_t ln;
+      read_raw(&ln, 4);
+      t.length = (uint32_t)ln;
+    }
+  }
+
+  std::string path_;
+  FILE *fh_ = nullptr;
+  int threads_ = 1;
+  uint64_t fpos_ = 0;
+  bool eof_ = false;
+  std::vector<uint8_t> data_, comp_;
+  std::vector<Span> spans_;
+  size_t cur_ = 0;
+  std::string header_text_;
+  std::vector<Target> targets_;
+};
+
+}  // namespace strling

@@ -1,0 +1,256 @@
+// `strling merge` (merge.nim:47-187) and the cluster loop of `strling call` (call.nim:50-130,223-235,280-281), with
+// grouping, sorting, clustering and bounds on the GPU (strgpu_cluster).  Host work: `.bin` decoding, the fragment
+// distribution medians that parameterise the kernels, and writing `-bounds.txt` / `-unplaced.txt`.
+// Not part of this build: spanning reads + genotypes (collect.nim, genotyper.nim), so `call` writes no
+// `-genotype.txt` and its bounds lines lack the trailing median-depth column (call.nim:255).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bam.hpp"
+#include "commands.hpp"
+#include "strgpu.h"
+#include "tread.hpp"
+
+namespace strling {
+
+namespace {
+
+const char *kBoundsHeader = "#chrom\tleft\tright\trepeat\tname\tleft_most\tright_most\tcenter_mass\tn_left\tn_right\tn_total";  // cluster.nim:89
+
+struct Args {
+  std::map<std::string, std::string> opt;
+  std::vector<std::string> pos;
+  bool has(const std::string &k) const { return opt.count(k) > 0; }
+  std::string get(const std::string &k, const std::string &d) const { auto it = opt.find(k); return it == opt.end() ? d : it->second; }
+};
+
+// options: {"-x", "--long", takes_value}
+struct OptSpec { const char *s, *l; bool value; };
+
+Args parse(int argc, char **argv, const std::vector<OptSpec> &specs, const char *usage) {
+  Args a;
+  for (int i = 0; i < argc; i++) {
+    std::string t = argv[i];
+    if (t == "-h" || t == "--help") { std::fputs(usage, stdout); std::exit(0); }
+    bool matched = false;
+    for (const auto &sp : specs) {
+      std::string val;
+      bool hit = false;
+      if (t == sp.s || t == sp.l) {
+        hit = true;
+        if (sp.value) {
+          if (i + 1 >= argc) { std::fprintf(stderr, "option %s needs a value\n", t.c_str()); std::exit(1); }
+          val = argv[++i];
+        }
+      } else if (sp.value && t.rfind(std::string(sp.l) + "=", 0) == 0) {
+        hit = true;
+        val = t.substr(std::strlen(sp.l) + 1);
+      }
+      if (hit) { a.opt[sp.l] = sp.value ? val : "1"; matched = true; break; }
+    }
+    if (!matched) {
+      if (t.size() > 1 && t[0] == '-' && !(t[1] >= '0' && t[1] <= '9')) { std::fprintf(stderr, "unknown option %s\n%s", t.c_str(), usage); std::exit(1); }
+      a.pos.push_back(t);
+    }
+  }
+  return a;
+}
+
+strgpu_tread to_pod(const Tread &t, int32_t sample) {
+  strgpu_tread p;
+  p.tid = t.tid; p.position = t.position;
+  std::memcpy(p.repeat, t.repeat.data(), 6);
+  p.flag = t.flag; p.split = t.split; p.mapping_quality = t.mapping_quality; p.repeat_count = t.repeat_count;
+  p.align_length = t.align_length; p.sample = sample;
+  return p;
+}
+
+std::string bounds_line(const strgpu_bounds &b, const std::vector<std::pair<std::string, uint32_t>> &targets) {  // cluster.nim:262-266
+  char unit[7] = {0};
+  std::memcpy(unit, b.repeat, 6);
+  char buf[512];
+  std::snprintf(buf, sizeof(buf), "%s\t%u\t%u\t%s\t\t%u\t%u\t%u\t%u\t%u\t%u", targets[(size_t)b.tid].first.c_str(), b.left, b.right, unit,
+                b.left_most, b.right_most, b.center_mass, (unsigned)b.n_left, (unsigned)b.n_right, (unsigned)b.n_total);
+  return buf;
+}
+
+std::vector<strgpu_bounds> run_cluster(const std::vector<strgpu_tread> &treads, const strgpu_cluster_params &p, int device, bool verbose) {
+  strgpu_ctx *gpu = nullptr;
+  int rc = strgpu_create(&gpu, device);
+  if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + strgpu_error_string(rc));
+  std::vector<strgpu_bounds> out(std::max<size_t>(1024, treads.size() / 4));
+  uint32_t n_out = 0;
+  rc = strgpu_cluster(gpu, treads.data(), (uint32_t)treads.size(), &p, out.data(), (uint32_t)out.size(), &n_out);
+  if (rc == STRGPU_ERR_OVERFLOW) {
+    out.resize(n_out);
+    rc = strgpu_cluster(gpu, treads.data(), (uint32_t)treads.size(), &p, out.data(), (uint32_t)out.size(), &n_out);
+  }
+  if (rc != STRGPU_OK) {
+    const std::string msg = strgpu_last_error(gpu);
+    strgpu_destroy(gpu);
+    throw std::runtime_error("[strling] gpu: cluster: " + msg);
+  }
+  if (verbose) std::fprintf(stderr, "[strling] gpu clustered %zu STR reads into %u records (%llu kernel launches)\n", treads.size(), n_out,
+                            (unsigned long long)strgpu_launch_count(gpu));
+  strgpu_destroy(gpu);
+  out.resize(n_out);
+  return out;
+}
+
+bool same_targets(const std::vector<std::pair<std::string, uint32_t>> &a, const std::vector<std::pair<std::string, uint32_t>> &b) {
+  return a == b;  // unpack.nim:46-56
+}
+
+}  // namespace
+
+int merge_main(int argc, char **argv) {
+  static const char *usage =
+      "strling merge [-f fasta] [-w window] [-m min-support] [--chromosome C] [-c min-clip] [-t min-clip-total] [-q min-mapq]\n"
+      "              [-o output-prefix] [-d] [-v] [--device N] <bin>...\n";
+  Args a = parse(argc, argv, {{"-f", "--fasta", true}, {"-w", "--window", true}, {"-m", "--min-support", true}, {"", "--chromosome", true},
+                              {"-c", "--min-clip", true}, {"-t", "--min-clip-total", true}, {"-q", "--min-mapq", true}, {"-l", "--bed", true},
+                              {"-o", "--output-prefix", true}, {"-d", "--diff-refs", false}, {"-v", "--verbose", false}, {"", "--device", true}},
+                 usage);
+  if (a.pos.empty()) { std::fputs(usage, stdout); return 0; }
+  if (a.has("--bed")) throw std::runtime_error("[strling merge] -l/--bed (assign_reads_locus, callclusters.nim:14) is not part of this build");
+  if (a.has("--diff-refs")) throw std::runtime_error("[strling merge] -d/--diff-refs is not part of this build");
+  int window = std::stoi(a.get("--window", "-1"));
+  const int min_support = std::stoi(a.get("--min-support", "5"));
+  const uint16_t min_clip = (uint16_t)std::stoi(a.get("--min-clip", "0"));
+  const uint16_t min_clip_total = (uint16_t)std::stoi(a.get("--min-clip-total", "0"));
+  const std::string prefix = a.get("--output-prefix", "strling");
+  const bool verbose = a.has("--verbose");
+  const std::string chromosome = a.get("--chromosome", "-2");
+
+  std::array<uint32_t, 4096> frag{};
+  std::vector<std::pair<std::string, uint32_t>> targets;
+  std::vector<strgpu_tread> treads;
+  int32_t requested_tid = INT32_MIN;
+  for (size_t si = 0; si < a.pos.size(); si++) {
+    if (verbose) std::fprintf(stderr, "[strling] reading bin file: %s\n", a.pos[si].c_str());
+    BinFile bf = read_bin(a.pos[si]);
+    auto tg = targets_from_header(bf.header);
+    if (targets.empty()) {
+      targets = tg;
+      if (chromosome != "-2") {  // the reference resolves the name against the fasta index (merge.nim:37-45); same names, same order
+        for (size_t t = 0; t < targets.size(); t++)
+          if (targets[t].first == chromosome) requested_tid = (int32_t)t;
+        if (requested_tid == INT32_MIN) throw std::runtime_error("[strling merge] chromosome: " + chromosome + " not found, check name and 'chr' prefix");
+      }
+    } else if (!same_targets(tg, targets)) {
+      throw std::runtime_error("[strling] Error: inconsistent bam header for " + a.pos[si] + ". Were all samples run on the same reference genome?");
+    }
+    for (size_t i = 0; i < 4096; i++) {
+      const uint32_t before = frag[i];
+      frag[i] += bf.frag_dist[i];
+      if (frag[i] < before) throw std::runtime_error("overflow");  // merge.nim:112-115
+    }
+    size_t kept = 0;
+    for (const Tread &t : bf.reads) {
+      if (requested_tid != INT32_MIN && t.tid != requested_tid) continue;
+      if (t.tid < 0) continue;  // drop_unplaced=true (merge.nim:101)
+      treads.push_back(to_pod(t, (int32_t)si));  // qname := sample index (merge.nim:121-124)
+      kept++;
+    }
+    std::fprintf(stderr, "[strling] read %zu STR reads from file: %s\n", kept, a.pos[si].c_str());
+  }
+  if (verbose) {
+    std::fprintf(stderr, "[strling] read %zu STR reads across all samples.\n", treads.size());
+    std::fprintf(stderr, "[strling] Calculated median fragment length accross all samples:%d\n", frag_median(frag));
+  }
+  if (window < 0) window = frag_median(frag, 0.98);
+  strgpu_cluster_params p;
+  p.window = (uint32_t)window;
+  p.min_support = min_support;
+  p.min_clip = min_clip;
+  p.min_clip_total = min_clip_total;
+  p.max_clip_dist = (uint16_t)(0.5 * (double)frag_median(frag, 0.5));  // merge.nim:181
+  p.merge_mode = 1;
+  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose);
+
+  std::ofstream out(prefix + "-bounds.txt");
+  if (!out) throw std::runtime_error("couldn't open output file");
+  out << kBoundsHeader << "\n";
+  for (const auto &b : bounds)
+    if (b.tid >= 0) out << bounds_line(b, targets) << "\n";
+  out.close();
+  if (verbose) std::fprintf(stderr, "[strling] Wrote merged str bounds to %s-bounds.txt\n", prefix.c_str());
+  return 0;
+}
+
+int call_main(int argc, char **argv) {
+  static const char *usage =
+      "strling call [-f fasta] [-m min-support] [-c min-clip] [-t min-clip-total] [-q min-mapq] [-o output-prefix] [-v] [--device N] <bam> <bin>\n"
+      "  (this build runs the discovery / cluster loop only: -bounds.txt and -unplaced.txt; no -l/-b, no genotypes)\n";
+  Args a = parse(argc, argv, {{"-f", "--fasta", true}, {"-m", "--min-support", true}, {"-c", "--min-clip", true}, {"-t", "--min-clip-total", true},
+                              {"-q", "--min-mapq", true}, {"-l", "--loci", true}, {"-b", "--bounds", true}, {"-o", "--output-prefix", true},
+                              {"-v", "--verbose", false}, {"", "--device", true}},
+                 usage);
+  if (a.pos.size() != 2) { std::fputs(usage, stdout); return a.pos.empty() ? 0 : 1; }
+  if (a.has("--loci") || a.has("--bounds")) throw std::runtime_error("[strling call] -l / -b (assign_reads_locus, callclusters.nim:14) are not part of this build");
+  const std::string prefix = a.get("--output-prefix", "strling");
+  const bool verbose = a.has("--verbose");
+  // call.nim:96-114 : the fragment distribution is re-derived from the BAM, window = its 0.99 quantile
+  const std::array<uint32_t, 4096> frag = fragment_length_distribution(a.pos[0], 0);
+  if (verbose) std::fprintf(stderr, "Calculated median fragment length:%d\n", frag_median(frag));
+  BinFile bf = read_bin(a.pos[1]);
+  auto targets = targets_from_header(bf.header);
+  {
+    BamReader rd(a.pos[0]);
+    std::vector<std::pair<std::string, uint32_t>> bt;
+    for (const auto &t : rd.targets()) bt.emplace_back(t.name, t.length);
+    if (!same_targets(bt, targets)) throw std::runtime_error("[strling] bin file and bam have different targets (call.nim:122)");
+  }
+  std::vector<strgpu_tread> treads;
+  treads.reserve(bf.reads.size());
+  for (const Tread &t : bf.reads) treads.push_back(to_pod(t, 0));
+  strgpu_cluster_params p;
+  p.window = (uint32_t)frag_median(frag, 0.99);
+  p.min_support = std::stoi(a.get("--min-support", "5"));
+  p.min_clip = (uint16_t)std::stoi(a.get("--min-clip", "0"));
+  p.min_clip_total = (uint16_t)std::stoi(a.get("--min-clip-total", "0"));
+  p.max_clip_dist = (uint16_t)(0.5 * (double)frag_median(frag, 0.5));  // call.nim:232
+  p.merge_mode = 0;
+  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose);
+
+  std::ofstream bo(prefix + "-bounds.txt"), un(prefix + "-unplaced.txt");
+  if (!bo || !un) throw std::runtime_error("couldn't open output file");
+  bo << kBoundsHeader << "\n";   // the reference appends "\tdepth" here (call.nim:145); depth needs collect.nim (not built)
+  for (const auto &b : bounds) {
+    if (b.tid >= 0) { bo << bounds_line(b, targets) << "\n"; continue; }
+    char unit[7] = {0};
+    std::memcpy(unit, b.repeat, 6);
+    un << unit << "\t" << b.n_reads << "\n";  // call.nim:280-281
+  }
+  return 0;
+}
+
+int extract_main(int argc, char **argv) {
+  static const char *usage =
+      "strling extract [-f fasta] [-g genome-repeats] [-p proportion-repeat=0.8] [-q min-mapq=40] [-v] [--device N] [--threads N]\n"
+      "                [--batch-reads N] <bam> <bin>\n";
+  Args a = parse(argc, argv, {{"-f", "--fasta", true}, {"-g", "--genome-repeats", true}, {"-p", "--proportion-repeat", true}, {"-q", "--min-mapq", true},
+                              {"-v", "--verbose", false}, {"", "--device", true}, {"", "--threads", true}, {"", "--batch-reads", true}},
+                 usage);
+  if (a.pos.size() != 2) { std::fputs(usage, stdout); return a.pos.empty() ? 0 : 1; }
+  ExtractArgs e;
+  e.fasta = a.get("--fasta", "");
+  e.genome_repeats = a.get("--genome-repeats", "");
+  e.proportion_repeat = std::stod(a.get("--proportion-repeat", "0.8"));
+  e.min_mapq = std::stoi(a.get("--min-mapq", "40"));
+  e.verbose = a.has("--verbose");
+  e.device = std::stoi(a.get("--device", "0"));
+  e.threads = std::stoi(a.get("--threads", "0"));
+  e.batch_reads = (uint32_t)std::stoul(a.get("--batch-reads", "1048576"));
+  e.bam = a.pos[0];
+  e.bin = a.pos[1];
+  return extract_run(e);
+}
+
+}  // namespace strling

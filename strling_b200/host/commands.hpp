@@ -1,0 +1,27 @@
+// Entry points of the `strling` command line (src/strling.nim:18-41 dispatcher) implemented by this build.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace strling {
+
+struct ExtractArgs {
+  std::string fasta, genome_repeats, bam, bin;
+  double proportion_repeat = 0.8;
+  int min_mapq = 40;
+  bool verbose = false;
+  int device = 0;
+  int threads = 0;
+  uint32_t batch_reads = 1u << 20;
+};
+int extract_run(const ExtractArgs &a);
+std::array<uint32_t, 4096> fragment_length_distribution(const std::string &bam, int threads);
+
+int extract_main(int argc, char **argv);
+int merge_main(int argc, char **argv);
+int call_main(int argc, char **argv);
+int debug_main(int argc, char **argv);
+
+}  // namespace strling

@@ -1,0 +1,458 @@
+// `strling extract` (extract.nim:250-350) with the per-read repeat-unit scan on the GPU.
+//
+// The scan (get_repeat, utils.nim:236) is a pure function of (bases, length, proportion_repeat), so every
+// candidate segment of a batch of records -- the whole read (unless the genome-STR filter of extract.nim:30-34 skips
+// it) and each soft-clipped end under both proportion classes add() may use (extract.nim:207-211,241-244) -- is
+// submitted to libstrgpu up front.  The order-dependent part (mate table, add_soft conditions, unplaced / adjust_by,
+// append order of cache.cache == `.bin` record order; extract.nim:93-132,192-248) is then replayed on the host in
+// file order with the scan results.  While the GPU scans batch n, the host decodes batch n+1 and replays batch n-1.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "bam.hpp"
+#include "commands.hpp"
+#include "strgpu.h"
+#include "tread.hpp"
+
+namespace strling {
+
+namespace {
+
+struct Intervals {  // stands in for Lapper[region] (read_bed.nim:30-50); find = any overlap with [start, stop)
+  std::vector<int64_t> start, max_stop;
+  bool find(int64_t s, int64_t e) const {
+    const size_t idx = (size_t)(std::lower_bound(start.begin(), start.end(), e) - start.begin());  // starts < e
+    return idx > 0 && max_stop[idx - 1] > s;
+  }
+};
+
+std::unordered_map<std::string, Intervals> read_bed(const std::string &path) {
+  std::ifstream in(path);
+  if (!in) throw std::runtime_error("[strling] couldn't open genome repeats file: " + path);
+  std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>> raw;
+  std::string line;
+  while (std::getline(in, line)) {
+    if (line.rfind("track ", 0) == 0 || (!line.empty() && line[0] == '#')) continue;
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+    const size_t a = line.find('\t');
+    if (a == std::string::npos) continue;
+    const size_t b = line.find('\t', a + 1);
+    if (b == std::string::npos) continue;
+    size_t c = line.find('\t', b + 1);
+    if (c == std::string::npos) c = line.size();
+    raw[line.substr(0, a)].emplace_back(std::stoll(line.substr(a + 1, b - a - 1)), std::stoll(line.substr(b + 1, c - b - 1)));
+  }
+  std::unordered_map<std::string, Intervals> out;
+  for (auto &kv : raw) {
+    std::sort(kv.second.begin(), kv.second.end());
+    Intervals iv;
+    int64_t mx = INT64_MIN;
+    for (auto &p : kv.second) {
+      iv.start.push_back(p.first);
+      mx = std::max(mx, p.second);
+      iv.max_stop.push_back(mx);
+    }
+    out.emplace(kv.first, std::move(iv));
+  }
+  return out;
+}
+
+constexpr int kClsRead = 0, kClsFirstSeen = 1, kClsSecondSeen = 2;
+
+struct Pending {  // what the replay needs from one BAM record
+  int32_t tid, pos, stop, mate_tid, mate_pos;
+  uint16_t flag, n_cigar;
+  uint8_t mapq;
+  uint32_t first_cig, last_cig;
+  int32_t l_seq, m_len;
+  int32_t seg_full;        // segment index or -1 (filtered by the genome-STR rule)
+  int32_t seg_clip[2][2];  // [0 left / 1 right][0 first-seen class / 1 second-seen class], -1 = none
+  uint32_t qname_off, qname_len;
+};
+
+struct Batch {
+  std::vector<Pending> recs;
+  std::vector<char> names;
+  uint8_t *seq2 = nullptr;       // pinned
+  uint32_t *nmask = nullptr;     // pinned
+  strgpu_segment *segs = nullptr;
+  strgpu_repeat *out = nullptr;
+  uint64_t n_bases = 0, cap_bases = 0;
+  uint32_t n_seg = 0, cap_seg = 0;
+  uint32_t max_len = 0;
+  bool any_n = false;
+  int ticket = -1;
+  bool in_flight = false;
+};
+
+struct Extractor {
+  strgpu_ctx *gpu = nullptr;
+  Options opts;
+  double p = 0.8;
+  const std::vector<Target> *targets = nullptr;
+  std::vector<const Intervals *> genome_str_by_tid;  // nullptr: chrom not in genome_str
+  std::unordered_map<std::string, Tread> tbl;        // Cache.tbl (extract.nim:89-91)
+  std::vector<Tread> cache;                          // Cache.cache
+  uint64_t n_reads = 0, n_scanned = 0, n_warned = 0;
+  bool verbose = false;
+
+  void gpu_check(int rc, const char *what) {
+    if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + what + ": " + strgpu_last_error(gpu));
+  }
+
+  void alloc_batch(Batch &b, uint64_t cap_bases, uint32_t cap_seg) {
+    b.cap_bases = cap_bases;
+    b.cap_seg = cap_seg;
+    void *p1, *p2, *p3, *p4;
+    gpu_check(strgpu_host_alloc(&p1, strgpu_seq2_bytes(cap_bases)), "host_alloc");
+    gpu_check(strgpu_host_alloc(&p2, strgpu_nmask_bytes(cap_bases)), "host_alloc");
+    gpu_check(strgpu_host_alloc(&p3, (size_t)cap_seg * sizeof(strgpu_segment)), "host_alloc");
+    gpu_check(strgpu_host_alloc(&p4, (size_t)cap_seg * sizeof(strgpu_repeat)), "host_alloc");
+    b.seq2 = (uint8_t *)p1; b.nmask = (uint32_t *)p2; b.segs = (strgpu_segment *)p3; b.out = (strgpu_repeat *)p4;
+    std::memset(b.nmask, 0, strgpu_nmask_bytes(cap_bases));
+  }
+  void free_batch(Batch &b) {
+    strgpu_host_free(b.seq2); strgpu_host_free(b.nmask); strgpu_host_free(b.segs); strgpu_host_free(b.out);
+  }
+  void reset_batch(Batch &b) {
+    if (b.any_n) std::memset(b.nmask, 0, (size_t)((b.n_bases + 31) / 32) * 4 + 8);
+    b.recs.clear(); b.names.clear();
+    b.n_bases = 0; b.n_seg = 0; b.max_len = 0; b.any_n = false; b.ticket = -1; b.in_flight = false;
+  }
+  bool batch_full(const Batch &b) const { return b.n_bases + 1024 > b.cap_bases || b.n_seg + 8 > b.cap_seg; }
+
+  int32_t add_segment(Batch &b, uint64_t base, uint32_t len, int cls, bool has_n) {
+    strgpu_segment &s = b.segs[b.n_seg];
+    s.base_off = (uint32_t)base;
+    s.len = (uint16_t)len;
+    s.pclass = (uint8_t)cls;
+    s.flags = has_n ? STRGPU_SEG_HAS_N : 0;
+    b.max_len = std::max(b.max_len, len);
+    return (int32_t)b.n_seg++;
+  }
+
+  // decode one record into the batch: everything the replay and the scan need
+  void stage(Batch &b, const BamRecord &r) {
+    Pending pr;
+    pr.tid = r.tid; pr.pos = r.pos; pr.stop = r.stop(); pr.mate_tid = r.mate_tid; pr.mate_pos = r.mate_pos;
+    pr.flag = r.flag; pr.n_cigar = r.n_cigar; pr.mapq = r.mapq; pr.l_seq = r.l_seq;
+    pr.first_cig = r.n_cigar ? r.cigar_at(0) : 0;
+    pr.last_cig = r.n_cigar ? r.cigar_at(r.n_cigar - 1) : 0;
+    pr.m_len = 0;
+    pr.seg_full = -1;
+    pr.seg_clip[0][0] = pr.seg_clip[0][1] = pr.seg_clip[1][0] = pr.seg_clip[1][1] = -1;
+    pr.qname_off = (uint32_t)b.names.size();
+    pr.qname_len = r.l_qname;
+    b.names.insert(b.names.end(), r.qname, r.qname + r.l_qname);
+    if (r.l_seq > STRGPU_MAX_SEGMENT_LEN)
+      throw std::runtime_error("[strling] read longer than " + std::to_string(STRGPU_MAX_SEGMENT_LEN) + " bp: " + std::string(r.qname));
+
+    // extract.nim:30-34 : exact single-M match outside every genome STR region -> no scan
+    bool skip = false;
+    if (r.n_cigar == 1 && BamRecord::op(pr.first_cig) == 0 && r.tid >= 0 && (size_t)r.tid < genome_str_by_tid.size() &&
+        genome_str_by_tid[(size_t)r.tid] != nullptr) {
+      if (!genome_str_by_tid[(size_t)r.tid]->find(r.pos, pr.stop)) {
+        skip = true;
+        pr.m_len = (int32_t)BamRecord::oplen(pr.first_cig);
+      }
+    }
+    // add_soft preconditions that do not depend on scan results (extract.nim:97-104)
+    bool clip_l = false, clip_r = false;
+    if (r.mapq >= opts.min_mapq && r.n_cigar > 0) {
+      clip_l = BamRecord::op(pr.first_cig) == 4;
+      clip_r = BamRecord::op(pr.last_cig) == 4;
+    }
+    if (!skip || clip_l || clip_r) {
+      const uint64_t base = b.n_bases;
+      const int n_other = strgpu_pack_bam4(r.seq, (uint32_t)r.l_seq, b.seq2, b.nmask, base);
+      if (n_other < 0) throw std::runtime_error("[strling] pack_bam4 failed");
+      const bool has_n = n_other > 0;
+      b.any_n = b.any_n || has_n;
+      b.n_bases = base + (((uint64_t)r.l_seq + 15) & ~15ull);
+      if (!skip) pr.seg_full = add_segment(b, base, (uint32_t)r.l_seq, kClsRead, has_n);
+      if (clip_l) {
+        const uint32_t len = std::min<uint32_t>(BamRecord::oplen(pr.first_cig), (uint32_t)r.l_seq);
+        pr.seg_clip[0][0] = add_segment(b, base, len, kClsFirstSeen, has_n);
+        pr.seg_clip[0][1] = add_segment(b, base, len, kClsSecondSeen, has_n);
+      }
+      if (clip_r && r.n_cigar > 1) {  // with a single op the "last" op is the first: handled as left twice (extract.nim:102-112)
+        const uint32_t len = std::min<uint32_t>(BamRecord::oplen(pr.last_cig), (uint32_t)r.l_seq);
+        pr.seg_clip[1][0] = add_segment(b, base + (uint64_t)r.l_seq - len, len, kClsFirstSeen, has_n);
+        pr.seg_clip[1][1] = add_segment(b, base + (uint64_t)r.l_seq - len, len, kClsSecondSeen, has_n);
+      }
+    }
+    b.recs.push_back(pr);
+  }
+
+  void submit(Batch &b) {
+    n_scanned += b.n_seg;
+    gpu_check(strgpu_scan_submit(gpu, b.seq2, b.n_bases, b.any_n ? b.nmask : nullptr, b.segs, b.n_seg, b.max_len, b.out, &b.ticket),
+              "scan_submit");
+    b.in_flight = true;
+  }
+  void wait(Batch &b) {
+    gpu_check(strgpu_scan_wait(gpu, b.ticket), "scan_wait");
+    b.in_flight = false;
+  }
+
+  // ---- replay: extract.nim:63-132,192-248 with scan results looked up instead of computed
+  Tread to_tread(const Batch &b, const Pending &r) {
+    Tread t;
+    t.tid = r.tid;
+    t.position = (uint32_t)std::max(0, r.pos);
+    t.flag = r.flag;
+    t.split = kNone;
+    t.mapping_quality = r.mapq;
+    t.qname.assign(b.names.data() + r.qname_off, r.qname_len);
+    int align_length = r.m_len, repeat_count = 0;
+    if (r.seg_full >= 0) {
+      const strgpu_repeat &res = b.out[r.seg_full];
+      std::memcpy(t.repeat.data(), res.unit, 6);
+      repeat_count = res.repeat_count;
+      align_length = r.l_seq;
+    }
+    if (repeat_count >= 256) throw std::runtime_error("[strling] repeat_count >= 256 for read " + t.qname);  // doAssert, extract.nim:72
+    t.repeat_count = (uint8_t)repeat_count;
+    t.align_length = (uint8_t)align_length;
+    if (r.n_cigar > 1 && BamRecord::op(r.first_cig) == 4 && BamRecord::oplen(r.first_cig) > 16) t.split = kNoneLeft;
+    if (r.n_cigar > 1 && BamRecord::op(r.last_cig) == 4 && BamRecord::oplen(r.last_cig) > 16) t.split = kNoneRight;
+    return t;
+  }
+
+  void add_soft(const Batch &b, const Pending &r, int cls_idx, const std::array<char, 6> &read_repeat, const std::string &qname) {
+    if (r.mapq < opts.min_mapq) return;
+    if (r.n_cigar == 0 || (BamRecord::op(r.first_cig) != 4 && BamRecord::op(r.last_cig) != 4)) return;
+    const int idxs[2] = {0, (int)r.n_cigar - 1};
+    for (int cig_index : idxs) {
+      const uint32_t c = cig_index == 0 ? r.first_cig : r.last_cig;
+      if (BamRecord::op(c) != 4) continue;
+      const uint32_t clen = BamRecord::oplen(c);
+      if (read_repeat[0] == 0 && clen <= 16) continue;
+      const bool is_left = cig_index == 0;
+      const int32_t si = r.seg_clip[is_left ? 0 : 1][cls_idx];
+      if (si < 0) continue;
+      const strgpu_repeat &res = b.out[si];
+      if (res.repeat_count == 0) continue;
+      Tread tr;
+      tr.tid = r.tid;
+      tr.position = (uint32_t)(is_left ? std::max(0, r.pos) : std::max(0, r.stop));
+      tr.flag = r.flag;
+      std::memcpy(tr.repeat.data(), res.unit, 6);
+      tr.repeat_count = (uint8_t)res.repeat_count;
+      tr.align_length = (uint8_t)std::min<uint32_t>(clen, (uint32_t)r.l_seq);
+      tr.split = is_left ? kLeft : kRight;
+      tr.mapping_quality = r.mapq;
+      tr.qname = qname;
+      if (p_repeat(tr) < 0.9) continue;
+      cache.push_back(std::move(tr));
+    }
+  }
+
+  void add(const Batch &b, const Pending &r) {
+    std::string qname(b.names.data() + r.qname_off, r.qname_len);
+    auto it = tbl.end();
+    bool after_mate = r.tid > r.mate_tid;
+    if (!after_mate && r.tid == r.mate_tid) {
+      if (r.pos > r.mate_pos) after_mate = true;
+      else if (r.pos == r.mate_pos) { it = tbl.find(qname); after_mate = it != tbl.end(); }
+    }
+    if (after_mate) {
+      if (it == tbl.end()) it = tbl.find(qname);
+      if (it == tbl.end()) return;
+      Tread mate = std::move(it->second);
+      tbl.erase(it);
+      Tread self = to_tread(b, r);
+      add_soft(b, r, 1, self.repeat, qname);  // opts.proportion_repeat = min(p, 0.6)
+      if (mate.repeat_count == 0 && self.repeat_count == 0) return;
+      if (unplaced_pair(self, mate, opts)) {
+        if (self.repeat[0] == 0 || mate.repeat[0] == 0) return;
+        self.repeat = canonical_repeat(self.repeat);
+        self.position = 0;
+        self.tid = -1;
+        mate.repeat = canonical_repeat(mate.repeat);
+        mate.position = 0;
+        mate.tid = -1;
+        cache.push_back(std::move(self));
+        cache.push_back(std::move(mate));
+        return;
+      }
+      const uint32_t mp = mate.position;
+      if (adjust_by(mate, self, opts, self.position)) cache.push_back(mate);
+      if (adjust_by(self, mate, opts, mp)) cache.push_back(std::move(self));
+    } else {
+      Tread tr = to_tread(b, r);
+      add_soft(b, r, 0, tr.repeat, qname);  // opts.proportion_repeat = p - 0.07
+      auto ins = tbl.emplace(qname, std::move(tr));
+      if (!ins.second) {  // hasKeyOrPut found the key: warn and drop it (extract.nim:245-248)
+        if (n_warned++ < 20)
+          std::fprintf(stderr, "[strling] warning. bad read (this happens with bwa-kit alignments):%s already in table\n", qname.c_str());
+        tbl.erase(ins.first);
+      }
+    }
+  }
+
+  void replay(const Batch &b) {
+    for (const Pending &r : b.recs) add(b, r);
+  }
+};
+
+}  // namespace
+
+// utils.nim:86-111 with n_reads = 2_000_000, skip_reads = 100_000 (extract.nim:273, call.nim:76)
+std::array<uint32_t, 4096> fragment_length_distribution(const std::string &bam, int threads) {
+  std::array<uint32_t, 4096> frag{};
+  BamReader rd(bam, threads);
+  BamRecord r;
+  int64_t i = -1, counted = 0;
+  std::vector<int32_t> skipped;
+  while (rd.next(r)) {
+    i++;
+    if (!(r.flag & 0x2)) continue;
+    if (r.flag & (0x800 | 0x100)) continue;
+    if (r.isize < 0 || r.isize > 4095) continue;
+    if (i < 100000) { skipped.push_back(r.isize); continue; }
+    skipped.clear();
+    frag[(size_t)r.isize]++;
+    if (++counted > 2000000) break;
+  }
+  uint64_t sum = 0;
+  for (uint32_t c : frag) sum += c;
+  if (sum == 0) {
+    std::fprintf(stderr, "using first reads in fragment_length_distribution calculation as there were not enough\n");
+    for (int32_t s : skipped) frag[(size_t)s]++;
+  }
+  return frag;
+}
+
+
+int extract_run(const ExtractArgs &a) {
+  using clk = std::chrono::steady_clock;
+  const auto t_start = clk::now();
+  // ---- pass 1: fragment length distribution (utils.nim:86-111), skip_reads = 100000 (extract.nim:273)
+  std::array<uint32_t, 4096> frag = fragment_length_distribution(a.bam, a.threads);
+  Extractor ex;
+  ex.verbose = a.verbose;
+  ex.p = a.proportion_repeat;
+  ex.opts.median_fragment_length = frag_median(frag);
+  ex.opts.proportion_repeat = a.proportion_repeat;
+  ex.opts.min_mapq = (uint8_t)a.min_mapq;
+  if (a.verbose) {
+    std::fprintf(stderr, "Calculated median fragment length:%d\n", ex.opts.median_fragment_length);
+    std::fprintf(stderr, "10th, 90th percentile of fragment length:%d %d\n", frag_median(frag, 0.1), frag_median(frag, 0.9));
+  }
+
+  BamReader rd(a.bam, a.threads);
+  ex.targets = &rd.targets();
+  std::unordered_map<std::string, Intervals> genome_str;
+  if (!a.genome_repeats.empty()) {
+    std::ifstream probe(a.genome_repeats);
+    if (!probe)
+      throw std::runtime_error("[strling] genome repeats file " + a.genome_repeats +
+                               " does not exist; building it (`strling index`) is not part of this build");
+    std::fprintf(stderr, "[strling] using existing file %s for genome repeats\n", a.genome_repeats.c_str());
+    genome_str = read_bed(a.genome_repeats);
+  } else {
+    std::fprintf(stderr, "[strling] no -g genome repeats file: every read is scanned (the reference would build the STR index from the fasta first)\n");
+  }
+  ex.genome_str_by_tid.assign(rd.targets().size(), nullptr);
+  for (size_t t = 0; t < rd.targets().size(); t++) {
+    auto it = genome_str.find(rd.targets()[t].name);
+    if (it != genome_str.end()) ex.genome_str_by_tid[t] = &it->second;
+  }
+
+  int rc = strgpu_create(&ex.gpu, a.device);
+  if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + strgpu_error_string(rc));
+  const double classes[3] = {a.proportion_repeat, a.proportion_repeat - 0.07, std::min(a.proportion_repeat, 0.6)};
+  ex.gpu_check(strgpu_set_proportions(ex.gpu, classes, 3), "set_proportions");
+
+  constexpr int kBatches = STRGPU_SLOTS;
+  Batch batches[kBatches];
+  const uint64_t cap_bases = (uint64_t)a.batch_reads * 160 + 4096;
+  const uint32_t cap_seg = (uint32_t)std::min<uint64_t>((uint64_t)a.batch_reads * 2 + 64, 0xfffffff0u);
+  for (auto &b : batches) ex.alloc_batch(b, cap_bases, cap_seg);
+
+  std::fprintf(stderr, "[strling] collecting str-like reads\n");
+  const auto t0 = clk::now();
+  uint64_t tail_voffset = 0;
+  bool have_tail = false;
+  int cur = 0;          // batch being filled
+  int oldest = -1;      // oldest batch in flight
+  int n_in_flight = 0;
+  auto flush = [&](bool final) {
+    Batch &b = batches[cur];
+    if (!b.recs.empty()) {
+      ex.submit(b);
+      if (oldest < 0) oldest = cur;
+      n_in_flight++;
+      cur = (cur + 1) % kBatches;
+    }
+    // keep at most kBatches-1 in flight so the batch being filled is always free; drain everything at the end
+    while (n_in_flight > (final ? 0 : kBatches - 1)) {
+      Batch &o = batches[oldest];
+      ex.wait(o);
+      ex.replay(o);
+      ex.reset_batch(o);
+      oldest = (oldest + 1) % kBatches;
+      n_in_flight--;
+    }
+    if (n_in_flight == 0) oldest = -1;
+  };
+  auto feed = [&](BamReader &reader, bool first_pass) {
+    BamRecord r;
+    int32_t tid_seen = -1;
+    while (reader.next(r)) {
+      if (first_pass && r.tid < 0 && !have_tail) { have_tail = true; tail_voffset = r.voffset; }
+      if (r.flag & (0x100 | 0x800)) continue;
+      if (first_pass && r.tid != tid_seen && r.tid >= 0) {
+        if (rd.targets()[(size_t)r.tid].length > 2000000u) std::fprintf(stderr, "[strling] extracting chromosome:%s\n", rd.targets()[(size_t)r.tid].name.c_str());
+        tid_seen = r.tid;
+      }
+      ex.n_reads++;
+      if (ex.verbose && ex.n_reads % 10000000 == 0) {
+        const double dt = std::chrono::duration<double>(clk::now() - t0).count();
+        std::fprintf(stderr, "%llu %.1f reads/sec tbl len: %zu cache len: %zu\n", (unsigned long long)ex.n_reads, ex.n_reads / dt, ex.tbl.size(), ex.cache.size());
+      }
+      ex.stage(batches[cur], r);
+      if (batches[cur].recs.size() >= a.batch_reads || ex.batch_full(batches[cur])) flush(false);
+    }
+  };
+  feed(rd, true);                       // pass 2: every record in file order (extract.nim:308-322)
+  flush(true);
+  std::fprintf(stderr, "[strling] extracting unmapped reads\n");
+  if (have_tail) {                      // ibam.query("*"): the no-coordinate tail again (extract.nim:326-329)
+    BamReader tail(a.bam, a.threads);
+    tail.seek(tail_voffset);
+    feed(tail, false);
+    flush(true);
+  }
+  const double dt = std::chrono::duration<double>(clk::now() - t0).count();
+
+  std::fprintf(stderr, "[strling] writing binary file:%s\n", a.bin.c_str());
+  BinFile bf;
+  bf.proportion_repeat = (float)a.proportion_repeat;
+  bf.min_mapq = (uint8_t)a.min_mapq;
+  bf.frag_dist = frag;
+  bf.header = rd.header_text();
+  bf.reads = std::move(ex.cache);
+  write_bin(a.bin, bf);
+  std::fprintf(stderr, "[strling] finished extraction\n");
+  if (a.verbose) {
+    const double total = std::chrono::duration<double>(clk::now() - t_start).count();
+    std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
+                 (unsigned long long)ex.n_reads, (unsigned long long)ex.n_scanned, bf.reads.size(), dt, ex.n_reads / std::max(dt, 1e-9), total,
+                 (unsigned long long)strgpu_launch_count(ex.gpu));
+  }
+  for (auto &b : batches) ex.free_batch(b);
+  strgpu_destroy(ex.gpu);
+  return 0;
+}
+
+}  // namespace strling

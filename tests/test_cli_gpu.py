@@ -1,0 +1,133 @@
+"""End-to-end drop-in checks on a B200: the `strling extract | call | merge` command line (C++ host + CUDA kernels)
+against the oracle pipeline on the same synthetic BAMs -- `.bin` byte-identical, bounds / unplaced lines identical.
+Configs follow SURVEY.md 8d: config 1 (1k reads, one unit) and a config-4 stand-in built on the reference's
+simulation loci (tests/golden/disease_loci.json).  Run with -m gpu."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import extract_oracle as eo
+from strling_b200 import bamio
+from strling_b200 import build as sb_build
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def cli():
+    return sb_build.build_cli()
+
+
+def run(cli, *args):
+    r = subprocess.run([cli, *args], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def disease_setup():
+    loci_json = json.load(open(os.path.join(HERE, "golden", "disease_loci.json")))
+    chroms = sorted({l["chrom"] for l in loci_json}, key=lambda c: (len(c), c))
+    targets = [(f"chr{c}", 2_000_000) for c in chroms]
+    loci = []
+    for l in loci_json:
+        start = 50_000 + l["start"] % 1_800_000
+        width = max(20, min(200, l["stop"] - l["start"]))
+        loci.append((chroms.index(l["chrom"]), start, start + width, l["unit"]))
+    return targets, loci
+
+
+def test_config1_single_unit_bin_identical(cli, tmp_path):
+    targets = [("chr1", 1_000_000)]
+    loci = [(0, 400_000, 400_150, "CAG")]
+    recs = bamio.simulate_alignments(1, 500, targets, loci, str_pair_frac=0.5)
+    assert len(recs) == 1000
+    bam, out = str(tmp_path / "c1.bam"), str(tmp_path / "c1.bin")
+    hdr = bamio.sam_header(targets)
+    bamio.write_bam(bam, hdr, targets, recs)
+    run(cli, "extract", "-v", bam, out)
+    exp, cache, _ = eo.extract(recs, targets, hdr)
+    assert len(cache) > 100
+    assert open(out, "rb").read() == exp
+
+
+@pytest.mark.parametrize("p,q,use_bed,batch", [(0.8, 40, False, 1048576), (0.8, 40, True, 4096), (0.7, 20, True, 1000), (0.9, 0, False, 777)])
+def test_config4_extract_bin_identical(cli, tmp_path, p, q, use_bed, batch):
+    targets, loci = disease_setup()
+    recs = bamio.simulate_alignments(7, 12_000, targets, loci, unmapped_pairs=150, n_frac=0.02)
+    hdr = bamio.sam_header(targets)
+    bam, out = str(tmp_path / "c4.bam"), str(tmp_path / "c4.bin")
+    bamio.write_bam(bam, hdr, targets, recs)
+    args = ["extract", "-p", repr(p), "-q", str(q), "--batch-reads", str(batch)]
+    genome_str = None
+    if use_bed:
+        bed = str(tmp_path / "ref.str")
+        with open(bed, "w") as fh:
+            for tid, s, e, u in loci:
+                fh.write(f"{targets[tid][0]}\t{s}\t{e}\t{u}\n")
+        args += ["-g", bed]
+        genome_str = eo.read_bed(bed)
+    run(cli, *args, bam, out)
+    exp, cache, _ = eo.extract(recs, targets, hdr, p, q, genome_str)
+    got = open(out, "rb").read()
+    if got != exp:
+        ug, ue = eo.unpack_bin(got), eo.unpack_bin(exp)
+        assert len(ug["treads"]) == len(ue["treads"]), (len(ug["treads"]), len(ue["treads"]))
+        bad = [i for i in range(len(ue["treads"])) if ug["treads"][i] != ue["treads"][i] or ug["qnames"][i] != ue["qnames"][i]]
+        raise AssertionError(f"{len(bad)} records differ; first {bad[:1]}: {ug['treads'][bad[0]]} {ug['qnames'][bad[0]]} vs {ue['treads'][bad[0]]} {ue['qnames'][bad[0]]}")
+    assert len(cache) > 1000
+
+
+def test_call_and_merge_outputs_identical(cli, tmp_path):
+    targets, loci = disease_setup()
+    hdr = bamio.sam_header(targets)
+    bins, datas = [], []
+    for s in range(3):
+        recs = bamio.simulate_alignments(20 + s, 10_000, targets, loci, unmapped_pairs=100)
+        bam, out = str(tmp_path / f"s{s}.bam"), str(tmp_path / f"s{s}.bin")
+        bamio.write_bam(bam, hdr, targets, recs)
+        run(cli, "extract", bam, out)
+        exp, _, _ = eo.extract(recs, targets, hdr)
+        assert open(out, "rb").read() == exp
+        bins.append(out)
+        datas.append(exp)
+        if s == 0:
+            first_bam, first_recs = bam, recs
+    # call: cluster loop of one sample (call.nim:223-235) -> -bounds.txt, -unplaced.txt
+    prefix = str(tmp_path / "call")
+    run(cli, "call", "-m", "3", "-o", prefix, first_bam, bins[0])
+    exp_lines, exp_unplaced, _ = eo.call_clusters(datas[0], eo.fragment_length_distribution(first_recs), min_support=3)
+    got = open(prefix + "-bounds.txt").read().splitlines()
+    assert got[0] == eo.BOUNDS_HEADER
+    assert len(exp_lines) > 10 and sorted(got[1:]) == sorted(exp_lines) and got[1:] == exp_lines
+    got_un = dict(l.split("\t") for l in open(prefix + "-unplaced.txt").read().splitlines())
+    assert {k.encode(): int(v) for k, v in got_un.items()} == exp_unplaced and len(exp_unplaced) > 0
+    # merge: joint clustering with per-sample support (merge.nim:172-187)
+    for ms, extra in ((5, []), (2, ["-c", "1", "-t", "3"]), (4, ["-w", "300"])):
+        prefix = str(tmp_path / f"merge{ms}")
+        run(cli, "merge", "-m", str(ms), *extra, "-o", prefix, *bins)
+        kw = dict(min_support=ms)
+        if extra[:1] == ["-c"]:
+            kw.update(min_clip=1, min_clip_total=3)
+        if extra[:1] == ["-w"]:
+            kw.update(window=300)
+        exp_lines, _ = eo.merge(datas, **kw)
+        got = open(prefix + "-bounds.txt").read().splitlines()
+        assert got[0] == eo.BOUNDS_HEADER and len(exp_lines) > 5
+        assert sorted(got[1:]) == sorted(exp_lines) and got[1:] == exp_lines
+    # --chromosome restricts parsing to one contig (merge.nim:52,89)
+    prefix = str(tmp_path / "merge_chr")
+    run(cli, "merge", "-m", "3", "--chromosome", targets[2][0], "-o", prefix, *bins)
+    got = open(prefix + "-bounds.txt").read().splitlines()[1:]
+    all_lines, _ = eo.merge(datas, min_support=3)
+    assert got == [l for l in all_lines if l.split("\t")[0] == targets[2][0]] and len(got) > 0
+
+
+def test_cli_errors(cli, tmp_path):
+    r = subprocess.run([cli, "extract", str(tmp_path / "missing.bam"), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode != 0 and "couldn't open bam" in r.stderr
+    r = subprocess.run([cli, "merge", str(tmp_path / "missing.bin")], capture_output=True, text=True)
+    assert r.returncode != 0 and "unable to open" in r.stderr
