@@ -106,17 +106,17 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
     got_un = dict(l.split("\t") for l in open(prefix + "-unplaced.txt").read().splitlines())
     assert {k.encode(): int(v) for k, v in got_un.items()} == exp_unplaced and len(exp_unplaced) > 0
     # merge: joint clustering with per-sample support (merge.nim:172-187)
-    for ms, extra in ((5, []), (2, ["-c", "1", "-t", "3"]), (4, ["-w", "300"])):
-        prefix = str(tmp_path / f"merge{ms}")
+    for ms, extra in ((5, []), (2, ["-c", "0", "-t", "3"]), (2, ["-c", "1", "-t", "1"]), (4, ["-w", "300"])):
+        prefix = str(tmp_path / f"merge{ms}{''.join(extra)}")
         run(cli, "merge", "-m", str(ms), *extra, "-o", prefix, *bins)
         kw = dict(min_support=ms)
         if extra[:1] == ["-c"]:
-            kw.update(min_clip=1, min_clip_total=3)
+            kw.update(min_clip=int(extra[1]), min_clip_total=int(extra[3]))
         if extra[:1] == ["-w"]:
             kw.update(window=300)
         exp_lines, _ = eo.merge(datas, **kw)
         got = open(prefix + "-bounds.txt").read().splitlines()
-        assert got[0] == eo.BOUNDS_HEADER and len(exp_lines) > 5
+        assert got[0] == eo.BOUNDS_HEADER and (len(exp_lines) > 5 or extra[:2] == ["-c", "1"])
         assert sorted(got[1:]) == sorted(exp_lines) and got[1:] == exp_lines
     # --chromosome restricts parsing to one contig (merge.nim:52,89)
     prefix = str(tmp_path / "merge_chr")
