@@ -43,6 +43,8 @@ struct strgpu_ctx {
   int device = -1;
   int sm_count = 0;
   uint16_t *d_thr = nullptr;
+  uint16_t *d_luts = nullptr;
+  int variant = 0;
   bool thr_set = false;
   Slot slots[STRGPU_SLOTS];
   int *d_status_dev = nullptr;  // sticky status for strgpu_scan_device launches
@@ -119,6 +121,14 @@ int strgpu_create(strgpu_ctx **out, int device) {
   CU(ctx, cudaSetDevice(device));
   CU(ctx, cudaMalloc(&ctx->d_thr, strgpu::kThrEntries * sizeof(uint16_t)));
   CU(ctx, cudaMalloc(&ctx->d_status_dev, sizeof(int)));
+  {
+    uint16_t luts[strgpu::kLaneLutEntries];
+    strgpu::build_lane_luts(luts);
+    CU(ctx, cudaMalloc(&ctx->d_luts, sizeof(luts)));
+    CU(ctx, cudaMemcpy(ctx->d_luts, luts, sizeof(luts), cudaMemcpyHostToDevice));
+    const char *v = getenv("STRGPU_SCAN_VARIANT");
+    ctx->variant = v ? atoi(v) : 0;
+  }
   CU(ctx, cudaMemset(ctx->d_status_dev, 0, sizeof(int)));
   for (auto &s : ctx->slots) {
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -150,6 +160,7 @@ void strgpu_destroy(strgpu_ctx *ctx) {
   if (ctx->d_cl_n) cudaFree(ctx->d_cl_n);
   if (ctx->cluster_stream) cudaStreamDestroy(ctx->cluster_stream);
   if (ctx->d_thr) cudaFree(ctx->d_thr);
+  if (ctx->d_luts) cudaFree(ctx->d_luts);
   if (ctx->d_status_dev) cudaFree(ctx->d_status_dev);
   delete ctx;
 }
@@ -226,8 +237,8 @@ int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, c
     CU(ctx, cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(strgpu_segment), cudaMemcpyHostToDevice, s.stream));
     CU(ctx, cudaMemsetAsync(s.d_status, 0, sizeof(int), s.stream));
     CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
-                                       (const strgpu_segment *)s.segs.p, n_seg, max_len, ctx->d_thr,
-                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, s.stream));
+                                       (const strgpu_segment *)s.segs.p, n_seg, max_len, ctx->d_thr, ctx->d_luts,
+                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, ctx->variant, s.stream));
     ctx->launches++;
     CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
     CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
@@ -267,8 +278,8 @@ int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask,
     return fail(ctx, STRGPU_ERR_INVALID, "scan_device: misaligned device pointer");
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_segs,
-                                     n_seg, max_len, ctx->d_thr, (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count,
-                                     (cudaStream_t)cuda_stream));
+                                     n_seg, max_len, ctx->d_thr, ctx->d_luts, (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count,
+                                     ctx->variant, (cudaStream_t)cuda_stream));
   if (n_seg) ctx->launches++;
   return STRGPU_OK;
 }

@@ -159,112 +159,406 @@ struct WarpScratch {
   uint8_t tab[kTab];
 };
 
+// decode (kmer.decode with alphabet "CATG") + reduce_repeat (utils.nim:220-233,271), one 8-byte store
+__device__ __forceinline__ void emit_result(strgpu_repeat *out, uint32_t s, const ScanState &st) {
+  strgpu_repeat res;
+#pragma unroll
+  for (int i = 0; i < 6; i++) res.unit[i] = 0;
+  res.repeat_count = 0;
+  if (st.unit_k > 0) {
+    const uint32_t alpha = 0x47544143u;  // 'C','A','T','G' little-endian
+    bool homo = true;
+    const uint32_t first = (st.unit_code >> (2 * (st.unit_k - 1))) & 3u;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      if (j < st.unit_k) {
+        const uint32_t b = (st.unit_code >> (2 * (st.unit_k - 1 - j))) & 3u;
+        res.unit[j] = (char)((alpha >> (8 * b)) & 0xffu);
+        homo = homo && (b == first);
+      }
+    }
+    int rc = st.rc;
+    if (homo) {
+#pragma unroll
+      for (int j = 1; j < 6; j++) res.unit[j] = 0;
+      rc *= st.unit_k;
+    }
+    res.repeat_count = (uint16_t)rc;
+  }
+  store_result(out, s, res);
+}
+
+// One segment on one warp: stage it, run the ladder from rung `start_k` with the given state, store the result.
+// ws.tab must be all zero on entry (it is left all zero).
+template <int MAXLEN>
+__device__ __forceinline__ void warp_scan_segment(WarpScratch<MAXLEN> &ws, const uint32_t *__restrict__ seq,
+                                                  const uint32_t *__restrict__ nmask, const strgpu_segment sg, uint32_t s,
+                                                  const uint16_t *__restrict__ thr, int lane, int start_k, ScanState st,
+                                                  strgpu_repeat *__restrict__ out, int *status) {
+  constexpr int MAXR2 = (MAXLEN / 2 + 31) / 32, MAXR3 = (MAXLEN / 3 + 31) / 32, MAXR4 = (MAXLEN / 4 + 31) / 32,
+                MAXR5 = (MAXLEN / 5 + 31) / 32, MAXR6 = (MAXLEN / 6 + 31) / 32;
+  constexpr int MAXP = (MAXLEN + 31) / 32;
+  const int L = sg.len;
+  if (L > MAXLEN || L > STRGPU_MAX_SEGMENT_LEN) {  // warp-uniform
+    if (lane == 0) {
+      atomicExch(status, (int)STRGPU_ERR_TOO_LONG);
+      emit_result(out, s, ScanState{-1, 0u, 0, 0});
+    }
+    return;
+  }
+  // ---- stage the segment: aligned big-endian words, base 0 at bit 31 of sw[0]
+  const int n_words = (2 * L + 31) >> 5;
+  __syncwarp();
+  for (int l = lane; l < n_words + 1; l += 32) {
+    uint32_t v = 0;
+    if (l < n_words) {
+      const uint32_t g = (sg.base_off >> 4) + (uint32_t)l;
+      const uint32_t hi = __byte_perm(seq[g], 0, 0x0123);
+      const uint32_t lo = __byte_perm(seq[g + 1], 0, 0x0123);
+      v = __funnelshift_l(lo, hi, 2u * (sg.base_off & 15u));
+    }
+    ws.sw[l] = v;
+  }
+  const bool has_n = (sg.flags & STRGPU_SEG_HAS_N) != 0;
+  int n_count = 0;
+  if (has_n) {  // warp-uniform
+    const int n_nw = (L + 31) >> 5;
+    for (int l = lane; l < n_nw + 1; l += 32) {
+      uint32_t v = 0;
+      if (l < n_nw) {
+        const uint32_t g = (sg.base_off >> 5) + (uint32_t)l;
+        v = __funnelshift_r(nmask[g], nmask[g + 1], sg.base_off & 31u);
+        const int rem = L - 32 * l;
+        if (rem < 32) v &= (1u << rem) - 1u;
+      }
+      ws.nm[l] = v;
+      n_count += __popc(v);
+    }
+    n_count = __reduce_add_sync(kFull, n_count);
+  }
+  __syncwarp();
+
+  if (n_count <= 20) {  // utils.nim:238
+    const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+    const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
+    const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen + L;
+    bool go = true;
+    if (start_k <= 2) go = ladder_step<2, MAXR2, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[0], tg[0], st);
+    if (go && start_k <= 3) go = ladder_step<3, MAXR3, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[kThrLen], tg[kThrLen], st);
+    if (go && start_k <= 4) go = ladder_step<4, MAXR4, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[2 * kThrLen], tg[2 * kThrLen], st);
+    if (go && start_k <= 5) go = ladder_step<5, MAXR5, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[3 * kThrLen], tg[3 * kThrLen], st);
+    if (go) ladder_step<6, MAXR6, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[4 * kThrLen], tg[4 * kThrLen], st);
+  }
+  if (lane == 0) emit_result(out, s, st);
+}
+
 template <int MAXLEN, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *__restrict__ seq,
                                                                const uint32_t *__restrict__ nmask,
                                                                const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                const uint16_t *__restrict__ thr,
                                                                strgpu_repeat *__restrict__ out, int *status) {
-  constexpr int MAXR2 = (MAXLEN / 2 + 31) / 32, MAXR3 = (MAXLEN / 3 + 31) / 32, MAXR4 = (MAXLEN / 4 + 31) / 32,
-                MAXR5 = (MAXLEN / 5 + 31) / 32, MAXR6 = (MAXLEN / 6 + 31) / 32;
-  constexpr int MAXP = (MAXLEN + 31) / 32;
   __shared__ WarpScratch<MAXLEN> scratch[WARPS];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   WarpScratch<MAXLEN> &ws = scratch[warp];
   for (int i = lane; i < WarpScratch<MAXLEN>::kTab; i += 32) ws.tab[i] = 0;
   __syncwarp();
-
   const uint32_t warps_total = gridDim.x * WARPS;
-  for (uint32_t s = blockIdx.x * WARPS + warp; s < n_seg; s += warps_total) {
-    const strgpu_segment sg = segs[s];
-    const int L = sg.len;
-    strgpu_repeat res;
-#pragma unroll
-    for (int i = 0; i < 6; i++) res.unit[i] = 0;
-    res.repeat_count = 0;
-    if (L > MAXLEN || L > STRGPU_MAX_SEGMENT_LEN) {  // warp-uniform
-      if (lane == 0) {
-        atomicExch(status, (int)STRGPU_ERR_TOO_LONG);
-        store_result(out, s, res);
-      }
-      continue;
-    }
-    // ---- stage the segment: aligned big-endian words, base 0 at bit 31 of sw[0]
-    const int n_words = (2 * L + 31) >> 5;
-    __syncwarp();
-    for (int l = lane; l < n_words + 1; l += 32) {
-      uint32_t v = 0;
-      if (l < n_words) {
-        const uint32_t g = (sg.base_off >> 4) + (uint32_t)l;
-        const uint32_t hi = __byte_perm(seq[g], 0, 0x0123);
-        const uint32_t lo = __byte_perm(seq[g + 1], 0, 0x0123);
-        v = __funnelshift_l(lo, hi, 2u * (sg.base_off & 15u));
-      }
-      ws.sw[l] = v;
-    }
-    const bool has_n = (sg.flags & STRGPU_SEG_HAS_N) != 0;
-    int n_count = 0;
-    if (has_n) {  // warp-uniform
-      const int n_nw = (L + 31) >> 5;
-      for (int l = lane; l < n_nw + 1; l += 32) {
-        uint32_t v = 0;
-        if (l < n_nw) {
-          const uint32_t g = (sg.base_off >> 5) + (uint32_t)l;
-          v = __funnelshift_r(nmask[g], nmask[g + 1], sg.base_off & 31u);
-          const int rem = L - 32 * l;
-          if (rem < 32) v &= (1u << rem) - 1u;
-        }
-        ws.nm[l] = v;
-        n_count += __popc(v);
-      }
-      n_count = __reduce_add_sync(kFull, n_count);
-    }
-    __syncwarp();
+  for (uint32_t s = blockIdx.x * WARPS + warp; s < n_seg; s += warps_total)
+    warp_scan_segment<MAXLEN>(ws, seq, nmask, segs[s], s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
+}
 
+// ================================================================================================
+// K1 v2: one LANE per segment (segments of <= 160 bases without non-ACGT bases).
+//   * each thread keeps its read as a private column of shared memory words ([word][thread]: bank == lane, conflict free),
+//   * k = 2, 3, 4: min-rotation class of every window through a small shared LUT, counted in a private column of
+//     uint32 counters ([class][thread], conflict free) with the running leader updated exactly like Seq.inc (strict >),
+//   * recount: bit-parallel pattern match over the ten words; popcount when no two matches can overlap, otherwise a
+//     run-wise greedy walk,
+//   * segments that survive to k = 5, 6 (a few per cent), segments with N, and nothing else, are compacted into a
+//     per-CTA queue and finished by the warp-per-segment code above on the same CTA.
+// ================================================================================================
+constexpr int kLaneThreads = 128;
+constexpr int kLaneWords = 11;         // ten words hold 160 bases; one more absorbs the re-alignment shift
+constexpr int kLaneClasses = 70;       // min-rotation classes of 4-mers (24 for 3-mers, 10 for 2-mers)
+constexpr int kLaneTabWords = kLaneClasses * kLaneThreads;
+constexpr int kLaneRdWords = kLaneWords * kLaneThreads;
+constexpr int kLutEntries = 16 + 64 + 256;       // class byte-offset LUTs for k = 2, 3, 4
+constexpr int kRevEntries = 10 + 24 + 70;        // class -> canonical code
+constexpr int kQueueWords = 4 * kLaneThreads;
+constexpr int kLaneSmemBytes = (kLaneTabWords + kLaneRdWords + kQueueWords + 4) * 4 + (kLutEntries + kRevEntries) * 2 + 16;
+static_assert(sizeof(WarpScratch<512>) * (kLaneThreads / 32) <= (size_t)kLaneTabWords * 4, "warp scratch must fit in the counter region");
+
+template <int K> struct LaneK;
+template <> struct LaneK<2> { static constexpr int wpw = 8, bits = 32, classes = 10, lut = 0, rev = 0; };
+template <> struct LaneK<3> { static constexpr int wpw = 5, bits = 30, classes = 24, lut = 16, rev = 10; };
+template <> struct LaneK<4> { static constexpr int wpw = 4, bits = 32, classes = 70, lut = 80, rev = 34; };
+
+// word `wi` of the k-specific window stream: k = 2, 4 use the aligned words as they are (8 / 4 windows each);
+// k = 3 re-cuts the bit stream into 30-bit pieces (5 windows each)
+template <int K>
+__device__ __forceinline__ uint32_t lane_word(const uint32_t *rd, int wi) {
+  if (K == 3) {
+    const int bit = 30 * wi;
+    const int a = bit >> 5;
+    return __funnelshift_l(rd[(a + 1) * kLaneThreads], rd[a * kLaneThreads], bit & 31) >> 2;
+  }
+  return rd[wi * kLaneThreads];
+}
+
+template <int K>
+__device__ __forceinline__ void lane_count(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, const uint16_t *rev, int L,
+                                           int &M, uint32_t &leader) {
+  using P = LaneK<K>;
+  constexpr uint32_t kMask = (1u << (2 * K)) - 1u;
+  const int W = L / K;
+  const int nfull = W / P::wpw;
+  const int rem = W - nfull * P::wpw;
+#pragma unroll
+  for (int c = 0; c < P::classes; c++) tab[c * kLaneThreads] = 0;
+  M = 0;
+  uint32_t lead_off = 0xffffffffu;
+  const uint16_t *l = lut + P::lut;
+  for (int wi = 0; wi < nfull; wi++) {
+    const uint32_t x = lane_word<K>(rd, wi);
+#pragma unroll
+    for (int t = 0; t < P::wpw; t++) {
+      const uint32_t code = (x >> (P::bits - 2 * K * (t + 1))) & kMask;
+      const uint32_t off = l[code];
+      uint32_t *slot = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(tab) + off);
+      const int cnt = (int)*slot + 1;
+      *slot = (uint32_t)cnt;
+      if (cnt > M) { M = cnt; lead_off = off; }   // Seq.inc: strict >, earlier leader keeps ties (utils.nim:192-195)
+    }
+  }
+  if (rem > 0) {
+    const uint32_t x = lane_word<K>(rd, nfull);
+    for (int t = 0; t < rem; t++) {
+      const uint32_t code = (x >> (P::bits - 2 * K * (t + 1))) & kMask;
+      const uint32_t off = l[code];
+      uint32_t *slot = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(tab) + off);
+      const int cnt = (int)*slot + 1;
+      *slot = (uint32_t)cnt;
+      if (cnt > M) { M = cnt; lead_off = off; }
+    }
+  }
+  leader = (lead_off == 0xffffffffu) ? kMask : (uint32_t)rev[P::rev + lead_off / (4 * kLaneThreads)];
+}
+
+// read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254)
+template <int K>
+__device__ __forceinline__ int lane_recount(const uint32_t *rd, int L, uint32_t pat) {
+  const int npos = L - K + 1;
+  if (npos <= 0) return 0;
+  constexpr uint32_t kLow = 0x55555555u;
+  uint32_t w[11], m[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) w[i] = rd[i * kLaneThreads];
+  w[10] = 0;
+#pragma unroll
+  for (int i = 0; i < 10; i++) m[i] = kLow;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const uint32_t rep = ((pat >> (2 * (K - 1 - j))) & 3u) * kLow;
+    uint32_t e[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+      const uint32_t t = w[i] ^ rep;
+      e[i] = ~(t | (t >> 1)) & kLow;          // slot LSB set <=> that base equals pattern base j
+    }
+#pragma unroll
+    for (int i = 0; i < 10; i++) m[i] &= (j == 0) ? e[i] : __funnelshift_l(e[i + 1], e[i], 2 * j);
+  }
+  // keep positions < npos (position p of word i sits at bit 30 - 2p)
+  uint32_t conflict = 0;
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const int n = npos - 16 * i;
+    const uint32_t vm = n >= 16 ? kLow : (n <= 0 ? 0u : (kLow & ~((1u << (32 - 2 * n)) - 1u)));
+    m[i] &= vm;
+  }
+#pragma unroll
+  for (int d = 1; d < K; d++) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) conflict |= m[i] & __funnelshift_l(i < 9 ? m[i + 1] : 0u, m[i], 2 * d);
+  }
+  int c = 0;
+  if (conflict == 0) {  // no two matches closer than K: every match counts
+#pragma unroll
+    for (int i = 0; i < 10; i++) c += __popc(m[i]);
+    return c;
+  }
+  int next = 0;  // first position the greedy walk may use
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    uint32_t mm = m[i];
+    while (mm) {
+      const int hb = 31 - __clz(mm);                       // earliest remaining match of this word
+      const uint32_t gap = ~mm & kLow & ((1u << hb) - 1u);  // first non-match slot after it
+      const int hb2 = gap ? 31 - __clz(gap) : -2;
+      const int p = 16 * i + ((30 - hb) >> 1);
+      const int e = 16 * i + ((30 - hb2) >> 1);            // run of consecutive matches [p, e)
+      const int s0 = p > next ? p : next;
+      if (s0 < e) {
+        const int n = (e - s0 + K - 1) / K;
+        c += n;
+        next = s0 + n * K;
+      }
+      mm = gap ? (mm & ((1u << hb2) - 1u)) : 0u;
+    }
+  }
+  return c;
+}
+
+template <int K>
+__device__ __forceinline__ bool lane_step(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, const uint16_t *rev, int L,
+                                          int thr_p, int thr_giveup, ScanState &st) {
+  int M;
+  uint32_t leader;
+  lane_count<K>(rd, tab, lut, rev, L, M, leader);
+  int score = M * K;
+  if (score <= st.best) return !(M < thr_giveup);
+  const int c = lane_recount<K>(rd, L, leader);
+  score = c * K;
+  if (score < st.best) return true;
+  st.best = score;
+  if (c > thr_p) {
+    st.unit_code = leader;
+    st.unit_k = K;
+    st.rc = c;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
+                                                                 const strgpu_segment *__restrict__ segs, uint32_t n_seg,
+                                                                 const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
+                                                                 strgpu_repeat *__restrict__ out, int *status) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t *tab_all = smem;                               // [class][thread] counters; warp scratch in the queue phase
+  uint32_t *rd_all = tab_all + kLaneTabWords;             // [word][thread] read columns
+  uint32_t *queue = rd_all + kLaneRdWords;                // {segment, best, unit_code | unit_k << 24, rc | start_k << 16}
+  uint32_t *qcount = queue + kQueueWords;
+  uint16_t *lut = reinterpret_cast<uint16_t *>(qcount + 4);
+  uint16_t *rev = lut + kLutEntries;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kLutEntries + kRevEntries; i += kLaneThreads) lut[i] = luts[i];
+  uint32_t *tab = tab_all + tid;
+  uint32_t *rd = rd_all + tid;
+  const uint32_t n_tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (tid == 0) *qcount = 0;
+    __syncthreads();
+    const uint32_t s = tile * kLaneThreads + tid;
+    const bool active = s < n_seg;
+    strgpu_segment sg{0, 0, 0, 0};
+    if (active) sg = segs[s];
+    const int L = sg.len;
+    const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
     ScanState st{-1, 0u, 0, 0};
-    if (n_count <= 20) {  // utils.nim:238
+    int handoff_k = (active && !lane_path) ? 2 : 0;       // 0: finished here
+    if (lane_path) {
+      // ---- stage: eleven words, re-aligned so that base 0 sits at bit 31 of word 0
+      const uint32_t g = sg.base_off >> 4;
+      const uint32_t sh = 2u * (sg.base_off & 15u);
+      const int n_words = (2 * L + 31) >> 5;
+      uint32_t raw[kLaneWords + 1];
+#pragma unroll
+      for (int j = 0; j < kLaneWords + 1; j++) raw[j] = (j <= n_words) ? __byte_perm(seq[g + j], 0, 0x0123) : 0u;
+#pragma unroll
+      for (int j = 0; j < kLaneWords; j++) rd[j * kLaneThreads] = __funnelshift_l(raw[j + 1], raw[j], sh);
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
       const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
       const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen + L;
-      bool go = ladder_step<2, MAXR2, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[0], tg[0], st);
-      if (go) go = ladder_step<3, MAXR3, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[kThrLen], tg[kThrLen], st);
-      if (go) go = ladder_step<4, MAXR4, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[2 * kThrLen], tg[2 * kThrLen], st);
-      if (go) go = ladder_step<5, MAXR5, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[3 * kThrLen], tg[3 * kThrLen], st);
-      if (go) ladder_step<6, MAXR6, MAXP>(ws.sw, ws.nm, has_n, ws.tab, L, lane, tp[4 * kThrLen], tg[4 * kThrLen], st);
+      bool go = lane_step<2>(rd, tab, lut, rev, L, tp[0], tg[0], st);
+      if (go) go = lane_step<3>(rd, tab, lut, rev, L, tp[kThrLen], tg[kThrLen], st);
+      if (go) go = lane_step<4>(rd, tab, lut, rev, L, tp[2 * kThrLen], tg[2 * kThrLen], st);
+      if (go) handoff_k = 5;
+      else emit_result(out, s, st);
     }
-    if (lane == 0) {
-      if (st.unit_k > 0) {
-        // decode (kmer.decode with alphabet "CATG") + reduce_repeat (utils.nim:220-233,271)
-        const uint32_t alpha = 0x47544143u;  // 'C','A','T','G' little-endian
-        bool homo = true;
-        const uint32_t first = (st.unit_code >> (2 * (st.unit_k - 1))) & 3u;
-        for (int j = 0; j < st.unit_k; j++) {
-          const uint32_t b = (st.unit_code >> (2 * (st.unit_k - 1 - j))) & 3u;
-          res.unit[j] = (char)((alpha >> (8 * b)) & 0xffu);
-          homo = homo && (b == first);
-        }
-        int rc = st.rc;
-        if (homo) {
-          for (int j = 1; j < st.unit_k; j++) res.unit[j] = 0;
-          rc *= st.unit_k;
-        }
-        res.repeat_count = (uint16_t)rc;
+    if (handoff_k) {
+      const uint32_t q = atomicAdd(qcount, 1u);
+      queue[4 * q + 0] = s;
+      queue[4 * q + 1] = (uint32_t)st.best;
+      queue[4 * q + 2] = st.unit_code | ((uint32_t)st.unit_k << 24);
+      queue[4 * q + 3] = (uint32_t)st.rc | ((uint32_t)handoff_k << 16);
+    }
+    __syncthreads();
+    const uint32_t nq = *qcount;
+    if (nq) {  // CTA-uniform: finish the queued segments warp-per-segment; the counter region becomes warp scratch
+      WarpScratch<512> &ws = reinterpret_cast<WarpScratch<512> *>(tab_all)[warp];
+      for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
+      __syncwarp();
+      for (uint32_t e = warp; e < nq; e += kLaneThreads / 32) {
+        const uint32_t qs = queue[4 * e + 0];
+        ScanState qst;
+        qst.best = (int)queue[4 * e + 1];
+        qst.unit_code = queue[4 * e + 2] & 0xffffffu;
+        qst.unit_k = (int)(queue[4 * e + 2] >> 24);
+        qst.rc = (int)(queue[4 * e + 3] & 0xffffu);
+        const int start_k = (int)(queue[4 * e + 3] >> 16);
+        warp_scan_segment<512>(ws, seq, nmask, segs[qs], qs, thr, lane, start_k, qst, out, status);
       }
-      store_result(out, s, res);
     }
+    __syncthreads();
   }
 }
 
 }  // namespace
 
+// class LUTs of the lane kernel: for k = 2, 3, 4 the byte offset (class * 4 * kLaneThreads) of every window code's
+// min-rotation class, then the canonical (minimal) code of every class
+void build_lane_luts(uint16_t *dst) {
+  int lut_off = 0, rev_off = kLutEntries;
+  for (int k = 2; k <= 4; k++) {
+    const int n = 1 << (2 * k);
+    const uint32_t mask = (uint32_t)n - 1u;
+    int n_classes = 0;
+    for (int code = 0; code < n; code++) {
+      uint32_t m = (uint32_t)code, x = (uint32_t)code;
+      for (int j = 1; j < k; j++) {
+        x = ((x << 2) | (x >> (2 * k - 2))) & mask;
+        if (x < m) m = x;
+      }
+      if (m == (uint32_t)code) dst[rev_off + n_classes++] = (uint16_t)code;  // canonical codes ascend, so class ids do too
+    }
+    for (int code = 0; code < n; code++) {
+      uint32_t m = (uint32_t)code, x = (uint32_t)code;
+      for (int j = 1; j < k; j++) {
+        x = ((x << 2) | (x >> (2 * k - 2))) & mask;
+        if (x < m) m = x;
+      }
+      int cls = 0;
+      while (dst[rev_off + cls] != (uint16_t)m) cls++;
+      dst[lut_off + code] = (uint16_t)(cls * 4 * kLaneThreads);
+    }
+    lut_off += n;
+    rev_off += n_classes;
+  }
+}
+
 cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
-                               uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, strgpu_repeat *d_out,
-                               int *d_status, int sm_count, cudaStream_t stream) {
+                               uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
+                               strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream) {
   if (n_seg == 0) return cudaSuccess;
   constexpr int kWarps = 8;
   const uint32_t blocks_needed = (n_seg + kWarps - 1) / kWarps;
-  if (max_len <= (uint32_t)kShortMaxLen) {
+  if (max_len <= (uint32_t)kShortMaxLen && variant != 1) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(repeat_scan_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmemBytes);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(repeat_scan_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
+    uint32_t grid = (uint32_t)sm_count * 5u;  // 5 resident CTAs of 128 threads per SM (shared-memory bound)
+    if (grid > tiles) grid = tiles;
+    repeat_scan_lane<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr, d_luts, d_out,
+                                                                     d_status);
+  } else if (max_len <= (uint32_t)kShortMaxLen) {
     uint32_t grid = (uint32_t)sm_count * 8u;  // 8 resident CTAs of 256 threads per SM
     if (grid > blocks_needed) grid = blocks_needed;
     repeat_scan_warp<kShortMaxLen, kWarps><<<grid, kWarps * 32, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr,

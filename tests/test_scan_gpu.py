@@ -114,12 +114,31 @@ def test_adversarial_short_and_periodic(gpu):
 
 
 def test_too_long_segment_is_reported(gpu):
-    seq2, nmask, segs, n_bases = sb.pack_reads(["A" * 200])
-    with pytest.raises(sb.StrGpuError) as e:
-        gpu.scan(seq2, n_bases, nmask, segs, max_len=160)  # caller lied about max_len
+    seq2, nmask, segs, n_bases = sb.pack_reads(["A" * 600])
+    with pytest.raises(sb.StrGpuError) as e:  # honest max_len: rejected on the host before anything is copied
+        gpu.scan(seq2, n_bases, nmask, segs)
     assert e.value.status == -4
-    res = gpu.scan(seq2, n_bases, nmask, segs)  # honest max_len picks the long-segment kernel
-    assert (bytes(res[0]["unit"]).rstrip(b"\0"), int(res[0]["repeat_count"])) == (b"A", 200)
+    with pytest.raises(sb.StrGpuError) as e:  # caller lied about max_len: the kernel reports it
+        gpu.scan(seq2, n_bases, nmask, segs, max_len=150)
+    assert e.value.status == -4
+    # a 200-base segment in a batch announced as <= 160 is still scanned correctly (handed to the long-segment path)
+    seq2, nmask, segs, n_bases = sb.pack_reads(["A" * 200, "CAG" * 50])
+    res = gpu.scan(seq2, n_bases, nmask, segs, max_len=160)
+    assert [(bytes(r["unit"]).rstrip(b"\0"), int(r["repeat_count"])) for r in res] == [(b"A", 200), (b"CAG", 50)]
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_both_kernel_variants_agree_with_oracle(variant, monkeypatch):
+    monkeypatch.setenv("STRGPU_SCAN_VARIANT", variant)  # 0: lane-per-segment kernel, 1: warp-per-segment kernel
+    g = sb.StrGpu(0)
+    try:
+        g.set_proportions(P)
+        reads, cls, lclip, rclip = synth.make_reads(100_000, seed=31, mix=(0.6, 0.1, 0.15, 0.15), noise=0.02, n_frac=0.01)
+        seq2, nmask, stride = synth.pack_matrix(reads)
+        segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+        check(g, reads, segs, stride, seq2, nmask)
+    finally:
+        g.close()
 
 
 def test_submit_wait_pipeline(gpu):
