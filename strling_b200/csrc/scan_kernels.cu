@@ -157,6 +157,7 @@ struct WarpScratch {
   uint32_t sw[kSeqWords];
   uint32_t nm[kNWords];
   uint8_t tab[kTab];
+  uint16_t wc[(MAXLEN / 2 + 31) / 32 * 32];  // window codes of the current k (compact path only)
 };
 
 // decode (kmer.decode with alphabet "CATG") + reduce_repeat (utils.nim:220-233,271), one 8-byte store
@@ -282,13 +283,9 @@ __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *_
 constexpr int kLaneThreads = 128;
 constexpr int kLaneWords = 11;         // ten words hold 160 bases; one more absorbs the re-alignment shift
 constexpr int kLaneClasses = 70;       // min-rotation classes of 4-mers (24 for 3-mers, 10 for 2-mers)
-constexpr int kLaneTabWords = kLaneClasses * kLaneThreads;
-constexpr int kLaneRdWords = kLaneWords * kLaneThreads;
 constexpr int kLutEntries = 16 + 64 + 256;       // class byte-offset LUTs for k = 2, 3, 4
 constexpr int kRevEntries = 10 + 24 + 70;        // class -> canonical code
-constexpr int kQueueWords = 4 * kLaneThreads;
-constexpr int kLaneSmemBytes = (kLaneTabWords + kLaneRdWords + kQueueWords + 4) * 4 + (kLutEntries + kRevEntries) * 2 + 16;
-static_assert(sizeof(WarpScratch<512>) * (kLaneThreads / 32) <= (size_t)kLaneTabWords * 4, "warp scratch must fit in the counter region");
+constexpr int kLaneSmemBytes = (kLaneThreads / 32) * (kLaneClasses * 32 + kLaneWords * 32) * 4 + (kLutEntries + kRevEntries) * 2 + 16;
 
 template <int K> struct LaneK;
 template <> struct LaneK<2> { static constexpr int wpw = 8, bits = 32, classes = 10, lut = 0, rev = 0; };
@@ -302,9 +299,9 @@ __device__ __forceinline__ uint32_t lane_word(const uint32_t *rd, int wi) {
   if (K == 3) {
     const int bit = 30 * wi;
     const int a = bit >> 5;
-    return __funnelshift_l(rd[(a + 1) * kLaneThreads], rd[a * kLaneThreads], bit & 31) >> 2;
+    return __funnelshift_l(rd[(a + 1) * 32], rd[a * 32], bit & 31) >> 2;
   }
-  return rd[wi * kLaneThreads];
+  return rd[wi * 32];
 }
 
 template <int K>
@@ -316,7 +313,7 @@ __device__ __forceinline__ void lane_count(const uint32_t *rd, uint32_t *tab, co
   const int nfull = W / P::wpw;
   const int rem = W - nfull * P::wpw;
 #pragma unroll
-  for (int c = 0; c < P::classes; c++) tab[c * kLaneThreads] = 0;
+  for (int c = 0; c < P::classes; c++) tab[c * 32] = 0;
   M = 0;
   uint32_t lead_off = 0xffffffffu;
   const uint16_t *l = lut + P::lut;
@@ -343,22 +340,25 @@ __device__ __forceinline__ void lane_count(const uint32_t *rd, uint32_t *tab, co
       if (cnt > M) { M = cnt; lead_off = off; }
     }
   }
-  leader = (lead_off == 0xffffffffu) ? kMask : (uint32_t)rev[P::rev + lead_off / (4 * kLaneThreads)];
+  leader = (lead_off == 0xffffffffu) ? kMask : (uint32_t)rev[P::rev + lead_off / 128u];
 }
 
-// read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254)
-template <int K>
-__device__ __forceinline__ int lane_recount(const uint32_t *rd, int L, uint32_t pat) {
+// read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254).
+// One copy for all k (kept out of line: instruction-cache footprint matters more than the call).
+__device__ __noinline__ int lane_recount(const uint32_t *rd, int L, uint32_t pat, int K) {
   const int npos = L - K + 1;
   if (npos <= 0) return 0;
   constexpr uint32_t kLow = 0x55555555u;
   uint32_t w[11], m[10];
 #pragma unroll
-  for (int i = 0; i < 10; i++) w[i] = rd[i * kLaneThreads];
+  for (int i = 0; i < 10; i++) w[i] = rd[i * 32];
   w[10] = 0;
 #pragma unroll
-  for (int i = 0; i < 10; i++) m[i] = kLow;
-#pragma unroll
+  for (int i = 0; i < 10; i++) {  // keep positions < npos (position p of word i sits at bit 30 - 2p)
+    const int n = npos - 16 * i;
+    m[i] = n >= 16 ? kLow : (n <= 0 ? 0u : (kLow & ~((1u << (32 - 2 * n)) - 1u)));
+  }
+#pragma unroll 1
   for (int j = 0; j < K; j++) {
     const uint32_t rep = ((pat >> (2 * (K - 1 - j))) & 3u) * kLow;
     uint32_t e[11];
@@ -368,17 +368,10 @@ __device__ __forceinline__ int lane_recount(const uint32_t *rd, int L, uint32_t 
       e[i] = ~(t | (t >> 1)) & kLow;          // slot LSB set <=> that base equals pattern base j
     }
 #pragma unroll
-    for (int i = 0; i < 10; i++) m[i] &= (j == 0) ? e[i] : __funnelshift_l(e[i + 1], e[i], 2 * j);
+    for (int i = 0; i < 10; i++) m[i] &= __funnelshift_l(e[i + 1], e[i], 2 * j);
   }
-  // keep positions < npos (position p of word i sits at bit 30 - 2p)
   uint32_t conflict = 0;
-#pragma unroll
-  for (int i = 0; i < 10; i++) {
-    const int n = npos - 16 * i;
-    const uint32_t vm = n >= 16 ? kLow : (n <= 0 ? 0u : (kLow & ~((1u << (32 - 2 * n)) - 1u)));
-    m[i] &= vm;
-  }
-#pragma unroll
+#pragma unroll 1
   for (int d = 1; d < K; d++) {
 #pragma unroll
     for (int i = 0; i < 10; i++) conflict |= m[i] & __funnelshift_l(i < 9 ? m[i + 1] : 0u, m[i], 2 * d);
@@ -419,7 +412,7 @@ __device__ __forceinline__ bool lane_step(const uint32_t *rd, uint32_t *tab, con
   lane_count<K>(rd, tab, lut, rev, L, M, leader);
   int score = M * K;
   if (score <= st.best) return !(M < thr_giveup);
-  const int c = lane_recount<K>(rd, L, leader);
+  const int c = lane_recount(rd, L, leader, K);
   score = c * K;
   if (score < st.best) return true;
   st.best = score;
@@ -431,26 +424,159 @@ __device__ __forceinline__ bool lane_step(const uint32_t *rd, uint32_t *tab, con
   return true;
 }
 
+// Compact warp-per-segment path (runtime k, rolled loops) for the few segments the lane path hands off: same
+// arithmetic as count_k / recount_k / ladder_step above, written for code size instead of speed.
+__device__ __noinline__ void warp_scan_compact(WarpScratch<512> &ws, const uint32_t *__restrict__ seq,
+                                               const uint32_t *__restrict__ nmask, const strgpu_segment sg, uint32_t s,
+                                               const uint16_t *__restrict__ thr, int lane, int start_k, ScanState st,
+                                               strgpu_repeat *__restrict__ out, int *status) {
+  const int L = sg.len;
+  if (L > STRGPU_MAX_SEGMENT_LEN) {
+    if (lane == 0) {
+      atomicExch(status, (int)STRGPU_ERR_TOO_LONG);
+      emit_result(out, s, ScanState{-1, 0u, 0, 0});
+    }
+    return;
+  }
+  const int n_words = (2 * L + 31) >> 5;
+  __syncwarp();
+  for (int l = lane; l < n_words + 1; l += 32) {
+    uint32_t v = 0;
+    if (l < n_words) {
+      const uint32_t g = (sg.base_off >> 4) + (uint32_t)l;
+      v = __funnelshift_l(__byte_perm(seq[g + 1], 0, 0x0123), __byte_perm(seq[g], 0, 0x0123), 2u * (sg.base_off & 15u));
+    }
+    ws.sw[l] = v;
+  }
+  const bool has_n = (sg.flags & STRGPU_SEG_HAS_N) != 0;
+  int n_count = 0;
+  if (has_n) {
+    const int n_nw = (L + 31) >> 5;
+    for (int l = lane; l < n_nw + 1; l += 32) {
+      uint32_t v = 0;
+      if (l < n_nw) {
+        const uint32_t g = (sg.base_off >> 5) + (uint32_t)l;
+        v = __funnelshift_r(nmask[g], nmask[g + 1], sg.base_off & 31u);
+        const int rem = L - 32 * l;
+        if (rem < 32) v &= (1u << rem) - 1u;
+      }
+      ws.nm[l] = v;
+      n_count += __popc(v);
+    }
+    n_count = __reduce_add_sync(kFull, n_count);
+  }
+  __syncwarp();
+  if (n_count <= 20) {
+    const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+    const uint32_t lane_le = kFull >> (31 - lane);
+#pragma unroll 1
+    for (int K = start_k; K <= 6; K++) {
+      const uint32_t kmask = (1u << (2 * K)) - 1u;
+      const int W = L / K;
+      const int rounds = (W + 31) >> 5;
+      int M = 0;
+      uint32_t leader = kmask;
+#pragma unroll 1
+      for (int r = 0; r < rounds; r++) {
+        const int w = 32 * r + lane;
+        const bool valid = w < W;
+        const uint32_t bit = valid ? 2u * (uint32_t)(K * w) : 0u;
+        uint32_t x = __funnelshift_l(ws.sw[(bit >> 5) + 1], ws.sw[bit >> 5], bit & 31u) >> (32 - 2 * K);
+        uint32_t c = x;
+#pragma unroll 1
+        for (int j = 1; j < K; j++) {
+          x = ((x << 2) | (x >> (2 * K - 2))) & kmask;
+          c = min(c, x);
+        }
+        ws.wc[32 * r + lane] = valid ? (uint16_t)c : (uint16_t)0xffffu;
+        const uint32_t grp = __match_any_sync(kFull, valid ? c : (0x80000000u | (uint32_t)lane));
+        int base = 0;
+        if (rounds > 1) {
+          if (valid) base = ws.tab[c];
+          __syncwarp();
+          if (valid && lane == 31 - __clz(grp)) ws.tab[c] = (uint8_t)(base + __popc(grp));
+          __syncwarp();
+        }
+        const int occ = valid ? base + __popc(grp & lane_le) : 0;
+        const int rmax = __reduce_max_sync(kFull, occ);
+        if (rmax > M) {
+          M = rmax;
+          const uint32_t b = __ballot_sync(kFull, valid && occ == rmax);
+          leader = __shfl_sync(kFull, c, __ffs(b) - 1);
+        }
+      }
+      if (rounds > 1) {
+#pragma unroll 1
+        for (int r = 0; r < rounds; r++) {
+          const uint32_t c = ws.wc[32 * r + lane];
+          if (c != 0xffffu) ws.tab[c] = 0;
+        }
+        __syncwarp();
+      }
+      const int thr_p = thr[(size_t)(pclass * 5 + K - 2) * kThrLen + L];
+      const int thr_giveup = thr[(size_t)(STRGPU_MAX_PCLASS * 5 + K - 2) * kThrLen + L];
+      int score = M * K;
+      if (score <= st.best) {
+        if (M < thr_giveup) break;
+        continue;
+      }
+      // recount
+      const int npos = L - K + 1;
+      int cnt = 0, next = 0;
+#pragma unroll 1
+      for (int r = 0; 32 * r < npos; r++) {
+        const int i = 32 * r + lane;
+        const bool valid = i < npos;
+        const uint32_t bit = valid ? 2u * (uint32_t)i : 0u;
+        const uint32_t x = __funnelshift_l(ws.sw[(bit >> 5) + 1], ws.sw[bit >> 5], bit & 31u) >> (32 - 2 * K);
+        bool eq = valid && x == leader;
+        if (has_n) eq = eq && ((__funnelshift_r(ws.nm[r], ws.nm[r + 1], lane) & ((1u << K) - 1u)) == 0u);
+        uint32_t m = __ballot_sync(kFull, eq);
+        const int rel = next - 32 * r;
+        if (rel > 0) m = (rel >= 32) ? 0u : (m & (kFull << rel));
+        while (m) {
+          const int nx = __ffs(m) - 1 + K;
+          cnt++;
+          m = (nx >= 32) ? 0u : (m & (kFull << nx));
+          next = 32 * r + nx;
+        }
+      }
+      score = cnt * K;
+      if (score < st.best) continue;
+      st.best = score;
+      if (cnt > thr_p) {
+        st.unit_code = leader;
+        st.unit_k = K;
+        st.rc = cnt;
+      }
+    }
+  }
+  if (lane == 0) emit_result(out, s, st);
+}
+
+constexpr int kLaneWarps = kLaneThreads / 32;
+constexpr int kWarpTabWords = kLaneClasses * 32;
+constexpr int kWarpRdWords = kLaneWords * 32;
+static_assert(sizeof(WarpScratch<512>) <= (size_t)kWarpTabWords * 4, "warp scratch must fit in the warp's counter region");
+
+// Every warp works on its own groups of 32 segments with its own shared-memory region: no block-level barrier.
 __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                  const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                  const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
                                                                  strgpu_repeat *__restrict__ out, int *status) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t *tab_all = smem;                               // [class][thread] counters; warp scratch in the queue phase
-  uint32_t *rd_all = tab_all + kLaneTabWords;             // [word][thread] read columns
-  uint32_t *queue = rd_all + kLaneRdWords;                // {segment, best, unit_code | unit_k << 24, rc | start_k << 16}
-  uint32_t *qcount = queue + kQueueWords;
-  uint16_t *lut = reinterpret_cast<uint16_t *>(qcount + 4);
-  uint16_t *rev = lut + kLutEntries;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kLaneWarps * (kWarpTabWords + kWarpRdWords));
+  uint16_t *rev = lut + kLutEntries;
   for (int i = tid; i < kLutEntries + kRevEntries; i += kLaneThreads) lut[i] = luts[i];
-  uint32_t *tab = tab_all + tid;
-  uint32_t *rd = rd_all + tid;
-  const uint32_t n_tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    if (tid == 0) *qcount = 0;
-    __syncthreads();
-    const uint32_t s = tile * kLaneThreads + tid;
+  __syncthreads();
+  uint32_t *tab_warp = smem + warp * (kWarpTabWords + kWarpRdWords);   // [class][lane] counters; warp scratch for hand-offs
+  uint32_t *tab = tab_warp + lane;
+  uint32_t *rd = tab_warp + kWarpTabWords + lane;                        // [word][lane] read columns
+  const uint32_t n_groups = (n_seg + 31) / 32;
+  const uint32_t warps_total = gridDim.x * kLaneWarps;
+  for (uint32_t grp = blockIdx.x * kLaneWarps + warp; grp < n_groups; grp += warps_total) {
+    const uint32_t s = grp * 32 + lane;
     const bool active = s < n_seg;
     strgpu_segment sg{0, 0, 0, 0};
     if (active) sg = segs[s];
@@ -458,6 +584,7 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
     const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
     ScanState st{-1, 0u, 0, 0};
     int handoff_k = (active && !lane_path) ? 2 : 0;       // 0: finished here
+    __syncwarp();
     if (lane_path) {
       // ---- stage: eleven words, re-aligned so that base 0 sits at bit 31 of word 0
       const uint32_t g = sg.base_off >> 4;
@@ -467,7 +594,7 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
 #pragma unroll
       for (int j = 0; j < kLaneWords + 1; j++) raw[j] = (j <= n_words) ? __byte_perm(seq[g + j], 0, 0x0123) : 0u;
 #pragma unroll
-      for (int j = 0; j < kLaneWords; j++) rd[j * kLaneThreads] = __funnelshift_l(raw[j + 1], raw[j], sh);
+      for (int j = 0; j < kLaneWords; j++) rd[j * 32] = __funnelshift_l(raw[j + 1], raw[j], sh);
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
       const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
       const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen + L;
@@ -477,31 +604,30 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
       if (go) handoff_k = 5;
       else emit_result(out, s, st);
     }
-    if (handoff_k) {
-      const uint32_t q = atomicAdd(qcount, 1u);
-      queue[4 * q + 0] = s;
-      queue[4 * q + 1] = (uint32_t)st.best;
-      queue[4 * q + 2] = st.unit_code | ((uint32_t)st.unit_k << 24);
-      queue[4 * q + 3] = (uint32_t)st.rc | ((uint32_t)handoff_k << 16);
-    }
-    __syncthreads();
-    const uint32_t nq = *qcount;
-    if (nq) {  // CTA-uniform: finish the queued segments warp-per-segment; the counter region becomes warp scratch
-      WarpScratch<512> &ws = reinterpret_cast<WarpScratch<512> *>(tab_all)[warp];
+    __syncwarp();
+    uint32_t pending = __ballot_sync(kFull, handoff_k != 0);
+    if (pending) {  // warp-uniform: finish the handed-off segments one at a time on the whole warp
+      WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(tab_warp);
       for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
       __syncwarp();
-      for (uint32_t e = warp; e < nq; e += kLaneThreads / 32) {
-        const uint32_t qs = queue[4 * e + 0];
+      while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
         ScanState qst;
-        qst.best = (int)queue[4 * e + 1];
-        qst.unit_code = queue[4 * e + 2] & 0xffffffu;
-        qst.unit_k = (int)(queue[4 * e + 2] >> 24);
-        qst.rc = (int)(queue[4 * e + 3] & 0xffffu);
-        const int start_k = (int)(queue[4 * e + 3] >> 16);
-        warp_scan_segment<512>(ws, seq, nmask, segs[qs], qs, thr, lane, start_k, qst, out, status);
+        qst.best = __shfl_sync(kFull, st.best, src);
+        qst.unit_code = __shfl_sync(kFull, st.unit_code, src);
+        qst.unit_k = __shfl_sync(kFull, st.unit_k, src);
+        qst.rc = __shfl_sync(kFull, st.rc, src);
+        const int start_k = __shfl_sync(kFull, handoff_k, src);
+        strgpu_segment qsg;
+        qsg.base_off = __shfl_sync(kFull, sg.base_off, src);
+        const uint32_t packed = __shfl_sync(kFull, (uint32_t)sg.len | ((uint32_t)sg.pclass << 16) | ((uint32_t)sg.flags << 24), src);
+        qsg.len = (uint16_t)(packed & 0xffffu);
+        qsg.pclass = (uint8_t)((packed >> 16) & 0xffu);
+        qsg.flags = (uint8_t)(packed >> 24);
+        warp_scan_compact(ws, seq, nmask, qsg, grp * 32 + (uint32_t)src, thr, lane, start_k, qst, out, status);
       }
     }
-    __syncthreads();
   }
 }
 
@@ -531,7 +657,7 @@ void build_lane_luts(uint16_t *dst) {
       }
       int cls = 0;
       while (dst[rev_off + cls] != (uint16_t)m) cls++;
-      dst[lut_off + code] = (uint16_t)(cls * 4 * kLaneThreads);
+      dst[lut_off + code] = (uint16_t)(cls * 4 * 32);
     }
     lut_off += n;
     rev_off += n_classes;
