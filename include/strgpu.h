@@ -165,6 +165,23 @@ typedef struct {
  * merge_mode == 0.  STRGPU_ERR_OVERFLOW if more than `cap` records were produced (*n_out = needed). */
 int strgpu_cluster(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,
                    strgpu_bounds *out, uint32_t cap, uint32_t *n_out);
+/* A locus from a `-l` bed or `-b` bounds file after parse_bedline / parse_boundsline (cluster.nim:111-163):
+ * the bucket key (tid, repeat) and the window [left_most, right_most] whose reads it takes. */
+typedef struct {
+  int32_t  tid;
+  uint32_t left_most;
+  uint32_t right_most;
+  char     repeat[6];
+  uint16_t n_left, n_right, n_total;   /* out: the counts assign_reads_locus writes into the Bounds (callclusters.nim:41-50) */
+} strgpu_locus;              /* 24 bytes */
+
+/* strgpu_cluster preceded by assign_reads_locus (callclusters.nim:14-50) for every locus in array order, as
+ * merge.nim:166-168 and call.nim:189-218 do before clustering: each locus takes the not-yet-taken reads of its
+ * bucket with left_most-1 <= position <= right_most, and -- like the reference (callclusters.nim:35-36) -- the
+ * first remaining read after that window is dropped as well.  loci[i].n_left/n_right/n_total are filled in. */
+int strgpu_cluster_loci(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,
+                        strgpu_locus *loci, uint32_t n_loci, strgpu_bounds *out, uint32_t cap, uint32_t *n_out);
+
 /* Device-resident variant: d_treads / d_out are device pointers, *d_n_out a device uint32; enqueued on
  * `cuda_stream` after an internal key-range probe (one small synchronising copy).  d_out needs room for
  * `cap` records; records past cap are dropped and counted in *d_n_out. */

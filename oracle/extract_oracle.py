@@ -260,8 +260,32 @@ def bounds_line(b, targets) -> str:  # cluster.nim:262-266 (name is empty for di
 BOUNDS_HEADER = "#chrom\tleft\tright\trepeat\tname\tleft_most\tright_most\tcenter_mass\tn_left\tn_right\tn_total"
 
 
-def merge(bins, window=-1, min_support=5, min_clip=0, min_clip_total=0):
-    """merge_main without -l / --chromosome (merge.nim:91-187) -> sorted list of bounds lines."""
+def parse_bed_loci(bed_lines, targets, window):
+    """parse_bed (cluster.nim:111-141) -> (LOCUS_DTYPE array, [(left, right, unit, name)])."""
+    names = [t[0] for t in targets]
+    loci = np.zeros(len(bed_lines), dtype=orc.LOCUS_DTYPE)
+    meta = []
+    for i, l in enumerate(bed_lines):
+        f = l.split()
+        assert len(f) in (4, 5)
+        tid = names.index(f[0])
+        left, right = int(f[1]), int(f[2])
+        loci[i]["tid"] = tid
+        loci[i]["repeat"] = f[3].encode()
+        loci[i]["left_most"] = max(left - window, 0)
+        loci[i]["right_most"] = min(right + window, targets[tid][1])
+        meta.append((left, right, f[3], f[4] if len(f) == 5 else ""))
+    return loci, meta
+
+
+def locus_line(locus, meta, targets) -> str:
+    left, right, unit, name = meta
+    return (f"{targets[int(locus['tid'])][0]}\t{left}\t{right}\t{unit}\t{name}\t{locus['left_most']}\t{locus['right_most']}\t0\t"
+            f"{locus['n_left']}\t{locus['n_right']}\t{locus['n_total']}")
+
+
+def merge(bins, window=-1, min_support=5, min_clip=0, min_clip_total=0, bed_lines=None):
+    """merge_main without --chromosome (merge.nim:91-187) -> list of bounds lines (loci first, as merge.nim:166-168)."""
     frag = np.zeros(4096, dtype=np.uint64)
     parts = []
     targets = None
@@ -279,6 +303,10 @@ def merge(bins, window=-1, min_support=5, min_clip=0, min_clip_total=0):
     if window < 0:
         window = orc.median(frag, 0.98)
     mcd = int(0.5 * float(orc.median(frag, 0.5))) & 0xFFFF
+    if bed_lines:
+        loci, meta = parse_bed_loci(bed_lines, targets, window)
+        loci, b, _ = orc.cluster_all_loci(treads, loci, window, min_support, min_clip, min_clip_total, mcd, merge_mode=True)
+        return [locus_line(l, m, targets) for l, m in zip(loci, meta)] + [bounds_line(x, targets) for x in b], targets
     b, _ = orc.cluster_all(treads, window, min_support, min_clip, min_clip_total, mcd, merge_mode=True)
     return [bounds_line(x, targets) for x in b], targets
 

@@ -28,6 +28,10 @@ BOUNDS_DTYPE = np.dtype(
 )
 assert BOUNDS_DTYPE.itemsize == 44
 
+LOCUS_DTYPE = np.dtype([("tid", "<i4"), ("left_most", "<u4"), ("right_most", "<u4"), ("repeat", "S6"),
+                        ("n_left", "<u2"), ("n_right", "<u2"), ("n_total", "<u2")])
+assert LOCUS_DTYPE.itemsize == 24
+
 LEFT, RIGHT, BOTH, NONE, NONE_RIGHT, NONE_LEFT = range(6)
 SOFT_NAMES = ["left", "right", "both", "none", "none_right", "none_left"]
 
@@ -77,6 +81,9 @@ def lib():
         L.orc_cluster_all.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_uint16, C.c_uint16, C.c_uint16, C.c_int,
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_cluster_all.restype = C.c_int
+        L.orc_cluster_all_loci.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_uint16, C.c_uint16, C.c_uint16,
+                                           C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.orc_cluster_all_loci.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -201,3 +208,21 @@ def cluster_all(treads: np.ndarray, window: int, min_support: int, min_clip: int
     assert nb >= 0
     unplaced = {bytes(uu[i]).rstrip(b"\0"): int(uc[i]) for i in range(nu.value)}
     return out[:nb].copy(), unplaced
+
+
+def cluster_all_loci(treads: np.ndarray, loci: np.ndarray, window: int, min_support: int, min_clip: int = 0, min_clip_total: int = 0,
+                     max_clip_dist: int = 200, merge_mode: bool = False):
+    """assign_reads_locus for every locus (file order) then the cluster loop.  Returns (loci with counts, bounds, unplaced)."""
+    treads = np.ascontiguousarray(treads, dtype=TREAD_DTYPE)
+    loci = np.ascontiguousarray(loci, dtype=LOCUS_DTYPE).copy()
+    n = len(treads)
+    out = np.zeros(max(n, 1), dtype=BOUNDS_DTYPE)
+    uu = np.zeros(max(n, 1), dtype="S6")
+    uc = np.zeros(max(n, 1), dtype=np.int32)
+    nu = C.c_int(0)
+    nb = lib().orc_cluster_all_loci(treads.ctypes.data, n, loci.ctypes.data, len(loci), window, min_support, min_clip, min_clip_total,
+                                    max_clip_dist, int(merge_mode), out.ctypes.data, len(out), uu.ctypes.data, uc.ctypes.data, len(uu),
+                                    C.byref(nu))
+    assert nb >= 0
+    unplaced = {bytes(uu[i]).rstrip(b"\0"): int(uc[i]) for i in range(nu.value)}
+    return loci, out[:nb].copy(), unplaced

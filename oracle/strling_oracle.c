@@ -480,6 +480,70 @@ static int has_per_sample_reads(const orc_tread *reads, int n, int supporting) {
   return best >= supporting;
 }
 
+/* callclusters.nim:14-50 on one bucket held as a growable array (literal: slices and re-concatenation) */
+static void assign_reads_locus(orc_locus *locus, orc_tread *trs, int *len) {
+  int n = *len;
+  uint32_t left_most = locus->left_most == 0 ? 0u : locus->left_most - 1u;
+  int li = 0, ri = 0;
+  while (li < n && trs[li].position < left_most) li++;          /* lowerBound(trs, left_most) */
+  while (ri < n && trs[ri].position <= locus->right_most) ri++;  /* upperBound(trs, right_most) */
+  locus->n_total = 0; locus->n_left = 0; locus->n_right = 0;
+  if (n > 0) {
+    for (int i = li; i < ri; i++) {                              /* result = trs[li..<ri] */
+      locus->n_total++;
+      if (trs[i].split == ORC_RIGHT) locus->n_right++;
+      else if (trs[i].split == ORC_LEFT) locus->n_left++;
+    }
+    int m = li < n ? li : n;                                     /* trs[0..<li] */
+    if (ri < n - 1) {                                            /* if ri < trs.high: add trs[ri+1..high] */
+      for (int i = ri + 1; i < n; i++) trs[m++] = trs[i];
+    }
+    if (ri < li) m = n;  /* empty slice with ri < li cannot happen for left_most <= right_most; keep all if it did */
+    *len = m;
+  }
+}
+
+int orc_cluster_all_loci(const orc_tread *treads, int n, orc_locus *loci, int n_loci, uint32_t window, int min_support,
+                         uint16_t min_clip, uint16_t min_clip_total, uint16_t max_clip_dist, int merge_mode,
+                         orc_bounds *out, int cap_bounds,
+                         char *unplaced_unit, int32_t *unplaced_count, int cap_unplaced, int *n_unplaced) {
+  if (n_unplaced) *n_unplaced = 0;
+  for (int j = 0; j < n_loci; j++) { loci[j].n_left = loci[j].n_right = loci[j].n_total = 0; }
+  if (n <= 0) return 0;
+  sort_rec *recs = (sort_rec *)malloc((size_t)n * sizeof(sort_rec));
+  orc_tread *sorted = (orc_tread *)malloc((size_t)n * sizeof(orc_tread));
+  for (int i = 0; i < n; i++) { recs[i].t = treads[i]; recs[i].idx = (uint32_t)i; }
+  qsort(recs, (size_t)n, sizeof(sort_rec), cmp_rec);
+  for (int i = 0; i < n; i++) sorted[i] = recs[i].t;
+  free(recs);
+  /* bucket table: start / length of every (tid, repeat) run; loci edit their bucket in place */
+  int nbk = 0;
+  int *bs = (int *)malloc((size_t)n * sizeof(int)), *bl = (int *)malloc((size_t)n * sizeof(int));
+  for (int s0 = 0; s0 < n;) {
+    int e = s0 + 1;
+    while (e < n && sorted[e].tid == sorted[s0].tid && memcmp(sorted[e].repeat, sorted[s0].repeat, 6) == 0) e++;
+    bs[nbk] = s0; bl[nbk] = e - s0; nbk++;
+    s0 = e;
+  }
+  for (int j = 0; j < n_loci; j++) {
+    for (int b = 0; b < nbk; b++) {
+      if (sorted[bs[b]].tid == loci[j].tid && memcmp(sorted[bs[b]].repeat, loci[j].repeat, 6) == 0 && bl[b] > 0) {
+        assign_reads_locus(&loci[j], sorted + bs[b], &bl[b]);
+        break;
+      }
+    }
+  }
+  /* compact the surviving reads (bucket order is unchanged) and cluster them */
+  orc_tread *kept = (orc_tread *)malloc((size_t)n * sizeof(orc_tread));
+  int nk = 0;
+  for (int b = 0; b < nbk; b++) for (int i = 0; i < bl[b]; i++) kept[nk++] = sorted[bs[b] + i];
+  free(bs); free(bl); free(sorted);
+  int r = orc_cluster_all(kept, nk, window, min_support, min_clip, min_clip_total, max_clip_dist, merge_mode, out, cap_bounds,
+                          unplaced_unit, unplaced_count, cap_unplaced, n_unplaced);
+  free(kept);
+  return r;
+}
+
 int orc_cluster_all(const orc_tread *treads, int n, uint32_t window, int min_support,
                     uint16_t min_clip, uint16_t min_clip_total, uint16_t max_clip_dist, int merge_mode,
                     orc_bounds *out, int cap_bounds,

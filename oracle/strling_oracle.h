@@ -116,6 +116,23 @@ int  orc_cluster_all(const orc_tread *treads, int n, uint32_t window, int min_su
                      char *unplaced_unit /* cap_unplaced*6 */, int32_t *unplaced_count, int cap_unplaced,
                      int *n_unplaced);
 
+/* A locus from a `-l` bed / `-b` bounds file after parse_bedline (cluster.nim:111-134): key + the window to collect. */
+typedef struct {
+  int32_t  tid;
+  uint32_t left_most;
+  uint32_t right_most;
+  char     repeat[6];
+  uint16_t n_left, n_right, n_total;   /* outputs of assign_reads_locus (callclusters.nim:41-50) */
+} orc_locus;             /* 24 bytes */
+
+/* orc_cluster_all preceded by assign_reads_locus (callclusters.nim:14-50) for every locus in file order, as
+ * merge.nim:166-168 / call.nim:189-218 do: the reads a locus takes (and the one extra read the reference drops,
+ * callclusters.nim:35-36) leave their bucket before clustering.  loci[i].n_* are filled in. */
+int  orc_cluster_all_loci(const orc_tread *treads, int n, orc_locus *loci, int n_loci, uint32_t window, int min_support,
+                          uint16_t min_clip, uint16_t min_clip_total, uint16_t max_clip_dist, int merge_mode,
+                          orc_bounds *out, int cap_bounds,
+                          char *unplaced_unit, int32_t *unplaced_count, int cap_unplaced, int *n_unplaced);
+
 #ifdef __cplusplus
 }
 #endif

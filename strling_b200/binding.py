@@ -22,12 +22,14 @@ BOUNDS_DTYPE = np.dtype(
      ("center_mass", "<u4"), ("n_left", "<u2"), ("n_right", "<u2"), ("n_total", "<u2"), ("repeat", "S6"),
      ("first_read", "<u4"), ("n_reads", "<u4"), ("reserved", "<u4")]
 )
+LOCUS_DTYPE = np.dtype([("tid", "<i4"), ("left_most", "<u4"), ("right_most", "<u4"), ("repeat", "S6"),
+                        ("n_left", "<u2"), ("n_right", "<u2"), ("n_total", "<u2")])
 CLUSTER_PARAMS_DTYPE = np.dtype(
     [("window", "<u4"), ("min_support", "<i4"), ("min_clip", "<u2"), ("min_clip_total", "<u2"),
      ("max_clip_dist", "<u2"), ("merge_mode", "<u2")]
 )
 assert SEGMENT_DTYPE.itemsize == 8 and REPEAT_DTYPE.itemsize == 8
-assert TREAD_DTYPE.itemsize == 24 and BOUNDS_DTYPE.itemsize == 48 and CLUSTER_PARAMS_DTYPE.itemsize == 16
+assert TREAD_DTYPE.itemsize == 24 and BOUNDS_DTYPE.itemsize == 48 and CLUSTER_PARAMS_DTYPE.itemsize == 16 and LOCUS_DTYPE.itemsize == 24
 SEG_HAS_N = 1
 MAX_SEGMENT_LEN = 510
 
@@ -76,6 +78,7 @@ def load_library():
     L.strgpu_scan_device.argtypes = [vp, vp, vp, vp, u32, u32, vp, vp]
     L.strgpu_device_status.argtypes = [vp, vp]
     L.strgpu_cluster.argtypes = [vp, vp, u32, vp, vp, u32, C.POINTER(u32)]
+    L.strgpu_cluster_loci.argtypes = [vp, vp, u32, vp, vp, u32, vp, u32, C.POINTER(u32)]
     L.strgpu_cluster_device.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp]
     _lib = L
     return L
@@ -211,6 +214,22 @@ class StrGpu:
         out = out[: n_out.value]
         unplaced = {bytes(r["repeat"]).rstrip(b"\0"): int(r["n_reads"]) for r in out[out["tid"] < 0]}
         return out[out["tid"] >= 0].copy(), unplaced
+
+    def cluster_loci(self, treads: np.ndarray, loci: np.ndarray, window: int, min_support: int, min_clip: int = 0,
+                     min_clip_total: int = 0, max_clip_dist: int = 200, merge_mode: bool = False):
+        """assign_reads_locus (callclusters.nim:14) for every locus in order, then the cluster loop.
+        Returns (loci with n_left/n_right/n_total filled in, bounds, unplaced)."""
+        treads = np.ascontiguousarray(treads, dtype=TREAD_DTYPE)
+        loci = np.ascontiguousarray(loci, dtype=LOCUS_DTYPE).copy()
+        p = self.cluster_params(window, min_support, min_clip, min_clip_total, max_clip_dist, merge_mode)
+        cap = max(16, len(treads))
+        out = np.zeros(cap, dtype=BOUNDS_DTYPE)
+        n_out = C.c_uint32(0)
+        self._check(self.L.strgpu_cluster_loci(self.h, treads.ctypes.data, len(treads), p.ctypes.data, loci.ctypes.data, len(loci),
+                                               out.ctypes.data, cap, C.byref(n_out)))
+        out = out[: n_out.value]
+        unplaced = {bytes(r["repeat"]).rstrip(b"\0"): int(r["n_reads"]) for r in out[out["tid"] < 0]}
+        return loci, out[out["tid"] >= 0].copy(), unplaced
 
     def cluster_device(self, d_treads: int, n: int, params: np.ndarray, d_out: int, cap: int, d_n_out: int, stream: int = 0):
         self._check(self.L.strgpu_cluster_device(self.h, d_treads, n, params.ctypes.data, d_out, cap, d_n_out, stream or None))

@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <numeric>
+#include <vector>
 
 #include "cluster_kernels.cuh"
 #include "scan_kernels.cuh"
@@ -18,6 +21,7 @@ static_assert(sizeof(strgpu_repeat) == 8, "strgpu_repeat layout");
 static_assert(sizeof(strgpu_tread) == 24, "strgpu_tread layout");
 static_assert(sizeof(strgpu_bounds) == 48, "strgpu_bounds layout");
 static_assert(sizeof(strgpu_cluster_params) == 16, "strgpu_cluster_params layout");
+static_assert(sizeof(strgpu_locus) == 24, "strgpu_locus layout");
 
 namespace {
 
@@ -50,7 +54,7 @@ struct strgpu_ctx {
   int *d_status_dev = nullptr;  // sticky status for strgpu_scan_device launches
   strgpu::ClusterWorkspace cluster_ws;
   cudaStream_t cluster_stream = nullptr;
-  DevBuf cl_in, cl_out;
+  DevBuf cl_in, cl_out, cl_loci;
   uint32_t *d_cl_n = nullptr;
   uint64_t launches = 0;
   char err[512] = {0};
@@ -157,6 +161,7 @@ void strgpu_destroy(strgpu_ctx *ctx) {
   strgpu::free_workspace(ctx->cluster_ws);
   if (ctx->cl_in.p) cudaFree(ctx->cl_in.p);
   if (ctx->cl_out.p) cudaFree(ctx->cl_out.p);
+  if (ctx->cl_loci.p) cudaFree(ctx->cl_loci.p);
   if (ctx->d_cl_n) cudaFree(ctx->d_cl_n);
   if (ctx->cluster_stream) cudaStreamDestroy(ctx->cluster_stream);
   if (ctx->d_thr) cudaFree(ctx->d_thr);
@@ -311,7 +316,13 @@ int strgpu_cluster_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, con
 
 int strgpu_cluster(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,
                    strgpu_bounds *out, uint32_t cap, uint32_t *n_out) {
-  if (!ctx || !params || !n_out || (n && !treads) || (cap && !out)) return fail(ctx, STRGPU_ERR_INVALID, "cluster: null argument");
+  return strgpu_cluster_loci(ctx, treads, n, params, nullptr, 0, out, cap, n_out);
+}
+
+int strgpu_cluster_loci(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,
+                        strgpu_locus *loci, uint32_t n_loci, strgpu_bounds *out, uint32_t cap, uint32_t *n_out) {
+  if (!ctx || !params || !n_out || (n && !treads) || (cap && !out) || (n_loci && !loci))
+    return fail(ctx, STRGPU_ERR_INVALID, "cluster: null argument");
   *n_out = 0;
   CU(ctx, cudaSetDevice(ctx->device));
   int rc;
@@ -319,8 +330,56 @@ int strgpu_cluster(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, cons
   if ((rc = ensure(ctx, ctx->cl_out, (size_t)cap * sizeof(strgpu_bounds) + 16))) return rc;
   cudaStream_t st = ctx->cluster_stream;
   if (n) CU(ctx, cudaMemcpyAsync(ctx->cl_in.p, treads, (size_t)n * sizeof(strgpu_tread), cudaMemcpyHostToDevice, st));
+  strgpu::LociArgs la;
+  std::vector<strgpu::DevLocus> hl;
+  std::vector<uint32_t> chain_start;
+  if (n_loci) {
+    // group the loci by bucket key, keeping file order inside a bucket (the reference handles them sequentially)
+    std::vector<uint32_t> order(n_loci);
+    std::iota(order.begin(), order.end(), 0u);
+    hl.resize(n_loci);
+    std::vector<strgpu::DevLocus> key(n_loci);
+    for (uint32_t i = 0; i < n_loci; i++) {
+      key[i].hi = (uint32_t)loci[i].tid ^ 0x80000000u;
+      key[i].mid = strgpu::unit_rank_host(loci[i].repeat);
+      key[i].left_most = loci[i].left_most;
+      key[i].right_most = loci[i].right_most;
+      key[i].orig = i;
+      loci[i].n_left = loci[i].n_right = loci[i].n_total = 0;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      return key[a].hi != key[b].hi ? key[a].hi < key[b].hi : key[a].mid < key[b].mid;
+    });
+    for (uint32_t i = 0; i < n_loci; i++) {
+      hl[i] = key[order[i]];
+      if (i == 0 || hl[i].hi != hl[i - 1].hi || hl[i].mid != hl[i - 1].mid) chain_start.push_back(i);
+    }
+    chain_start.push_back(n_loci);
+    if ((rc = ensure(ctx, ctx->cl_loci, hl.size() * sizeof(strgpu::DevLocus) + chain_start.size() * 4 + (size_t)n_loci * 6 + 64))) return rc;
+    char *base = (char *)ctx->cl_loci.p;
+    const size_t off_chain = (hl.size() * sizeof(strgpu::DevLocus) + 15) & ~(size_t)15;
+    const size_t off_counts = (off_chain + chain_start.size() * 4 + 15) & ~(size_t)15;
+    CU(ctx, cudaMemcpyAsync(base, hl.data(), hl.size() * sizeof(strgpu::DevLocus), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(base + off_chain, chain_start.data(), chain_start.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemsetAsync(base + off_counts, 0, (size_t)n_loci * 6, st));
+    la.d_loci = (const strgpu::DevLocus *)base;
+    la.d_chain_start = (const uint32_t *)(base + off_chain);
+    la.n_chains = (uint32_t)chain_start.size() - 1;
+    la.d_counts = (uint16_t *)(base + off_counts);
+  }
+  if (n == 0 && n_loci == 0) return STRGPU_OK;
   CU(ctx, strgpu::run_cluster(ctx->cluster_ws, (const strgpu_tread *)ctx->cl_in.p, n, *params, (strgpu_bounds *)ctx->cl_out.p, cap,
-                              ctx->d_cl_n, st, &ctx->launches));
+                              ctx->d_cl_n, st, &ctx->launches, n_loci && n ? &la : nullptr));
+  if (n_loci && n) {
+    std::vector<uint16_t> counts((size_t)n_loci * 3);
+    CU(ctx, cudaMemcpyAsync(counts.data(), la.d_counts, counts.size() * 2, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n_loci; i++) {
+      loci[i].n_left = counts[3 * i];
+      loci[i].n_right = counts[3 * i + 1];
+      loci[i].n_total = counts[3 * i + 2];
+    }
+  }
   uint32_t produced = 0;
   CU(ctx, cudaMemcpyAsync(&produced, ctx->d_cl_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));

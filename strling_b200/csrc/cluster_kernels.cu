@@ -205,6 +205,74 @@ __global__ void gather_treads(const strgpu_tread *__restrict__ treads, const Sor
   dst[2] = src[2];
 }
 
+// ------------------------------------------------------------------------------------------- C10 assign_reads_locus
+// One thread per chain (= the loci of one bucket, in file order): callclusters.nim:14-50 on the sorted records with
+// removal expressed as marks.  Earlier loci change what later loci of the same bucket see, hence the serial chain.
+__global__ void assign_loci(const SortRec *__restrict__ recs, const strgpu_tread *__restrict__ sorted, uint32_t n,
+                            const DevLocus *__restrict__ loci, const uint32_t *__restrict__ chain_start, uint32_t n_chains,
+                            uint32_t *__restrict__ removed, uint16_t *__restrict__ counts) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  const DevLocus first = loci[chain_start[c]];
+  // bucket [bs, be): records whose (hi, mid) equals the key
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t m = lo + ((hi - lo) >> 1);
+    const SortRec r = recs[m];
+    if (r.hi < first.hi || (r.hi == first.hi && r.mid < first.mid)) lo = m + 1; else hi = m;
+  }
+  const uint32_t bs = lo;
+  hi = n;
+  while (lo < hi) {
+    const uint32_t m = lo + ((hi - lo) >> 1);
+    const SortRec r = recs[m];
+    if (r.hi == first.hi && r.mid == first.mid) lo = m + 1; else hi = m;
+  }
+  const uint32_t be = lo;
+  for (uint32_t j = chain_start[c]; j < chain_start[c + 1]; j++) {
+    const DevLocus L = loci[j];
+    uint16_t n_left = 0, n_right = 0, n_total = 0;
+    if (be > bs) {
+      const uint32_t lm1 = L.left_most == 0 ? 0u : L.left_most - 1u;
+      uint32_t a = bs, b = be;
+      while (a < b) { const uint32_t m = a + ((b - a) >> 1); if (recs[m].pos < lm1) a = m + 1; else b = m; }
+      const uint32_t li = a;
+      b = be;
+      while (a < b) { const uint32_t m = a + ((b - a) >> 1); if (recs[m].pos <= L.right_most) a = m + 1; else b = m; }
+      const uint32_t ri = a;
+      for (uint32_t i = li; i < ri; i++) {
+        if (removed[i]) continue;
+        removed[i] = 1;
+        n_total++;
+        const uint8_t sp = sorted[i].split;
+        if (sp == SOFT_RIGHT) n_right++; else if (sp == SOFT_LEFT) n_left++;
+      }
+      for (uint32_t i = ri; i < be; i++)  // the element at `ri` of the shrunken bucket is dropped too (callclusters.nim:35-36)
+        if (!removed[i]) { removed[i] = 1; break; }
+    }
+    counts[3 * L.orig + 0] = n_left;
+    counts[3 * L.orig + 1] = n_right;
+    counts[3 * L.orig + 2] = n_total;
+  }
+}
+
+__global__ void invert_flags(const uint32_t *__restrict__ removed, uint32_t n, uint32_t *__restrict__ keep) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = removed[i] ? 0u : 1u;
+}
+
+__global__ void compact_sorted(const SortRec *__restrict__ recs, const strgpu_tread *__restrict__ sorted, const uint32_t *__restrict__ keep,
+                               const uint32_t *__restrict__ dst, uint32_t n, SortRec *__restrict__ recs_out,
+                               strgpu_tread *__restrict__ sorted_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  const uint32_t d = dst[i];
+  recs_out[d] = recs[i];
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(sorted + i);
+  unsigned long long *o = reinterpret_cast<unsigned long long *>(sorted_out + d);
+  o[0] = src[0]; o[1] = src[1]; o[2] = src[2];
+}
+
 // ------------------------------------------------------------------------------------------- K3 chain
 __device__ __forceinline__ bool same_bucket(const SortRec &a, const SortRec &b) { return a.hi == b.hi && a.mid == b.mid; }
 
@@ -506,7 +574,7 @@ __global__ void compact_bounds(const strgpu_bounds *__restrict__ out2, const uin
 
 // ------------------------------------------------------------------------------------------- host driver
 enum { WS_RECS_A, WS_RECS_B, WS_COUNTS, WS_BLOCKSUMS, WS_SORTED, WS_NEXT, WS_BEND, WS_HEAD, WS_CID, WS_CLSTART, WS_CLEND,
-       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL };
+       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL, WS_SORTED_B };
 
 cudaError_t ws_ensure(ClusterWorkspace &ws, int which, size_t bytes) {
   if (bytes <= ws.cap[which]) return cudaSuccess;
@@ -540,8 +608,25 @@ cudaError_t exclusive_scan(ClusterWorkspace &ws, const uint32_t *in, uint32_t *o
 
 }  // namespace
 
+uint32_t unit_rank_host(const char repeat[6]) {
+  uint32_t m = 0;
+  for (int j = 0; j < 6; j++) {
+    uint32_t r;
+    switch (repeat[j]) {
+      case 0: r = 0; break;
+      case 'A': r = 1; break;
+      case 'C': r = 2; break;
+      case 'G': r = 3; break;
+      case 'T': r = 4; break;
+      default: r = 5;
+    }
+    m = (m << 3) | r;
+  }
+  return m;
+}
+
 void free_workspace(ClusterWorkspace &ws) {
-  for (int i = 0; i < 16; i++) {
+  for (int i = 0; i < 17; i++) {
     if (ws.buf[i]) cudaFree(ws.buf[i]);
     ws.buf[i] = nullptr;
     ws.cap[i] = 0;
@@ -549,7 +634,8 @@ void free_workspace(ClusterWorkspace &ws) {
 }
 
 cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
-                        strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t st, uint64_t *launches) {
+                        strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t st, uint64_t *launches,
+                        const LociArgs *loci) {
   if (n == 0) return cudaMemsetAsync(d_n_out, 0, 4, st);
   const int T = 256;
   const uint32_t nb = (n + T - 1) / T;
@@ -587,6 +673,32 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   gather_treads<<<nb, T, 0, st>>>(d_treads, ra, n, sorted);
   ++*launches;
 
+  // ---- C10: loci take their reads out of the sorted buckets before clustering
+  if (loci && loci->n_chains) {
+    CK(ws_ensure(ws, WS_HEAD, (size_t)n * 4));
+    CK(ws_ensure(ws, WS_NEXT, (size_t)n * 4));
+    CK(ws_ensure(ws, WS_CID, (size_t)n * 4));
+    CK(ws_ensure(ws, WS_SORTED_B, (size_t)n * sizeof(strgpu_tread)));
+    uint32_t *removed = (uint32_t *)ws.buf[WS_HEAD], *keep = (uint32_t *)ws.buf[WS_NEXT], *dst = (uint32_t *)ws.buf[WS_CID];
+    CK(cudaMemsetAsync(removed, 0, (size_t)n * 4, st));
+    assign_loci<<<(loci->n_chains + 63) / 64, 64, 0, st>>>(ra, sorted, n, loci->d_loci, loci->d_chain_start, loci->n_chains, removed,
+                                                            loci->d_counts);
+    invert_flags<<<nb, T, 0, st>>>(removed, n, keep);
+    *launches += 2;
+    CK(exclusive_scan(ws, keep, dst, n, d_small + 5, st, launches));
+    strgpu_tread *sorted_b = (strgpu_tread *)ws.buf[WS_SORTED_B];
+    compact_sorted<<<nb, T, 0, st>>>(ra, sorted, keep, dst, n, rb, sorted_b);
+    ++*launches;
+    uint32_t n_kept = 0;
+    CK(cudaMemcpyAsync(&n_kept, d_small + 5, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    SortRec *t = ra; ra = rb; rb = t;
+    sorted = sorted_b;
+    n = n_kept;
+    if (n == 0) return cudaMemsetAsync(d_n_out, 0, 4, st);
+  }
+  const uint32_t nb2 = (n + T - 1) / T;
+
   // ---- K3: next(i), bucket heads, cluster ids
   CK(ws_ensure(ws, WS_NEXT, (size_t)n * 4));
   CK(ws_ensure(ws, WS_BEND, (size_t)n * 4));
@@ -594,8 +706,8 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   CK(ws_ensure(ws, WS_CID, (size_t)n * 4));
   uint32_t *next = (uint32_t *)ws.buf[WS_NEXT], *bend = (uint32_t *)ws.buf[WS_BEND], *head = (uint32_t *)ws.buf[WS_HEAD],
            *cid = (uint32_t *)ws.buf[WS_CID];
-  cluster_next<<<nb, T, 0, st>>>(ra, n, p.window, next, bend, head);
-  cluster_heads<<<nb, T, 0, st>>>(ra, n, next, bend, head);
+  cluster_next<<<nb2, T, 0, st>>>(ra, n, p.window, next, bend, head);
+  cluster_heads<<<nb2, T, 0, st>>>(ra, n, next, bend, head);
   *launches += 2;
   CK(exclusive_scan(ws, head, cid, n, d_small + 3, st, launches));
   uint32_t n_clusters = 0;
@@ -605,7 +717,7 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   CK(ws_ensure(ws, WS_CLSTART, (size_t)n_clusters * 4));
   CK(ws_ensure(ws, WS_CLEND, (size_t)n_clusters * 4));
   uint32_t *cl_start = (uint32_t *)ws.buf[WS_CLSTART], *cl_end = (uint32_t *)ws.buf[WS_CLEND];
-  cluster_fill<<<nb, T, 0, st>>>(head, cid, next, n, cl_start, cl_end);
+  cluster_fill<<<nb2, T, 0, st>>>(head, cid, next, n, cl_start, cl_end);
   ++*launches;
 
   // ---- K4: bounds per cluster, then ordered compaction

@@ -16,15 +16,31 @@ struct SortRec {  // 16-byte radix-sort record: key fields + the tread's index i
 
 // Growable device workspace owned by the ctx; every pointer is device memory.
 struct ClusterWorkspace {
-  void *buf[16] = {nullptr};
-  size_t cap[16] = {0};
+  void *buf[17] = {nullptr};
+  size_t cap[17] = {0};
 };
+
+// Loci for assign_reads_locus, already grouped on the host: loci of one bucket are consecutive ("chain") and keep
+// their file order; chain_start has n_chains + 1 entries.
+struct DevLocus {
+  uint32_t hi, mid;              // bucket key in sort-record encoding
+  uint32_t left_most, right_most;
+  uint32_t orig;                 // index in the caller's array
+};
+struct LociArgs {
+  const DevLocus *d_loci = nullptr;
+  const uint32_t *d_chain_start = nullptr;
+  uint32_t n_chains = 0;
+  uint16_t *d_counts = nullptr;  // [orig][3] = n_left, n_right, n_total
+};
+uint32_t unit_rank_host(const char repeat[6]);
 
 // Runs the whole cluster path for n treads already in device memory.  Synchronises `stream` internally
 // (key-range probe, cluster count).  Returns cudaSuccess or the failing call's error; *launches is
 // incremented per kernel launch.  d_n_out receives the number of records produced (may exceed cap).
 cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
-                        strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t stream, uint64_t *launches);
+                        strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t stream, uint64_t *launches,
+                        const LociArgs *loci = nullptr);
 
 void free_workspace(ClusterWorkspace &ws);
 

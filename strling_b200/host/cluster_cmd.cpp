@@ -1,9 +1,11 @@
 // `strling merge` (merge.nim:47-187) and the cluster loop of `strling call` (call.nim:50-130,223-235,280-281), with
 // grouping, sorting, clustering and bounds on the GPU (strgpu_cluster).  Host work: `.bin` decoding, the fragment
 // distribution medians that parameterise the kernels, and writing `-bounds.txt` / `-unplaced.txt`.
+// `-l` / `-b` loci take their reads first (assign_reads_locus, callclusters.nim:14-50; also on the GPU).
 // Not part of this build: spanning reads + genotypes (collect.nim, genotyper.nim), so `call` writes no
 // `-genotype.txt` and its bounds lines lack the trailing median-depth column (call.nim:255).
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -80,17 +82,131 @@ std::string bounds_line(const strgpu_bounds &b, const std::vector<std::pair<std:
   return buf;
 }
 
-std::vector<strgpu_bounds> run_cluster(const std::vector<strgpu_tread> &treads, const strgpu_cluster_params &p, int device, bool verbose) {
+struct LocusLine {  // a Bounds read from a bed / bounds file (cluster.nim:111-163)
+  strgpu_locus key;
+  uint32_t left = 0, right = 0, center_mass = 0;
+  std::string repeat, name;
+};
+
+std::vector<std::string> split_ws(const std::string &l) {
+  std::vector<std::string> f;
+  size_t i = 0;
+  while (i < l.size()) {
+    while (i < l.size() && std::isspace((unsigned char)l[i])) i++;
+    size_t j = i;
+    while (j < l.size() && !std::isspace((unsigned char)l[j])) j++;
+    if (j > i) f.push_back(l.substr(i, j - i));
+    i = j;
+  }
+  return f;
+}
+
+int tid_of(const std::string &name, const std::vector<std::pair<std::string, uint32_t>> &targets) {
+  for (size_t t = 0; t < targets.size(); t++)
+    if (targets[t].first == name) return (int)t;
+  return -1;
+}
+
+void check_dna(const std::string &rep, const std::string &line) {
+  for (char c : rep)
+    if (c != 'A' && c != 'T' && c != 'C' && c != 'G')
+      throw std::runtime_error("Error reading loci bed file. Expected DNA (ATCG only) in the 4th field, and got an unexpected character on line: " + line);
+}
+
+// parse_bed (cluster.nim:111-141)
+std::vector<LocusLine> parse_bed(const std::string &path, const std::vector<std::pair<std::string, uint32_t>> &targets, uint32_t window, int32_t only_tid) {
+  std::ifstream in(path);
+  if (!in) throw std::runtime_error("couldn't open bed file");
+  std::vector<LocusLine> out;
+  std::string line;
+  while (std::getline(in, line)) {
+    const auto f = split_ws(line);
+    if (f.size() != 4 && f.size() != 5)
+      throw std::runtime_error("Error reading loci bed file. Expected 4 or 5 fields and got " + std::to_string(f.size()) + " on line: " + line);
+    LocusLine L;
+    if (f.size() == 5) L.name = f[4];
+    const int tid = tid_of(f[0], targets);
+    if (tid < 0) throw std::runtime_error("Error reading loci bed file. Unknown chromosome on line: " + line);
+    L.left = (uint32_t)std::stoul(f[1]);
+    L.right = (uint32_t)std::stoul(f[2]);
+    L.repeat = f[3];
+    if (L.repeat.size() > 6)
+      throw std::runtime_error("ERROR: STRling currently only supports 1-6 bp repeat units. Input bed contains repeat unit length " + std::to_string(L.repeat.size()) + "\n" + line);
+    check_dna(L.repeat, line);
+    std::memset(&L.key, 0, sizeof(L.key));
+    L.key.tid = tid;
+    L.key.left_most = (uint32_t)std::max((int32_t)L.left - (int32_t)window, 0);
+    L.key.right_most = std::min(L.right + window, targets[(size_t)tid].second);
+    std::memcpy(L.key.repeat, L.repeat.data(), L.repeat.size());
+    if (L.left > L.right || L.key.left_most > L.key.right_most) throw std::runtime_error("bad locus: " + line);
+    if (only_tid != INT32_MIN && tid != only_tid) continue;
+    out.push_back(L);
+  }
+  return out;
+}
+
+// parse_bounds (cluster.nim:143-169)
+std::vector<LocusLine> parse_bounds(const std::string &path, const std::vector<std::pair<std::string, uint32_t>> &targets) {
+  std::ifstream in(path);
+  if (!in) throw std::runtime_error("couldn't open bounds file");
+  std::vector<LocusLine> out;
+  std::string line;
+  while (std::getline(in, line)) {
+    if (!line.empty() && line[0] == '#') continue;
+    std::vector<std::string> f;
+    size_t i = 0;
+    while (true) {
+      const size_t j = line.find('\t', i);
+      f.push_back(line.substr(i, j == std::string::npos ? std::string::npos : j - i));
+      if (j == std::string::npos) break;
+      i = j + 1;
+    }
+    if (f.size() != 11) throw std::runtime_error("Error reading loci bed file. Expected 11 fields and got " + std::to_string(f.size()) + " on line: " + line);
+    LocusLine L;
+    const int tid = tid_of(f[0], targets);
+    if (tid < 0) throw std::runtime_error("Error reading bounds file. Unknown chromosome on line: " + line);
+    L.left = (uint32_t)std::stoul(f[1]);
+    L.right = (uint32_t)std::stoul(f[2]);
+    L.repeat = f[3];
+    L.name = f[4];
+    check_dna(L.repeat, line);
+    std::memset(&L.key, 0, sizeof(L.key));
+    L.key.tid = tid;
+    L.key.left_most = (uint32_t)std::stoul(f[5]);
+    L.key.right_most = (uint32_t)std::stoul(f[6]);
+    L.center_mass = (uint32_t)std::stoul(f[7]);
+    std::memcpy(L.key.repeat, L.repeat.data(), std::min<size_t>(6, L.repeat.size()));
+    if (L.left > L.right || L.key.left_most > L.key.right_most) throw std::runtime_error("bad bounds line: " + line);
+    out.push_back(L);
+  }
+  return out;
+}
+
+std::string locus_line(const LocusLine &L, const std::vector<std::pair<std::string, uint32_t>> &targets) {  // Bounds.tostring
+  char buf[640];
+  std::snprintf(buf, sizeof(buf), "%s\t%u\t%u\t%s\t%s\t%u\t%u\t%u\t%u\t%u\t%u", targets[(size_t)L.key.tid].first.c_str(), L.left, L.right,
+                L.repeat.c_str(), L.name.c_str(), L.key.left_most, L.key.right_most, L.center_mass, (unsigned)L.key.n_left,
+                (unsigned)L.key.n_right, (unsigned)L.key.n_total);
+  return buf;
+}
+
+std::vector<strgpu_bounds> run_cluster(const std::vector<strgpu_tread> &treads, const strgpu_cluster_params &p, int device, bool verbose,
+                                       std::vector<LocusLine> *loci = nullptr) {
   strgpu_ctx *gpu = nullptr;
   int rc = strgpu_create(&gpu, device);
   if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + strgpu_error_string(rc));
   std::vector<strgpu_bounds> out(std::max<size_t>(1024, treads.size() / 4));
   uint32_t n_out = 0;
-  rc = strgpu_cluster(gpu, treads.data(), (uint32_t)treads.size(), &p, out.data(), (uint32_t)out.size(), &n_out);
+  std::vector<strgpu_locus> keys;
+  if (loci)
+    for (const auto &l : *loci) keys.push_back(l.key);
+  rc = strgpu_cluster_loci(gpu, treads.data(), (uint32_t)treads.size(), &p, keys.data(), (uint32_t)keys.size(), out.data(), (uint32_t)out.size(), &n_out);
   if (rc == STRGPU_ERR_OVERFLOW) {
     out.resize(n_out);
-    rc = strgpu_cluster(gpu, treads.data(), (uint32_t)treads.size(), &p, out.data(), (uint32_t)out.size(), &n_out);
+    rc = strgpu_cluster_loci(gpu, treads.data(), (uint32_t)treads.size(), &p, keys.data(), (uint32_t)keys.size(), out.data(), (uint32_t)out.size(), &n_out);
   }
+  if (loci)
+    for (size_t i = 0; i < keys.size(); i++) (*loci)[i].key = keys[i];
   if (rc != STRGPU_OK) {
     const std::string msg = strgpu_last_error(gpu);
     strgpu_destroy(gpu);
@@ -118,7 +234,6 @@ int merge_main(int argc, char **argv) {
                               {"-o", "--output-prefix", true}, {"-d", "--diff-refs", false}, {"-v", "--verbose", false}, {"", "--device", true}},
                  usage);
   if (a.pos.empty()) { std::fputs(usage, stdout); return 0; }
-  if (a.has("--bed")) throw std::runtime_error("[strling merge] -l/--bed (assign_reads_locus, callclusters.nim:14) is not part of this build");
   if (a.has("--diff-refs")) throw std::runtime_error("[strling merge] -d/--diff-refs is not part of this build");
   int window = std::stoi(a.get("--window", "-1"));
   const int min_support = std::stoi(a.get("--min-support", "5"));
@@ -172,11 +287,14 @@ int merge_main(int argc, char **argv) {
   p.min_clip_total = min_clip_total;
   p.max_clip_dist = (uint16_t)(0.5 * (double)frag_median(frag, 0.5));  // merge.nim:181
   p.merge_mode = 1;
-  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose);
+  std::vector<LocusLine> loci;
+  if (a.has("--bed")) loci = parse_bed(a.get("--bed", ""), targets, (uint32_t)window, requested_tid);  // merge.nim:154-157
+  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose, loci.empty() ? nullptr : &loci);
 
   std::ofstream out(prefix + "-bounds.txt");
   if (!out) throw std::runtime_error("couldn't open output file");
   out << kBoundsHeader << "\n";
+  for (const auto &l : loci) out << locus_line(l, targets) << "\n";  // merge.nim:166-168
   for (const auto &b : bounds)
     if (b.tid >= 0) out << bounds_line(b, targets) << "\n";
   out.close();
@@ -193,7 +311,6 @@ int call_main(int argc, char **argv) {
                               {"-v", "--verbose", false}, {"", "--device", true}},
                  usage);
   if (a.pos.size() != 2) { std::fputs(usage, stdout); return a.pos.empty() ? 0 : 1; }
-  if (a.has("--loci") || a.has("--bounds")) throw std::runtime_error("[strling call] -l / -b (assign_reads_locus, callclusters.nim:14) are not part of this build");
   const std::string prefix = a.get("--output-prefix", "strling");
   const bool verbose = a.has("--verbose");
   // call.nim:96-114 : the fragment distribution is re-derived from the BAM, window = its 0.99 quantile
@@ -217,11 +334,19 @@ int call_main(int argc, char **argv) {
   p.min_clip_total = (uint16_t)std::stoi(a.get("--min-clip-total", "0"));
   p.max_clip_dist = (uint16_t)(0.5 * (double)frag_median(frag, 0.5));  // call.nim:232
   p.merge_mode = 0;
-  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose);
+  // call.nim:189-218: bounds (-b) then loci (-l) take their reads first; genotyping them needs collect.nim (not built)
+  std::vector<LocusLine> loci;
+  if (a.has("--bounds")) loci = parse_bounds(a.get("--bounds", ""), targets);
+  if (a.has("--loci")) {
+    auto more = parse_bed(a.get("--loci", ""), targets, p.window, INT32_MIN);
+    loci.insert(loci.end(), more.begin(), more.end());
+  }
+  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose, loci.empty() ? nullptr : &loci);
 
   std::ofstream bo(prefix + "-bounds.txt"), un(prefix + "-unplaced.txt");
   if (!bo || !un) throw std::runtime_error("couldn't open output file");
   bo << kBoundsHeader << "\n";   // the reference appends "\tdepth" here (call.nim:145); depth needs collect.nim (not built)
+  for (const auto &l : loci) bo << locus_line(l, targets) << "\n";
   for (const auto &b : bounds) {
     if (b.tid >= 0) { bo << bounds_line(b, targets) << "\n"; continue; }
     char unit[7] = {0};

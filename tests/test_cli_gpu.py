@@ -118,6 +118,16 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
         got = open(prefix + "-bounds.txt").read().splitlines()
         assert got[0] == eo.BOUNDS_HEADER and (len(exp_lines) > 5 or extra[:2] == ["-c", "1"])
         assert sorted(got[1:]) == sorted(exp_lines) and got[1:] == exp_lines
+    # -l bed: listed loci take their reads before clustering and are reported first (merge.nim:154-168, callclusters.nim:14-50)
+    bed = str(tmp_path / "loci.bed")
+    bed_lines = [f"{targets[tid][0]}\t{s}\t{e}\t{u}\tL{i}" if i % 2 else f"{targets[tid][0]} {s} {e} {u}" for i, (tid, s, e, u) in enumerate(loci[:12])]
+    bed_lines.append(f"{targets[0][0]}\t5\t9\tGGGGGC")  # a bucket that does not exist
+    open(bed, "w").write("\n".join(bed_lines) + "\n")
+    prefix = str(tmp_path / "merge_bed")
+    run(cli, "merge", "-m", "3", "-l", bed, "-o", prefix, *bins)
+    exp_lines, _ = eo.merge(datas, min_support=3, bed_lines=bed_lines)
+    got = open(prefix + "-bounds.txt").read().splitlines()
+    assert got[1:] == exp_lines and sum(int(l.split("\t")[10]) for l in got[1:14]) > 50
     # --chromosome restricts parsing to one contig (merge.nim:52,89)
     prefix = str(tmp_path / "merge_chr")
     run(cli, "merge", "-m", "3", "--chromosome", targets[2][0], "-o", prefix, *bins)

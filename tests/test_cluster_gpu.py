@@ -111,3 +111,30 @@ def test_large_scale_properties(gpu):
     assert np.all(got["left"] <= got["right"]) and np.all(got["left_most"] <= got["left"]) and np.all(got["right_most"] >= got["right"])
     key = np.stack([got["tid"].astype(np.int64), got["first_read"].astype(np.int64)], axis=1)
     assert np.all((key[1:, 0] > key[:-1, 0]) | ((key[1:, 0] == key[:-1, 0]) & (key[1:, 1] > key[:-1, 1])))  # output is ordered
+
+
+def test_assign_reads_locus_then_cluster(gpu):
+    # callclusters.nim:14-50 before the cluster loop (merge -l / call -l -b): loci of one bucket are sequential, the
+    # read right after each window is dropped too, unknown buckets and empty windows are no-ops
+    rng = np.random.default_rng(17)
+    for seed, dense in ((5, True), (6, False)):
+        treads = synth.make_treads(2000, seed=seed, noise_reads=15000, unplaced=200, dense=dense, n_tids=4 if dense else 24, n_samples=3)
+        units = np.unique(treads["repeat"])
+        k = 400
+        loci = np.zeros(k, dtype=orc.LOCUS_DTYPE)
+        loci["tid"] = rng.integers(-1, 5 if dense else 24, size=k)
+        loci["repeat"] = rng.choice(np.concatenate([units, np.array([b"GGGGGC"], dtype="S6")]), size=k)
+        left = rng.integers(0, 6000 if dense else 100_000_000, size=k)
+        loci["left_most"] = np.where(rng.random(k) < 0.1, 0, left)
+        loci["right_most"] = loci["left_most"] + rng.integers(0, 1500, size=k)
+        # overlapping windows in the same bucket exercise the sequential dependency
+        loci[1::7] = loci[0::7][: len(loci[1::7])]
+        for merge_mode in (False, True):
+            el, eb, eu = orc.cluster_all_loci(treads.astype(orc.TREAD_DTYPE), loci, 450, 3, 0, 0, 180, merge_mode)
+            gl, gb, gu = gpu.cluster_loci(treads, loci.astype(sb.binding.LOCUS_DTYPE), 450, 3, 0, 0, 180, merge_mode)
+            for f in ("n_left", "n_right", "n_total"):
+                assert np.array_equal(gl[f], el[f]), f
+            assert el["n_total"].sum() > 100
+            assert len(gb) == len(eb) and gu == eu
+            for f in FIELDS:
+                assert np.array_equal(gb[f], eb[f]), f
