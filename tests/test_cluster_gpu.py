@@ -124,7 +124,12 @@ def test_assign_reads_locus_then_cluster(gpu):
         loci = np.zeros(k, dtype=orc.LOCUS_DTYPE)
         loci["tid"] = rng.integers(-1, 5 if dense else 24, size=k)
         loci["repeat"] = rng.choice(np.concatenate([units, np.array([b"GGGGGC"], dtype="S6")]), size=k)
-        left = rng.integers(0, 6000 if dense else 100_000_000, size=k)
+        left = rng.integers(0, 6000, size=k)
+        if not dense:  # centre the windows on real reads, and use their buckets
+            pick = treads[rng.integers(0, len(treads), size=k)]
+            left = np.maximum(pick["position"].astype(np.int64) - rng.integers(0, 700, size=k), 0)
+            loci["tid"] = np.where(rng.random(k) < 0.8, pick["tid"], loci["tid"])
+            loci["repeat"] = np.where(rng.random(k) < 0.8, pick["repeat"], loci["repeat"])
         loci["left_most"] = np.where(rng.random(k) < 0.1, 0, left)
         loci["right_most"] = loci["left_most"] + rng.integers(0, 1500, size=k)
         # overlapping windows in the same bucket exercise the sequential dependency
