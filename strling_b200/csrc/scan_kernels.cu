@@ -271,77 +271,30 @@ __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *_
 }
 
 // ================================================================================================
-// K1 v2: one LANE per segment (segments of <= 160 bases without non-ACGT bases).
-//   * each thread keeps its read as a private column of shared memory words ([word][thread]: bank == lane, conflict free),
-//   * k = 2, 3, 4: min-rotation class of every window through a small shared LUT, counted in a private column of
-//     uint32 counters ([class][thread], conflict free) with the running leader updated exactly like Seq.inc (strict >),
-//   * recount: bit-parallel pattern match over the ten words; popcount when no two matches can overlap, otherwise a
-//     run-wise greedy walk,
-//   * segments that survive to k = 5, 6 (a few per cent), segments with N, and nothing else, are compacted into a
-//     per-CTA queue and finished by the warp-per-segment code above on the same CTA.
+// K1 v3: one LANE per segment (segments of <= 160 bases without non-ACGT bases).
+//   * each lane keeps its read as a private column of shared-memory words ([word][lane]: bank == lane, conflict free),
+//   * k = 2, 3 and 4 are counted in ONE pass over the read: every window's min-rotation class comes from a small shared
+//     LUT and is counted in the lane's private column of uint32 counters ([class][lane], conflict free); the three
+//     histograms are independent read-modify-write chains, interleaved by hand so three shared-memory loads are in
+//     flight per lane; the running leader is updated exactly like Seq.inc (strict >, utils.nim:192-195),
+//   * the ladder (utils.nim:250-265) then runs on the three (M, leader) pairs; the recount is bit-parallel over the
+//     ten words (popcount when no two matches can overlap, a run-wise greedy walk otherwise),
+//   * lanes that survive to k = 5 (~12 % of random reads) are compacted into a warp-local queue and counted 32 at a
+//     time with packed uint8 counters; only k = 6 survivors (~1 %), segments with N and segments longer than 160
+//     bases are finished one per warp by the compact warp-per-segment code.
+// Every warp owns its shared-memory region and its queues: there is no block-level barrier after start-up.
 // ================================================================================================
 constexpr int kLaneThreads = 128;
-constexpr int kLaneWords = 11;         // ten words hold 160 bases; one more absorbs the re-alignment shift
-constexpr int kLaneClasses = 70;       // min-rotation classes of 4-mers (24 for 3-mers, 10 for 2-mers)
-constexpr int kLutEntries = 16 + 64 + 256;       // class byte-offset LUTs for k = 2, 3, 4
-constexpr int kRevEntries = 10 + 24 + 70;        // class -> canonical code
-constexpr int kLaneSmemBytes = (kLaneThreads / 32) * (kLaneClasses * 32 + kLaneWords * 32) * 4 + (kLutEntries + kRevEntries) * 2 + 16;
-
-template <int K> struct LaneK;
-template <> struct LaneK<2> { static constexpr int wpw = 8, bits = 32, classes = 10, lut = 0, rev = 0; };
-template <> struct LaneK<3> { static constexpr int wpw = 5, bits = 30, classes = 24, lut = 16, rev = 10; };
-template <> struct LaneK<4> { static constexpr int wpw = 4, bits = 32, classes = 70, lut = 80, rev = 34; };
-
-// word `wi` of the k-specific window stream: k = 2, 4 use the aligned words as they are (8 / 4 windows each);
-// k = 3 re-cuts the bit stream into 30-bit pieces (5 windows each)
-template <int K>
-__device__ __forceinline__ uint32_t lane_word(const uint32_t *rd, int wi) {
-  if (K == 3) {
-    const int bit = 30 * wi;
-    const int a = bit >> 5;
-    return __funnelshift_l(rd[(a + 1) * 32], rd[a * 32], bit & 31) >> 2;
-  }
-  return rd[wi * 32];
-}
-
-template <int K>
-__device__ __forceinline__ void lane_count(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, const uint16_t *rev, int L,
-                                           int &M, uint32_t &leader) {
-  using P = LaneK<K>;
-  constexpr uint32_t kMask = (1u << (2 * K)) - 1u;
-  const int W = L / K;
-  const int nfull = W / P::wpw;
-  const int rem = W - nfull * P::wpw;
-#pragma unroll
-  for (int c = 0; c < P::classes; c++) tab[c * 32] = 0;
-  M = 0;
-  uint32_t lead_off = 0xffffffffu;
-  const uint16_t *l = lut + P::lut;
-  for (int wi = 0; wi < nfull; wi++) {
-    const uint32_t x = lane_word<K>(rd, wi);
-#pragma unroll
-    for (int t = 0; t < P::wpw; t++) {
-      const uint32_t code = (x >> (P::bits - 2 * K * (t + 1))) & kMask;
-      const uint32_t off = l[code];
-      uint32_t *slot = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(tab) + off);
-      const int cnt = (int)*slot + 1;
-      *slot = (uint32_t)cnt;
-      if (cnt > M) { M = cnt; lead_off = off; }   // Seq.inc: strict >, earlier leader keeps ties (utils.nim:192-195)
-    }
-  }
-  if (rem > 0) {
-    const uint32_t x = lane_word<K>(rd, nfull);
-    for (int t = 0; t < rem; t++) {
-      const uint32_t code = (x >> (P::bits - 2 * K * (t + 1))) & kMask;
-      const uint32_t off = l[code];
-      uint32_t *slot = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(tab) + off);
-      const int cnt = (int)*slot + 1;
-      *slot = (uint32_t)cnt;
-      if (cnt > M) { M = cnt; lead_off = off; }
-    }
-  }
-  leader = (lead_off == 0xffffffffu) ? kMask : (uint32_t)rev[P::rev + lead_off / 128u];
-}
+constexpr int kLaneWarps = kLaneThreads / 32;
+constexpr int kLaneWords = 11;                 // ten words hold 160 bases; one more absorbs the re-alignment shift
+constexpr int kCls2 = 10, kCls3 = 24, kCls4 = 70, kCls5 = 208;
+constexpr int kTabWords = kCls2 + kCls3 + kCls4;  // 104 uint32 counters per lane (k = 5 reuses 52 of them as 208 uint8)
+constexpr int kLut2 = 0, kLut3 = 16, kLut4 = 80, kRev234 = 336, kLut5 = 440, kRev5 = 1464;  // offsets into the uint16 table
+constexpr int kLutTotal = 1672;
+constexpr int kQueueCap = 64;
+constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + 2 * kQueueCap * 3;
+constexpr int kLaneSmemBytes = kLaneWarps * kWarpSmemWords * 4 + kLutTotal * 2 + 16;
+static_assert(sizeof(WarpScratch<512>) <= (size_t)kTabWords * 32 * 4, "warp scratch must fit in the warp's counter region");
 
 // read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254).
 // One copy for all k (kept out of line: instruction-cache footprint matters more than the call).
@@ -402,26 +355,6 @@ __device__ __noinline__ int lane_recount(const uint32_t *rd, int L, uint32_t pat
     }
   }
   return c;
-}
-
-template <int K>
-__device__ __forceinline__ bool lane_step(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, const uint16_t *rev, int L,
-                                          int thr_p, int thr_giveup, ScanState &st) {
-  int M;
-  uint32_t leader;
-  lane_count<K>(rd, tab, lut, rev, L, M, leader);
-  int score = M * K;
-  if (score <= st.best) return !(M < thr_giveup);
-  const int c = lane_recount(rd, L, leader, K);
-  score = c * K;
-  if (score < st.best) return true;
-  st.best = score;
-  if (c > thr_p) {
-    st.unit_code = leader;
-    st.unit_k = K;
-    st.rc = c;
-  }
-  return true;
 }
 
 // Compact warp-per-segment path (runtime k, rolled loops) for the few segments the lane path hands off: same
@@ -554,113 +487,312 @@ __device__ __noinline__ void warp_scan_compact(WarpScratch<512> &ws, const uint3
   if (lane == 0) emit_result(out, s, st);
 }
 
-constexpr int kLaneWarps = kLaneThreads / 32;
-constexpr int kWarpTabWords = kLaneClasses * 32;
-constexpr int kWarpRdWords = kLaneWords * 32;
-static_assert(sizeof(WarpScratch<512>) <= (size_t)kWarpTabWords * 4, "warp scratch must fit in the warp's counter region");
 
-// Every warp works on its own groups of 32 segments with its own shared-memory region: no block-level barrier.
+// NB bits at bit offset BIT of the 96-bit big-endian chunk w0:w1:w2 (all compile time)
+template <int BIT, int NB>
+__device__ __forceinline__ uint32_t chunk_field(uint32_t w0, uint32_t w1, uint32_t w2) {
+  constexpr int word = BIT >> 5, sh = BIT & 31;
+  if constexpr (sh + NB <= 32) {
+    const uint32_t w = word == 0 ? w0 : (word == 1 ? w1 : w2);
+    return (w >> (32 - sh - NB)) & ((1u << NB) - 1u);
+  } else {
+    const uint32_t hi = word == 0 ? w0 : w1, lo = word == 0 ? w1 : w2;
+    return __funnelshift_l(lo, hi, sh) >> (32 - NB);
+  }
+}
+
+struct Lead {
+  int M;
+  uint32_t off;
+};
+__device__ __forceinline__ uint32_t *slot_at(uint32_t *tab, uint32_t off) {
+  return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(tab) + off);
+}
+__device__ __forceinline__ void lead_update(Lead &l, int c, uint32_t off) {
+  if (c > l.M) { l.M = c; l.off = off; }   // strict >: the earlier leader keeps ties
+}
+__device__ __forceinline__ void bump1(uint32_t *tab, uint32_t o, Lead &l) {
+  uint32_t *p = slot_at(tab, o);
+  const int c = (int)*p + 1;
+  *p = (uint32_t)c;
+  lead_update(l, c, o);
+}
+// three independent histograms: issue the three loads before the three stores
+__device__ __forceinline__ void bump3(uint32_t *tab, uint32_t o2, uint32_t o3, uint32_t o4, Lead &l2, Lead &l3, Lead &l4) {
+  uint32_t *p2 = slot_at(tab, o2), *p3 = slot_at(tab, o3), *p4 = slot_at(tab, o4);
+  const int c2 = (int)*p2 + 1, c3 = (int)*p3 + 1, c4 = (int)*p4 + 1;
+  *p2 = (uint32_t)c2; *p3 = (uint32_t)c3; *p4 = (uint32_t)c4;
+  lead_update(l2, c2, o2); lead_update(l3, c3, o3); lead_update(l4, c4, o4);
+}
+__device__ __forceinline__ void bump2(uint32_t *tab, uint32_t oa, uint32_t ob, Lead &la, Lead &lb) {
+  uint32_t *pa = slot_at(tab, oa), *pb = slot_at(tab, ob);
+  const int ca = (int)*pa + 1, cb = (int)*pb + 1;
+  *pa = (uint32_t)ca; *pb = (uint32_t)cb;
+  lead_update(la, ca, oa); lead_update(lb, cb, ob);
+}
+
+// twelve bases (24 bits at offset 24*G of the chunk): six 2-mer, four 3-mer and three 4-mer windows
+template <int G>
+__device__ __forceinline__ void count_group(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t *tab, const uint16_t *lut, Lead &l2,
+                                            Lead &l3, Lead &l4) {
+  constexpr int B = 24 * G;
+  const uint32_t a0 = lut[kLut2 + chunk_field<B + 0, 4>(w0, w1, w2)], a1 = lut[kLut2 + chunk_field<B + 4, 4>(w0, w1, w2)],
+                 a2 = lut[kLut2 + chunk_field<B + 8, 4>(w0, w1, w2)], a3 = lut[kLut2 + chunk_field<B + 12, 4>(w0, w1, w2)],
+                 a4 = lut[kLut2 + chunk_field<B + 16, 4>(w0, w1, w2)], a5 = lut[kLut2 + chunk_field<B + 20, 4>(w0, w1, w2)];
+  const uint32_t b0 = lut[kLut3 + chunk_field<B + 0, 6>(w0, w1, w2)], b1 = lut[kLut3 + chunk_field<B + 6, 6>(w0, w1, w2)],
+                 b2 = lut[kLut3 + chunk_field<B + 12, 6>(w0, w1, w2)], b3 = lut[kLut3 + chunk_field<B + 18, 6>(w0, w1, w2)];
+  const uint32_t c0 = lut[kLut4 + chunk_field<B + 0, 8>(w0, w1, w2)], c1 = lut[kLut4 + chunk_field<B + 8, 8>(w0, w1, w2)],
+                 c2 = lut[kLut4 + chunk_field<B + 16, 8>(w0, w1, w2)];
+  bump3(tab, a0, b0, c0, l2, l3, l4);
+  bump3(tab, a1, b1, c1, l2, l3, l4);
+  bump3(tab, a2, b2, c2, l2, l3, l4);
+  bump2(tab, a3, b3, l2, l3);
+  bump1(tab, a4, l2);
+  bump1(tab, a5, l2);
+}
+
+// count(read, k, counts[k]) for k = 2, 3, 4 in one pass (utils.nim:205-211 three times)
+__device__ __forceinline__ void lane_count234(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, int L, Lead &l2, Lead &l3,
+                                              Lead &l4) {
+#pragma unroll
+  for (int c = 0; c < kTabWords; c++) tab[c * 32] = 0;
+  l2 = Lead{0, 0xffffffffu};
+  l3 = Lead{0, 0xffffffffu};
+  l4 = Lead{0, 0xffffffffu};
+  const int n_chunks = L / 48;
+#pragma unroll 1
+  for (int c = 0; c < n_chunks; c++) {
+    const uint32_t w0 = rd[(3 * c) * 32], w1 = rd[(3 * c + 1) * 32], w2 = rd[(3 * c + 2) * 32];
+    count_group<0>(w0, w1, w2, tab, lut, l2, l3, l4);
+    count_group<1>(w0, w1, w2, tab, lut, l2, l3, l4);
+    count_group<2>(w0, w1, w2, tab, lut, l2, l3, l4);
+    count_group<3>(w0, w1, w2, tab, lut, l2, l3, l4);
+  }
+  // tail: the windows that start in the last, partial chunk
+  const int r2 = L / 2 - 24 * n_chunks, r3 = L / 3 - 16 * n_chunks, r4 = L / 4 - 12 * n_chunks;
+  const uint32_t *tw = rd + 3 * n_chunks * 32;
+#pragma unroll 1
+  for (int t = 0; t < r2; t++) {
+    {
+      const uint32_t bit = 4u * t;
+      bump1(tab, lut[kLut2 + (__funnelshift_l(tw[((bit >> 5) + 1) * 32], tw[(bit >> 5) * 32], bit & 31u) >> 28)], l2);
+    }
+    if (t < r3) {
+      const uint32_t bit = 6u * t;
+      bump1(tab, lut[kLut3 + (__funnelshift_l(tw[((bit >> 5) + 1) * 32], tw[(bit >> 5) * 32], bit & 31u) >> 26)], l3);
+    }
+    if (t < r4) {
+      const uint32_t bit = 8u * t;
+      bump1(tab, lut[kLut4 + (__funnelshift_l(tw[((bit >> 5) + 1) * 32], tw[(bit >> 5) * 32], bit & 31u) >> 24)], l4);
+    }
+  }
+}
+
+// one rung of the ladder (utils.nim:246-265) given this k's count result.  Returns false on `break`.
+__device__ __forceinline__ bool lane_decide(const uint32_t *rd, int L, int K, int M, uint32_t leader, int thr_p, int thr_giveup,
+                                            ScanState &st) {
+  int score = M * K;
+  if (score <= st.best) return !(M < thr_giveup);
+  const int c = lane_recount(rd, L, leader, K);
+  score = c * K;
+  if (score < st.best) return true;
+  st.best = score;
+  if (c > thr_p) {
+    st.unit_code = leader;
+    st.unit_k = K;
+    st.rc = c;
+  }
+  return true;
+}
+
+// stage the lane's read: eleven words, re-aligned so that base 0 sits at bit 31 of word 0
+__device__ __forceinline__ void lane_stage(const uint32_t *__restrict__ seq, const strgpu_segment &sg, uint32_t *rd) {
+  const uint32_t g = sg.base_off >> 4;
+  const uint32_t sh = 2u * (sg.base_off & 15u);
+  const int n_words = (2 * (int)sg.len + 31) >> 5;
+  uint32_t raw[kLaneWords + 1];
+#pragma unroll
+  for (int j = 0; j < kLaneWords + 1; j++) raw[j] = (j <= n_words) ? __byte_perm(seq[g + j], 0, 0x0123) : 0u;
+#pragma unroll
+  for (int j = 0; j < kLaneWords; j++) rd[j * 32] = __funnelshift_l(raw[j + 1], raw[j], sh);
+}
+
+// count(read, 5, counts[5]) with 208 packed uint8 counters ([class / 4][lane] words)
+__device__ __forceinline__ void lane_count5(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, int L, int &M, uint32_t &leader) {
+#pragma unroll
+  for (int c = 0; c < kCls5 / 4; c++) tab[c * 32] = 0;
+  M = 0;
+  uint32_t lead = 0xffffffffu;
+  const int W = L / 5;
+#pragma unroll 2
+  for (int j = 0; j < W; j++) {
+    const uint32_t bit = 10u * j;
+    const uint32_t code = __funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 22;
+    const uint32_t e = lut[kLut5 + code];        // (class / 4) * 128 | (class % 4) * 8
+    uint32_t *p = slot_at(tab, e & 0xff80u);
+    const uint32_t sh = e & 31u;
+    const uint32_t v = *p + (1u << sh);
+    *p = v;
+    const int c = (int)((v >> sh) & 0xffu);
+    if (c > M) { M = c; lead = e; }
+  }
+  leader = (lead == 0xffffffffu) ? 0x3ffu : (uint32_t)lut[kRev5 + (lead >> 7) * 4 + ((lead & 31u) >> 3)];
+}
+
+struct LaneQueue {  // warp-local FIFO of handed-on segments: {segment, best << 16 | rc, unit_code | unit_k << 16 | start_k << 24}
+  uint32_t *buf;
+  int n;
+};
+__device__ __forceinline__ void queue_push(LaneQueue &q, bool want, int lane, uint32_t s, const ScanState &st, int start_k) {
+  const uint32_t m = __ballot_sync(kFull, want);
+  if (want) {
+    const int i = q.n + __popc(m & ((1u << lane) - 1u));
+    q.buf[3 * i + 0] = s;
+    q.buf[3 * i + 1] = ((uint32_t)(st.best & 0xffff) << 16) | (uint32_t)(st.rc & 0xffff);
+    q.buf[3 * i + 2] = (st.unit_code & 0xffffu) | ((uint32_t)st.unit_k << 16) | ((uint32_t)start_k << 24);
+  }
+  q.n += __popc(m);
+  __syncwarp();
+}
+__device__ __forceinline__ void queue_read(const LaneQueue &q, int i, uint32_t &s, ScanState &st, int &start_k) {
+  s = q.buf[3 * i + 0];
+  const uint32_t a = q.buf[3 * i + 1], b = q.buf[3 * i + 2];
+  st.best = (int)(int16_t)(a >> 16);
+  st.rc = (int)(a & 0xffffu);
+  st.unit_code = b & 0xffffu;
+  st.unit_k = (int)((b >> 16) & 0xffu);
+  start_k = (int)(b >> 24);
+}
+
 __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                  const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                  const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
                                                                  strgpu_repeat *__restrict__ out, int *status) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kLaneWarps * (kWarpTabWords + kWarpRdWords));
-  uint16_t *rev = lut + kLutEntries;
-  for (int i = tid; i < kLutEntries + kRevEntries; i += kLaneThreads) lut[i] = luts[i];
+  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kLaneWarps * kWarpSmemWords);
+  for (int i = tid; i < kLutTotal; i += kLaneThreads) lut[i] = luts[i];
   __syncthreads();
-  uint32_t *tab_warp = smem + warp * (kWarpTabWords + kWarpRdWords);   // [class][lane] counters; warp scratch for hand-offs
-  uint32_t *tab = tab_warp + lane;
-  uint32_t *rd = tab_warp + kWarpTabWords + lane;                        // [word][lane] read columns
+  uint32_t *warp_base = smem + warp * kWarpSmemWords;
+  uint32_t *tab = warp_base + lane;                      // [class][lane] counters; warp scratch for the k = 6 hand-offs
+  uint32_t *rd = warp_base + kTabWords * 32 + lane;      // [word][lane] read columns
+  LaneQueue q5{warp_base + kTabWords * 32 + kLaneWords * 32, 0};
+  LaneQueue q6{q5.buf + 3 * kQueueCap, 0};
+  const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
   const uint32_t n_groups = (n_seg + 31) / 32;
   const uint32_t warps_total = gridDim.x * kLaneWarps;
-  for (uint32_t grp = blockIdx.x * kLaneWarps + warp; grp < n_groups; grp += warps_total) {
-    const uint32_t s = grp * 32 + lane;
-    const bool active = s < n_seg;
-    strgpu_segment sg{0, 0, 0, 0};
-    if (active) sg = segs[s];
-    const int L = sg.len;
-    const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
-    ScanState st{-1, 0u, 0, 0};
-    int handoff_k = (active && !lane_path) ? 2 : 0;       // 0: finished here
-    __syncwarp();
-    if (lane_path) {
-      // ---- stage: eleven words, re-aligned so that base 0 sits at bit 31 of word 0
-      const uint32_t g = sg.base_off >> 4;
-      const uint32_t sh = 2u * (sg.base_off & 15u);
-      const int n_words = (2 * L + 31) >> 5;
-      uint32_t raw[kLaneWords + 1];
-#pragma unroll
-      for (int j = 0; j < kLaneWords + 1; j++) raw[j] = (j <= n_words) ? __byte_perm(seq[g + j], 0, 0x0123) : 0u;
-#pragma unroll
-      for (int j = 0; j < kLaneWords; j++) rd[j * 32] = __funnelshift_l(raw[j + 1], raw[j], sh);
-      const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-      const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
-      const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen + L;
-      bool go = lane_step<2>(rd, tab, lut, rev, L, tp[0], tg[0], st);
-      if (go) go = lane_step<3>(rd, tab, lut, rev, L, tp[kThrLen], tg[kThrLen], st);
-      if (go) go = lane_step<4>(rd, tab, lut, rev, L, tp[2 * kThrLen], tg[2 * kThrLen], st);
-      if (go) handoff_k = 5;
-      else emit_result(out, s, st);
+  uint32_t grp = blockIdx.x * kLaneWarps + warp;
+  while (true) {
+    const bool more = grp < n_groups;
+    if (more) {
+      // ---- stage A: k = 2, 3, 4 for the next 32 segments
+      const uint32_t s = grp * 32 + lane;
+      grp += warps_total;
+      const bool active = s < n_seg;
+      strgpu_segment sg{0, 0, 0, 0};
+      if (active) sg = segs[s];
+      const int L = sg.len;
+      const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
+      ScanState st{-1, 0u, 0, 0};
+      bool to5 = false;
+      if (lane_path) {
+        lane_stage(seq, sg, rd);
+        Lead l2, l3, l4;
+        lane_count234(rd, tab, lut, L, l2, l3, l4);
+        const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+        const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
+        const uint32_t lead2 = l2.off == 0xffffffffu ? 0xfu : (uint32_t)lut[kRev234 + (l2.off >> 7)];
+        bool go = lane_decide(rd, L, 2, l2.M, lead2, tp[0], tg[L], st);
+        if (go) {
+          const uint32_t lead3 = l3.off == 0xffffffffu ? 0x3fu : (uint32_t)lut[kRev234 + (l3.off >> 7)];
+          go = lane_decide(rd, L, 3, l3.M, lead3, tp[kThrLen], tg[kThrLen + L], st);
+        }
+        if (go) {
+          const uint32_t lead4 = l4.off == 0xffffffffu ? 0xffu : (uint32_t)lut[kRev234 + (l4.off >> 7)];
+          go = lane_decide(rd, L, 4, l4.M, lead4, tp[2 * kThrLen], tg[2 * kThrLen + L], st);
+        }
+        if (go) to5 = true;
+        else emit_result(out, s, st);
+      }
+      __syncwarp();
+      queue_push(q5, to5, lane, s, st, 5);
+      queue_push(q6, active && !lane_path, lane, s, st, 2);
     }
-    __syncwarp();
-    uint32_t pending = __ballot_sync(kFull, handoff_k != 0);
-    if (pending) {  // warp-uniform: finish the handed-off segments one at a time on the whole warp
-      WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(tab_warp);
+    // ---- stage 5: k = 5 for up to 32 queued segments (full batches while input remains)
+    if (q5.n >= 32 || (!more && q5.n > 0)) {
+      const int nb = q5.n < 32 ? q5.n : 32;
+      const int first = q5.n - nb;   // take the newest nb entries; order between segments does not matter
+      uint32_t s = 0;
+      ScanState st{-1, 0u, 0, 0};
+      int start_k = 0;
+      bool to6 = false;
+      if (lane < nb) {
+        queue_read(q5, first + lane, s, st, start_k);
+        const strgpu_segment sg = segs[s];
+        const int L = sg.len;
+        lane_stage(seq, sg, rd);
+        int M;
+        uint32_t leader;
+        lane_count5(rd, tab, lut, L, M, leader);
+        const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+        const bool go = lane_decide(rd, L, 5, M, leader, thr[(size_t)(pclass * 5 + 3) * kThrLen + L], tg[3 * kThrLen + L], st);
+        if (go) to6 = true;
+        else emit_result(out, s, st);
+      }
+      __syncwarp();
+      q5.n = first;
+      queue_push(q6, to6, lane, s, st, 6);
+    }
+    // ---- k = 6 survivors, N-containing and long segments: one at a time on the whole warp
+    if (q6.n > 0) {
+      WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(warp_base);
       for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
       __syncwarp();
-      while (pending) {
-        const int src = __ffs(pending) - 1;
-        pending &= pending - 1;
-        ScanState qst;
-        qst.best = __shfl_sync(kFull, st.best, src);
-        qst.unit_code = __shfl_sync(kFull, st.unit_code, src);
-        qst.unit_k = __shfl_sync(kFull, st.unit_k, src);
-        qst.rc = __shfl_sync(kFull, st.rc, src);
-        const int start_k = __shfl_sync(kFull, handoff_k, src);
-        strgpu_segment qsg;
-        qsg.base_off = __shfl_sync(kFull, sg.base_off, src);
-        const uint32_t packed = __shfl_sync(kFull, (uint32_t)sg.len | ((uint32_t)sg.pclass << 16) | ((uint32_t)sg.flags << 24), src);
-        qsg.len = (uint16_t)(packed & 0xffffu);
-        qsg.pclass = (uint8_t)((packed >> 16) & 0xffu);
-        qsg.flags = (uint8_t)(packed >> 24);
-        warp_scan_compact(ws, seq, nmask, qsg, grp * 32 + (uint32_t)src, thr, lane, start_k, qst, out, status);
+      for (int e = 0; e < q6.n; e++) {
+        uint32_t s;
+        ScanState st;
+        int start_k;
+        queue_read(q6, e, s, st, start_k);
+        warp_scan_compact(ws, seq, nmask, segs[s], s, thr, lane, start_k, st, out, status);
       }
+      __syncwarp();
+      q6.n = 0;
     }
+    if (!more && q5.n == 0) break;
   }
 }
 
 }  // namespace
 
-// class LUTs of the lane kernel: for k = 2, 3, 4 the byte offset (class * 4 * kLaneThreads) of every window code's
-// min-rotation class, then the canonical (minimal) code of every class
+// Class LUTs of the lane kernel (uint16 each, kLutTotal entries):
+//   [kLut2, kLut3, kLut4)  byte offset of the counter of every 2/3/4-mer code's min-rotation class in the lane's column,
+//   [kRev234)              canonical (minimal) code of each of the 10 + 24 + 70 classes,
+//   [kLut5)                for 5-mer codes: (class / 4) * 128 | (class % 4) * 8 (word offset | bit shift of its uint8 counter),
+//   [kRev5)                canonical code of each of the 208 5-mer classes.
 void build_lane_luts(uint16_t *dst) {
-  int lut_off = 0, rev_off = kLutEntries;
-  for (int k = 2; k <= 4; k++) {
+  const int lut_off[6] = {0, 0, kLut2, kLut3, kLut4, kLut5};
+  const int rev_off[6] = {0, 0, kRev234, kRev234 + kCls2, kRev234 + kCls2 + kCls3, kRev5};
+  const int cls_base[6] = {0, 0, 0, kCls2, kCls2 + kCls3, 0};
+  for (int k = 2; k <= 5; k++) {
     const int n = 1 << (2 * k);
     const uint32_t mask = (uint32_t)n - 1u;
+    auto canon = [&](uint32_t code) {
+      uint32_t m = code, x = code;
+      for (int j = 1; j < k; j++) {
+        x = ((x << 2) | (x >> (2 * k - 2))) & mask;
+        if (x < m) m = x;
+      }
+      return m;
+    };
     int n_classes = 0;
+    for (int code = 0; code < n; code++)
+      if (canon((uint32_t)code) == (uint32_t)code) dst[rev_off[k] + n_classes++] = (uint16_t)code;  // canonical codes ascend
     for (int code = 0; code < n; code++) {
-      uint32_t m = (uint32_t)code, x = (uint32_t)code;
-      for (int j = 1; j < k; j++) {
-        x = ((x << 2) | (x >> (2 * k - 2))) & mask;
-        if (x < m) m = x;
-      }
-      if (m == (uint32_t)code) dst[rev_off + n_classes++] = (uint16_t)code;  // canonical codes ascend, so class ids do too
-    }
-    for (int code = 0; code < n; code++) {
-      uint32_t m = (uint32_t)code, x = (uint32_t)code;
-      for (int j = 1; j < k; j++) {
-        x = ((x << 2) | (x >> (2 * k - 2))) & mask;
-        if (x < m) m = x;
-      }
+      const uint16_t m = (uint16_t)canon((uint32_t)code);
       int cls = 0;
-      while (dst[rev_off + cls] != (uint16_t)m) cls++;
-      dst[lut_off + code] = (uint16_t)(cls * 4 * 32);
+      while (dst[rev_off[k] + cls] != m) cls++;
+      dst[lut_off[k] + code] = (k < 5) ? (uint16_t)((cls_base[k] + cls) * 128) : (uint16_t)(((cls >> 2) * 128) | ((cls & 3) * 8));
     }
-    lut_off += n;
-    rev_off += n_classes;
   }
 }
 
@@ -680,7 +812,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
       configured = true;
     }
     const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
-    uint32_t grid = (uint32_t)sm_count * 5u;  // 5 resident CTAs of 128 threads per SM (shared-memory bound)
+    uint32_t grid = (uint32_t)sm_count * 3u;  // 3 resident CTAs of 128 threads per SM (shared-memory bound)
     if (grid > tiles) grid = tiles;
     repeat_scan_lane<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr, d_luts, d_out,
                                                                      d_status);

@@ -19,7 +19,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
                                uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
                                strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream);
 
-constexpr int kLaneLutEntries = 16 + 64 + 256 + 10 + 24 + 70;
+constexpr int kLaneLutEntries = 1672;  // see build_lane_luts
 void build_lane_luts(uint16_t *dst);  // host: fills kLaneLutEntries uint16
 
 }  // namespace strgpu
