@@ -288,17 +288,20 @@ constexpr int kLaneThreads = 128;
 constexpr int kLaneWarps = kLaneThreads / 32;
 constexpr int kLaneWords = 11;                 // ten words hold 160 bases; one more absorbs the re-alignment shift
 constexpr int kCls2 = 10, kCls3 = 24, kCls4 = 70, kCls5 = 208;
-constexpr int kTabWords = kCls2 + kCls3 + kCls4;  // 104 uint32 counters per lane (k = 5 reuses 52 of them as 208 uint8)
+constexpr int kCls4Words = (kCls4 + 3) / 4;       // 4-mer classes are counted in packed uint8 (18 words) to keep smem small
+constexpr int kTabWords = kCls2 + kCls3 + kCls4Words;  // 52 words per lane; k = 5 reuses them as 208 packed uint8
 constexpr int kLut2 = 0, kLut3 = 16, kLut4 = 80, kRev234 = 336, kLut5 = 440, kRev5 = 1464;  // offsets into the uint16 table
 constexpr int kLutTotal = 1672;
 constexpr int kQueueCap = 64;
 constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + 2 * kQueueCap * 3;
 constexpr int kLaneSmemBytes = kLaneWarps * kWarpSmemWords * 4 + kLutTotal * 2 + 16;
 static_assert(sizeof(WarpScratch<512>) <= (size_t)kTabWords * 32 * 4, "warp scratch must fit in the warp's counter region");
+static_assert(kCls5 / 4 <= kTabWords, "k = 5 counters must fit");
 
 // read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254).
-// One copy for all k (kept out of line: instruction-cache footprint matters more than the call).
-__device__ __noinline__ int lane_recount(const uint32_t *rd, int L, uint32_t pat, int K) {
+// One copy for all k, kept out of line (instruction-cache footprint).  `scratch` is the lane's counter column (dead by
+// now); `magic` = 65536 / K + 1 turns the one division of the slow path into a multiply.
+__device__ __noinline__ int lane_recount(const uint32_t *rd, uint32_t *scratch, int L, uint32_t pat, int K, uint32_t magic) {
   const int npos = L - K + 1;
   if (npos <= 0) return 0;
   constexpr uint32_t kLow = 0x55555555u;
@@ -335,10 +338,13 @@ __device__ __noinline__ int lane_recount(const uint32_t *rd, int L, uint32_t pat
     for (int i = 0; i < 10; i++) c += __popc(m[i]);
     return c;
   }
-  int next = 0;  // first position the greedy walk may use
+  // self-overlapping pattern (homopolymers, ACAC..): walk the runs of consecutive match positions
 #pragma unroll
+  for (int i = 0; i < 10; i++) scratch[i * 32] = m[i];
+  int next = 0;  // first position the greedy walk may use
+#pragma unroll 1
   for (int i = 0; i < 10; i++) {
-    uint32_t mm = m[i];
+    uint32_t mm = scratch[i * 32];
     while (mm) {
       const int hb = 31 - __clz(mm);                       // earliest remaining match of this word
       const uint32_t gap = ~mm & kLow & ((1u << hb) - 1u);  // first non-match slot after it
@@ -347,7 +353,7 @@ __device__ __noinline__ int lane_recount(const uint32_t *rd, int L, uint32_t pat
       const int e = 16 * i + ((30 - hb2) >> 1);            // run of consecutive matches [p, e)
       const int s0 = p > next ? p : next;
       if (s0 < e) {
-        const int n = (e - s0 + K - 1) / K;
+        const int n = (int)(((uint32_t)(e - s0 + K - 1) * magic) >> 16);
         c += n;
         next = s0 + n * K;
       }
@@ -488,19 +494,6 @@ __device__ __noinline__ void warp_scan_compact(WarpScratch<512> &ws, const uint3
 }
 
 
-// NB bits at bit offset BIT of the 96-bit big-endian chunk w0:w1:w2 (all compile time)
-template <int BIT, int NB>
-__device__ __forceinline__ uint32_t chunk_field(uint32_t w0, uint32_t w1, uint32_t w2) {
-  constexpr int word = BIT >> 5, sh = BIT & 31;
-  if constexpr (sh + NB <= 32) {
-    const uint32_t w = word == 0 ? w0 : (word == 1 ? w1 : w2);
-    return (w >> (32 - sh - NB)) & ((1u << NB) - 1u);
-  } else {
-    const uint32_t hi = word == 0 ? w0 : w1, lo = word == 0 ? w1 : w2;
-    return __funnelshift_l(lo, hi, sh) >> (32 - NB);
-  }
-}
-
 struct Lead {
   int M;
   uint32_t off;
@@ -517,12 +510,22 @@ __device__ __forceinline__ void bump1(uint32_t *tab, uint32_t o, Lead &l) {
   *p = (uint32_t)c;
   lead_update(l, c, o);
 }
+// packed uint8 counter: entry = word byte offset | bit shift of the class's byte
+__device__ __forceinline__ void bump1p(uint32_t *tab, uint32_t e, Lead &l) {
+  uint32_t *p = slot_at(tab, e & 0xff80u);
+  const uint32_t sh = e & 31u;
+  const uint32_t v = *p + (1u << sh);
+  *p = v;
+  lead_update(l, (int)((v >> sh) & 0xffu), e);
+}
 // three independent histograms: issue the three loads before the three stores
-__device__ __forceinline__ void bump3(uint32_t *tab, uint32_t o2, uint32_t o3, uint32_t o4, Lead &l2, Lead &l3, Lead &l4) {
-  uint32_t *p2 = slot_at(tab, o2), *p3 = slot_at(tab, o3), *p4 = slot_at(tab, o4);
-  const int c2 = (int)*p2 + 1, c3 = (int)*p3 + 1, c4 = (int)*p4 + 1;
-  *p2 = (uint32_t)c2; *p3 = (uint32_t)c3; *p4 = (uint32_t)c4;
-  lead_update(l2, c2, o2); lead_update(l3, c3, o3); lead_update(l4, c4, o4);
+__device__ __forceinline__ void bump3(uint32_t *tab, uint32_t o2, uint32_t o3, uint32_t e4, Lead &l2, Lead &l3, Lead &l4) {
+  uint32_t *p2 = slot_at(tab, o2), *p3 = slot_at(tab, o3), *p4 = slot_at(tab, e4 & 0xff80u);
+  const uint32_t sh = e4 & 31u;
+  const int c2 = (int)*p2 + 1, c3 = (int)*p3 + 1;
+  const uint32_t v4 = *p4 + (1u << sh);
+  *p2 = (uint32_t)c2; *p3 = (uint32_t)c3; *p4 = v4;
+  lead_update(l2, c2, o2); lead_update(l3, c3, o3); lead_update(l4, (int)((v4 >> sh) & 0xffu), e4);
 }
 __device__ __forceinline__ void bump2(uint32_t *tab, uint32_t oa, uint32_t ob, Lead &la, Lead &lb) {
   uint32_t *pa = slot_at(tab, oa), *pb = slot_at(tab, ob);
@@ -531,27 +534,8 @@ __device__ __forceinline__ void bump2(uint32_t *tab, uint32_t oa, uint32_t ob, L
   lead_update(la, ca, oa); lead_update(lb, cb, ob);
 }
 
-// twelve bases (24 bits at offset 24*G of the chunk): six 2-mer, four 3-mer and three 4-mer windows
-template <int G>
-__device__ __forceinline__ void count_group(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t *tab, const uint16_t *lut, Lead &l2,
-                                            Lead &l3, Lead &l4) {
-  constexpr int B = 24 * G;
-  const uint32_t a0 = lut[kLut2 + chunk_field<B + 0, 4>(w0, w1, w2)], a1 = lut[kLut2 + chunk_field<B + 4, 4>(w0, w1, w2)],
-                 a2 = lut[kLut2 + chunk_field<B + 8, 4>(w0, w1, w2)], a3 = lut[kLut2 + chunk_field<B + 12, 4>(w0, w1, w2)],
-                 a4 = lut[kLut2 + chunk_field<B + 16, 4>(w0, w1, w2)], a5 = lut[kLut2 + chunk_field<B + 20, 4>(w0, w1, w2)];
-  const uint32_t b0 = lut[kLut3 + chunk_field<B + 0, 6>(w0, w1, w2)], b1 = lut[kLut3 + chunk_field<B + 6, 6>(w0, w1, w2)],
-                 b2 = lut[kLut3 + chunk_field<B + 12, 6>(w0, w1, w2)], b3 = lut[kLut3 + chunk_field<B + 18, 6>(w0, w1, w2)];
-  const uint32_t c0 = lut[kLut4 + chunk_field<B + 0, 8>(w0, w1, w2)], c1 = lut[kLut4 + chunk_field<B + 8, 8>(w0, w1, w2)],
-                 c2 = lut[kLut4 + chunk_field<B + 16, 8>(w0, w1, w2)];
-  bump3(tab, a0, b0, c0, l2, l3, l4);
-  bump3(tab, a1, b1, c1, l2, l3, l4);
-  bump3(tab, a2, b2, c2, l2, l3, l4);
-  bump2(tab, a3, b3, l2, l3);
-  bump1(tab, a4, l2);
-  bump1(tab, a5, l2);
-}
-
-// count(read, k, counts[k]) for k = 2, 3, 4 in one pass (utils.nim:205-211 three times)
+// count(read, k, counts[k]) for k = 2, 3, 4 in one pass (utils.nim:205-211 three times): the read is walked in groups
+// of twelve bases (six 2-mer, four 3-mer and three 4-mer windows); the loop body fits the L0 instruction cache.
 __device__ __forceinline__ void lane_count234(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, int L, Lead &l2, Lead &l3,
                                               Lead &l4) {
 #pragma unroll
@@ -559,41 +543,49 @@ __device__ __forceinline__ void lane_count234(const uint32_t *rd, uint32_t *tab,
   l2 = Lead{0, 0xffffffffu};
   l3 = Lead{0, 0xffffffffu};
   l4 = Lead{0, 0xffffffffu};
-  const int n_chunks = L / 48;
+  const int n_groups = L / 12;
 #pragma unroll 1
-  for (int c = 0; c < n_chunks; c++) {
-    const uint32_t w0 = rd[(3 * c) * 32], w1 = rd[(3 * c + 1) * 32], w2 = rd[(3 * c + 2) * 32];
-    count_group<0>(w0, w1, w2, tab, lut, l2, l3, l4);
-    count_group<1>(w0, w1, w2, tab, lut, l2, l3, l4);
-    count_group<2>(w0, w1, w2, tab, lut, l2, l3, l4);
-    count_group<3>(w0, w1, w2, tab, lut, l2, l3, l4);
+  for (int g = 0; g < n_groups; g++) {
+    const uint32_t bit = 24u * g;
+    const uint32_t x = __funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 8;  // the group's 24 bits
+    const uint32_t a0 = lut[kLut2 + (x >> 20)], a1 = lut[kLut2 + ((x >> 16) & 15u)], a2 = lut[kLut2 + ((x >> 12) & 15u)],
+                   a3 = lut[kLut2 + ((x >> 8) & 15u)], a4 = lut[kLut2 + ((x >> 4) & 15u)], a5 = lut[kLut2 + (x & 15u)];
+    const uint32_t b0 = lut[kLut3 + (x >> 18)], b1 = lut[kLut3 + ((x >> 12) & 63u)], b2 = lut[kLut3 + ((x >> 6) & 63u)],
+                   b3 = lut[kLut3 + (x & 63u)];
+    const uint32_t c0 = lut[kLut4 + (x >> 16)], c1 = lut[kLut4 + ((x >> 8) & 255u)], c2 = lut[kLut4 + (x & 255u)];
+    bump3(tab, a0, b0, c0, l2, l3, l4);
+    bump3(tab, a1, b1, c1, l2, l3, l4);
+    bump3(tab, a2, b2, c2, l2, l3, l4);
+    bump2(tab, a3, b3, l2, l3);
+    bump1(tab, a4, l2);
+    bump1(tab, a5, l2);
   }
-  // tail: the windows that start in the last, partial chunk
-  const int r2 = L / 2 - 24 * n_chunks, r3 = L / 3 - 16 * n_chunks, r4 = L / 4 - 12 * n_chunks;
-  const uint32_t *tw = rd + 3 * n_chunks * 32;
+  // tail: fewer than twelve bases left
+  const int r2 = L / 2 - 6 * n_groups, r3 = L / 3 - 4 * n_groups, r4 = L / 4 - 3 * n_groups;
+  const uint32_t base = 24u * n_groups;
 #pragma unroll 1
   for (int t = 0; t < r2; t++) {
     {
-      const uint32_t bit = 4u * t;
-      bump1(tab, lut[kLut2 + (__funnelshift_l(tw[((bit >> 5) + 1) * 32], tw[(bit >> 5) * 32], bit & 31u) >> 28)], l2);
+      const uint32_t bit = base + 4u * t;
+      bump1(tab, lut[kLut2 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 28)], l2);
     }
     if (t < r3) {
-      const uint32_t bit = 6u * t;
-      bump1(tab, lut[kLut3 + (__funnelshift_l(tw[((bit >> 5) + 1) * 32], tw[(bit >> 5) * 32], bit & 31u) >> 26)], l3);
+      const uint32_t bit = base + 6u * t;
+      bump1(tab, lut[kLut3 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 26)], l3);
     }
     if (t < r4) {
-      const uint32_t bit = 8u * t;
-      bump1(tab, lut[kLut4 + (__funnelshift_l(tw[((bit >> 5) + 1) * 32], tw[(bit >> 5) * 32], bit & 31u) >> 24)], l4);
+      const uint32_t bit = base + 8u * t;
+      bump1p(tab, lut[kLut4 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 24)], l4);
     }
   }
 }
 
 // one rung of the ladder (utils.nim:246-265) given this k's count result.  Returns false on `break`.
-__device__ __forceinline__ bool lane_decide(const uint32_t *rd, int L, int K, int M, uint32_t leader, int thr_p, int thr_giveup,
-                                            ScanState &st) {
+__device__ __forceinline__ bool lane_decide(const uint32_t *rd, uint32_t *tab, int L, int K, int M, uint32_t leader, int thr_p,
+                                            int thr_giveup, ScanState &st) {
   int score = M * K;
   if (score <= st.best) return !(M < thr_giveup);
-  const int c = lane_recount(rd, L, leader, K);
+  const int c = lane_recount(rd, tab, L, leader, K, 65536u / (uint32_t)K + 1u);
   score = c * K;
   if (score < st.best) return true;
   st.best = score;
@@ -702,14 +694,16 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
         const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
         const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
         const uint32_t lead2 = l2.off == 0xffffffffu ? 0xfu : (uint32_t)lut[kRev234 + (l2.off >> 7)];
-        bool go = lane_decide(rd, L, 2, l2.M, lead2, tp[0], tg[L], st);
+        bool go = lane_decide(rd, tab, L, 2, l2.M, lead2, tp[0], tg[L], st);
         if (go) {
           const uint32_t lead3 = l3.off == 0xffffffffu ? 0x3fu : (uint32_t)lut[kRev234 + (l3.off >> 7)];
-          go = lane_decide(rd, L, 3, l3.M, lead3, tp[kThrLen], tg[kThrLen + L], st);
+          go = lane_decide(rd, tab, L, 3, l3.M, lead3, tp[kThrLen], tg[kThrLen + L], st);
         }
         if (go) {
-          const uint32_t lead4 = l4.off == 0xffffffffu ? 0xffu : (uint32_t)lut[kRev234 + (l4.off >> 7)];
-          go = lane_decide(rd, L, 4, l4.M, lead4, tp[2 * kThrLen], tg[2 * kThrLen + L], st);
+          const uint32_t lead4 = l4.off == 0xffffffffu
+                                     ? 0xffu
+                                     : (uint32_t)lut[kRev234 + kCls2 + kCls3 + ((l4.off >> 7) - (kCls2 + kCls3)) * 4 + ((l4.off & 31u) >> 3)];
+          go = lane_decide(rd, tab, L, 4, l4.M, lead4, tp[2 * kThrLen], tg[2 * kThrLen + L], st);
         }
         if (go) to5 = true;
         else emit_result(out, s, st);
@@ -735,7 +729,7 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
         uint32_t leader;
         lane_count5(rd, tab, lut, L, M, leader);
         const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-        const bool go = lane_decide(rd, L, 5, M, leader, thr[(size_t)(pclass * 5 + 3) * kThrLen + L], tg[3 * kThrLen + L], st);
+        const bool go = lane_decide(rd, tab, L, 5, M, leader, thr[(size_t)(pclass * 5 + 3) * kThrLen + L], tg[3 * kThrLen + L], st);
         if (go) to6 = true;
         else emit_result(out, s, st);
       }
@@ -765,7 +759,8 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
 }  // namespace
 
 // Class LUTs of the lane kernel (uint16 each, kLutTotal entries):
-//   [kLut2, kLut3, kLut4)  byte offset of the counter of every 2/3/4-mer code's min-rotation class in the lane's column,
+//   [kLut2, kLut3)         byte offset of the uint32 counter of every 2/3-mer code's min-rotation class in the lane's column,
+//   [kLut4)                for 4-mer codes: word byte offset | bit shift of the class's packed uint8 counter,
 //   [kRev234)              canonical (minimal) code of each of the 10 + 24 + 70 classes,
 //   [kLut5)                for 5-mer codes: (class / 4) * 128 | (class % 4) * 8 (word offset | bit shift of its uint8 counter),
 //   [kRev5)                canonical code of each of the 208 5-mer classes.
@@ -791,7 +786,8 @@ void build_lane_luts(uint16_t *dst) {
       const uint16_t m = (uint16_t)canon((uint32_t)code);
       int cls = 0;
       while (dst[rev_off[k] + cls] != m) cls++;
-      dst[lut_off[k] + code] = (k < 5) ? (uint16_t)((cls_base[k] + cls) * 128) : (uint16_t)(((cls >> 2) * 128) | ((cls & 3) * 8));
+      if (k < 4) dst[lut_off[k] + code] = (uint16_t)((cls_base[k] + cls) * 128);
+      else dst[lut_off[k] + code] = (uint16_t)(((cls_base[k] + (cls >> 2)) * 128) | ((cls & 3) * 8));  // packed uint8 counters
     }
   }
 }
@@ -812,7 +808,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
       configured = true;
     }
     const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
-    uint32_t grid = (uint32_t)sm_count * 3u;  // 3 resident CTAs of 128 threads per SM (shared-memory bound)
+    uint32_t grid = (uint32_t)sm_count * 5u;  // 5 resident CTAs of 128 threads per SM (shared-memory bound)
     if (grid > tiles) grid = tiles;
     repeat_scan_lane<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr, d_luts, d_out,
                                                                      d_status);
