@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *_
 //     bases are finished one per warp by the compact warp-per-segment code.
 // Every warp owns its shared-memory region and its queues: there is no block-level barrier after start-up.
 // ================================================================================================
-constexpr int kLaneThreads = 128;
+constexpr int kLaneThreads = 640;               // one CTA of 20 independent warps per SM (shared-memory bound)
 constexpr int kLaneWarps = kLaneThreads / 32;
 constexpr int kLaneWords = 11;                 // ten words hold 160 bases; one more absorbs the re-alignment shift
 constexpr int kCls2 = 10, kCls3 = 24, kCls4 = 70, kCls5 = 208;
@@ -292,8 +292,9 @@ constexpr int kCls4Words = (kCls4 + 3) / 4;       // 4-mer classes are counted i
 constexpr int kTabWords = kCls2 + kCls3 + kCls4Words;  // 52 words per lane; k = 5 reuses them as 208 packed uint8
 constexpr int kLut2 = 0, kLut3 = 16, kLut4 = 80, kRev234 = 336, kLut5 = 440, kRev5 = 1464;  // offsets into the uint16 table
 constexpr int kLutTotal = 1672;
-constexpr int kQueueCap = 64;
-constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + 2 * kQueueCap * 3;
+constexpr int kQueueCap = 64;                  // a batch is taken at 32 entries and a stage adds at most 32
+constexpr int kQueueWords = kQueueCap * 4 + kQueueCap * 3 + kQueueCap * 3 + 32;  // QR (4 words/entry), Q5, Q6 (3), QW (1, cap 32)
+constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + kQueueWords;
 constexpr int kLaneSmemBytes = kLaneWarps * kWarpSmemWords * 4 + kLutTotal * 2 + 16;
 static_assert(sizeof(WarpScratch<512>) <= (size_t)kTabWords * 32 * 4, "warp scratch must fit in the warp's counter region");
 static_assert(kCls5 / 4 <= kTabWords, "k = 5 counters must fit");
@@ -631,53 +632,174 @@ __device__ __forceinline__ void lane_count5(const uint32_t *rd, uint32_t *tab, c
   leader = (lead == 0xffffffffu) ? 0x3ffu : (uint32_t)lut[kRev5 + (lead >> 7) * 4 + ((lead & 31u) >> 3)];
 }
 
-struct LaneQueue {  // warp-local FIFO of handed-on segments: {segment, best << 16 | rc, unit_code | unit_k << 16 | start_k << 24}
+// count(read, 6, counts[6]) for one lane: at most 26 windows, counted in an open-addressing table of 52 slots
+// ({canonical code + 1, count} per uint32 word of the lane's column); the min-rotation is taken in the ALU.
+__device__ __forceinline__ void lane_count6(const uint32_t *rd, uint32_t *tab, int L, int &M, uint32_t &leader) {
+#pragma unroll
+  for (int c = 0; c < kTabWords; c++) tab[c * 32] = 0;
+  M = 0;
+  leader = 0xfffu;
+  const int W = L / 6;
+#pragma unroll 1
+  for (int j = 0; j < W; j++) {
+    const uint32_t bit = 12u * j;
+    uint32_t x = __funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 20;
+    const uint32_t c = min_rotation<6>(x);
+    const uint32_t key = (c + 1u) << 16;
+    uint32_t h = (((c * 40503u) & 0xffffu) * (uint32_t)kTabWords) >> 16;
+    int cnt;
+    while (true) {
+      const uint32_t v = tab[h * 32];
+      if (v == 0u) { tab[h * 32] = key | 1u; cnt = 1; break; }
+      if ((v & 0xffff0000u) == key) { tab[h * 32] = v + 1u; cnt = (int)(v & 0xffffu) + 1; break; }
+      h = (h + 1u == (uint32_t)kTabWords) ? 0u : h + 1u;
+    }
+    if (cnt > M) { M = cnt; leader = c; }   // strict >: the earlier leader keeps ties
+  }
+}
+
+// Warp-local FIFOs of segments waiting for their next stage.  Entry words:
+//   0: segment index      1: best << 16 | repeat_count      2: unit_code | unit_k << 16 | next_k << 24
+//   3 (QR only): M3 | M4 << 8 | leader3 << 16 | leader4 << 22
+struct LaneQueue {
   uint32_t *buf;
   int n;
+  int stride;
 };
-__device__ __forceinline__ void queue_push(LaneQueue &q, bool want, int lane, uint32_t s, const ScanState &st, int start_k) {
+__device__ __forceinline__ void queue_push(LaneQueue &q, bool want, int lane, uint32_t s, const ScanState &st, int next_k,
+                                           uint32_t extra = 0) {
   const uint32_t m = __ballot_sync(kFull, want);
   if (want) {
-    const int i = q.n + __popc(m & ((1u << lane) - 1u));
-    q.buf[3 * i + 0] = s;
-    q.buf[3 * i + 1] = ((uint32_t)(st.best & 0xffff) << 16) | (uint32_t)(st.rc & 0xffff);
-    q.buf[3 * i + 2] = (st.unit_code & 0xffffu) | ((uint32_t)st.unit_k << 16) | ((uint32_t)start_k << 24);
+    uint32_t *e = q.buf + q.stride * (q.n + __popc(m & ((1u << lane) - 1u)));
+    e[0] = s;
+    if (q.stride > 1) {
+      e[1] = ((uint32_t)(st.best & 0xffff) << 16) | (uint32_t)(st.rc & 0xffff);
+      e[2] = (st.unit_code & 0xffffu) | ((uint32_t)st.unit_k << 16) | ((uint32_t)next_k << 24);
+    }
+    if (q.stride > 3) e[3] = extra;
   }
   q.n += __popc(m);
   __syncwarp();
 }
-__device__ __forceinline__ void queue_read(const LaneQueue &q, int i, uint32_t &s, ScanState &st, int &start_k) {
-  s = q.buf[3 * i + 0];
-  const uint32_t a = q.buf[3 * i + 1], b = q.buf[3 * i + 2];
+__device__ __forceinline__ void queue_read(const LaneQueue &q, int i, uint32_t &s, ScanState &st, int &next_k, uint32_t &extra) {
+  const uint32_t *e = q.buf + q.stride * i;
+  s = e[0];
+  const uint32_t a = e[1], b = e[2];
   st.best = (int)(int16_t)(a >> 16);
   st.rc = (int)(a & 0xffffu);
   st.unit_code = b & 0xffffu;
   st.unit_k = (int)((b >> 16) & 0xffu);
-  start_k = (int)(b >> 24);
+  next_k = (int)(b >> 24);
+  extra = q.stride > 3 ? e[3] : 0u;
 }
 
-__global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
-                                                                 const strgpu_segment *__restrict__ segs, uint32_t n_seg,
-                                                                 const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
-                                                                 strgpu_repeat *__restrict__ out, int *status) {
+__global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
+                                                                    const strgpu_segment *__restrict__ segs, uint32_t n_seg,
+                                                                    const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
+                                                                    strgpu_repeat *__restrict__ out, int *status) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kLaneWarps * kWarpSmemWords);
   for (int i = tid; i < kLutTotal; i += kLaneThreads) lut[i] = luts[i];
   __syncthreads();
   uint32_t *warp_base = smem + warp * kWarpSmemWords;
-  uint32_t *tab = warp_base + lane;                      // [class][lane] counters; warp scratch for the k = 6 hand-offs
+  uint32_t *tab = warp_base + lane;                      // [class][lane] counters; warp scratch for the warp path
   uint32_t *rd = warp_base + kTabWords * 32 + lane;      // [word][lane] read columns
-  LaneQueue q5{warp_base + kTabWords * 32 + kLaneWords * 32, 0};
-  LaneQueue q6{q5.buf + 3 * kQueueCap, 0};
+  uint32_t *qmem = warp_base + kTabWords * 32 + kLaneWords * 32;
+  LaneQueue qr{qmem, 0, 4};
+  LaneQueue q5{qmem + kQueueCap * 4, 0, 3};
+  LaneQueue q6{qmem + kQueueCap * 7, 0, 3};
+  LaneQueue qw{qmem + kQueueCap * 10, 0, 1};
   const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
   const uint32_t n_groups = (n_seg + 31) / 32;
   const uint32_t warps_total = gridDim.x * kLaneWarps;
   uint32_t grp = blockIdx.x * kLaneWarps + warp;
+  // Queue discipline (capacity 64 each): at the top of an iteration qr, q5 <= 63 and q6 < 32.  Downstream stages run
+  // before upstream ones, and {5, 6} run once more after R, so no push can overflow: R adds <= 32 to q5 (< 32 by then),
+  // stage 5 adds <= 32 to q6 (< 32 by then), stage A adds <= 32 to qr and q5 (both < 32 by then).
   while (true) {
     const bool more = grp < n_groups;
+#pragma unroll 1
+    for (int rep = 0; rep < 2; rep++) {
+      if (rep == 1) {
+        // ---- stage R: the k = 3 / k = 4 rungs that need a recount, 32 segments at a time
+        if (qr.n >= 32 || (!more && qr.n > 0)) {
+          const int nb = qr.n < 32 ? qr.n : 32;
+          const int first = qr.n - nb;
+          uint32_t s = 0, extra = 0;
+          ScanState st{-1, 0u, 0, 0};
+          int k = 0;
+          bool to5 = false;
+          if (lane < nb) {
+            queue_read(qr, first + lane, s, st, k, extra);
+            const strgpu_segment sg = segs[s];
+            const int L = sg.len;
+            lane_stage(seq, sg, rd);
+            const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+            bool go = true;
+            for (; go && k <= 4; k++) {  // one call site: lanes at k = 3 and k = 4 recount together
+              const int M = k == 3 ? (int)(extra & 0xffu) : (int)((extra >> 8) & 0xffu);
+              const uint32_t leader = k == 3 ? ((extra >> 16) & 0x3fu) : ((extra >> 22) & 0xffu);
+              go = lane_decide(rd, tab, L, k, M, leader, thr[(size_t)(pclass * 5 + k - 2) * kThrLen + L], tg[(k - 2) * kThrLen + L], st);
+            }
+            if (go) to5 = true;
+            else emit_result(out, s, st);
+          }
+          __syncwarp();
+          qr.n = first;
+          queue_push(q5, to5, lane, s, st, 5);
+        }
+      }
+      // ---- stage 5: k = 5 with packed uint8 counters
+      if (q5.n >= 32 || (!more && qr.n == 0 && q5.n > 0)) {
+        const int nb = q5.n < 32 ? q5.n : 32;
+        const int first = q5.n - nb;
+        uint32_t s = 0, extra = 0;
+        ScanState st{-1, 0u, 0, 0};
+        int k = 0;
+        bool to6 = false;
+        if (lane < nb) {
+          queue_read(q5, first + lane, s, st, k, extra);
+          const strgpu_segment sg = segs[s];
+          const int L = sg.len;
+          lane_stage(seq, sg, rd);
+          int M;
+          uint32_t leader;
+          lane_count5(rd, tab, lut, L, M, leader);
+          const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+          const bool go = lane_decide(rd, tab, L, 5, M, leader, thr[(size_t)(pclass * 5 + 3) * kThrLen + L], tg[3 * kThrLen + L], st);
+          if (go) to6 = true;
+          else emit_result(out, s, st);
+        }
+        __syncwarp();
+        q5.n = first;
+        queue_push(q6, to6, lane, s, st, 6);
+      }
+      // ---- stage 6: k = 6 in an open-addressing table; the ladder ends here
+      if (q6.n >= 32 || (!more && qr.n == 0 && q5.n == 0 && q6.n > 0)) {
+        const int nb = q6.n < 32 ? q6.n : 32;
+        const int first = q6.n - nb;
+        if (lane < nb) {
+          uint32_t s, extra;
+          ScanState st;
+          int k;
+          queue_read(q6, first + lane, s, st, k, extra);
+          const strgpu_segment sg = segs[s];
+          const int L = sg.len;
+          lane_stage(seq, sg, rd);
+          int M;
+          uint32_t leader;
+          lane_count6(rd, tab, L, M, leader);
+          const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+          lane_decide(rd, tab, L, 6, M, leader, thr[(size_t)(pclass * 5 + 4) * kThrLen + L], tg[4 * kThrLen + L], st);
+          emit_result(out, s, st);
+        }
+        __syncwarp();
+        q6.n = first;
+      }
+    }
     if (more) {
-      // ---- stage A: k = 2, 3, 4 for the next 32 segments
+      // ---- stage A: count k = 2, 3, 4; k = 2 decision (its recount is warp-uniform); later rungs as far as they need no recount
       const uint32_t s = grp * 32 + lane;
       grp += warps_total;
       const bool active = s < n_seg;
@@ -686,7 +808,8 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
       const int L = sg.len;
       const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
       ScanState st{-1, 0u, 0, 0};
-      bool to5 = false;
+      int next_k = 0;  // 0: finished, 3 / 4: needs that rung's recount (QR), 5: goes on to k = 5
+      uint32_t extra = 0;
       if (lane_path) {
         lane_stage(seq, sg, rd);
         Lead l2, l3, l4;
@@ -694,65 +817,41 @@ __global__ void __launch_bounds__(kLaneThreads) repeat_scan_lane(const uint32_t 
         const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
         const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
         const uint32_t lead2 = l2.off == 0xffffffffu ? 0xfu : (uint32_t)lut[kRev234 + (l2.off >> 7)];
+        const uint32_t lead3 = l3.off == 0xffffffffu ? 0x3fu : (uint32_t)lut[kRev234 + (l3.off >> 7)];
+        const uint32_t lead4 = l4.off == 0xffffffffu
+                                   ? 0xffu
+                                   : (uint32_t)lut[kRev234 + kCls2 + kCls3 + ((l4.off >> 7) - (kCls2 + kCls3)) * 4 + ((l4.off & 31u) >> 3)];
+        extra = (uint32_t)l3.M | ((uint32_t)l4.M << 8) | (lead3 << 16) | (lead4 << 22);
         bool go = lane_decide(rd, tab, L, 2, l2.M, lead2, tp[0], tg[L], st);
         if (go) {
-          const uint32_t lead3 = l3.off == 0xffffffffu ? 0x3fu : (uint32_t)lut[kRev234 + (l3.off >> 7)];
-          go = lane_decide(rd, tab, L, 3, l3.M, lead3, tp[kThrLen], tg[kThrLen + L], st);
+          if (3 * l3.M > st.best) next_k = 3;                       // needs the k = 3 recount
+          else go = !(l3.M < (int)tg[kThrLen + L]);
         }
-        if (go) {
-          const uint32_t lead4 = l4.off == 0xffffffffu
-                                     ? 0xffu
-                                     : (uint32_t)lut[kRev234 + kCls2 + kCls3 + ((l4.off >> 7) - (kCls2 + kCls3)) * 4 + ((l4.off & 31u) >> 3)];
-          go = lane_decide(rd, tab, L, 4, l4.M, lead4, tp[2 * kThrLen], tg[2 * kThrLen + L], st);
+        if (go && next_k == 0) {
+          if (4 * l4.M > st.best) next_k = 4;                       // needs the k = 4 recount
+          else go = !(l4.M < (int)tg[2 * kThrLen + L]);
         }
-        if (go) to5 = true;
-        else emit_result(out, s, st);
+        if (go && next_k == 0) next_k = 5;
+        if (!go) emit_result(out, s, st);
       }
       __syncwarp();
-      queue_push(q5, to5, lane, s, st, 5);
-      queue_push(q6, active && !lane_path, lane, s, st, 2);
+      queue_push(qr, next_k == 3 || next_k == 4, lane, s, st, next_k, extra);
+      queue_push(q5, next_k == 5, lane, s, st, 5);
+      queue_push(qw, active && !lane_path, lane, s, st, 2);
     }
-    // ---- stage 5: k = 5 for up to 32 queued segments (full batches while input remains)
-    if (q5.n >= 32 || (!more && q5.n > 0)) {
-      const int nb = q5.n < 32 ? q5.n : 32;
-      const int first = q5.n - nb;   // take the newest nb entries; order between segments does not matter
-      uint32_t s = 0;
-      ScanState st{-1, 0u, 0, 0};
-      int start_k = 0;
-      bool to6 = false;
-      if (lane < nb) {
-        queue_read(q5, first + lane, s, st, start_k);
-        const strgpu_segment sg = segs[s];
-        const int L = sg.len;
-        lane_stage(seq, sg, rd);
-        int M;
-        uint32_t leader;
-        lane_count5(rd, tab, lut, L, M, leader);
-        const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-        const bool go = lane_decide(rd, tab, L, 5, M, leader, thr[(size_t)(pclass * 5 + 3) * kThrLen + L], tg[3 * kThrLen + L], st);
-        if (go) to6 = true;
-        else emit_result(out, s, st);
-      }
-      __syncwarp();
-      q5.n = first;
-      queue_push(q6, to6, lane, s, st, 6);
-    }
-    // ---- k = 6 survivors, N-containing and long segments: one at a time on the whole warp
-    if (q6.n > 0) {
+    // ---- segments with non-ACGT bases or longer than 160 bases: one at a time on the whole warp
+    if (qw.n > 0) {
       WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(warp_base);
       for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
       __syncwarp();
-      for (int e = 0; e < q6.n; e++) {
-        uint32_t s;
-        ScanState st;
-        int start_k;
-        queue_read(q6, e, s, st, start_k);
-        warp_scan_compact(ws, seq, nmask, segs[s], s, thr, lane, start_k, st, out, status);
+      for (int e = 0; e < qw.n; e++) {
+        const uint32_t s = qw.buf[e];
+        warp_scan_compact(ws, seq, nmask, segs[s], s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
       }
       __syncwarp();
-      q6.n = 0;
+      qw.n = 0;
     }
-    if (!more && q5.n == 0) break;
+    if (!more && qr.n == 0 && q5.n == 0 && q6.n == 0) break;
   }
 }
 
@@ -808,7 +907,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
       configured = true;
     }
     const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
-    uint32_t grid = (uint32_t)sm_count * 5u;  // 5 resident CTAs of 128 threads per SM (shared-memory bound)
+    uint32_t grid = (uint32_t)sm_count;  // one persistent CTA of 20 warps per SM
     if (grid > tiles) grid = tiles;
     repeat_scan_lane<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr, d_luts, d_out,
                                                                      d_status);
