@@ -339,7 +339,36 @@ __device__ __noinline__ int lane_recount(const uint32_t *rd, uint32_t *scratch, 
     for (int i = 0; i < 10; i++) c += __popc(m[i]);
     return c;
   }
-  // self-overlapping pattern (homopolymers, ACAC..): walk the runs of consecutive match positions
+  if (K == 2) {
+    // Self-overlap at K = 2 means a homopolymer pattern XX.  Matches then form runs of consecutive positions and the
+    // greedy walk takes every other one from each run's start: ceil(r / 2) = the run's positions that share the
+    // parity of its start.  Runs that start on even positions are isolated with one multi-word add (the carry
+    // runs through exactly those runs), so the count is two popcounts per word instead of a serial walk.
+    uint32_t f[10], sel = 0;
+    int cy = 0;
+    c = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {            // LSB-first: position p of word i -> bits 2p, 2p+1 (both set for a match)
+      const uint32_t r = __brev(m[i]);        // match bit of position p now at bit 2p + 1
+      f[i] = r | (r >> 1);
+    }
+    uint32_t prev_top = 0;                     // was the last position of the previous word a match?
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      const uint32_t prevm = (f[i] << 2) | (prev_top ? 3u : 0u);   // match state of position p - 1
+      const uint32_t starts = f[i] & ~prevm & 0x55555555u;          // low bit of each run's first position
+      const uint32_t es = starts & 0x11111111u;                     // runs starting on an even position
+      const unsigned long long sum = (unsigned long long)f[i] + es + (unsigned)cy;
+      cy = (int)(sum >> 32);
+      const uint32_t even_runs = f[i] & ~(uint32_t)sum;             // every bit of a run that started even (carry cleared it)
+      const uint32_t odd_runs = f[i] & (uint32_t)sum;               // (a carry entering from the previous word continues a run)
+      sel = (even_runs & 0x11111111u) | (odd_runs & 0x44444444u);   // even-start runs count even positions, odd-start odd ones
+      c += __popc(sel);
+      prev_top = f[i] >> 31;
+    }
+    return c;
+  }
+  // other self-overlapping patterns (ACAC.., AAA.. at k >= 3): walk the runs of consecutive match positions
 #pragma unroll
   for (int i = 0; i < 10; i++) scratch[i * 32] = m[i];
   int next = 0;  // first position the greedy walk may use
