@@ -320,3 +320,55 @@ def call_clusters(data: bytes, frag_dist=None, min_support=5, min_clip=0, min_cl
     mcd = int(0.5 * float(orc.median(frag, 0.5))) & 0xFFFF
     b, unplaced = orc.cluster_all(u["treads"], window, min_support, min_clip, min_clip_total, mcd, merge_mode=False)
     return [bounds_line(x, targets) for x in b], unplaced, targets
+
+
+# ------------------------------------------------------------------------------------------------ strling index
+def _trim(start, stop, repeat: str, dna: str):  # genome_strs.nim:22-59
+    assert len(dna) == stop - start
+    k = len(repeat)
+    expected = int(orc.slide_by(repeat, k)[0])
+    for enc in orc.slide_by(dna, k):
+        if int(enc) != expected:
+            start += k
+        else:
+            break
+    assert start < stop, "repeat not found in expected region"
+    expected = int(orc.slide_by(repeat[::-1], k)[0])
+    for enc in orc.slide_by(dna[::-1], k):
+        if int(enc) != expected:
+            stop -= k
+        else:
+            break
+    assert start < stop, "repeat not found in expected region"
+    return start, stop
+
+
+def genome_repeat_lines(chroms, proportion_repeat=0.8, window_size=100, step=60):
+    """repeat_windows + the bed lines genome_repeats writes (genome_strs.nim:61-92,121-125).  chroms: [(name, seq)]."""
+    lines = []
+    for name, seq in chroms:
+        seq = seq.upper()
+        L = len(seq)
+        last = None  # [start, stop, repeat]
+
+        def flush(w):
+            if w is not None and w[1] - w[0] >= (window_size - step):
+                a = max(0, w[0] - window_size)
+                b = min(w[1] + window_size, L)
+                s2, e2 = _trim(a, b, w[2], seq[a:b])
+                lines.append(f"{name}\t{s2}\t{e2}\t{w[2]}")
+
+        start = 0
+        while start < L:
+            dna = seq[start:min(L, start + window_size)]
+            unit, rc = orc.get_repeat(dna, proportion_repeat)
+            if rc > 0:
+                w = [start, start + len(dna), unit.decode()]
+                if last is None or last[2] != w[2] or w[0] > last[1] + (window_size - step):
+                    flush(last)
+                    last = w
+                else:
+                    last[1] = w[1]
+            start += step
+        flush(last)
+    return lines

@@ -57,6 +57,8 @@ def lib():
         L.orc_get_repeat_batch.restype = None
         L.orc_count.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.orc_count.restype = C.c_int
+        L.orc_slide_by.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_slide_by.restype = C.c_int
         L.orc_reduce_repeat.argtypes = [C.c_char_p]
         L.orc_reduce_repeat.restype = C.c_int
         L.orc_min_rev_complement.argtypes = [C.c_char_p]
@@ -115,6 +117,13 @@ def get_repeat_batch(seqs: np.ndarray, off: np.ndarray, length: np.ndarray, p: n
     lib().orc_get_repeat_batch(seqs.ctypes.data, off.ctypes.data, length.ctypes.data, p.ctypes.data, n,
                                units.ctypes.data, counts.ctypes.data)
     return units, counts
+
+
+def slide_by(read, k: int) -> np.ndarray:
+    r = read.encode() if isinstance(read, str) else bytes(read)
+    out = np.zeros(max(1, len(r) // max(k, 1) + 1), dtype=np.uint64)
+    n = lib().orc_slide_by(r, len(r), k, out.ctypes.data, len(out))
+    return out[:n]
 
 
 def count(read, k: int):

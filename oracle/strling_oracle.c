@@ -85,6 +85,25 @@ static int count_k(const char *s, int len, int k, orc_seq *cnt) {
   return (int)cnt->A[cnt->imax];
 }
 
+int orc_slide_by(const char *s, int len, int k, uint64_t *out, int cap) { /* utils.nim:10-34, literal */
+  int n = 0;
+  if (k <= len && k > 0) {
+    uint64_t f = kmer_encode(s, k);
+    uint64_t kmin = f;
+    for (int j = 0; j < k; j++) { kmer_forward_add(&f, s[j], k); if (f < kmin) kmin = f; }
+    if (n < cap) out[n] = kmin;
+    n++;
+    for (int i = k; i <= (len - 1) - k + 1; i += k) {
+      for (int m = 0; m < k; m++) kmer_forward_add(&f, s[i + m], k);
+      kmin = f;
+      for (int j = 0; j < k; j++) { kmer_forward_add(&f, s[i + j], k); if (f < kmin) kmin = f; }
+      if (n < cap) out[n] = kmin;
+      n++;
+    }
+  }
+  return n;
+}
+
 int orc_count(const char *read, int len, int k, uint64_t *leader) {
   if (!g_counts_init) counts_init();
   int c = count_k(read, len, k, &g_counts[k]);

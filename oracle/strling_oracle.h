@@ -66,6 +66,8 @@ void orc_get_repeat_batch(const char *seqs, const uint64_t *off, const uint32_t 
                           uint64_t n, char *out_unit, int32_t *out_count);
 /* utils.nim:205-211 + :197 : max multiplicity and leader code of min-rotation k-mers (leader = UINT64_MAX if no window) */
 int  orc_count(const char *read, int len, int k, uint64_t *leader);
+/* utils.nim:10-34 : every window's min-rotation code; returns the number of windows (writes at most cap) */
+int  orc_slide_by(const char *s, int len, int k, uint64_t *out, int cap);
 /* utils.nim:220-233 */
 int  orc_reduce_repeat(char rep[6]);
 /* utils.nim:61-80 */

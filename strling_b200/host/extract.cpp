@@ -352,16 +352,35 @@ int extract_run(const ExtractArgs &a) {
   BamReader rd(a.bam, a.threads);
   ex.targets = &rd.targets();
   std::unordered_map<std::string, Intervals> genome_str;
+  // genome_repeats (genome_strs.nim:107-141): use the -g bed if it exists, otherwise build it from the fasta
+  // (into -g when given, else only in memory -- the reference uses a temporary file)
+  bool have_bed = false;
   if (!a.genome_repeats.empty()) {
     std::ifstream probe(a.genome_repeats);
-    if (!probe)
-      throw std::runtime_error("[strling] genome repeats file " + a.genome_repeats +
-                               " does not exist; building it (`strling index`) is not part of this build");
+    have_bed = (bool)probe;
+  }
+  if (have_bed) {
     std::fprintf(stderr, "[strling] using existing file %s for genome repeats\n", a.genome_repeats.c_str());
     genome_str = read_bed(a.genome_repeats);
+  } else if (!a.fasta.empty()) {
+    const std::vector<std::string> lines = genome_repeat_lines(a.fasta, a.proportion_repeat, a.device);
+    std::fprintf(stderr, "[strling] found %zu STR-like regions in the genome\n", lines.size());
+    std::string path = a.genome_repeats;
+    const bool tmp = path.empty();
+    if (tmp) path = a.bin + ".genome_repeats.tmp";
+    {
+      std::ofstream out(path);
+      if (!out) throw std::runtime_error("[strling] couldn't open bed file: " + path + " for writing");
+      for (const auto &l : lines) out << l << "\n";
+    }
+    genome_str = read_bed(path);
+    if (tmp) std::remove(path.c_str());
   } else {
-    std::fprintf(stderr, "[strling] no -g genome repeats file: every read is scanned (the reference would build the STR index from the fasta first)\n");
+    if (!a.genome_repeats.empty())
+      throw std::runtime_error("[strling] genome repeats file " + a.genome_repeats + " does not exist and no -f fasta was given to build it");
+    std::fprintf(stderr, "[strling] no -f fasta / -g genome repeats: every read is scanned (the reference requires -f)\n");
   }
+  std::fprintf(stderr, "[strling] got STR repeats from genome into an interval tree\n");
   ex.genome_str_by_tid.assign(rd.targets().size(), nullptr);
   for (size_t t = 0; t < rd.targets().size(); t++) {
     auto it = genome_str.find(rd.targets()[t].name);

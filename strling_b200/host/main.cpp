@@ -12,6 +12,7 @@ int main(int argc, char **argv) {
       "strling-b200 (STRling 0.6.0 hot path on B200)\n\nCommands:\n"
       "  extract       :   extract informative STR reads from a BAM (repeat-unit scan on the GPU)\n"
       "  merge         :   merge putative STR loci from multiple samples (clustering on the GPU)\n"
+      "  index         :   find STR-like regions of a reference genome (the genome-repeats file of extract -g)\n"
       "  call          :   discover STR loci of one sample (clustering on the GPU; no genotypes in this build)\n";
   if (argc < 2 || !std::strcmp(argv[1], "-h") || !std::strcmp(argv[1], "--help")) {
     std::fputs(usage, stdout);
@@ -22,6 +23,7 @@ int main(int argc, char **argv) {
     if (cmd == "extract") return strling::extract_main(argc - 2, argv + 2);
     if (cmd == "merge") return strling::merge_main(argc - 2, argv + 2);
     if (cmd == "call") return strling::call_main(argc - 2, argv + 2);
+    if (cmd == "index") return strling::index_main(argc - 2, argv + 2);
     if (cmd == "debug") return strling::debug_main(argc - 2, argv + 2);
     if (cmd == "--version" || cmd == "version") { std::printf("%s\n", strgpu_version()); return 0; }
     std::fprintf(stderr, "unknown program '%s'\n%s", cmd.c_str(), usage);

@@ -136,6 +136,57 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
     assert got == [l for l in all_lines if l.split("\t")[0] == targets[2][0]] and len(got) > 0
 
 
+def _random_genome(seed, targets):
+    rng = np.random.default_rng(seed)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, size=n))
+
+    chroms = []
+    for name, ln in targets:
+        parts, used = [], 0
+        while used < ln:
+            n = int(rng.integers(200, 3000))
+            parts.append(rnd(n))
+            unit = ["CAG", "A", "AC", "AAAG", "ATTCT", "CACGAT", "GGC", "T"][int(rng.integers(0, 8))]
+            rep = unit * int(rng.integers(5, 90))
+            if rng.random() < 0.3:
+                rep = rep.lower()            # soft-masked reference sequence is upper-cased first (genome_strs.nim:72)
+            if rng.random() < 0.2:
+                rep = rep[: len(rep) // 2] + "N" * int(rng.integers(1, 40)) + rep[len(rep) // 2:]
+            parts.append(rep)
+            used += n + len(rep)
+        chroms.append((name, "".join(parts)[:ln]))
+    return chroms
+
+
+def test_index_matches_oracle_and_feeds_extract(cli, tmp_path):
+    # `strling index` (genome_strs.nim:61-131): 100-bp windows, step 60, merge + trim -> bed of STR-like regions
+    targets = [("chr1", 60_000), ("chr2", 45_000), ("chrS", 130)]
+    chroms = _random_genome(3, targets)
+    fasta = str(tmp_path / "ref.fa")
+    with open(fasta, "w") as fh:
+        for name, seq in chroms:
+            fh.write(f">{name} some description\n")
+            for i in range(0, len(seq), 60):
+                fh.write(seq[i:i + 60] + "\n")
+    bed = str(tmp_path / "ref.fa.str")
+    run(cli, "index", "-g", bed, fasta)
+    exp = eo.genome_repeat_lines(chroms, 0.8)
+    got = open(bed).read().splitlines()
+    assert len(exp) > 20 and got == exp
+    # extract without an existing -g file builds the same index first (genome_strs.nim:117-128) and then filters with it
+    loci = [(0, 10_000, 10_150, "CAG"), (1, 20_000, 20_090, "AAAG")]
+    recs = bamio.simulate_alignments(11, 4000, targets[:2], loci, unmapped_pairs=30)
+    hdr = bamio.sam_header(targets[:2])
+    bam, out, bed2 = str(tmp_path / "x.bam"), str(tmp_path / "x.bin"), str(tmp_path / "built.str")
+    bamio.write_bam(bam, hdr, targets[:2], recs)
+    run(cli, "extract", "-f", fasta, "-g", bed2, bam, out)
+    assert open(bed2).read().splitlines() == exp
+    expected_bin, cache, _ = eo.extract(recs, targets[:2], hdr, 0.8, 40, eo.read_bed(bed2))
+    assert open(out, "rb").read() == expected_bin and len(cache) > 100
+
+
 def test_cli_errors(cli, tmp_path):
     r = subprocess.run([cli, "extract", str(tmp_path / "missing.bam"), str(tmp_path / "o.bin")], capture_output=True, text=True)
     assert r.returncode != 0 and "couldn't open bam" in r.stderr
