@@ -107,6 +107,16 @@ int strgpu_scan_wait(strgpu_ctx *ctx, int ticket);
 /* submit + wait */
 int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask,
                 const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len, strgpu_repeat *out);
+/* Uniform-read batches without descriptors (saves the 8 B/read of host-to-device traffic that whole-read descriptors
+ * cost): read i occupies bases [i * stride_bases, i * stride_bases + read_len) of seq2 and is scanned with
+ * proportion class `pclass`; stride_bases must be a multiple of 4 and read_len <= 160 (longer uniform reads are
+ * expanded into descriptors inside the library).  With nmask != NULL every read's mask bits are inspected on the
+ * device.  `extra` (may be NULL) are ordinary descriptors for the other segments of the batch (soft clips);
+ * out[0 .. n_reads) receives the reads' results, out[n_reads .. n_reads + n_extra) the extra segments'. */
+int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
+                             uint32_t pclass, const uint32_t *nmask, const strgpu_segment *extra, uint32_t n_extra,
+                             uint32_t extra_max_len, strgpu_repeat *out, int *ticket);
+
 /* Device-resident variant: all pointers are device pointers on ctx's device; the kernel is enqueued on
  * `cuda_stream` (a cudaStream_t, NULL = default stream) and the call returns without synchronising.
  * A too-long segment is reported by the next strgpu_device_status(). */

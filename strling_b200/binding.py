@@ -73,6 +73,7 @@ def load_library():
     L.strgpu_pack_ascii.argtypes = [vp, u32, vp, vp, u64]
     L.strgpu_pack_bam4.argtypes = [vp, u32, vp, vp, u64]
     L.strgpu_scan_submit.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp, C.POINTER(i32)]
+    L.strgpu_scan_reads_submit.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, u32, u32, vp, C.POINTER(i32)]
     L.strgpu_scan_wait.argtypes = [vp, i32]
     L.strgpu_scan.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp]
     L.strgpu_scan_device.argtypes = [vp, vp, vp, vp, u32, u32, vp, vp]
@@ -172,6 +173,16 @@ class StrGpu:
         t = C.c_int(-1)
         self._check(self.L.strgpu_scan_submit(self.h, seq2.ctypes.data, n_bases, None if nmask is None else nmask.ctypes.data,
                                               segs.ctypes.data, len(segs), max_len, out.ctypes.data, C.byref(t)))
+        return t.value
+
+    def scan_reads_submit(self, seq2, n_reads: int, read_len: int, stride_bases: int, pclass: int, nmask, extra, extra_max_len: int, out) -> int:
+        """Uniform whole reads without descriptors (+ optional explicit extra segments); results: reads first, then extras."""
+        t = C.c_int(-1)
+        n_extra = 0 if extra is None else len(extra)
+        self._check(self.L.strgpu_scan_reads_submit(self.h, seq2.ctypes.data, n_reads, read_len, stride_bases, pclass,
+                                                    None if nmask is None else nmask.ctypes.data,
+                                                    None if extra is None else extra.ctypes.data, n_extra, extra_max_len,
+                                                    out.ctypes.data, C.byref(t)))
         return t.value
 
     def scan_wait(self, ticket: int):

@@ -256,6 +256,72 @@ int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, c
   return STRGPU_OK;
 }
 
+int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
+                             uint32_t pclass, const uint32_t *nmask, const strgpu_segment *extra, uint32_t n_extra,
+                             uint32_t extra_max_len, strgpu_repeat *out, int *ticket) {
+  if (!ctx || !ticket || ((n_reads || n_extra) && (!seq2 || !out)) || (n_extra && !extra))
+    return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_submit: null argument");
+  if ((stride_bases & 3u) || stride_bases < read_len || pclass >= STRGPU_MAX_PCLASS)
+    return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_submit: stride %u / read_len %u / pclass %u", stride_bases, read_len, pclass);
+  if ((uint64_t)n_reads * stride_bases > 0xffffffffull) return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_submit: batch addresses more than 2^32 bases");
+  if (read_len > STRGPU_MAX_SEGMENT_LEN || extra_max_len > STRGPU_MAX_SEGMENT_LEN)
+    return fail(ctx, STRGPU_ERR_TOO_LONG, "read_len %u / extra_max_len %u > %d", read_len, extra_max_len, STRGPU_MAX_SEGMENT_LEN);
+  if (read_len > (uint32_t)strgpu::kShortMaxLen || extra_max_len > (uint32_t)strgpu::kShortMaxLen) {
+    // long reads: expand into ordinary descriptors on the host and take the general path
+    std::vector<strgpu_segment> all((size_t)n_reads + n_extra);
+    for (uint32_t i = 0; i < n_reads; i++) {
+      bool has_n = false;
+      if (nmask)
+        for (uint64_t b = (uint64_t)i * stride_bases; b < (uint64_t)i * stride_bases + read_len && !has_n; b++)
+          has_n = (nmask[b >> 5] >> (b & 31)) & 1u;
+      all[i] = strgpu_segment{i * stride_bases, (uint16_t)read_len, (uint8_t)pclass, (uint8_t)(has_n ? STRGPU_SEG_HAS_N : 0)};
+    }
+    for (uint32_t i = 0; i < n_extra; i++) all[n_reads + i] = extra[i];
+    return strgpu_scan_submit(ctx, seq2, (uint64_t)n_reads * stride_bases, nmask, all.data(), n_reads + n_extra,
+                              read_len > extra_max_len ? read_len : extra_max_len, out, ticket);
+  }
+  int si = -1;
+  for (int i = 0; i < STRGPU_SLOTS; i++)
+    if (!ctx->slots[i].busy) { si = i; break; }
+  if (si < 0) return fail(ctx, STRGPU_ERR_BUSY, "all %d submit slots in flight", STRGPU_SLOTS);
+  Slot &s = ctx->slots[si];
+  CU(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n_bases = (uint64_t)n_reads * stride_bases;
+  const size_t seq_bytes = (size_t)((n_bases + 3) / 4);
+  const size_t nm_bytes = nmask ? (size_t)((n_bases + 31) / 32) * 4 : 0;
+  const uint32_t n_seg = n_reads + n_extra;
+  int rc;
+  if ((rc = ensure(ctx, s.seq, seq_bytes + 16))) return rc;
+  if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
+  if ((rc = ensure(ctx, s.segs, (size_t)n_extra * sizeof(strgpu_segment) + 16))) return rc;
+  if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
+  s.n_seg = n_seg;
+  s.host_out = out;
+  if (n_seg) {
+    CU(ctx, cudaMemcpyAsync(s.seq.p, seq2, seq_bytes, cudaMemcpyHostToDevice, s.stream));
+    CU(ctx, cudaMemsetAsync((char *)s.seq.p + seq_bytes, 0, 16, s.stream));
+    if (nmask) {
+      CU(ctx, cudaMemcpyAsync(s.nmask.p, nmask, nm_bytes, cudaMemcpyHostToDevice, s.stream));
+      CU(ctx, cudaMemsetAsync((char *)s.nmask.p + nm_bytes, 0, 16, s.stream));
+    }
+    if (n_extra) CU(ctx, cudaMemcpyAsync(s.segs.p, extra, (size_t)n_extra * sizeof(strgpu_segment), cudaMemcpyHostToDevice, s.stream));
+    CU(ctx, cudaMemsetAsync(s.d_status, 0, sizeof(int), s.stream));
+    const strgpu::UniformReads u{n_reads, read_len, stride_bases, pclass};
+    CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
+                                       (const strgpu_segment *)s.segs.p, n_seg, read_len, ctx->d_thr, ctx->d_luts,
+                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, 0, s.stream, &u));
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
+    CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  } else {
+    *s.h_status = 0;
+  }
+  CU(ctx, cudaEventRecord(s.done, s.stream));
+  s.busy = true;
+  *ticket = si;
+  return STRGPU_OK;
+}
+
 int strgpu_scan_wait(strgpu_ctx *ctx, int ticket) {
   if (!ctx || ticket < 0 || ticket >= STRGPU_SLOTS || !ctx->slots[ticket].busy)
     return fail(ctx, STRGPU_ERR_TICKET, "scan_wait: bad ticket %d", ticket);

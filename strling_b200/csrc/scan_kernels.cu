@@ -722,8 +722,35 @@ __device__ __forceinline__ void queue_read(const LaneQueue &q, int i, uint32_t &
   extra = q.stride > 3 ? e[3] : 0u;
 }
 
+// Segment s of the batch: the first u.n_reads are implicit whole reads of one length on a fixed stride (no descriptor
+// is read; non-ACGT bases are detected from the mask itself), the rest come from the descriptor array.
+__device__ __forceinline__ strgpu_segment load_segment(const strgpu_segment *__restrict__ segs, const uint32_t *__restrict__ nmask,
+                                                       const UniformReads &u, uint32_t s) {
+  if (s >= u.n_reads) return segs[s - u.n_reads];
+  strgpu_segment sg;
+  sg.base_off = s * u.stride;
+  sg.len = (uint16_t)u.read_len;
+  sg.pclass = (uint8_t)u.pclass;
+  sg.flags = 0;
+  if (nmask != nullptr) {
+    uint32_t any = 0;
+    const uint32_t first = sg.base_off >> 5, last = (sg.base_off + u.read_len + 31u) >> 5;
+    for (uint32_t w = first; w < last; w++) {
+      uint32_t v = nmask[w];
+      if (w == first) v &= kFull << (sg.base_off & 31u);
+      const uint32_t end = sg.base_off + u.read_len;
+      if (w == (end >> 5) && (end & 31u)) v &= (1u << (end & 31u)) - 1u;
+      if (w > (end >> 5) || (w == (end >> 5) && !(end & 31u))) v = 0;
+      any |= v;
+    }
+    if (any) sg.flags = STRGPU_SEG_HAS_N;
+  }
+  return sg;
+}
+
 __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                     const strgpu_segment *__restrict__ segs, uint32_t n_seg,
+                                                                    const UniformReads u,
                                                                     const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
                                                                     strgpu_repeat *__restrict__ out, int *status) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -761,7 +788,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
           bool to5 = false;
           if (lane < nb) {
             queue_read(qr, first + lane, s, st, k, extra);
-            const strgpu_segment sg = segs[s];
+            const strgpu_segment sg = load_segment(segs, nmask, u, s);
             const int L = sg.len;
             lane_stage(seq, sg, rd);
             const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
@@ -789,7 +816,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
         bool to6 = false;
         if (lane < nb) {
           queue_read(q5, first + lane, s, st, k, extra);
-          const strgpu_segment sg = segs[s];
+          const strgpu_segment sg = load_segment(segs, nmask, u, s);
           const int L = sg.len;
           lane_stage(seq, sg, rd);
           int M;
@@ -813,7 +840,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
           ScanState st;
           int k;
           queue_read(q6, first + lane, s, st, k, extra);
-          const strgpu_segment sg = segs[s];
+          const strgpu_segment sg = load_segment(segs, nmask, u, s);
           const int L = sg.len;
           lane_stage(seq, sg, rd);
           int M;
@@ -833,7 +860,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
       grp += warps_total;
       const bool active = s < n_seg;
       strgpu_segment sg{0, 0, 0, 0};
-      if (active) sg = segs[s];
+      if (active) sg = load_segment(segs, nmask, u, s);
       const int L = sg.len;
       const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
       ScanState st{-1, 0u, 0, 0};
@@ -875,7 +902,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
       __syncwarp();
       for (int e = 0; e < qw.n; e++) {
         const uint32_t s = qw.buf[e];
-        warp_scan_compact(ws, seq, nmask, segs[s], s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
+        warp_scan_compact(ws, seq, nmask, load_segment(segs, nmask, u, s), s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
       }
       __syncwarp();
       qw.n = 0;
@@ -922,8 +949,15 @@ void build_lane_luts(uint16_t *dst) {
 
 cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
                                uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
-                               strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream) {
+                               strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,
+                               const UniformReads *uniform) {
   if (n_seg == 0) return cudaSuccess;
+  UniformReads u{0, 0, 0, 0};
+  if (uniform) {
+    u = *uniform;
+    if (u.read_len > (uint32_t)kShortMaxLen) return cudaErrorInvalidValue;  // callers expand long uniform reads into descriptors
+    variant = 0;
+  }
   constexpr int kWarps = 8;
   const uint32_t blocks_needed = (n_seg + kWarps - 1) / kWarps;
   if (max_len <= (uint32_t)kShortMaxLen && variant != 1) {
@@ -938,7 +972,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
     const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
     uint32_t grid = (uint32_t)sm_count;  // one persistent CTA of 20 warps per SM
     if (grid > tiles) grid = tiles;
-    repeat_scan_lane<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr, d_luts, d_out,
+    repeat_scan_lane<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out,
                                                                      d_status);
   } else if (max_len <= (uint32_t)kShortMaxLen) {
     uint32_t grid = (uint32_t)sm_count * 8u;  // 8 resident CTAs of 256 threads per SM

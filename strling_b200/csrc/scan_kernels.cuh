@@ -13,11 +13,17 @@ constexpr int kThrEntries = kThrClasses * 5 * kThrLen;
 constexpr int kShortMaxLen = 160;               // kernel variant with the read in <= 10 words
 
 // thr[(cls * 5 + (k - 2)) * kThrLen + len] = int(len * p_cls / k); cls == STRGPU_MAX_PCLASS holds int(len * 0.12 / k)
+// Implicit whole-read segments: read i = bases [i * stride, i * stride + read_len), proportion class pclass.
+struct UniformReads {
+  uint32_t n_reads, read_len, stride, pclass;
+};
+
 // variant: 0 = default (lane-per-segment kernel for batches of <= 160-base segments, warp-per-segment otherwise),
 //          1 = force the warp-per-segment kernel (kept for A/B measurements and as the long-segment path)
 cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
                                uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
-                               strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream);
+                               strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,
+                               const UniformReads *uniform = nullptr);
 
 constexpr int kLaneLutEntries = 1672;  // see build_lane_luts
 void build_lane_luts(uint16_t *dst);  // host: fills kLaneLutEntries uint16

@@ -156,3 +156,22 @@ def test_submit_wait_pipeline(gpu):
     flat, off, lens = synth.segment_ascii(reads, segs, stride)
     units, counts = oracle_for(flat, off, lens, segs["pclass"])
     assert np.array_equal(outs[0]["unit"], units) and np.array_equal(outs[0]["repeat_count"], counts)
+
+
+@pytest.mark.parametrize("length,n_frac", [(150, 0.0), (150, 0.05), (151, 0.02), (100, 0.0), (37, 0.1), (250, 0.02)])
+def test_uniform_reads_without_descriptors(gpu, length, n_frac):
+    # strgpu_scan_reads_submit: implicit whole-read segments (+ explicit clip segments) == the descriptor path == oracle
+    reads, cls, lclip, rclip = synth.make_reads(40_000, seed=length, length=length, mix=(0.7, 0.1, 0.1, 0.1), n_frac=n_frac)
+    lclip = np.minimum(lclip, length)
+    rclip = np.minimum(rclip, length)
+    seq2, nmask, stride = synth.pack_matrix(reads, align_bases=4)
+    assert stride % 4 == 0 and stride - length < 4
+    segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+    n = reads.shape[0]
+    extra = np.ascontiguousarray(segs[n:])
+    out = np.zeros(len(segs), dtype=sb.REPEAT_DTYPE)
+    t = gpu.scan_reads_submit(seq2, n, length, stride, 0, nmask, extra if len(extra) else None, int(extra["len"].max()) if len(extra) else 0, out)
+    gpu.scan_wait(t)
+    flat, off, lens = synth.segment_ascii(reads, segs, stride)
+    units, counts = oracle_for(flat, off, lens, segs["pclass"])
+    assert np.array_equal(out["unit"], units) and np.array_equal(out["repeat_count"], counts)
