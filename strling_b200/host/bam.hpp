@@ -1,7 +1,14 @@
 // BGZF + BAM reader for the host side of `strling extract` / `strling call` (stands in for htslib, which the
 // reference reaches through hts-nim: extract.nim:275-329).  Blocks are inflated in parallel batches (zlib).
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+
+#include <chrono>
+#include <cstdlib>
 
 #include <cstdint>
 #include <cstdio>
@@ -98,6 +105,12 @@ class BamReader {
       throw std::runtime_error("corrupt BAM record (field lengths)");
     cur_ += 4 + (size_t)block_size;
     return true;
+  }
+
+  // BGZF virtual offset of the next record (valid right after construction: the first record)
+  uint64_t tell() {
+    if (!ensure(1)) return (fpos_ << 16);
+    return voffset_at(cur_);
   }
 
   // restart iteration at a BGZF virtual offset previously taken from BamRecord::voffset
@@ -280,6 +293,253 @@ class BamReader {
   size_t cur_ = 0;
   std::string header_text_;
   std::vector<Target> targets_;
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// Chunked reader for the extract pipeline: hands out large buffers of WHOLE decoded records (the file is memory
+// mapped, BGZF blocks are inflated in parallel straight from the mapping) together with the record offsets, so that
+// staging can be spread over threads and the buffer's ownership can travel with the batch (record fields such as
+// qname are then used in place, never copied).
+struct RawBuffer {  // uninitialised, growable byte buffer (std::vector would zero-fill hundreds of MB per chunk)
+  uint8_t *p = nullptr;
+  size_t size = 0, cap = 0;
+  RawBuffer() = default;
+  RawBuffer(const RawBuffer &) = delete;
+  RawBuffer &operator=(const RawBuffer &) = delete;
+  RawBuffer(RawBuffer &&o) noexcept : p(o.p), size(o.size), cap(o.cap) { o.p = nullptr; o.size = o.cap = 0; }
+  RawBuffer &operator=(RawBuffer &&o) noexcept {
+    if (this != &o) { std::free(p); p = o.p; size = o.size; cap = o.cap; o.p = nullptr; o.size = o.cap = 0; }
+    return *this;
+  }
+  ~RawBuffer() { std::free(p); }
+  void resize(size_t n) {
+    if (n > cap) {
+      const size_t nc = n + n / 8 + 4096;
+      uint8_t *q = static_cast<uint8_t *>(std::realloc(p, nc));
+      if (!q) throw std::runtime_error("out of memory");
+      p = q;
+      cap = nc;
+    }
+    size = n;
+  }
+  uint8_t *data() { return p; }
+  const uint8_t *data() const { return p; }
+};
+
+struct BamChunk {
+  RawBuffer data;                   // decoded bytes; records [rec_off[i], rec_off[i+1])
+  std::vector<uint32_t> rec_off;    // n_records + 1 entries
+  struct Span { uint32_t begin; uint64_t coffset; uint32_t skip; };  // data[begin..] came from block coffset, starting `skip` bytes into it
+  std::vector<Span> spans;
+  size_t n_records() const { return rec_off.empty() ? 0 : rec_off.size() - 1; }
+  uint64_t voffset_of(size_t rec) const {
+    const uint32_t pos = rec_off[rec];
+    size_t lo = 0, hi = spans.size();
+    while (hi - lo > 1) {
+      const size_t mid = (lo + hi) / 2;
+      if (spans[mid].begin <= pos) lo = mid; else hi = mid;
+    }
+    return (spans[lo].coffset << 16) | (uint64_t)(pos - spans[lo].begin + spans[lo].skip);
+  }
+  static BamRecord view(const uint8_t *rec) {
+    BamRecord r;
+    const uint8_t *p = rec + 4;
+    std::memcpy(&r.tid, p, 4);
+    std::memcpy(&r.pos, p + 4, 4);
+    const uint8_t l_read_name = p[8];
+    r.mapq = p[9];
+    std::memcpy(&r.n_cigar, p + 12, 2);
+    std::memcpy(&r.flag, p + 14, 2);
+    std::memcpy(&r.l_seq, p + 16, 4);
+    std::memcpy(&r.mate_tid, p + 20, 4);
+    std::memcpy(&r.mate_pos, p + 24, 4);
+    std::memcpy(&r.isize, p + 28, 4);
+    r.qname = reinterpret_cast<const char *>(p + 32);
+    r.l_qname = l_read_name ? (uint32_t)l_read_name - 1 : 0;
+    r.cigar = reinterpret_cast<const uint32_t *>(p + 32 + l_read_name);
+    r.seq = p + 32 + l_read_name + 4 * (size_t)r.n_cigar;
+    r.voffset = 0;
+    return r;
+  }
+};
+
+class BamChunkReader {
+ public:
+  BamChunkReader(const std::string &path, uint64_t start_voffset, int threads) {
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) throw std::runtime_error("couldn't open bam");
+    struct stat st;
+    if (::fstat(fd_, &st) != 0) throw std::runtime_error("couldn't stat bam");
+    file_size_ = (size_t)st.st_size;
+    if (file_size_) {
+      map_ = static_cast<const uint8_t *>(::mmap(nullptr, file_size_, PROT_READ, MAP_PRIVATE, fd_, 0));
+      if (map_ == MAP_FAILED) throw std::runtime_error("couldn't mmap bam");
+      ::madvise(const_cast<uint8_t *>(map_), file_size_, MADV_SEQUENTIAL);
+    }
+    threads_ = threads > 0 ? threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    fpos_ = start_voffset >> 16;
+    first_skip_ = (uint32_t)(start_voffset & 0xffff);
+  }
+  ~BamChunkReader() {
+    if (map_ && map_ != MAP_FAILED) ::munmap(const_cast<uint8_t *>(map_), file_size_);
+    if (fd_ >= 0) ::close(fd_);
+  }
+  BamChunkReader(const BamChunkReader &) = delete;
+  BamChunkReader &operator=(const BamChunkReader &) = delete;
+
+  double t_read = 0, t_alloc = 0, t_inflate = 0, t_walk = 0;  // seconds spent per phase (diagnostics)
+
+  // Fills `c` with the next whole records (about max_blocks BGZF blocks); false at EOF.
+  bool next(BamChunk &c, size_t max_blocks) {
+    using clk = std::chrono::steady_clock;
+    const auto q0 = clk::now();
+    c.rec_off.clear();
+    c.spans.clear();
+    struct Blk { uint64_t in_off; uint32_t csize, isize; uint64_t fpos; };
+    std::vector<Blk> blks;
+    blks.reserve(max_blocks);
+    size_t total_out = 0;
+    while (blks.size() < max_blocks && fpos_ < file_size_) {
+      if (fpos_ + 18 > file_size_) throw std::runtime_error("truncated BGZF header");
+      const uint8_t *hdr = map_ + fpos_;
+      if (hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) throw std::runtime_error("not a BGZF file");
+      uint16_t xlen;
+      std::memcpy(&xlen, hdr + 10, 2);
+      if (fpos_ + 12 + xlen > file_size_) throw std::runtime_error("truncated BGZF header");
+      uint32_t bsize = 0;
+      for (size_t o = 0; o + 4 <= xlen;) {
+        const uint8_t *e = hdr + 12 + o;
+        uint16_t slen;
+        std::memcpy(&slen, e + 2, 2);
+        if (e[0] == 'B' && e[1] == 'C' && slen == 2) {
+          uint16_t bs;
+          std::memcpy(&bs, e + 4, 2);
+          bsize = (uint32_t)bs + 1;
+          break;
+        }
+        o += 4 + slen;
+      }
+      if (!bsize || bsize < (uint32_t)xlen + 20) throw std::runtime_error("BGZF block without BC field");
+      if (fpos_ + bsize > file_size_) throw std::runtime_error("truncated BGZF block");
+      const uint32_t csize = bsize - xlen - 12 - 8;
+      uint32_t isize;
+      std::memcpy(&isize, hdr + bsize - 4, 4);
+      blks.push_back(Blk{fpos_ + 12 + xlen, csize, isize, fpos_});
+      fpos_ += bsize;
+      total_out += isize;
+    }
+    const bool eof = fpos_ >= file_size_;
+    const auto q1 = clk::now();
+    // bytes of a record that straddled the previous chunk's end come first
+    const size_t base = carry_.size();
+    if (base + total_out > 0xfffffff0ull) throw std::runtime_error("BAM chunk too large");
+    c.data.resize(base + total_out);
+    if (base) std::memcpy(c.data.data(), carry_.data(), base);
+    for (const auto &sp : carry_spans_) c.spans.push_back(sp);
+    carry_.clear();
+    carry_spans_.clear();
+    std::vector<size_t> outoff(blks.size());
+    size_t o = base;
+    for (size_t i = 0; i < blks.size(); i++) {
+      outoff[i] = o;
+      o += blks[i].isize;
+    }
+    const auto q2 = clk::now();
+    uint8_t *out = c.data.data();
+    auto work = [&](size_t from, size_t to, std::string *err) {
+      z_stream zs;
+      for (size_t i = from; i < to; i++) {
+        if (blks[i].isize == 0) continue;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { *err = "inflateInit2"; return; }
+        zs.next_in = const_cast<uint8_t *>(map_ + blks[i].in_off);
+        zs.avail_in = blks[i].csize;
+        zs.next_out = out + outoff[i];
+        zs.avail_out = blks[i].isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) { *err = "inflate failed"; return; }
+      }
+    };
+    const int nt = (int)std::min<size_t>((size_t)threads_, (blks.size() + 7) / 8);
+    std::vector<std::string> errs((size_t)std::max(nt, 1));
+    if (nt <= 1) {
+      work(0, blks.size(), &errs[0]);
+    } else {
+      std::vector<std::thread> th;
+      const size_t per = (blks.size() + (size_t)nt - 1) / (size_t)nt;
+      for (int t = 0; t < nt; t++) {
+        const size_t a = (size_t)t * per, b = std::min(blks.size(), a + per);
+        if (a >= b) break;
+        th.emplace_back(work, a, b, &errs[(size_t)t]);
+      }
+      for (auto &x : th) x.join();
+    }
+    for (auto &e : errs)
+      if (!e.empty()) throw std::runtime_error("BGZF: " + e);
+    const auto q3 = clk::now();
+    for (size_t i = 0; i < blks.size(); i++)
+      if (blks[i].isize) c.spans.push_back(BamChunk::Span{(uint32_t)outoff[i], blks[i].fpos, 0});
+    size_t n = c.data.size;
+    // a stream opened at a virtual offset starts mid-block: drop the bytes before it
+    if (first_skip_ && !blks.empty()) {
+      const size_t drop = first_skip_;
+      if (drop > blks[0].isize) throw std::runtime_error("bad virtual offset");
+      std::memmove(out + base, out + base + drop, n - base - drop);
+      n -= drop;
+      bool first = true;
+      for (auto &sp : c.spans) {
+        if (sp.begin < base) continue;
+        if (first) { sp.skip = (uint32_t)drop; first = false; }
+        else sp.begin -= (uint32_t)drop;
+      }
+      first_skip_ = 0;
+    }
+    // walk the records; keep the incomplete tail for the next call
+    size_t pos = 0;
+    c.rec_off.reserve(n / 200 + 16);
+    while (pos + 4 <= n) {
+      int32_t block_size;
+      std::memcpy(&block_size, out + pos, 4);
+      if (block_size < 32) throw std::runtime_error("corrupt BAM record");
+      if (pos + 4 + (size_t)block_size > n) break;
+      c.rec_off.push_back((uint32_t)pos);
+      pos += 4 + (size_t)block_size;
+      __builtin_prefetch(out + pos + 512);
+    }
+    c.rec_off.push_back((uint32_t)pos);
+    if (pos < n) {
+      if (eof && blks.empty()) throw std::runtime_error("truncated BAM record at end of file");
+      carry_.assign(out + pos, out + n);
+      for (size_t i = 0; i < c.spans.size(); i++) {  // spans that cover the carried bytes, rebased to the carry buffer
+        const size_t sb = c.spans[i].begin;
+        const size_t se = (i + 1 < c.spans.size()) ? c.spans[i + 1].begin : n;
+        if (se <= pos) continue;
+        BamChunk::Span sp = c.spans[i];
+        if (sb < pos) { sp.skip += (uint32_t)(pos - sb); sp.begin = 0; }
+        else sp.begin = (uint32_t)(sb - pos);
+        carry_spans_.push_back(sp);
+      }
+    }
+    c.data.size = pos;
+    const auto q4 = clk::now();
+    t_read += std::chrono::duration<double>(q1 - q0).count();
+    t_alloc += std::chrono::duration<double>(q2 - q1).count();
+    t_inflate += std::chrono::duration<double>(q3 - q2).count();
+    t_walk += std::chrono::duration<double>(q4 - q3).count();
+    return c.n_records() > 0 || !eof || !carry_.empty();
+  }
+
+ private:
+  int fd_ = -1;
+  const uint8_t *map_ = nullptr;
+  size_t file_size_ = 0;
+  int threads_ = 1;
+  uint64_t fpos_ = 0;
+  uint32_t first_skip_ = 0;
+  std::vector<uint8_t> carry_;
+  std::vector<BamChunk::Span> carry_spans_;
 };
 
 }  // namespace strling

@@ -1,6 +1,8 @@
 // `strling debug ...`: CPU-only introspection of the host side (BAM decode, `.bin` codec, pair arithmetic) so that
 // tests can compare it with the oracle without a GPU.  Not part of the reference CLI.
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -56,6 +58,20 @@ int debug_main(int argc, char **argv) {
       std::printf("%s\t%u\t%d\t%d\t%u\t%s\t%d\t%d\t%d\t%s\t%d\n", r.qname, (unsigned)r.flag, r.tid, r.pos, (unsigned)r.mapq, cig.empty() ? "*" : cig.c_str(),
                   r.mate_tid, r.mate_pos, r.isize, seq.c_str(), r.stop());
     }
+    return 0;
+  }
+  if (what == "chunks" && argc >= 2) {  // timing of the chunked reader alone
+    BamReader hdr(argv[1]);
+    const int threads = argc >= 3 ? std::atoi(argv[2]) : 0;
+    const size_t blocks = argc >= 4 ? (size_t)std::atol(argv[3]) : 4096;
+    BamChunkReader rd(argv[1], hdr.tell(), threads);
+    BamChunk c;
+    size_t n = 0, chunks = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (rd.next(c, blocks)) { n += c.n_records(); chunks++; }
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("records\t%zu\tchunks\t%zu\tseconds\t%.3f\tread\t%.3f\talloc\t%.3f\tinflate\t%.3f\twalk\t%.3f\n", n, chunks, dt, rd.t_read, rd.t_alloc,
+                rd.t_inflate, rd.t_walk);
     return 0;
   }
   if (what == "fragdist" && argc >= 2) {

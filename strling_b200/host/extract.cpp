@@ -5,9 +5,15 @@
 // it) and each soft-clipped end under both proportion classes add() may use (extract.nim:207-211,241-244) -- is
 // submitted to libstrgpu up front.  The order-dependent part (mate table, add_soft conditions, unplaced / adjust_by,
 // append order of cache.cache == `.bin` record order; extract.nim:93-132,192-248) is then replayed on the host in
-// file order with the scan results.  While the GPU scans batch n, the host decodes batch n+1 and replays batch n-1.
+// file order with the scan results.  Inflate, decode and staging are spread over the host threads (the decode buffer
+// travels with the batch, so qnames are never copied); a consumer thread waits for the GPU and replays batch n-1 while
+// the producer stages batch n+1.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -67,20 +73,26 @@ std::unordered_map<std::string, Intervals> read_bed(const std::string &path) {
 
 constexpr int kClsRead = 0, kClsFirstSeen = 1, kClsSecondSeen = 2;
 
-struct Pending {  // what the replay needs from one BAM record
+struct Pending {  // what the replay needs from one BAM record (qname stays in the batch's decode buffer)
   int32_t tid, pos, stop, mate_tid, mate_pos;
   uint16_t flag, n_cigar;
   uint8_t mapq;
+  uint8_t n_seg;           // segments this record contributes (0..5)
   uint32_t first_cig, last_cig;
   int32_t l_seq, m_len;
   int32_t seg_full;        // segment index or -1 (filtered by the genome-STR rule)
   int32_t seg_clip[2][2];  // [0 left / 1 right][0 first-seen class / 1 second-seen class], -1 = none
-  uint32_t qname_off, qname_len;
+  const char *qname;
+  uint32_t qname_len;
+  uint32_t aligned_bases;  // bases reserved in seq2 (0: the record's SEQ is not needed)
+  bool skip, clip_l, clip_r, primary;
 };
 
 struct Batch {
-  std::vector<Pending> recs;
-  std::vector<char> names;
+  BamChunk chunk;                // owns the decoded records (qname / SEQ are used in place)
+  std::vector<Pending> recs;     // one per record of the chunk, file order
+  std::vector<uint64_t> base_off;
+  std::vector<uint32_t> seg_off;
   uint8_t *seq2 = nullptr;       // pinned
   uint32_t *nmask = nullptr;     // pinned
   strgpu_segment *segs = nullptr;
@@ -90,7 +102,6 @@ struct Batch {
   uint32_t max_len = 0;
   bool any_n = false;
   int ticket = -1;
-  bool in_flight = false;
 };
 
 struct Extractor {
@@ -102,7 +113,9 @@ struct Extractor {
   std::unordered_map<std::string, Tread> tbl;        // Cache.tbl (extract.nim:89-91)
   std::vector<Tread> cache;                          // Cache.cache
   uint64_t n_reads = 0, n_scanned = 0, n_warned = 0;
+  double t_wait = 0, t_replay = 0, t_submit = 0, t_decode = 0, t_stage = 0;  // host stage timers (seconds)
   bool verbose = false;
+  int threads = 1;
 
   void gpu_check(int rc, const char *what) {
     if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + what + ": " + strgpu_last_error(gpu));
@@ -122,85 +135,137 @@ struct Extractor {
   void free_batch(Batch &b) {
     strgpu_host_free(b.seq2); strgpu_host_free(b.nmask); strgpu_host_free(b.segs); strgpu_host_free(b.out);
   }
-  void reset_batch(Batch &b) {
-    if (b.any_n) std::memset(b.nmask, 0, (size_t)((b.n_bases + 31) / 32) * 4 + 8);
-    b.recs.clear(); b.names.clear();
-    b.n_bases = 0; b.n_seg = 0; b.max_len = 0; b.any_n = false; b.ticket = -1; b.in_flight = false;
-  }
-  bool batch_full(const Batch &b) const { return b.n_bases + 1024 > b.cap_bases || b.n_seg + 8 > b.cap_seg; }
-
-  int32_t add_segment(Batch &b, uint64_t base, uint32_t len, int cls, bool has_n) {
-    strgpu_segment &s = b.segs[b.n_seg];
-    s.base_off = (uint32_t)base;
-    s.len = (uint16_t)len;
-    s.pclass = (uint8_t)cls;
-    s.flags = has_n ? STRGPU_SEG_HAS_N : 0;
-    b.max_len = std::max(b.max_len, len);
-    return (int32_t)b.n_seg++;
+  void grow_batch(Batch &b, uint64_t need_bases, uint32_t need_seg) {
+    if (need_bases <= b.cap_bases && need_seg <= b.cap_seg) return;
+    free_batch(b);
+    alloc_batch(b, std::max<uint64_t>(need_bases + need_bases / 8, b.cap_bases), std::max<uint32_t>(need_seg + need_seg / 8, b.cap_seg));
   }
 
-  // decode one record into the batch: everything the replay and the scan need
-  void stage(Batch &b, const BamRecord &r) {
-    Pending pr;
-    pr.tid = r.tid; pr.pos = r.pos; pr.stop = r.stop(); pr.mate_tid = r.mate_tid; pr.mate_pos = r.mate_pos;
-    pr.flag = r.flag; pr.n_cigar = r.n_cigar; pr.mapq = r.mapq; pr.l_seq = r.l_seq;
-    pr.first_cig = r.n_cigar ? r.cigar_at(0) : 0;
-    pr.last_cig = r.n_cigar ? r.cigar_at(r.n_cigar - 1) : 0;
-    pr.m_len = 0;
-    pr.seg_full = -1;
-    pr.seg_clip[0][0] = pr.seg_clip[0][1] = pr.seg_clip[1][0] = pr.seg_clip[1][1] = -1;
-    pr.qname_off = (uint32_t)b.names.size();
-    pr.qname_len = r.l_qname;
-    b.names.insert(b.names.end(), r.qname, r.qname + r.l_qname);
-    if (r.l_seq > STRGPU_MAX_SEGMENT_LEN)
-      throw std::runtime_error("[strling] read longer than " + std::to_string(STRGPU_MAX_SEGMENT_LEN) + " bp: " + std::string(r.qname));
+  template <typename F>
+  void parallel_for(size_t n, F f) {  // f(begin, end, thread)
+    const int nt = (int)std::min<size_t>((size_t)threads, (n + 4095) / 4096);
+    if (nt <= 1) { f((size_t)0, n, 0); return; }
+    std::vector<std::thread> th;
+    std::vector<std::string> errs((size_t)nt);
+    const size_t per = (n + (size_t)nt - 1) / (size_t)nt;
+    for (int t = 0; t < nt; t++) {
+      const size_t a = (size_t)t * per, e = std::min(n, a + per);
+      if (a >= e) break;
+      th.emplace_back([&, a, e, t]() {
+        try { f(a, e, t); } catch (const std::exception &ex) { errs[(size_t)t] = ex.what(); }
+      });
+    }
+    for (auto &x : th) x.join();
+    for (auto &e : errs)
+      if (!e.empty()) throw std::runtime_error(e);
+  }
 
-    // extract.nim:30-34 : exact single-M match outside every genome STR region -> no scan
-    bool skip = false;
-    if (r.n_cigar == 1 && BamRecord::op(pr.first_cig) == 0 && r.tid >= 0 && (size_t)r.tid < genome_str_by_tid.size() &&
-        genome_str_by_tid[(size_t)r.tid] != nullptr) {
-      if (!genome_str_by_tid[(size_t)r.tid]->find(r.pos, pr.stop)) {
-        skip = true;
-        pr.m_len = (int32_t)BamRecord::oplen(pr.first_cig);
+  // Decode every record of the chunk and lay the batch out: phase 1 (parallel) parses the fields and decides which
+  // segments a record contributes; a prefix sum fixes every record's place in seq2 / segs; phase 2 (parallel) packs the
+  // SEQ fields and writes the descriptors.
+  void stage(Batch &b) {
+    const size_t n = b.chunk.n_records();
+    b.recs.resize(n);
+    b.base_off.resize(n + 1);
+    b.seg_off.resize(n + 1);
+    const uint8_t *data = b.chunk.data.data();  // RawBuffer
+    parallel_for(n, [&](size_t lo, size_t hi, int) {
+      for (size_t i = lo; i < hi; i++) {
+        const BamRecord r = BamChunk::view(data + b.chunk.rec_off[i]);
+        Pending &pr = b.recs[i];
+        pr.tid = r.tid; pr.pos = r.pos; pr.stop = r.stop(); pr.mate_tid = r.mate_tid; pr.mate_pos = r.mate_pos;
+        pr.flag = r.flag; pr.n_cigar = r.n_cigar; pr.mapq = r.mapq; pr.l_seq = r.l_seq;
+        pr.first_cig = r.n_cigar ? r.cigar_at(0) : 0;
+        pr.last_cig = r.n_cigar ? r.cigar_at(r.n_cigar - 1) : 0;
+        pr.m_len = 0;
+        pr.seg_full = -1;
+        pr.seg_clip[0][0] = pr.seg_clip[0][1] = pr.seg_clip[1][0] = pr.seg_clip[1][1] = -1;
+        pr.qname = r.qname;
+        pr.qname_len = r.l_qname;
+        pr.primary = !(r.flag & (0x100 | 0x800));
+        pr.skip = pr.clip_l = pr.clip_r = false;
+        pr.n_seg = 0;
+        pr.aligned_bases = 0;
+        if (!pr.primary) continue;
+        if (r.l_seq > STRGPU_MAX_SEGMENT_LEN)
+          throw std::runtime_error("[strling] read longer than " + std::to_string(STRGPU_MAX_SEGMENT_LEN) + " bp: " + std::string(r.qname));
+        // extract.nim:30-34 : exact single-M match outside every genome STR region -> no scan
+        if (r.n_cigar == 1 && BamRecord::op(pr.first_cig) == 0 && r.tid >= 0 && (size_t)r.tid < genome_str_by_tid.size() &&
+            genome_str_by_tid[(size_t)r.tid] != nullptr && !genome_str_by_tid[(size_t)r.tid]->find(r.pos, pr.stop)) {
+          pr.skip = true;
+          pr.m_len = (int32_t)BamRecord::oplen(pr.first_cig);
+        }
+        // add_soft preconditions that do not depend on scan results (extract.nim:97-104)
+        if (r.mapq >= opts.min_mapq && r.n_cigar > 0) {
+          pr.clip_l = BamRecord::op(pr.first_cig) == 4;
+          pr.clip_r = BamRecord::op(pr.last_cig) == 4 && r.n_cigar > 1;  // a single op is handled as "left" twice (extract.nim:102-112)
+        }
+        pr.n_seg = (uint8_t)((pr.skip ? 0 : 1) + (pr.clip_l ? 2 : 0) + (pr.clip_r ? 2 : 0));
+        if (pr.n_seg) pr.aligned_bases = ((uint32_t)r.l_seq + 31u) & ~31u;  // 32-base alignment: no two records share an nmask word
       }
+    });
+    uint64_t nb = 0;
+    uint32_t ns = 0;
+    for (size_t i = 0; i < n; i++) {
+      b.base_off[i] = nb;
+      b.seg_off[i] = ns;
+      nb += b.recs[i].aligned_bases;
+      ns += b.recs[i].n_seg;
     }
-    // add_soft preconditions that do not depend on scan results (extract.nim:97-104)
-    bool clip_l = false, clip_r = false;
-    if (r.mapq >= opts.min_mapq && r.n_cigar > 0) {
-      clip_l = BamRecord::op(pr.first_cig) == 4;
-      clip_r = BamRecord::op(pr.last_cig) == 4;
-    }
-    if (!skip || clip_l || clip_r) {
-      const uint64_t base = b.n_bases;
-      const int n_other = strgpu_pack_bam4(r.seq, (uint32_t)r.l_seq, b.seq2, b.nmask, base);
-      if (n_other < 0) throw std::runtime_error("[strling] pack_bam4 failed");
-      const bool has_n = n_other > 0;
-      b.any_n = b.any_n || has_n;
-      b.n_bases = base + (((uint64_t)r.l_seq + 15) & ~15ull);
-      if (!skip) pr.seg_full = add_segment(b, base, (uint32_t)r.l_seq, kClsRead, has_n);
-      if (clip_l) {
-        const uint32_t len = std::min<uint32_t>(BamRecord::oplen(pr.first_cig), (uint32_t)r.l_seq);
-        pr.seg_clip[0][0] = add_segment(b, base, len, kClsFirstSeen, has_n);
-        pr.seg_clip[0][1] = add_segment(b, base, len, kClsSecondSeen, has_n);
+    b.base_off[n] = nb;
+    b.seg_off[n] = ns;
+    if (nb > 0xffffff00ull) throw std::runtime_error("[strling] batch too large: lower --batch-reads");
+    grow_batch(b, nb + 64, ns + 8);
+    b.n_bases = nb;
+    b.n_seg = ns;
+    std::vector<uint32_t> tmax((size_t)threads + 1, 0);
+    std::vector<uint8_t> tany((size_t)threads + 1, 0);
+    parallel_for(n, [&](size_t lo, size_t hi, int t) {
+      uint32_t mx = 0;
+      bool any = false;
+      for (size_t i = lo; i < hi; i++) {
+        Pending &pr = b.recs[i];
+        if (!pr.n_seg) continue;
+        const BamRecord r = BamChunk::view(data + b.chunk.rec_off[i]);
+        const uint64_t base = b.base_off[i];
+        const int n_other = strgpu_pack_bam4(r.seq, (uint32_t)r.l_seq, b.seq2, b.nmask, base);
+        if (n_other < 0) throw std::runtime_error("[strling] pack_bam4 failed");
+        const bool has_n = n_other > 0;
+        any = any || has_n;
+        uint32_t si = b.seg_off[i];
+        auto put = [&](uint64_t off, uint32_t len, int cls) {
+          b.segs[si] = strgpu_segment{(uint32_t)off, (uint16_t)len, (uint8_t)cls, (uint8_t)(has_n ? STRGPU_SEG_HAS_N : 0)};
+          mx = std::max(mx, len);
+          return (int32_t)si++;
+        };
+        if (!pr.skip) pr.seg_full = put(base, (uint32_t)r.l_seq, kClsRead);
+        if (pr.clip_l) {
+          const uint32_t len = std::min<uint32_t>(BamRecord::oplen(pr.first_cig), (uint32_t)r.l_seq);
+          pr.seg_clip[0][0] = put(base, len, kClsFirstSeen);
+          pr.seg_clip[0][1] = put(base, len, kClsSecondSeen);
+        }
+        if (pr.clip_r) {
+          const uint32_t len = std::min<uint32_t>(BamRecord::oplen(pr.last_cig), (uint32_t)r.l_seq);
+          pr.seg_clip[1][0] = put(base + (uint64_t)r.l_seq - len, len, kClsFirstSeen);
+          pr.seg_clip[1][1] = put(base + (uint64_t)r.l_seq - len, len, kClsSecondSeen);
+        }
       }
-      if (clip_r && r.n_cigar > 1) {  // with a single op the "last" op is the first: handled as left twice (extract.nim:102-112)
-        const uint32_t len = std::min<uint32_t>(BamRecord::oplen(pr.last_cig), (uint32_t)r.l_seq);
-        pr.seg_clip[1][0] = add_segment(b, base + (uint64_t)r.l_seq - len, len, kClsFirstSeen, has_n);
-        pr.seg_clip[1][1] = add_segment(b, base + (uint64_t)r.l_seq - len, len, kClsSecondSeen, has_n);
-      }
-    }
-    b.recs.push_back(pr);
+      tmax[(size_t)t] = mx;
+      tany[(size_t)t] = any;
+    });
+    b.max_len = *std::max_element(tmax.begin(), tmax.end());
+    b.any_n = std::any_of(tany.begin(), tany.end(), [](uint8_t v) { return v != 0; });
   }
 
   void submit(Batch &b) {
     n_scanned += b.n_seg;
     gpu_check(strgpu_scan_submit(gpu, b.seq2, b.n_bases, b.any_n ? b.nmask : nullptr, b.segs, b.n_seg, b.max_len, b.out, &b.ticket),
               "scan_submit");
-    b.in_flight = true;
   }
-  void wait(Batch &b) {
-    gpu_check(strgpu_scan_wait(gpu, b.ticket), "scan_wait");
-    b.in_flight = false;
+  void wait(Batch &b) { gpu_check(strgpu_scan_wait(gpu, b.ticket), "scan_wait"); }
+  void recycle(Batch &b) {
+    if (b.any_n) std::memset(b.nmask, 0, (size_t)((b.n_bases + 31) / 32) * 4 + 8);
+    b.n_bases = 0; b.n_seg = 0; b.max_len = 0; b.any_n = false; b.ticket = -1;
   }
 
   // ---- replay: extract.nim:63-132,192-248 with scan results looked up instead of computed
@@ -211,7 +276,7 @@ struct Extractor {
     t.flag = r.flag;
     t.split = kNone;
     t.mapping_quality = r.mapq;
-    t.qname.assign(b.names.data() + r.qname_off, r.qname_len);
+    t.qname.assign(r.qname, r.qname_len);
     int align_length = r.m_len, repeat_count = 0;
     if (r.seg_full >= 0) {
       const strgpu_repeat &res = b.out[r.seg_full];
@@ -257,7 +322,7 @@ struct Extractor {
   }
 
   void add(const Batch &b, const Pending &r) {
-    std::string qname(b.names.data() + r.qname_off, r.qname_len);
+    std::string qname(r.qname, r.qname_len);
     auto it = tbl.end();
     bool after_mate = r.tid > r.mate_tid;
     if (!after_mate && r.tid == r.mate_tid) {
@@ -300,7 +365,8 @@ struct Extractor {
   }
 
   void replay(const Batch &b) {
-    for (const Pending &r : b.recs) add(b, r);
+    for (const Pending &r : b.recs)
+      if (r.primary) add(b, r);
   }
 };
 
@@ -392,66 +458,179 @@ int extract_run(const ExtractArgs &a) {
   const double classes[3] = {a.proportion_repeat, a.proportion_repeat - 0.07, std::min(a.proportion_repeat, 0.6)};
   ex.gpu_check(strgpu_set_proportions(ex.gpu, classes, 3), "set_proportions");
 
-  constexpr int kBatches = STRGPU_SLOTS;
+  ex.threads = a.threads > 0 ? a.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  const uint64_t first_voffset = rd.tell();
+  constexpr int kBatches = STRGPU_SLOTS + 1;  // one being inflated, one being staged, up to two on the GPU / in replay
   Batch batches[kBatches];
-  const uint64_t cap_bases = (uint64_t)a.batch_reads * 160 + 4096;
-  const uint32_t cap_seg = (uint32_t)std::min<uint64_t>((uint64_t)a.batch_reads * 2 + 64, 0xfffffff0u);
-  for (auto &b : batches) ex.alloc_batch(b, cap_bases, cap_seg);
+  for (auto &b : batches) ex.alloc_batch(b, (uint64_t)a.batch_reads * 160 + 4096, (uint32_t)std::min<uint64_t>((uint64_t)a.batch_reads * 2 + 64, 0xfffffff0u));
+  const size_t blocks_per_chunk = std::max<size_t>(16, (size_t)a.batch_reads / 200);  // ~64 KiB blocks of ~300-byte records
 
   std::fprintf(stderr, "[strling] collecting str-like reads\n");
   const auto t0 = clk::now();
+  // producer (this thread): inflate + decode + stage (all parallel) + submit.  consumer: wait for the GPU, replay in
+  // file order (the mate table makes that part sequential), recycle the batch.
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<int> submitted;
+  bool is_free[kBatches];
+  for (bool &f : is_free) f = true;
+  bool done = false;
+  std::string consumer_error;
+  bool first_pass = true;
+  int32_t tid_seen = -1;
+  std::thread consumer([&]() {
+    try {
+      while (true) {
+        int bi;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&]() { return !submitted.empty() || done; });
+          if (submitted.empty()) return;
+          bi = submitted.front();
+          submitted.pop_front();
+        }
+        Batch &b = batches[bi];
+        const auto w0 = clk::now();
+        ex.wait(b);
+        const auto w1 = clk::now();
+        for (const Pending &r : b.recs) {
+          if (!r.primary) continue;
+          if (first_pass && r.tid != tid_seen && r.tid >= 0) {
+            if (rd.targets()[(size_t)r.tid].length > 2000000u)
+              std::fprintf(stderr, "[strling] extracting chromosome:%s\n", rd.targets()[(size_t)r.tid].name.c_str());
+            tid_seen = r.tid;
+          }
+          ex.n_reads++;
+          if (ex.verbose && ex.n_reads % 10000000 == 0) {
+            const double dt = std::chrono::duration<double>(clk::now() - t0).count();
+            std::fprintf(stderr, "%llu %.1f reads/sec tbl len: %zu cache len: %zu\n", (unsigned long long)ex.n_reads, ex.n_reads / dt,
+                         ex.tbl.size(), ex.cache.size());
+          }
+          ex.add(b, r);
+        }
+        ex.recycle(b);
+        ex.t_wait += std::chrono::duration<double>(w1 - w0).count();
+        ex.t_replay += std::chrono::duration<double>(clk::now() - w1).count();
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          is_free[bi] = true;
+        }
+        cv.notify_all();
+      }
+    } catch (const std::exception &e) {
+      std::lock_guard<std::mutex> lk(mu);
+      consumer_error = e.what();
+      for (bool &f : is_free) f = true;
+      cv.notify_all();
+    }
+  });
   uint64_t tail_voffset = 0;
   bool have_tail = false;
-  int cur = 0;          // batch being filled
-  int oldest = -1;      // oldest batch in flight
-  int n_in_flight = 0;
-  auto flush = [&](bool final) {
-    Batch &b = batches[cur];
-    if (!b.recs.empty()) {
-      ex.submit(b);
-      if (oldest < 0) oldest = cur;
-      n_in_flight++;
-      cur = (cur + 1) % kBatches;
-    }
-    // keep at most kBatches-1 in flight so the batch being filled is always free; drain everything at the end
-    while (n_in_flight > (final ? 0 : kBatches - 1)) {
-      Batch &o = batches[oldest];
-      ex.wait(o);
-      ex.replay(o);
-      ex.reset_batch(o);
-      oldest = (oldest + 1) % kBatches;
-      n_in_flight--;
-    }
-    if (n_in_flight == 0) oldest = -1;
+  auto drain = [&]() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&]() { return (submitted.empty() && std::all_of(is_free, is_free + kBatches, [](bool f) { return f; })) || !consumer_error.empty(); });
   };
-  auto feed = [&](BamReader &reader, bool first_pass) {
-    BamRecord r;
-    int32_t tid_seen = -1;
-    while (reader.next(r)) {
-      if (first_pass && r.tid < 0 && !have_tail) { have_tail = true; tail_voffset = r.voffset; }
-      if (r.flag & (0x100 | 0x800)) continue;
-      if (first_pass && r.tid != tid_seen && r.tid >= 0) {
-        if (rd.targets()[(size_t)r.tid].length > 2000000u) std::fprintf(stderr, "[strling] extracting chromosome:%s\n", rd.targets()[(size_t)r.tid].name.c_str());
-        tid_seen = r.tid;
-      }
-      ex.n_reads++;
-      if (ex.verbose && ex.n_reads % 10000000 == 0) {
-        const double dt = std::chrono::duration<double>(clk::now() - t0).count();
-        std::fprintf(stderr, "%llu %.1f reads/sec tbl len: %zu cache len: %zu\n", (unsigned long long)ex.n_reads, ex.n_reads / dt, ex.tbl.size(), ex.cache.size());
-      }
-      ex.stage(batches[cur], r);
-      if (batches[cur].recs.size() >= a.batch_reads || ex.batch_full(batches[cur])) flush(false);
-    }
+  auto acquire_free = [&]() -> int {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&]() { return std::any_of(is_free, is_free + kBatches, [](bool f) { return f; }) || !consumer_error.empty(); });
+    if (!consumer_error.empty()) return -1;
+    for (int i = 0; i < kBatches; i++)
+      if (is_free[i]) { is_free[i] = false; return i; }
+    return -1;
   };
-  feed(rd, true);                       // pass 2: every record in file order (extract.nim:308-322)
-  flush(true);
-  std::fprintf(stderr, "[strling] extracting unmapped reads\n");
-  if (have_tail) {                      // ibam.query("*"): the no-coordinate tail again (extract.nim:326-329)
-    BamReader tail(a.bam, a.threads);
-    tail.seek(tail_voffset);
-    feed(tail, false);
-    flush(true);
+  auto feed = [&](uint64_t voffset, bool pass1) {
+    // reader thread: inflate the next chunk into a free batch while this thread stages the previous one
+    std::deque<int> decoded;
+    bool reader_done = false;
+    std::string reader_error;
+    std::thread reader_thread([&]() {
+      try {
+        BamChunkReader reader(a.bam, voffset, ex.threads);
+        while (true) {
+          const int bi = acquire_free();
+          if (bi < 0) break;
+          const auto d0 = clk::now();
+          const bool more = reader.next(batches[bi].chunk, blocks_per_chunk);
+          ex.t_decode += std::chrono::duration<double>(clk::now() - d0).count();
+          std::lock_guard<std::mutex> lk(mu);
+          if (more && batches[bi].chunk.n_records() > 0) decoded.push_back(bi);
+          else is_free[bi] = true;
+          cv.notify_all();
+          if (!more) break;
+        }
+      } catch (const std::exception &e) {
+        std::lock_guard<std::mutex> lk(mu);
+        reader_error = e.what();
+      }
+      std::lock_guard<std::mutex> lk(mu);
+      reader_done = true;
+      cv.notify_all();
+    });
+    std::string stage_error;
+    while (true) {
+      int bi = -1;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return !decoded.empty() || reader_done; });
+        if (decoded.empty()) break;
+        bi = decoded.front();
+        decoded.pop_front();
+      }
+      Batch &b = batches[bi];
+      if (!stage_error.empty() || !consumer_error.empty()) {  // keep draining so the reader can finish
+        std::lock_guard<std::mutex> lk(mu);
+        is_free[bi] = true;
+        cv.notify_all();
+        continue;
+      }
+      try {
+        const auto d1 = clk::now();
+        ex.stage(b);
+        if (pass1 && !have_tail)
+          for (size_t i = 0; i < b.recs.size(); i++)
+            if (b.recs[i].tid < 0) { have_tail = true; tail_voffset = b.chunk.voffset_of(i); break; }
+        const auto d2 = clk::now();
+        ex.t_stage += std::chrono::duration<double>(d2 - d1).count();
+        ex.submit(b);
+        ex.t_submit += std::chrono::duration<double>(clk::now() - d2).count();
+        std::lock_guard<std::mutex> lk(mu);
+        submitted.push_back(bi);
+      } catch (const std::exception &e) {
+        stage_error = e.what();
+        std::lock_guard<std::mutex> lk(mu);
+        is_free[bi] = true;
+      }
+      cv.notify_all();
+    }
+    reader_thread.join();
+    if (!reader_error.empty()) throw std::runtime_error(reader_error);
+    if (!stage_error.empty()) throw std::runtime_error(stage_error);
+  };
+  try {
+    feed(first_voffset, true);            // pass 2: every record in file order (extract.nim:308-322)
+    drain();
+    std::fprintf(stderr, "[strling] extracting unmapped reads\n");
+    if (have_tail && consumer_error.empty()) {  // ibam.query("*"): the no-coordinate tail again (extract.nim:326-329)
+      first_pass = false;
+      feed(tail_voffset, false);
+      drain();
+    }
+  } catch (...) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      done = true;
+    }
+    cv.notify_all();
+    consumer.join();
+    throw;
   }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    done = true;
+  }
+  cv.notify_all();
+  consumer.join();
+  if (!consumer_error.empty()) throw std::runtime_error(consumer_error);
   const double dt = std::chrono::duration<double>(clk::now() - t0).count();
 
   std::fprintf(stderr, "[strling] writing binary file:%s\n", a.bin.c_str());
@@ -465,8 +644,9 @@ int extract_run(const ExtractArgs &a) {
   std::fprintf(stderr, "[strling] finished extraction\n");
   if (a.verbose) {
     const double total = std::chrono::duration<double>(clk::now() - t_start).count();
-    std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
-                 (unsigned long long)ex.n_reads, (unsigned long long)ex.n_scanned, bf.reads.size(), dt, ex.n_reads / std::max(dt, 1e-9), total,
+    std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"threads\": %d, \"inflate_s\": %.3f, \"stage_s\": %.3f, \"submit_s\": %.3f, \"gpu_wait_s\": %.3f, \"replay_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
+                 (unsigned long long)ex.n_reads, (unsigned long long)ex.n_scanned, bf.reads.size(), dt, ex.threads, ex.t_decode, ex.t_stage, ex.t_submit,
+                 ex.t_wait, ex.t_replay, ex.n_reads / std::max(dt, 1e-9), total,
                  (unsigned long long)strgpu_launch_count(ex.gpu));
   }
   for (auto &b : batches) ex.free_batch(b);
