@@ -372,7 +372,7 @@ int extract_main(int argc, char **argv) {
   e.verbose = a.has("--verbose");
   e.device = std::stoi(a.get("--device", "0"));
   e.threads = std::stoi(a.get("--threads", "0"));
-  e.batch_reads = (uint32_t)std::stoul(a.get("--batch-reads", "1048576"));
+  e.batch_reads = (uint32_t)std::stoul(a.get("--batch-reads", "262144"));
   e.bam = a.pos[0];
   e.bin = a.pos[1];
   return extract_run(e);

@@ -14,7 +14,7 @@ struct ExtractArgs {
   bool verbose = false;
   int device = 0;
   int threads = 0;
-  uint32_t batch_reads = 1u << 20;
+  uint32_t batch_reads = 1u << 18;
 };
 int extract_run(const ExtractArgs &a);
 std::array<uint32_t, 4096> fragment_length_distribution(const std::string &bam, int threads);
