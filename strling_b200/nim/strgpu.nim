@@ -44,6 +44,12 @@ type
     min_support*: int32
     min_clip*, min_clip_total*, max_clip_dist*, merge_mode*: uint16
 
+  StrGpuLocus* {.bycopy.} = object     ## strgpu_locus: a -l / -b locus after parse_bedline / parse_boundsline
+    tid*: int32
+    left_most*, right_most*: uint32
+    repeat*: array[6, char]
+    n_left*, n_right*, n_total*: uint16
+
 const STRGPU_SEG_HAS_N* = 1'u8
 
 proc strgpu_create*(ctx: ptr StrGpuCtx, device: cint): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
@@ -59,6 +65,10 @@ proc strgpu_scan_submit*(ctx: StrGpuCtx, seq2: ptr uint8, n_bases: uint64, nmask
 proc strgpu_scan_wait*(ctx: StrGpuCtx, ticket: cint): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
 proc strgpu_scan*(ctx: StrGpuCtx, seq2: ptr uint8, n_bases: uint64, nmask: ptr uint32, segs: ptr StrGpuSegment,
                   n_seg: uint32, max_len: uint32, res: ptr StrGpuRepeat): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
+proc strgpu_scan_reads_submit*(ctx: StrGpuCtx, seq2: ptr uint8, n_reads, read_len, stride_bases, pclass: uint32, nmask: ptr uint32,
+                               extra: ptr StrGpuSegment, n_extra, extra_max_len: uint32, res: ptr StrGpuRepeat, ticket: ptr cint): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
+proc strgpu_cluster_loci*(ctx: StrGpuCtx, treads: ptr StrGpuTread, n: uint32, params: ptr StrGpuClusterParams, loci: ptr StrGpuLocus,
+                          n_loci: uint32, res: ptr StrGpuBounds, cap: uint32, n_out: ptr uint32): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
 proc strgpu_cluster*(ctx: StrGpuCtx, treads: ptr StrGpuTread, n: uint32, params: ptr StrGpuClusterParams,
                      res: ptr StrGpuBounds, cap: uint32, n_out: ptr uint32): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
 

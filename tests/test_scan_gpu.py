@@ -175,3 +175,25 @@ def test_uniform_reads_without_descriptors(gpu, length, n_frac):
     flat, off, lens = synth.segment_ascii(reads, segs, stride)
     units, counts = oracle_for(flat, off, lens, segs["pclass"])
     assert np.array_equal(out["unit"], units) and np.array_equal(out["repeat_count"], counts)
+
+
+def test_scale_permutation_invariance(gpu):
+    # Size-independent property at scale: a segment's result depends only on its bases, length and class -- not on where it
+    # sits in the batch, which lane / warp / queue handles it, or what its neighbours are.  8M segments = one 250k-read
+    # shard referenced 32 times in shuffled order (every copy lands in a different group of 32 and queue slot).
+    reads, cls, lclip, rclip = synth.make_reads(250_000, seed=77, mix=(0.8, 0.1, 0.05, 0.05), n_frac=0.002)
+    seq2, nmask, stride = synth.pack_matrix(reads)
+    segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+    flat, off, lens = synth.segment_ascii(reads, segs, stride)
+    units, counts = oracle_for(flat, off, lens, segs["pclass"])
+    rng = np.random.default_rng(5)
+    reps = 32
+    perm = np.concatenate([rng.permutation(len(segs)) for _ in range(reps)])
+    big = np.ascontiguousarray(segs[perm])
+    res = gpu.scan(seq2, reads.shape[0] * stride, nmask, big, max_len=150)
+    assert np.array_equal(res["unit"], units[perm]) and np.array_equal(res["repeat_count"], counts[perm])
+    # checksum of checksums: every copy of the shard folds to the same digest
+    key = res["repeat_count"].astype(np.uint64) * np.uint64(1315423911) + np.frombuffer(res["unit"].tobytes(), dtype=np.uint8).reshape(-1, 6).astype(np.uint64).dot(np.array([1, 7, 49, 343, 2401, 16807], dtype=np.uint64))
+    inv = np.argsort(perm.reshape(reps, -1), axis=1)
+    digests = {int(np.bitwise_xor.reduce(key.reshape(reps, -1)[r][inv[r]] * (np.arange(len(segs), dtype=np.uint64) + np.uint64(1)))) for r in range(reps)}
+    assert len(digests) == 1
