@@ -160,6 +160,10 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from strling_b200 import build as sb_build
+
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        sb_build.build_lib()  # no-op when strling_b200/libstrgpu.so is up to date (it travels with the repo snapshot)
     import strling_b200 as sb
     from strling_b200 import synth
 

@@ -293,7 +293,7 @@ constexpr int kTabWords = kCls2 + kCls3 + kCls4Words;  // 52 words per lane; k =
 constexpr int kLut2 = 0, kLut3 = 16, kLut4 = 80, kRev234 = 336, kLut5 = 440, kRev5 = 1464;  // offsets into the uint16 table
 constexpr int kLutTotal = 1672;
 constexpr int kQueueCap = 64;                  // a batch is taken at 32 entries and a stage adds at most 32
-constexpr int kQueueWords = kQueueCap * 4 + kQueueCap * 3 + kQueueCap * 3 + 32;  // QR (4 words/entry), Q5, Q6 (3), QW (1, cap 32)
+constexpr int kQueueWords = 4 * kQueueCap * 3 + 32;  // QR, Q4, Q5, Q6 (3 words/entry), QW (1 word/entry, cap 32)
 constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + kQueueWords;
 constexpr int kLaneSmemBytes = kLaneWarps * kWarpSmemWords * 4 + kLutTotal * 2 + 16;
 static_assert(sizeof(WarpScratch<512>) <= (size_t)kTabWords * 32 * 4, "warp scratch must fit in the warp's counter region");
@@ -531,49 +531,30 @@ struct Lead {
 __device__ __forceinline__ uint32_t *slot_at(uint32_t *tab, uint32_t off) {
   return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(tab) + off);
 }
-__device__ __forceinline__ void lead_update(Lead &l, int c, uint32_t off) {
-  if (c > l.M) { l.M = c; l.off = off; }   // strict >: the earlier leader keeps ties
+
+// Time-stamped counters for k = 2 and k = 3: a class's word holds count << 8 | (255 - t), t = index of the window that
+// last incremented it.  One update is LDS, LOP3, IADD3, STS -- no per-window leader bookkeeping: after the pass the
+// leader is the class with the largest word, because among classes with the maximal count the one whose LAST increment
+// came first is the one that reached that count first (Seq.inc keeps the first to reach the maximum, utils.nim:192-195).
+__device__ __forceinline__ void stamp2(uint32_t *tab, uint32_t oa, uint32_t ob, uint32_t adda, uint32_t addb) {
+  uint32_t *pa = slot_at(tab, oa), *pb = slot_at(tab, ob);   // two independent histograms: both loads before both stores
+  const uint32_t va = *pa, vb = *pb;
+  *pa = (va | 0xffu) + adda;
+  *pb = (vb | 0xffu) + addb;
 }
-__device__ __forceinline__ void bump1(uint32_t *tab, uint32_t o, Lead &l) {
+__device__ __forceinline__ void stamp1(uint32_t *tab, uint32_t o, uint32_t add) {
   uint32_t *p = slot_at(tab, o);
-  const int c = (int)*p + 1;
-  *p = (uint32_t)c;
-  lead_update(l, c, o);
-}
-// packed uint8 counter: entry = word byte offset | bit shift of the class's byte
-__device__ __forceinline__ void bump1p(uint32_t *tab, uint32_t e, Lead &l) {
-  uint32_t *p = slot_at(tab, e & 0xff80u);
-  const uint32_t sh = e & 31u;
-  const uint32_t v = *p + (1u << sh);
-  *p = v;
-  lead_update(l, (int)((v >> sh) & 0xffu), e);
-}
-// three independent histograms: issue the three loads before the three stores
-__device__ __forceinline__ void bump3(uint32_t *tab, uint32_t o2, uint32_t o3, uint32_t e4, Lead &l2, Lead &l3, Lead &l4) {
-  uint32_t *p2 = slot_at(tab, o2), *p3 = slot_at(tab, o3), *p4 = slot_at(tab, e4 & 0xff80u);
-  const uint32_t sh = e4 & 31u;
-  const int c2 = (int)*p2 + 1, c3 = (int)*p3 + 1;
-  const uint32_t v4 = *p4 + (1u << sh);
-  *p2 = (uint32_t)c2; *p3 = (uint32_t)c3; *p4 = v4;
-  lead_update(l2, c2, o2); lead_update(l3, c3, o3); lead_update(l4, (int)((v4 >> sh) & 0xffu), e4);
-}
-__device__ __forceinline__ void bump2(uint32_t *tab, uint32_t oa, uint32_t ob, Lead &la, Lead &lb) {
-  uint32_t *pa = slot_at(tab, oa), *pb = slot_at(tab, ob);
-  const int ca = (int)*pa + 1, cb = (int)*pb + 1;
-  *pa = (uint32_t)ca; *pb = (uint32_t)cb;
-  lead_update(la, ca, oa); lead_update(lb, cb, ob);
+  *p = (*p | 0xffu) + add;
 }
 
-// count(read, k, counts[k]) for k = 2, 3, 4 in one pass (utils.nim:205-211 three times): the read is walked in groups
-// of twelve bases (six 2-mer, four 3-mer and three 4-mer windows); the loop body fits the L0 instruction cache.
-__device__ __forceinline__ void lane_count234(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, int L, Lead &l2, Lead &l3,
-                                              Lead &l4) {
+// count(read, k, counts[k]) for k = 2 and k = 3 in one pass (utils.nim:205-211 twice): the read is walked in groups of
+// twelve bases (six 2-mer and four 3-mer windows).  Returns each k's best word << 5 | class (0 when there is no window).
+__device__ __forceinline__ void lane_count23(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, int L, uint32_t &best2,
+                                             uint32_t &best3) {
 #pragma unroll
-  for (int c = 0; c < kTabWords; c++) tab[c * 32] = 0;
-  l2 = Lead{0, 0xffffffffu};
-  l3 = Lead{0, 0xffffffffu};
-  l4 = Lead{0, 0xffffffffu};
+  for (int c = 0; c < kCls2 + kCls3; c++) tab[c * 32] = 0;
   const int n_groups = L / 12;
+  uint32_t add2 = 256u, add3 = 256u;   // 256 - (index of the group's first window)
 #pragma unroll 1
   for (int g = 0; g < n_groups; g++) {
     const uint32_t bit = 24u * g;
@@ -582,32 +563,77 @@ __device__ __forceinline__ void lane_count234(const uint32_t *rd, uint32_t *tab,
                    a3 = lut[kLut2 + ((x >> 8) & 15u)], a4 = lut[kLut2 + ((x >> 4) & 15u)], a5 = lut[kLut2 + (x & 15u)];
     const uint32_t b0 = lut[kLut3 + (x >> 18)], b1 = lut[kLut3 + ((x >> 12) & 63u)], b2 = lut[kLut3 + ((x >> 6) & 63u)],
                    b3 = lut[kLut3 + (x & 63u)];
-    const uint32_t c0 = lut[kLut4 + (x >> 16)], c1 = lut[kLut4 + ((x >> 8) & 255u)], c2 = lut[kLut4 + (x & 255u)];
-    bump3(tab, a0, b0, c0, l2, l3, l4);
-    bump3(tab, a1, b1, c1, l2, l3, l4);
-    bump3(tab, a2, b2, c2, l2, l3, l4);
-    bump2(tab, a3, b3, l2, l3);
-    bump1(tab, a4, l2);
-    bump1(tab, a5, l2);
+    stamp2(tab, a0, b0, add2, add3);
+    stamp2(tab, a1, b1, add2 - 1u, add3 - 1u);
+    stamp2(tab, a2, b2, add2 - 2u, add3 - 2u);
+    stamp2(tab, a3, b3, add2 - 3u, add3 - 3u);
+    stamp1(tab, a4, add2 - 4u);
+    stamp1(tab, a5, add2 - 5u);
+    add2 -= 6u;
+    add3 -= 4u;
   }
   // tail: fewer than twelve bases left
-  const int r2 = L / 2 - 6 * n_groups, r3 = L / 3 - 4 * n_groups, r4 = L / 4 - 3 * n_groups;
+  const int r2 = L / 2 - 6 * n_groups, r3 = L / 3 - 4 * n_groups;
   const uint32_t base = 24u * n_groups;
 #pragma unroll 1
   for (int t = 0; t < r2; t++) {
     {
       const uint32_t bit = base + 4u * t;
-      bump1(tab, lut[kLut2 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 28)], l2);
+      stamp1(tab, lut[kLut2 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 28)], add2 - (uint32_t)t);
     }
     if (t < r3) {
       const uint32_t bit = base + 6u * t;
-      bump1(tab, lut[kLut3 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 26)], l3);
-    }
-    if (t < r4) {
-      const uint32_t bit = base + 8u * t;
-      bump1p(tab, lut[kLut4 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 24)], l4);
+      stamp1(tab, lut[kLut3 + (__funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 26)], add3 - (uint32_t)t);
     }
   }
+  best2 = 0;
+  best3 = 0;
+#pragma unroll
+  for (int c = 0; c < kCls2; c++) best2 = max(best2, (tab[c * 32] << 5) | (uint32_t)c);
+#pragma unroll
+  for (int c = 0; c < kCls3; c++) best3 = max(best3, (tab[(kCls2 + c) * 32] << 5) | (uint32_t)c);
+}
+
+// count(read, 4, counts[4]) with 70 packed uint8 counters ([class / 4][lane] words 34..51 of the lane's column)
+__device__ __forceinline__ void lane_count4(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, int L, int &M, uint32_t &leader) {
+#pragma unroll
+  for (int c = 0; c < kCls4Words; c++) tab[(kCls2 + kCls3 + c) * 32] = 0;
+  M = 0;
+  uint32_t lead = 0xffffffffu;
+  const int W = L / 4;
+  const int n_words = W / 4;
+#pragma unroll 1
+  for (int wi = 0; wi < n_words; wi++) {
+    const uint32_t x = rd[wi * 32];
+    const uint32_t e0 = lut[kLut4 + (x >> 24)], e1 = lut[kLut4 + ((x >> 16) & 255u)], e2 = lut[kLut4 + ((x >> 8) & 255u)],
+                   e3 = lut[kLut4 + (x & 255u)];
+#pragma unroll
+    for (int t = 0; t < 4; t += 2) {
+      // two windows at a time: both counter words are loaded before either is stored (two loads in flight); if the
+      // windows share a word the second update is applied on top of the first
+      const uint32_t ea = t == 0 ? e0 : e2, eb = t == 0 ? e1 : e3;
+      uint32_t *pa = slot_at(tab, ea & 0xff80u), *pb = slot_at(tab, eb & 0xff80u);
+      const uint32_t sa = ea & 31u, sb = eb & 31u;
+      const uint32_t va = *pa + (1u << sa);
+      const uint32_t vb0 = *pb;
+      const uint32_t vb = (pa == pb ? va : vb0) + (1u << sb);
+      *pa = va;
+      *pb = vb;
+      const int ca = (int)((va >> sa) & 0xffu), cb = (int)((vb >> sb) & 0xffu);
+      if (ca > M) { M = ca; lead = ea; }   // strict >: the earlier leader keeps ties
+      if (cb > M) { M = cb; lead = eb; }
+    }
+  }
+  for (int w = 4 * n_words; w < W; w++) {
+    const uint32_t e = lut[kLut4 + ((rd[(w >> 2) * 32] >> (24 - 8 * (w & 3))) & 255u)];
+    uint32_t *p = slot_at(tab, e & 0xff80u);
+    const uint32_t sh = e & 31u;
+    const uint32_t v = *p + (1u << sh);
+    *p = v;
+    const int c = (int)((v >> sh) & 0xffu);
+    if (c > M) { M = c; lead = e; }
+  }
+  leader = (lead == 0xffffffffu) ? 0xffu : (uint32_t)lut[kRev234 + kCls2 + kCls3 + ((lead >> 7) - (kCls2 + kCls3)) * 4 + ((lead & 31u) >> 3)];
 }
 
 // one rung of the ladder (utils.nim:246-265) given this k's count result.  Returns false on `break`.
@@ -687,39 +713,29 @@ __device__ __forceinline__ void lane_count6(const uint32_t *rd, uint32_t *tab, i
   }
 }
 
-// Warp-local FIFOs of segments waiting for their next stage.  Entry words:
-//   0: segment index      1: best << 16 | repeat_count      2: unit_code | unit_k << 16 | next_k << 24
-//   3 (QR only): M3 | M4 << 8 | leader3 << 16 | leader4 << 22
-struct LaneQueue {
-  uint32_t *buf;
-  int n;
-  int stride;
-};
-__device__ __forceinline__ void queue_push(LaneQueue &q, bool want, int lane, uint32_t s, const ScanState &st, int next_k,
-                                           uint32_t extra = 0) {
+// Warp-local FIFOs of segments waiting for their next stage (three words per entry):
+//   0: segment index      1: best << 16 | repeat_count      2: unit_code | unit_k << 12 | extra << 16
+// (extra: M3 | leader3 << 8 for the k = 3 recount queue)
+__device__ __forceinline__ void queue_push(uint32_t *buf, int &n, bool want, int lane, uint32_t s, const ScanState &st, uint32_t extra) {
   const uint32_t m = __ballot_sync(kFull, want);
   if (want) {
-    uint32_t *e = q.buf + q.stride * (q.n + __popc(m & ((1u << lane) - 1u)));
+    uint32_t *e = buf + 3 * (n + __popc(m & ((1u << lane) - 1u)));
     e[0] = s;
-    if (q.stride > 1) {
-      e[1] = ((uint32_t)(st.best & 0xffff) << 16) | (uint32_t)(st.rc & 0xffff);
-      e[2] = (st.unit_code & 0xffffu) | ((uint32_t)st.unit_k << 16) | ((uint32_t)next_k << 24);
-    }
-    if (q.stride > 3) e[3] = extra;
+    e[1] = ((uint32_t)(st.best & 0xffff) << 16) | (uint32_t)(st.rc & 0xffff);
+    e[2] = (st.unit_code & 0xfffu) | ((uint32_t)st.unit_k << 12) | (extra << 16);
   }
-  q.n += __popc(m);
+  n += __popc(m);
   __syncwarp();
 }
-__device__ __forceinline__ void queue_read(const LaneQueue &q, int i, uint32_t &s, ScanState &st, int &next_k, uint32_t &extra) {
-  const uint32_t *e = q.buf + q.stride * i;
+__device__ __forceinline__ void queue_read(const uint32_t *buf, int i, uint32_t &s, ScanState &st, uint32_t &extra) {
+  const uint32_t *e = buf + 3 * i;
   s = e[0];
   const uint32_t a = e[1], b = e[2];
   st.best = (int)(int16_t)(a >> 16);
   st.rc = (int)(a & 0xffffu);
-  st.unit_code = b & 0xffffu;
-  st.unit_k = (int)((b >> 16) & 0xffu);
-  next_k = (int)(b >> 24);
-  extra = q.stride > 3 ? e[3] : 0u;
+  st.unit_code = b & 0xfffu;
+  st.unit_k = (int)((b >> 12) & 0xfu);
+  extra = b >> 16;
 }
 
 // Segment s of the batch: the first u.n_reads are implicit whole reads of one length on a fixed stride (no descriptor
@@ -762,100 +778,32 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   uint32_t *tab = warp_base + lane;                      // [class][lane] counters; warp scratch for the warp path
   uint32_t *rd = warp_base + kTabWords * 32 + lane;      // [word][lane] read columns
   uint32_t *qmem = warp_base + kTabWords * 32 + kLaneWords * 32;
-  LaneQueue qr{qmem, 0, 4};
-  LaneQueue q5{qmem + kQueueCap * 4, 0, 3};
-  LaneQueue q6{qmem + kQueueCap * 7, 0, 3};
-  LaneQueue qw{qmem + kQueueCap * 10, 0, 1};
+  // queue i (0: k = 3 rungs that need a recount, 1: k = 4, 2: k = 5, 3: k = 6) lives at qmem + i * kQueueCap * 3
+  int n3 = 0, n4 = 0, n5 = 0, n6 = 0;
+  uint32_t *qw = qmem + 4 * kQueueCap * 3;
   const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
   const uint32_t n_groups = (n_seg + 31) / 32;
   const uint32_t warps_total = gridDim.x * kLaneWarps;
   uint32_t grp = blockIdx.x * kLaneWarps + warp;
-  // Queue discipline (capacity 64 each): at the top of an iteration qr, q5 <= 63 and q6 < 32.  Downstream stages run
-  // before upstream ones, and {5, 6} run once more after R, so no push can overflow: R adds <= 32 to q5 (< 32 by then),
-  // stage 5 adds <= 32 to q6 (< 32 by then), stage A adds <= 32 to qr and q5 (both < 32 by then).
+  // Stage selection (all queues hold <= 64 entries): a stage pops <= 32 entries and pushes <= 32 into the next queue, and
+  // it only runs when that next queue holds < 32 -- downstream queues are served first; upstream work (new segments)
+  // is taken only when every queue is below a full batch; at the end the queues are drained upstream-first.
   while (true) {
     const bool more = grp < n_groups;
-#pragma unroll 1
-    for (int rep = 0; rep < 2; rep++) {
-      if (rep == 1) {
-        // ---- stage R: the k = 3 / k = 4 rungs that need a recount, 32 segments at a time
-        if (qr.n >= 32 || (!more && qr.n > 0)) {
-          const int nb = qr.n < 32 ? qr.n : 32;
-          const int first = qr.n - nb;
-          uint32_t s = 0, extra = 0;
-          ScanState st{-1, 0u, 0, 0};
-          int k = 0;
-          bool to5 = false;
-          if (lane < nb) {
-            queue_read(qr, first + lane, s, st, k, extra);
-            const strgpu_segment sg = load_segment(segs, nmask, u, s);
-            const int L = sg.len;
-            lane_stage(seq, sg, rd);
-            const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-            bool go = true;
-            for (; go && k <= 4; k++) {  // one call site: lanes at k = 3 and k = 4 recount together
-              const int M = k == 3 ? (int)(extra & 0xffu) : (int)((extra >> 8) & 0xffu);
-              const uint32_t leader = k == 3 ? ((extra >> 16) & 0x3fu) : ((extra >> 22) & 0xffu);
-              go = lane_decide(rd, tab, L, k, M, leader, thr[(size_t)(pclass * 5 + k - 2) * kThrLen + L], tg[(k - 2) * kThrLen + L], st);
-            }
-            if (go) to5 = true;
-            else emit_result(out, s, st);
-          }
-          __syncwarp();
-          qr.n = first;
-          queue_push(q5, to5, lane, s, st, 5);
-        }
-      }
-      // ---- stage 5: k = 5 with packed uint8 counters
-      if (q5.n >= 32 || (!more && qr.n == 0 && q5.n > 0)) {
-        const int nb = q5.n < 32 ? q5.n : 32;
-        const int first = q5.n - nb;
-        uint32_t s = 0, extra = 0;
-        ScanState st{-1, 0u, 0, 0};
-        int k = 0;
-        bool to6 = false;
-        if (lane < nb) {
-          queue_read(q5, first + lane, s, st, k, extra);
-          const strgpu_segment sg = load_segment(segs, nmask, u, s);
-          const int L = sg.len;
-          lane_stage(seq, sg, rd);
-          int M;
-          uint32_t leader;
-          lane_count5(rd, tab, lut, L, M, leader);
-          const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-          const bool go = lane_decide(rd, tab, L, 5, M, leader, thr[(size_t)(pclass * 5 + 3) * kThrLen + L], tg[3 * kThrLen + L], st);
-          if (go) to6 = true;
-          else emit_result(out, s, st);
-        }
-        __syncwarp();
-        q5.n = first;
-        queue_push(q6, to6, lane, s, st, 6);
-      }
-      // ---- stage 6: k = 6 in an open-addressing table; the ladder ends here
-      if (q6.n >= 32 || (!more && qr.n == 0 && q5.n == 0 && q6.n > 0)) {
-        const int nb = q6.n < 32 ? q6.n : 32;
-        const int first = q6.n - nb;
-        if (lane < nb) {
-          uint32_t s, extra;
-          ScanState st;
-          int k;
-          queue_read(q6, first + lane, s, st, k, extra);
-          const strgpu_segment sg = load_segment(segs, nmask, u, s);
-          const int L = sg.len;
-          lane_stage(seq, sg, rd);
-          int M;
-          uint32_t leader;
-          lane_count6(rd, tab, L, M, leader);
-          const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-          lane_decide(rd, tab, L, 6, M, leader, thr[(size_t)(pclass * 5 + 4) * kThrLen + L], tg[4 * kThrLen + L], st);
-          emit_result(out, s, st);
-        }
-        __syncwarp();
-        q6.n = first;
-      }
-    }
-    if (more) {
-      // ---- stage A: count k = 2, 3, 4; k = 2 decision (its recount is warp-uniform); later rungs as far as they need no recount
+    int stage;
+    if (n6 >= 32) stage = 6;
+    else if (n5 >= 32) stage = 5;
+    else if (n4 >= 32) stage = 4;
+    else if (n3 >= 32) stage = 3;
+    else if (more) stage = 2;
+    else if (n3 > 0) stage = 3;
+    else if (n4 > 0) stage = 4;
+    else if (n5 > 0) stage = 5;
+    else if (n6 > 0) stage = 6;
+    else break;
+
+    if (stage == 2) {
+      // ---- stage A: count k = 2 and 3; the k = 2 rung (its recount is warp-uniform); the k = 3 rung if it needs no recount
       const uint32_t s = grp * 32 + lane;
       grp += warps_total;
       const bool active = s < n_seg;
@@ -864,50 +812,81 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
       const int L = sg.len;
       const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
       ScanState st{-1, 0u, 0, 0};
-      int next_k = 0;  // 0: finished, 3 / 4: needs that rung's recount (QR), 5: goes on to k = 5
+      int next_k = 0;  // 0: finished, 3: needs the k = 3 recount (QR), 4: goes on to k = 4
       uint32_t extra = 0;
       if (lane_path) {
         lane_stage(seq, sg, rd);
-        Lead l2, l3, l4;
-        lane_count234(rd, tab, lut, L, l2, l3, l4);
+        uint32_t best2, best3;
+        lane_count23(rd, tab, lut, L, best2, best3);
         const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
         const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
-        const uint32_t lead2 = l2.off == 0xffffffffu ? 0xfu : (uint32_t)lut[kRev234 + (l2.off >> 7)];
-        const uint32_t lead3 = l3.off == 0xffffffffu ? 0x3fu : (uint32_t)lut[kRev234 + (l3.off >> 7)];
-        const uint32_t lead4 = l4.off == 0xffffffffu
-                                   ? 0xffu
-                                   : (uint32_t)lut[kRev234 + kCls2 + kCls3 + ((l4.off >> 7) - (kCls2 + kCls3)) * 4 + ((l4.off & 31u) >> 3)];
-        extra = (uint32_t)l3.M | ((uint32_t)l4.M << 8) | (lead3 << 16) | (lead4 << 22);
-        bool go = lane_decide(rd, tab, L, 2, l2.M, lead2, tp[0], tg[L], st);
+        const int M2 = (int)(best2 >> 13), M3 = (int)(best3 >> 13);
+        const uint32_t lead2 = M2 ? (uint32_t)lut[kRev234 + (best2 & 31u)] : 0xfu;
+        const uint32_t lead3 = M3 ? (uint32_t)lut[kRev234 + kCls2 + (best3 & 31u)] : 0x3fu;
+        extra = (uint32_t)M3 | (lead3 << 8);
+        bool go = lane_decide(rd, tab, L, 2, M2, lead2, tp[0], tg[L], st);
         if (go) {
-          if (3 * l3.M > st.best) next_k = 3;                       // needs the k = 3 recount
-          else go = !(l3.M < (int)tg[kThrLen + L]);
+          if (3 * M3 > st.best) next_k = 3;                       // needs the k = 3 recount
+          else go = !(M3 < (int)tg[kThrLen + L]);
         }
-        if (go && next_k == 0) {
-          if (4 * l4.M > st.best) next_k = 4;                       // needs the k = 4 recount
-          else go = !(l4.M < (int)tg[2 * kThrLen + L]);
-        }
-        if (go && next_k == 0) next_k = 5;
+        if (go && next_k == 0) next_k = 4;
         if (!go) emit_result(out, s, st);
       }
       __syncwarp();
-      queue_push(qr, next_k == 3 || next_k == 4, lane, s, st, next_k, extra);
-      queue_push(q5, next_k == 5, lane, s, st, 5);
-      queue_push(qw, active && !lane_path, lane, s, st, 2);
-    }
-    // ---- segments with non-ACGT bases or longer than 160 bases: one at a time on the whole warp
-    if (qw.n > 0) {
-      WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(warp_base);
-      for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
+      queue_push(qmem, n3, next_k == 3, lane, s, st, extra);
+      queue_push(qmem + kQueueCap * 3, n4, next_k == 4, lane, s, st, 0);
+      // segments with non-ACGT bases or longer than 160 bases: one at a time on the whole warp
+      const uint32_t wm = __ballot_sync(kFull, active && !lane_path);
+      if (active && !lane_path) qw[__popc(wm & ((1u << lane) - 1u))] = s;
+      const int nw = __popc(wm);
       __syncwarp();
-      for (int e = 0; e < qw.n; e++) {
-        const uint32_t s = qw.buf[e];
-        warp_scan_compact(ws, seq, nmask, load_segment(segs, nmask, u, s), s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
+      if (nw > 0) {
+        WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(warp_base);
+        for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
+        __syncwarp();
+        for (int e = 0; e < nw; e++) {
+          const uint32_t ws_s = qw[e];
+          warp_scan_compact(ws, seq, nmask, load_segment(segs, nmask, u, ws_s), ws_s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      qw.n = 0;
+      continue;
     }
-    if (!more && qr.n == 0 && q5.n == 0 && q6.n == 0) break;
+
+    // ---- queued stages: 32 segments at a time, one per lane
+    uint32_t *qbuf = qmem + (stage - 3) * (kQueueCap * 3);
+    const int qn = stage == 3 ? n3 : (stage == 4 ? n4 : (stage == 5 ? n5 : n6));
+    const int nb = qn < 32 ? qn : 32;
+    const int first = qn - nb;
+    uint32_t s = 0, extra = 0;
+    ScanState st{-1, 0u, 0, 0};
+    bool go = false;
+    if (lane < nb) {
+      queue_read(qbuf, first + lane, s, st, extra);
+      const strgpu_segment sg = load_segment(segs, nmask, u, s);
+      const int L = sg.len;
+      lane_stage(seq, sg, rd);
+      const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+      int M;
+      uint32_t leader;
+      if (stage == 3) {          // the k = 3 rung with its recount; counts were taken in stage A
+        M = (int)(extra & 0xffu);
+        leader = (extra >> 8) & 0x3fu;
+      } else if (stage == 4) {
+        lane_count4(rd, tab, lut, L, M, leader);
+      } else if (stage == 5) {
+        lane_count5(rd, tab, lut, L, M, leader);
+      } else {
+        lane_count6(rd, tab, L, M, leader);
+      }
+      go = lane_decide(rd, tab, L, stage, M, leader, thr[(size_t)(pclass * 5 + stage - 2) * kThrLen + L], tg[(stage - 2) * kThrLen + L], st);
+      if (!go || stage == 6) emit_result(out, s, st);
+    }
+    __syncwarp();
+    if (stage == 3) { n3 = first; queue_push(qmem + kQueueCap * 3, n4, go, lane, s, st, 0); }
+    else if (stage == 4) { n4 = first; queue_push(qmem + kQueueCap * 6, n5, go, lane, s, st, 0); }
+    else if (stage == 5) { n5 = first; queue_push(qmem + kQueueCap * 9, n6, go, lane, s, st, 0); }
+    else n6 = first;
   }
 }
 
