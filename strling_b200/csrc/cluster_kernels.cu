@@ -7,7 +7,8 @@
 //       are skipped.
 //   K3  next(i) = first read NOT absorbed by a cluster started at read i (trcluster, cluster.nim:323-362) is a
 //       pure function of i: <= 8 explicit steps while the median-of-first-9 still moves, then one binary search.
-//       Bucket heads then chase next() to mark cluster starts.
+//       Bucket heads then chase next() to mark cluster starts; the chase is cut into 256-record pieces (exit tables per
+//       piece, a piece-to-piece hop per bucket, a marking sweep per piece) so it stays parallel for huge buckets.
 //   K4  one thread per chained cluster: trim, left/right_most, min_support + anchor test, split_cluster, bounds,
 //       filters, has_per_sample_reads.  CountTable.largest ties follow Nim's slot order (hashWangYi1 + linear
 //       probing + growth), emulated in a per-cluster scratch region.
@@ -132,14 +133,20 @@ __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint3
     d1 = r.mid ^ fm;
     d2 = r.hi ^ ((uint32_t)f.tid ^ 0x80000000u);
   }
+  // OR-reduce over the block, then one atomic per block and field
+  __shared__ uint32_t blk[3];
+  if (threadIdx.x < 3) blk[threadIdx.x] = 0;
+  __syncthreads();
   d0 = __reduce_or_sync(kFull, d0);
   d1 = __reduce_or_sync(kFull, d1);
   d2 = __reduce_or_sync(kFull, d2);
   if ((threadIdx.x & 31) == 0) {
-    if (d0) atomicOr(&varbits[0], d0);
-    if (d1) atomicOr(&varbits[1], d1);
-    if (d2) atomicOr(&varbits[2], d2);
+    if (d0) atomicOr(&blk[0], d0);
+    if (d1) atomicOr(&blk[1], d1);
+    if (d2) atomicOr(&blk[2], d2);
   }
+  __syncthreads();
+  if (threadIdx.x < 3 && blk[threadIdx.x]) atomicOr(&varbits[threadIdx.x], blk[threadIdx.x]);
 }
 
 __device__ __forceinline__ uint32_t digit_of(const SortRec &r, int field, int shift) {
@@ -313,16 +320,55 @@ __global__ void cluster_next(const SortRec *__restrict__ recs, uint32_t n, uint3
   next[i] = j;
 }
 
-__global__ void cluster_heads(const SortRec *__restrict__ recs, uint32_t n, const uint32_t *__restrict__ next,
-                              const uint32_t *__restrict__ bucket_end, uint32_t *__restrict__ head) {
+// Cluster starts = the chain bucket_start -> next -> next ... of every bucket.  The walk is cut into pieces of kSeg records
+// so that no thread takes more than kSeg steps (a bucket can hold 10^5 reads):
+//   seg_exits : for every record i of a piece, exit[i] = the first index >= the piece's end that the chain through i reaches
+//               (a reverse sweep of the piece; next[i] > i always)
+//   seg_entry : one thread per bucket hops piece to piece (entry -> exit[entry]) and records each piece's entry point
+//   seg_mark  : one thread per entered piece marks the cluster starts inside it
+constexpr uint32_t kSeg = 256;
+
+__global__ void seg_exits(const uint32_t *__restrict__ next, const uint32_t *__restrict__ bucket_end, uint32_t n,
+                          uint32_t *__restrict__ exit_of) {
+  const uint32_t sgi = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lo = sgi * kSeg;
+  if (lo >= n) return;
+  const uint32_t hi = min(n, lo + kSeg);
+  for (uint32_t i = hi; i-- > lo;) {
+    const uint32_t nx = next[i];
+    // a chain never leaves its bucket: next[i] <= bucket_end[i]; stop at the piece end or the bucket end
+    exit_of[i] = (nx >= hi || nx >= bucket_end[i]) ? nx : exit_of[nx];
+  }
+}
+
+__global__ void seg_entry(const SortRec *__restrict__ recs, uint32_t n, const uint32_t *__restrict__ bucket_end,
+                          const uint32_t *__restrict__ exit_of, uint32_t *__restrict__ entry_of_seg) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (i > 0 && same_bucket(recs[i - 1], recs[i])) return;  // only bucket starts walk their chain
+  if (i > 0 && same_bucket(recs[i - 1], recs[i])) return;  // bucket starts only
   const uint32_t be = bucket_end[i];
   uint32_t h = i;
   while (h < be) {
-    head[h] = 1;
-    h = next[h];
+    // several buckets can start inside one piece: keep the piece's entries as a linked list through the records
+    entry_of_seg[h] = 1;   // h is a cluster start and the point where the chain enters (or re-enters) its piece
+    h = exit_of[h];
+  }
+}
+
+__global__ void seg_mark(const uint32_t *__restrict__ next, const uint32_t *__restrict__ bucket_end, uint32_t n,
+                         const uint32_t *__restrict__ entry_flag, uint32_t *__restrict__ head) {
+  const uint32_t sgi = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lo = sgi * kSeg;
+  if (lo >= n) return;
+  const uint32_t hi = min(n, lo + kSeg);
+  for (uint32_t e = lo; e < hi; e++) {
+    if (!entry_flag[e]) continue;          // chains enter the piece here (one per bucket that touches the piece)
+    const uint32_t be = bucket_end[e];
+    uint32_t h = e;
+    while (h < hi && h < be) {
+      head[h] = 1;
+      h = next[h];
+    }
   }
 }
 
@@ -707,8 +753,17 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   uint32_t *next = (uint32_t *)ws.buf[WS_NEXT], *bend = (uint32_t *)ws.buf[WS_BEND], *head = (uint32_t *)ws.buf[WS_HEAD],
            *cid = (uint32_t *)ws.buf[WS_CID];
   cluster_next<<<nb2, T, 0, st>>>(ra, n, p.window, next, bend, head);
-  cluster_heads<<<nb2, T, 0, st>>>(ra, n, next, bend, head);
-  *launches += 2;
+  {
+    // chain walk in pieces of kSeg records (see seg_exits): cid doubles as exit_of, the scatter buffer rb as entry flags
+    uint32_t *exit_of = cid;
+    uint32_t *entry_flag = reinterpret_cast<uint32_t *>(rb);
+    const uint32_t n_seg = (n + kSeg - 1) / kSeg;
+    CK(cudaMemsetAsync(entry_flag, 0, (size_t)n * 4, st));
+    seg_exits<<<(n_seg + 63) / 64, 64, 0, st>>>(next, bend, n, exit_of);
+    seg_entry<<<nb2, T, 0, st>>>(ra, n, bend, exit_of, entry_flag);
+    seg_mark<<<(n_seg + 63) / 64, 64, 0, st>>>(next, bend, n, entry_flag, head);
+  }
+  *launches += 4;
   CK(exclusive_scan(ws, head, cid, n, d_small + 3, st, launches));
   uint32_t n_clusters = 0;
   CK(cudaMemcpyAsync(&n_clusters, d_small + 3, 4, cudaMemcpyDeviceToHost, st));
