@@ -201,6 +201,12 @@ int strgpu_set_proportions(strgpu_ctx *ctx, const double *p, int n) {
         h[(cls * 5 + (k - 2)) * strgpu::kThrLen + len] = (uint16_t)v;
       }
   }
+  for (int cls = 0; cls < STRGPU_MAX_PCLASS; cls++)
+    for (int len = 0; len < strgpu::kThrLen; len++) {
+      uint16_t m = 65535;
+      for (int k = 2; k <= 6; k++) m = std::min(m, h[(cls * 5 + (k - 2)) * strgpu::kThrLen + len]);
+      h[strgpu::kThrMinOff + cls * strgpu::kThrLen + len] = m;
+    }
   // all slots idle? thresholds are read by in-flight kernels, so drain first
   for (auto &s : ctx->slots) CU(ctx, cudaStreamSynchronize(s.stream));
   cudaError_t e = cudaMemcpy(ctx->d_thr, h, strgpu::kThrEntries * sizeof(uint16_t), cudaMemcpyHostToDevice);

@@ -293,7 +293,10 @@ constexpr int kTabWords = kCls2 + kCls3 + kCls4Words;  // 52 words per lane; k =
 constexpr int kLut2 = 0, kLut3 = 16, kLut4 = 80, kRev234 = 336, kLut5 = 440, kRev5 = 1464;  // offsets into the uint16 table
 constexpr int kLutTotal = 1672;
 constexpr int kQueueCap = 64;                  // a batch is taken at 32 entries and a stage adds at most 32
-constexpr int kQueueWords = 4 * kQueueCap * 3 + 32;  // QR, Q4, Q5, Q6 (3 words/entry), QW (1 word/entry, cap 32)
+// Q3 (3 words/entry), Q4, Q5, Q6 (2 words/entry), Q2 (filter survivors, 1 word/entry), QW (1 word/entry, cap 32)
+constexpr int kQ3Off = 0, kQ4Off = kQueueCap * 3, kQ5Off = kQ4Off + kQueueCap * 2, kQ6Off = kQ5Off + kQueueCap * 2,
+              kQ2Off = kQ6Off + kQueueCap * 2, kQWOff = kQ2Off + kQueueCap;
+constexpr int kQueueWords = kQWOff + 32;
 constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + kQueueWords;
 constexpr int kLaneSmemBytes = kLaneWarps * kWarpSmemWords * 4 + kLutTotal * 2 + 16;
 static_assert(sizeof(WarpScratch<512>) <= (size_t)kTabWords * 32 * 4, "warp scratch must fit in the warp's counter region");
@@ -713,29 +716,31 @@ __device__ __forceinline__ void lane_count6(const uint32_t *rd, uint32_t *tab, i
   }
 }
 
-// Warp-local FIFOs of segments waiting for their next stage (three words per entry):
-//   0: segment index      1: best << 16 | repeat_count      2: unit_code | unit_k << 12 | extra << 16
-// (extra: M3 | leader3 << 8 for the k = 3 recount queue)
+// Warp-local FIFOs of segments waiting for their next stage.  Q4..Q6 entries are two words, Q3 entries three:
+//   0: segment index      1: best << 24 | repeat_count << 16 | unit_k << 12 | unit_code      2 (Q3 only): M3 | leader3 << 8
+// (entries are written after the k = 2 rung, so 0 <= best <= 160 and repeat_count <= 80)
+template <int WORDS>
 __device__ __forceinline__ void queue_push(uint32_t *buf, int &n, bool want, int lane, uint32_t s, const ScanState &st, uint32_t extra) {
   const uint32_t m = __ballot_sync(kFull, want);
   if (want) {
-    uint32_t *e = buf + 3 * (n + __popc(m & ((1u << lane) - 1u)));
+    uint32_t *e = buf + WORDS * (n + __popc(m & ((1u << lane) - 1u)));
     e[0] = s;
-    e[1] = ((uint32_t)(st.best & 0xffff) << 16) | (uint32_t)(st.rc & 0xffff);
-    e[2] = (st.unit_code & 0xfffu) | ((uint32_t)st.unit_k << 12) | (extra << 16);
+    if (WORDS >= 2) e[1] = ((uint32_t)(st.best & 0xff) << 24) | ((uint32_t)(st.rc & 0xff) << 16) | ((uint32_t)st.unit_k << 12) | (st.unit_code & 0xfffu);
+    if (WORDS >= 3) e[2] = extra;
   }
   n += __popc(m);
   __syncwarp();
 }
+template <int WORDS>
 __device__ __forceinline__ void queue_read(const uint32_t *buf, int i, uint32_t &s, ScanState &st, uint32_t &extra) {
-  const uint32_t *e = buf + 3 * i;
+  const uint32_t *e = buf + WORDS * i;
   s = e[0];
-  const uint32_t a = e[1], b = e[2];
-  st.best = (int)(int16_t)(a >> 16);
-  st.rc = (int)(a & 0xffffu);
-  st.unit_code = b & 0xfffu;
-  st.unit_k = (int)((b >> 12) & 0xfu);
-  extra = b >> 16;
+  const uint32_t a = e[1];
+  st.best = (int)(a >> 24);
+  st.rc = (int)((a >> 16) & 0xffu);
+  st.unit_k = (int)((a >> 12) & 0xfu);
+  st.unit_code = a & 0xfffu;
+  extra = WORDS >= 3 ? e[2] : 0u;
 }
 
 // Segment s of the batch: the first u.n_reads are implicit whole reads of one length on a fixed stride (no descriptor
@@ -764,6 +769,87 @@ __device__ __forceinline__ strgpu_segment load_segment(const strgpu_segment *__r
   return sg;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Stage 1: the exact pre-filter.  get_repeat (utils.nim:236-271) can only return a unit when, at some rung k, the
+// greedy non-overlapping count of a k-mer s (read.count(s), utils.nim:254) exceeds int(L * p / k) (utils.nim:259).  That
+// count is at most the number of positions where s starts, which is at most the number of positions where the 2-mer
+// s[0..2) starts.  So a segment whose most frequent 2-mer (all L - 1 overlapping positions) occurs at most
+// T = min_k int(L * p / k) times returns the empty unit with repeat_count 0 whatever path the ladder takes: it is
+// finished here, bit-exactly, without ever being counted.  ~95 % of the reads of a sequencing run end here.
+//
+// The 16 occurrence counts are taken bit-parallel.  Two 16-base words are merged into dense 32-position planes
+// (hi / lo bit of every base; the odd bits of a plane belong to the first word, the even bits to the second), once for
+// the bases themselves (P) and once for their successors (Q); E_a = positions holding base a, E_a & (Q == b) =
+// positions where the 2-mer ab starts.  Only b = 0..2 are counted, b = 3 follows from popc(E_a).
+constexpr uint32_t kOdd = 0xaaaaaaaau, kEven = 0x55555555u;
+
+// valid-position masks of the five word pairs for a segment of L bases (positions 0 .. L - 2 start a 2-mer)
+__device__ __forceinline__ void filter_masks(int L, uint32_t (&V)[5]) {
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const int v = L - 1 - 32 * j;
+    const int v0 = min(max(v, 0), 16), v1 = min(max(v - 16, 0), 16);
+    const uint32_t m0 = v0 >= 16 ? kOdd : (kOdd & ~(kFull >> (2 * v0)));
+    const uint32_t m1 = v1 >= 16 ? kEven : (kEven & ~(kFull >> (2 * v1)));
+    V[j] = m0 | m1;
+  }
+}
+
+template <int VARIANT>
+__device__ __forceinline__ int lane_filter_max2(const uint32_t (&w)[11], const uint32_t (&V)[5]) {
+  uint32_t E[5][4], Qh[5], Ql[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const uint32_t w0 = w[2 * j], w1 = w[2 * j + 1], w2 = w[2 * j + 2];
+    const uint32_t n0 = __funnelshift_l(w1, w0, 2), n1 = __funnelshift_l(w2, w1, 2);   // successor of every base
+    const uint32_t Ph = (w0 & kOdd) | ((w1 >> 1) & kEven), Pl = ((w0 << 1) & kOdd) | (w1 & kEven);
+    Qh[j] = (n0 & kOdd) | ((n1 >> 1) & kEven);
+    Ql[j] = ((n0 << 1) & kOdd) | (n1 & kEven);
+    E[j][0] = ~Ph & ~Pl & V[j];
+    E[j][1] = ~Ph & Pl & V[j];
+    E[j][2] = Ph & ~Pl & V[j];
+    E[j][3] = Ph & Pl & V[j];
+  }
+  int best = 0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    int ca[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      uint32_t m[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const uint32_t e = E[j][a];
+        m[j] = b == 0 ? (e & ~Qh[j] & ~Ql[j]) : (b == 1 ? (e & ~Qh[j] & Ql[j]) : (b == 2 ? (e & Qh[j] & ~Ql[j]) : e));
+      }
+      if (VARIANT == 0) {
+        ca[b] = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]);
+      } else {  // carry-save: five words -> one "ones" and two "twos" words, three popcounts instead of five
+        const uint32_t s1 = m[0] ^ m[1] ^ m[2], c1 = (m[0] & m[1]) | (m[2] & (m[0] | m[1]));
+        const uint32_t s2 = s1 ^ m[3] ^ m[4], c2 = (s1 & m[3]) | (m[4] & (s1 | m[3]));
+        ca[b] = __popc(s2) + 2 * (__popc(c1) + __popc(c2));
+      }
+    }
+    ca[3] -= ca[0] + ca[1] + ca[2];
+    best = max(best, max(max(ca[0], ca[1]), max(ca[2], ca[3])));
+  }
+  return best;
+}
+
+// the lane's segment as eleven aligned words in registers (base 0 at bit 31 of w[0]); w[10] only ever feeds a masked slot
+__device__ __forceinline__ void lane_load(const uint32_t *__restrict__ seq, const strgpu_segment &sg, uint32_t (&w)[11]) {
+  const uint32_t g = sg.base_off >> 4;
+  const uint32_t sh = 2u * (sg.base_off & 15u);
+  const int n_words = (2 * (int)sg.len + 31) >> 5;
+  uint32_t raw[kLaneWords];
+#pragma unroll
+  for (int j = 0; j < kLaneWords; j++) raw[j] = (j <= n_words) ? __byte_perm(seq[g + j], 0, 0x0123) : 0u;
+#pragma unroll
+  for (int j = 0; j < kLaneWords - 1; j++) w[j] = __funnelshift_l(raw[j + 1], raw[j], sh);
+  w[kLaneWords - 1] = 0u;
+}
+
+template <int FILTER>
 __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                     const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                     const UniformReads u,
@@ -778,13 +864,15 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   uint32_t *tab = warp_base + lane;                      // [class][lane] counters; warp scratch for the warp path
   uint32_t *rd = warp_base + kTabWords * 32 + lane;      // [word][lane] read columns
   uint32_t *qmem = warp_base + kTabWords * 32 + kLaneWords * 32;
-  // queue i (0: k = 3 rungs that need a recount, 1: k = 4, 2: k = 5, 3: k = 6) lives at qmem + i * kQueueCap * 3
-  int n3 = 0, n4 = 0, n5 = 0, n6 = 0;
-  uint32_t *qw = qmem + 4 * kQueueCap * 3;
+  uint32_t *q2 = qmem + kQ2Off, *q3 = qmem + kQ3Off, *q4 = qmem + kQ4Off, *q5 = qmem + kQ5Off, *q6 = qmem + kQ6Off, *qw = qmem + kQWOff;
+  int n2 = 0, n3 = 0, n4 = 0, n5 = 0, n6 = 0;
   const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
+  const uint16_t *tmin = thr + kThrMinOff;
   const uint32_t n_groups = (n_seg + 31) / 32;
   const uint32_t warps_total = gridDim.x * kLaneWarps;
   uint32_t grp = blockIdx.x * kLaneWarps + warp;
+  uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
+  int v_len = -1;
   // Stage selection (all queues hold <= 64 entries): a stage pops <= 32 entries and pushes <= 32 into the next queue, and
   // it only runs when that next queue holds < 32 -- downstream queues are served first; upstream work (new segments)
   // is taken only when every queue is below a full batch; at the end the queues are drained upstream-first.
@@ -795,26 +883,67 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
     else if (n5 >= 32) stage = 5;
     else if (n4 >= 32) stage = 4;
     else if (n3 >= 32) stage = 3;
-    else if (more) stage = 2;
+    else if (n2 >= 32) stage = 2;
+    else if (more) stage = 1;
+    else if (n2 > 0) stage = 2;
     else if (n3 > 0) stage = 3;
     else if (n4 > 0) stage = 4;
     else if (n5 > 0) stage = 5;
     else if (n6 > 0) stage = 6;
     else break;
 
+    if (stage == 1) {
+      // ---- stage 1: new segments, 32 per pass: the 2-mer pre-filter finishes most of them; survivors go to Q2
+      do {
+        const uint32_t s = grp * 32 + lane;
+        grp += warps_total;
+        const bool active = s < n_seg;
+        strgpu_segment sg{0, 0, 0, 0};
+        if (active) sg = load_segment(segs, nmask, u, s);
+        const int L = sg.len;
+        const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
+        bool survive = lane_path;
+        if (lane_path && FILTER >= 0) {
+          uint32_t w[kLaneWords];
+          lane_load(seq, sg, w);
+          if (L != v_len) {
+            filter_masks(L, V);
+            v_len = L;
+          }
+          const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+          survive = lane_filter_max2<(FILTER > 0 ? 1 : 0)>(w, V) > (int)tmin[pclass * kThrLen + L];
+          if (!survive) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
+        }
+        queue_push<1>(q2, n2, survive, lane, s, ScanState{0, 0u, 0, 0}, 0);
+        // segments with non-ACGT bases or longer than 160 bases: one at a time on the whole warp
+        const uint32_t wm = __ballot_sync(kFull, active && !lane_path);
+        if (wm != 0u) {
+          if (active && !lane_path) qw[__popc(wm & ((1u << lane) - 1u))] = s;
+          const int nw = __popc(wm);
+          WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(warp_base);
+          for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
+          __syncwarp();
+          for (int e = 0; e < nw; e++) {
+            const uint32_t ws_s = qw[e];
+            warp_scan_compact(ws, seq, nmask, load_segment(segs, nmask, u, ws_s), ws_s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
+          }
+          __syncwarp();
+        }
+      } while (grp < n_groups && n2 < 32);
+      continue;
+    }
+
     if (stage == 2) {
-      // ---- stage A: count k = 2 and 3; the k = 2 rung (its recount is warp-uniform); the k = 3 rung if it needs no recount
-      const uint32_t s = grp * 32 + lane;
-      grp += warps_total;
-      const bool active = s < n_seg;
-      strgpu_segment sg{0, 0, 0, 0};
-      if (active) sg = load_segment(segs, nmask, u, s);
-      const int L = sg.len;
-      const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
+      // ---- stage 2: count k = 2 and 3; the k = 2 rung (its recount is warp-uniform); the k = 3 rung if it needs no recount
+      const int nb = n2 < 32 ? n2 : 32;
+      const int first = n2 - nb;
+      uint32_t s = 0, extra = 0;
       ScanState st{-1, 0u, 0, 0};
-      int next_k = 0;  // 0: finished, 3: needs the k = 3 recount (QR), 4: goes on to k = 4
-      uint32_t extra = 0;
-      if (lane_path) {
+      int next_k = 0;  // 0: finished, 3: needs the k = 3 recount (Q3), 4: goes on to k = 4
+      if (lane < nb) {
+        s = q2[first + lane];
+        const strgpu_segment sg = load_segment(segs, nmask, u, s);
+        const int L = sg.len;
         lane_stage(seq, sg, rd);
         uint32_t best2, best3;
         lane_count23(rd, tab, lut, L, best2, best3);
@@ -833,28 +962,13 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
         if (!go) emit_result(out, s, st);
       }
       __syncwarp();
-      queue_push(qmem, n3, next_k == 3, lane, s, st, extra);
-      queue_push(qmem + kQueueCap * 3, n4, next_k == 4, lane, s, st, 0);
-      // segments with non-ACGT bases or longer than 160 bases: one at a time on the whole warp
-      const uint32_t wm = __ballot_sync(kFull, active && !lane_path);
-      if (active && !lane_path) qw[__popc(wm & ((1u << lane) - 1u))] = s;
-      const int nw = __popc(wm);
-      __syncwarp();
-      if (nw > 0) {
-        WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(warp_base);
-        for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
-        __syncwarp();
-        for (int e = 0; e < nw; e++) {
-          const uint32_t ws_s = qw[e];
-          warp_scan_compact(ws, seq, nmask, load_segment(segs, nmask, u, ws_s), ws_s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
-        }
-        __syncwarp();
-      }
+      n2 = first;
+      queue_push<3>(q3, n3, next_k == 3, lane, s, st, extra);
+      queue_push<2>(q4, n4, next_k == 4, lane, s, st, 0);
       continue;
     }
 
     // ---- queued stages: 32 segments at a time, one per lane
-    uint32_t *qbuf = qmem + (stage - 3) * (kQueueCap * 3);
     const int qn = stage == 3 ? n3 : (stage == 4 ? n4 : (stage == 5 ? n5 : n6));
     const int nb = qn < 32 ? qn : 32;
     const int first = qn - nb;
@@ -862,14 +976,15 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
     ScanState st{-1, 0u, 0, 0};
     bool go = false;
     if (lane < nb) {
-      queue_read(qbuf, first + lane, s, st, extra);
+      if (stage == 3) queue_read<3>(q3, first + lane, s, st, extra);
+      else queue_read<2>(stage == 4 ? q4 : (stage == 5 ? q5 : q6), first + lane, s, st, extra);
       const strgpu_segment sg = load_segment(segs, nmask, u, s);
       const int L = sg.len;
       lane_stage(seq, sg, rd);
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
       int M;
       uint32_t leader;
-      if (stage == 3) {          // the k = 3 rung with its recount; counts were taken in stage A
+      if (stage == 3) {          // the k = 3 rung with its recount; counts were taken in stage 2
         M = (int)(extra & 0xffu);
         leader = (extra >> 8) & 0x3fu;
       } else if (stage == 4) {
@@ -883,9 +998,9 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
       if (!go || stage == 6) emit_result(out, s, st);
     }
     __syncwarp();
-    if (stage == 3) { n3 = first; queue_push(qmem + kQueueCap * 3, n4, go, lane, s, st, 0); }
-    else if (stage == 4) { n4 = first; queue_push(qmem + kQueueCap * 6, n5, go, lane, s, st, 0); }
-    else if (stage == 5) { n5 = first; queue_push(qmem + kQueueCap * 9, n6, go, lane, s, st, 0); }
+    if (stage == 3) { n3 = first; queue_push<2>(q4, n4, go, lane, s, st, 0); }
+    else if (stage == 4) { n4 = first; queue_push<2>(q5, n5, go, lane, s, st, 0); }
+    else if (stage == 5) { n5 = first; queue_push<2>(q6, n6, go, lane, s, st, 0); }
     else n6 = first;
   }
 }
@@ -935,24 +1050,25 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
   if (uniform) {
     u = *uniform;
     if (u.read_len > (uint32_t)kShortMaxLen) return cudaErrorInvalidValue;  // callers expand long uniform reads into descriptors
-    variant = 0;
+    if (variant == 1) variant = 0;
   }
   constexpr int kWarps = 8;
   const uint32_t blocks_needed = (n_seg + kWarps - 1) / kWarps;
   if (max_len <= (uint32_t)kShortMaxLen && variant != 1) {
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(repeat_scan_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmemBytes);
+    // variant 0: pre-filter with plain popcounts, 2: pre-filter with carry-save popcounts, 3: no pre-filter (A/B runs)
+    auto kernel = variant == 2 ? repeat_scan_lane<1> : (variant == 3 ? repeat_scan_lane<-1> : repeat_scan_lane<0>);
+    static bool configured[4] = {false, false, false, false};
+    if (!configured[variant & 3]) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmemBytes);
       if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(repeat_scan_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       if (e != cudaSuccess) return e;
-      configured = true;
+      configured[variant & 3] = true;
     }
     const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
     uint32_t grid = (uint32_t)sm_count;  // one persistent CTA of 20 warps per SM
     if (grid > tiles) grid = tiles;
-    repeat_scan_lane<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out,
-                                                                     d_status);
+    kernel<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out, d_status);
   } else if (max_len <= (uint32_t)kShortMaxLen) {
     uint32_t grid = (uint32_t)sm_count * 8u;  // 8 resident CTAs of 256 threads per SM
     if (grid > blocks_needed) grid = blocks_needed;

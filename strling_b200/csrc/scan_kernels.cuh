@@ -9,17 +9,21 @@ namespace strgpu {
 
 constexpr int kThrLen = 512;                    // thresholds tabulated for len 0..511
 constexpr int kThrClasses = STRGPU_MAX_PCLASS + 1;  // + the 0.12 "give up" class (utils.nim:251)
-constexpr int kThrEntries = kThrClasses * 5 * kThrLen;
+constexpr int kThrMinOff = kThrClasses * 5 * kThrLen;       // then min over k = 2..6 per (proportion class, len): the pre-filter bound
+constexpr int kThrEntries = kThrMinOff + STRGPU_MAX_PCLASS * kThrLen;
 constexpr int kShortMaxLen = 160;               // kernel variant with the read in <= 10 words
 
-// thr[(cls * 5 + (k - 2)) * kThrLen + len] = int(len * p_cls / k); cls == STRGPU_MAX_PCLASS holds int(len * 0.12 / k)
+// thr[(cls * 5 + (k - 2)) * kThrLen + len] = int(len * p_cls / k); cls == STRGPU_MAX_PCLASS holds int(len * 0.12 / k);
+// thr[kThrMinOff + cls * kThrLen + len] = min over k of the class's thresholds
 // Implicit whole-read segments: read i = bases [i * stride, i * stride + read_len), proportion class pclass.
 struct UniformReads {
   uint32_t n_reads, read_len, stride, pclass;
 };
 
-// variant: 0 = default (lane-per-segment kernel for batches of <= 160-base segments, warp-per-segment otherwise),
-//          1 = force the warp-per-segment kernel (kept for A/B measurements and as the long-segment path)
+// variant: 0 = default (lane-per-segment kernel with the 2-mer pre-filter for batches of <= 160-base segments,
+//              warp-per-segment otherwise),
+//          1 = force the warp-per-segment kernel (kept for A/B measurements and as the long-segment path),
+//          2 = lane kernel, pre-filter with carry-save popcounts, 3 = lane kernel without the pre-filter (A/B)
 cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
                                uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
                                strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,

@@ -127,9 +127,49 @@ def test_too_long_segment_is_reported(gpu):
     assert [(bytes(r["unit"]).rstrip(b"\0"), int(r["repeat_count"])) for r in res] == [(b"A", 200), (b"CAG", 50)]
 
 
-@pytest.mark.parametrize("variant", ["0", "1"])
+def test_prefilter_threshold_boundary(gpu):
+    # The lane kernel finishes a segment early when its most frequent 2-mer occurs <= min_k int(L * p / k) times
+    # (exact: no k-mer can then beat its threshold, utils.nim:254-259).  Reads built to sit on both sides of that bound:
+    # c scattered copies of a k-mer with c around int(L * p / k), the rest random filler.
+    rng = np.random.default_rng(123)
+    cases = {0: [], 1: [], 2: []}
+    for pcls, p in enumerate(P):
+        for L in (150, 151, 160, 149, 120, 100, 75, 60, 48, 33, 17):
+            for k in range(2, 7):
+                t = int(float(L) * p / float(k))
+                for c in (t - 1, t, t + 1, t + 2):
+                    for _ in range(6):
+                        if c < 0 or c * k > L:
+                            continue
+                        unit = "".join(rng.choice(list("ACGT"), size=k))
+                        gaps = L - c * k
+                        cuts = np.sort(rng.integers(0, gaps + 1, size=c)) if c else np.zeros(0, dtype=int)
+                        filler = "".join(rng.choice(list("ACGT"), size=gaps))
+                        parts, prev = [], 0
+                        for cut in cuts:
+                            parts.append(filler[prev:cut])
+                            parts.append(unit)
+                            prev = cut
+                        parts.append(filler[prev:])
+                        r = "".join(parts)
+                        assert len(r) == L
+                        cases[pcls].append(r)
+    n_found = 0
+    for pcls, p in enumerate(P):
+        reads = cases[pcls]
+        seq2, nmask, segs, n_bases = sb.pack_reads(reads, pcls)
+        res = gpu.scan(seq2, n_bases, nmask, segs)
+        for r, got in zip(reads, res):
+            exp = orc.get_repeat(r, p)
+            assert (bytes(got["unit"]).rstrip(b"\0"), int(got["repeat_count"])) == exp, (r, p, got, exp)
+            n_found += exp[1] > 0
+    assert n_found > 500  # both sides of the bound are exercised
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
 def test_both_kernel_variants_agree_with_oracle(variant, monkeypatch):
-    monkeypatch.setenv("STRGPU_SCAN_VARIANT", variant)  # 0: lane-per-segment kernel, 1: warp-per-segment kernel
+    # 0: lane-per-segment kernel with the 2-mer pre-filter, 1: warp-per-segment kernel, 2: carry-save pre-filter, 3: no pre-filter
+    monkeypatch.setenv("STRGPU_SCAN_VARIANT", variant)
     g = sb.StrGpu(0)
     try:
         g.set_proportions(P)
