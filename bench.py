@@ -241,10 +241,16 @@ def run_ours(args):
         cl_stats["bounds_local"] = n_local
         cl_stats["bounds_all"] = int(sum(counts))
 
+    n_extra = n_seg - shard_reads           # soft-clip segments: the only ones that carry descriptors
+    extra_max = int(segs["len"][shard_reads:].max()) if n_extra else 0
+
     def step_device():
+        # the same entry-point family as the end-to-end leg (uniform reads without descriptors + clip descriptors),
+        # on device-resident buffers
         for b in range(n_sub):
-            g.scan_device(d_seq.data_ptr() + b * seq_bytes, None, d_segs.data_ptr() + b * n_seg * 8, n_seg, READ_LEN,
-                          d_out.data_ptr() + b * n_seg * 8, stream)
+            g.scan_reads_device(d_seq.data_ptr() + b * seq_bytes, shard_reads, READ_LEN, stride, 0, None,
+                                d_segs.data_ptr() + (b * n_seg + shard_reads) * 8, n_extra, extra_max,
+                                d_out.data_ptr() + b * n_seg * 8, stream)
         cluster_device_leg()
 
     # end-to-end leg: the descriptor-free uniform-read call (reads packed on a 152-base stride = 38 B/read; only the soft-clip
@@ -310,7 +316,7 @@ def run_ours(args):
     timed_ev = cl_events[-args.steps:]
     cluster_ms = float(np.mean([a.elapsed_time(b) for a, b, c in timed_ev]))
     gather_ms = float(np.mean([b.elapsed_time(c) for a, b, c in timed_ev]))
-    scan_launches = n_sub * args.steps
+    scan_launches = n_sub * args.steps      # library calls; each is a pre-filter kernel + a scan kernel over its survivors
     # spot-check: device-resident results of the last sub-batch equal the host-API results of the same shard
     sec_e2e, _, _ = timed(step_e2e, False)
     last = d_out[(n_sub - 1) * n_seg * 8:].cpu().numpy().view(sb.REPEAT_DTYPE)

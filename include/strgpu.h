@@ -122,6 +122,12 @@ int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_re
  * A too-long segment is reported by the next strgpu_device_status(). */
 int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask, const void *d_segs,
                        uint32_t n_seg, uint32_t max_len, void *d_out, void *cuda_stream);
+/* Device-resident variant of strgpu_scan_reads_submit (same argument meaning; d_seq2 must be 16-byte aligned for the
+ * TMA-staged path, otherwise per-lane loads are used): d_out[0 .. n_reads) receives the reads' results,
+ * d_out[n_reads .. n_reads + n_extra) the extra segments'. */
+int strgpu_scan_reads_device(strgpu_ctx *ctx, const void *d_seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
+                             uint32_t pclass, const void *d_nmask, const void *d_extra, uint32_t n_extra,
+                             uint32_t extra_max_len, void *d_out, void *cuda_stream);
 /* synchronises `cuda_stream` and returns the sticky device-side status of launches since the last call */
 int strgpu_device_status(strgpu_ctx *ctx, void *cuda_stream);
 

@@ -77,6 +77,7 @@ def load_library():
     L.strgpu_scan_wait.argtypes = [vp, i32]
     L.strgpu_scan.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp]
     L.strgpu_scan_device.argtypes = [vp, vp, vp, vp, u32, u32, vp, vp]
+    L.strgpu_scan_reads_device.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, u32, u32, vp, vp]
     L.strgpu_device_status.argtypes = [vp, vp]
     L.strgpu_cluster.argtypes = [vp, vp, u32, vp, vp, u32, C.POINTER(u32)]
     L.strgpu_cluster_loci.argtypes = [vp, vp, u32, vp, vp, u32, vp, u32, C.POINTER(u32)]
@@ -187,6 +188,12 @@ class StrGpu:
 
     def scan_wait(self, ticket: int):
         self._check(self.L.strgpu_scan_wait(self.h, ticket))
+
+    def scan_reads_device(self, d_seq2: int, n_reads: int, read_len: int, stride_bases: int, pclass: int, d_nmask: int | None,
+                          d_extra: int | None, n_extra: int, extra_max_len: int, d_out: int, stream: int = 0):
+        """Device-resident uniform-read batch (strgpu_scan_reads_device): all pointers are device addresses."""
+        self._check(self.L.strgpu_scan_reads_device(self.h, d_seq2, n_reads, read_len, stride_bases, pclass, d_nmask or None,
+                                                    d_extra or None, n_extra, extra_max_len, d_out, stream or None))
 
     def scan_device(self, d_seq2: int, d_nmask: int | None, d_segs: int, n_seg: int, max_len: int, d_out: int, stream: int = 0):
         self._check(self.L.strgpu_scan_device(self.h, d_seq2, d_nmask, d_segs, n_seg, max_len, d_out, stream or None))

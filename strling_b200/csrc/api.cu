@@ -33,7 +33,7 @@ struct DevBuf {
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
-  DevBuf seq, nmask, segs, out;
+  DevBuf seq, nmask, segs, out, list;  // list: survivor list of the pre-filter kernel (n_seg + 1 words)
   bool busy = false;
   strgpu_repeat *host_out = nullptr;
   uint32_t n_seg = 0;
@@ -55,6 +55,8 @@ struct strgpu_ctx {
   strgpu::ClusterWorkspace cluster_ws;
   cudaStream_t cluster_stream = nullptr;
   DevBuf cl_in, cl_out, cl_loci;
+  DevBuf dev_list;                   // survivor list for strgpu_scan_device launches
+  cudaEvent_t dev_list_done = nullptr;
   uint32_t *d_cl_n = nullptr;
   uint64_t launches = 0;
   char err[512] = {0};
@@ -141,6 +143,7 @@ int strgpu_create(strgpu_ctx **out, int device) {
     CU(ctx, cudaMallocHost(&s.h_status, sizeof(int)));
   }
   CU(ctx, cudaStreamCreateWithFlags(&ctx->cluster_stream, cudaStreamNonBlocking));
+  CU(ctx, cudaEventCreateWithFlags(&ctx->dev_list_done, cudaEventDisableTiming));
   CU(ctx, cudaMalloc(&ctx->d_cl_n, sizeof(uint32_t)));
   const double dflt[3] = {0.8, 0.8 - 0.07, 0.6};  // extract.nim:255,208,242 defaults
   return strgpu_set_proportions(ctx, dflt, 3);
@@ -151,7 +154,7 @@ void strgpu_destroy(strgpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &s : ctx->slots) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    for (DevBuf *b : {&s.seq, &s.nmask, &s.segs, &s.out})
+    for (DevBuf *b : {&s.seq, &s.nmask, &s.segs, &s.out, &s.list})
       if (b->p) cudaFree(b->p);
     if (s.d_status) cudaFree(s.d_status);
     if (s.h_status) cudaFreeHost(s.h_status);
@@ -162,6 +165,8 @@ void strgpu_destroy(strgpu_ctx *ctx) {
   if (ctx->cl_in.p) cudaFree(ctx->cl_in.p);
   if (ctx->cl_out.p) cudaFree(ctx->cl_out.p);
   if (ctx->cl_loci.p) cudaFree(ctx->cl_loci.p);
+  if (ctx->dev_list.p) cudaFree(ctx->dev_list.p);
+  if (ctx->dev_list_done) cudaEventDestroy(ctx->dev_list_done);
   if (ctx->d_cl_n) cudaFree(ctx->d_cl_n);
   if (ctx->cluster_stream) cudaStreamDestroy(ctx->cluster_stream);
   if (ctx->d_thr) cudaFree(ctx->d_thr);
@@ -236,6 +241,7 @@ int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, c
   if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
   if ((rc = ensure(ctx, s.segs, (size_t)n_seg * sizeof(strgpu_segment) + 16))) return rc;
   if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
+  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 1) * sizeof(uint32_t)))) return rc;
   s.n_seg = n_seg;
   s.host_out = out;
   if (n_seg) {
@@ -249,8 +255,9 @@ int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, c
     CU(ctx, cudaMemsetAsync(s.d_status, 0, sizeof(int), s.stream));
     CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
                                        (const strgpu_segment *)s.segs.p, n_seg, max_len, ctx->d_thr, ctx->d_luts,
-                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, ctx->variant, s.stream));
-    ctx->launches++;
+                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, ctx->variant, s.stream, nullptr,
+                                       (uint32_t *)s.list.p));
+    ctx->launches += strgpu::scan_launches(max_len, ctx->variant);
     CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
     CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   } else {
@@ -301,6 +308,7 @@ int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_re
   if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
   if ((rc = ensure(ctx, s.segs, (size_t)n_extra * sizeof(strgpu_segment) + 16))) return rc;
   if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
+  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 1) * sizeof(uint32_t)))) return rc;
   s.n_seg = n_seg;
   s.host_out = out;
   if (n_seg) {
@@ -315,8 +323,9 @@ int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_re
     const strgpu::UniformReads u{n_reads, read_len, stride_bases, pclass};
     CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
                                        (const strgpu_segment *)s.segs.p, n_seg, read_len, ctx->d_thr, ctx->d_luts,
-                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, 0, s.stream, &u));
-    ctx->launches++;
+                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, ctx->variant, s.stream, &u,
+                                       (uint32_t *)s.list.p));
+    ctx->launches += strgpu::scan_launches(read_len, ctx->variant);
     CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
     CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   } else {
@@ -354,10 +363,45 @@ int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask,
   if (((uintptr_t)d_seq2 & 3) || ((uintptr_t)d_nmask & 3) || ((uintptr_t)d_segs & 7) || ((uintptr_t)d_out & 7))
     return fail(ctx, STRGPU_ERR_INVALID, "scan_device: misaligned device pointer");
   CU(ctx, cudaSetDevice(ctx->device));
+  // the survivor list is one scratch buffer per context: launches that use it are chained through an event, so calls on
+  // different streams stay correct (they serialise)
+  int rc;
+  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 1) * sizeof(uint32_t)))) return rc;
+  CU(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->dev_list_done, 0));
   CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_segs,
                                      n_seg, max_len, ctx->d_thr, ctx->d_luts, (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count,
-                                     ctx->variant, (cudaStream_t)cuda_stream));
-  if (n_seg) ctx->launches++;
+                                     ctx->variant, (cudaStream_t)cuda_stream, nullptr, (uint32_t *)ctx->dev_list.p));
+  CU(ctx, cudaEventRecord(ctx->dev_list_done, (cudaStream_t)cuda_stream));
+  if (n_seg) ctx->launches += strgpu::scan_launches(max_len, ctx->variant);
+  return STRGPU_OK;
+}
+
+int strgpu_scan_reads_device(strgpu_ctx *ctx, const void *d_seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
+                             uint32_t pclass, const void *d_nmask, const void *d_extra, uint32_t n_extra,
+                             uint32_t extra_max_len, void *d_out, void *cuda_stream) {
+  if (!ctx || ((n_reads || n_extra) && (!d_seq2 || !d_out)) || (n_extra && !d_extra))
+    return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_device: null argument");
+  if ((stride_bases & 3u) || stride_bases < read_len || pclass >= STRGPU_MAX_PCLASS)
+    return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_device: stride %u / read_len %u / pclass %u", stride_bases, read_len, pclass);
+  if ((uint64_t)n_reads * stride_bases > 0xffffffffull) return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_device: batch addresses more than 2^32 bases");
+  if (read_len > (uint32_t)strgpu::kShortMaxLen || extra_max_len > (uint32_t)strgpu::kShortMaxLen)
+    return fail(ctx, STRGPU_ERR_TOO_LONG, "scan_reads_device: read_len %u / extra_max_len %u > %d (use strgpu_scan_device)", read_len,
+                extra_max_len, strgpu::kShortMaxLen);
+  if (((uintptr_t)d_seq2 & 3) || ((uintptr_t)d_nmask & 3) || ((uintptr_t)d_extra & 7) || ((uintptr_t)d_out & 7))
+    return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_device: misaligned device pointer");
+  const uint32_t n_seg = n_reads + n_extra;
+  if (n_seg == 0) return STRGPU_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 1) * sizeof(uint32_t)))) return rc;
+  CU(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->dev_list_done, 0));
+  const strgpu::UniformReads u{n_reads, read_len, stride_bases, pclass};
+  CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_extra, n_seg,
+                                     read_len > extra_max_len ? read_len : extra_max_len, ctx->d_thr, ctx->d_luts,
+                                     (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count, ctx->variant, (cudaStream_t)cuda_stream, &u,
+                                     (uint32_t *)ctx->dev_list.p));
+  CU(ctx, cudaEventRecord(ctx->dev_list_done, (cudaStream_t)cuda_stream));
+  ctx->launches += strgpu::scan_launches(read_len, ctx->variant);
   return STRGPU_OK;
 }
 

@@ -13,6 +13,8 @@
 // Integer / bitwise work only: no tensor cores.  Thresholds come from a host-built fp64-exact table.
 #include "scan_kernels.cuh"
 
+#include <cstdlib>
+
 namespace strgpu {
 
 namespace {
@@ -849,14 +851,241 @@ __device__ __forceinline__ void lane_load(const uint32_t *__restrict__ seq, cons
   w[kLaneWords - 1] = 0u;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// repeat_prefilter: the pre-filter as a streaming kernel of its own (no shared-memory tables, 64 registers, 32 resident
+// warps per SM, so the HBM latency of the read words is covered by occupancy).  Every segment is read once; segments the
+// bound finishes get their empty result here, the others -- and segments with non-ACGT bases or more than 160 bases --
+// are appended to the survivor list that repeat_scan_lane then works through 32 at a time.
+//
+// Same counting as lane_filter_max2 with a cheaper successor plane: word j is paired with word j + 5 (odd bits: positions
+// 16 j .., even bits: positions 16 (j + 5) ..), so the successor of every position of plane j is plane j shifted up by one
+// slot with the top slot pair of plane j + 1 shifted in -- one funnel shift.  CSA of the 16 streams are popcounted through
+// carry-save adders (3 POPC + 4 LOP3 instead of 5 POPC): POPC runs on the 16-lane XU pipe, LOP3 on the 64-lane ALU pipe.
+constexpr int kPreThreads = 256;
+constexpr int kPreCsaDefault = 8;
+
+__device__ __forceinline__ void prefilter_masks(int L, uint32_t (&V)[5]) {
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const int v0 = min(max(L - 1 - 16 * j, 0), 16), v1 = min(max(L - 1 - 16 * (j + 5), 0), 16);
+    const uint32_t m0 = v0 >= 16 ? kOdd : (kOdd & ~(kFull >> (2 * v0)));
+    const uint32_t m1 = v1 >= 16 ? kEven : (kEven & ~(kFull >> (2 * v1)));
+    V[j] = m0 | m1;
+  }
+}
+
+template <int CSA>
+__device__ __forceinline__ int prefilter_max2(const uint32_t (&w)[10], const uint32_t (&V)[5]) {
+  uint32_t Dh[6], Dl[6];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    Dh[j] = (w[j] & kOdd) | ((w[j + 5] >> 1) & kEven);
+    Dl[j] = ((w[j] << 1) & kOdd) | (w[j + 5] & kEven);
+  }
+  Dh[5] = w[5];        // only its top slot pair is used: base 0 of word 5 (the even bit feeds a slot that is never valid)
+  Dl[5] = w[5] << 1;
+  uint32_t E[5][4], Qh[5], Ql[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    Qh[j] = __funnelshift_l(Dh[j + 1], Dh[j], 2);
+    Ql[j] = __funnelshift_l(Dl[j + 1], Dl[j], 2);
+    E[j][0] = ~Dh[j] & ~Dl[j] & V[j];
+    E[j][1] = ~Dh[j] & Dl[j] & V[j];
+    E[j][2] = Dh[j] & ~Dl[j] & V[j];
+    E[j][3] = Dh[j] & Dl[j] & V[j];
+  }
+  int best = 0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    int ca[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      uint32_t m[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const uint32_t e = E[j][a];
+        m[j] = b == 0 ? (e & ~Qh[j] & ~Ql[j]) : (b == 1 ? (e & ~Qh[j] & Ql[j]) : (b == 2 ? (e & Qh[j] & ~Ql[j]) : e));
+      }
+      if (a * 4 + b >= CSA) {
+        ca[b] = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]);
+      } else {
+        const uint32_t s1 = m[0] ^ m[1] ^ m[2], c1 = (m[0] & m[1]) | (m[2] & (m[0] | m[1]));
+        const uint32_t s2 = s1 ^ m[3] ^ m[4], c2 = (s1 & m[3]) | (m[4] & (s1 | m[3]));
+        ca[b] = __popc(s2) + 2 * (__popc(c1) + __popc(c2));
+      }
+    }
+    ca[3] -= ca[0] + ca[1] + ca[2];
+    best = max(best, max(max(ca[0], ca[1]), max(ca[2], ca[3])));
+  }
+  return best;
+}
+
+// ---- TMA plumbing (sm_90+ PTX): one mbarrier per staging buffer, bulk global -> shared copies completing on it
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// the filter decision for one lane-path segment whose words start at `src` (global or shared memory)
+template <int CSA>
+__device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh, int L, int pclass, const uint16_t *__restrict__ tmin,
+                                               uint32_t (&V)[5], int &v_len, int &v_pc, int &v_thr) {
+  const int n_words = (2 * L + 31) >> 5;
+  uint32_t raw[11], w[10];
+#pragma unroll
+  for (int j = 0; j < 11; j++) raw[j] = (j <= n_words) ? __byte_perm(src[j], 0, 0x0123) : 0u;
+#pragma unroll
+  for (int j = 0; j < 10; j++) w[j] = __funnelshift_l(raw[j + 1], raw[j], sh);
+  if (L != v_len || pclass != v_pc) {
+    prefilter_masks(L, V);
+    v_thr = tmin[pclass * kThrLen + L];
+    v_len = L;
+    v_pc = pclass;
+  }
+  return prefilter_max2<CSA>(w, V) > v_thr;
+}
+
+// appends the kept segments of this warp's group to the survivor list (one atomic per warp)
+__device__ __forceinline__ void survivors_push(uint32_t *__restrict__ list, bool keep, uint32_t s, int lane) {
+  const uint32_t km = __ballot_sync(kFull, keep);
+  if (km != 0u) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(list, (uint32_t)__popc(km));
+    base = __shfl_sync(kFull, base, 0);
+    if (keep) list[1 + base + __popc(km & ((1u << lane) - 1u))] = s;
+  }
+}
+
+// Staging: a group of 32 uniform reads is one contiguous span of 8 * stride bytes.  Lane 0 of the warp that owns the group
+// arms an mbarrier and issues ONE bulk copy (TMA, cp.async.bulk) of the span into the warp's shared-memory buffer; the copy
+// of the next group is in flight while the current one is counted (two buffers per warp), so no warp ever waits on an HBM
+// load with its registers tied up.  16 bytes past the span are copied too (the re-alignment of the last lane reads one word
+// beyond its read), which is why the batch's last group -- and everything that is not a uniform read -- takes the LDG path.
+constexpr int kStageBytes = 8 * kShortMaxLen + 32;   // 1312: spans of up to 8 * 160 bytes + 16, kept 16-byte aligned
+constexpr int kPreWarps = kPreThreads / 32;
+
+template <int CSA>
+__global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
+                                                                   const strgpu_segment *__restrict__ segs, uint32_t n_seg,
+                                                                   const UniformReads u, const uint16_t *__restrict__ thr,
+                                                                   strgpu_repeat *__restrict__ out, uint32_t *__restrict__ list,
+                                                                   uint32_t n_tma_groups) {
+  __shared__ __align__(128) unsigned char stage_buf[kPreWarps][2][kStageBytes];
+  __shared__ __align__(8) uint64_t stage_bar[kPreWarps][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint16_t *tmin = thr + kThrMinOff;
+  const uint32_t warps_total = gridDim.x * kPreWarps;
+  const uint32_t warp_global = blockIdx.x * kPreWarps + warp;
+  uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
+  int v_len = -1, v_pc = -1, v_thr = 0;
+
+  // ---- part 1: uniform reads, staged through shared memory by bulk copies
+  if (n_tma_groups != 0u) {
+    if (lane == 0) {
+      mbar_init(&stage_bar[warp][0], 1);
+      mbar_init(&stage_bar[warp][1], 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the initialised barriers visible to the copy engine
+    }
+    __syncwarp();
+    const uint32_t span = 8u * u.stride;                 // bytes of 32 reads
+    const uint32_t lane_byte = (uint32_t)lane * (u.stride >> 2);
+    const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(seq);
+    const int L = (int)u.read_len;
+    const int pclass = (int)u.pclass;
+    uint32_t parity = 0;   // bit b = phase of buffer b
+    int b = 0;
+    uint32_t g = warp_global;
+    if (g < n_tma_groups && lane == 0) {
+      mbar_expect_tx(&stage_bar[warp][0], span + 16u);
+      bulk_load(stage_buf[warp][0], gsrc + (size_t)g * span, span + 16u, &stage_bar[warp][0]);
+    }
+    while (g < n_tma_groups) {
+      const uint32_t gn = g + warps_total;
+      if (gn < n_tma_groups && lane == 0) {
+        mbar_expect_tx(&stage_bar[warp][b ^ 1], span + 16u);
+        bulk_load(stage_buf[warp][b ^ 1], gsrc + (size_t)gn * span, span + 16u, &stage_bar[warp][b ^ 1]);
+      }
+      mbar_wait(&stage_bar[warp][b], (parity >> b) & 1u);
+      parity ^= 1u << b;
+      const uint32_t s = g * 32u + (uint32_t)lane;
+      bool has_n = false;
+      if (nmask != nullptr) {
+        const uint32_t b0 = s * u.stride, b1 = b0 + u.read_len;
+        uint32_t any = 0;
+        for (uint32_t wd = b0 >> 5; wd <= ((b1 - 1u) >> 5); wd++) {
+          uint32_t v = nmask[wd];
+          if (wd == (b0 >> 5)) v &= kFull << (b0 & 31u);
+          if (wd == ((b1 - 1u) >> 5) && (b1 & 31u)) v &= (1u << (b1 & 31u)) - 1u;
+          any |= v;
+        }
+        has_n = any != 0u;
+      }
+      bool keep = has_n;
+      if (!has_n) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(stage_buf[warp][b] + (lane_byte & ~3u));
+        keep = prefilter_keep<CSA>(src, 8u * (lane_byte & 3u), L, pclass, tmin, V, v_len, v_pc, v_thr);
+        if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
+      }
+      survivors_push(list, keep, s, lane);
+      __syncwarp();   // every lane has read this buffer before the next iteration refills it
+      g = gn;
+      b ^= 1;
+    }
+  }
+
+  // ---- part 2: everything else (descriptor segments, the batch's last uniform group): per-lane loads
+  const uint32_t first = n_tma_groups * 32u;
+  const uint32_t n_groups = (n_seg - first + 31u) / 32u;
+  for (uint32_t grp = warp_global; grp < n_groups; grp += warps_total) {
+    const uint32_t s = first + grp * 32u + (uint32_t)lane;
+    const bool active = s < n_seg;
+    strgpu_segment sg{0, 0, 0, 0};
+    if (active) sg = load_segment(segs, nmask, u, s);
+    const int L = sg.len;
+    const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
+    bool keep = active && !lane_path;   // non-ACGT bases or > 160 bases: the scan kernel's warp path
+    if (lane_path) {
+      const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+      keep = prefilter_keep<CSA>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tmin, V, v_len, v_pc, v_thr);
+      if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;
+    }
+    survivors_push(list, keep, s, lane);
+  }
+}
+
 template <int FILTER>
 __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                     const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                     const UniformReads u,
                                                                     const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
-                                                                    strgpu_repeat *__restrict__ out, int *status) {
+                                                                    strgpu_repeat *__restrict__ out, int *status,
+                                                                    const uint32_t *__restrict__ list) {
+  // list == nullptr: every segment of the batch; else list[0] = number of entries, list[1..] = segment indices (the
+  // survivors of repeat_prefilter)
   extern __shared__ __align__(16) uint32_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_items = list ? list[0] : n_seg;
   uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kLaneWarps * kWarpSmemWords);
   for (int i = tid; i < kLutTotal; i += kLaneThreads) lut[i] = luts[i];
   __syncthreads();
@@ -868,7 +1097,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   int n2 = 0, n3 = 0, n4 = 0, n5 = 0, n6 = 0;
   const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
   const uint16_t *tmin = thr + kThrMinOff;
-  const uint32_t n_groups = (n_seg + 31) / 32;
+  const uint32_t n_groups = (n_items + 31) / 32;
   const uint32_t warps_total = gridDim.x * kLaneWarps;
   uint32_t grp = blockIdx.x * kLaneWarps + warp;
   uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
@@ -895,9 +1124,10 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
     if (stage == 1) {
       // ---- stage 1: new segments, 32 per pass: the 2-mer pre-filter finishes most of them; survivors go to Q2
       do {
-        const uint32_t s = grp * 32 + lane;
+        const uint32_t item = grp * 32 + lane;
         grp += warps_total;
-        const bool active = s < n_seg;
+        const bool active = item < n_items;
+        const uint32_t s = (list && active) ? list[1 + item] : item;
         strgpu_segment sg{0, 0, 0, 0};
         if (active) sg = load_segment(segs, nmask, u, s);
         const int L = sg.len;
@@ -1044,7 +1274,7 @@ void build_lane_luts(uint16_t *dst) {
 cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
                                uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
                                strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,
-                               const UniformReads *uniform) {
+                               const UniformReads *uniform, uint32_t *d_list) {
   if (n_seg == 0) return cudaSuccess;
   UniformReads u{0, 0, 0, 0};
   if (uniform) {
@@ -1052,23 +1282,46 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
     if (u.read_len > (uint32_t)kShortMaxLen) return cudaErrorInvalidValue;  // callers expand long uniform reads into descriptors
     if (variant == 1) variant = 0;
   }
+  if (variant < 0 || variant > 7) variant = 0;
+  if (d_list == nullptr && (variant == 0 || variant >= 5)) variant = 2;   // no survivor list: fused kernel
   constexpr int kWarps = 8;
   const uint32_t blocks_needed = (n_seg + kWarps - 1) / kWarps;
   if (max_len <= (uint32_t)kShortMaxLen && variant != 1) {
-    // variant 0: pre-filter with plain popcounts, 2: pre-filter with carry-save popcounts, 3: no pre-filter (A/B runs)
-    auto kernel = variant == 2 ? repeat_scan_lane<1> : (variant == 3 ? repeat_scan_lane<-1> : repeat_scan_lane<0>);
-    static bool configured[4] = {false, false, false, false};
-    if (!configured[variant & 3]) {
+    // 0: repeat_prefilter + repeat_scan_lane over its survivor list (5..7: the same with 0 / 8 / 16 carry-save streams);
+    // 2 / 4: one fused kernel (plain / carry-save popcounts); 3: no pre-filter (A/B runs)
+    auto kernel = variant == 2 ? repeat_scan_lane<0> : (variant == 4 ? repeat_scan_lane<1> : repeat_scan_lane<-1>);
+    static bool configured[8] = {false, false, false, false, false, false, false, false};
+    if (!configured[variant]) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmemBytes);
       if (e != cudaSuccess) return e;
       e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       if (e != cudaSuccess) return e;
-      configured[variant & 3] = true;
+      configured[variant] = true;
+    }
+    const bool split = variant == 0 || variant >= 5;
+    static const bool no_tma = getenv("STRGPU_NO_TMA") != nullptr;   // A/B: per-lane loads for uniform reads too
+    if (split) {
+      cudaError_t e = cudaMemsetAsync(d_list, 0, sizeof(uint32_t), stream);
+      if (e != cudaSuccess) return e;
+      const uint32_t groups = (n_seg + 31) / 32;
+      uint32_t pre_grid = (uint32_t)sm_count * 4u;   // 4 resident CTAs of 8 warps per SM, grid-stride over groups of 32
+      const uint32_t pre_need = (groups + kPreThreads / 32 - 1) / (kPreThreads / 32);
+      if (pre_grid > pre_need) pre_grid = pre_need;
+      auto pre = variant == 5 ? repeat_prefilter<0> : (variant == 7 ? repeat_prefilter<16> : (variant == 6 ? repeat_prefilter<8> : repeat_prefilter<kPreCsaDefault>));
+      // uniform reads go through the TMA-staged part when their 32-read spans fit the staging buffers (all groups but the
+      // batch's last one: the copy reads 16 bytes past its span)
+      uint32_t n_tma = 0;
+      if (u.n_reads >= 64u && u.read_len >= 1u && 8u * u.stride + 16u <= (uint32_t)kStageBytes && ((uintptr_t)d_seq_words & 15u) == 0 && !no_tma)
+        n_tma = u.n_reads / 32u - 1u;
+      pre<<<pre_grid, kPreThreads, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_out, d_list, n_tma);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
     }
     const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
     uint32_t grid = (uint32_t)sm_count;  // one persistent CTA of 20 warps per SM
     if (grid > tiles) grid = tiles;
-    kernel<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out, d_status);
+    kernel<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out, d_status,
+                                                           split ? d_list : nullptr);
   } else if (max_len <= (uint32_t)kShortMaxLen) {
     uint32_t grid = (uint32_t)sm_count * 8u;  // 8 resident CTAs of 256 threads per SM
     if (grid > blocks_needed) grid = blocks_needed;

@@ -67,6 +67,8 @@ proc strgpu_scan*(ctx: StrGpuCtx, seq2: ptr uint8, n_bases: uint64, nmask: ptr u
                   n_seg: uint32, max_len: uint32, res: ptr StrGpuRepeat): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
 proc strgpu_scan_reads_submit*(ctx: StrGpuCtx, seq2: ptr uint8, n_reads, read_len, stride_bases, pclass: uint32, nmask: ptr uint32,
                                extra: ptr StrGpuSegment, n_extra, extra_max_len: uint32, res: ptr StrGpuRepeat, ticket: ptr cint): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
+proc strgpu_scan_reads_device*(ctx: StrGpuCtx, d_seq2: pointer, n_reads, read_len, stride_bases, pclass: uint32, d_nmask, d_extra: pointer,
+                               n_extra, extra_max_len: uint32, d_out, cuda_stream: pointer): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
 proc strgpu_cluster_loci*(ctx: StrGpuCtx, treads: ptr StrGpuTread, n: uint32, params: ptr StrGpuClusterParams, loci: ptr StrGpuLocus,
                           n_loci: uint32, res: ptr StrGpuBounds, cap: uint32, n_out: ptr uint32): cint {.importc, cdecl, dynlib: "libstrgpu.so".}
 proc strgpu_cluster*(ctx: StrGpuCtx, treads: ptr StrGpuTread, n: uint32, params: ptr StrGpuClusterParams,

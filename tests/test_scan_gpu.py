@@ -166,9 +166,10 @@ def test_prefilter_threshold_boundary(gpu):
     assert n_found > 500  # both sides of the bound are exercised
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5", "7"])
 def test_both_kernel_variants_agree_with_oracle(variant, monkeypatch):
-    # 0: lane-per-segment kernel with the 2-mer pre-filter, 1: warp-per-segment kernel, 2: carry-save pre-filter, 3: no pre-filter
+    # 0: pre-filter kernel + lane-per-segment kernel over its survivors, 1: warp-per-segment kernel, 2 / 4: fused pre-filter,
+    # 3: no pre-filter, 5 / 7: split with 0 / 16 carry-save popcount streams
     monkeypatch.setenv("STRGPU_SCAN_VARIANT", variant)
     g = sb.StrGpu(0)
     try:
@@ -237,3 +238,41 @@ def test_scale_permutation_invariance(gpu):
     inv = np.argsort(perm.reshape(reps, -1), axis=1)
     digests = {int(np.bitwise_xor.reduce(key.reshape(reps, -1)[r][inv[r]] * (np.arange(len(segs), dtype=np.uint64) + np.uint64(1)))) for r in range(reps)}
     assert len(digests) == 1
+
+
+@pytest.mark.parametrize("length,align,n_frac", [(150, 16, 0.0), (150, 4, 0.0), (150, 4, 0.02), (101, 4, 0.0), (160, 16, 0.01), (33, 4, 0.0)])
+def test_device_resident_uniform_reads(gpu, length, align, n_frac):
+    # strgpu_scan_reads_device (uniform reads staged through shared memory by TMA bulk copies + clip descriptors) ==
+    # strgpu_scan_device (descriptors, per-lane loads) == oracle, on caller-owned device buffers and stream
+    import torch
+
+    reads, cls, lclip, rclip = synth.make_reads(70_001, seed=1000 + length, length=length, mix=(0.75, 0.1, 0.08, 0.07), n_frac=n_frac)
+    lclip = np.minimum(lclip, length)
+    rclip = np.minimum(rclip, length)
+    seq2, nmask, stride = synth.pack_matrix(reads, align_bases=align)
+    segs, _ = synth.segments_for(reads, lclip, rclip, stride)
+    n = reads.shape[0]
+    flat, off, lens = synth.segment_ascii(reads, segs, stride)
+    units, counts = oracle_for(flat, off, lens, segs["pclass"])
+    dev = torch.device("cuda", 0)
+    pad = (-len(seq2)) % 16 + 16
+    d_seq = torch.from_numpy(np.concatenate([seq2, np.zeros(pad, dtype=np.uint8)])).to(dev)
+    d_nm = torch.from_numpy(nmask.view(np.uint8).copy()).to(dev) if nmask is not None else None
+    d_segs = torch.from_numpy(segs.view(np.uint8).reshape(-1).copy()).to(dev)
+    stream = torch.cuda.Stream(device=dev)
+    results = []
+    for which in ("reads", "segments"):
+        d_out = torch.full((len(segs) * 8,), 0xEE, dtype=torch.uint8, device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        if which == "reads":
+            n_extra = len(segs) - n
+            gpu.scan_reads_device(d_seq.data_ptr(), n, length, stride, 0, d_nm.data_ptr() if d_nm is not None else None,
+                                  d_segs.data_ptr() + n * 8 if n_extra else None, n_extra,
+                                  int(segs["len"][n:].max()) if n_extra else 0, d_out.data_ptr(), stream.cuda_stream)
+        else:
+            gpu.scan_device(d_seq.data_ptr(), d_nm.data_ptr() if d_nm is not None else None, d_segs.data_ptr(), len(segs), length,
+                            d_out.data_ptr(), stream.cuda_stream)
+        gpu.device_status(stream.cuda_stream)
+        results.append(d_out.cpu().numpy().view(sb.REPEAT_DTYPE))
+    for res in results:
+        assert np.array_equal(res["unit"], units) and np.array_equal(res["repeat_count"], counts)
