@@ -874,8 +874,9 @@ __device__ __forceinline__ void prefilter_masks(int L, uint32_t (&V)[5]) {
   }
 }
 
+// returns the largest and the second largest of the 16 occurrence counts
 template <int CSA>
-__device__ __forceinline__ int prefilter_max2(const uint32_t (&w)[10], const uint32_t (&V)[5]) {
+__device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const uint32_t (&V)[5], int &s1, int &s2) {
   uint32_t Dh[6], Dl[6];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
@@ -894,7 +895,8 @@ __device__ __forceinline__ int prefilter_max2(const uint32_t (&w)[10], const uin
     E[j][2] = Dh[j] & ~Dl[j] & V[j];
     E[j][3] = Dh[j] & Dl[j] & V[j];
   }
-  int best = 0;
+  s1 = 0;
+  s2 = 0;
 #pragma unroll
   for (int a = 0; a < 4; a++) {
     int ca[4];
@@ -915,9 +917,12 @@ __device__ __forceinline__ int prefilter_max2(const uint32_t (&w)[10], const uin
       }
     }
     ca[3] -= ca[0] + ca[1] + ca[2];
-    best = max(best, max(max(ca[0], ca[1]), max(ca[2], ca[3])));
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      s2 = max(s2, min(s1, ca[b]));
+      s1 = max(s1, ca[b]);
+    }
   }
-  return best;
 }
 
 // ---- TMA plumbing (sm_90+ PTX): one mbarrier per staging buffer, bulk global -> shared copies completing on it
@@ -947,33 +952,62 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
-// the filter decision for one lane-path segment whose words start at `src` (global or shared memory)
+// The filter decision for one lane-path segment whose words start at `src` (global or shared memory).
+// Bound: c non-overlapping occurrences of a k-mer u put c * (k - 1) distinct positions into the occurrence sets of the
+// (at most k - 1 distinct) 2-mers inside u, so the k - 1 largest 2-mer counts sum to at least c * (k - 1).  With s1 >= s2 the two
+// largest counts that sum is at most s1 + (k - 2) * s2; a unit needs c >= int(L * p / k) + 1 (utils.nim:259).  A segment with
+// s1 + (k - 2) * s2 < (int(L * p / k) + 1) * (k - 1) for every k = 2..6 therefore returns the empty unit whatever the ladder does.
+struct FilterCache {
+  uint32_t V[5];
+  int len, pclass;
+  int r[5];   // (int(L * p / k) + 1) * (k - 1), k = 2..6
+};
 template <int CSA>
-__device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh, int L, int pclass, const uint16_t *__restrict__ tmin,
-                                               uint32_t (&V)[5], int &v_len, int &v_pc, int &v_thr) {
+__device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh, int L, int pclass, const uint16_t *__restrict__ tfilt,
+                                               FilterCache &fc) {
   const int n_words = (2 * L + 31) >> 5;
   uint32_t raw[11], w[10];
 #pragma unroll
   for (int j = 0; j < 11; j++) raw[j] = (j <= n_words) ? __byte_perm(src[j], 0, 0x0123) : 0u;
 #pragma unroll
   for (int j = 0; j < 10; j++) w[j] = __funnelshift_l(raw[j + 1], raw[j], sh);
-  if (L != v_len || pclass != v_pc) {
-    prefilter_masks(L, V);
-    v_thr = tmin[pclass * kThrLen + L];
-    v_len = L;
-    v_pc = pclass;
+  if (L != fc.len || pclass != fc.pclass) {
+    prefilter_masks(L, fc.V);
+    const uint4 t = *reinterpret_cast<const uint4 *>(tfilt + (size_t)(pclass * kThrLen + L) * 8);
+    fc.r[0] = (int)(t.x & 0xffffu);
+    fc.r[1] = (int)(t.x >> 16);
+    fc.r[2] = (int)(t.y & 0xffffu);
+    fc.r[3] = (int)(t.y >> 16);
+    fc.r[4] = (int)(t.z & 0xffffu);
+    fc.len = L;
+    fc.pclass = pclass;
   }
-  return prefilter_max2<CSA>(w, V) > v_thr;
+  int s1, s2;
+  prefilter_top2<CSA>(w, fc.V, s1, s2);
+  return s1 >= fc.r[0] || s1 + s2 >= fc.r[1] || s1 + 2 * s2 >= fc.r[2] || s1 + 3 * s2 >= fc.r[3] || s1 + 4 * s2 >= fc.r[4];
 }
 
-// appends the kept segments of this warp's group to the survivor list (one atomic per warp)
-__device__ __forceinline__ void survivors_push(uint32_t *__restrict__ list, bool keep, uint32_t s, int lane) {
+// Appends the kept segments of this warp's group to the survivor list (one atomic per warp and class).  The list has two
+// ends: list[0] long segments (>= kLongLen bases, and everything bound for the warp path) filling list[2 ..] upwards,
+// list[1] short segments filling list[2 + cap - 1 ..] downwards, so that the scan kernel's batches of 32 hold segments of
+// similar length (its per-lane loops run for the longest lane of a warp).
+constexpr int kLongLen = 96;
+__device__ __forceinline__ void survivors_push(uint32_t *__restrict__ list, uint32_t cap, bool keep, bool is_short, uint32_t s, int lane) {
   const uint32_t km = __ballot_sync(kFull, keep);
-  if (km != 0u) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(list, (uint32_t)__popc(km));
-    base = __shfl_sync(kFull, base, 0);
-    if (keep) list[1 + base + __popc(km & ((1u << lane) - 1u))] = s;
+  if (km == 0u) return;
+  const uint32_t sm = __ballot_sync(kFull, keep && is_short);
+  const uint32_t lm = km & ~sm;
+  const uint32_t below = (1u << lane) - 1u;
+  uint32_t base_l = 0, base_s = 0;
+  if (lane == 0) {
+    if (lm) base_l = atomicAdd(list, (uint32_t)__popc(lm));
+    if (sm) base_s = atomicAdd(list + 1, (uint32_t)__popc(sm));
+  }
+  base_l = __shfl_sync(kFull, base_l, 0);
+  base_s = __shfl_sync(kFull, base_s, 0);
+  if (keep) {
+    if (is_short) list[2u + cap - 1u - (base_s + __popc(sm & below))] = s;
+    else list[2u + base_l + __popc(lm & below)] = s;
   }
 }
 
@@ -994,11 +1028,12 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
   __shared__ __align__(128) unsigned char stage_buf[kPreWarps][2][kStageBytes];
   __shared__ __align__(8) uint64_t stage_bar[kPreWarps][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint16_t *tmin = thr + kThrMinOff;
+  const uint16_t *tfilt = thr + kThrFiltOff;
   const uint32_t warps_total = gridDim.x * kPreWarps;
   const uint32_t warp_global = blockIdx.x * kPreWarps + warp;
-  uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
-  int v_len = -1, v_pc = -1, v_thr = 0;
+  FilterCache fc;
+  fc.len = -1;
+  fc.pclass = -1;
 
   // ---- part 1: uniform reads, staged through shared memory by bulk copies
   if (n_tma_groups != 0u) {
@@ -1044,10 +1079,10 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
       bool keep = has_n;
       if (!has_n) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(stage_buf[warp][b] + (lane_byte & ~3u));
-        keep = prefilter_keep<CSA>(src, 8u * (lane_byte & 3u), L, pclass, tmin, V, v_len, v_pc, v_thr);
+        keep = prefilter_keep<CSA>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc);
         if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
       }
-      survivors_push(list, keep, s, lane);
+      survivors_push(list, n_seg, keep, !has_n && L < kLongLen, s, lane);
       __syncwarp();   // every lane has read this buffer before the next iteration refills it
       g = gn;
       b ^= 1;
@@ -1067,10 +1102,10 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
     bool keep = active && !lane_path;   // non-ACGT bases or > 160 bases: the scan kernel's warp path
     if (lane_path) {
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-      keep = prefilter_keep<CSA>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tmin, V, v_len, v_pc, v_thr);
+      keep = prefilter_keep<CSA>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc);
       if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;
     }
-    survivors_push(list, keep, s, lane);
+    survivors_push(list, n_seg, keep, lane_path && L < kLongLen, s, lane);
   }
 }
 
@@ -1081,11 +1116,12 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
                                                                     const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
                                                                     strgpu_repeat *__restrict__ out, int *status,
                                                                     const uint32_t *__restrict__ list) {
-  // list == nullptr: every segment of the batch; else list[0] = number of entries, list[1..] = segment indices (the
-  // survivors of repeat_prefilter)
+  // list == nullptr: every segment of the batch; else the two-ended survivor list of repeat_prefilter (survivors_push):
+  // groups of 32 long segments first, then groups of 32 short ones
   extern __shared__ __align__(16) uint32_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t n_items = list ? list[0] : n_seg;
+  const uint32_t n_long = list ? list[0] : n_seg, n_short = list ? list[1] : 0u;
+  const uint32_t groups_long = (n_long + 31) / 32;
   uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kLaneWarps * kWarpSmemWords);
   for (int i = tid; i < kLutTotal; i += kLaneThreads) lut[i] = luts[i];
   __syncthreads();
@@ -1097,7 +1133,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   int n2 = 0, n3 = 0, n4 = 0, n5 = 0, n6 = 0;
   const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
   const uint16_t *tmin = thr + kThrMinOff;
-  const uint32_t n_groups = (n_items + 31) / 32;
+  const uint32_t n_groups = groups_long + (n_short + 31) / 32;
   const uint32_t warps_total = gridDim.x * kLaneWarps;
   uint32_t grp = blockIdx.x * kLaneWarps + warp;
   uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
@@ -1124,10 +1160,11 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
     if (stage == 1) {
       // ---- stage 1: new segments, 32 per pass: the 2-mer pre-filter finishes most of them; survivors go to Q2
       do {
-        const uint32_t item = grp * 32 + lane;
+        const bool in_long = grp < groups_long;
+        const uint32_t item = (in_long ? grp : grp - groups_long) * 32 + lane;
         grp += warps_total;
-        const bool active = item < n_items;
-        const uint32_t s = (list && active) ? list[1 + item] : item;
+        const bool active = item < (in_long ? n_long : n_short);
+        const uint32_t s = (list && active) ? (in_long ? list[2u + item] : list[2u + n_seg - 1u - item]) : item;
         strgpu_segment sg{0, 0, 0, 0};
         if (active) sg = load_segment(segs, nmask, u, s);
         const int L = sg.len;
@@ -1301,7 +1338,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
     const bool split = variant == 0 || variant >= 5;
     static const bool no_tma = getenv("STRGPU_NO_TMA") != nullptr;   // A/B: per-lane loads for uniform reads too
     if (split) {
-      cudaError_t e = cudaMemsetAsync(d_list, 0, sizeof(uint32_t), stream);
+      cudaError_t e = cudaMemsetAsync(d_list, 0, 2 * sizeof(uint32_t), stream);
       if (e != cudaSuccess) return e;
       const uint32_t groups = (n_seg + 31) / 32;
       uint32_t pre_grid = (uint32_t)sm_count * 4u;   // 4 resident CTAs of 8 warps per SM, grid-stride over groups of 32

@@ -9,12 +9,14 @@ namespace strgpu {
 
 constexpr int kThrLen = 512;                    // thresholds tabulated for len 0..511
 constexpr int kThrClasses = STRGPU_MAX_PCLASS + 1;  // + the 0.12 "give up" class (utils.nim:251)
-constexpr int kThrMinOff = kThrClasses * 5 * kThrLen;       // then min over k = 2..6 per (proportion class, len): the pre-filter bound
-constexpr int kThrEntries = kThrMinOff + STRGPU_MAX_PCLASS * kThrLen;
+constexpr int kThrMinOff = kThrClasses * 5 * kThrLen;       // then min over k = 2..6 per (proportion class, len): the fused pre-filter's bound
+constexpr int kThrFiltOff = kThrMinOff + STRGPU_MAX_PCLASS * kThrLen;   // then 8 uint16 per (class, len): the pre-filter kernel's bounds
+constexpr int kThrEntries = kThrFiltOff + STRGPU_MAX_PCLASS * kThrLen * 8;
 constexpr int kShortMaxLen = 160;               // kernel variant with the read in <= 10 words
 
 // thr[(cls * 5 + (k - 2)) * kThrLen + len] = int(len * p_cls / k); cls == STRGPU_MAX_PCLASS holds int(len * 0.12 / k);
 // thr[kThrMinOff + cls * kThrLen + len] = min over k of the class's thresholds
+// thr[kThrFiltOff + (cls * kThrLen + len) * 8 + (k - 2)] = (int(len * p_cls / k) + 1) * (k - 1), k = 2..6 (entries 5..7 unused)
 // Implicit whole-read segments: read i = bases [i * stride, i * stride + read_len), proportion class pclass.
 struct UniformReads {
   uint32_t n_reads, read_len, stride, pclass;
@@ -29,7 +31,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
                                uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
                                strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,
                                const UniformReads *uniform = nullptr, uint32_t *d_list = nullptr);
-// d_list: device scratch of n_seg + 1 uint32 (survivor list of the pre-filter kernel); without it the fused kernel runs
+// d_list: device scratch of n_seg + 2 uint32 (survivor list of the pre-filter kernel); without it the fused kernel runs
 
 // kernels one launch_repeat_scan call issues (for the library's launch counter)
 inline int scan_launches(uint32_t max_len, int variant) {

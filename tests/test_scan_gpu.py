@@ -138,13 +138,19 @@ def test_prefilter_threshold_boundary(gpu):
             for k in range(2, 7):
                 t = int(float(L) * p / float(k))
                 for c in (t - 1, t, t + 1, t + 2):
-                    for _ in range(6):
+                    for rep in range(6):
                         if c < 0 or c * k > L:
                             continue
                         unit = "".join(rng.choice(list("ACGT"), size=k))
                         gaps = L - c * k
                         cuts = np.sort(rng.integers(0, gaps + 1, size=c)) if c else np.zeros(0, dtype=int)
-                        filler = "".join(rng.choice(list("ACGT"), size=gaps))
+                        other = [x for x in "ACGT" if x not in unit]
+                        if rep >= 3 and len(other) >= 2:
+                            # filler that adds nothing to the unit's 2-mer counts: the bound is met with equality at c = t + 1
+                            filler = (other[0] + other[1]) * (gaps // 2 + 1)
+                            filler = filler[:gaps]
+                        else:
+                            filler = "".join(rng.choice(list("ACGT"), size=gaps))
                         parts, prev = [], 0
                         for cut in cuts:
                             parts.append(filler[prev:cut])
