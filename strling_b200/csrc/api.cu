@@ -246,7 +246,7 @@ int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, c
   if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
   if ((rc = ensure(ctx, s.segs, (size_t)n_seg * sizeof(strgpu_segment) + 16))) return rc;
   if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
-  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 2) * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
   s.n_seg = n_seg;
   s.host_out = out;
   if (n_seg) {
@@ -313,7 +313,7 @@ int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_re
   if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
   if ((rc = ensure(ctx, s.segs, (size_t)n_extra * sizeof(strgpu_segment) + 16))) return rc;
   if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
-  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 2) * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
   s.n_seg = n_seg;
   s.host_out = out;
   if (n_seg) {
@@ -371,7 +371,7 @@ int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask,
   // the survivor list is one scratch buffer per context: launches that use it are chained through an event, so calls on
   // different streams stay correct (they serialise)
   int rc;
-  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 2) * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
   CU(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->dev_list_done, 0));
   CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_segs,
                                      n_seg, max_len, ctx->d_thr, ctx->d_luts, (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count,
@@ -398,7 +398,7 @@ int strgpu_scan_reads_device(strgpu_ctx *ctx, const void *d_seq2, uint32_t n_rea
   if (n_seg == 0) return STRGPU_OK;
   CU(ctx, cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 2) * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
   CU(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->dev_list_done, 0));
   const strgpu::UniformReads u{n_reads, read_len, stride_bases, pclass};
   CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_extra, n_seg,

@@ -917,11 +917,11 @@ __device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const ui
       }
     }
     ca[3] -= ca[0] + ca[1] + ca[2];
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      s2 = max(s2, min(s1, ca[b]));
-      s1 = max(s1, ca[b]);
-    }
+    // the two largest of the four, merged into the running pair
+    const int m1 = max(ca[0], ca[1]), n1 = min(ca[0], ca[1]), m2 = max(ca[2], ca[3]), n2 = min(ca[2], ca[3]);
+    const int t1 = max(m1, m2), t2 = max(min(m1, m2), max(n1, n2));
+    s2 = max(min(s1, t1), max(s2, t2));
+    s1 = max(s1, t1);
   }
 }
 
@@ -962,13 +962,14 @@ struct FilterCache {
   int len, pclass;
   int r[5];   // (int(L * p / k) + 1) * (k - 1), k = 2..6
 };
-template <int CSA>
+// ALL_WORDS: all eleven words may be read whatever L is (staging buffer; words past the segment only feed masked slots)
+template <int CSA, bool ALL_WORDS>
 __device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh, int L, int pclass, const uint16_t *__restrict__ tfilt,
                                                FilterCache &fc) {
   const int n_words = (2 * L + 31) >> 5;
   uint32_t raw[11], w[10];
 #pragma unroll
-  for (int j = 0; j < 11; j++) raw[j] = (j <= n_words) ? __byte_perm(src[j], 0, 0x0123) : 0u;
+  for (int j = 0; j < 11; j++) raw[j] = (ALL_WORDS || j <= n_words) ? __byte_perm(src[j], 0, 0x0123) : 0u;
 #pragma unroll
   for (int j = 0; j < 10; j++) w[j] = __funnelshift_l(raw[j + 1], raw[j], sh);
   if (L != fc.len || pclass != fc.pclass) {
@@ -988,10 +989,11 @@ __device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh,
 }
 
 // Appends the kept segments of this warp's group to the survivor list (one atomic per warp and class).  The list has two
-// ends: list[0] long segments (>= kLongLen bases, and everything bound for the warp path) filling list[2 ..] upwards,
+// ends: list[0] long segments (>= kLongLen bases, and everything bound for the warp path) filling list[kListHdr ..] upwards,
 // list[1] short segments filling list[2 + cap - 1 ..] downwards, so that the scan kernel's batches of 32 hold segments of
 // similar length (its per-lane loops run for the longest lane of a warp).
 constexpr int kLongLen = 96;
+constexpr uint32_t kListHdr = 4;   // list[0] long count, list[1] short count, list[2] next group to hand out (scan kernel), list[3] unused
 __device__ __forceinline__ void survivors_push(uint32_t *__restrict__ list, uint32_t cap, bool keep, bool is_short, uint32_t s, int lane) {
   const uint32_t km = __ballot_sync(kFull, keep);
   if (km == 0u) return;
@@ -1006,27 +1008,27 @@ __device__ __forceinline__ void survivors_push(uint32_t *__restrict__ list, uint
   base_l = __shfl_sync(kFull, base_l, 0);
   base_s = __shfl_sync(kFull, base_s, 0);
   if (keep) {
-    if (is_short) list[2u + cap - 1u - (base_s + __popc(sm & below))] = s;
-    else list[2u + base_l + __popc(lm & below)] = s;
+    if (is_short) list[kListHdr + cap - 1u - (base_s + __popc(sm & below))] = s;
+    else list[kListHdr + base_l + __popc(lm & below)] = s;
   }
 }
 
 // Staging: a group of 32 uniform reads is one contiguous span of 8 * stride bytes.  Lane 0 of the warp that owns the group
 // arms an mbarrier and issues ONE bulk copy (TMA, cp.async.bulk) of the span into the warp's shared-memory buffer; the copy
-// of the next group is in flight while the current one is counted (two buffers per warp), so no warp ever waits on an HBM
+// of the next STAGES - 1 groups are in flight while the current one is counted (a ring of buffers per warp), so no warp waits on an HBM
 // load with its registers tied up.  16 bytes past the span are copied too (the re-alignment of the last lane reads one word
 // beyond its read), which is why the batch's last group -- and everything that is not a uniform read -- takes the LDG path.
 constexpr int kStageBytes = 8 * kShortMaxLen + 32;   // 1312: spans of up to 8 * 160 bytes + 16, kept 16-byte aligned
 constexpr int kPreWarps = kPreThreads / 32;
 
-template <int CSA>
+template <int CSA, int STAGES>
 __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                    const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                    const UniformReads u, const uint16_t *__restrict__ thr,
                                                                    strgpu_repeat *__restrict__ out, uint32_t *__restrict__ list,
                                                                    uint32_t n_tma_groups) {
-  __shared__ __align__(128) unsigned char stage_buf[kPreWarps][2][kStageBytes];
-  __shared__ __align__(8) uint64_t stage_bar[kPreWarps][2];
+  __shared__ __align__(128) unsigned char stage_buf[kPreWarps][STAGES][kStageBytes];
+  __shared__ __align__(8) uint64_t stage_bar[kPreWarps][STAGES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint16_t *tfilt = thr + kThrFiltOff;
   const uint32_t warps_total = gridDim.x * kPreWarps;
@@ -1038,8 +1040,8 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
   // ---- part 1: uniform reads, staged through shared memory by bulk copies
   if (n_tma_groups != 0u) {
     if (lane == 0) {
-      mbar_init(&stage_bar[warp][0], 1);
-      mbar_init(&stage_bar[warp][1], 1);
+#pragma unroll
+      for (int i = 0; i < STAGES; i++) mbar_init(&stage_bar[warp][i], 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the initialised barriers visible to the copy engine
     }
     __syncwarp();
@@ -1050,16 +1052,24 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
     const int pclass = (int)u.pclass;
     uint32_t parity = 0;   // bit b = phase of buffer b
     int b = 0;
-    uint32_t g = warp_global;
-    if (g < n_tma_groups && lane == 0) {
-      mbar_expect_tx(&stage_bar[warp][0], span + 16u);
-      bulk_load(stage_buf[warp][0], gsrc + (size_t)g * span, span + 16u, &stage_bar[warp][0]);
+    uint32_t g = warp_global, g_issue = warp_global;
+    // STAGES - 1 groups are in flight while one is being counted
+#pragma unroll
+    for (int i = 0; i < STAGES - 1; i++) {
+      if (g_issue < n_tma_groups && lane == 0) {
+        mbar_expect_tx(&stage_bar[warp][i], span + 16u);
+        bulk_load(stage_buf[warp][i], gsrc + (size_t)g_issue * span, span + 16u, &stage_bar[warp][i]);
+      }
+      g_issue += warps_total;
     }
     while (g < n_tma_groups) {
-      const uint32_t gn = g + warps_total;
-      if (gn < n_tma_groups && lane == 0) {
-        mbar_expect_tx(&stage_bar[warp][b ^ 1], span + 16u);
-        bulk_load(stage_buf[warp][b ^ 1], gsrc + (size_t)gn * span, span + 16u, &stage_bar[warp][b ^ 1]);
+      {
+        const int bi = b == 0 ? STAGES - 1 : b - 1;     // the buffer the previous iteration finished reading
+        if (g_issue < n_tma_groups && lane == 0) {
+          mbar_expect_tx(&stage_bar[warp][bi], span + 16u);
+          bulk_load(stage_buf[warp][bi], gsrc + (size_t)g_issue * span, span + 16u, &stage_bar[warp][bi]);
+        }
+        g_issue += warps_total;
       }
       mbar_wait(&stage_bar[warp][b], (parity >> b) & 1u);
       parity ^= 1u << b;
@@ -1079,13 +1089,13 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
       bool keep = has_n;
       if (!has_n) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(stage_buf[warp][b] + (lane_byte & ~3u));
-        keep = prefilter_keep<CSA>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc);
+        keep = prefilter_keep<CSA, true>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc);
         if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
       }
       survivors_push(list, n_seg, keep, !has_n && L < kLongLen, s, lane);
       __syncwarp();   // every lane has read this buffer before the next iteration refills it
-      g = gn;
-      b ^= 1;
+      g += warps_total;
+      b = b + 1 == STAGES ? 0 : b + 1;
     }
   }
 
@@ -1102,7 +1112,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
     bool keep = active && !lane_path;   // non-ACGT bases or > 160 bases: the scan kernel's warp path
     if (lane_path) {
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-      keep = prefilter_keep<CSA>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc);
+      keep = prefilter_keep<CSA, false>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc);
       if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;
     }
     survivors_push(list, n_seg, keep, lane_path && L < kLongLen, s, lane);
@@ -1115,7 +1125,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
                                                                     const UniformReads u,
                                                                     const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
                                                                     strgpu_repeat *__restrict__ out, int *status,
-                                                                    const uint32_t *__restrict__ list) {
+                                                                    uint32_t *__restrict__ list) {
   // list == nullptr: every segment of the batch; else the two-ended survivor list of repeat_prefilter (survivors_push):
   // groups of 32 long segments first, then groups of 32 short ones
   extern __shared__ __align__(16) uint32_t smem[];
@@ -1135,7 +1145,14 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   const uint16_t *tmin = thr + kThrMinOff;
   const uint32_t n_groups = groups_long + (n_short + 31) / 32;
   const uint32_t warps_total = gridDim.x * kLaneWarps;
+  // groups are handed out dynamically when they come from the survivor list (their cost varies a lot: a warp takes the
+  // next group whenever its queues run low), statically otherwise
+  uint32_t *next_group = list ? list + 2 : nullptr;
   uint32_t grp = blockIdx.x * kLaneWarps + warp;
+  if (next_group) {
+    if (lane == 0) grp = atomicAdd(next_group, 1u);
+    grp = __shfl_sync(kFull, grp, 0);
+  }
   uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
   int v_len = -1;
   // Stage selection (all queues hold <= 64 entries): a stage pops <= 32 entries and pushes <= 32 into the next queue, and
@@ -1162,9 +1179,15 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
       do {
         const bool in_long = grp < groups_long;
         const uint32_t item = (in_long ? grp : grp - groups_long) * 32 + lane;
-        grp += warps_total;
+        if (next_group) {
+          uint32_t g = 0;
+          if (lane == 0) g = atomicAdd(next_group, 1u);
+          grp = __shfl_sync(kFull, g, 0);
+        } else {
+          grp += warps_total;
+        }
         const bool active = item < (in_long ? n_long : n_short);
-        const uint32_t s = (list && active) ? (in_long ? list[2u + item] : list[2u + n_seg - 1u - item]) : item;
+        const uint32_t s = (list && active) ? (in_long ? list[kListHdr + item] : list[kListHdr + n_seg - 1u - item]) : item;
         strgpu_segment sg{0, 0, 0, 0};
         if (active) sg = load_segment(segs, nmask, u, s);
         const int L = sg.len;
@@ -1324,7 +1347,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
   constexpr int kWarps = 8;
   const uint32_t blocks_needed = (n_seg + kWarps - 1) / kWarps;
   if (max_len <= (uint32_t)kShortMaxLen && variant != 1) {
-    // 0: repeat_prefilter + repeat_scan_lane over its survivor list (5..7: the same with 0 / 8 / 16 carry-save streams);
+    // 0: repeat_prefilter + repeat_scan_lane over its survivor list (5..7: the same with 0 / 12 / 16 carry-save streams);
     // 2 / 4: one fused kernel (plain / carry-save popcounts); 3: no pre-filter (A/B runs)
     auto kernel = variant == 2 ? repeat_scan_lane<0> : (variant == 4 ? repeat_scan_lane<1> : repeat_scan_lane<-1>);
     static bool configured[8] = {false, false, false, false, false, false, false, false};
@@ -1338,13 +1361,15 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
     const bool split = variant == 0 || variant >= 5;
     static const bool no_tma = getenv("STRGPU_NO_TMA") != nullptr;   // A/B: per-lane loads for uniform reads too
     if (split) {
-      cudaError_t e = cudaMemsetAsync(d_list, 0, 2 * sizeof(uint32_t), stream);
+      cudaError_t e = cudaMemsetAsync(d_list, 0, 4 * sizeof(uint32_t), stream);
       if (e != cudaSuccess) return e;
       const uint32_t groups = (n_seg + 31) / 32;
       uint32_t pre_grid = (uint32_t)sm_count * 4u;   // 4 resident CTAs of 8 warps per SM, grid-stride over groups of 32
       const uint32_t pre_need = (groups + kPreThreads / 32 - 1) / (kPreThreads / 32);
       if (pre_grid > pre_need) pre_grid = pre_need;
-      auto pre = variant == 5 ? repeat_prefilter<0> : (variant == 7 ? repeat_prefilter<16> : (variant == 6 ? repeat_prefilter<8> : repeat_prefilter<kPreCsaDefault>));
+      static const int stages = getenv("STRGPU_STAGES") ? atoi(getenv("STRGPU_STAGES")) : 4;   // A/B: staging depth
+      auto pre = variant == 7 ? (stages == 2 ? repeat_prefilter<16, 2> : repeat_prefilter<16, 4>)
+                              : (stages == 2 ? repeat_prefilter<kPreCsaDefault, 2> : repeat_prefilter<kPreCsaDefault, 4>);
       // uniform reads go through the TMA-staged part when their 32-read spans fit the staging buffers (all groups but the
       // batch's last one: the copy reads 16 bytes past its span)
       uint32_t n_tma = 0;

@@ -26,12 +26,12 @@ struct UniformReads {
 //              survivors; warp-per-segment kernel otherwise),
 //          1 = force the warp-per-segment kernel (kept for A/B measurements and as the long-segment path),
 //          2 / 4 = pre-filter fused into the lane kernel (plain / carry-save popcounts), 3 = lane kernel without the
-//          pre-filter, 5 / 6 / 7 = like 0 with 0 / 8 / 16 of the 16 popcount streams through carry-save adders (A/B)
+//          pre-filter, 5 / 6 / 7 = like 0 with 0 / 12 / 16 of the 16 popcount streams through carry-save adders (A/B)
 cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
                                uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
                                strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,
                                const UniformReads *uniform = nullptr, uint32_t *d_list = nullptr);
-// d_list: device scratch of n_seg + 2 uint32 (survivor list of the pre-filter kernel); without it the fused kernel runs
+// d_list: device scratch of n_seg + 4 uint32 (survivor list of the pre-filter kernel); without it the fused kernel runs
 
 // kernels one launch_repeat_scan call issues (for the library's launch counter)
 inline int scan_launches(uint32_t max_len, int variant) {
