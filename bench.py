@@ -338,7 +338,7 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # dominant kernel = the scan: its average launch time = (step time - cluster leg) / scan launches
+    # dominant kernels = the scan (pre-filter + ladder kernel per library call): average time per call = (step time - cluster leg) / calls
     launch_s = (sec_dev - args.steps * (cluster_ms + gather_ms) / 1e3) / max(1, scan_launches)
     achieved = ALGO_BYTES_PER_READ * shard_reads / launch_s / 1e9
     traffic = None
@@ -373,8 +373,8 @@ def run_ours(args):
                     "allgather_ms": gather_ms, "collective": "all_gather of 48-byte bounds records (NCCL)" if world > 1 else "none (1 GPU)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "repeat_scan",
-                     "note": "integer-issue bound, not HBM bound: see DESIGN.md"},
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "repeat_prefilter + repeat_scan_lane (one library call)",
+                     "note": "achieved = 62 B x reads per call / measured time of the call's two kernels; integer-pipe bound, not HBM bound: see DESIGN.md"},
         "clocks": clocks,
     }
     if cpu:
