@@ -30,6 +30,8 @@ ALGO_BYTES_PER_READ = 62  # ceil(150/4)=38 B 2-bit SEQ + 8 B descriptor + 16 B r
 READ_LEN = 150
 P_CLASSES = [0.8, 0.8 - 0.07, 0.6]
 METRIC = "reads/sec through extract+cluster at 150 bp; HBM GB/s vs roofline"
+WORKLOAD = ("configs[1]: 30x-WGS-scale synthetic 150 bp reads, config-2 class mix: repeat-unit scan of every read (extract K1) + "
+            "clustering of the shard's STR reads (K2-K4) + exchange / all-gather of cluster records")
 
 
 def log(*a):
@@ -67,22 +69,24 @@ class OracleTimer:
         self.job = (flat, off[order], lens[order], p[order], np.array_split(np.arange(len(off)), cores))
         self.n_reads, self.cores = n_reads, cores
 
-    def run(self) -> float:
+    def run(self, passes: int = 1) -> float:
         global _JOB
         _JOB = self.job
         t0 = time.perf_counter()
         if self.cores == 1:
-            _oracle_worker(0)
+            for _ in range(passes):
+                _oracle_worker(0)
         else:
             with mp.get_context("fork").Pool(self.cores) as pool:
-                pool.map(_oracle_worker, range(self.cores))
+                for _ in range(passes):
+                    pool.map(_oracle_worker, range(self.cores))
         return time.perf_counter() - t0
 
 
-def time_oracle(n_reads: int, seed: int, cores: int):
-    """Returns (reads/s, seconds, n_reads)."""
-    dt = OracleTimer(n_reads, seed, cores).run()
-    return n_reads / dt, dt, n_reads
+def time_oracle(n_reads: int, seed: int, cores: int, passes: int = 1):
+    """Returns (reads/s, seconds, reads processed)."""
+    dt = OracleTimer(n_reads, seed, cores).run(passes)
+    return n_reads * passes / dt, dt, n_reads * passes
 
 
 def run_reference(args):
@@ -105,7 +109,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1] class mix, 150 bp reads, CPU sample", "reads_per_step": per_step, "read_len": READ_LEN},
+        "config": {"workload": WORKLOAD, "sample": "bounded CPU sample of the same read mix (scan only: the path's dominant cost)",
+                   "reads_per_step": per_step, "read_len": READ_LEN},
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} reads/step of the config-2 mix, oracle (C restatement of utils.nim get_repeat; the Nim reference cannot be built here), {cores} processes"},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -125,7 +130,31 @@ class ClockSampler:
         self._t = None
         self.max_mhz = None
 
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            return False
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for nm, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -220,26 +249,39 @@ def run_ours(args):
     n_treads = len(treads)
     h_treads = torch.from_numpy(treads.view(np.uint8).reshape(-1).copy()).pin_memory()
     d_treads = h_treads.to(dev)
-    cap_bounds = max(1024, n_treads // 4)
+    cap_bounds = max(1024, n_treads // 2)
     d_bounds = torch.zeros(cap_bounds * 48, dtype=torch.uint8, device=dev)
     d_nb = torch.zeros(1, dtype=torch.int32, device=dev)
     cparams = sb.StrGpu.cluster_params(window=480, min_support=5, max_clip_dist=190)
     h_bounds = np.zeros(cap_bounds, dtype=sb.BOUNDS_DTYPE)
+    t32 = d_treads.view(torch.int32).view(-1, 6)
     log(f"[rank {rank}] cluster leg: {n_treads} treads ({time.time() - t0:.1f}s host gen)")
     cl_events = []
     cl_stats = {}
 
-    def cluster_device_leg():
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        g.cluster_device(d_treads.data_ptr(), n_treads, cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(), stream)
-        e1.record()
+    def cluster_owned(owned):
+        g.cluster_device(owned.data_ptr(), owned.shape[0], cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(), stream)
         n_local = int(d_nb.item())
-        allb, counts = parallel.allgather_records(d_bounds, min(n_local, cap_bounds))
+        if n_local > cap_bounds:
+            raise SystemExit("bench.py: bounds capacity too small")
+        return d_bounds, n_local
+
+    def cluster_device_leg():
+        # N > 1: every (tid, repeat) bucket has an owner rank; the STR-read records go to their owner (all-to-all over
+        # NVLink), every rank clusters the buckets it owns, the 48-byte cluster records are all-gathered
+        e0, ex, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        e0.record()
+        owned = parallel.exchange_by_owner(t32)
+        ex.record()
+        _, n_local = cluster_owned(owned)
+        e1.record()
+        allb, counts = parallel.allgather_records(d_bounds, n_local)
         e2.record()
-        cl_events.append((e0, e1, e2))
+        cl_events.append((e0, ex, e1, e2))
         cl_stats["bounds_local"] = n_local
         cl_stats["bounds_all"] = int(sum(counts))
+        cl_stats["treads_owned"] = int(owned.shape[0])
+        cl_stats["gathered"] = allb
 
     n_extra = n_seg - shard_reads           # soft-clip segments: the only ones that carry descriptors
     extra_max = int(segs["len"][shard_reads:].max()) if n_extra else 0
@@ -288,7 +330,9 @@ def run_ours(args):
         for _ in range(args.warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) and local < len(vis.split(",")) else local
+        sampler = ClockSampler(phys)
         if rank == 0:
             sampler.start()
         launches0 = g.launch_count
@@ -314,8 +358,33 @@ def run_ours(args):
     g.device_status(stream)
     torch.cuda.synchronize()
     timed_ev = cl_events[-args.steps:]
-    cluster_ms = float(np.mean([a.elapsed_time(b) for a, b, c in timed_ev]))
-    gather_ms = float(np.mean([b.elapsed_time(c) for a, b, c in timed_ev]))
+    exchange_ms = float(np.mean([a.elapsed_time(x) for a, x, b, c in timed_ev]))
+    cluster_ms = float(np.mean([a.elapsed_time(b) for a, x, b, c in timed_ev]))   # exchange + sort + chain + bounds kernels
+    gather_ms = float(np.mean([b.elapsed_time(c) for a, x, b, c in timed_ev]))
+    # N > 1, outside the timing: the sharded result equals ONE GPU clustering the concatenation of every rank's records
+    sharded_ok = None
+    if world > 1:
+        n_all = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(n_all, torch.tensor([n_treads], dtype=torch.int64, device=dev))
+        n_max = int(n_all.max())
+        pad = torch.zeros((n_max, 6), dtype=torch.int32, device=dev)
+        pad[:n_treads] = t32
+        everyone = torch.empty((world * n_max, 6), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(everyone, pad)
+        if rank == 0:
+            cat = torch.cat([everyone[r * n_max: r * n_max + int(n_all[r])] for r in range(world)]).contiguous()
+            cap1 = max(1024, cat.shape[0] // 2)
+            d_b1 = torch.zeros(cap1 * 48, dtype=torch.uint8, device=dev)
+            g.cluster_device(cat.data_ptr(), cat.shape[0], cparams, d_b1.data_ptr(), cap1, d_nb.data_ptr(), stream)
+            n1 = int(d_nb.item())
+            one = parallel.sort_bounds(parallel.bounds_from_bytes(d_b1[: n1 * 48]))
+            many = parallel.sort_bounds(parallel.bounds_from_bytes(cl_stats["gathered"]))
+            fields = ("tid", "left", "left_most", "right", "right_most", "center_mass", "n_left", "n_right", "n_total", "repeat", "n_reads")
+            sharded_ok = len(one) == len(many) and all(np.array_equal(one[f], many[f]) for f in fields)
+            if not sharded_ok:
+                raise SystemExit("bench.py: sharded clustering differs from one GPU over the concatenated records")
+            del d_b1, cat
+        del everyone, pad
     scan_launches = n_sub * args.steps      # library calls; each is a pre-filter kernel + a scan kernel over its survivors
     # spot-check: device-resident results of the last sub-batch equal the host-API results of the same shard
     sec_e2e, _, _ = timed(step_e2e, False)
@@ -351,16 +420,17 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate1, _, _ = time_oracle(20_000, seed=1, cores=1)
-        n_cpu = int(min(8_000_000, max(100_000, rate1 * cores * 12.0)))
-        v, dt, n = time_oracle(n_cpu, seed=2, cores=cores)
+        n_cpu = int(min(8_000_000, max(100_000, rate1 * cores * 3.0)))
+        passes = 5      # ~15 s of CPU work on every core
+        v, dt, n = time_oracle(n_cpu, seed=2, cores=cores, passes=passes)
         cpu = {"value": v, "unit": "reads/s", "cores": cores, "kind": "port", "single_core_value": rate1,
-               "sample": f"{n} reads of the same config-2 mix in {dt:.1f}s, oracle (C restatement of the reference CPU path), {cores} processes"}
+               "sample": f"{n} reads ({passes} passes over {n_cpu} reads of the same config-2 mix) in {dt:.1f}s, oracle (C restatement of the reference CPU path), {cores} processes"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sec_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: 30x-WGS-scale synthetic 150 bp reads, config-2 class mix: repeat-unit scan of every read (extract K1) + clustering of the shard's STR reads (K2-K4) + all-gather of cluster records",
+        "config": {"workload": WORKLOAD,
                    "reads_per_gpu": reads_per_gpu, "segments_per_gpu": n_seg * n_sub, "read_len": READ_LEN,
                    "sub_batches_per_step": n_sub, "reads_per_launch": shard_reads,
                    "l2": f"each launch streams {(seq_bytes + 16 * n_seg) / 1e6:.0f} MB of its own HBM region (> 126 MB L2); {n_sub} distinct regions per step",
@@ -370,7 +440,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(n_sub * n_seg * 8 + cl_stats.get("bounds_local", 0) * 48), "ms_per_step": 1e3 * sec_e2e / args.steps},
         "cluster": {"treads_per_gpu": n_treads, "ms_per_step": cluster_ms, "treads_per_s": n_treads / (cluster_ms / 1e3),
                     "bounds_per_gpu": cl_stats.get("bounds_local"), "bounds_gathered": cl_stats.get("bounds_all"),
-                    "allgather_ms": gather_ms, "collective": "all_gather of 48-byte bounds records (NCCL)" if world > 1 else "none (1 GPU)"},
+                    "allgather_ms": gather_ms, "exchange_ms": exchange_ms, "treads_owned": cl_stats.get("treads_owned"),
+                    "collective": "all_to_all of 24-byte STR-read records by bucket owner + all_gather of 48-byte bounds records (NCCL)" if world > 1 else "none (1 GPU)",
+                    "sharded_equals_single_gpu": sharded_ok},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "repeat_prefilter + repeat_scan_lane (one library call)",

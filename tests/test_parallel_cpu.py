@@ -64,3 +64,57 @@ def test_single_process_passthrough():
     buf = torch.from_numpy(mine.view(np.uint8).copy())
     allb, counts = parallel.allgather_records(buf, 4)
     assert counts == [4] and np.array_equal(parallel.bounds_from_bytes(allb), mine)
+
+
+# ---- sharded clustering: exchange by bucket owner + per-rank clustering + all-gather == one process over the concatenation
+def _shard_treads(rank):
+    from strling_b200 import synth
+
+    return synth.make_treads(60, seed=500 + rank, n_tids=5, n_samples=2, noise_reads=400, unplaced=30, dense=True)
+
+
+def _oracle_cluster_fn(t32):
+    # CPU stand-in for strgpu_cluster_device in this test: the oracle's cluster loop (tests may use the oracle)
+    from oracle import oracle as orc
+
+    treads = t32.numpy().view(np.uint8).reshape(-1).view(orc.TREAD_DTYPE) if t32.shape[0] else np.zeros(0, dtype=orc.TREAD_DTYPE)
+    b, unplaced = orc.cluster_all(treads, 480, 3, 0, 0, 190)
+    out = np.zeros(len(b) + len(unplaced), dtype=BOUNDS_DTYPE)
+    for f in ("tid", "left", "left_most", "right", "right_most", "center_mass", "n_left", "n_right", "n_total", "repeat", "n_reads"):
+        out[f][: len(b)] = b[f]
+    for i, (unit, cnt) in enumerate(sorted(unplaced.items())):
+        out["tid"][len(b) + i], out["repeat"][len(b) + i], out["n_reads"][len(b) + i] = -1, unit, cnt
+    return torch.from_numpy(out.view(np.uint8).reshape(-1).copy()), len(out)
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = _shard_treads(rank)
+    t32 = torch.from_numpy(mine.view(np.uint8).reshape(-1).view(np.int32).reshape(-1, 6).copy())
+    owned = parallel.exchange_by_owner(t32)
+    # every record of a bucket lands on one rank, in concatenation order
+    own = parallel.bucket_owner(owned, world)
+    assert bool((own == rank).all())
+    res, counts = parallel.cluster_sharded(_oracle_cluster_fn, t32)
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), res)
+    np.save(os.path.join(out_dir, f"o{rank}.npy"), owned.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_clustering_equals_single_process_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    allt = np.concatenate([_shard_treads(0), _shard_treads(1)])
+    t32 = torch.from_numpy(allt.view(np.uint8).reshape(-1).view(np.int32).reshape(-1, 6).copy())
+    raw, n = _oracle_cluster_fn(t32)
+    expect = parallel.sort_bounds(parallel.bounds_from_bytes(raw[: n * BOUNDS_DTYPE.itemsize]))
+    # owned records: a partition of the concatenation that keeps its order inside every bucket
+    owned = [np.load(tmp_path / f"o{r}.npy") for r in range(2)]
+    assert sum(len(o) for o in owned) == len(allt)
+    for r in range(2):
+        got = np.load(tmp_path / f"s{r}.npy")
+        assert len(got) == len(expect) and len(expect) > 20
+        for f in ("tid", "left", "left_most", "right", "right_most", "center_mass", "n_left", "n_right", "n_total", "repeat", "n_reads"):
+            assert np.array_equal(got[f], expect[f]), f
