@@ -307,41 +307,43 @@ static_assert(kCls5 / 4 <= kTabWords, "k = 5 counters must fit");
 // read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254).
 // One copy for all k, kept out of line (instruction-cache footprint).  `scratch` is the lane's counter column (dead by
 // now); `magic` = 65536 / K + 1 turns the one division of the slow path into a multiply.
+// NW: words that hold the segment (4: segments of <= 64 bases, the soft clips; 10: up to 160 bases).
+template <int NW>
 __device__ __noinline__ int lane_recount(const uint32_t *rd, uint32_t *scratch, int L, uint32_t pat, int K, uint32_t magic) {
   const int npos = L - K + 1;
   if (npos <= 0) return 0;
   constexpr uint32_t kLow = 0x55555555u;
-  uint32_t w[11], m[10];
+  uint32_t w[NW + 1], m[NW];
 #pragma unroll
-  for (int i = 0; i < 10; i++) w[i] = rd[i * 32];
-  w[10] = 0;
+  for (int i = 0; i < NW; i++) w[i] = rd[i * 32];
+  w[NW] = 0;
 #pragma unroll
-  for (int i = 0; i < 10; i++) {  // keep positions < npos (position p of word i sits at bit 30 - 2p)
+  for (int i = 0; i < NW; i++) {  // keep positions < npos (position p of word i sits at bit 30 - 2p)
     const int n = npos - 16 * i;
     m[i] = n >= 16 ? kLow : (n <= 0 ? 0u : (kLow & ~((1u << (32 - 2 * n)) - 1u)));
   }
 #pragma unroll 1
   for (int j = 0; j < K; j++) {
     const uint32_t rep = ((pat >> (2 * (K - 1 - j))) & 3u) * kLow;
-    uint32_t e[11];
+    uint32_t e[NW + 1];
 #pragma unroll
-    for (int i = 0; i < 11; i++) {
+    for (int i = 0; i < NW + 1; i++) {
       const uint32_t t = w[i] ^ rep;
       e[i] = ~(t | (t >> 1)) & kLow;          // slot LSB set <=> that base equals pattern base j
     }
 #pragma unroll
-    for (int i = 0; i < 10; i++) m[i] &= __funnelshift_l(e[i + 1], e[i], 2 * j);
+    for (int i = 0; i < NW; i++) m[i] &= __funnelshift_l(e[i + 1], e[i], 2 * j);
   }
   uint32_t conflict = 0;
 #pragma unroll 1
   for (int d = 1; d < K; d++) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) conflict |= m[i] & __funnelshift_l(i < 9 ? m[i + 1] : 0u, m[i], 2 * d);
+    for (int i = 0; i < NW; i++) conflict |= m[i] & __funnelshift_l(i < NW - 1 ? m[i + 1] : 0u, m[i], 2 * d);
   }
   int c = 0;
   if (conflict == 0) {  // no two matches closer than K: every match counts
 #pragma unroll
-    for (int i = 0; i < 10; i++) c += __popc(m[i]);
+    for (int i = 0; i < NW; i++) c += __popc(m[i]);
     return c;
   }
   if (K == 2) {
@@ -349,17 +351,17 @@ __device__ __noinline__ int lane_recount(const uint32_t *rd, uint32_t *scratch, 
     // greedy walk takes every other one from each run's start: ceil(r / 2) = the run's positions that share the
     // parity of its start.  Runs that start on even positions are isolated with one multi-word add (the carry
     // runs through exactly those runs), so the count is two popcounts per word instead of a serial walk.
-    uint32_t f[10], sel = 0;
+    uint32_t f[NW], sel = 0;
     int cy = 0;
     c = 0;
 #pragma unroll
-    for (int i = 0; i < 10; i++) {            // LSB-first: position p of word i -> bits 2p, 2p+1 (both set for a match)
+    for (int i = 0; i < NW; i++) {            // LSB-first: position p of word i -> bits 2p, 2p+1 (both set for a match)
       const uint32_t r = __brev(m[i]);        // match bit of position p now at bit 2p + 1
       f[i] = r | (r >> 1);
     }
     uint32_t prev_top = 0;                     // was the last position of the previous word a match?
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < NW; i++) {
       const uint32_t prevm = (f[i] << 2) | (prev_top ? 3u : 0u);   // match state of position p - 1
       const uint32_t starts = f[i] & ~prevm & 0x55555555u;          // low bit of each run's first position
       const uint32_t es = starts & 0x11111111u;                     // runs starting on an even position
@@ -375,10 +377,10 @@ __device__ __noinline__ int lane_recount(const uint32_t *rd, uint32_t *scratch, 
   }
   // other self-overlapping patterns (ACAC.., AAA.. at k >= 3): walk the runs of consecutive match positions
 #pragma unroll
-  for (int i = 0; i < 10; i++) scratch[i * 32] = m[i];
+  for (int i = 0; i < NW; i++) scratch[i * 32] = m[i];
   int next = 0;  // first position the greedy walk may use
 #pragma unroll 1
-  for (int i = 0; i < 10; i++) {
+  for (int i = 0; i < NW; i++) {
     uint32_t mm = scratch[i * 32];
     while (mm) {
       const int hb = 31 - __clz(mm);                       // earliest remaining match of this word
@@ -646,7 +648,8 @@ __device__ __forceinline__ bool lane_decide(const uint32_t *rd, uint32_t *tab, i
                                             int thr_giveup, ScanState &st) {
   int score = M * K;
   if (score <= st.best) return !(M < thr_giveup);
-  const int c = lane_recount(rd, tab, L, leader, K, 65536u / (uint32_t)K + 1u);
+  const uint32_t magic = 65536u / (uint32_t)K + 1u;
+  const int c = L <= 64 ? lane_recount<4>(rd, tab, L, leader, K, magic) : lane_recount<10>(rd, tab, L, leader, K, magic);
   score = c * K;
   if (score < st.best) return true;
   st.best = score;
@@ -1155,20 +1158,25 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   }
   uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
   int v_len = -1;
-  // Stage selection (all queues hold <= 64 entries): a stage pops <= 32 entries and pushes <= 32 into the next queue, and
-  // it only runs when that next queue holds < 32 -- downstream queues are served first; upstream work (new segments)
-  // is taken only when every queue is below a full batch; at the end the queues are drained upstream-first.
+  // Stages: 1 new segments (pre-filter when fused) -> Q2; 2 counts k = 2, 3 and decides the k = 2 rung; 4, 5, 6 count k = 4, 5, 6;
+  // R = every recount a rung k >= 3 needs (read.count(s), utils.nim:254) followed by that rung's decision: lanes that need one are
+  // pushed to QR (q3) with their k, M and leader instead of recounting divergently inside the counting stage, so recounts run 32
+  // lanes wide.  All queues hold <= 64 entries; a stage pops <= 32 and pushes <= 32 into any queue downstream of it, and runs only
+  // when those queues have room for a full batch -- except that a counting stage whose recount queue is full recounts in place
+  // (the pre-v7 behaviour), which is what makes the schedule deadlock free.  Downstream stages are served first; new segments are
+  // taken only when no queue holds a full batch; at the end the queues are drained upstream-first.
   while (true) {
     const bool more = grp < n_groups;
+    const bool r_ok = n4 <= 32 && n5 <= 32 && n6 <= 32;   // stage R pushes into Q4 / Q5 / Q6
     int stage;
     if (n6 >= 32) stage = 6;
     else if (n5 >= 32) stage = 5;
     else if (n4 >= 32) stage = 4;
-    else if (n3 >= 32) stage = 3;
+    else if (n3 >= 32 && r_ok) stage = 3;
     else if (n2 >= 32) stage = 2;
     else if (more) stage = 1;
     else if (n2 > 0) stage = 2;
-    else if (n3 > 0) stage = 3;
+    else if (n3 > 0 && r_ok) stage = 3;
     else if (n4 > 0) stage = 4;
     else if (n5 > 0) stage = 5;
     else if (n6 > 0) stage = 6;
@@ -1224,12 +1232,12 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
     }
 
     if (stage == 2) {
-      // ---- stage 2: count k = 2 and 3; the k = 2 rung (its recount is warp-uniform); the k = 3 rung if it needs no recount
+      // ---- stage 2: count k = 2 and 3; the k = 2 rung (every lane recounts: best is still -1); the k = 3 rung if it needs no recount
       const int nb = n2 < 32 ? n2 : 32;
       const int first = n2 - nb;
       uint32_t s = 0, extra = 0;
       ScanState st{-1, 0u, 0, 0};
-      int next_k = 0;  // 0: finished, 3: needs the k = 3 recount (Q3), 4: goes on to k = 4
+      int next_k = 0;  // 0: finished, 3: needs the k = 3 recount (QR), 4: goes on to k = 4
       if (lane < nb) {
         s = q2[first + lane];
         const strgpu_segment sg = load_segment(segs, nmask, u, s);
@@ -1242,7 +1250,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
         const int M2 = (int)(best2 >> 13), M3 = (int)(best3 >> 13);
         const uint32_t lead2 = M2 ? (uint32_t)lut[kRev234 + (best2 & 31u)] : 0xfu;
         const uint32_t lead3 = M3 ? (uint32_t)lut[kRev234 + kCls2 + (best3 & 31u)] : 0x3fu;
-        extra = (uint32_t)M3 | (lead3 << 8);
+        extra = (uint32_t)M3 | (lead3 << 8) | (3u << 20);
         bool go = lane_decide(rd, tab, L, 2, M2, lead2, tp[0], tg[L], st);
         if (go) {
           if (3 * M3 > st.best) next_k = 3;                       // needs the k = 3 recount
@@ -1258,40 +1266,80 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
       continue;
     }
 
-    // ---- queued stages: 32 segments at a time, one per lane
-    const int qn = stage == 3 ? n3 : (stage == 4 ? n4 : (stage == 5 ? n5 : n6));
+    if (stage == 3) {
+      // ---- stage R: recounts of any rung k = 3..6, 32 lanes wide; then the rung's decision (utils.nim:254-265)
+      const int nb = n3 < 32 ? n3 : 32;
+      const int first = n3 - nb;
+      uint32_t s = 0, extra = 0;
+      ScanState st{-1, 0u, 0, 0};
+      int k = 0;
+      if (lane < nb) {
+        queue_read<3>(q3, first + lane, s, st, extra);
+        k = (int)(extra >> 20);
+        const uint32_t leader = (extra >> 8) & 0xfffu;
+        const strgpu_segment sg = load_segment(segs, nmask, u, s);
+        const int L = sg.len;
+        lane_stage(seq, sg, rd);
+        const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
+        const uint32_t magic = 65536u / (uint32_t)k + 1u;
+        const int c = L <= 64 ? lane_recount<4>(rd, tab, L, leader, k, magic) : lane_recount<10>(rd, tab, L, leader, k, magic);
+        const int score = c * k;
+        if (score >= st.best) {
+          st.best = score;
+          if (c > (int)thr[(size_t)(pclass * 5 + k - 2) * kThrLen + L]) {
+            st.unit_code = leader;
+            st.unit_k = k;
+            st.rc = c;
+          }
+        }
+        if (k == 6) emit_result(out, s, st);
+      }
+      __syncwarp();
+      n3 = first;
+      queue_push<2>(q4, n4, k == 3, lane, s, st, 0);
+      queue_push<2>(q5, n5, k == 4, lane, s, st, 0);
+      queue_push<2>(q6, n6, k == 5, lane, s, st, 0);
+      continue;
+    }
+
+    // ---- counting stages k = 4, 5, 6: 32 segments at a time, one per lane
+    const int qn = stage == 4 ? n4 : (stage == 5 ? n5 : n6);
     const int nb = qn < 32 ? qn : 32;
     const int first = qn - nb;
+    const bool defer = n3 <= 32;            // room for a full batch in the recount queue; else recount in place
     uint32_t s = 0, extra = 0;
     ScanState st{-1, 0u, 0, 0};
-    bool go = false;
+    int what = 0;                           // 0: finished (emitted), 1: next counting stage, 2: recount queue
     if (lane < nb) {
-      if (stage == 3) queue_read<3>(q3, first + lane, s, st, extra);
-      else queue_read<2>(stage == 4 ? q4 : (stage == 5 ? q5 : q6), first + lane, s, st, extra);
+      queue_read<2>(stage == 4 ? q4 : (stage == 5 ? q5 : q6), first + lane, s, st, extra);
       const strgpu_segment sg = load_segment(segs, nmask, u, s);
       const int L = sg.len;
       lane_stage(seq, sg, rd);
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
       int M;
       uint32_t leader;
-      if (stage == 3) {          // the k = 3 rung with its recount; counts were taken in stage 2
-        M = (int)(extra & 0xffu);
-        leader = (extra >> 8) & 0x3fu;
-      } else if (stage == 4) {
-        lane_count4(rd, tab, lut, L, M, leader);
-      } else if (stage == 5) {
-        lane_count5(rd, tab, lut, L, M, leader);
+      if (stage == 4) lane_count4(rd, tab, lut, L, M, leader);
+      else if (stage == 5) lane_count5(rd, tab, lut, L, M, leader);
+      else lane_count6(rd, tab, L, M, leader);
+      if (M * stage <= st.best) {           // no recount: break or continue (utils.nim:250-253)
+        what = (M < (int)tg[(stage - 2) * kThrLen + L]) ? 0 : 1;
+      } else if (defer) {
+        what = 2;
+        extra = (uint32_t)M | (leader << 8) | ((uint32_t)stage << 20);
       } else {
-        lane_count6(rd, tab, L, M, leader);
+        lane_decide(rd, tab, L, stage, M, leader, thr[(size_t)(pclass * 5 + stage - 2) * kThrLen + L], tg[(stage - 2) * kThrLen + L], st);
+        what = 1;
       }
-      go = lane_decide(rd, tab, L, stage, M, leader, thr[(size_t)(pclass * 5 + stage - 2) * kThrLen + L], tg[(stage - 2) * kThrLen + L], st);
-      if (!go || stage == 6) emit_result(out, s, st);
+      if (what == 0 || (what == 1 && stage == 6)) {
+        emit_result(out, s, st);
+        what = 0;
+      }
     }
     __syncwarp();
-    if (stage == 3) { n3 = first; queue_push<2>(q4, n4, go, lane, s, st, 0); }
-    else if (stage == 4) { n4 = first; queue_push<2>(q5, n5, go, lane, s, st, 0); }
-    else if (stage == 5) { n5 = first; queue_push<2>(q6, n6, go, lane, s, st, 0); }
+    if (stage == 4) { n4 = first; queue_push<2>(q5, n5, what == 1, lane, s, st, 0); }
+    else if (stage == 5) { n5 = first; queue_push<2>(q6, n6, what == 1, lane, s, st, 0); }
     else n6 = first;
+    queue_push<3>(q3, n3, what == 2, lane, s, st, extra);
   }
 }
 
