@@ -484,7 +484,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-gpu", type=int, default=600_000_000)
-    ap.add_argument("--shard-reads", type=int, default=6_000_000)
+    ap.add_argument("--shard-reads", type=int, default=12_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     quiet_stdout()

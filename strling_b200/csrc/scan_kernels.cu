@@ -1169,10 +1169,10 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
     const bool more = grp < n_groups;
     const bool r_ok = n4 <= 32 && n5 <= 32 && n6 <= 32;   // stage R pushes into Q4 / Q5 / Q6
     int stage;
-    if (n6 >= 32) stage = 6;
+    if (n3 >= 32 && r_ok) stage = 3;       // keep the recount queue below a full batch so that counting stages can defer into it
+    else if (n6 >= 32) stage = 6;
     else if (n5 >= 32) stage = 5;
     else if (n4 >= 32) stage = 4;
-    else if (n3 >= 32 && r_ok) stage = 3;
     else if (n2 >= 32) stage = 2;
     else if (more) stage = 1;
     else if (n2 > 0) stage = 2;
