@@ -23,6 +23,7 @@ int extract_main(int argc, char **argv);
 int merge_main(int argc, char **argv);
 int call_main(int argc, char **argv);
 int debug_main(int argc, char **argv);
+int debug_genotype(int argc, char **argv);
 int index_main(int argc, char **argv);
 std::vector<std::string> genome_repeat_lines(const std::string &fasta, double proportion_repeat, int device);
 

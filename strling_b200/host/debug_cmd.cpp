@@ -44,6 +44,7 @@ Tread read_tread(std::istream &in) {
 int debug_main(int argc, char **argv) {
   if (argc < 1) return 1;
   const std::string what = argv[0];
+  if (what == "genotype") return debug_genotype(argc - 1, argv + 1);
   if (what == "bam" && argc >= 2) {
     BamReader rd(argv[1]);
     std::printf("@targets %zu\n", rd.targets().size());

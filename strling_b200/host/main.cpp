@@ -13,7 +13,7 @@ int main(int argc, char **argv) {
       "  extract       :   extract informative STR reads from a BAM (repeat-unit scan on the GPU)\n"
       "  merge         :   merge putative STR loci from multiple samples (clustering on the GPU)\n"
       "  index         :   find STR-like regions of a reference genome (the genome-repeats file of extract -g)\n"
-      "  call          :   discover STR loci of one sample (clustering on the GPU; no genotypes in this build)\n";
+      "  call          :   discover and genotype the STR loci of one sample (clustering on the GPU)\n";
   if (argc < 2 || !std::strcmp(argv[1], "-h") || !std::strcmp(argv[1], "--help")) {
     std::fputs(usage, stdout);
     return argc < 2 ? 1 : 0;

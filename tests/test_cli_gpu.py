@@ -9,6 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
+from oracle import call_oracle as co
 from oracle import extract_oracle as eo
 from strling_b200 import bamio
 from strling_b200 import build as sb_build
@@ -96,15 +97,18 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
         datas.append(exp)
         if s == 0:
             first_bam, first_recs = bam, recs
-    # call: cluster loop of one sample (call.nim:223-235) -> -bounds.txt, -unplaced.txt
+    # call: cluster loop of one sample on the GPU, then spanning evidence + genotypes on the host (call.nim:223-281)
+    # -> -bounds.txt (with the depth column), -unplaced.txt, -genotype.txt
     prefix = str(tmp_path / "call")
     run(cli, "call", "-m", "3", "-o", prefix, first_bam, bins[0])
-    exp_lines, exp_unplaced, _ = eo.call_clusters(datas[0], eo.fragment_length_distribution(first_recs), min_support=3)
+    exp_gt, exp_lines, exp_unplaced = co.call(first_recs, datas[0], min_support=3)
     got = open(prefix + "-bounds.txt").read().splitlines()
-    assert got[0] == eo.BOUNDS_HEADER
+    assert got[0] == eo.BOUNDS_HEADER + "\tdepth"
     assert len(exp_lines) > 10 and sorted(got[1:]) == sorted(exp_lines) and got[1:] == exp_lines
     got_un = dict(l.split("\t") for l in open(prefix + "-unplaced.txt").read().splitlines())
     assert {k.encode(): int(v) for k, v in got_un.items()} == exp_unplaced and len(exp_unplaced) > 0
+    got_gt = open(prefix + "-genotype.txt").read().splitlines()
+    assert got_gt[0] == co.GT_HEADER and len(exp_gt) == len(exp_lines) and sorted(got_gt[1:]) == sorted(exp_gt)
     # merge: joint clustering with per-sample support (merge.nim:172-187)
     for ms, extra in ((5, []), (2, ["-c", "0", "-t", "3"]), (2, ["-c", "1", "-t", "1"]), (4, ["-w", "300"])):
         prefix = str(tmp_path / f"merge{ms}{''.join(extra)}")
