@@ -422,8 +422,77 @@ def sorted_tread_order(treads) -> np.ndarray:
     return np.lexsort(keys)
 
 
-def call(records, bin_data: bytes, min_support=5, min_clip=0, min_clip_total=0, min_mapq=40):
-    """call_main without -l / -b (call.nim:96-130,223-281).  Returns (genotype lines, bounds lines incl. depth, unplaced dict)."""
+def parse_bounds_lines(lines, targets):  # cluster.nim:143-169
+    names = [t[0] for t in targets]
+    out = []
+    for l in lines:
+        if l.startswith("#"):
+            continue
+        f = l.split("\t")
+        assert len(f) == 11
+        out.append(dict(tid=names.index(f[0]), left=int(f[1]), right=int(f[2]), repeat=f[3], name=f[4], left_most=int(f[5]),
+                        right_most=int(f[6]), center_mass=int(f[7]), n_left=int(f[8]), n_right=int(f[9]), n_total=int(f[10])))
+    return out
+
+
+def parse_bed_lines(lines, targets, window):  # cluster.nim:111-141
+    names = [t[0] for t in targets]
+    out = []
+    for l in lines:
+        f = l.split()
+        assert len(f) in (4, 5)
+        tid = names.index(f[0])
+        left, right = int(f[1]), int(f[2])
+        out.append(dict(tid=tid, left=left, right=right, repeat=f[3], name=f[4] if len(f) == 5 else "", left_most=max(left - window, 0),
+                        right_most=min(right + window, targets[tid][1]), center_mass=0, n_left=0, n_right=0, n_total=0))
+    return out
+
+
+def merge_loci_into_bounds(bounds, loci):  # call.nim:168-187
+    loci = list(loci)
+    for bound in bounds:
+        for i, locus in enumerate(loci):
+            if locus["tid"] == bound["tid"] and locus["repeat"] == bound["repeat"] and max(locus["left"], bound["left"]) <= min(locus["right"], bound["right"]):
+                bound["name"], bound["left"], bound["right"] = locus["name"], locus["left"], locus["right"]
+                loci[i] = loci[-1]      # seq.del(i)
+                loci.pop()
+                break
+    return bounds + loci
+
+
+def assign_reads_locus(locus, buckets, treads):  # callclusters.nim:14-50; buckets: {(tid, repeat bytes): [record indices by position]}
+    key = (locus["tid"], locus["repeat"].encode())
+    trs = buckets.get(key, [])
+    lm = 0 if locus["left_most"] == 0 else locus["left_most"] - 1
+    pos = [int(treads["position"][i]) for i in trs]
+    import bisect
+
+    li = bisect.bisect_left(pos, lm)
+    ri = bisect.bisect_right(pos, locus["right_most"])
+    res = []
+    if trs:
+        res = trs[li:ri]
+        keep = trs[:li]
+        if ri < len(trs) - 1:
+            keep = keep + trs[ri + 1:]
+        buckets[key] = keep
+    locus["n_total"] = locus["n_left"] = locus["n_right"] = 0
+    for i in res:
+        locus["n_total"] += 1
+        if int(treads["split"][i]) == orc.RIGHT:
+            locus["n_right"] += 1
+        elif int(treads["split"][i]) == orc.LEFT:
+            locus["n_left"] += 1
+    return res
+
+
+def locus_bounds_line(b, targets) -> str:  # cluster.nim:262-266
+    return (f"{targets[b['tid']][0]}\t{b['left']}\t{b['right']}\t{b['repeat']}\t{b['name']}\t{b['left_most']}\t{b['right_most']}\t{b['center_mass']}\t"
+            f"{b['n_left']}\t{b['n_right']}\t{b['n_total']}")
+
+
+def call(records, bin_data: bytes, min_support=5, min_clip=0, min_clip_total=0, min_mapq=40, bounds_lines=None, bed_lines=None):
+    """call_main (call.nim:96-281).  Returns (genotype lines, bounds lines incl. depth, unplaced dict)."""
     u = eo.unpack_bin(bin_data)
     targets = eo.targets_from_header(u["header"])
     frag = eo.fragment_length_distribution(records)
@@ -432,27 +501,46 @@ def call(records, bin_data: bytes, min_support=5, min_clip=0, min_clip_total=0, 
     mcd = int(0.5 * float(med)) & 0xFFFF
     opts = dict(min_clip=min_clip, min_clip_total=min_clip_total, min_support=min_support, median_fragment_length=med)
     treads, qnames = u["treads"], u["qnames"]
-    b, unplaced = orc.cluster_all(treads, window, min_support, min_clip, min_clip_total, mcd, merge_mode=False)
-    order = sorted_tread_order(treads)
     cd = cumulative(frag)
-    placed = [a for a in records if a.tid >= 0]
     by_tid = {}
-    for a in placed:
-        by_tid.setdefault(a.tid, []).append(a)
-    calls, bounds_lines = [], []
-    for x in b:
-        tid, left, right = int(x["tid"]), int(x["left"]), int(x["right"])
-        rep = bytes(x["repeat"]).rstrip(b"\0").decode()
+    for a in records:
+        if a.tid >= 0:
+            by_tid.setdefault(a.tid, []).append(a)
+    calls, bounds_out = [], []
+
+    def genotype_one(tid, left, right, rep, n_left, n_right, idx, line):
         sup, md, expected = spanners(by_tid.get(tid, []), tid, left, right, rep, window, frag, cd, min_mapq)
         if len(sup) > 5000 or md == -1:
-            continue
-        idx = order[int(x["first_read"]): int(x["first_read"]) + int(x["n_reads"])]
+            return
         tandems = [(int(treads["repeat_count"][i]), int(treads["split"][i]), qnames[i]) for i in idx]
-        c = genotype(targets[tid][0], left, right, int(x["n_left"]), int(x["n_right"]), rep, tandems, sup, opts, float(md))
+        c = genotype(targets[tid][0], left, right, n_left, n_right, rep, tandems, sup, opts, float(md))
         c["expected_spanning_fragments"] = expected
         c["canon"] = orc.canonical_repeat(rep)
         calls.append(c)
-        bounds_lines.append(eo.bounds_line(x, targets) + "\t" + str(md))
+        bounds_out.append(line + "\t" + str(md))
+
+    # -b / -l loci take their reads first (call.nim:158-218)
+    keep = np.arange(len(treads))
+    if bounds_lines or bed_lines:
+        lb = merge_loci_into_bounds(parse_bounds_lines(bounds_lines or [], targets), parse_bed_lines(bed_lines or [], targets, window))
+        order_all = sorted_tread_order(treads)
+        buckets = {}
+        for i in order_all:
+            buckets.setdefault((int(treads["tid"][i]), bytes(treads["repeat"][i]).rstrip(b"\0")), []).append(int(i))
+        for b in lb:
+            idx = assign_reads_locus(b, buckets, treads)
+            if b["right"] - b["left"] > 1000:
+                continue
+            genotype_one(b["tid"], b["left"], b["right"], b["repeat"], b["n_left"], b["n_right"], idx, locus_bounds_line(b, targets))
+        keep = np.array(sorted(i for v in buckets.values() for i in v), dtype=np.int64)
+    sub = treads[keep]
+    b, unplaced = orc.cluster_all(sub, window, min_support, min_clip, min_clip_total, mcd, merge_mode=False)
+    order = sorted_tread_order(sub)
+    for x in b:
+        tid, left, right = int(x["tid"]), int(x["left"]), int(x["right"])
+        rep = bytes(x["repeat"]).rstrip(b"\0").decode()
+        idx = [int(keep[j]) for j in order[int(x["first_read"]): int(x["first_read"]) + int(x["n_reads"])]]
+        genotype_one(tid, left, right, rep, int(x["n_left"]), int(x["n_right"]), idx, eo.bounds_line(x, targets))
     add_percentile(calls)
     by_rep = {}
     for c in calls:
@@ -462,9 +550,9 @@ def call(records, bin_data: bytes, min_support=5, min_clip=0, min_clip_total=0, 
         gts = by_rep[rep]
         large = [g for g in gts if g["is_large"]][:2]
         if len(large) == 1:
-            n_un = unplaced.get(rep.encode() if isinstance(rep, str) else rep, 0)
+            n_un = unplaced.get(rep, 0)
             large[0]["unplaced_reads"] = n_un
             if n_un > 2:
                 large[0]["allele2"] = unplaced_est(n_un, large[0]["depth"]) / float(len(large[0]["repeat"]))
         lines += [call_line(g) for g in gts]
-    return lines, bounds_lines, unplaced
+    return lines, bounds_out, unplaced, (sub, b)

@@ -305,18 +305,84 @@ int merge_main(int argc, char **argv) {
   return 0;
 }
 
+// The -b / -l part of call_main before clustering (call.nim:158-218 minus the genotyping): fills `loci` (output order), the reads
+// each locus takes, and -- when there are loci -- `remaining`, the records left for the cluster loop in `.bin` order.
+void prepare_call_loci(const BinFile &bf, const std::vector<std::pair<std::string, uint32_t>> &targets, uint32_t window, const std::string &bounds_path,
+                       const std::string &bed_path, std::vector<LocusLine> &loci, std::vector<std::vector<const Tread *>> &loci_reads,
+                       std::vector<Tread> &remaining) {
+  // call.nim:158-187: -b bounds, then -l loci; a locus that overlaps a bound (same contig and unit) overwrites its name and
+  // interval and is consumed (seq.del: the last locus moves into its place); the remaining loci are appended
+  if (!bounds_path.empty()) loci = parse_bounds(bounds_path, targets);
+  if (!bed_path.empty()) {
+    std::vector<LocusLine> bed = parse_bed(bed_path, targets, window, INT32_MIN);
+    for (LocusLine &bound : loci)
+      for (size_t i = 0; i < bed.size(); i++) {
+        const LocusLine &l = bed[i];
+        if (l.key.tid == bound.key.tid && l.repeat == bound.repeat && std::max(l.left, bound.left) <= std::min(l.right, bound.right)) {  // cluster.nim:96-100
+          bound.name = l.name;
+          bound.left = l.left;
+          bound.right = l.right;
+          bed[i] = bed.back();
+          bed.pop_back();
+          break;
+        }
+      }
+    loci.insert(loci.end(), bed.begin(), bed.end());
+  }
+  // assign_reads_locus (callclusters.nim:14-50) on the host, in list order: a locus takes the reads of its (tid, repeat) bucket with
+  // left_most - 1 <= position <= right_most; the first read after that window is dropped from the bucket as well (the reference's
+  // `ri + 1`).  The genotyper needs the reads themselves, so `call` does this here rather than through strgpu_cluster_loci.
+  loci_reads.assign(loci.size(), {});
+  if (!loci.empty()) {
+    std::map<std::pair<int32_t, std::array<char, 6>>, std::vector<uint32_t>> buckets;
+    for (uint32_t i = 0; i < bf.reads.size(); i++) buckets[{bf.reads[i].tid, bf.reads[i].repeat}].push_back(i);
+    for (auto &kv : buckets)
+      std::stable_sort(kv.second.begin(), kv.second.end(), [&](uint32_t x, uint32_t y) { return bf.reads[x].position < bf.reads[y].position; });
+    for (size_t li = 0; li < loci.size(); li++) {
+      LocusLine &L = loci[li];
+      std::array<char, 6> ru{{0, 0, 0, 0, 0, 0}};
+      std::memcpy(ru.data(), L.repeat.data(), std::min<size_t>(6, L.repeat.size()));
+      L.key.n_left = L.key.n_right = L.key.n_total = 0;
+      auto it = buckets.find({L.key.tid, ru});
+      if (it == buckets.end() || it->second.empty()) continue;
+      std::vector<uint32_t> &trs = it->second;
+      const uint32_t lm = L.key.left_most == 0 ? 0u : L.key.left_most - 1u;
+      const size_t lo = (size_t)(std::lower_bound(trs.begin(), trs.end(), lm, [&](uint32_t x, uint32_t v) { return bf.reads[x].position < v; }) - trs.begin());
+      const size_t hi = (size_t)(std::upper_bound(trs.begin(), trs.end(), L.key.right_most, [&](uint32_t v, uint32_t x) { return v < bf.reads[x].position; }) - trs.begin());
+      for (size_t j = lo; j < hi; j++) {
+        const Tread &r = bf.reads[trs[j]];
+        loci_reads[li].push_back(&r);
+        L.key.n_total++;
+        if (r.split == kRight) L.key.n_right++;
+        else if (r.split == kLeft) L.key.n_left++;
+      }
+      std::vector<uint32_t> keep(trs.begin(), trs.begin() + (long)lo);
+      if (hi + 1 < trs.size()) keep.insert(keep.end(), trs.begin() + (long)hi + 1, trs.end());   // `if ri < trs.high: add trs[ri + 1 ..]`
+      trs.swap(keep);
+    }
+    std::vector<uint32_t> left_over;
+    for (auto &kv : buckets) left_over.insert(left_over.end(), kv.second.begin(), kv.second.end());
+    std::sort(left_over.begin(), left_over.end());    // back to .bin order
+    remaining.reserve(left_over.size());
+    for (uint32_t i : left_over) remaining.push_back(bf.reads[i]);
+  }
+}
+
 // call.nim:223-281 downstream of the cluster kernels: spanning evidence, genotypes, the three output files.  `bounds` is what
 // strgpu_cluster returned for bf.reads (ascending tid, repeat, position; unplaced buckets as tid == -1 records).
-void write_call_outputs(const std::vector<strgpu_bounds> &bounds, const BinFile &bf, const std::vector<std::pair<std::string, uint32_t>> &targets,
+// `loci` (may be null): the -b / -l Bounds with the reads assign_reads_locus gave them (call.nim:189-218); they are genotyped and
+// written first.  `reads` is the record array the cluster records index (all of the .bin, or what the loci left over).
+void write_call_outputs(const std::vector<strgpu_bounds> &bounds, const std::vector<Tread> &reads, const std::vector<std::pair<std::string, uint32_t>> &targets,
                         const std::array<uint32_t, 4096> &frag, const strgpu_cluster_params &p, uint8_t min_mapq, const std::string &bam,
-                        std::ostream &bo, std::ostream &un, std::ostream &gt, bool verbose) {
+                        std::ostream &bo, std::ostream &un, std::ostream &gt, bool verbose,
+                        const std::vector<LocusLine> *loci = nullptr, const std::vector<std::vector<const Tread *>> *loci_reads = nullptr) {
   bo << kBoundsHeader << "\tdepth\n";   // call.nim:145
 
   // The cluster's reads (call.nim:225 `c.reads`) = n_reads records from first_read of the (tid, repeat, position)-sorted order.
-  std::vector<uint32_t> order(bf.reads.size());
+  std::vector<uint32_t> order(reads.size());
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-    const Tread &A = bf.reads[x], &B = bf.reads[y];
+    const Tread &A = reads[x], &B = reads[y];
     if (A.tid != B.tid) return A.tid < B.tid;
     const int c = std::memcmp(A.repeat.data(), B.repeat.data(), 6);
     if (c != 0) return c < 0;
@@ -324,8 +390,22 @@ void write_call_outputs(const std::vector<strgpu_bounds> &bounds, const BinFile 
   });
   // spanning evidence for every discovered locus in one pass over the BAM (collect.nim:130-183)
   std::vector<GLocus> gl;
-  std::vector<size_t> gl_bound;
+  std::vector<size_t> gl_bound;      // index into `bounds`, or into `loci` when gl_locus is set
+  std::vector<char> gl_locus;
   std::map<std::string, uint32_t> unplaced_counts;
+  if (loci)
+    for (size_t i = 0; i < loci->size(); i++) {
+      const LocusLine &ll = (*loci)[i];
+      if (ll.right - ll.left > 1000u) {   // call.nim:192-194
+        std::fprintf(stderr, "large bounds:%s skipping\n", locus_line(ll, targets).c_str());
+        continue;
+      }
+      GLocus L;
+      L.tid = ll.key.tid; L.left = ll.left; L.right = ll.right; L.repeat = ll.repeat; L.n_left = ll.key.n_left; L.n_right = ll.key.n_right;
+      gl.push_back(std::move(L));
+      gl_bound.push_back(i);
+      gl_locus.push_back(1);
+    }
   for (size_t i = 0; i < bounds.size(); i++) {
     const strgpu_bounds &b = bounds[i];
     char unit[7] = {0};
@@ -339,6 +419,7 @@ void write_call_outputs(const std::vector<strgpu_bounds> &bounds, const BinFile 
     L.tid = b.tid; L.left = b.left; L.right = b.right; L.repeat = unit; L.n_left = b.n_left; L.n_right = b.n_right;
     gl.push_back(std::move(L));
     gl_bound.push_back(i);
+    gl_locus.push_back(0);
   }
   collect_evidence(bam, gl, (int)p.window, frag, min_mapq);
   GenotypeOpts go;
@@ -347,19 +428,25 @@ void write_call_outputs(const std::vector<strgpu_bounds> &bounds, const BinFile 
   std::vector<std::string> canon;
   for (size_t k = 0; k < gl.size(); k++) {
     const GLocus &L = gl[k];
-    const strgpu_bounds &b = bounds[gl_bound[k]];
-    if (L.support.size() > 5000 || L.median_depth_v == -1) continue;   // call.nim:236-241
+    if (L.support.size() > 5000 || L.median_depth_v == -1) continue;   // call.nim:196-202,236-241
+    const bool is_locus = gl_locus[k] != 0;
     std::vector<const Tread *> tandems;
-    tandems.reserve(b.n_reads);
-    for (uint32_t j = 0; j < b.n_reads; j++) tandems.push_back(&bf.reads[order[(size_t)b.first_read + j]]);
-    Call c = genotype(L, targets[(size_t)b.tid].first, tandems, go);
+    if (is_locus) {
+      tandems = (*loci_reads)[gl_bound[k]];
+    } else {
+      const strgpu_bounds &b = bounds[gl_bound[k]];
+      tandems.reserve(b.n_reads);
+      for (uint32_t j = 0; j < b.n_reads; j++) tandems.push_back(&reads[order[(size_t)b.first_read + j]]);
+    }
+    Call c = genotype(L, targets[(size_t)L.tid].first, tandems, go);
     c.expected_spanning_fragments = L.expected;
     std::array<char, 6> ru{{0, 0, 0, 0, 0, 0}};
-    std::memcpy(ru.data(), b.repeat, 6);
+    std::memcpy(ru.data(), L.repeat.data(), std::min<size_t>(6, L.repeat.size()));
     const std::array<char, 6> cr = canonical_repeat(ru);
     canon.emplace_back(cr.data(), (size_t)unit_length(cr));
     calls.push_back(std::move(c));
-    bo << bounds_line(b, targets) << "\t" << L.median_depth_v << "\n";   // call.nim:255
+    if (is_locus) bo << locus_line((*loci)[gl_bound[k]], targets) << "\t" << L.median_depth_v << "\n";   // call.nim:214
+    else bo << bounds_line(bounds[gl_bound[k]], targets) << "\t" << L.median_depth_v << "\n";                   // call.nim:255
   }
   add_percentile(calls);
   // call.nim:266-278: per canonical repeat unit; a lone "large" genotype takes the unit's unplaced-read count.  (The reference
@@ -414,33 +501,23 @@ int call_main(int argc, char **argv) {
   p.min_clip_total = (uint16_t)std::stoi(a.get("--min-clip-total", "0"));
   p.max_clip_dist = (uint16_t)(0.5 * (double)frag_median(frag, 0.5));  // call.nim:232
   p.merge_mode = 0;
-  // call.nim:189-218: bounds (-b) then loci (-l) take their reads first; genotyping them needs collect.nim (not built)
   std::vector<LocusLine> loci;
-  if (a.has("--bounds")) loci = parse_bounds(a.get("--bounds", ""), targets);
-  if (a.has("--loci")) {
-    auto more = parse_bed(a.get("--loci", ""), targets, p.window, INT32_MIN);
-    loci.insert(loci.end(), more.begin(), more.end());
+  std::vector<std::vector<const Tread *>> loci_reads;
+  std::vector<Tread> remaining;
+  prepare_call_loci(bf, targets, p.window, a.get("--bounds", ""), a.get("--loci", ""), loci, loci_reads, remaining);
+  const std::vector<Tread> *cluster_reads = &bf.reads;
+  if (!loci.empty()) {
+    cluster_reads = &remaining;
+    treads.clear();
+    for (const Tread &t : remaining) treads.push_back(to_pod(t, 0));
   }
-  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose, loci.empty() ? nullptr : &loci);
+  std::vector<strgpu_bounds> bounds = run_cluster(treads, p, std::stoi(a.get("--device", "0")), verbose, nullptr);
 
   std::ofstream bo(prefix + "-bounds.txt"), un(prefix + "-unplaced.txt"), gt(prefix + "-genotype.txt");
   if (!bo || !un || !gt) throw std::runtime_error("couldn't open output file");
   gt << kGtHeader << "\n";
-  if (!loci.empty()) {
-    // -l / -b: the listed loci take their reads first and are reported (call.nim:189-218); genotyping THEM is not built yet, so
-    // this mode keeps the round-1 output: bounds lines without the depth column, no genotype lines
-    std::fprintf(stderr, "[strling] note: genotypes are not produced together with -l / -b in this build\n");
-    bo << kBoundsHeader << "\n";
-    for (const auto &l : loci) bo << locus_line(l, targets) << "\n";
-    for (const auto &b : bounds) {
-      if (b.tid >= 0) { bo << bounds_line(b, targets) << "\n"; continue; }
-      char unit[7] = {0};
-      std::memcpy(unit, b.repeat, 6);
-      un << unit << "\t" << b.n_reads << "\n";  // call.nim:280-281
-    }
-    return 0;
-  }
-  write_call_outputs(bounds, bf, targets, frag, p, (uint8_t)std::stoi(a.get("--min-mapq", "40")), a.pos[0], bo, un, gt, verbose);
+  write_call_outputs(bounds, *cluster_reads, targets, frag, p, (uint8_t)std::stoi(a.get("--min-mapq", "40")), a.pos[0], bo, un, gt, verbose,
+                     loci.empty() ? nullptr : &loci, loci.empty() ? nullptr : &loci_reads);
   return 0;
 }
 
@@ -448,7 +525,7 @@ int call_main(int argc, char **argv) {
 // cluster records read from a file (tid left right repeat left_most right_most center_mass n_left n_right n_total first_read
 // n_reads per line) instead of coming from the GPU, so that it can be compared with the oracle on a machine without one.
 int debug_genotype(int argc, char **argv) {
-  if (argc != 7) { std::fprintf(stderr, "usage: debug genotype bam bin clusters.tsv prefix window min_support min_mapq\n"); return 1; }
+  if (argc != 7 && argc != 9) { std::fprintf(stderr, "usage: debug genotype bam bin clusters.tsv prefix window min_support min_mapq [bounds|- bed|-]\n"); return 1; }
   const std::array<uint32_t, 4096> frag = fragment_length_distribution(argv[0], 0);
   BinFile bf = read_bin(argv[1]);
   auto targets = targets_from_header(bf.header);
@@ -475,7 +552,13 @@ int debug_genotype(int argc, char **argv) {
   std::ofstream bo(prefix + "-bounds.txt"), un(prefix + "-unplaced.txt"), gt(prefix + "-genotype.txt");
   if (!bo || !un || !gt) throw std::runtime_error("couldn't open output file");
   gt << kGtHeader << "\n";
-  write_call_outputs(bounds, bf, targets, frag, p, (uint8_t)std::stoi(argv[6]), argv[0], bo, un, gt, true);
+  std::vector<LocusLine> loci;
+  std::vector<std::vector<const Tread *>> loci_reads;
+  std::vector<Tread> remaining;
+  if (argc == 9)
+    prepare_call_loci(bf, targets, p.window, std::string(argv[7]) == "-" ? "" : argv[7], std::string(argv[8]) == "-" ? "" : argv[8], loci, loci_reads, remaining);
+  write_call_outputs(bounds, loci.empty() ? bf.reads : remaining, targets, frag, p, (uint8_t)std::stoi(argv[6]), argv[0], bo, un, gt, true,
+                     loci.empty() ? nullptr : &loci, loci.empty() ? nullptr : &loci_reads);
   return 0;
 }
 

@@ -115,7 +115,7 @@ def test_host_genotyping_matches_oracle(cli, tmp_path, seed, min_support, min_ma
     prefix = str(tmp_path / "out")
     r = subprocess.run([cli, "debug", "genotype", bam, binp, cl, prefix, str(window), str(min_support), str(min_mapq)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    exp_gt, exp_bounds, exp_unplaced = co.call(recs, data, min_support=min_support, min_mapq=min_mapq)
+    exp_gt, exp_bounds, exp_unplaced, _ = co.call(recs, data, min_support=min_support, min_mapq=min_mapq)
     got_gt = open(prefix + "-genotype.txt").read().splitlines()
     got_bounds = open(prefix + "-bounds.txt").read().splitlines()
     assert got_gt[0] == co.GT_HEADER and got_bounds[0] == eo.BOUNDS_HEADER + "\tdepth"
@@ -126,3 +126,64 @@ def test_host_genotyping_matches_oracle(cli, tmp_path, seed, min_support, min_ma
     assert any(int(c[7]) > 0 for c in cols) and any(int(c[8]) > 0 for c in cols) and any(c[4] not in ("0.00", "nan") for c in cols)
     got_un = dict(l.split("\t") for l in open(prefix + "-unplaced.txt").read().splitlines())
     assert {k.encode(): int(v) for k, v in got_un.items()} == exp_unplaced
+
+
+def test_host_genotyping_with_bounds_and_loci_files(cli, tmp_path):
+    # call.nim:158-218: -b bounds and -l loci are merged (a locus overwrites the bound it overlaps), take their reads first
+    # (assign_reads_locus incl. its dropped read), are genotyped and reported first; the rest is clustered as usual
+    targets = [("chr1", 300_000), ("chr2", 200_000)]
+    loci = [(0, 50_000, 50_060, "CAG"), (0, 120_000, 120_040, "AAAG"), (1, 80_000, 80_090, "AC"), (1, 150_000, 150_030, "CCG")]
+    recs = bamio.simulate_alignments(31, 9000, targets, loci, str_pair_frac=0.25, unmapped_pairs=40)
+    recs = [a for a in recs if a.tid >= 0] + _spanning_extras(targets, loci, 31) + [a for a in recs if a.tid < 0]
+    recs = sorted([a for a in recs if a.tid >= 0], key=lambda a: (a.tid, a.pos)) + [a for a in recs if a.tid < 0]
+    hdr = bamio.sam_header(targets)
+    bam, binp, cl = str(tmp_path / "a.bam"), str(tmp_path / "a.bin"), str(tmp_path / "cl.tsv")
+    bamio.write_bam(bam, hdr, targets, recs)
+    data, _, _ = eo.extract(recs, targets, hdr)
+    open(binp, "wb").write(data)
+    frag = eo.fragment_length_distribution(recs)
+    window = orc.median(frag, 0.99)
+    # a bounds file: two discovered bounds of a first pass (depth column stripped), one of them overlapped by a bed locus,
+    # plus a bound wider than 1000 bp (takes reads but is not genotyped)
+    _, first_bounds, _, _ = co.call(recs, data, min_support=3)
+    cag = [l for l in first_bounds if l.split("\t")[3] == "CAG"][:1]
+    other = [l for l in first_bounds if l.split("\t")[3] == "CA"][:1]
+    bounds_lines = ["\t".join(l.split("\t")[:11]) for l in cag + other]
+    bounds_lines.append("chr2\t149000\t150900\tCCG\twide\t148500\t151400\t150000\t0\t0\t0")
+    bed_lines = ["chr1\t50000\t50060\tCAG\tHTT_like", "chr1 120000 120040 AAAG", "chr2\t10\t20\tGGGGGC\tempty_bucket"]
+    bpath, lpath = str(tmp_path / "in-bounds.txt"), str(tmp_path / "loci.bed")
+    open(bpath, "w").write("#header\n" + "\n".join(bounds_lines) + "\n")
+    open(lpath, "w").write("\n".join(bed_lines) + "\n")
+    exp_gt, exp_bounds, exp_unplaced, (sub, b) = co.call(recs, data, min_support=3, bounds_lines=bounds_lines, bed_lines=bed_lines)
+    with open(cl, "w") as fh:
+        for unit, cnt in sorted(exp_unplaced.items()):
+            fh.write(f"-1 0 0 {unit.decode()} 0 0 0 0 0 0 0 {cnt}\n")
+        for x in b:
+            rep = bytes(x["repeat"]).rstrip(b"\0").decode()
+            fh.write(f"{x['tid']} {x['left']} {x['right']} {rep} {x['left_most']} {x['right_most']} {x['center_mass']} {x['n_left']} "
+                     f"{x['n_right']} {x['n_total']} {x['first_read']} {x['n_reads']}\n")
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([cli, "debug", "genotype", bam, binp, cl, prefix, str(window), "3", "40", bpath, lpath], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got_gt = open(prefix + "-genotype.txt").read().splitlines()
+    got_bounds = open(prefix + "-bounds.txt").read().splitlines()
+    assert sorted(got_gt[1:]) == sorted(exp_gt) and got_bounds[1:] == exp_bounds
+    # the merged locus carries the bed name and interval, the wide bound is not reported, the listed loci come first
+    assert got_bounds[1].split("\t")[:5] == ["chr1", "50000", "50060", "CAG", "HTT_like"]
+    assert not any("wide" in l for l in got_bounds) and "large bounds" in r.stderr
+    assert int(got_bounds[1].split("\t")[10]) > 20 and any("empty_bucket" in l for l in got_bounds)
+    # the oracle's own device-style assignment (orc.cluster_all_loci) agrees on the per-locus read counts
+    u = eo.unpack_bin(data)
+    lb = co.merge_loci_into_bounds(co.parse_bounds_lines(bounds_lines, targets), co.parse_bed_lines(bed_lines, targets, window))
+    arr = np.zeros(len(lb), dtype=orc.LOCUS_DTYPE)
+    for i, x in enumerate(lb):
+        arr[i]["tid"], arr[i]["left_most"], arr[i]["right_most"], arr[i]["repeat"] = x["tid"], x["left_most"], x["right_most"], x["repeat"].encode()
+    med = orc.median(frag, 0.5)
+    arr2, b2, _ = orc.cluster_all_loci(u["treads"], arr, window, 3, 0, 0, int(0.5 * float(med)) & 0xFFFF, merge_mode=False)
+    buckets = {}
+    for i in co.sorted_tread_order(u["treads"]):
+        buckets.setdefault((int(u["treads"]["tid"][i]), bytes(u["treads"]["repeat"][i]).rstrip(b"\0")), []).append(int(i))
+    for i, x in enumerate(lb):
+        co.assign_reads_locus(x, buckets, u["treads"])
+        assert (x["n_left"], x["n_right"], x["n_total"]) == (int(arr2[i]["n_left"]), int(arr2[i]["n_right"]), int(arr2[i]["n_total"]))
+    assert len(b2) == len(b)

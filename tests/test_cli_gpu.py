@@ -101,7 +101,7 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
     # -> -bounds.txt (with the depth column), -unplaced.txt, -genotype.txt
     prefix = str(tmp_path / "call")
     run(cli, "call", "-m", "3", "-o", prefix, first_bam, bins[0])
-    exp_gt, exp_lines, exp_unplaced = co.call(first_recs, datas[0], min_support=3)
+    exp_gt, exp_lines, exp_unplaced, _ = co.call(first_recs, datas[0], min_support=3)
     got = open(prefix + "-bounds.txt").read().splitlines()
     assert got[0] == eo.BOUNDS_HEADER + "\tdepth"
     assert len(exp_lines) > 10 and sorted(got[1:]) == sorted(exp_lines) and got[1:] == exp_lines
@@ -109,6 +109,20 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
     assert {k.encode(): int(v) for k, v in got_un.items()} == exp_unplaced and len(exp_unplaced) > 0
     got_gt = open(prefix + "-genotype.txt").read().splitlines()
     assert got_gt[0] == co.GT_HEADER and len(exp_gt) == len(exp_lines) and sorted(got_gt[1:]) == sorted(exp_gt)
+    # call -b -l: listed bounds / loci are merged, take their reads first, are genotyped and reported first (call.nim:158-218)
+    bounds_in = ["\t".join(l.split("\t")[:11]) for l in exp_lines[:3]]
+    t0, s0, e0, u0 = loci[0]
+    bed_in = [f"{targets[t0][0]}\t{s0}\t{e0}\t{u0}\tfirst_locus", f"{targets[loci[1][0]][0]} {loci[1][1]} {loci[1][2]} {loci[1][3]}"]
+    bpath, lpath = str(tmp_path / "in-bounds.txt"), str(tmp_path / "in-loci.bed")
+    open(bpath, "w").write(eo.BOUNDS_HEADER + "\n" + "\n".join(bounds_in) + "\n")
+    open(lpath, "w").write("\n".join(bed_in) + "\n")
+    prefix = str(tmp_path / "call_loci")
+    run(cli, "call", "-m", "3", "-b", bpath, "-l", lpath, "-o", prefix, first_bam, bins[0])
+    exp_gt2, exp_lines2, exp_unplaced2, _ = co.call(first_recs, datas[0], min_support=3, bounds_lines=bounds_in, bed_lines=bed_in)
+    got = open(prefix + "-bounds.txt").read().splitlines()
+    assert got[0] == eo.BOUNDS_HEADER + "\tdepth" and got[1:] == exp_lines2 and len(exp_lines2) > 10
+    got_gt = open(prefix + "-genotype.txt").read().splitlines()
+    assert sorted(got_gt[1:]) == sorted(exp_gt2) and len(exp_gt2) == len(exp_lines2)
     # merge: joint clustering with per-sample support (merge.nim:172-187)
     for ms, extra in ((5, []), (2, ["-c", "0", "-t", "3"]), (2, ["-c", "1", "-t", "1"]), (4, ["-w", "300"])):
         prefix = str(tmp_path / f"merge{ms}{''.join(extra)}")
