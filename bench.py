@@ -286,13 +286,28 @@ def run_ours(args):
     n_extra = n_seg - shard_reads           # soft-clip segments: the only ones that carry descriptors
     extra_max = int(segs["len"][shard_reads:].max()) if n_extra else 0
 
+    # --streams 2: library calls alternate between two contexts on two streams, so that call i's scan kernel (ALU + shared-memory
+    # bound, low issue rate) runs next to call i + 1's pre-filter (ALU + popcount bound) on the same SMs (STRGPU_SHARE_SM geometry)
+    lanes = [(g, torch.cuda.current_stream())]
+    if args.streams > 1:
+        for _ in range(args.streams - 1):
+            gx = sb.StrGpu(local)
+            gx.set_proportions(P_CLASSES)
+            lanes.append((gx, torch.cuda.Stream(device=dev)))
+
     def step_device():
         # the same entry-point family as the end-to-end leg (uniform reads without descriptors + clip descriptors),
         # on device-resident buffers
+        main = torch.cuda.current_stream()
+        for gx, st in lanes[1:]:
+            st.wait_stream(main)
         for b in range(n_sub):
-            g.scan_reads_device(d_seq.data_ptr() + b * seq_bytes, shard_reads, READ_LEN, stride, 0, None,
-                                d_segs.data_ptr() + (b * n_seg + shard_reads) * 8, n_extra, extra_max,
-                                d_out.data_ptr() + b * n_seg * 8, stream)
+            gx, st = lanes[b % len(lanes)]
+            gx.scan_reads_device(d_seq.data_ptr() + b * seq_bytes, shard_reads, READ_LEN, stride, 0, None,
+                                 d_segs.data_ptr() + (b * n_seg + shard_reads) * 8, n_extra, extra_max,
+                                 d_out.data_ptr() + b * n_seg * 8, st.cuda_stream)
+        for gx, st in lanes[1:]:
+            main.wait_stream(st)
         cluster_device_leg()
 
     # end-to-end leg: the descriptor-free uniform-read call (reads packed on a 152-base stride = 38 B/read; only the soft-clip
@@ -335,7 +350,7 @@ def run_ours(args):
         sampler = ClockSampler(phys)
         if rank == 0:
             sampler.start()
-        launches0 = g.launch_count
+        launches0 = sum(gx.launch_count for gx, _ in lanes)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
@@ -345,7 +360,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         sec = e0.elapsed_time(e1) / 1e3 if device_events else wall
-        launches = g.launch_count - launches0
+        launches = sum(gx.launch_count for gx, _ in lanes) - launches0
         clocks = sampler.stop() if rank == 0 else None
         if world > 1:
             t = torch.tensor([sec], dtype=torch.float64, device=dev)
@@ -434,6 +449,7 @@ def run_ours(args):
                    "reads_per_gpu": reads_per_gpu, "segments_per_gpu": n_seg * n_sub, "read_len": READ_LEN,
                    "sub_batches_per_step": n_sub, "reads_per_launch": shard_reads,
                    "l2": f"each launch streams {(seq_bytes + 16 * n_seg) / 1e6:.0f} MB of its own HBM region (> 126 MB L2); {n_sub} distinct regions per step",
+                   "streams": f"{len(lanes)} library contexts on {len(lanes)} CUDA streams, calls alternate (call i's ladder kernel overlaps call i+1's pre-filter)",
                    "parallelism": f"read batches sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(n_sub * (seq_bytes_e + len(extra_np) * 8) + n_treads * 24),
                 "api": "strgpu_scan_reads_submit/wait (3 slots in flight) + strgpu_cluster, pinned host buffers",
@@ -486,6 +502,7 @@ def main():
     ap.add_argument("--reads-per-gpu", type=int, default=600_000_000)
     ap.add_argument("--shard-reads", type=int, default=12_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2)
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

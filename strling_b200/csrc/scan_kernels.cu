@@ -301,6 +301,7 @@ constexpr int kQ3Off = 0, kQ4Off = kQueueCap * 3, kQ5Off = kQ4Off + kQueueCap * 
 constexpr int kQueueWords = kQWOff + 32;
 constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + kQueueWords;
 constexpr int kLaneSmemBytes = kLaneWarps * kWarpSmemWords * 4 + kLutTotal * 2 + 16;
+constexpr int lane_smem_bytes(int warps) { return warps * kWarpSmemWords * 4 + kLutTotal * 2 + 16; }
 static_assert(sizeof(WarpScratch<512>) <= (size_t)kTabWords * 32 * 4, "warp scratch must fit in the warp's counter region");
 static_assert(kCls5 / 4 <= kTabWords, "k = 5 counters must fit");
 
@@ -1122,8 +1123,8 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
   }
 }
 
-template <int FILTER>
-__global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
+template <int FILTER, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == kLaneWarps ? 1 : 2) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                     const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                     const UniformReads u,
                                                                     const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
@@ -1135,8 +1136,8 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_long = list ? list[0] : n_seg, n_short = list ? list[1] : 0u;
   const uint32_t groups_long = (n_long + 31) / 32;
-  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kLaneWarps * kWarpSmemWords);
-  for (int i = tid; i < kLutTotal; i += kLaneThreads) lut[i] = luts[i];
+  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + WARPS * kWarpSmemWords);
+  for (int i = tid; i < kLutTotal; i += WARPS * 32) lut[i] = luts[i];
   __syncthreads();
   uint32_t *warp_base = smem + warp * kWarpSmemWords;
   uint32_t *tab = warp_base + lane;                      // [class][lane] counters; warp scratch for the warp path
@@ -1147,11 +1148,11 @@ __global__ void __launch_bounds__(kLaneThreads, 1) repeat_scan_lane(const uint32
   const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
   const uint16_t *tmin = thr + kThrMinOff;
   const uint32_t n_groups = groups_long + (n_short + 31) / 32;
-  const uint32_t warps_total = gridDim.x * kLaneWarps;
+  const uint32_t warps_total = gridDim.x * WARPS;
   // groups are handed out dynamically when they come from the survivor list (their cost varies a lot: a warp takes the
   // next group whenever its queues run low), statically otherwise
   uint32_t *next_group = list ? list + 2 : nullptr;
-  uint32_t grp = blockIdx.x * kLaneWarps + warp;
+  uint32_t grp = blockIdx.x * WARPS + warp;
   if (next_group) {
     if (lane == 0) grp = atomicAdd(next_group, 1u);
     grp = __shfl_sync(kFull, grp, 0);
@@ -1397,16 +1398,20 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
   if (max_len <= (uint32_t)kShortMaxLen && variant != 1) {
     // 0: repeat_prefilter + repeat_scan_lane over its survivor list (5..7: the same with 0 / 12 / 16 carry-save streams);
     // 2 / 4: one fused kernel (plain / carry-save popcounts); 3: no pre-filter (A/B runs)
-    auto kernel = variant == 2 ? repeat_scan_lane<0> : (variant == 4 ? repeat_scan_lane<1> : repeat_scan_lane<-1>);
-    static bool configured[8] = {false, false, false, false, false, false, false, false};
+    const bool split = variant == 0 || variant >= 5;
+    // (A geometry that lets batch i's scan kernel share the SMs with batch i + 1's pre-filter -- 12-warp scan CTAs next to 2 pre-filter
+    // CTAs -- was measured and is slower than letting whole kernels of two streams interleave: 2.22e10 vs 2.54e10 reads/s.)
+    auto kernel = variant == 2 ? repeat_scan_lane<0, kLaneWarps> : (variant == 4 ? repeat_scan_lane<1, kLaneWarps> : repeat_scan_lane<-1, kLaneWarps>);
+    const int lane_warps = kLaneWarps;
+    const int lane_smem = lane_smem_bytes(lane_warps);
+    static bool configured[8] = {false};
     if (!configured[variant]) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmemBytes);
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem);
       if (e != cudaSuccess) return e;
       e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       if (e != cudaSuccess) return e;
       configured[variant] = true;
     }
-    const bool split = variant == 0 || variant >= 5;
     static const bool no_tma = getenv("STRGPU_NO_TMA") != nullptr;   // A/B: per-lane loads for uniform reads too
     if (split) {
       cudaError_t e = cudaMemsetAsync(d_list, 0, 4 * sizeof(uint32_t), stream);
@@ -1427,11 +1432,11 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;
     }
-    const uint32_t tiles = (n_seg + kLaneThreads - 1) / kLaneThreads;
-    uint32_t grid = (uint32_t)sm_count;  // one persistent CTA of 20 warps per SM
+    const uint32_t tiles = (n_seg + lane_warps * 32 - 1) / (lane_warps * 32);
+    uint32_t grid = (uint32_t)sm_count;  // one persistent CTA per SM
     if (grid > tiles) grid = tiles;
-    kernel<<<grid, kLaneThreads, kLaneSmemBytes, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out, d_status,
-                                                           split ? d_list : nullptr);
+    kernel<<<grid, lane_warps * 32, lane_smem, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out, d_status,
+                                                          split ? d_list : nullptr);
   } else if (max_len <= (uint32_t)kShortMaxLen) {
     uint32_t grid = (uint32_t)sm_count * 8u;  // 8 resident CTAs of 256 threads per SM
     if (grid > blocks_needed) grid = blocks_needed;
