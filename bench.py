@@ -453,7 +453,9 @@ def run_ours(args):
                    "parallelism": f"read batches sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(n_sub * (seq_bytes_e + len(extra_np) * 8) + n_treads * 24),
                 "api": "strgpu_scan_reads_submit/wait (3 slots in flight) + strgpu_cluster, pinned host buffers",
-                "d2h_bytes_per_step": int(n_sub * n_seg * 8 + cl_stats.get("bounds_local", 0) * 48), "ms_per_step": 1e3 * sec_e2e / args.steps},
+                "d2h_bytes_per_step": int(n_sub * n_seg * 8 + cl_stats.get("bounds_local", 0) * 48), "ms_per_step": 1e3 * sec_e2e / args.steps,
+                "h2d_gb_per_s_per_gpu": (n_sub * (seq_bytes_e + len(extra_np) * 8) + n_treads * 24) / (sec_e2e / args.steps) / 1e9,
+                "bound": "PCIe host-to-device copy of the 2-bit reads (38 B per 150-bp read); kernels and the device-to-host copy of the results overlap it"},
         "cluster": {"treads_per_gpu": n_treads, "ms_per_step": cluster_ms, "treads_per_s": n_treads / (cluster_ms / 1e3),
                     "bounds_per_gpu": cl_stats.get("bounds_local"), "bounds_gathered": cl_stats.get("bounds_all"),
                     "allgather_ms": gather_ms, "exchange_ms": exchange_ms, "treads_owned": cl_stats.get("treads_owned"),

@@ -645,12 +645,14 @@ __device__ __forceinline__ void lane_count4(const uint32_t *rd, uint32_t *tab, c
 }
 
 // one rung of the ladder (utils.nim:246-265) given this k's count result.  Returns false on `break`.
+// wide: recount over ten words (any segment) instead of four (segments of <= 64 bases); callers make it uniform over the lanes
+// that recount together so that only one of the two instances runs
 __device__ __forceinline__ bool lane_decide(const uint32_t *rd, uint32_t *tab, int L, int K, int M, uint32_t leader, int thr_p,
-                                            int thr_giveup, ScanState &st) {
+                                            int thr_giveup, ScanState &st, bool wide) {
   int score = M * K;
   if (score <= st.best) return !(M < thr_giveup);
   const uint32_t magic = 65536u / (uint32_t)K + 1u;
-  const int c = L <= 64 ? lane_recount<4>(rd, tab, L, leader, K, magic) : lane_recount<10>(rd, tab, L, leader, K, magic);
+  const int c = wide ? lane_recount<10>(rd, tab, L, leader, K, magic) : lane_recount<4>(rd, tab, L, leader, K, magic);
   score = c * K;
   if (score < st.best) return true;
   st.best = score;
@@ -1252,7 +1254,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kLaneWarps ? 1 : 2) repea
         const uint32_t lead2 = M2 ? (uint32_t)lut[kRev234 + (best2 & 31u)] : 0xfu;
         const uint32_t lead3 = M3 ? (uint32_t)lut[kRev234 + kCls2 + (best3 & 31u)] : 0x3fu;
         extra = (uint32_t)M3 | (lead3 << 8) | (3u << 20);
-        bool go = lane_decide(rd, tab, L, 2, M2, lead2, tp[0], tg[L], st);
+        const bool wide = __any_sync(nb == 32 ? kFull : ((1u << nb) - 1u), L > 64);
+        bool go = lane_decide(rd, tab, L, 2, M2, lead2, tp[0], tg[L], st, wide);
         if (go) {
           if (3 * M3 > st.best) next_k = 3;                       // needs the k = 3 recount
           else go = !(M3 < (int)tg[kThrLen + L]);
@@ -1283,7 +1286,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kLaneWarps ? 1 : 2) repea
         lane_stage(seq, sg, rd);
         const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
         const uint32_t magic = 65536u / (uint32_t)k + 1u;
-        const int c = L <= 64 ? lane_recount<4>(rd, tab, L, leader, k, magic) : lane_recount<10>(rd, tab, L, leader, k, magic);
+        const bool wide = __any_sync(nb == 32 ? kFull : ((1u << nb) - 1u), L > 64);
+        const int c = wide ? lane_recount<10>(rd, tab, L, leader, k, magic) : lane_recount<4>(rd, tab, L, leader, k, magic);
         const int score = c * k;
         if (score >= st.best) {
           st.best = score;
@@ -1328,7 +1332,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == kLaneWarps ? 1 : 2) repea
         what = 2;
         extra = (uint32_t)M | (leader << 8) | ((uint32_t)stage << 20);
       } else {
-        lane_decide(rd, tab, L, stage, M, leader, thr[(size_t)(pclass * 5 + stage - 2) * kThrLen + L], tg[(stage - 2) * kThrLen + L], st);
+        lane_decide(rd, tab, L, stage, M, leader, thr[(size_t)(pclass * 5 + stage - 2) * kThrLen + L], tg[(stage - 2) * kThrLen + L], st, L > 64);
         what = 1;
       }
       if (what == 0 || (what == 1 && stage == 6)) {
