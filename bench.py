@@ -427,7 +427,9 @@ def run_ours(args):
     achieved = ALGO_BYTES_PER_READ * shard_reads / launch_s / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        # ncu measured one library call of tj["reads_per_launch"] reads; DRAM traffic is linear in the reads of a call
+        traffic = float(tj["dram_bytes_per_launch"]) * shard_reads / float(tj["reads_per_launch"])
     except Exception:
         pass
 

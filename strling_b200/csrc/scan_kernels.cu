@@ -1408,13 +1408,16 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
     auto kernel = variant == 2 ? repeat_scan_lane<0, kLaneWarps> : (variant == 4 ? repeat_scan_lane<1, kLaneWarps> : repeat_scan_lane<-1, kLaneWarps>);
     const int lane_warps = kLaneWarps;
     const int lane_smem = lane_smem_bytes(lane_warps);
-    static bool configured[8] = {false};
-    if (!configured[variant]) {
+    // function attributes are per device: remember which (device, variant) pairs have been configured
+    static bool configured[64][8] = {{false}};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev][variant]) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem);
       if (e != cudaSuccess) return e;
       e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       if (e != cudaSuccess) return e;
-      configured[variant] = true;
+      configured[dev][variant] = true;
     }
     static const bool no_tma = getenv("STRGPU_NO_TMA") != nullptr;   // A/B: per-lane loads for uniform reads too
     if (split) {
