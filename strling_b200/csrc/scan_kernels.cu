@@ -1429,7 +1429,9 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
       if (pre_grid > pre_need) pre_grid = pre_need;
       static const int stages = getenv("STRGPU_STAGES") ? atoi(getenv("STRGPU_STAGES")) : 4;   // A/B: staging depth
       auto pre = variant == 7 ? (stages == 2 ? repeat_prefilter<16, 2> : repeat_prefilter<16, 4>)
-                              : (stages == 2 ? repeat_prefilter<kPreCsaDefault, 2> : repeat_prefilter<kPreCsaDefault, 4>);
+                 : variant == 6 ? repeat_prefilter<12, 4>
+                 : variant == 5 ? repeat_prefilter<4, 4>
+                                : (stages == 2 ? repeat_prefilter<kPreCsaDefault, 2> : repeat_prefilter<kPreCsaDefault, 4>);
       // uniform reads go through the TMA-staged part when their 32-read spans fit the staging buffers (all groups but the
       // batch's last one: the copy reads 16 bytes past its span)
       uint32_t n_tma = 0;
