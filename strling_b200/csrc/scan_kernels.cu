@@ -881,8 +881,10 @@ __device__ __forceinline__ void prefilter_masks(int L, uint32_t (&V)[5]) {
 }
 
 // returns the largest and the second largest of the 16 occurrence counts
+// `one` is the runtime constant 1 (a kernel argument): a * one + b compiles to IMAD on the FMA pipe, which is idle here, instead of
+// IADD3 on the ALU pipe, which is the bottleneck (every ALU instruction costs two issue cycles)
 template <int CSA>
-__device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const uint32_t (&V)[5], int &s1, int &s2) {
+__device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const uint32_t (&V)[5], int &s1, int &s2, int one) {
   uint32_t Dh[6], Dl[6];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
@@ -915,14 +917,14 @@ __device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const ui
         m[j] = b == 0 ? (e & ~Qh[j] & ~Ql[j]) : (b == 1 ? (e & ~Qh[j] & Ql[j]) : (b == 2 ? (e & Qh[j] & ~Ql[j]) : e));
       }
       if (a * 4 + b >= CSA) {
-        ca[b] = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]);
+        ca[b] = (((__popc(m[0]) * one + __popc(m[1])) * one + __popc(m[2])) * one + __popc(m[3])) * one + __popc(m[4]);
       } else {
-        const uint32_t s1 = m[0] ^ m[1] ^ m[2], c1 = (m[0] & m[1]) | (m[2] & (m[0] | m[1]));
-        const uint32_t s2 = s1 ^ m[3] ^ m[4], c2 = (s1 & m[3]) | (m[4] & (s1 | m[3]));
-        ca[b] = __popc(s2) + 2 * (__popc(c1) + __popc(c2));
+        const uint32_t x1 = m[0] ^ m[1] ^ m[2], c1 = (m[0] & m[1]) | (m[2] & (m[0] | m[1]));
+        const uint32_t x2 = x1 ^ m[3] ^ m[4], c2 = (x1 & m[3]) | (m[4] & (x1 | m[3]));
+        ca[b] = (__popc(c1) * one + __popc(c2)) * (one + one) + __popc(x2);
       }
     }
-    ca[3] -= ca[0] + ca[1] + ca[2];
+    ca[3] = ((ca[0] * one + ca[1]) * one + ca[2]) * (-one) + ca[3];
     // the two largest of the four, merged into the running pair
     const int m1 = max(ca[0], ca[1]), n1 = min(ca[0], ca[1]), m2 = max(ca[2], ca[3]), n2 = min(ca[2], ca[3]);
     const int t1 = max(m1, m2), t2 = max(min(m1, m2), max(n1, n2));
@@ -971,7 +973,7 @@ struct FilterCache {
 // ALL_WORDS: all eleven words may be read whatever L is (staging buffer; words past the segment only feed masked slots)
 template <int CSA, bool ALL_WORDS>
 __device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh, int L, int pclass, const uint16_t *__restrict__ tfilt,
-                                               FilterCache &fc) {
+                                               FilterCache &fc, int one) {
   const int n_words = (2 * L + 31) >> 5;
   uint32_t raw[11], w[10];
 #pragma unroll
@@ -990,7 +992,7 @@ __device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh,
     fc.pclass = pclass;
   }
   int s1, s2;
-  prefilter_top2<CSA>(w, fc.V, s1, s2);
+  prefilter_top2<CSA>(w, fc.V, s1, s2, one);
   return s1 >= fc.r[0] || s1 + s2 >= fc.r[1] || s1 + 2 * s2 >= fc.r[2] || s1 + 3 * s2 >= fc.r[3] || s1 + 4 * s2 >= fc.r[4];
 }
 
@@ -1032,7 +1034,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
                                                                    const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                    const UniformReads u, const uint16_t *__restrict__ thr,
                                                                    strgpu_repeat *__restrict__ out, uint32_t *__restrict__ list,
-                                                                   uint32_t n_tma_groups) {
+                                                                   uint32_t n_tma_groups, int one) {
   __shared__ __align__(128) unsigned char stage_buf[kPreWarps][STAGES][kStageBytes];
   __shared__ __align__(8) uint64_t stage_bar[kPreWarps][STAGES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1095,7 +1097,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
       bool keep = has_n;
       if (!has_n) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(stage_buf[warp][b] + (lane_byte & ~3u));
-        keep = prefilter_keep<CSA, true>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc);
+        keep = prefilter_keep<CSA, true>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc, one);
         if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
       }
       survivors_push(list, n_seg, keep, !has_n && L < kLongLen, s, lane);
@@ -1118,7 +1120,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
     bool keep = active && !lane_path;   // non-ACGT bases or > 160 bases: the scan kernel's warp path
     if (lane_path) {
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-      keep = prefilter_keep<CSA, false>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc);
+      keep = prefilter_keep<CSA, false>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc, one);
       if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;
     }
     survivors_push(list, n_seg, keep, lane_path && L < kLongLen, s, lane);
@@ -1437,7 +1439,7 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
       uint32_t n_tma = 0;
       if (u.n_reads >= 64u && u.read_len >= 1u && 8u * u.stride + 16u <= (uint32_t)kStageBytes && ((uintptr_t)d_seq_words & 15u) == 0 && !no_tma)
         n_tma = u.n_reads / 32u - 1u;
-      pre<<<pre_grid, kPreThreads, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_out, d_list, n_tma);
+      pre<<<pre_grid, kPreThreads, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_out, d_list, n_tma, 1);
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;
     }
