@@ -136,6 +136,13 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
         got = open(prefix + "-bounds.txt").read().splitlines()
         assert got[0] == eo.BOUNDS_HEADER and (len(exp_lines) > 5 or extra[:2] == ["-c", "1"])
         assert sorted(got[1:]) == sorted(exp_lines) and got[1:] == exp_lines
+    # the multi-GPU joint merge (strling_b200/joint.py; here one process / one GPU) writes the same file as `strling merge`
+    import sys
+    prefix = str(tmp_path / "joint")
+    r = subprocess.run([sys.executable, "-m", "strling_b200.joint", "-m", "5", "-o", prefix, *bins], capture_output=True, text=True,
+                       cwd=os.path.dirname(HERE))
+    assert r.returncode == 0, r.stderr
+    assert open(prefix + "-bounds.txt").read() == open(str(tmp_path / "merge5") + "-bounds.txt").read()
     # -l bed: listed loci take their reads before clustering and are reported first (merge.nim:154-168, callclusters.nim:14-50)
     bed = str(tmp_path / "loci.bed")
     bed_lines = [f"{targets[tid][0]}\t{s}\t{e}\t{u}\tL{i}" if i % 2 else f"{targets[tid][0]} {s} {e} {u}" for i, (tid, s, e, u) in enumerate(loci[:12])]

@@ -118,3 +118,54 @@ def test_sharded_clustering_equals_single_process_world2(tmp_path):
         assert len(got) == len(expect) and len(expect) > 20
         for f in ("tid", "left", "left_most", "right", "right_most", "center_mass", "n_left", "n_right", "n_total", "repeat", "n_reads"):
             assert np.array_equal(got[f], expect[f]), f
+
+
+# ---- config 5: joint merge of several samples' .bin files over ranks == `strling merge` semantics on one process
+def _joint_oracle_cluster_fn(t32, params):
+    from oracle import oracle as orc
+
+    treads = t32.numpy().view(np.uint8).reshape(-1).view(orc.TREAD_DTYPE) if t32.shape[0] else np.zeros(0, dtype=orc.TREAD_DTYPE)
+    b, _ = orc.cluster_all(treads, params["window"], params["min_support"], params["min_clip"], params["min_clip_total"],
+                           params["max_clip_dist"], merge_mode=True)
+    out = np.zeros(len(b), dtype=BOUNDS_DTYPE)
+    for f in ("tid", "left", "left_most", "right", "right_most", "center_mass", "n_left", "n_right", "n_total", "repeat", "n_reads"):
+        out[f] = b[f]
+    return torch.from_numpy(out.view(np.uint8).reshape(-1).copy()), len(out)
+
+
+def _joint_worker(rank, world, port, paths, out_dir, kw):
+    from strling_b200 import joint
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lines, counts = joint.joint_merge(paths, _joint_oracle_cluster_fn, torch.device("cpu"), **kw)
+    if rank == 0:
+        open(os.path.join(out_dir, "joint.txt"), "w").write("\n".join(lines))
+    else:
+        assert lines is None
+    dist.destroy_process_group()
+
+
+def test_joint_merge_world2_matches_single_process_merge(tmp_path):
+    from oracle import extract_oracle as eo
+    from strling_b200 import bamio, joint
+
+    targets = [("chr1", 400_000), ("chr2", 300_000)]
+    loci = [(0, 50_000, 50_060, "CAG"), (0, 220_000, 220_040, "AAAG"), (1, 80_000, 80_090, "AC"), (1, 150_000, 150_030, "CCG")]
+    hdr = bamio.sam_header(targets)
+    paths, datas = [], []
+    for s in range(5):
+        recs = bamio.simulate_alignments(70 + s, 2500, targets, loci, str_pair_frac=0.4, unmapped_pairs=20)
+        data, _, _ = eo.extract(recs, targets, hdr)
+        p = str(tmp_path / f"s{s}.bin")
+        open(p, "wb").write(data)
+        paths.append(p)
+        datas.append(data)
+    assert joint.files_of_rank(5, 0, 2) == [0, 1, 2] and joint.files_of_rank(5, 1, 2) == [3, 4]
+    for kw in (dict(min_support=3), dict(min_support=2, min_clip=1, min_clip_total=1), dict(min_support=4, window=300)):
+        port = _free_port()
+        mp.spawn(_joint_worker, args=(2, port, paths, str(tmp_path), kw), nprocs=2, join=True)
+        got = [l for l in open(tmp_path / "joint.txt").read().split("\n") if l]
+        exp, _ = eo.merge(datas, **kw)
+        assert got == exp and (len(exp) > 3 or "min_clip" in kw)
