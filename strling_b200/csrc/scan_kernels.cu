@@ -888,7 +888,7 @@ __device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const ui
   uint32_t Dh[6], Dl[6];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
-    Dh[j] = (w[j] & kOdd) | ((w[j + 5] >> 1) & kEven);
+    Dh[j] = (w[j] & kOdd) | (__umulhi(w[j + 5], 0x80000000u) & kEven);   // x >> 1 as a high multiply: FMA pipe, not ALU
     Dl[j] = ((w[j] << 1) & kOdd) | (w[j + 5] & kEven);
   }
   Dh[5] = w[5];        // only its top slot pair is used: base 0 of word 5 (the even bit feeds a slot that is never valid)
@@ -971,15 +971,21 @@ struct FilterCache {
   int r[5];   // (int(L * p / k) + 1) * (k - 1), k = 2..6
 };
 // ALL_WORDS: all eleven words may be read whatever L is (staging buffer; words past the segment only feed masked slots)
+// aligned (warp-uniform): every lane's segment starts on a word boundary (sh == 0), the re-alignment shifts are skipped
 template <int CSA, bool ALL_WORDS>
 __device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh, int L, int pclass, const uint16_t *__restrict__ tfilt,
-                                               FilterCache &fc, int one) {
+                                               FilterCache &fc, int one, bool aligned) {
   const int n_words = (2 * L + 31) >> 5;
   uint32_t raw[11], w[10];
 #pragma unroll
   for (int j = 0; j < 11; j++) raw[j] = (ALL_WORDS || j <= n_words) ? __byte_perm(src[j], 0, 0x0123) : 0u;
+  if (aligned) {
 #pragma unroll
-  for (int j = 0; j < 10; j++) w[j] = __funnelshift_l(raw[j + 1], raw[j], sh);
+    for (int j = 0; j < 10; j++) w[j] = raw[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 10; j++) w[j] = __funnelshift_l(raw[j + 1], raw[j], sh);
+  }
   if (L != fc.len || pclass != fc.pclass) {
     prefilter_masks(L, fc.V);
     const uint4 t = *reinterpret_cast<const uint4 *>(tfilt + (size_t)(pclass * kThrLen + L) * 8);
@@ -1055,6 +1061,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
     __syncwarp();
     const uint32_t span = 8u * u.stride;                 // bytes of 32 reads
     const uint32_t lane_byte = (uint32_t)lane * (u.stride >> 2);
+    const bool stride_aligned = (u.stride & 15u) == 0u;   // 16-base stride: every read starts on a word boundary
     const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(seq);
     const int L = (int)u.read_len;
     const int pclass = (int)u.pclass;
@@ -1097,7 +1104,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
       bool keep = has_n;
       if (!has_n) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(stage_buf[warp][b] + (lane_byte & ~3u));
-        keep = prefilter_keep<CSA, true>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc, one);
+        keep = prefilter_keep<CSA, true>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc, one, stride_aligned);
         if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
       }
       survivors_push(list, n_seg, keep, !has_n && L < kLongLen, s, lane);
@@ -1120,7 +1127,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
     bool keep = active && !lane_path;   // non-ACGT bases or > 160 bases: the scan kernel's warp path
     if (lane_path) {
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-      keep = prefilter_keep<CSA, false>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc, one);
+      keep = prefilter_keep<CSA, false>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc, one, false);
       if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;
     }
     survivors_push(list, n_seg, keep, lane_path && L < kLongLen, s, lane);
