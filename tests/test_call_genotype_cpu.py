@@ -187,3 +187,49 @@ def test_host_genotyping_with_bounds_and_loci_files(cli, tmp_path):
         co.assign_reads_locus(x, buckets, u["treads"])
         assert (x["n_left"], x["n_right"], x["n_total"]) == (int(arr2[i]["n_left"]), int(arr2[i]["n_right"]), int(arr2[i]["n_total"]))
     assert len(b2) == len(b)
+
+
+def test_high_depth_loci_are_skipped_like_the_reference(cli, tmp_path):
+    # call.nim:236-241 / collect.nim:166-169: a locus with more than 5000 supporting records, or more than 20000 read names in
+    # its window, is dropped from -bounds.txt and -genotype.txt (its reads stay consumed); other loci are unaffected
+    rng = np.random.default_rng(5)
+    targets = [("chr1", 400_000)]
+    loci = [(0, 50_000, 50_060, "CAG"), (0, 150_000, 150_040, "AAAG"), (0, 300_000, 300_050, "AC")]
+    recs = bamio.simulate_alignments(41, 4000, targets, loci, str_pair_frac=0.3, unmapped_pairs=10)
+    extra = []
+    seq = bamio._rand_seq(rng, 150)
+    for i in range(5600):      # > 5000 reads overlapping the bounds of locus 1, few read names beyond that
+        pos = 149_930 + (i % 40)
+        extra.append(Aln(f"deep{i}", 0, 0, pos, 60, [("M", 150)], -1, -1, 0, seq))
+    for i in range(23_000):    # > 20000 read names inside the window of locus 2, none of them overlapping its bounds
+        pos = 299_650 + (i % 200)
+        extra.append(Aln(f"wide{i}", 99, 0, pos, 60, [("M", 150)], 0, pos + 200, 350, seq))
+    placed = sorted([a for a in recs if a.tid >= 0] + extra, key=lambda a: (a.tid, a.pos))
+    recs = placed + [a for a in recs if a.tid < 0]
+    hdr = bamio.sam_header(targets)
+    bam, binp, cl = str(tmp_path / "a.bam"), str(tmp_path / "a.bin"), str(tmp_path / "cl.tsv")
+    bamio.write_bam(bam, hdr, targets, recs)
+    data, _, _ = eo.extract(recs, targets, hdr)
+    open(binp, "wb").write(data)
+    u = eo.unpack_bin(data)
+    frag = eo.fragment_length_distribution(recs)
+    window, med = orc.median(frag, 0.99), orc.median(frag, 0.5)
+    b, unplaced = orc.cluster_all(u["treads"], window, 3, 0, 0, int(0.5 * float(med)) & 0xFFFF, merge_mode=False)
+    with open(cl, "w") as fh:
+        for unit, cnt in sorted(unplaced.items()):
+            fh.write(f"-1 0 0 {unit.decode()} 0 0 0 0 0 0 0 {cnt}\n")
+        for x in b:
+            rep = bytes(x["repeat"]).rstrip(b"\0").decode()
+            fh.write(f"{x['tid']} {x['left']} {x['right']} {rep} {x['left_most']} {x['right_most']} {x['center_mass']} {x['n_left']} "
+                     f"{x['n_right']} {x['n_total']} {x['first_read']} {x['n_reads']}\n")
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([cli, "debug", "genotype", bam, binp, cl, prefix, str(window), "3", "40"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exp_gt, exp_bounds, _, _ = co.call(recs, data, min_support=3)
+    got_gt = open(prefix + "-genotype.txt").read().splitlines()[1:]
+    got_bounds = open(prefix + "-bounds.txt").read().splitlines()[1:]
+    assert sorted(got_gt) == sorted(exp_gt) and got_bounds == exp_bounds
+    pos = [int(l.split("\t")[1]) for l in got_bounds]
+    assert any(abs(p - 50_000) < 500 for p in pos)                                   # the ordinary locus is reported
+    assert not any(abs(p - 150_000) < 500 for p in pos) and not any(abs(p - 300_000) < 500 for p in pos)   # the deep ones are not
+    assert len(got_bounds) < len(b)
