@@ -169,3 +169,29 @@ def test_joint_merge_world2_matches_single_process_merge(tmp_path):
         got = [l for l in open(tmp_path / "joint.txt").read().split("\n") if l]
         exp, _ = eo.merge(datas, **kw)
         assert got == exp and (len(exp) > 3 or "min_clip" in kw)
+
+
+def test_joint_helpers_agree_with_the_oracle(tmp_path):
+    # the product-side .bin reader and quantile of strling_b200/joint.py against the oracle's (unpack.nim:58-133, utils.nim:139-146)
+    from oracle import extract_oracle as eo
+    from oracle import oracle as orc
+    from strling_b200 import bamio, joint
+
+    targets = [("chr1", 200_000)]
+    loci = [(0, 50_000, 50_060, "CAG")]
+    recs = bamio.simulate_alignments(3, 1500, targets, loci, str_pair_frac=0.5, unmapped_pairs=30)
+    data, _, _ = eo.extract(recs, targets, bamio.sam_header(targets))
+    p = str(tmp_path / "x.bin")
+    open(p, "wb").write(data)
+    frag, header, t = joint.read_bin(p)
+    u = eo.unpack_bin(data)
+    keep = u["treads"]["tid"] >= 0
+    assert header == u["header"] and np.array_equal(frag, u["frag_dist"]) and len(t) == int(keep.sum()) and len(t) > 100
+    for f in ("tid", "position", "repeat", "flag", "split", "mapq", "repeat_count", "align_length"):
+        assert np.array_equal(t[f], u["treads"][f][keep]), f
+    assert joint.targets_from_header(header) == targets
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        fd = rng.integers(0, 5000, size=4096).astype(np.uint32) * (rng.random(4096) < 0.3)
+        for pct in (0.5, 0.98, 0.99, 0.1):
+            assert joint.frag_median(fd.astype(np.uint32), pct) == orc.median(fd.astype(np.uint32), pct)
