@@ -7,7 +7,8 @@
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * strgpu_status; nothing aborts or exits (the reference `quit`s / doAsserts -- the shim maps a non-zero
- * status to `quit`).  One ctx per host thread and per GPU.  All structs are little-endian PODs with the
+ * status to `quit`).  One ctx per GPU; a ctx may be shared by ONE submitting and ONE waiting host thread (slot
+ * bookkeeping is locked inside the library), every other use is one thread at a time.  All structs are little-endian PODs with the
  * exact layouts below (static_asserted in the implementation).
  */
 #ifndef STRGPU_H
@@ -44,8 +45,11 @@ typedef enum {
  * with (utils.nim:14,19,245).  A non-ACGT base is stored as 1 ('A', as that package encodes it) and is
  * additionally flagged in nmask: bit (b & 31) of 32-bit word (b >> 5), b = absolute base index.
  * nmask may be NULL when no segment has STRGPU_SEG_HAS_N set.
+ * xmask (same layout, optional) flags the non-ACGT bases that are NOT the literal 'N' (IUPAC ambiguity codes, '='):
+ * the reference's `read.count('N') > 20` gate (utils.nim:238) counts 'N' only, while every non-ACGT base scans as 'A'
+ * and never matches in the recount (utils.nim:254 compares raw characters).  xmask == NULL: every flagged base is 'N'.
  * The seq2 buffer handed to the library must be readable for 8 bytes past the last base
- * (strgpu_seq2_bytes() includes that slack); nmask for 8 bytes past its last word likewise.
+ * (strgpu_seq2_bytes() includes that slack); nmask / xmask for 8 bytes past their last word likewise.
  */
 #define STRGPU_SEG_HAS_N 0x01u
 
@@ -68,7 +72,8 @@ typedef struct {
 /* ---- lifetime ---------------------------------------------------------------------------------- */
 const char *strgpu_version(void);
 const char *strgpu_error_string(int status);
-/* device: CUDA ordinal.  Fails with STRGPU_ERR_NO_DEVICE unless it is compute capability 10.x. */
+/* device: CUDA ordinal.  Fails with STRGPU_ERR_NO_DEVICE unless it is compute capability 10.x.
+ * On any failure *ctx is NULL and nothing is left to destroy. */
 int  strgpu_create(strgpu_ctx **ctx, int device);
 void strgpu_destroy(strgpu_ctx *ctx);
 const char *strgpu_last_error(const strgpu_ctx *ctx);
@@ -93,19 +98,19 @@ size_t strgpu_nmask_bytes(uint64_t n_bases);
 /* Host packers: write `len` bases at base index base_off.  Return the number of non-ACGT bases.
  * ascii: what hts-nim's aln.sequence() yields (extract.nim:37); bam4: the BAM record's 4-bit SEQ field.
  * base_off must be a multiple of 4 for the packers (segments themselves may start anywhere). */
-int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint64_t base_off);
-int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint64_t base_off);
+int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint32_t *xmask, uint64_t base_off);
+int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint32_t *xmask, uint64_t base_off);
 
 /* Asynchronous host API.  Copies the batch to the device on an internal stream, runs the scan, copies the
  * results back; strgpu_scan_wait blocks until `out` (n_seg records) is filled.  Buffers must stay valid
  * until the wait returns.  max_len: upper bound of segment lengths in this batch (selects the kernel
  * variant; a longer segment yields STRGPU_ERR_TOO_LONG at wait). */
-int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask,
+int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask, const uint32_t *xmask,
                        const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len,
                        strgpu_repeat *out, int *ticket);
 int strgpu_scan_wait(strgpu_ctx *ctx, int ticket);
 /* submit + wait */
-int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask,
+int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask, const uint32_t *xmask,
                 const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len, strgpu_repeat *out);
 /* Uniform-read batches without descriptors (saves the 8 B/read of host-to-device traffic that whole-read descriptors
  * cost): read i occupies bases [i * stride_bases, i * stride_bases + read_len) of seq2 and is scanned with
@@ -114,19 +119,19 @@ int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const ui
  * device.  `extra` (may be NULL) are ordinary descriptors for the other segments of the batch (soft clips);
  * out[0 .. n_reads) receives the reads' results, out[n_reads .. n_reads + n_extra) the extra segments'. */
 int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
-                             uint32_t pclass, const uint32_t *nmask, const strgpu_segment *extra, uint32_t n_extra,
-                             uint32_t extra_max_len, strgpu_repeat *out, int *ticket);
+                             uint32_t pclass, const uint32_t *nmask, const uint32_t *xmask, const strgpu_segment *extra,
+                             uint32_t n_extra, uint32_t extra_max_len, strgpu_repeat *out, int *ticket);
 
 /* Device-resident variant: all pointers are device pointers on ctx's device; the kernel is enqueued on
  * `cuda_stream` (a cudaStream_t, NULL = default stream) and the call returns without synchronising.
  * A too-long segment is reported by the next strgpu_device_status(). */
-int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask, const void *d_segs,
+int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask, const void *d_xmask, const void *d_segs,
                        uint32_t n_seg, uint32_t max_len, void *d_out, void *cuda_stream);
 /* Device-resident variant of strgpu_scan_reads_submit (same argument meaning; d_seq2 must be 16-byte aligned for the
  * TMA-staged path, otherwise per-lane loads are used): d_out[0 .. n_reads) receives the reads' results,
  * d_out[n_reads .. n_reads + n_extra) the extra segments'. */
 int strgpu_scan_reads_device(strgpu_ctx *ctx, const void *d_seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
-                             uint32_t pclass, const void *d_nmask, const void *d_extra, uint32_t n_extra,
+                             uint32_t pclass, const void *d_nmask, const void *d_xmask, const void *d_extra, uint32_t n_extra,
                              uint32_t extra_max_len, void *d_out, void *cuda_stream);
 /* synchronises `cuda_stream` and returns the sticky device-side status of launches since the last call */
 int strgpu_device_status(strgpu_ctx *ctx, void *cuda_stream);

@@ -4,6 +4,7 @@ behind a C ABI (include/strgpu.h, strling_b200/libstrgpu.so).  This package is t
 ABI used by the tests and bench.py; there is no CPU fallback: without the built CUDA library it raises."""
 from .binding import (  # noqa: F401
     BOUNDS_DTYPE,
+    Masks,
     REPEAT_DTYPE,
     TREAD_DTYPE,
     SEGMENT_DTYPE,

@@ -70,14 +70,14 @@ def load_library():
     L.strgpu_seq2_bytes.restype = C.c_size_t
     L.strgpu_nmask_bytes.argtypes = [u64]
     L.strgpu_nmask_bytes.restype = C.c_size_t
-    L.strgpu_pack_ascii.argtypes = [vp, u32, vp, vp, u64]
-    L.strgpu_pack_bam4.argtypes = [vp, u32, vp, vp, u64]
-    L.strgpu_scan_submit.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp, C.POINTER(i32)]
-    L.strgpu_scan_reads_submit.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, u32, u32, vp, C.POINTER(i32)]
+    L.strgpu_pack_ascii.argtypes = [vp, u32, vp, vp, vp, u64]
+    L.strgpu_pack_bam4.argtypes = [vp, u32, vp, vp, vp, u64]
+    L.strgpu_scan_submit.argtypes = [vp, vp, u64, vp, vp, vp, u32, u32, vp, C.POINTER(i32)]
+    L.strgpu_scan_reads_submit.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp, u32, u32, vp, C.POINTER(i32)]
     L.strgpu_scan_wait.argtypes = [vp, i32]
-    L.strgpu_scan.argtypes = [vp, vp, u64, vp, vp, u32, u32, vp]
-    L.strgpu_scan_device.argtypes = [vp, vp, vp, vp, u32, u32, vp, vp]
-    L.strgpu_scan_reads_device.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, u32, u32, vp, vp]
+    L.strgpu_scan.argtypes = [vp, vp, u64, vp, vp, vp, u32, u32, vp]
+    L.strgpu_scan_device.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, vp]
+    L.strgpu_scan_reads_device.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp, u32, u32, vp, vp]
     L.strgpu_device_status.argtypes = [vp, vp]
     L.strgpu_cluster.argtypes = [vp, vp, u32, vp, vp, u32, C.POINTER(u32)]
     L.strgpu_cluster_loci.argtypes = [vp, vp, u32, vp, vp, u32, vp, u32, C.POINTER(u32)]
@@ -86,9 +86,26 @@ def load_library():
     return L
 
 
+class Masks(tuple):
+    """(nmask, xmask): the non-ACGT plane and the plane of non-ACGT bases that are not the literal 'N' (include/strgpu.h).
+    Accepted wherever an `nmask` argument is: a bare array means "every flagged base is N"."""
+
+    def __new__(cls, nmask, xmask):
+        return super().__new__(cls, (nmask, xmask))
+
+
+def _mask_ptrs(nmask):
+    if nmask is None:
+        return None, None
+    if isinstance(nmask, Masks):
+        n, x = nmask
+        return (None if n is None else n.ctypes.data), (None if x is None or n is None else x.ctypes.data)
+    return nmask.ctypes.data, None
+
+
 def pack_reads(reads, pclass=0, align_bases: int = 16):
-    """Packs ASCII reads into one seq2 buffer (+ N mask) and one whole-read segment per read.
-    Each read starts at a multiple of `align_bases` (>= 4).  Returns (seq2 u8, nmask u32 or None, segments, n_bases)."""
+    """Packs ASCII reads into one seq2 buffer (+ N masks) and one whole-read segment per read.
+    Each read starts at a multiple of `align_bases` (>= 4).  Returns (seq2 u8, Masks or None, segments, n_bases)."""
     L = load_library()
     reads = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
     n = len(reads)
@@ -100,19 +117,20 @@ def pack_reads(reads, pclass=0, align_bases: int = 16):
     n_bases = int(padded.sum())
     seq2 = np.zeros(L.strgpu_seq2_bytes(n_bases), dtype=np.uint8)
     nmask = np.zeros(L.strgpu_nmask_bytes(n_bases) // 4, dtype=np.uint32)
+    xmask = np.zeros(L.strgpu_nmask_bytes(n_bases) // 4, dtype=np.uint32)
     segs = np.zeros(n, dtype=SEGMENT_DTYPE)
     segs["base_off"] = offs
     segs["len"] = lens
     segs["pclass"] = pclass
     any_n = False
     for i, r in enumerate(reads):
-        k = L.strgpu_pack_ascii(r, len(r), seq2.ctypes.data, nmask.ctypes.data, int(offs[i]))
+        k = L.strgpu_pack_ascii(r, len(r), seq2.ctypes.data, nmask.ctypes.data, xmask.ctypes.data, int(offs[i]))
         if k < 0:
             raise StrGpuError(k, "pack_ascii")
         if k:
             segs["flags"][i] |= SEG_HAS_N
             any_n = True
-    return seq2, (nmask if any_n else None), segs, n_bases
+    return seq2, (Masks(nmask, xmask if xmask.any() else None) if any_n else None), segs, n_bases
 
 
 class StrGpu:
@@ -166,22 +184,23 @@ class StrGpu:
         out = np.zeros(len(segs), dtype=REPEAT_DTYPE)
         if max_len is None:
             max_len = int(segs["len"].max()) if len(segs) else 0
-        self._check(self.L.strgpu_scan(self.h, seq2.ctypes.data, n_bases, None if nmask is None else nmask.ctypes.data,
-                                       segs.ctypes.data, len(segs), max_len, out.ctypes.data))
+        nm, xm = _mask_ptrs(nmask)
+        self._check(self.L.strgpu_scan(self.h, seq2.ctypes.data, n_bases, nm, xm, segs.ctypes.data, len(segs), max_len, out.ctypes.data))
         return out
 
     def scan_submit(self, seq2, n_bases, nmask, segs, max_len, out) -> int:
         t = C.c_int(-1)
-        self._check(self.L.strgpu_scan_submit(self.h, seq2.ctypes.data, n_bases, None if nmask is None else nmask.ctypes.data,
-                                              segs.ctypes.data, len(segs), max_len, out.ctypes.data, C.byref(t)))
+        nm, xm = _mask_ptrs(nmask)
+        self._check(self.L.strgpu_scan_submit(self.h, seq2.ctypes.data, n_bases, nm, xm, segs.ctypes.data, len(segs), max_len,
+                                              out.ctypes.data, C.byref(t)))
         return t.value
 
     def scan_reads_submit(self, seq2, n_reads: int, read_len: int, stride_bases: int, pclass: int, nmask, extra, extra_max_len: int, out) -> int:
         """Uniform whole reads without descriptors (+ optional explicit extra segments); results: reads first, then extras."""
         t = C.c_int(-1)
         n_extra = 0 if extra is None else len(extra)
-        self._check(self.L.strgpu_scan_reads_submit(self.h, seq2.ctypes.data, n_reads, read_len, stride_bases, pclass,
-                                                    None if nmask is None else nmask.ctypes.data,
+        nm, xm = _mask_ptrs(nmask)
+        self._check(self.L.strgpu_scan_reads_submit(self.h, seq2.ctypes.data, n_reads, read_len, stride_bases, pclass, nm, xm,
                                                     None if extra is None else extra.ctypes.data, n_extra, extra_max_len,
                                                     out.ctypes.data, C.byref(t)))
         return t.value
@@ -190,13 +209,14 @@ class StrGpu:
         self._check(self.L.strgpu_scan_wait(self.h, ticket))
 
     def scan_reads_device(self, d_seq2: int, n_reads: int, read_len: int, stride_bases: int, pclass: int, d_nmask: int | None,
-                          d_extra: int | None, n_extra: int, extra_max_len: int, d_out: int, stream: int = 0):
+                          d_extra: int | None, n_extra: int, extra_max_len: int, d_out: int, stream: int = 0, d_xmask: int | None = None):
         """Device-resident uniform-read batch (strgpu_scan_reads_device): all pointers are device addresses."""
         self._check(self.L.strgpu_scan_reads_device(self.h, d_seq2, n_reads, read_len, stride_bases, pclass, d_nmask or None,
-                                                    d_extra or None, n_extra, extra_max_len, d_out, stream or None))
+                                                    d_xmask or None, d_extra or None, n_extra, extra_max_len, d_out, stream or None))
 
-    def scan_device(self, d_seq2: int, d_nmask: int | None, d_segs: int, n_seg: int, max_len: int, d_out: int, stream: int = 0):
-        self._check(self.L.strgpu_scan_device(self.h, d_seq2, d_nmask, d_segs, n_seg, max_len, d_out, stream or None))
+    def scan_device(self, d_seq2: int, d_nmask: int | None, d_segs: int, n_seg: int, max_len: int, d_out: int, stream: int = 0,
+                    d_xmask: int | None = None):
+        self._check(self.L.strgpu_scan_device(self.h, d_seq2, d_nmask, d_xmask or None, d_segs, n_seg, max_len, d_out, stream or None))
 
     def device_status(self, stream: int = 0):
         self._check(self.L.strgpu_device_status(self.h, stream or None))

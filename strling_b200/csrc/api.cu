@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <numeric>
 #include <vector>
@@ -33,7 +34,7 @@ struct DevBuf {
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
-  DevBuf seq, nmask, segs, out, list;  // list: survivor list of the pre-filter kernel (n_seg + 1 words)
+  DevBuf seq, nmask, xmask, segs, out, list;  // list: survivor / stage lists of the scan kernels (scan_scratch_words)
   bool busy = false;
   strgpu_repeat *host_out = nullptr;
   uint32_t n_seg = 0;
@@ -60,12 +61,17 @@ struct strgpu_ctx {
   uint32_t *d_cl_n = nullptr;
   uint64_t launches = 0;
   char err[512] = {0};
+  // submit and wait may be called from two different host threads (a producer that stages batches and a consumer that
+  // replays results): slot bookkeeping, the launch counter and the error text are guarded by this mutex
+  std::mutex mu;
+  std::mutex err_mu;
 };
 
 namespace {
 
 int fail(strgpu_ctx *ctx, int status, const char *fmt, ...) {
   if (ctx) {
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
@@ -111,7 +117,19 @@ const char *strgpu_error_string(int status) {
   }
 }
 
+static int create_impl(strgpu_ctx **out, int device);
+
 int strgpu_create(strgpu_ctx **out, int device) {
+  // a context that failed half way is destroyed here: on error *out is NULL and there is nothing for the caller to free
+  const int rc = create_impl(out, device);
+  if (rc != STRGPU_OK && out && *out) {
+    strgpu_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+static int create_impl(strgpu_ctx **out, int device) {
   if (!out) return STRGPU_ERR_INVALID;
   *out = nullptr;
   int n = 0;
@@ -154,7 +172,7 @@ void strgpu_destroy(strgpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &s : ctx->slots) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    for (DevBuf *b : {&s.seq, &s.nmask, &s.segs, &s.out, &s.list})
+    for (DevBuf *b : {&s.seq, &s.nmask, &s.xmask, &s.segs, &s.out, &s.list})
       if (b->p) cudaFree(b->p);
     if (s.d_status) cudaFree(s.d_status);
     if (s.h_status) cudaFreeHost(s.h_status);
@@ -229,54 +247,89 @@ int strgpu_set_proportions(strgpu_ctx *ctx, const double *p, int n) {
 size_t strgpu_seq2_bytes(uint64_t n_bases) { return (size_t)((n_bases + 3) / 4) + 8; }
 size_t strgpu_nmask_bytes(uint64_t n_bases) { return (size_t)((n_bases + 31) / 32) * 4 + 8; }
 
-int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask,
-                       const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len, strgpu_repeat *out, int *ticket) {
-  if (!ctx || !ticket || (n_seg && (!seq2 || !segs || !out))) return fail(ctx, STRGPU_ERR_INVALID, "scan_submit: null argument");
-  if (max_len > STRGPU_MAX_SEGMENT_LEN) return fail(ctx, STRGPU_ERR_TOO_LONG, "max_len %u > %d", max_len, STRGPU_MAX_SEGMENT_LEN);
+}  // extern "C"
+
+namespace {
+
+// Common part of the two asynchronous submits: claim a slot, copy the batch in, run the scan, copy the results out.
+// `uniform` != nullptr: the first uniform->n_reads segments are implicit whole reads, `segs` holds the n_desc others.
+int submit_batch(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask, const uint32_t *xmask,
+                 const strgpu_segment *segs, uint32_t n_desc, const strgpu::UniformReads *uniform, uint32_t max_len,
+                 strgpu_repeat *out, int *ticket) {
   int si = -1;
-  for (int i = 0; i < STRGPU_SLOTS; i++)
-    if (!ctx->slots[i].busy) { si = i; break; }
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (int i = 0; i < STRGPU_SLOTS; i++)
+      if (!ctx->slots[i].busy) { si = i; break; }
+    if (si >= 0) ctx->slots[si].busy = true;   // claimed: no other submit takes it; scan_wait releases it
+  }
   if (si < 0) return fail(ctx, STRGPU_ERR_BUSY, "all %d submit slots in flight", STRGPU_SLOTS);
   Slot &s = ctx->slots[si];
-  CU(ctx, cudaSetDevice(ctx->device));
-  const size_t seq_bytes = (size_t)((n_bases + 3) / 4);
-  const size_t nm_bytes = nmask ? (size_t)((n_bases + 31) / 32) * 4 : 0;
-  int rc;
-  if ((rc = ensure(ctx, s.seq, seq_bytes + 16))) return rc;
-  if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
-  if ((rc = ensure(ctx, s.segs, (size_t)n_seg * sizeof(strgpu_segment) + 16))) return rc;
-  if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
-  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
-  s.n_seg = n_seg;
-  s.host_out = out;
-  if (n_seg) {
-    CU(ctx, cudaMemcpyAsync(s.seq.p, seq2, seq_bytes, cudaMemcpyHostToDevice, s.stream));
-    CU(ctx, cudaMemsetAsync((char *)s.seq.p + seq_bytes, 0, 16, s.stream));
-    if (nmask) {
-      CU(ctx, cudaMemcpyAsync(s.nmask.p, nmask, nm_bytes, cudaMemcpyHostToDevice, s.stream));
-      CU(ctx, cudaMemsetAsync((char *)s.nmask.p + nm_bytes, 0, 16, s.stream));
+  const uint32_t n_seg = (uniform ? uniform->n_reads : 0u) + n_desc;
+  auto body = [&]() -> int {
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t seq_bytes = (size_t)((n_bases + 3) / 4);
+    const size_t nm_bytes = nmask ? (size_t)((n_bases + 31) / 32) * 4 : 0;
+    const bool use_x = nmask && xmask;
+    int rc;
+    if ((rc = ensure(ctx, s.seq, seq_bytes + 16))) return rc;
+    if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
+    if (use_x && (rc = ensure(ctx, s.xmask, nm_bytes + 16))) return rc;
+    if ((rc = ensure(ctx, s.segs, (size_t)n_desc * sizeof(strgpu_segment) + 16))) return rc;
+    if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
+    if ((rc = ensure(ctx, s.list, strgpu::scan_scratch_words(n_seg) * sizeof(uint32_t)))) return rc;
+    s.n_seg = n_seg;
+    s.host_out = out;
+    if (n_seg) {
+      CU(ctx, cudaMemcpyAsync(s.seq.p, seq2, seq_bytes, cudaMemcpyHostToDevice, s.stream));
+      CU(ctx, cudaMemsetAsync((char *)s.seq.p + seq_bytes, 0, 16, s.stream));
+      if (nmask) {
+        CU(ctx, cudaMemcpyAsync(s.nmask.p, nmask, nm_bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(ctx, cudaMemsetAsync((char *)s.nmask.p + nm_bytes, 0, 16, s.stream));
+      }
+      if (use_x) {
+        CU(ctx, cudaMemcpyAsync(s.xmask.p, xmask, nm_bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(ctx, cudaMemsetAsync((char *)s.xmask.p + nm_bytes, 0, 16, s.stream));
+      }
+      if (n_desc) CU(ctx, cudaMemcpyAsync(s.segs.p, segs, (size_t)n_desc * sizeof(strgpu_segment), cudaMemcpyHostToDevice, s.stream));
+      CU(ctx, cudaMemsetAsync(s.d_status, 0, sizeof(int), s.stream));
+      CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
+                                         use_x ? (const uint32_t *)s.xmask.p : nullptr, (const strgpu_segment *)s.segs.p, n_seg,
+                                         max_len, ctx->d_thr, ctx->d_luts, (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count,
+                                         ctx->variant, s.stream, uniform, (uint32_t *)s.list.p));
+      CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
+      CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      *s.h_status = 0;
     }
-    CU(ctx, cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(strgpu_segment), cudaMemcpyHostToDevice, s.stream));
-    CU(ctx, cudaMemsetAsync(s.d_status, 0, sizeof(int), s.stream));
-    CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
-                                       (const strgpu_segment *)s.segs.p, n_seg, max_len, ctx->d_thr, ctx->d_luts,
-                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, ctx->variant, s.stream, nullptr,
-                                       (uint32_t *)s.list.p));
-    ctx->launches += strgpu::scan_launches(max_len, ctx->variant);
-    CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
-    CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-  } else {
-    *s.h_status = 0;
+    CU(ctx, cudaEventRecord(s.done, s.stream));
+    return STRGPU_OK;
+  };
+  const int rc = body();
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (rc != STRGPU_OK) {
+    s.busy = false;
+    return rc;
   }
-  CU(ctx, cudaEventRecord(s.done, s.stream));
-  s.busy = true;
+  if (n_seg) ctx->launches += strgpu::scan_launches(max_len, ctx->variant);
   *ticket = si;
   return STRGPU_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int strgpu_scan_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask, const uint32_t *xmask,
+                       const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len, strgpu_repeat *out, int *ticket) {
+  if (!ctx || !ticket || (n_seg && (!seq2 || !segs || !out))) return fail(ctx, STRGPU_ERR_INVALID, "scan_submit: null argument");
+  if (max_len > STRGPU_MAX_SEGMENT_LEN) return fail(ctx, STRGPU_ERR_TOO_LONG, "max_len %u > %d", max_len, STRGPU_MAX_SEGMENT_LEN);
+  return submit_batch(ctx, seq2, n_bases, nmask, xmask, segs, n_seg, nullptr, max_len, out, ticket);
+}
+
 int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
-                             uint32_t pclass, const uint32_t *nmask, const strgpu_segment *extra, uint32_t n_extra,
-                             uint32_t extra_max_len, strgpu_repeat *out, int *ticket) {
+                             uint32_t pclass, const uint32_t *nmask, const uint32_t *xmask, const strgpu_segment *extra,
+                             uint32_t n_extra, uint32_t extra_max_len, strgpu_repeat *out, int *ticket) {
   if (!ctx || !ticket || ((n_reads || n_extra) && (!seq2 || !out)) || (n_extra && !extra))
     return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_submit: null argument");
   if ((stride_bases & 3u) || stride_bases < read_len || pclass >= STRGPU_MAX_PCLASS)
@@ -295,94 +348,65 @@ int strgpu_scan_reads_submit(strgpu_ctx *ctx, const uint8_t *seq2, uint32_t n_re
       all[i] = strgpu_segment{i * stride_bases, (uint16_t)read_len, (uint8_t)pclass, (uint8_t)(has_n ? STRGPU_SEG_HAS_N : 0)};
     }
     for (uint32_t i = 0; i < n_extra; i++) all[n_reads + i] = extra[i];
-    return strgpu_scan_submit(ctx, seq2, (uint64_t)n_reads * stride_bases, nmask, all.data(), n_reads + n_extra,
-                              read_len > extra_max_len ? read_len : extra_max_len, out, ticket);
+    // the descriptor array is copied to the device before this function returns (pageable memory: the copy is staged)
+    return submit_batch(ctx, seq2, (uint64_t)n_reads * stride_bases, nmask, xmask, all.data(), n_reads + n_extra, nullptr,
+                        read_len > extra_max_len ? read_len : extra_max_len, out, ticket);
   }
-  int si = -1;
-  for (int i = 0; i < STRGPU_SLOTS; i++)
-    if (!ctx->slots[i].busy) { si = i; break; }
-  if (si < 0) return fail(ctx, STRGPU_ERR_BUSY, "all %d submit slots in flight", STRGPU_SLOTS);
-  Slot &s = ctx->slots[si];
-  CU(ctx, cudaSetDevice(ctx->device));
-  const uint64_t n_bases = (uint64_t)n_reads * stride_bases;
-  const size_t seq_bytes = (size_t)((n_bases + 3) / 4);
-  const size_t nm_bytes = nmask ? (size_t)((n_bases + 31) / 32) * 4 : 0;
-  const uint32_t n_seg = n_reads + n_extra;
-  int rc;
-  if ((rc = ensure(ctx, s.seq, seq_bytes + 16))) return rc;
-  if ((rc = ensure(ctx, s.nmask, nm_bytes + 16))) return rc;
-  if ((rc = ensure(ctx, s.segs, (size_t)n_extra * sizeof(strgpu_segment) + 16))) return rc;
-  if ((rc = ensure(ctx, s.out, (size_t)n_seg * sizeof(strgpu_repeat) + 16))) return rc;
-  if ((rc = ensure(ctx, s.list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
-  s.n_seg = n_seg;
-  s.host_out = out;
-  if (n_seg) {
-    CU(ctx, cudaMemcpyAsync(s.seq.p, seq2, seq_bytes, cudaMemcpyHostToDevice, s.stream));
-    CU(ctx, cudaMemsetAsync((char *)s.seq.p + seq_bytes, 0, 16, s.stream));
-    if (nmask) {
-      CU(ctx, cudaMemcpyAsync(s.nmask.p, nmask, nm_bytes, cudaMemcpyHostToDevice, s.stream));
-      CU(ctx, cudaMemsetAsync((char *)s.nmask.p + nm_bytes, 0, 16, s.stream));
-    }
-    if (n_extra) CU(ctx, cudaMemcpyAsync(s.segs.p, extra, (size_t)n_extra * sizeof(strgpu_segment), cudaMemcpyHostToDevice, s.stream));
-    CU(ctx, cudaMemsetAsync(s.d_status, 0, sizeof(int), s.stream));
-    const strgpu::UniformReads u{n_reads, read_len, stride_bases, pclass};
-    CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)s.seq.p, nmask ? (const uint32_t *)s.nmask.p : nullptr,
-                                       (const strgpu_segment *)s.segs.p, n_seg, read_len, ctx->d_thr, ctx->d_luts,
-                                       (strgpu_repeat *)s.out.p, s.d_status, ctx->sm_count, ctx->variant, s.stream, &u,
-                                       (uint32_t *)s.list.p));
-    ctx->launches += strgpu::scan_launches(read_len, ctx->variant);
-    CU(ctx, cudaMemcpyAsync(out, s.out.p, (size_t)n_seg * sizeof(strgpu_repeat), cudaMemcpyDeviceToHost, s.stream));
-    CU(ctx, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-  } else {
-    *s.h_status = 0;
-  }
-  CU(ctx, cudaEventRecord(s.done, s.stream));
-  s.busy = true;
-  *ticket = si;
-  return STRGPU_OK;
+  const strgpu::UniformReads u{n_reads, read_len, stride_bases, pclass};
+  return submit_batch(ctx, seq2, (uint64_t)n_reads * stride_bases, nmask, xmask, extra, n_extra, &u, read_len, out, ticket);
 }
 
 int strgpu_scan_wait(strgpu_ctx *ctx, int ticket) {
-  if (!ctx || ticket < 0 || ticket >= STRGPU_SLOTS || !ctx->slots[ticket].busy)
-    return fail(ctx, STRGPU_ERR_TICKET, "scan_wait: bad ticket %d", ticket);
+  if (!ctx || ticket < 0 || ticket >= STRGPU_SLOTS) return fail(ctx, STRGPU_ERR_TICKET, "scan_wait: bad ticket %d", ticket);
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->slots[ticket].busy) return fail(ctx, STRGPU_ERR_TICKET, "scan_wait: bad ticket %d", ticket);
+  }
   Slot &s = ctx->slots[ticket];
   cudaError_t e = cudaEventSynchronize(s.done);
-  s.busy = false;
+  const int st = *s.h_status;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    s.busy = false;
+  }
   if (e != cudaSuccess) return fail(ctx, STRGPU_ERR_CUDA, "scan_wait: %s", cudaGetErrorString(e));
-  if (*s.h_status != 0) return fail(ctx, *s.h_status, "scan: %s", strgpu_error_string(*s.h_status));
+  if (st != 0) return fail(ctx, st, "scan: %s", strgpu_error_string(st));
   return STRGPU_OK;
 }
 
-int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask, const strgpu_segment *segs,
-                uint32_t n_seg, uint32_t max_len, strgpu_repeat *out) {
+int strgpu_scan(strgpu_ctx *ctx, const uint8_t *seq2, uint64_t n_bases, const uint32_t *nmask, const uint32_t *xmask,
+                const strgpu_segment *segs, uint32_t n_seg, uint32_t max_len, strgpu_repeat *out) {
   int t = -1;
-  int rc = strgpu_scan_submit(ctx, seq2, n_bases, nmask, segs, n_seg, max_len, out, &t);
+  int rc = strgpu_scan_submit(ctx, seq2, n_bases, nmask, xmask, segs, n_seg, max_len, out, &t);
   if (rc) return rc;
   return strgpu_scan_wait(ctx, t);
 }
 
-int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask, const void *d_segs, uint32_t n_seg,
-                       uint32_t max_len, void *d_out, void *cuda_stream) {
+int strgpu_scan_device(strgpu_ctx *ctx, const void *d_seq2, const void *d_nmask, const void *d_xmask, const void *d_segs,
+                       uint32_t n_seg, uint32_t max_len, void *d_out, void *cuda_stream) {
   if (!ctx || (n_seg && (!d_seq2 || !d_segs || !d_out))) return fail(ctx, STRGPU_ERR_INVALID, "scan_device: null argument");
   if (max_len > STRGPU_MAX_SEGMENT_LEN) return fail(ctx, STRGPU_ERR_TOO_LONG, "max_len %u > %d", max_len, STRGPU_MAX_SEGMENT_LEN);
-  if (((uintptr_t)d_seq2 & 3) || ((uintptr_t)d_nmask & 3) || ((uintptr_t)d_segs & 7) || ((uintptr_t)d_out & 7))
+  if (((uintptr_t)d_seq2 & 3) || ((uintptr_t)d_nmask & 3) || ((uintptr_t)d_xmask & 3) || ((uintptr_t)d_segs & 7) || ((uintptr_t)d_out & 7))
     return fail(ctx, STRGPU_ERR_INVALID, "scan_device: misaligned device pointer");
+  if (n_seg == 0) return STRGPU_OK;
   CU(ctx, cudaSetDevice(ctx->device));
-  // the survivor list is one scratch buffer per context: launches that use it are chained through an event, so calls on
+  // the scratch lists are one buffer per context: launches that use it are chained through an event, so calls on
   // different streams stay correct (they serialise)
   int rc;
-  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(ctx, ctx->dev_list, strgpu::scan_scratch_words(n_seg) * sizeof(uint32_t)))) return rc;
   CU(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->dev_list_done, 0));
-  CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_segs,
-                                     n_seg, max_len, ctx->d_thr, ctx->d_luts, (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count,
-                                     ctx->variant, (cudaStream_t)cuda_stream, nullptr, (uint32_t *)ctx->dev_list.p));
+  CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, d_nmask ? (const uint32_t *)d_xmask : nullptr,
+                                     (const strgpu_segment *)d_segs, n_seg, max_len, ctx->d_thr, ctx->d_luts, (strgpu_repeat *)d_out,
+                                     ctx->d_status_dev, ctx->sm_count, ctx->variant, (cudaStream_t)cuda_stream, nullptr,
+                                     (uint32_t *)ctx->dev_list.p));
   CU(ctx, cudaEventRecord(ctx->dev_list_done, (cudaStream_t)cuda_stream));
-  if (n_seg) ctx->launches += strgpu::scan_launches(max_len, ctx->variant);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->launches += strgpu::scan_launches(max_len, ctx->variant);
   return STRGPU_OK;
 }
 
 int strgpu_scan_reads_device(strgpu_ctx *ctx, const void *d_seq2, uint32_t n_reads, uint32_t read_len, uint32_t stride_bases,
-                             uint32_t pclass, const void *d_nmask, const void *d_extra, uint32_t n_extra,
+                             uint32_t pclass, const void *d_nmask, const void *d_xmask, const void *d_extra, uint32_t n_extra,
                              uint32_t extra_max_len, void *d_out, void *cuda_stream) {
   if (!ctx || ((n_reads || n_extra) && (!d_seq2 || !d_out)) || (n_extra && !d_extra))
     return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_device: null argument");
@@ -392,20 +416,21 @@ int strgpu_scan_reads_device(strgpu_ctx *ctx, const void *d_seq2, uint32_t n_rea
   if (read_len > (uint32_t)strgpu::kShortMaxLen || extra_max_len > (uint32_t)strgpu::kShortMaxLen)
     return fail(ctx, STRGPU_ERR_TOO_LONG, "scan_reads_device: read_len %u / extra_max_len %u > %d (use strgpu_scan_device)", read_len,
                 extra_max_len, strgpu::kShortMaxLen);
-  if (((uintptr_t)d_seq2 & 3) || ((uintptr_t)d_nmask & 3) || ((uintptr_t)d_extra & 7) || ((uintptr_t)d_out & 7))
+  if (((uintptr_t)d_seq2 & 3) || ((uintptr_t)d_nmask & 3) || ((uintptr_t)d_xmask & 3) || ((uintptr_t)d_extra & 7) || ((uintptr_t)d_out & 7))
     return fail(ctx, STRGPU_ERR_INVALID, "scan_reads_device: misaligned device pointer");
   const uint32_t n_seg = n_reads + n_extra;
   if (n_seg == 0) return STRGPU_OK;
   CU(ctx, cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = ensure(ctx, ctx->dev_list, ((size_t)n_seg + 4) * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(ctx, ctx->dev_list, strgpu::scan_scratch_words(n_seg) * sizeof(uint32_t)))) return rc;
   CU(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->dev_list_done, 0));
   const strgpu::UniformReads u{n_reads, read_len, stride_bases, pclass};
-  CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, (const strgpu_segment *)d_extra, n_seg,
-                                     read_len > extra_max_len ? read_len : extra_max_len, ctx->d_thr, ctx->d_luts,
-                                     (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count, ctx->variant, (cudaStream_t)cuda_stream, &u,
-                                     (uint32_t *)ctx->dev_list.p));
+  CU(ctx, strgpu::launch_repeat_scan((const uint32_t *)d_seq2, (const uint32_t *)d_nmask, d_nmask ? (const uint32_t *)d_xmask : nullptr,
+                                     (const strgpu_segment *)d_extra, n_seg, read_len > extra_max_len ? read_len : extra_max_len,
+                                     ctx->d_thr, ctx->d_luts, (strgpu_repeat *)d_out, ctx->d_status_dev, ctx->sm_count, ctx->variant,
+                                     (cudaStream_t)cuda_stream, &u, (uint32_t *)ctx->dev_list.p));
   CU(ctx, cudaEventRecord(ctx->dev_list_done, (cudaStream_t)cuda_stream));
+  std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->launches += strgpu::scan_launches(read_len, ctx->variant);
   return STRGPU_OK;
 }

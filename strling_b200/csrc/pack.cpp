@@ -1,6 +1,7 @@
 // Host-side sequence packers of libstrgpu (include/strgpu.h): ASCII or BAM 4-bit SEQ -> 2-bit + N mask.
 // Base codes follow the `kmer` nimble package the reference scans with (utils.nim:14): C=0 A=1 T=2 G=3,
-// anything else is stored as 1 ('A') and flagged in the N mask.
+// anything else is stored as 1 ('A') and flagged in the N mask; a non-ACGT base that is not the literal 'N' (an IUPAC
+// ambiguity code, '=') is flagged in the second plane too, because the reference's N > 20 gate counts 'N' only (utils.nim:238).
 #include <cstdint>
 #include <cstring>
 
@@ -47,12 +48,16 @@ struct Bam4Lut {
 const Bam4Lut kBam4;
 
 inline void set_n(uint32_t *nmask, uint64_t b) { nmask[b >> 5] |= 1u << (b & 31); }
+inline void flag(uint32_t *nmask, uint32_t *xmask, uint64_t b, bool literal_n) {
+  if (nmask) set_n(nmask, b);
+  if (xmask && !literal_n) set_n(xmask, b);
+}
 
 }  // namespace
 
 extern "C" {
 
-int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint64_t base_off) {
+int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint32_t *xmask, uint64_t base_off) {
   if (!seq2 || (len && !seq) || (base_off & 3)) return STRGPU_ERR_INVALID;
   uint8_t *dst = seq2 + (base_off >> 2);
   int n_other = 0;
@@ -63,7 +68,7 @@ int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nm
     const int o = kAscii.other[a] | kAscii.other[b] | kAscii.other[c] | kAscii.other[d];
     if (o) {
       for (int j = 0; j < 4; j++)
-        if (kAscii.other[(unsigned char)seq[i + j]]) { n_other++; if (nmask) set_n(nmask, base_off + i + j); }
+        if (kAscii.other[(unsigned char)seq[i + j]]) { n_other++; flag(nmask, xmask, base_off + i + j, seq[i + j] == 'N'); }
     }
   }
   if (i < len) {
@@ -73,7 +78,7 @@ int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nm
       if (i + j < len) {
         const unsigned char ch = seq[i + j];
         c = kAscii.code[ch];
-        if (kAscii.other[ch]) { n_other++; if (nmask) set_n(nmask, base_off + i + j); }
+        if (kAscii.other[ch]) { n_other++; flag(nmask, xmask, base_off + i + j, ch == 'N'); }
       }
       v = (uint8_t)((v << 2) | c);
     }
@@ -82,7 +87,7 @@ int strgpu_pack_ascii(const char *seq, uint32_t len, uint8_t *seq2, uint32_t *nm
   return n_other;
 }
 
-int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint64_t base_off) {
+int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32_t *nmask, uint32_t *xmask, uint64_t base_off) {
   if (!seq2 || (len && !bam_seq) || (base_off & 3)) return STRGPU_ERR_INVALID;
   uint8_t *dst = seq2 + (base_off >> 2);
   int n_other = 0;
@@ -93,7 +98,12 @@ int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32
     const int o = (kBam4.pair_other[b0] << 2) | kBam4.pair_other[b1];
     if (o) {
       for (int j = 0; j < 4; j++)
-        if (o & (8 >> j)) { n_other++; if (nmask) set_n(nmask, base_off + i + j); }
+        if (o & (8 >> j)) {
+          const uint32_t b = i + j;
+          const uint8_t nib = (b & 1) ? (bam_seq[b >> 1] & 15) : (bam_seq[b >> 1] >> 4);
+          n_other++;
+          flag(nmask, xmask, base_off + b, nib == 15);
+        }
     }
   }
   if (i < len) {
@@ -104,7 +114,7 @@ int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32
         const uint32_t b = i + j;
         const uint8_t nib = (b & 1) ? (bam_seq[b >> 1] & 15) : (bam_seq[b >> 1] >> 4);
         c = kBam4.code[nib];
-        if (kBam4.other[nib]) { n_other++; if (nmask) set_n(nmask, base_off + b); }
+        if (kBam4.other[nib]) { n_other++; flag(nmask, xmask, base_off + b, nib == 15); }
       }
       v = (uint8_t)((v << 2) | c);
     }

@@ -13,7 +13,9 @@
 // Integer / bitwise work only: no tensor cores.  Thresholds come from a host-built fp64-exact table.
 #include "scan_kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 namespace strgpu {
 
@@ -195,7 +197,8 @@ __device__ __forceinline__ void emit_result(strgpu_repeat *out, uint32_t s, cons
 // ws.tab must be all zero on entry (it is left all zero).
 template <int MAXLEN>
 __device__ __forceinline__ void warp_scan_segment(WarpScratch<MAXLEN> &ws, const uint32_t *__restrict__ seq,
-                                                  const uint32_t *__restrict__ nmask, const strgpu_segment sg, uint32_t s,
+                                                  const uint32_t *__restrict__ nmask, const uint32_t *__restrict__ xmask,
+                                                  const strgpu_segment sg, uint32_t s,
                                                   const uint16_t *__restrict__ thr, int lane, int start_k, ScanState st,
                                                   strgpu_repeat *__restrict__ out, int *status) {
   constexpr int MAXR2 = (MAXLEN / 2 + 31) / 32, MAXR3 = (MAXLEN / 3 + 31) / 32, MAXR4 = (MAXLEN / 4 + 31) / 32,
@@ -227,15 +230,18 @@ __device__ __forceinline__ void warp_scan_segment(WarpScratch<MAXLEN> &ws, const
   if (has_n) {  // warp-uniform
     const int n_nw = (L + 31) >> 5;
     for (int l = lane; l < n_nw + 1; l += 32) {
-      uint32_t v = 0;
+      uint32_t v = 0, x = 0;
       if (l < n_nw) {
         const uint32_t g = (sg.base_off >> 5) + (uint32_t)l;
         v = __funnelshift_r(nmask[g], nmask[g + 1], sg.base_off & 31u);
         const int rem = L - 32 * l;
         if (rem < 32) v &= (1u << rem) - 1u;
+        // utils.nim:238 counts the literal 'N' only: bases flagged in xmask (IUPAC codes other than N) never match in the
+        // recount but do not count towards the gate
+        if (xmask != nullptr) x = __funnelshift_r(xmask[g], xmask[g + 1], sg.base_off & 31u);
       }
       ws.nm[l] = v;
-      n_count += __popc(v);
+      n_count += __popc(v & ~x);
     }
     n_count = __reduce_add_sync(kFull, n_count);
   }
@@ -258,6 +264,7 @@ __device__ __forceinline__ void warp_scan_segment(WarpScratch<MAXLEN> &ws, const
 template <int MAXLEN, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *__restrict__ seq,
                                                                const uint32_t *__restrict__ nmask,
+                                                               const uint32_t *__restrict__ xmask,
                                                                const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                const uint16_t *__restrict__ thr,
                                                                strgpu_repeat *__restrict__ out, int *status) {
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *_
   __syncwarp();
   const uint32_t warps_total = gridDim.x * WARPS;
   for (uint32_t s = blockIdx.x * WARPS + warp; s < n_seg; s += warps_total)
-    warp_scan_segment<MAXLEN>(ws, seq, nmask, segs[s], s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
+    warp_scan_segment<MAXLEN>(ws, seq, nmask, xmask, segs[s], s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
 }
 
 // ================================================================================================
@@ -286,24 +293,14 @@ __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *_
 //     bases are finished one per warp by the compact warp-per-segment code.
 // Every warp owns its shared-memory region and its queues: there is no block-level barrier after start-up.
 // ================================================================================================
-constexpr int kLaneThreads = 640;               // one CTA of 20 independent warps per SM (shared-memory bound)
-constexpr int kLaneWarps = kLaneThreads / 32;
 constexpr int kLaneWords = 11;                 // ten words hold 160 bases; one more absorbs the re-alignment shift
 constexpr int kCls2 = 10, kCls3 = 24, kCls4 = 70, kCls5 = 208;
 constexpr int kCls4Words = (kCls4 + 3) / 4;       // 4-mer classes are counted in packed uint8 (18 words) to keep smem small
 constexpr int kTabWords = kCls2 + kCls3 + kCls4Words;  // 52 words per lane; k = 5 reuses them as 208 packed uint8
 constexpr int kLut2 = 0, kLut3 = 16, kLut4 = 80, kRev234 = 336, kLut5 = 440, kRev5 = 1464;  // offsets into the uint16 table
 constexpr int kLutTotal = 1672;
-constexpr int kQueueCap = 64;                  // a batch is taken at 32 entries and a stage adds at most 32
-// Q3 (3 words/entry), Q4, Q5, Q6 (2 words/entry), Q2 (filter survivors, 1 word/entry), QW (1 word/entry, cap 32)
-constexpr int kQ3Off = 0, kQ4Off = kQueueCap * 3, kQ5Off = kQ4Off + kQueueCap * 2, kQ6Off = kQ5Off + kQueueCap * 2,
-              kQ2Off = kQ6Off + kQueueCap * 2, kQWOff = kQ2Off + kQueueCap;
-constexpr int kQueueWords = kQWOff + 32;
-constexpr int kWarpSmemWords = kTabWords * 32 + kLaneWords * 32 + kQueueWords;
-constexpr int kLaneSmemBytes = kLaneWarps * kWarpSmemWords * 4 + kLutTotal * 2 + 16;
-constexpr int lane_smem_bytes(int warps) { return warps * kWarpSmemWords * 4 + kLutTotal * 2 + 16; }
-static_assert(sizeof(WarpScratch<512>) <= (size_t)kTabWords * 32 * 4, "warp scratch must fit in the warp's counter region");
 static_assert(kCls5 / 4 <= kTabWords, "k = 5 counters must fit");
+static_assert(kLutTotal == kLaneLutEntries, "LUT size");
 
 // read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254).
 // One copy for all k, kept out of line (instruction-cache footprint).  `scratch` is the lane's counter column (dead by
@@ -404,7 +401,8 @@ __device__ __noinline__ int lane_recount(const uint32_t *rd, uint32_t *scratch, 
 // Compact warp-per-segment path (runtime k, rolled loops) for the few segments the lane path hands off: same
 // arithmetic as count_k / recount_k / ladder_step above, written for code size instead of speed.
 __device__ __noinline__ void warp_scan_compact(WarpScratch<512> &ws, const uint32_t *__restrict__ seq,
-                                               const uint32_t *__restrict__ nmask, const strgpu_segment sg, uint32_t s,
+                                               const uint32_t *__restrict__ nmask, const uint32_t *__restrict__ xmask,
+                                               const strgpu_segment sg, uint32_t s,
                                                const uint16_t *__restrict__ thr, int lane, int start_k, ScanState st,
                                                strgpu_repeat *__restrict__ out, int *status) {
   const int L = sg.len;
@@ -430,15 +428,18 @@ __device__ __noinline__ void warp_scan_compact(WarpScratch<512> &ws, const uint3
   if (has_n) {
     const int n_nw = (L + 31) >> 5;
     for (int l = lane; l < n_nw + 1; l += 32) {
-      uint32_t v = 0;
+      uint32_t v = 0, x = 0;
       if (l < n_nw) {
         const uint32_t g = (sg.base_off >> 5) + (uint32_t)l;
         v = __funnelshift_r(nmask[g], nmask[g + 1], sg.base_off & 31u);
         const int rem = L - 32 * l;
         if (rem < 32) v &= (1u << rem) - 1u;
+        // utils.nim:238 counts the literal 'N' only: bases flagged in xmask (IUPAC codes other than N) never match in the
+        // recount but do not count towards the gate
+        if (xmask != nullptr) x = __funnelshift_r(xmask[g], xmask[g + 1], sg.base_off & 31u);
       }
       ws.nm[l] = v;
-      n_count += __popc(v);
+      n_count += __popc(v & ~x);
     }
     n_count = __reduce_add_sync(kFull, n_count);
   }
@@ -724,33 +725,6 @@ __device__ __forceinline__ void lane_count6(const uint32_t *rd, uint32_t *tab, i
   }
 }
 
-// Warp-local FIFOs of segments waiting for their next stage.  Q4..Q6 entries are two words, Q3 entries three:
-//   0: segment index      1: best << 24 | repeat_count << 16 | unit_k << 12 | unit_code      2 (Q3 only): M3 | leader3 << 8
-// (entries are written after the k = 2 rung, so 0 <= best <= 160 and repeat_count <= 80)
-template <int WORDS>
-__device__ __forceinline__ void queue_push(uint32_t *buf, int &n, bool want, int lane, uint32_t s, const ScanState &st, uint32_t extra) {
-  const uint32_t m = __ballot_sync(kFull, want);
-  if (want) {
-    uint32_t *e = buf + WORDS * (n + __popc(m & ((1u << lane) - 1u)));
-    e[0] = s;
-    if (WORDS >= 2) e[1] = ((uint32_t)(st.best & 0xff) << 24) | ((uint32_t)(st.rc & 0xff) << 16) | ((uint32_t)st.unit_k << 12) | (st.unit_code & 0xfffu);
-    if (WORDS >= 3) e[2] = extra;
-  }
-  n += __popc(m);
-  __syncwarp();
-}
-template <int WORDS>
-__device__ __forceinline__ void queue_read(const uint32_t *buf, int i, uint32_t &s, ScanState &st, uint32_t &extra) {
-  const uint32_t *e = buf + WORDS * i;
-  s = e[0];
-  const uint32_t a = e[1];
-  st.best = (int)(a >> 24);
-  st.rc = (int)((a >> 16) & 0xffu);
-  st.unit_k = (int)((a >> 12) & 0xfu);
-  st.unit_code = a & 0xfffu;
-  extra = WORDS >= 3 ? e[2] : 0u;
-}
-
 // Segment s of the batch: the first u.n_reads are implicit whole reads of one length on a fixed stride (no descriptor
 // is read; non-ACGT bases are detected from the mask itself), the rest come from the descriptor array.
 __device__ __forceinline__ strgpu_segment load_segment(const strgpu_segment *__restrict__ segs, const uint32_t *__restrict__ nmask,
@@ -791,72 +765,6 @@ __device__ __forceinline__ strgpu_segment load_segment(const strgpu_segment *__r
 // positions where the 2-mer ab starts.  Only b = 0..2 are counted, b = 3 follows from popc(E_a).
 constexpr uint32_t kOdd = 0xaaaaaaaau, kEven = 0x55555555u;
 
-// valid-position masks of the five word pairs for a segment of L bases (positions 0 .. L - 2 start a 2-mer)
-__device__ __forceinline__ void filter_masks(int L, uint32_t (&V)[5]) {
-#pragma unroll
-  for (int j = 0; j < 5; j++) {
-    const int v = L - 1 - 32 * j;
-    const int v0 = min(max(v, 0), 16), v1 = min(max(v - 16, 0), 16);
-    const uint32_t m0 = v0 >= 16 ? kOdd : (kOdd & ~(kFull >> (2 * v0)));
-    const uint32_t m1 = v1 >= 16 ? kEven : (kEven & ~(kFull >> (2 * v1)));
-    V[j] = m0 | m1;
-  }
-}
-
-template <int VARIANT>
-__device__ __forceinline__ int lane_filter_max2(const uint32_t (&w)[11], const uint32_t (&V)[5]) {
-  uint32_t E[5][4], Qh[5], Ql[5];
-#pragma unroll
-  for (int j = 0; j < 5; j++) {
-    const uint32_t w0 = w[2 * j], w1 = w[2 * j + 1], w2 = w[2 * j + 2];
-    const uint32_t n0 = __funnelshift_l(w1, w0, 2), n1 = __funnelshift_l(w2, w1, 2);   // successor of every base
-    const uint32_t Ph = (w0 & kOdd) | ((w1 >> 1) & kEven), Pl = ((w0 << 1) & kOdd) | (w1 & kEven);
-    Qh[j] = (n0 & kOdd) | ((n1 >> 1) & kEven);
-    Ql[j] = ((n0 << 1) & kOdd) | (n1 & kEven);
-    E[j][0] = ~Ph & ~Pl & V[j];
-    E[j][1] = ~Ph & Pl & V[j];
-    E[j][2] = Ph & ~Pl & V[j];
-    E[j][3] = Ph & Pl & V[j];
-  }
-  int best = 0;
-#pragma unroll
-  for (int a = 0; a < 4; a++) {
-    int ca[4];
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      uint32_t m[5];
-#pragma unroll
-      for (int j = 0; j < 5; j++) {
-        const uint32_t e = E[j][a];
-        m[j] = b == 0 ? (e & ~Qh[j] & ~Ql[j]) : (b == 1 ? (e & ~Qh[j] & Ql[j]) : (b == 2 ? (e & Qh[j] & ~Ql[j]) : e));
-      }
-      if (VARIANT == 0) {
-        ca[b] = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]);
-      } else {  // carry-save: five words -> one "ones" and two "twos" words, three popcounts instead of five
-        const uint32_t s1 = m[0] ^ m[1] ^ m[2], c1 = (m[0] & m[1]) | (m[2] & (m[0] | m[1]));
-        const uint32_t s2 = s1 ^ m[3] ^ m[4], c2 = (s1 & m[3]) | (m[4] & (s1 | m[3]));
-        ca[b] = __popc(s2) + 2 * (__popc(c1) + __popc(c2));
-      }
-    }
-    ca[3] -= ca[0] + ca[1] + ca[2];
-    best = max(best, max(max(ca[0], ca[1]), max(ca[2], ca[3])));
-  }
-  return best;
-}
-
-// the lane's segment as eleven aligned words in registers (base 0 at bit 31 of w[0]); w[10] only ever feeds a masked slot
-__device__ __forceinline__ void lane_load(const uint32_t *__restrict__ seq, const strgpu_segment &sg, uint32_t (&w)[11]) {
-  const uint32_t g = sg.base_off >> 4;
-  const uint32_t sh = 2u * (sg.base_off & 15u);
-  const int n_words = (2 * (int)sg.len + 31) >> 5;
-  uint32_t raw[kLaneWords];
-#pragma unroll
-  for (int j = 0; j < kLaneWords; j++) raw[j] = (j <= n_words) ? __byte_perm(seq[g + j], 0, 0x0123) : 0u;
-#pragma unroll
-  for (int j = 0; j < kLaneWords - 1; j++) w[j] = __funnelshift_l(raw[j + 1], raw[j], sh);
-  w[kLaneWords - 1] = 0u;
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // repeat_prefilter: the pre-filter as a streaming kernel of its own (no shared-memory tables, 64 registers, 32 resident
 // warps per SM, so the HBM latency of the read words is covered by occupancy).  Every segment is read once; segments the
@@ -868,7 +776,7 @@ __device__ __forceinline__ void lane_load(const uint32_t *__restrict__ seq, cons
 // slot with the top slot pair of plane j + 1 shifted in -- one funnel shift.  CSA of the 16 streams are popcounted through
 // carry-save adders (3 POPC + 4 LOP3 instead of 5 POPC): POPC runs on the 16-lane XU pipe, LOP3 on the 64-lane ALU pipe.
 constexpr int kPreThreads = 256;
-constexpr int kPreCsaDefault = 8;
+constexpr int kPreCsaDefault = 6;
 
 __device__ __forceinline__ void prefilter_masks(int L, uint32_t (&V)[5]) {
 #pragma unroll
@@ -880,11 +788,29 @@ __device__ __forceinline__ void prefilter_masks(int L, uint32_t (&V)[5]) {
   }
 }
 
-// returns the largest and the second largest of the 16 occurrence counts
+// Upper bounds s1 >= s2 of the two largest of the sixteen 2-mer occurrence counts c[a][b] (positions 0 .. L - 2).
+// Only NINE of the sixteen cells are counted (a, b < 3) plus three row sums n[a] = occurrences of base a at positions 0 .. L - 2;
+// the other seven follow from the margins of the 4 x 4 table:
+//   n[3]    = (L - 1) - n[0] - n[1] - n[2]                        c[a][3] = n[a] - c[a][0] - c[a][1] - c[a][2]     (exact)
+//   column sum f[b] = occurrences of b at positions 1 .. L - 1 = n[b] - [base 0 == b] + [base L-1 == b], so with
+//   f-[b] = n[b] - [base 0 == b] <= f[b] <= f-[b] + 1:            c[3][b] <= f-[b] + 1 - (c[0][b] + c[1][b] + c[2][b])
+//                                                                 c[3][3] <= n[3] - sum_b (f-[b] - (c[0][b] + c[1][b] + c[2][b]))
+// -- the last four are over-estimates by at most one, which keeps the filter sound (a segment it finishes really has the
+// empty result; at worst a borderline segment more reaches the ladder kernels, which are exact).  12 popcount streams
+// instead of 16 and 45 + 15 mask LOP3 instead of 60 + 20: this kernel is bound by the ALU / popcount pipes.
 // `one` is the runtime constant 1 (a kernel argument): a * one + b compiles to IMAD on the FMA pipe, which is idle here, instead of
-// IADD3 on the ALU pipe, which is the bottleneck (every ALU instruction costs two issue cycles)
+// IADD3 on the ALU pipe, which is the bottleneck (every ALU instruction costs two issue cycles).
+// The top-2 selection runs on packed 16x2 values (VIMNMX.U16x2 / VIMNMX3: half the min/max instructions).
 template <int CSA>
-__device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const uint32_t (&V)[5], int &s1, int &s2, int one) {
+__device__ __forceinline__ int popc5(const uint32_t (&m)[5], int idx, int one) {
+  if (idx >= CSA) return (((__popc(m[0]) * one + __popc(m[1])) * one + __popc(m[2])) * one + __popc(m[3])) * one + __popc(m[4]);
+  const uint32_t x1 = m[0] ^ m[1] ^ m[2], c1 = (m[0] & m[1]) | (m[2] & (m[0] | m[1]));
+  const uint32_t x2 = x1 ^ m[3] ^ m[4], c2 = (x1 & m[3]) | (m[4] & (x1 | m[3]));
+  return (__popc(c1) * one + __popc(c2)) * (one + one) + __popc(x2);
+}
+
+template <int CSA>
+__device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const uint32_t (&V)[5], int n_valid, int &s1, int &s2, int one) {
   uint32_t Dh[6], Dl[6];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
@@ -893,7 +819,7 @@ __device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const ui
   }
   Dh[5] = w[5];        // only its top slot pair is used: base 0 of word 5 (the even bit feeds a slot that is never valid)
   Dl[5] = w[5] << 1;
-  uint32_t E[5][4], Qh[5], Ql[5];
+  uint32_t E[5][3], Qh[5], Ql[5];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
     Qh[j] = __funnelshift_l(Dh[j + 1], Dh[j], 2);
@@ -901,36 +827,55 @@ __device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const ui
     E[j][0] = ~Dh[j] & ~Dl[j] & V[j];
     E[j][1] = ~Dh[j] & Dl[j] & V[j];
     E[j][2] = Dh[j] & ~Dl[j] & V[j];
-    E[j][3] = Dh[j] & Dl[j] & V[j];
   }
-  s1 = 0;
-  s2 = 0;
+  int c[4][4], n[4], col[3];
 #pragma unroll
-  for (int a = 0; a < 4; a++) {
-    int ca[4];
+  for (int a = 0; a < 3; a++) {
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
+    for (int b = 0; b < 3; b++) {
       uint32_t m[5];
 #pragma unroll
       for (int j = 0; j < 5; j++) {
         const uint32_t e = E[j][a];
-        m[j] = b == 0 ? (e & ~Qh[j] & ~Ql[j]) : (b == 1 ? (e & ~Qh[j] & Ql[j]) : (b == 2 ? (e & Qh[j] & ~Ql[j]) : e));
+        m[j] = b == 0 ? (e & ~Qh[j] & ~Ql[j]) : (b == 1 ? (e & ~Qh[j] & Ql[j]) : (e & Qh[j] & ~Ql[j]));
       }
-      if (a * 4 + b >= CSA) {
-        ca[b] = (((__popc(m[0]) * one + __popc(m[1])) * one + __popc(m[2])) * one + __popc(m[3])) * one + __popc(m[4]);
-      } else {
-        const uint32_t x1 = m[0] ^ m[1] ^ m[2], c1 = (m[0] & m[1]) | (m[2] & (m[0] | m[1]));
-        const uint32_t x2 = x1 ^ m[3] ^ m[4], c2 = (x1 & m[3]) | (m[4] & (x1 | m[3]));
-        ca[b] = (__popc(c1) * one + __popc(c2)) * (one + one) + __popc(x2);
-      }
+      c[a][b] = popc5<CSA>(m, a * 4 + b, one);
     }
-    ca[3] = ((ca[0] * one + ca[1]) * one + ca[2]) * (-one) + ca[3];
-    // the two largest of the four, merged into the running pair
-    const int m1 = max(ca[0], ca[1]), n1 = min(ca[0], ca[1]), m2 = max(ca[2], ca[3]), n2 = min(ca[2], ca[3]);
-    const int t1 = max(m1, m2), t2 = max(min(m1, m2), max(n1, n2));
-    s2 = max(min(s1, t1), max(s2, t2));
-    s1 = max(s1, t1);
+    uint32_t m[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) m[j] = E[j][a];
+    n[a] = popc5<CSA>(m, a * 4 + 3, one);
+    c[a][3] = ((c[a][0] * one + c[a][1]) * one + c[a][2]) * (-one) + n[a];
   }
+  n[3] = ((n[0] * one + n[1]) * one + n[2]) * (-one) + n_valid;
+  int rest = n[3];   // becomes the bound of c[3][3]
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    col[b] = (c[0][b] * one + c[1][b]) * one + c[2][b];
+    const int fminus = (int)__umulhi(E[0][b], 2u) * (-one) + n[b];   // n[b] - [base 0 == b]: position 0 is bit 31 of plane 0
+    const int d = col[b] * (-one) + fminus;                           // >= -1
+    c[3][b] = d * one + one;
+    rest = d * (-one) + rest;
+  }
+  c[3][3] = rest;
+  // top two of the sixteen: pack cell i with cell i + 8 (all values are in 0 .. 161), select on both halves at once
+  const int k16 = one << 16;
+  uint32_t P[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) P[i] = (uint32_t)(c[2 + (i >> 2)][i & 3] * k16 + c[i >> 2][i & 3]);
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    hi[i] = __vmaxu2(P[2 * i], P[2 * i + 1]);
+    lo[i] = __vminu2(P[2 * i], P[2 * i + 1]);
+  }
+  // merge (hi, lo) pairs: first = max of the firsts, second = max(min of the firsts, both seconds)
+  const uint32_t a1 = __vmaxu2(hi[0], hi[1]), a2 = __vmaxu2(__vmaxu2(__vminu2(hi[0], hi[1]), lo[0]), lo[1]);
+  const uint32_t b1 = __vmaxu2(hi[2], hi[3]), b2 = __vmaxu2(__vmaxu2(__vminu2(hi[2], hi[3]), lo[2]), lo[3]);
+  const uint32_t t1 = __vmaxu2(a1, b1), t2 = __vmaxu2(__vmaxu2(__vminu2(a1, b1), a2), b2);
+  const int t1l = (int)(t1 & 0xffffu), t1h = (int)__umulhi(t1, 65536u), t2l = (int)(t2 & 0xffffu), t2h = (int)__umulhi(t2, 65536u);
+  s1 = max(t1l, t1h);
+  s2 = max(max(min(t1l, t1h), t2l), t2h);
 }
 
 // ---- TMA plumbing (sm_90+ PTX): one mbarrier per staging buffer, bulk global -> shared copies completing on it
@@ -968,6 +913,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 struct FilterCache {
   uint32_t V[5];
   int len, pclass;
+  int nv;     // valid 2-mer start positions: max(L - 1, 0)
   int r[5];   // (int(L * p / k) + 1) * (k - 1), k = 2..6
 };
 // ALL_WORDS: all eleven words may be read whatever L is (staging buffer; words past the segment only feed masked slots)
@@ -996,35 +942,61 @@ __device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh,
     fc.r[4] = (int)(t.z & 0xffffu);
     fc.len = L;
     fc.pclass = pclass;
+    fc.nv = L > 0 ? L - 1 : 0;
   }
   int s1, s2;
-  prefilter_top2<CSA>(w, fc.V, s1, s2, one);
+  prefilter_top2<CSA>(w, fc.V, fc.nv, s1, s2, one);
   return s1 >= fc.r[0] || s1 + s2 >= fc.r[1] || s1 + 2 * s2 >= fc.r[2] || s1 + 3 * s2 >= fc.r[3] || s1 + 4 * s2 >= fc.r[4];
 }
 
-// Appends the kept segments of this warp's group to the survivor list (one atomic per warp and class).  The list has two
-// ends: list[0] long segments (>= kLongLen bases, and everything bound for the warp path) filling list[kListHdr ..] upwards,
-// list[1] short segments filling list[2 + cap - 1 ..] downwards, so that the scan kernel's batches of 32 hold segments of
-// similar length (its per-lane loops run for the longest lane of a warp).
+// Device scratch of one library call (uint32 words; sized by scan_scratch_words()):
+//   hdr[0] long lane-path survivors, hdr[1] short ones, hdr[2] warp-path segments,
+//   hdr[3 + i] entries appended to stage list i (R3, C4, R4, C5, R5, C6, R6), hdr[10 + j] group cursor of ladder kernel j
+//   listA[n_seg]  lane-path survivors of the pre-filter, two-ended: long segments (>= kLongLen bases) fill it upwards from 0,
+//                 short ones downwards from n_seg - 1, so that the groups of 32 a warp takes hold segments of similar length
+//   listW[n_seg]  segments for the warp-per-segment kernel: non-ACGT bases, more than 160 bases, stage-list overflow
+//   7 stage lists of `cap` entries each, structure of arrays: segment index, packed ScanState, M | leader << 8
+struct StageLists {
+  uint32_t *hdr, *listA, *listW, *stage;
+  uint32_t cap, n_seg;
+};
 constexpr int kLongLen = 96;
-constexpr uint32_t kListHdr = 4;   // list[0] long count, list[1] short count, list[2] next group to hand out (scan kernel), list[3] unused
-__device__ __forceinline__ void survivors_push(uint32_t *__restrict__ list, uint32_t cap, bool keep, bool is_short, uint32_t s, int lane) {
-  const uint32_t km = __ballot_sync(kFull, keep);
-  if (km == 0u) return;
-  const uint32_t sm = __ballot_sync(kFull, keep && is_short);
+enum { kListR3 = 0, kListC4, kListR4, kListC5, kListR5, kListC6, kListR6, kNumStageLists };
+static_assert(kNumStageLists == kScanStageLists, "stage list count");
+
+__device__ __forceinline__ StageLists stage_lists(uint32_t *scratch, uint32_t n_seg, uint32_t cap) {
+  StageLists sl;
+  sl.hdr = scratch;
+  sl.listA = scratch + kScanScratchHdr;
+  sl.listW = sl.listA + n_seg;
+  sl.stage = sl.listW + n_seg;
+  sl.cap = cap;
+  sl.n_seg = n_seg;
+  return sl;
+}
+
+// the pre-filter's survivors (one atomic per warp and list)
+__device__ __forceinline__ void survivors_push(const StageLists &sl, bool keep_lane, bool is_short, bool keep_warp, uint32_t s, int lane) {
+  const uint32_t km = __ballot_sync(kFull, keep_lane);
+  const uint32_t wm = __ballot_sync(kFull, keep_warp);
+  if ((km | wm) == 0u) return;
+  const uint32_t sm = __ballot_sync(kFull, keep_lane && is_short);
   const uint32_t lm = km & ~sm;
   const uint32_t below = (1u << lane) - 1u;
-  uint32_t base_l = 0, base_s = 0;
+  uint32_t base_l = 0, base_s = 0, base_w = 0;
   if (lane == 0) {
-    if (lm) base_l = atomicAdd(list, (uint32_t)__popc(lm));
-    if (sm) base_s = atomicAdd(list + 1, (uint32_t)__popc(sm));
+    if (lm) base_l = atomicAdd(sl.hdr, (uint32_t)__popc(lm));
+    if (sm) base_s = atomicAdd(sl.hdr + 1, (uint32_t)__popc(sm));
+    if (wm) base_w = atomicAdd(sl.hdr + 2, (uint32_t)__popc(wm));
   }
   base_l = __shfl_sync(kFull, base_l, 0);
   base_s = __shfl_sync(kFull, base_s, 0);
-  if (keep) {
-    if (is_short) list[kListHdr + cap - 1u - (base_s + __popc(sm & below))] = s;
-    else list[kListHdr + base_l + __popc(lm & below)] = s;
+  base_w = __shfl_sync(kFull, base_w, 0);
+  if (keep_lane) {
+    if (is_short) sl.listA[sl.n_seg - 1u - (base_s + __popc(sm & below))] = s;
+    else sl.listA[base_l + __popc(lm & below)] = s;
   }
+  if (keep_warp) sl.listW[base_w + __popc(wm & below)] = s;
 }
 
 // Staging: a group of 32 uniform reads is one contiguous span of 8 * stride bytes.  Lane 0 of the warp that owns the group
@@ -1039,12 +1011,13 @@ template <int CSA, int STAGES>
 __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
                                                                    const strgpu_segment *__restrict__ segs, uint32_t n_seg,
                                                                    const UniformReads u, const uint16_t *__restrict__ thr,
-                                                                   strgpu_repeat *__restrict__ out, uint32_t *__restrict__ list,
-                                                                   uint32_t n_tma_groups, int one) {
+                                                                   strgpu_repeat *__restrict__ out, uint32_t *__restrict__ scratch,
+                                                                   uint32_t stage_cap, uint32_t n_tma_groups, int one) {
   __shared__ __align__(128) unsigned char stage_buf[kPreWarps][STAGES][kStageBytes];
   __shared__ __align__(8) uint64_t stage_bar[kPreWarps][STAGES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint16_t *tfilt = thr + kThrFiltOff;
+  const StageLists sl = stage_lists(scratch, n_seg, stage_cap);
   const uint32_t warps_total = gridDim.x * kPreWarps;
   const uint32_t warp_global = blockIdx.x * kPreWarps + warp;
   FilterCache fc;
@@ -1107,7 +1080,7 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
         keep = prefilter_keep<CSA, true>(src, 8u * (lane_byte & 3u), L, pclass, tfilt, fc, one, stride_aligned);
         if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
       }
-      survivors_push(list, n_seg, keep, !has_n && L < kLongLen, s, lane);
+      survivors_push(sl, keep && !has_n, L < kLongLen, has_n, s, lane);
       __syncwarp();   // every lane has read this buffer before the next iteration refills it
       g += warps_total;
       b = b + 1 == STAGES ? 0 : b + 1;
@@ -1130,236 +1103,215 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
       keep = prefilter_keep<CSA, false>(seq + (sg.base_off >> 4), 2u * (sg.base_off & 15u), L, pclass, tfilt, fc, one, false);
       if (!keep) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;
     }
-    survivors_push(list, n_seg, keep, lane_path && L < kLongLen, s, lane);
+    survivors_push(sl, keep && lane_path, L < kLongLen, active && !lane_path, s, lane);
   }
 }
 
-template <int FILTER, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == kLaneWarps ? 1 : 2) repeat_scan_lane(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
-                                                                    const strgpu_segment *__restrict__ segs, uint32_t n_seg,
-                                                                    const UniformReads u,
-                                                                    const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts,
-                                                                    strgpu_repeat *__restrict__ out, int *status,
-                                                                    uint32_t *__restrict__ list) {
-  // list == nullptr: every segment of the batch; else the two-ended survivor list of repeat_prefilter (survivors_push):
-  // groups of 32 long segments first, then groups of 32 short ones
+// ------------------------------------------------------------------------------------------------------------------
+// The ladder for the pre-filter's survivors (utils.nim:242-265), one LANE per segment, one kernel per rung:
+//   ladder_stage<2>  counts k = 2 and 3, decides the k = 2 rung (every lane recounts: best is still -1) and the k = 3
+//                    rung when it needs no recount; appends to R3 (k = 3 recount pending) or C4
+//   ladder_stage<K>  K = 4, 5, 6: first the entries of R(K-1) -- the pending recount read.count(s) of rung K - 1
+//                    (utils.nim:254) and that rung's decision --, then, for them and for the entries of C(K), the count of
+//                    rung K; appends to R(K) (recount pending) or C(K+1), or stores the result
+//   ladder_stage<7>  the pending k = 6 recounts; stores the result
+// Every kernel works on a DENSE list: all 32 lanes of a warp run the same rung (the recount lists are kept apart from the
+// count lists, and a group of 32 never mixes the two), so there is no divergent work and no partially filled batch except
+// the last group of a list.  Each kernel only carries the shared memory its own tables need (45 / 29 / 63 / 63 / 21 words
+// per lane), which is what lets 24-32 warps share an SM.  State travels between the kernels as 12-byte list entries in
+// HBM / L2.  A list that overflows its capacity spills the segment to listW: the warp-per-segment kernel, which runs last,
+// redoes it from rung 2.
+constexpr int kStageThreads = 256;
+constexpr int kStageWarps = kStageThreads / 32;
+template <int K> struct StageCfg;
+template <> struct StageCfg<2> { static constexpr int tab = kCls2 + kCls3, list_r = -1, list_c = -1, out_r = kListR3, out_c = kListC4, cursor = 0; };
+template <> struct StageCfg<4> { static constexpr int tab = kCls4Words, list_r = kListR3, list_c = kListC4, out_r = kListR4, out_c = kListC5, cursor = 1; };
+template <> struct StageCfg<5> { static constexpr int tab = kTabWords, list_r = kListR4, list_c = kListC5, out_r = kListR5, out_c = kListC6, cursor = 2; };
+template <> struct StageCfg<6> { static constexpr int tab = kTabWords, list_r = kListR5, list_c = kListC6, out_r = kListR6, out_c = -1, cursor = 3; };
+template <> struct StageCfg<7> { static constexpr int tab = 10, list_r = kListR6, list_c = -1, out_r = -1, out_c = -1, cursor = 4; };
+template <int K> struct StageSize {
+  static constexpr int warp_words = (StageCfg<K>::tab + kLaneWords) * 32;
+  static constexpr int smem_bytes = kStageWarps * warp_words * 4 + kLutTotal * 2 + 16;
+};
+
+__device__ __forceinline__ uint32_t pack_state(const ScanState &st) {
+  // written after the k = 2 rung: 0 <= best <= 160, repeat_count <= 80
+  return ((uint32_t)(st.best & 0xff) << 24) | ((uint32_t)(st.rc & 0xff) << 16) | ((uint32_t)st.unit_k << 12) | (st.unit_code & 0xfffu);
+}
+__device__ __forceinline__ ScanState unpack_state(uint32_t a) {
+  ScanState st;
+  st.best = (int)(a >> 24);
+  st.rc = (int)((a >> 16) & 0xffu);
+  st.unit_k = (int)((a >> 12) & 0xfu);
+  st.unit_code = a & 0xfffu;
+  return st;
+}
+
+// warp-aggregated append to stage list `which` (every lane of the warp calls this)
+__device__ __forceinline__ void stage_push(const StageLists &sl, int which, bool want, int lane, uint32_t s, uint32_t st, uint32_t extra) {
+  const uint32_t m = __ballot_sync(kFull, want);
+  if (m == 0u) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(sl.hdr + 3 + which, (uint32_t)__popc(m));
+  base = __shfl_sync(kFull, base, 0);
+  if (want) {
+    const uint32_t i = base + __popc(m & ((1u << lane) - 1u));
+    if (i < sl.cap) {
+      uint32_t *q = sl.stage + (size_t)which * 3u * sl.cap;
+      q[i] = s;
+      q[sl.cap + i] = st;
+      q[2u * sl.cap + i] = extra;
+    } else {
+      sl.listW[atomicAdd(sl.hdr + 2, 1u)] = s;   // no room: the warp kernel redoes this segment from rung 2
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kStageThreads, (K == 5 || K == 6) ? 3 : 4)
+ladder_stage(const uint32_t *__restrict__ seq, const strgpu_segment *__restrict__ segs, const UniformReads u,
+             const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts, strgpu_repeat *__restrict__ out,
+             uint32_t *__restrict__ scratch, uint32_t n_seg, uint32_t stage_cap) {
+  using Cfg = StageCfg<K>;
   extern __shared__ __align__(16) uint32_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t n_long = list ? list[0] : n_seg, n_short = list ? list[1] : 0u;
-  const uint32_t groups_long = (n_long + 31) / 32;
-  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + WARPS * kWarpSmemWords);
-  for (int i = tid; i < kLutTotal; i += WARPS * 32) lut[i] = luts[i];
-  __syncthreads();
-  uint32_t *warp_base = smem + warp * kWarpSmemWords;
-  uint32_t *tab = warp_base + lane;                      // [class][lane] counters; warp scratch for the warp path
-  uint32_t *rd = warp_base + kTabWords * 32 + lane;      // [word][lane] read columns
-  uint32_t *qmem = warp_base + kTabWords * 32 + kLaneWords * 32;
-  uint32_t *q2 = qmem + kQ2Off, *q3 = qmem + kQ3Off, *q4 = qmem + kQ4Off, *q5 = qmem + kQ5Off, *q6 = qmem + kQ6Off, *qw = qmem + kQWOff;
-  int n2 = 0, n3 = 0, n4 = 0, n5 = 0, n6 = 0;
-  const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
-  const uint16_t *tmin = thr + kThrMinOff;
-  const uint32_t n_groups = groups_long + (n_short + 31) / 32;
-  const uint32_t warps_total = gridDim.x * WARPS;
-  // groups are handed out dynamically when they come from the survivor list (their cost varies a lot: a warp takes the
-  // next group whenever its queues run low), statically otherwise
-  uint32_t *next_group = list ? list + 2 : nullptr;
-  uint32_t grp = blockIdx.x * WARPS + warp;
-  if (next_group) {
-    if (lane == 0) grp = atomicAdd(next_group, 1u);
-    grp = __shfl_sync(kFull, grp, 0);
+  const StageLists sl = stage_lists(scratch, n_seg, stage_cap);
+  uint32_t n_r, n_c;   // entries of the first / second input list
+  if (K == 2) {
+    n_r = sl.hdr[0];   // long survivors
+    n_c = sl.hdr[1];   // short survivors
+  } else {
+    n_r = min(sl.hdr[3 + Cfg::list_r], sl.cap);
+    n_c = Cfg::list_c >= 0 ? min(sl.hdr[3 + (Cfg::list_c >= 0 ? Cfg::list_c : 0)], sl.cap) : 0u;
   }
-  uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
-  int v_len = -1;
-  // Stages: 1 new segments (pre-filter when fused) -> Q2; 2 counts k = 2, 3 and decides the k = 2 rung; 4, 5, 6 count k = 4, 5, 6;
-  // R = every recount a rung k >= 3 needs (read.count(s), utils.nim:254) followed by that rung's decision: lanes that need one are
-  // pushed to QR (q3) with their k, M and leader instead of recounting divergently inside the counting stage, so recounts run 32
-  // lanes wide.  All queues hold <= 64 entries; a stage pops <= 32 and pushes <= 32 into any queue downstream of it, and runs only
-  // when those queues have room for a full batch -- except that a counting stage whose recount queue is full recounts in place
-  // (the pre-v7 behaviour), which is what makes the schedule deadlock free.  Downstream stages are served first; new segments are
-  // taken only when no queue holds a full batch; at the end the queues are drained upstream-first.
+  const uint32_t groups_r = (n_r + 31u) / 32u, n_groups = groups_r + (n_c + 31u) / 32u;
+  if (blockIdx.x * kStageWarps >= n_groups) return;   // nothing for this CTA (the grid is sized for the worst case)
+  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kStageWarps * StageSize<K>::warp_words);
+  if (K != 6 && K != 7) {
+    for (int i = tid; i < kLutTotal; i += kStageThreads) lut[i] = luts[i];
+    __syncthreads();
+  }
+  uint32_t *warp_base = smem + warp * StageSize<K>::warp_words;
+  uint32_t *scr = warp_base + lane;                                   // [word][lane]: recount scratch, counter column
+  uint32_t *tab = K == 4 ? scr - (kCls2 + kCls3) * 32 : scr;          // the 4-mer LUT addresses words 34..51 of a full column
+  uint32_t *rd = warp_base + Cfg::tab * 32 + lane;                   // [word][lane] read column
+  const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
+  uint32_t *cursor = sl.hdr + 10 + Cfg::cursor;
+  const uint32_t *q_r = Cfg::list_r >= 0 ? sl.stage + (size_t)(Cfg::list_r >= 0 ? Cfg::list_r : 0) * 3u * sl.cap : nullptr;
+  const uint32_t *q_c = Cfg::list_c >= 0 ? sl.stage + (size_t)(Cfg::list_c >= 0 ? Cfg::list_c : 0) * 3u * sl.cap : nullptr;
+
   while (true) {
-    const bool more = grp < n_groups;
-    const bool r_ok = n4 <= 32 && n5 <= 32 && n6 <= 32;   // stage R pushes into Q4 / Q5 / Q6
-    int stage;
-    if (n3 >= 32 && r_ok) stage = 3;       // keep the recount queue below a full batch so that counting stages can defer into it
-    else if (n6 >= 32) stage = 6;
-    else if (n5 >= 32) stage = 5;
-    else if (n4 >= 32) stage = 4;
-    else if (n2 >= 32) stage = 2;
-    else if (more) stage = 1;
-    else if (n2 > 0) stage = 2;
-    else if (n3 > 0 && r_ok) stage = 3;
-    else if (n4 > 0) stage = 4;
-    else if (n5 > 0) stage = 5;
-    else if (n6 > 0) stage = 6;
-    else break;
-
-    if (stage == 1) {
-      // ---- stage 1: new segments, 32 per pass: the 2-mer pre-filter finishes most of them; survivors go to Q2
-      do {
-        const bool in_long = grp < groups_long;
-        const uint32_t item = (in_long ? grp : grp - groups_long) * 32 + lane;
-        if (next_group) {
-          uint32_t g = 0;
-          if (lane == 0) g = atomicAdd(next_group, 1u);
-          grp = __shfl_sync(kFull, g, 0);
-        } else {
-          grp += warps_total;
-        }
-        const bool active = item < (in_long ? n_long : n_short);
-        const uint32_t s = (list && active) ? (in_long ? list[kListHdr + item] : list[kListHdr + n_seg - 1u - item]) : item;
-        strgpu_segment sg{0, 0, 0, 0};
-        if (active) sg = load_segment(segs, nmask, u, s);
-        const int L = sg.len;
-        const bool lane_path = active && L <= kShortMaxLen && !(sg.flags & STRGPU_SEG_HAS_N);
-        bool survive = lane_path;
-        if (lane_path && FILTER >= 0) {
-          uint32_t w[kLaneWords];
-          lane_load(seq, sg, w);
-          if (L != v_len) {
-            filter_masks(L, V);
-            v_len = L;
-          }
-          const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-          survive = lane_filter_max2<(FILTER > 0 ? 1 : 0)>(w, V) > (int)tmin[pclass * kThrLen + L];
-          if (!survive) reinterpret_cast<unsigned long long *>(out)[s] = 0ull;   // empty unit, repeat_count 0
-        }
-        queue_push<1>(q2, n2, survive, lane, s, ScanState{0, 0u, 0, 0}, 0);
-        // segments with non-ACGT bases or longer than 160 bases: one at a time on the whole warp
-        const uint32_t wm = __ballot_sync(kFull, active && !lane_path);
-        if (wm != 0u) {
-          if (active && !lane_path) qw[__popc(wm & ((1u << lane) - 1u))] = s;
-          const int nw = __popc(wm);
-          WarpScratch<512> &ws = *reinterpret_cast<WarpScratch<512> *>(warp_base);
-          for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
-          __syncwarp();
-          for (int e = 0; e < nw; e++) {
-            const uint32_t ws_s = qw[e];
-            warp_scan_compact(ws, seq, nmask, load_segment(segs, nmask, u, ws_s), ws_s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
-          }
-          __syncwarp();
-        }
-      } while (grp < n_groups && n2 < 32);
-      continue;
-    }
-
-    if (stage == 2) {
-      // ---- stage 2: count k = 2 and 3; the k = 2 rung (every lane recounts: best is still -1); the k = 3 rung if it needs no recount
-      const int nb = n2 < 32 ? n2 : 32;
-      const int first = n2 - nb;
-      uint32_t s = 0, extra = 0;
-      ScanState st{-1, 0u, 0, 0};
-      int next_k = 0;  // 0: finished, 3: needs the k = 3 recount (QR), 4: goes on to k = 4
-      if (lane < nb) {
-        s = q2[first + lane];
-        const strgpu_segment sg = load_segment(segs, nmask, u, s);
-        const int L = sg.len;
-        lane_stage(seq, sg, rd);
-        uint32_t best2, best3;
-        lane_count23(rd, tab, lut, L, best2, best3);
-        const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-        const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
-        const int M2 = (int)(best2 >> 13), M3 = (int)(best3 >> 13);
-        const uint32_t lead2 = M2 ? (uint32_t)lut[kRev234 + (best2 & 31u)] : 0xfu;
-        const uint32_t lead3 = M3 ? (uint32_t)lut[kRev234 + kCls2 + (best3 & 31u)] : 0x3fu;
-        extra = (uint32_t)M3 | (lead3 << 8) | (3u << 20);
-        const bool wide = __any_sync(nb == 32 ? kFull : ((1u << nb) - 1u), L > 64);
-        bool go = lane_decide(rd, tab, L, 2, M2, lead2, tp[0], tg[L], st, wide);
-        if (go) {
-          if (3 * M3 > st.best) next_k = 3;                       // needs the k = 3 recount
-          else go = !(M3 < (int)tg[kThrLen + L]);
-        }
-        if (go && next_k == 0) next_k = 4;
-        if (!go) emit_result(out, s, st);
-      }
-      __syncwarp();
-      n2 = first;
-      queue_push<3>(q3, n3, next_k == 3, lane, s, st, extra);
-      queue_push<2>(q4, n4, next_k == 4, lane, s, st, 0);
-      continue;
-    }
-
-    if (stage == 3) {
-      // ---- stage R: recounts of any rung k = 3..6, 32 lanes wide; then the rung's decision (utils.nim:254-265)
-      const int nb = n3 < 32 ? n3 : 32;
-      const int first = n3 - nb;
-      uint32_t s = 0, extra = 0;
-      ScanState st{-1, 0u, 0, 0};
-      int k = 0;
-      if (lane < nb) {
-        queue_read<3>(q3, first + lane, s, st, extra);
-        k = (int)(extra >> 20);
-        const uint32_t leader = (extra >> 8) & 0xfffu;
-        const strgpu_segment sg = load_segment(segs, nmask, u, s);
-        const int L = sg.len;
-        lane_stage(seq, sg, rd);
-        const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-        const uint32_t magic = 65536u / (uint32_t)k + 1u;
-        const bool wide = __any_sync(nb == 32 ? kFull : ((1u << nb) - 1u), L > 64);
-        const int c = wide ? lane_recount<10>(rd, tab, L, leader, k, magic) : lane_recount<4>(rd, tab, L, leader, k, magic);
-        const int score = c * k;
-        if (score >= st.best) {
-          st.best = score;
-          if (c > (int)thr[(size_t)(pclass * 5 + k - 2) * kThrLen + L]) {
-            st.unit_code = leader;
-            st.unit_k = k;
-            st.rc = c;
-          }
-        }
-        if (k == 6) emit_result(out, s, st);
-      }
-      __syncwarp();
-      n3 = first;
-      queue_push<2>(q4, n4, k == 3, lane, s, st, 0);
-      queue_push<2>(q5, n5, k == 4, lane, s, st, 0);
-      queue_push<2>(q6, n6, k == 5, lane, s, st, 0);
-      continue;
-    }
-
-    // ---- counting stages k = 4, 5, 6: 32 segments at a time, one per lane
-    const int qn = stage == 4 ? n4 : (stage == 5 ? n5 : n6);
-    const int nb = qn < 32 ? qn : 32;
-    const int first = qn - nb;
-    const bool defer = n3 <= 32;            // room for a full batch in the recount queue; else recount in place
+    uint32_t grp = 0;
+    if (lane == 0) grp = atomicAdd(cursor, 1u);
+    grp = __shfl_sync(kFull, grp, 0);
+    if (grp >= n_groups) break;
+    const bool first_list = grp < groups_r;                            // warp-uniform
+    const uint32_t item = (first_list ? grp : grp - groups_r) * 32u + (uint32_t)lane;
+    const bool active = item < (first_list ? n_r : n_c);
+    const uint32_t act_mask = __ballot_sync(kFull, active);
     uint32_t s = 0, extra = 0;
     ScanState st{-1, 0u, 0, 0};
-    int what = 0;                           // 0: finished (emitted), 1: next counting stage, 2: recount queue
-    if (lane < nb) {
-      queue_read<2>(stage == 4 ? q4 : (stage == 5 ? q5 : q6), first + lane, s, st, extra);
-      const strgpu_segment sg = load_segment(segs, nmask, u, s);
+    int what = 0;   // 0: finished, 1: next count list, 2: recount list
+    if (active) {
+      if (K == 2) {
+        s = first_list ? sl.listA[item] : sl.listA[n_seg - 1u - item];
+      } else {
+        const uint32_t *q = first_list ? q_r : q_c;
+        s = q[item];
+        st = unpack_state(q[sl.cap + item]);
+        extra = q[2u * sl.cap + item];
+      }
+      const strgpu_segment sg = load_segment(segs, nullptr, u, s);    // lane-path segments hold no non-ACGT base
       const int L = sg.len;
       lane_stage(seq, sg, rd);
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
-      int M;
-      uint32_t leader;
-      if (stage == 4) lane_count4(rd, tab, lut, L, M, leader);
-      else if (stage == 5) lane_count5(rd, tab, lut, L, M, leader);
-      else lane_count6(rd, tab, L, M, leader);
-      if (M * stage <= st.best) {           // no recount: break or continue (utils.nim:250-253)
-        what = (M < (int)tg[(stage - 2) * kThrLen + L]) ? 0 : 1;
-      } else if (defer) {
-        what = 2;
-        extra = (uint32_t)M | (leader << 8) | ((uint32_t)stage << 20);
+      const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
+      const bool wide = __any_sync(act_mask, L > 64);
+      if (K == 2) {
+        uint32_t best2, best3;
+        lane_count23(rd, tab, lut, L, best2, best3);
+        const int M2 = (int)(best2 >> 13), M3 = (int)(best3 >> 13);
+        const uint32_t lead2 = M2 ? (uint32_t)lut[kRev234 + (best2 & 31u)] : 0xfu;
+        const uint32_t lead3 = M3 ? (uint32_t)lut[kRev234 + kCls2 + (best3 & 31u)] : 0x3fu;
+        bool go = lane_decide(rd, scr, L, 2, M2, lead2, tp[0], tg[L], st, wide);
+        if (go) {
+          if (3 * M3 > st.best) {                        // the k = 3 rung needs its recount
+            what = 2;
+            extra = (uint32_t)M3 | (lead3 << 8);
+          } else {
+            what = (M3 < (int)tg[kThrLen + L]) ? 0 : 1;   // break / continue (utils.nim:250-253)
+          }
+        }
       } else {
-        lane_decide(rd, tab, L, stage, M, leader, thr[(size_t)(pclass * 5 + stage - 2) * kThrLen + L], tg[(stage - 2) * kThrLen + L], st, L > 64);
-        what = 1;
+        if (Cfg::list_r >= 0 && first_list) {
+          // the recount rung K - 1 was waiting for (utils.nim:254-262)
+          constexpr int KR = K - 1;
+          const uint32_t leader = (extra >> 8) & 0xfffu;
+          const uint32_t magic = 65536u / (uint32_t)KR + 1u;
+          const int c = wide ? lane_recount<10>(rd, scr, L, leader, KR, magic) : lane_recount<4>(rd, scr, L, leader, KR, magic);
+          const int score = c * KR;
+          if (score >= st.best) {
+            st.best = score;
+            if (c > (int)tp[(KR - 2) * kThrLen]) {
+              st.unit_code = leader;
+              st.unit_k = KR;
+              st.rc = c;
+            }
+          }
+        }
+        if (K <= 6) {
+          int M;
+          uint32_t leader;
+          if (K == 4) lane_count4(rd, tab, lut, L, M, leader);
+          else if (K == 5) lane_count5(rd, tab, lut, L, M, leader);
+          else lane_count6(rd, tab, L, M, leader);
+          if (M * K <= st.best) {                         // no recount: break or continue (utils.nim:250-253)
+            what = (M < (int)tg[(K - 2) * kThrLen + L]) ? 0 : 1;
+          } else {
+            what = 2;
+            extra = (uint32_t)M | (leader << 8);
+          }
+          if (K == 6 && what == 1) what = 0;              // the ladder ends after k = 6
+        }
       }
-      if (what == 0 || (what == 1 && stage == 6)) {
-        emit_result(out, s, st);
-        what = 0;
-      }
+      if (what == 0) emit_result(out, s, st);
     }
     __syncwarp();
-    if (stage == 4) { n4 = first; queue_push<2>(q5, n5, what == 1, lane, s, st, 0); }
-    else if (stage == 5) { n5 = first; queue_push<2>(q6, n6, what == 1, lane, s, st, 0); }
-    else n6 = first;
-    queue_push<3>(q3, n3, what == 2, lane, s, st, extra);
+    const uint32_t packed = pack_state(st);
+    if (Cfg::out_r >= 0) stage_push(sl, Cfg::out_r >= 0 ? Cfg::out_r : 0, what == 2, lane, s, packed, extra);
+    if (Cfg::out_c >= 0) stage_push(sl, Cfg::out_c >= 0 ? Cfg::out_c : 0, what == 1, lane, s, packed, 0u);
+  }
+}
+
+// the segments of listW (non-ACGT bases, more than 160 bases, stage-list overflow): one warp per segment, from rung 2
+__global__ void __launch_bounds__(kStageThreads) ladder_warp_list(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ nmask,
+                                                                  const uint32_t *__restrict__ xmask,
+                                                                  const strgpu_segment *__restrict__ segs, const UniformReads u,
+                                                                  const uint16_t *__restrict__ thr, strgpu_repeat *__restrict__ out,
+                                                                  int *status, uint32_t *__restrict__ scratch, uint32_t n_seg,
+                                                                  uint32_t stage_cap) {
+  __shared__ WarpScratch<512> scratch_w[kStageWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const StageLists sl = stage_lists(scratch, n_seg, stage_cap);
+  const uint32_t n = min(sl.hdr[2], n_seg);
+  if (blockIdx.x * kStageWarps >= n) return;
+  WarpScratch<512> &ws = scratch_w[warp];
+  for (int i = lane; i < WarpScratch<512>::kTab / 4; i += 32) reinterpret_cast<uint32_t *>(ws.tab)[i] = 0;
+  __syncwarp();
+  uint32_t *cursor = sl.hdr + 10 + 5;
+  while (true) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(cursor, 1u);
+    i = __shfl_sync(kFull, i, 0);
+    if (i >= n) break;
+    const uint32_t s = sl.listW[i];
+    warp_scan_compact(ws, seq, nmask, xmask, load_segment(segs, nmask, u, s), s, thr, lane, 2, ScanState{-1, 0u, 0, 0}, out, status);
   }
 }
 
 }  // namespace
 
-// Class LUTs of the lane kernel (uint16 each, kLutTotal entries):
+// Class LUTs of the lane kernels (uint16 each, kLutTotal entries):
 //   [kLut2, kLut3)         byte offset of the uint32 counter of every 2/3-mer code's min-rotation class in the lane's column,
 //   [kLut4)                for 4-mer codes: word byte offset | bit shift of the class's packed uint8 counter,
 //   [kRev234)              canonical (minimal) code of each of the 10 + 24 + 70 classes,
@@ -1393,10 +1345,48 @@ void build_lane_luts(uint16_t *dst) {
   }
 }
 
-cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
-                               uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
-                               strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,
-                               const UniformReads *uniform, uint32_t *d_list) {
+uint32_t scan_stage_cap(uint32_t n_seg) {
+  uint64_t cap = (uint64_t)n_seg / 8u;
+  if (cap < 4096u) cap = 4096u;
+  return (uint32_t)((cap + 31u) & ~(uint64_t)31u);
+}
+
+size_t scan_scratch_words(uint32_t n_seg) {
+  return (size_t)kScanScratchHdr + 2u * (size_t)n_seg + (size_t)kScanStageLists * 3u * scan_stage_cap(n_seg) + 4u;
+}
+
+namespace {
+std::once_flag g_attr_once[64];
+cudaError_t g_attr_err[64];
+
+template <typename Kern>
+cudaError_t set_smem(Kern kern, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
+// function attributes are per device: set once per device, whichever host thread comes first
+cudaError_t configure_device(int dev) {
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::call_once(g_attr_once[dev], [dev]() {
+    cudaError_t e = set_smem(ladder_stage<2>, StageSize<2>::smem_bytes);
+    if (e == cudaSuccess) e = set_smem(ladder_stage<4>, StageSize<4>::smem_bytes);
+    if (e == cudaSuccess) e = set_smem(ladder_stage<5>, StageSize<5>::smem_bytes);
+    if (e == cudaSuccess) e = set_smem(ladder_stage<6>, StageSize<6>::smem_bytes);
+    if (e == cudaSuccess) e = set_smem(ladder_stage<7>, StageSize<7>::smem_bytes);
+    g_attr_err[dev] = e;
+  });
+  return g_attr_err[dev];
+}
+}  // namespace
+
+int scan_launches(uint32_t max_len, int variant) { return (max_len <= (uint32_t)kShortMaxLen && variant != 1) ? 7 : 1; }
+
+cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const uint32_t *d_xmask,
+                               const strgpu_segment *d_segs, uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr,
+                               const uint16_t *d_luts, strgpu_repeat *d_out, int *d_status, int sm_count, int variant,
+                               cudaStream_t stream, const UniformReads *uniform, uint32_t *d_scratch) {
   if (n_seg == 0) return cudaSuccess;
   UniformReads u{0, 0, 0, 0};
   if (uniform) {
@@ -1404,66 +1394,52 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
     if (u.read_len > (uint32_t)kShortMaxLen) return cudaErrorInvalidValue;  // callers expand long uniform reads into descriptors
     if (variant == 1) variant = 0;
   }
-  if (variant < 0 || variant > 7) variant = 0;
-  if (d_list == nullptr && (variant == 0 || variant >= 5)) variant = 2;   // no survivor list: fused kernel
   constexpr int kWarps = 8;
   const uint32_t blocks_needed = (n_seg + kWarps - 1) / kWarps;
-  if (max_len <= (uint32_t)kShortMaxLen && variant != 1) {
-    // 0: repeat_prefilter + repeat_scan_lane over its survivor list (5..7: the same with 0 / 12 / 16 carry-save streams);
-    // 2 / 4: one fused kernel (plain / carry-save popcounts); 3: no pre-filter (A/B runs)
-    const bool split = variant == 0 || variant >= 5;
-    // (A geometry that lets batch i's scan kernel share the SMs with batch i + 1's pre-filter -- 12-warp scan CTAs next to 2 pre-filter
-    // CTAs -- was measured and is slower than letting whole kernels of two streams interleave: 2.22e10 vs 2.54e10 reads/s.)
-    auto kernel = variant == 2 ? repeat_scan_lane<0, kLaneWarps> : (variant == 4 ? repeat_scan_lane<1, kLaneWarps> : repeat_scan_lane<-1, kLaneWarps>);
-    const int lane_warps = kLaneWarps;
-    const int lane_smem = lane_smem_bytes(lane_warps);
-    // function attributes are per device: remember which (device, variant) pairs have been configured
-    static bool configured[64][8] = {{false}};
+  if (max_len <= (uint32_t)kShortMaxLen && variant != 1 && d_scratch != nullptr) {
+    // variants (A/B runs and tests): 0 default; 5 / 7: 0 / 12 of the 12 popcount streams through carry-save adders;
+    // 8: stage lists of 64 entries (forces the overflow path)
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (!configured[dev][variant]) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      if (e != cudaSuccess) return e;
-      configured[dev][variant] = true;
-    }
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    cudaError_t e = configure_device(dev);
+    if (e != cudaSuccess) return e;
+    const uint32_t cap = variant == 8 ? 64u : scan_stage_cap(n_seg);
+    e = cudaMemsetAsync(d_scratch, 0, kScanScratchHdr * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
     static const bool no_tma = getenv("STRGPU_NO_TMA") != nullptr;   // A/B: per-lane loads for uniform reads too
-    if (split) {
-      cudaError_t e = cudaMemsetAsync(d_list, 0, 4 * sizeof(uint32_t), stream);
-      if (e != cudaSuccess) return e;
-      const uint32_t groups = (n_seg + 31) / 32;
-      uint32_t pre_grid = (uint32_t)sm_count * 4u;   // 4 resident CTAs of 8 warps per SM, grid-stride over groups of 32
-      const uint32_t pre_need = (groups + kPreThreads / 32 - 1) / (kPreThreads / 32);
-      if (pre_grid > pre_need) pre_grid = pre_need;
-      static const int stages = getenv("STRGPU_STAGES") ? atoi(getenv("STRGPU_STAGES")) : 4;   // A/B: staging depth
-      auto pre = variant == 7 ? (stages == 2 ? repeat_prefilter<16, 2> : repeat_prefilter<16, 4>)
-                 : variant == 6 ? repeat_prefilter<12, 4>
-                 : variant == 5 ? repeat_prefilter<4, 4>
-                                : (stages == 2 ? repeat_prefilter<kPreCsaDefault, 2> : repeat_prefilter<kPreCsaDefault, 4>);
-      // uniform reads go through the TMA-staged part when their 32-read spans fit the staging buffers (all groups but the
-      // batch's last one: the copy reads 16 bytes past its span)
-      uint32_t n_tma = 0;
-      if (u.n_reads >= 64u && u.read_len >= 1u && 8u * u.stride + 16u <= (uint32_t)kStageBytes && ((uintptr_t)d_seq_words & 15u) == 0 && !no_tma)
-        n_tma = u.n_reads / 32u - 1u;
-      pre<<<pre_grid, kPreThreads, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_out, d_list, n_tma, 1);
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return e;
-    }
-    const uint32_t tiles = (n_seg + lane_warps * 32 - 1) / (lane_warps * 32);
-    uint32_t grid = (uint32_t)sm_count;  // one persistent CTA per SM
-    if (grid > tiles) grid = tiles;
-    kernel<<<grid, lane_warps * 32, lane_smem, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_luts, d_out, d_status,
-                                                          split ? d_list : nullptr);
+    static const int stages = getenv("STRGPU_STAGES") ? atoi(getenv("STRGPU_STAGES")) : 4;   // A/B: staging depth
+    const uint32_t groups = (n_seg + 31) / 32;
+    uint32_t pre_grid = (uint32_t)sm_count * 4u;   // 4 resident CTAs of 8 warps per SM, grid-stride over groups of 32
+    const uint32_t pre_need = (groups + kPreWarps - 1) / kPreWarps;
+    if (pre_grid > pre_need) pre_grid = pre_need;
+    auto pre = variant == 7 ? (stages == 2 ? repeat_prefilter<12, 2> : repeat_prefilter<12, 4>)
+               : variant == 5 ? repeat_prefilter<0, 4>
+                              : (stages == 2 ? repeat_prefilter<kPreCsaDefault, 2> : repeat_prefilter<kPreCsaDefault, 4>);
+    // uniform reads go through the TMA-staged part when their 32-read spans fit the staging buffers (all groups but the
+    // batch's last one: the copy reads 16 bytes past its span)
+    uint32_t n_tma = 0;
+    if (u.n_reads >= 64u && u.read_len >= 1u && 8u * u.stride + 16u <= (uint32_t)kStageBytes && ((uintptr_t)d_seq_words & 15u) == 0 && !no_tma)
+      n_tma = u.n_reads / 32u - 1u;
+    pre<<<pre_grid, kPreThreads, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_out, d_scratch, cap, n_tma, 1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // the ladder kernels: grids sized for the worst case (every segment survives), CTAs without work exit at once
+    const uint32_t stage_need = (groups + kStageWarps - 1) / kStageWarps + 1u;
+    auto grid_for = [&](int ctas_per_sm) { return std::min((uint32_t)(sm_count * ctas_per_sm), stage_need); };
+    ladder_stage<2><<<grid_for(4), kStageThreads, StageSize<2>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
+    ladder_stage<4><<<grid_for(4), kStageThreads, StageSize<4>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
+    ladder_stage<5><<<grid_for(3), kStageThreads, StageSize<5>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
+    ladder_stage<6><<<grid_for(3), kStageThreads, StageSize<6>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
+    ladder_stage<7><<<grid_for(4), kStageThreads, StageSize<7>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
+    ladder_warp_list<<<grid_for(4), kStageThreads, 0, stream>>>(d_seq_words, d_nmask, d_xmask, d_segs, u, d_thr, d_out, d_status, d_scratch, n_seg, cap);
   } else if (max_len <= (uint32_t)kShortMaxLen) {
     uint32_t grid = (uint32_t)sm_count * 8u;  // 8 resident CTAs of 256 threads per SM
     if (grid > blocks_needed) grid = blocks_needed;
-    repeat_scan_warp<kShortMaxLen, kWarps><<<grid, kWarps * 32, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr,
+    repeat_scan_warp<kShortMaxLen, kWarps><<<grid, kWarps * 32, 0, stream>>>(d_seq_words, d_nmask, d_xmask, d_segs, n_seg, d_thr,
                                                                               d_out, d_status);
   } else {
     uint32_t grid = (uint32_t)sm_count * 4u;
     if (grid > blocks_needed) grid = blocks_needed;
-    repeat_scan_warp<512, kWarps><<<grid, kWarps * 32, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, d_thr, d_out,
+    repeat_scan_warp<512, kWarps><<<grid, kWarps * 32, 0, stream>>>(d_seq_words, d_nmask, d_xmask, d_segs, n_seg, d_thr, d_out,
                                                                      d_status);
   }
   return cudaGetLastError();

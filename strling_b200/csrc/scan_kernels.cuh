@@ -22,21 +22,26 @@ struct UniformReads {
   uint32_t n_reads, read_len, stride, pclass;
 };
 
-// variant: 0 = default (batches of <= 160-base segments: repeat_prefilter, then the lane-per-segment kernel over its
-//              survivors; warp-per-segment kernel otherwise),
+// variant: 0 = default (batches of <= 160-base segments: repeat_prefilter, then one ladder kernel per rung over dense
+//              survivor lists, then the warp-per-segment kernel over the segments with non-ACGT bases; batches with longer
+//              segments: the warp-per-segment kernel),
 //          1 = force the warp-per-segment kernel (kept for A/B measurements and as the long-segment path),
-//          2 / 4 = pre-filter fused into the lane kernel (plain / carry-save popcounts), 3 = lane kernel without the
-//          pre-filter, 5 / 6 / 7 = like 0 with 0 / 12 / 16 of the 16 popcount streams through carry-save adders (A/B)
-cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const strgpu_segment *d_segs,
-                               uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr, const uint16_t *d_luts,
-                               strgpu_repeat *d_out, int *d_status, int sm_count, int variant, cudaStream_t stream,
-                               const UniformReads *uniform = nullptr, uint32_t *d_list = nullptr);
-// d_list: device scratch of n_seg + 4 uint32 (survivor list of the pre-filter kernel); without it the fused kernel runs
+//          5 / 7 = like 0 with 0 / 12 of the 12 popcount streams through carry-save adders (A/B),
+//          8 = like 0 with stage lists of 64 entries (exercises the overflow path)
+// d_xmask: optional plane of the non-ACGT bases that are NOT the literal 'N' (they stay out of the N > 20 gate)
+// d_scratch: device scratch of scan_scratch_words(n_seg) uint32; without it the warp-per-segment kernel runs
+cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const uint32_t *d_xmask,
+                               const strgpu_segment *d_segs, uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr,
+                               const uint16_t *d_luts, strgpu_repeat *d_out, int *d_status, int sm_count, int variant,
+                               cudaStream_t stream, const UniformReads *uniform = nullptr, uint32_t *d_scratch = nullptr);
+
+constexpr uint32_t kScanScratchHdr = 32;   // header words of the scratch buffer (list counts, group cursors)
+constexpr int kScanStageLists = 7;
+uint32_t scan_stage_cap(uint32_t n_seg);
+size_t scan_scratch_words(uint32_t n_seg);
 
 // kernels one launch_repeat_scan call issues (for the library's launch counter)
-inline int scan_launches(uint32_t max_len, int variant) {
-  return (max_len <= (uint32_t)kShortMaxLen && (variant == 0 || variant >= 5)) ? 2 : 1;
-}
+int scan_launches(uint32_t max_len, int variant);
 
 constexpr int kLaneLutEntries = 1672;  // see build_lane_luts
 void build_lane_luts(uint16_t *dst);  // host: fills kLaneLutEntries uint16

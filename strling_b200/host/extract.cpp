@@ -95,6 +95,7 @@ struct Batch {
   std::vector<uint32_t> seg_off;
   uint8_t *seq2 = nullptr;       // pinned
   uint32_t *nmask = nullptr;     // pinned
+  uint32_t *xmask = nullptr;     // pinned: non-ACGT bases other than the literal N (stay out of the N > 20 gate, utils.nim:238)
   strgpu_segment *segs = nullptr;
   strgpu_repeat *out = nullptr;
   uint64_t n_bases = 0, cap_bases = 0;
@@ -124,16 +125,19 @@ struct Extractor {
   void alloc_batch(Batch &b, uint64_t cap_bases, uint32_t cap_seg) {
     b.cap_bases = cap_bases;
     b.cap_seg = cap_seg;
-    void *p1, *p2, *p3, *p4;
+    void *p1, *p2, *p3, *p4, *p5;
     gpu_check(strgpu_host_alloc(&p1, strgpu_seq2_bytes(cap_bases)), "host_alloc");
     gpu_check(strgpu_host_alloc(&p2, strgpu_nmask_bytes(cap_bases)), "host_alloc");
     gpu_check(strgpu_host_alloc(&p3, (size_t)cap_seg * sizeof(strgpu_segment)), "host_alloc");
     gpu_check(strgpu_host_alloc(&p4, (size_t)cap_seg * sizeof(strgpu_repeat)), "host_alloc");
+    gpu_check(strgpu_host_alloc(&p5, strgpu_nmask_bytes(cap_bases)), "host_alloc");
     b.seq2 = (uint8_t *)p1; b.nmask = (uint32_t *)p2; b.segs = (strgpu_segment *)p3; b.out = (strgpu_repeat *)p4;
+    b.xmask = (uint32_t *)p5;
     std::memset(b.nmask, 0, strgpu_nmask_bytes(cap_bases));
+    std::memset(b.xmask, 0, strgpu_nmask_bytes(cap_bases));
   }
   void free_batch(Batch &b) {
-    strgpu_host_free(b.seq2); strgpu_host_free(b.nmask); strgpu_host_free(b.segs); strgpu_host_free(b.out);
+    strgpu_host_free(b.seq2); strgpu_host_free(b.nmask); strgpu_host_free(b.xmask); strgpu_host_free(b.segs); strgpu_host_free(b.out);
   }
   void grow_batch(Batch &b, uint64_t need_bases, uint32_t need_seg) {
     if (need_bases <= b.cap_bases && need_seg <= b.cap_seg) return;
@@ -228,7 +232,7 @@ struct Extractor {
         if (!pr.n_seg) continue;
         const BamRecord r = BamChunk::view(data + b.chunk.rec_off[i]);
         const uint64_t base = b.base_off[i];
-        const int n_other = strgpu_pack_bam4(r.seq, (uint32_t)r.l_seq, b.seq2, b.nmask, base);
+        const int n_other = strgpu_pack_bam4(r.seq, (uint32_t)r.l_seq, b.seq2, b.nmask, b.xmask, base);
         if (n_other < 0) throw std::runtime_error("[strling] pack_bam4 failed");
         const bool has_n = n_other > 0;
         any = any || has_n;
@@ -259,12 +263,16 @@ struct Extractor {
 
   void submit(Batch &b) {
     n_scanned += b.n_seg;
-    gpu_check(strgpu_scan_submit(gpu, b.seq2, b.n_bases, b.any_n ? b.nmask : nullptr, b.segs, b.n_seg, b.max_len, b.out, &b.ticket),
+    gpu_check(strgpu_scan_submit(gpu, b.seq2, b.n_bases, b.any_n ? b.nmask : nullptr, b.any_n ? b.xmask : nullptr, b.segs, b.n_seg,
+                                 b.max_len, b.out, &b.ticket),
               "scan_submit");
   }
   void wait(Batch &b) { gpu_check(strgpu_scan_wait(gpu, b.ticket), "scan_wait"); }
   void recycle(Batch &b) {
-    if (b.any_n) std::memset(b.nmask, 0, (size_t)((b.n_bases + 31) / 32) * 4 + 8);
+    if (b.any_n) {
+      std::memset(b.nmask, 0, (size_t)((b.n_bases + 31) / 32) * 4 + 8);
+      std::memset(b.xmask, 0, (size_t)((b.n_bases + 31) / 32) * 4 + 8);
+    }
     b.n_bases = 0; b.n_seg = 0; b.max_len = 0; b.any_n = false; b.ticket = -1;
   }
 
@@ -472,6 +480,7 @@ int extract_run(const ExtractArgs &a) {
   std::mutex mu;
   std::condition_variable cv;
   std::deque<int> submitted;
+  int on_gpu = 0;   // batches submitted and not yet waited for: never more than the library's STRGPU_SLOTS submit slots
   bool is_free[kBatches];
   for (bool &f : is_free) f = true;
   bool done = false;
@@ -492,9 +501,15 @@ int extract_run(const ExtractArgs &a) {
         Batch &b = batches[bi];
         const auto w0 = clk::now();
         ex.wait(b);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          on_gpu--;
+        }
+        cv.notify_all();
         const auto w1 = clk::now();
         for (const Pending &r : b.recs) {
           if (!r.primary) continue;
+          if (!first_pass && r.tid >= 0) continue;   // ibam.query("*") returns no-coordinate records only
           if (first_pass && r.tid != tid_seen && r.tid >= 0) {
             if (rd.targets()[(size_t)r.tid].length > 2000000u)
               std::fprintf(stderr, "[strling] extracting chromosome:%s\n", rd.targets()[(size_t)r.tid].name.c_str());
@@ -521,6 +536,7 @@ int extract_run(const ExtractArgs &a) {
       std::lock_guard<std::mutex> lk(mu);
       consumer_error = e.what();
       for (bool &f : is_free) f = true;
+      on_gpu = 0;
       cv.notify_all();
     }
   });
@@ -591,6 +607,13 @@ int extract_run(const ExtractArgs &a) {
             if (b.recs[i].tid < 0) { have_tail = true; tail_voffset = b.chunk.voffset_of(i); break; }
         const auto d2 = clk::now();
         ex.t_stage += std::chrono::duration<double>(d2 - d1).count();
+        {
+          // back-pressure instead of STRGPU_ERR_BUSY: wait until the consumer has waited for an earlier ticket
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&]() { return on_gpu < STRGPU_SLOTS || !consumer_error.empty(); });
+          if (!consumer_error.empty()) throw std::runtime_error(consumer_error);
+          on_gpu++;
+        }
         ex.submit(b);
         ex.t_submit += std::chrono::duration<double>(clk::now() - d2).count();
         std::lock_guard<std::mutex> lk(mu);

@@ -100,8 +100,8 @@ std::vector<std::string> genome_repeat_lines(const std::string &fasta, double pr
     if (L == 0) continue;
     if (L > 0xfffffff0ll) throw std::runtime_error("[strling] chromosome too long: " + c.name);
     std::vector<uint8_t> seq2(strgpu_seq2_bytes((uint64_t)L), 0);
-    std::vector<uint32_t> nmask(strgpu_nmask_bytes((uint64_t)L) / 4, 0);
-    const int n_other = strgpu_pack_ascii(c.seq.data(), (uint32_t)L, seq2.data(), nmask.data(), 0);
+    std::vector<uint32_t> nmask(strgpu_nmask_bytes((uint64_t)L) / 4, 0), xmask(strgpu_nmask_bytes((uint64_t)L) / 4, 0);
+    const int n_other = strgpu_pack_ascii(c.seq.data(), (uint32_t)L, seq2.data(), nmask.data(), xmask.data(), 0);
     if (n_other < 0) throw std::runtime_error("[strling] pack_ascii failed");
     const int64_t n_win = (L + kStep - 1) / kStep;
     std::vector<strgpu_segment> segs((size_t)n_win);
@@ -116,7 +116,8 @@ std::vector<std::string> genome_repeat_lines(const std::string &fasta, double pr
     const int64_t kChunk = 1 << 22;
     for (int64_t a = 0; a < n_win; a += kChunk) {
       const uint32_t n = (uint32_t)std::min<int64_t>(kChunk, n_win - a);
-      check(strgpu_scan(gpu, seq2.data(), (uint64_t)L, n_other ? nmask.data() : nullptr, segs.data() + a, n, kWindow, res.data() + a), "scan");
+      check(strgpu_scan(gpu, seq2.data(), (uint64_t)L, n_other ? nmask.data() : nullptr, n_other ? xmask.data() : nullptr, segs.data() + a, n, kWindow,
+                        res.data() + a), "scan");
     }
     // genome_strs.nim:70-92 : merge adjacent windows of the same unit (one window may be skipped), pad, trim
     Window last;

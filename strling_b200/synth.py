@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .binding import SEG_HAS_N, SEGMENT_DTYPE
+from .binding import SEG_HAS_N, SEGMENT_DTYPE, Masks
 
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 # ASCII -> 2-bit code of the library (C=0 A=1 T=2 G=3, everything else 1) and the non-ACGT flag
@@ -21,11 +21,13 @@ CLASS_PLAIN, CLASS_MESSY, CLASS_CLIPPED_STR, CLASS_STR = 0, 1, 2, 3
 
 
 def make_reads(n: int, seed: int, length: int = 150, mix=(0.90, 0.07, 0.02, 0.01), noise: float = 0.01,
-               n_frac: float = 0.0):
+               n_frac: float = 0.0, iupac_frac: float = 0.0):
     """Returns (ascii uint8 [n, length], cls uint8 [n], lclip uint8 [n], rclip uint8 [n]).
     plain/messy: uniform ACGT.  clipped-STR: a soft clip of 17..60 bases on one end filled with a repeat.
     STR: >= 80 % of the read is a repeat of a random 1-6 bp unit, random phase, `noise` substitutions.
-    n_frac: fraction of reads that get 1..30 'N' bases (0 for the benchmark; used by parity tests)."""
+    n_frac: fraction of reads that get 1..30 'N' bases (0 for the benchmark; used by parity tests).
+    iupac_frac: fraction of reads that get 1..40 IUPAC ambiguity codes other than N (they scan as 'A', never match in the
+    recount and -- unlike N -- do not count towards the N > 20 gate of utils.nim:238)."""
     rng = np.random.default_rng(seed)
     reads = _ACGT[rng.integers(0, 4, size=(n, length), dtype=np.uint8)]
     cls = rng.choice(4, size=n, p=np.asarray(mix) / np.sum(mix)).astype(np.uint8)
@@ -70,12 +72,20 @@ def make_reads(n: int, seed: int, length: int = 150, mix=(0.90, 0.07, 0.02, 0.01
         for r in rows:  # small counts only (tests)
             k = int(rng.integers(1, 31))
             reads[r, rng.choice(length, size=k, replace=False)] = ord("N")
+    if iupac_frac > 0:
+        codes = np.frombuffer(b"RYMKSWHBVD", dtype=np.uint8)
+        rows = np.nonzero(rng.random(n) < iupac_frac)[0]
+        for r in rows:
+            k = int(rng.integers(1, min(41, length + 1)))
+            where = rng.choice(length, size=k, replace=False)
+            reads[r, where] = codes[rng.integers(0, len(codes), size=k)]
     return reads, cls, lclip, rclip
 
 
 def pack_matrix(reads: np.ndarray, align_bases: int = 16):
     """Packs an [n, L] ASCII matrix: every read starts at a multiple of align_bases.  Returns
-    (seq2 uint8 with 8 bytes slack, nmask uint32 (+slack) or None, stride_bases)."""
+    (seq2 uint8 with 8 bytes slack, nmask uint32 (+slack) or None, stride_bases); when the reads hold non-ACGT bases other than
+    the literal 'N', nmask is a binding.Masks pair (nmask, xmask)."""
     n, length = reads.shape
     stride = (length + align_bases - 1) // align_bases * align_bases
     codes = np.zeros((n, stride), dtype=np.uint8)
@@ -93,6 +103,13 @@ def pack_matrix(reads: np.ndarray, align_bases: int = 16):
         nb = np.zeros(nmask.size * 4, dtype=np.uint8)
         nb[: bits.size] = bits
         nmask[:] = nb.view("<u4")
+        xother = other.copy()
+        xother[:, :length] &= (reads != ord("N")).astype(np.uint8)
+        if xother.any():
+            bits = np.packbits(xother.reshape(-1), bitorder="little")
+            xb = np.zeros(nmask.size * 4, dtype=np.uint8)
+            xb[: bits.size] = bits
+            nmask = Masks(nmask, xb.view("<u4").copy())
     return seq2, nmask, stride
 
 

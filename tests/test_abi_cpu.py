@@ -50,7 +50,7 @@ def test_pack_ascii_matches_numpy(lib):
     seq2, nmask, segs, n_bases = sb.pack_reads([bytes(r) for r in reads])
     assert n_bases == 300 * stride
     assert np.array_equal(seq2[: n_bases // 4], seq2_np[: n_bases // 4])
-    assert nmask is not None and np.array_equal(nmask[: n_bases // 32], nmask_np[: n_bases // 32])
+    assert nmask is not None and nmask[1] is None and np.array_equal(nmask[0][: n_bases // 32], nmask_np[: n_bases // 32])
     assert np.array_equal(segs["base_off"], np.arange(300) * stride)
 
 
@@ -67,8 +67,21 @@ def test_pack_bam4_matches_ascii(lib):
         a2 = np.zeros(lib.strgpu_seq2_bytes(nb), dtype=np.uint8)
         b2 = np.zeros_like(a2)
         am = np.zeros(lib.strgpu_nmask_bytes(nb) // 4, dtype=np.uint32)
-        bm = np.zeros_like(am)
-        ka = lib.strgpu_pack_ascii(ascii_seq, length, a2.ctypes.data, am.ctypes.data, 0)
-        kb = lib.strgpu_pack_bam4(bam.ctypes.data, length, b2.ctypes.data, bm.ctypes.data, 0)
+        bm, ax, bx = np.zeros_like(am), np.zeros_like(am), np.zeros_like(am)
+        ka = lib.strgpu_pack_ascii(ascii_seq, length, a2.ctypes.data, am.ctypes.data, ax.ctypes.data, 0)
+        kb = lib.strgpu_pack_bam4(bam.ctypes.data, length, b2.ctypes.data, bm.ctypes.data, bx.ctypes.data, 0)
         assert ka == kb == sum(c not in b"ACGT" for c in ascii_seq)
-        assert np.array_equal(a2, b2) and np.array_equal(am, bm)
+        assert np.array_equal(a2, b2) and np.array_equal(am, bm) and np.array_equal(ax, bx)
+        # nmask: every non-ACGT base; xmask: those that are not the literal 'N' (utils.nim:238 counts 'N' only)
+        bits = lambda m: [(int(m[i >> 5]) >> (i & 31)) & 1 for i in range(length)]
+        assert bits(am) == [int(c not in b"ACGT") for c in ascii_seq]
+        assert bits(ax) == [int(c not in b"ACGTN") for c in ascii_seq]
+
+
+def test_pack_reads_and_synth_agree_on_iupac_planes(lib):
+    reads, _, _, _ = synth.make_reads(200, seed=6, length=150, n_frac=0.2, iupac_frac=0.2)
+    seq2_np, masks_np, stride = synth.pack_matrix(reads)
+    seq2, masks, segs, n_bases = sb.pack_reads([bytes(r) for r in reads])
+    assert isinstance(masks_np, sb.Masks) and masks[1] is not None
+    assert np.array_equal(masks[0][: n_bases // 32], masks_np[0][: n_bases // 32])
+    assert np.array_equal(masks[1][: n_bases // 32], masks_np[1][: n_bases // 32])
