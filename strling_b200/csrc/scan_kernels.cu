@@ -296,11 +296,14 @@ __global__ void __launch_bounds__(WARPS * 32) repeat_scan_warp(const uint32_t *_
 constexpr int kLaneWords = 11;                 // ten words hold 160 bases; one more absorbs the re-alignment shift
 constexpr int kCls2 = 10, kCls3 = 24, kCls4 = 70, kCls5 = 208;
 constexpr int kCls4Words = (kCls4 + 3) / 4;       // 4-mer classes are counted in packed uint8 (18 words) to keep smem small
-constexpr int kTabWords = kCls2 + kCls3 + kCls4Words;  // 52 words per lane; k = 5 reuses them as 208 packed uint8
 constexpr int kLut2 = 0, kLut3 = 16, kLut4 = 80, kRev234 = 336, kLut5 = 440, kRev5 = 1464;  // offsets into the uint16 table
-constexpr int kLutTotal = 1672;
-static_assert(kCls5 / 4 <= kTabWords, "k = 5 counters must fit");
-static_assert(kLutTotal == kLaneLutEntries, "LUT size");
+constexpr int kLutTotal = 1672;                // the k = 2..5 tables (copied to shared memory by the ladder kernels that use them)
+constexpr int kCls6 = 700;                     // necklace classes of 6-mers over 4 letters
+constexpr int kLut6 = kLutTotal, kRev6 = kLut6 + 4096;   // class rank of every 6-mer code; canonical code of every rank
+constexpr int kLut5R = kRev6 + kCls6;                    // class rank of every 5-mer code (its canonical codes: kRev5)
+constexpr int kRankWords = (4096 + 1024) / 2;            // the two rank tables as shared-memory words (6-mers first)
+static_assert(kLut5R + 1024 == kLaneLutEntries, "LUT size");
+static_assert(kLut5R % 2 == 0 && kLut6 % 2 == 0, "tables are copied as 32-bit words");
 
 // read.count(s) for one lane: greedy leftmost non-overlapping matches of the K-base pattern (utils.nim:254).
 // One copy for all k, kept out of line (instruction-cache footprint).  `scratch` is the lane's counter column (dead by
@@ -665,64 +668,76 @@ __device__ __forceinline__ bool lane_decide(const uint32_t *rd, uint32_t *tab, i
   return true;
 }
 
-// stage the lane's read: eleven words, re-aligned so that base 0 sits at bit 31 of word 0
-__device__ __forceinline__ void lane_stage(const uint32_t *__restrict__ seq, const strgpu_segment &sg, uint32_t *rd) {
-  const uint32_t g = sg.base_off >> 4;
-  const uint32_t sh = 2u * (sg.base_off & 15u);
-  const int n_words = (2 * (int)sg.len + 31) >> 5;
-  uint32_t raw[kLaneWords + 1];
-#pragma unroll
-  for (int j = 0; j < kLaneWords + 1; j++) raw[j] = (j <= n_words) ? __byte_perm(seq[g + j], 0, 0x0123) : 0u;
-#pragma unroll
-  for (int j = 0; j < kLaneWords; j++) rd[j * 32] = __funnelshift_l(raw[j + 1], raw[j], sh);
+// count(read, K, counts[K]) for K = 5 and 6, one lane, without any table: the at most 32 (K = 5) / 26 (K = 6) windows of a
+// <= 160-base segment become keys (class rank << 5 | window index; the class rank of a K-mer code comes from a table in
+// shared memory), the keys are SORTED in registers -- two independent 16-key merge-exchange networks run side by side on
+// packed 16x2 values (VIMNMX.U16x2), then one bitonic merge across the halves -- and a single sweep over the sorted keys
+// finds the longest run of equal classes.  Seq.inc keeps the FIRST class to reach the final maximum (strict >,
+// utils.nim:192-195): among the classes with the maximal count that is the one whose LAST window comes first, i.e. the
+// maximum of (run length so far, 31 - window index) over all keys.  No shared-memory counters, no probing loop, no divergence.
+__device__ __forceinline__ void cmpx(uint32_t &a, uint32_t &b) {
+  const uint32_t lo = __vminu2(a, b), hi = __vmaxu2(a, b);
+  a = lo;
+  b = hi;
 }
-
-// count(read, 5, counts[5]) with 208 packed uint8 counters ([class / 4][lane] words)
-__device__ __forceinline__ void lane_count5(const uint32_t *rd, uint32_t *tab, const uint16_t *lut, int L, int &M, uint32_t &leader) {
+// K is a RUN-TIME argument (5 or 6) and the function is kept out of line: one copy of the two unrolled networks serves
+// both rungs (instruction-cache footprint).  rank_lut: the rung's class-rank table in shared memory; n_classes: 208 / 700.
+__device__ __noinline__ uint32_t lane_count_sorted(const uint32_t *rd, const uint16_t *rank_lut, int L, int K, int n_classes) {
+  const int W = L / K;
+  const uint32_t top = 32u - 2u * (uint32_t)K;
+  uint32_t v[16];
 #pragma unroll
-  for (int c = 0; c < kCls5 / 4; c++) tab[c * 32] = 0;
-  M = 0;
-  uint32_t lead = 0xffffffffu;
-  const int W = L / 5;
-#pragma unroll 2
-  for (int j = 0; j < W; j++) {
-    const uint32_t bit = 10u * j;
-    const uint32_t code = __funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 22;
-    const uint32_t e = lut[kLut5 + code];        // (class / 4) * 128 | (class % 4) * 8
-    uint32_t *p = slot_at(tab, e & 0xff80u);
-    const uint32_t sh = e & 31u;
-    const uint32_t v = *p + (1u << sh);
-    *p = v;
-    const int c = (int)((v >> sh) & 0xffu);
-    if (c > M) { M = c; lead = e; }
-  }
-  leader = (lead == 0xffffffffu) ? 0x3ffu : (uint32_t)lut[kRev5 + (lead >> 7) * 4 + ((lead & 31u) >> 3)];
-}
-
-// count(read, 6, counts[6]) for one lane: at most 26 windows, counted in an open-addressing table of 52 slots
-// ({canonical code + 1, count} per uint32 word of the lane's column); the min-rotation is taken in the ALU.
-__device__ __forceinline__ void lane_count6(const uint32_t *rd, uint32_t *tab, int L, int &M, uint32_t &leader) {
+  for (int i = 0; i < 16; i++) {
+    uint32_t e[2];
 #pragma unroll
-  for (int c = 0; c < kTabWords; c++) tab[c * 32] = 0;
-  M = 0;
-  leader = 0xfffu;
-  const int W = L / 6;
-#pragma unroll 1
-  for (int j = 0; j < W; j++) {
-    const uint32_t bit = 12u * j;
-    uint32_t x = __funnelshift_l(rd[((bit >> 5) + 1) * 32], rd[(bit >> 5) * 32], bit & 31u) >> 20;
-    const uint32_t c = min_rotation<6>(x);
-    const uint32_t key = (c + 1u) << 16;
-    uint32_t h = (((c * 40503u) & 0xffffu) * (uint32_t)kTabWords) >> 16;
-    int cnt;
-    while (true) {
-      const uint32_t v = tab[h * 32];
-      if (v == 0u) { tab[h * 32] = key | 1u; cnt = 1; break; }
-      if ((v & 0xffff0000u) == key) { tab[h * 32] = v + 1u; cnt = (int)(v & 0xffffu) + 1; break; }
-      h = (h + 1u == (uint32_t)kTabWords) ? 0u : h + 1u;
+    for (int h = 0; h < 2; h++) {
+      const int j = i + 16 * h;                                        // window index
+      e[h] = (uint32_t)((n_classes + j) * 32 + 31);                    // padding: a class of its own, ranked after every real one
+      if (j < W) {
+        const uint32_t bit = (uint32_t)(2 * j) * (uint32_t)K;
+        const uint32_t *p = rd + (bit >> 5) * 32u;
+        const uint32_t code = __funnelshift_l(p[32], p[0], bit & 31u) >> top;
+        e[h] = (uint32_t)rank_lut[code] * 32u + (uint32_t)j;
+      }
     }
-    if (cnt > M) { M = cnt; leader = c; }   // strict >: the earlier leader keeps ties
+    v[i] = e[1] * 65536u + e[0];
   }
+  // merge-exchange sort (Batcher) of 16 keys, both halves at once
+#pragma unroll
+  for (int p = 1; p < 16; p *= 2)
+#pragma unroll
+    for (int k = p; k >= 1; k /= 2)
+#pragma unroll
+      for (int j = k % p; j <= 15 - k; j += 2 * k)
+#pragma unroll
+        for (int i = 0; i <= (k - 1 < 15 - j - k ? k - 1 : 15 - j - k); i++)
+          if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) cmpx(v[i + j], v[i + j + k]);
+  // bitonic merge of the two sorted halves: low key i against high key 15 - i, then half-cleaners inside each half
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t a = v[i], t = __byte_perm(v[15 - i], 0, 0x1032);
+    const uint32_t mn = __vminu2(a, t), mx = __vmaxu2(a, t);
+    v[i] = __byte_perm(mn, mx, 0x7610);
+    v[15 - i] = __byte_perm(mn, mx, 0x5432);
+  }
+#pragma unroll
+  for (int st = 8; st >= 1; st /= 2)
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      if ((i & st) == 0) cmpx(v[i], v[i + st]);
+  // sweep: longest run of equal classes, earliest completion first.  best = (run length so far * 32 + 31 - window index) << 16 | key:
+  // the window index is unique, so the appended key never decides a comparison
+  uint32_t prev = 0xffffffffu, cur = 0, best = 0;
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint32_t e = h == 0 ? (v[i] & 0xffffu) : __umulhi(v[i], 65536u);
+      cur = ((e ^ prev) < 32u) ? cur + 1u : 1u;
+      best = max(best, (cur * 32u + ((e & 31u) ^ 31u)) * 65536u + e);
+      prev = e;
+    }
+  return W == 0 ? 0u : best;   // run length: best >> 21, class rank: (best & 0xffff) >> 5
 }
 
 // Segment s of the batch: the first u.n_reads are implicit whole reads of one length on a fixed stride (no descriptor
@@ -789,15 +804,15 @@ __device__ __forceinline__ void prefilter_masks(int L, uint32_t (&V)[5]) {
 }
 
 // Upper bounds s1 >= s2 of the two largest of the sixteen 2-mer occurrence counts c[a][b] (positions 0 .. L - 2).
-// Only NINE of the sixteen cells are counted (a, b < 3) plus three row sums n[a] = occurrences of base a at positions 0 .. L - 2;
+// Only NINE of the sixteen cells are counted (a, b < 3) plus three column sums f[b] = positions 0 .. L - 2 whose SUCCESSOR is b;
 // the other seven follow from the margins of the 4 x 4 table:
-//   n[3]    = (L - 1) - n[0] - n[1] - n[2]                        c[a][3] = n[a] - c[a][0] - c[a][1] - c[a][2]     (exact)
-//   column sum f[b] = occurrences of b at positions 1 .. L - 1 = n[b] - [base 0 == b] + [base L-1 == b], so with
-//   f-[b] = n[b] - [base 0 == b] <= f[b] <= f-[b] + 1:            c[3][b] <= f-[b] + 1 - (c[0][b] + c[1][b] + c[2][b])
-//                                                                 c[3][3] <= n[3] - sum_b (f-[b] - (c[0][b] + c[1][b] + c[2][b]))
+//   f[3]    = (L - 1) - f[0] - f[1] - f[2]                        c[3][b] = f[b] - c[0][b] - c[1][b] - c[2][b]     (exact)
+//   row sum n[a] = occurrences of a at positions 0 .. L - 2 = f[a] + [base 0 == a] - [base L-1 == a], so with
+//   n+[a] = f[a] + [base 0 == a] >= n[a] >= n+[a] - 1:            c[a][3] <= n+[a] - (c[a][0] + c[a][1] + c[a][2])
+//                                                                 c[3][3] <= f[3] - sum_a (n+[a] - 1 - (c[a][0] + c[a][1] + c[a][2]))
 // -- the last four are over-estimates by at most one, which keeps the filter sound (a segment it finishes really has the
 // empty result; at worst a borderline segment more reaches the ladder kernels, which are exact).  12 popcount streams
-// instead of 16 and 45 + 15 mask LOP3 instead of 60 + 20: this kernel is bound by the ALU / popcount pipes.
+// instead of 16 and 45 + 15 + 3 mask LOP3 instead of 60 + 20: this kernel is bound by the ALU / popcount pipes.
 // `one` is the runtime constant 1 (a kernel argument): a * one + b compiles to IMAD on the FMA pipe, which is idle here, instead of
 // IADD3 on the ALU pipe, which is the bottleneck (every ALU instruction costs two issue cycles).
 // The top-2 selection runs on packed 16x2 values (VIMNMX.U16x2 / VIMNMX3: half the min/max instructions).
@@ -809,53 +824,63 @@ __device__ __forceinline__ int popc5(const uint32_t (&m)[5], int idx, int one) {
   return (__popc(c1) * one + __popc(c2)) * (one + one) + __popc(x2);
 }
 
+// (a & mask) | (b & ~mask) as ONE LOP3 (the compiler emits two for the spelled-out form with the constants kOdd / kEven)
+__device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t mask) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(mask));
+  return d;
+}
+
 template <int CSA>
 __device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const uint32_t (&V)[5], int n_valid, int &s1, int &s2, int one) {
   uint32_t Dh[6], Dl[6];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
-    Dh[j] = (w[j] & kOdd) | (__umulhi(w[j + 5], 0x80000000u) & kEven);   // x >> 1 as a high multiply: FMA pipe, not ALU
-    Dl[j] = ((w[j] << 1) & kOdd) | (w[j + 5] & kEven);
+    Dh[j] = bitselect(w[j], __umulhi(w[j + 5], 0x80000000u), kOdd);   // x >> 1 as a high multiply: FMA pipe, not ALU
+    Dl[j] = bitselect(w[j] << 1, w[j + 5], kOdd);
   }
   Dh[5] = w[5];        // only its top slot pair is used: base 0 of word 5 (the even bit feeds a slot that is never valid)
   Dl[5] = w[5] << 1;
-  uint32_t E[5][3], Qh[5], Ql[5];
+  uint32_t G[5][3];   // positions whose successor is b (and that start a 2-mer of the segment)
 #pragma unroll
   for (int j = 0; j < 5; j++) {
-    Qh[j] = __funnelshift_l(Dh[j + 1], Dh[j], 2);
-    Ql[j] = __funnelshift_l(Dl[j + 1], Dl[j], 2);
-    E[j][0] = ~Dh[j] & ~Dl[j] & V[j];
-    E[j][1] = ~Dh[j] & Dl[j] & V[j];
-    E[j][2] = Dh[j] & ~Dl[j] & V[j];
+    const uint32_t Qh = __funnelshift_l(Dh[j + 1], Dh[j], 2), Ql = __funnelshift_l(Dl[j + 1], Dl[j], 2);
+    G[j][0] = ~Qh & ~Ql & V[j];
+    G[j][1] = ~Qh & Ql & V[j];
+    G[j][2] = Qh & ~Ql & V[j];
   }
-  int c[4][4], n[4], col[3];
+  int c[4][4], f[4];
 #pragma unroll
-  for (int a = 0; a < 3; a++) {
+  for (int b = 0; b < 3; b++) {
+    int col = 0;
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
+    for (int a = 0; a < 3; a++) {
       uint32_t m[5];
 #pragma unroll
       for (int j = 0; j < 5; j++) {
-        const uint32_t e = E[j][a];
-        m[j] = b == 0 ? (e & ~Qh[j] & ~Ql[j]) : (b == 1 ? (e & ~Qh[j] & Ql[j]) : (e & Qh[j] & ~Ql[j]));
+        const uint32_t g = G[j][b];
+        m[j] = a == 0 ? (g & ~Dh[j] & ~Dl[j]) : (a == 1 ? (g & ~Dh[j] & Dl[j]) : (g & Dh[j] & ~Dl[j]));
       }
-      c[a][b] = popc5<CSA>(m, a * 4 + b, one);
+      c[a][b] = popc5<CSA>(m, b * 4 + a, one);
+      col = a == 0 ? c[a][b] : col * one + c[a][b];
     }
     uint32_t m[5];
 #pragma unroll
-    for (int j = 0; j < 5; j++) m[j] = E[j][a];
-    n[a] = popc5<CSA>(m, a * 4 + 3, one);
-    c[a][3] = ((c[a][0] * one + c[a][1]) * one + c[a][2]) * (-one) + n[a];
+    for (int j = 0; j < 5; j++) m[j] = G[j][b];
+    f[b] = popc5<CSA>(m, b * 4 + 3, one);
+    c[3][b] = col * (-one) + f[b];
   }
-  n[3] = ((n[0] * one + n[1]) * one + n[2]) * (-one) + n_valid;
-  int rest = n[3];   // becomes the bound of c[3][3]
+  f[3] = ((f[0] * one + f[1]) * one + f[2]) * (-one) + n_valid;
+  int rest = f[3];   // becomes the bound of c[3][3]
 #pragma unroll
-  for (int b = 0; b < 3; b++) {
-    col[b] = (c[0][b] * one + c[1][b]) * one + c[2][b];
-    const int fminus = (int)__umulhi(E[0][b], 2u) * (-one) + n[b];   // n[b] - [base 0 == b]: position 0 is bit 31 of plane 0
-    const int d = col[b] * (-one) + fminus;                           // >= -1
-    c[3][b] = d * one + one;
-    rest = d * (-one) + rest;
+  for (int a = 0; a < 3; a++) {
+    const int row = (c[a][0] * one + c[a][1]) * one + c[a][2];
+    // [base 0 == a]: position 0 is bit 31 of plane 0
+    const uint32_t e0 = a == 0 ? (V[0] & ~Dh[0] & ~Dl[0]) : (a == 1 ? (V[0] & ~Dh[0] & Dl[0]) : (V[0] & Dh[0] & ~Dl[0]));
+    const int nplus = (int)__umulhi(e0, 2u) * one + f[a];
+    const int d = row * (-one) + nplus;     // >= c[a][3] >= d - 1
+    c[a][3] = d;
+    rest = (d * (-one) + rest) * one + one;
   }
   c[3][3] = rest;
   // top two of the sixteen: pack cell i with cell i + 8 (all values are in 0 .. 161), select on both halves at once
@@ -951,17 +976,17 @@ __device__ __forceinline__ bool prefilter_keep(const uint32_t *src, uint32_t sh,
 
 // Device scratch of one library call (uint32 words; sized by scan_scratch_words()):
 //   hdr[0] long lane-path survivors, hdr[1] short ones, hdr[2] warp-path segments,
-//   hdr[3 + i] entries appended to stage list i (R3, C4, R4, C5, R5, C6, R6), hdr[10 + j] group cursor of ladder kernel j
+//   hdr[3 + i] entries appended to stage list i (R3, C4), hdr[10 + j] group cursor of ladder kernel j
 //   listA[n_seg]  lane-path survivors of the pre-filter, two-ended: long segments (>= kLongLen bases) fill it upwards from 0,
 //                 short ones downwards from n_seg - 1, so that the groups of 32 a warp takes hold segments of similar length
 //   listW[n_seg]  segments for the warp-per-segment kernel: non-ACGT bases, more than 160 bases, stage-list overflow
-//   7 stage lists of `cap` entries each, structure of arrays: segment index, packed ScanState, M | leader << 8
+//   2 stage lists of `cap` entries each, structure of arrays: segment index, packed ScanState, M | leader << 8
 struct StageLists {
   uint32_t *hdr, *listA, *listW, *stage;
   uint32_t cap, n_seg;
 };
 constexpr int kLongLen = 96;
-enum { kListR3 = 0, kListC4, kListR4, kListC5, kListR5, kListC6, kListR6, kNumStageLists };
+enum { kListR3 = 0, kListC4, kNumStageLists };
 static_assert(kNumStageLists == kScanStageLists, "stage list count");
 
 __device__ __forceinline__ StageLists stage_lists(uint32_t *scratch, uint32_t n_seg, uint32_t cap) {
@@ -1108,30 +1133,26 @@ __global__ void __launch_bounds__(kPreThreads, 4) repeat_prefilter(const uint32_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// The ladder for the pre-filter's survivors (utils.nim:242-265), one LANE per segment, one kernel per rung:
-//   ladder_stage<2>  counts k = 2 and 3, decides the k = 2 rung (every lane recounts: best is still -1) and the k = 3
-//                    rung when it needs no recount; appends to R3 (k = 3 recount pending) or C4
-//   ladder_stage<K>  K = 4, 5, 6: first the entries of R(K-1) -- the pending recount read.count(s) of rung K - 1
-//                    (utils.nim:254) and that rung's decision --, then, for them and for the entries of C(K), the count of
-//                    rung K; appends to R(K) (recount pending) or C(K+1), or stores the result
-//   ladder_stage<7>  the pending k = 6 recounts; stores the result
-// Every kernel works on a DENSE list: all 32 lanes of a warp run the same rung (the recount lists are kept apart from the
-// count lists, and a group of 32 never mixes the two), so there is no divergent work and no partially filled batch except
-// the last group of a list.  Each kernel only carries the shared memory its own tables need (45 / 29 / 63 / 63 / 21 words
-// per lane), which is what lets 24-32 warps share an SM.  State travels between the kernels as 12-byte list entries in
-// HBM / L2.  A list that overflows its capacity spills the segment to listW: the warp-per-segment kernel, which runs last,
-// redoes it from rung 2.
+// The ladder for the pre-filter's survivors (utils.nim:242-265), one LANE per segment, two kernels over DENSE lists:
+//   ladder_stage<2>  counts k = 2 and 3 (time-stamped counters in shared memory), decides the k = 2 rung (every lane
+//                    recounts: best is still -1) and the k = 3 rung when it needs no recount; appends the segment to R3
+//                    (its k = 3 recount read.count(s), utils.nim:254, is pending) or to C4, or stores the result
+//   ladder_stage<4>  first the entries of R3 -- the pending recount and the k = 3 decision, 32 lanes wide --, then, for them
+//                    and for the entries of C4, the rungs k = 4, 5, 6: k = 4 in packed uint8 counters, k = 5 and 6 by sorting
+//                    the windows' class ranks in registers (lane_count_sorted); stores the result
+// A group of 32 never mixes R3 and C4 entries, so the k = 3 recount -- the one a third of the repeat-bearing reads need --
+// runs without divergence; the recounts of rungs 4..6 are rarer and run in place.  State travels between the two kernels
+// as 12-byte list entries in HBM / L2.  A list that overflows its capacity spills the segment to listW: the warp-per-segment
+// kernel, which runs last, redoes it from rung 2.
 constexpr int kStageThreads = 256;
 constexpr int kStageWarps = kStageThreads / 32;
 template <int K> struct StageCfg;
-template <> struct StageCfg<2> { static constexpr int tab = kCls2 + kCls3, list_r = -1, list_c = -1, out_r = kListR3, out_c = kListC4, cursor = 0; };
-template <> struct StageCfg<4> { static constexpr int tab = kCls4Words, list_r = kListR3, list_c = kListC4, out_r = kListR4, out_c = kListC5, cursor = 1; };
-template <> struct StageCfg<5> { static constexpr int tab = kTabWords, list_r = kListR4, list_c = kListC5, out_r = kListR5, out_c = kListC6, cursor = 2; };
-template <> struct StageCfg<6> { static constexpr int tab = kTabWords, list_r = kListR5, list_c = kListC6, out_r = kListR6, out_c = -1, cursor = 3; };
-template <> struct StageCfg<7> { static constexpr int tab = 10, list_r = kListR6, list_c = -1, out_r = -1, out_c = -1, cursor = 4; };
+template <> struct StageCfg<2> { static constexpr int tab = kCls2 + kCls3, list_r = -1, list_c = -1, out_r = kListR3, out_c = kListC4; };
+template <> struct StageCfg<4> { static constexpr int tab = kCls4Words, list_r = kListR3, list_c = kListC4, out_r = -1, out_c = -1; };
 template <int K> struct StageSize {
   static constexpr int warp_words = (StageCfg<K>::tab + kLaneWords) * 32;
-  static constexpr int smem_bytes = kStageWarps * warp_words * 4 + kLutTotal * 2 + 16;
+  static constexpr int lut_words = kLutTotal / 2 + (K == 4 ? kRankWords : 0);   // K = 4 also holds the 5- / 6-mer rank tables
+  static constexpr int smem_bytes = kStageWarps * warp_words * 4 + lut_words * 4 + 16;
 };
 
 __device__ __forceinline__ uint32_t pack_state(const ScanState &st) {
@@ -1147,28 +1168,59 @@ __device__ __forceinline__ ScanState unpack_state(uint32_t a) {
   return st;
 }
 
-// warp-aggregated append to stage list `which` (every lane of the warp calls this)
-__device__ __forceinline__ void stage_push(const StageLists &sl, int which, bool want, int lane, uint32_t s, uint32_t st, uint32_t extra) {
-  const uint32_t m = __ballot_sync(kFull, want);
-  if (m == 0u) return;
+// Warp-aggregated append of this group's lanes to the recount list `which_r` (lanes with what == 2) and / or the count list
+// `which_c` (what == 1); every lane of the warp calls this.  Lane 0 / lane 1 issue the two atomics at the same time, so the
+// warp pays one L2 round trip for both lists.
+__device__ __forceinline__ void stage_push2(const StageLists &sl, int which_r, int which_c, int what, int lane, uint32_t s, uint32_t st,
+                                            uint32_t extra) {
+  const uint32_t mr = which_r >= 0 ? __ballot_sync(kFull, what == 2) : 0u;
+  const uint32_t mc = which_c >= 0 ? __ballot_sync(kFull, what == 1) : 0u;
+  if ((mr | mc) == 0u) return;
   uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(sl.hdr + 3 + which, (uint32_t)__popc(m));
-  base = __shfl_sync(kFull, base, 0);
-  if (want) {
-    const uint32_t i = base + __popc(m & ((1u << lane) - 1u));
+  if (lane == 0 && mr) base = atomicAdd(sl.hdr + 3 + which_r, (uint32_t)__popc(mr));
+  if (lane == 1 && mc) base = atomicAdd(sl.hdr + 3 + which_c, (uint32_t)__popc(mc));
+  const uint32_t base_r = __shfl_sync(kFull, base, 0), base_c = __shfl_sync(kFull, base, 1);
+  const uint32_t below = (1u << lane) - 1u;
+  if (what == 1 || what == 2) {
+    const bool r = what == 2;
+    const uint32_t i = r ? base_r + __popc(mr & below) : base_c + __popc(mc & below);
     if (i < sl.cap) {
-      uint32_t *q = sl.stage + (size_t)which * 3u * sl.cap;
+      uint32_t *q = sl.stage + (size_t)(r ? which_r : which_c) * 3u * sl.cap;
       q[i] = s;
       q[sl.cap + i] = st;
-      q[2u * sl.cap + i] = extra;
+      q[2u * sl.cap + i] = r ? extra : 0u;
     } else {
       sl.listW[atomicAdd(sl.hdr + 2, 1u)] = s;   // no room: the warp kernel redoes this segment from rung 2
     }
   }
 }
 
+// one lane's work item of a ladder kernel: a list entry and the segment it names
+struct StageItem {
+  uint32_t s, st, extra;
+  strgpu_segment sg;
+  bool active;
+};
+
+// the twelve raw words that hold the lane's segment (issued together; nothing waits on them here)
+__device__ __forceinline__ void lane_fetch(const uint32_t *__restrict__ seq, const strgpu_segment &sg, bool active, uint32_t (&raw)[kLaneWords + 1]) {
+  const uint32_t g = sg.base_off >> 4;
+  const int n_words = active ? (2 * (int)sg.len + 31) >> 5 : -1;
+#pragma unroll
+  for (int j = 0; j < kLaneWords + 1; j++) raw[j] = (j <= n_words) ? seq[g + j] : 0u;
+}
+// re-align (base 0 at bit 31 of word 0) and store as the lane's column of shared memory
+__device__ __forceinline__ void lane_put(const uint32_t (&raw)[kLaneWords + 1], const strgpu_segment &sg, uint32_t *rd) {
+  const uint32_t sh = 2u * (sg.base_off & 15u);
+  uint32_t be[kLaneWords + 1];
+#pragma unroll
+  for (int j = 0; j < kLaneWords + 1; j++) be[j] = __byte_perm(raw[j], 0, 0x0123);
+#pragma unroll
+  for (int j = 0; j < kLaneWords; j++) rd[j * 32] = __funnelshift_l(be[j + 1], be[j], sh);
+}
+
 template <int K>
-__global__ void __launch_bounds__(kStageThreads, (K == 5 || K == 6) ? 3 : 4)
+__global__ void __launch_bounds__(kStageThreads, 4)
 ladder_stage(const uint32_t *__restrict__ seq, const strgpu_segment *__restrict__ segs, const UniformReads u,
              const uint16_t *__restrict__ thr, const uint16_t *__restrict__ luts, strgpu_repeat *__restrict__ out,
              uint32_t *__restrict__ scratch, uint32_t n_seg, uint32_t stage_cap) {
@@ -1181,49 +1233,73 @@ ladder_stage(const uint32_t *__restrict__ seq, const strgpu_segment *__restrict_
     n_r = sl.hdr[0];   // long survivors
     n_c = sl.hdr[1];   // short survivors
   } else {
-    n_r = min(sl.hdr[3 + Cfg::list_r], sl.cap);
-    n_c = Cfg::list_c >= 0 ? min(sl.hdr[3 + (Cfg::list_c >= 0 ? Cfg::list_c : 0)], sl.cap) : 0u;
+    n_r = min(sl.hdr[3 + (Cfg::list_r >= 0 ? Cfg::list_r : 0)], sl.cap);
+    n_c = min(sl.hdr[3 + (Cfg::list_c >= 0 ? Cfg::list_c : 0)], sl.cap);
   }
   const uint32_t groups_r = (n_r + 31u) / 32u, n_groups = groups_r + (n_c + 31u) / 32u;
   if (blockIdx.x * kStageWarps >= n_groups) return;   // nothing for this CTA (the grid is sized for the worst case)
   uint16_t *lut = reinterpret_cast<uint16_t *>(smem + kStageWarps * StageSize<K>::warp_words);
-  if (K != 6 && K != 7) {
-    for (int i = tid; i < kLutTotal; i += kStageThreads) lut[i] = luts[i];
+  {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
+    for (int i = tid; i < kLutTotal / 2; i += kStageThreads) dst[i] = reinterpret_cast<const uint32_t *>(luts)[i];
+    if (K == 4) {   // rank tables: 6-mers, then 5-mers
+      for (int i = tid; i < 4096 / 2; i += kStageThreads) dst[kLutTotal / 2 + i] = reinterpret_cast<const uint32_t *>(luts + kLut6)[i];
+      for (int i = tid; i < 1024 / 2; i += kStageThreads) dst[kLutTotal / 2 + 2048 + i] = reinterpret_cast<const uint32_t *>(luts + kLut5R)[i];
+    }
     __syncthreads();
   }
+  const uint16_t *rank6 = lut + kLutTotal, *rank5 = rank6 + 4096;
   uint32_t *warp_base = smem + warp * StageSize<K>::warp_words;
   uint32_t *scr = warp_base + lane;                                   // [word][lane]: recount scratch, counter column
   uint32_t *tab = K == 4 ? scr - (kCls2 + kCls3) * 32 : scr;          // the 4-mer LUT addresses words 34..51 of a full column
   uint32_t *rd = warp_base + Cfg::tab * 32 + lane;                   // [word][lane] read column
   const uint16_t *tg = thr + (size_t)(STRGPU_MAX_PCLASS * 5) * kThrLen;
-  uint32_t *cursor = sl.hdr + 10 + Cfg::cursor;
   const uint32_t *q_r = Cfg::list_r >= 0 ? sl.stage + (size_t)(Cfg::list_r >= 0 ? Cfg::list_r : 0) * 3u * sl.cap : nullptr;
   const uint32_t *q_c = Cfg::list_c >= 0 ? sl.stage + (size_t)(Cfg::list_c >= 0 ? Cfg::list_c : 0) * 3u * sl.cap : nullptr;
 
-  while (true) {
-    uint32_t grp = 0;
-    if (lane == 0) grp = atomicAdd(cursor, 1u);
-    grp = __shfl_sync(kFull, grp, 0);
-    if (grp >= n_groups) break;
-    const bool first_list = grp < groups_r;                            // warp-uniform
+  // groups of 32 entries are dealt round-robin over the grid's warps (no atomic, so the next group is known in advance and
+  // its loads are issued early: its list entry + descriptor while the current group is being counted, its read words while
+  // the current group's list appends wait for their atomics)
+  auto load_item = [&](uint32_t grp) {
+    StageItem it;
+    it.s = 0; it.st = 0; it.extra = 0; it.sg = strgpu_segment{0, 0, 0, 0};
+    const bool first_list = grp < groups_r;
     const uint32_t item = (first_list ? grp : grp - groups_r) * 32u + (uint32_t)lane;
-    const bool active = item < (first_list ? n_r : n_c);
-    const uint32_t act_mask = __ballot_sync(kFull, active);
-    uint32_t s = 0, extra = 0;
-    ScanState st{-1, 0u, 0, 0};
-    int what = 0;   // 0: finished, 1: next count list, 2: recount list
-    if (active) {
+    it.active = grp < n_groups && item < (first_list ? n_r : n_c);
+    if (it.active) {
       if (K == 2) {
-        s = first_list ? sl.listA[item] : sl.listA[n_seg - 1u - item];
+        it.s = first_list ? sl.listA[item] : sl.listA[n_seg - 1u - item];
       } else {
         const uint32_t *q = first_list ? q_r : q_c;
-        s = q[item];
-        st = unpack_state(q[sl.cap + item]);
-        extra = q[2u * sl.cap + item];
+        it.s = q[item];
+        it.st = q[sl.cap + item];
+        it.extra = q[2u * sl.cap + item];
       }
-      const strgpu_segment sg = load_segment(segs, nullptr, u, s);    // lane-path segments hold no non-ACGT base
+      it.sg = load_segment(segs, nullptr, u, it.s);    // lane-path segments hold no non-ACGT base
+    }
+    return it;
+  };
+  const uint32_t warps_total = gridDim.x * kStageWarps;
+  uint32_t grp = blockIdx.x * kStageWarps + warp;
+  if (grp >= n_groups) return;
+  StageItem cur = load_item(grp);
+  uint32_t raw[kLaneWords + 1];
+  lane_fetch(seq, cur.sg, cur.active, raw);
+  while (true) {
+    const bool first_list = grp < groups_r;                            // warp-uniform
+    const bool active = cur.active;
+    const uint32_t act_mask = __ballot_sync(kFull, active);
+    const uint32_t s = cur.s;
+    uint32_t extra = cur.extra;
+    ScanState st = K == 2 ? ScanState{-1, 0u, 0, 0} : unpack_state(cur.st);
+    int what = 0;   // 0: finished, 1: next count list, 2: recount list
+    __syncwarp();
+    if (active) lane_put(raw, cur.sg, rd);
+    const uint32_t next = grp + warps_total;
+    StageItem nxt = load_item(next);                                   // in flight while this group is counted
+    if (active) {
+      const strgpu_segment sg = cur.sg;
       const int L = sg.len;
-      lane_stage(seq, sg, rd);
       const int pclass = sg.pclass < STRGPU_MAX_PCLASS ? sg.pclass : STRGPU_MAX_PCLASS - 1;
       const uint16_t *tp = thr + (size_t)(pclass * 5) * kThrLen + L;
       const bool wide = __any_sync(act_mask, L > 64);
@@ -1243,43 +1319,42 @@ ladder_stage(const uint32_t *__restrict__ seq, const strgpu_segment *__restrict_
           }
         }
       } else {
-        if (Cfg::list_r >= 0 && first_list) {
-          // the recount rung K - 1 was waiting for (utils.nim:254-262)
-          constexpr int KR = K - 1;
+        if (first_list) {
+          // the recount the k = 3 rung was waiting for (utils.nim:254-262)
           const uint32_t leader = (extra >> 8) & 0xfffu;
-          const uint32_t magic = 65536u / (uint32_t)KR + 1u;
-          const int c = wide ? lane_recount<10>(rd, scr, L, leader, KR, magic) : lane_recount<4>(rd, scr, L, leader, KR, magic);
-          const int score = c * KR;
+          const int c = wide ? lane_recount<10>(rd, scr, L, leader, 3, 65536u / 3u + 1u) : lane_recount<4>(rd, scr, L, leader, 3, 65536u / 3u + 1u);
+          const int score = c * 3;
           if (score >= st.best) {
             st.best = score;
-            if (c > (int)tp[(KR - 2) * kThrLen]) {
+            if (c > (int)tp[kThrLen]) {
               st.unit_code = leader;
-              st.unit_k = KR;
+              st.unit_k = 3;
               st.rc = c;
             }
           }
         }
-        if (K <= 6) {
-          int M;
-          uint32_t leader;
-          if (K == 4) lane_count4(rd, tab, lut, L, M, leader);
-          else if (K == 5) lane_count5(rd, tab, lut, L, M, leader);
-          else lane_count6(rd, tab, L, M, leader);
-          if (M * K <= st.best) {                         // no recount: break or continue (utils.nim:250-253)
-            what = (M < (int)tg[(K - 2) * kThrLen + L]) ? 0 : 1;
-          } else {
-            what = 2;
-            extra = (uint32_t)M | (leader << 8);
-          }
-          if (K == 6 && what == 1) what = 0;              // the ladder ends after k = 6
+        // rungs k = 4, 5, 6 (utils.nim:246-265); a false return is the ladder's `break`
+        int M;
+        uint32_t leader;
+        lane_count4(rd, tab, lut, L, M, leader);
+        bool go = lane_decide(rd, scr, L, 4, M, leader, tp[2 * kThrLen], tg[2 * kThrLen + L], st, wide);
+#pragma unroll 1
+        for (int k = 5; k <= 6 && go; k++) {
+          const uint32_t b = lane_count_sorted(rd, k == 5 ? rank5 : rank6, L, k, k == 5 ? kCls5 : kCls6);
+          M = (int)(b >> 21);
+          leader = M ? (uint32_t)luts[(k == 5 ? kRev5 : kRev6) + ((b & 0xffffu) >> 5)] : (1u << (2 * k)) - 1u;   // no window: all ones
+          go = lane_decide(rd, scr, L, k, M, leader, tp[(k - 2) * kThrLen], tg[(k - 2) * kThrLen + L], st, wide);
         }
+        what = 0;
       }
       if (what == 0) emit_result(out, s, st);
     }
     __syncwarp();
-    const uint32_t packed = pack_state(st);
-    if (Cfg::out_r >= 0) stage_push(sl, Cfg::out_r >= 0 ? Cfg::out_r : 0, what == 2, lane, s, packed, extra);
-    if (Cfg::out_c >= 0) stage_push(sl, Cfg::out_c >= 0 ? Cfg::out_c : 0, what == 1, lane, s, packed, 0u);
+    if (next < n_groups) lane_fetch(seq, nxt.sg, nxt.active, raw);     // in flight while the appends wait for their atomics
+    if (Cfg::out_r >= 0 || Cfg::out_c >= 0) stage_push2(sl, Cfg::out_r, Cfg::out_c, what, lane, s, pack_state(st), extra);
+    if (next >= n_groups) break;
+    cur = nxt;
+    grp = next;
   }
 }
 
@@ -1343,6 +1418,30 @@ void build_lane_luts(uint16_t *dst) {
       else dst[lut_off[k] + code] = (uint16_t)(((cls_base[k] + (cls >> 2)) * 128) | ((cls & 3) * 8));  // packed uint8 counters
     }
   }
+  // k = 6: rank of every code's min-rotation class (canonical codes ascend with the rank) and the canonical code of every rank
+  {
+    auto canon6 = [](uint32_t code) {
+      uint32_t m = code, x = code;
+      for (int j = 1; j < 6; j++) {
+        x = ((x << 2) | (x >> 10)) & 0xfffu;
+        if (x < m) m = x;
+      }
+      return m;
+    };
+    int n_classes = 0;
+    uint16_t rank_of[4096];
+    for (uint32_t code = 0; code < 4096; code++)
+      if (canon6(code) == code) {
+        rank_of[code] = (uint16_t)n_classes;
+        dst[kRev6 + n_classes++] = (uint16_t)code;
+      }
+    for (uint32_t code = 0; code < 4096; code++) dst[kLut6 + code] = rank_of[canon6(code)];
+  }
+  // k = 5: class rank of every code, recovered from the packed-counter address table (class = word * 4 + byte)
+  for (int code = 0; code < 1024; code++) {
+    const uint16_t e = dst[kLut5 + code];
+    dst[kLut5R + code] = (uint16_t)((e >> 7) * 4 + ((e & 31) >> 3));
+  }
 }
 
 uint32_t scan_stage_cap(uint32_t n_seg) {
@@ -1372,16 +1471,13 @@ cudaError_t configure_device(int dev) {
   std::call_once(g_attr_once[dev], [dev]() {
     cudaError_t e = set_smem(ladder_stage<2>, StageSize<2>::smem_bytes);
     if (e == cudaSuccess) e = set_smem(ladder_stage<4>, StageSize<4>::smem_bytes);
-    if (e == cudaSuccess) e = set_smem(ladder_stage<5>, StageSize<5>::smem_bytes);
-    if (e == cudaSuccess) e = set_smem(ladder_stage<6>, StageSize<6>::smem_bytes);
-    if (e == cudaSuccess) e = set_smem(ladder_stage<7>, StageSize<7>::smem_bytes);
     g_attr_err[dev] = e;
   });
   return g_attr_err[dev];
 }
 }  // namespace
 
-int scan_launches(uint32_t max_len, int variant) { return (max_len <= (uint32_t)kShortMaxLen && variant != 1) ? 7 : 1; }
+int scan_launches(uint32_t max_len, int variant) { return (max_len <= (uint32_t)kShortMaxLen && variant != 1) ? 4 : 1; }
 
 cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nmask, const uint32_t *d_xmask,
                                const strgpu_segment *d_segs, uint32_t n_seg, uint32_t max_len, const uint16_t *d_thr,
@@ -1422,14 +1518,14 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
       n_tma = u.n_reads / 32u - 1u;
     pre<<<pre_grid, kPreThreads, 0, stream>>>(d_seq_words, d_nmask, d_segs, n_seg, u, d_thr, d_out, d_scratch, cap, n_tma, 1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    static const int max_stage = getenv("STRGPU_MAX_STAGE") ? atoi(getenv("STRGPU_MAX_STAGE")) : 99;   // profiling only: stop early
+    if (max_stage < 2) return cudaSuccess;
     // the ladder kernels: grids sized for the worst case (every segment survives), CTAs without work exit at once
     const uint32_t stage_need = (groups + kStageWarps - 1) / kStageWarps + 1u;
     auto grid_for = [&](int ctas_per_sm) { return std::min((uint32_t)(sm_count * ctas_per_sm), stage_need); };
     ladder_stage<2><<<grid_for(4), kStageThreads, StageSize<2>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
+    if (max_stage < 4) return cudaGetLastError();
     ladder_stage<4><<<grid_for(4), kStageThreads, StageSize<4>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
-    ladder_stage<5><<<grid_for(3), kStageThreads, StageSize<5>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
-    ladder_stage<6><<<grid_for(3), kStageThreads, StageSize<6>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
-    ladder_stage<7><<<grid_for(4), kStageThreads, StageSize<7>::smem_bytes, stream>>>(d_seq_words, d_segs, u, d_thr, d_luts, d_out, d_scratch, n_seg, cap);
     ladder_warp_list<<<grid_for(4), kStageThreads, 0, stream>>>(d_seq_words, d_nmask, d_xmask, d_segs, u, d_thr, d_out, d_status, d_scratch, n_seg, cap);
   } else if (max_len <= (uint32_t)kShortMaxLen) {
     uint32_t grid = (uint32_t)sm_count * 8u;  // 8 resident CTAs of 256 threads per SM

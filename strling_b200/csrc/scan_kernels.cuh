@@ -36,14 +36,14 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
                                cudaStream_t stream, const UniformReads *uniform = nullptr, uint32_t *d_scratch = nullptr);
 
 constexpr uint32_t kScanScratchHdr = 32;   // header words of the scratch buffer (list counts, group cursors)
-constexpr int kScanStageLists = 7;
+constexpr int kScanStageLists = 2;
 uint32_t scan_stage_cap(uint32_t n_seg);
 size_t scan_scratch_words(uint32_t n_seg);
 
 // kernels one launch_repeat_scan call issues (for the library's launch counter)
 int scan_launches(uint32_t max_len, int variant);
 
-constexpr int kLaneLutEntries = 1672;  // see build_lane_luts
+constexpr int kLaneLutEntries = 1672 + 4096 + 700 + 1024;  // see build_lane_luts
 void build_lane_luts(uint16_t *dst);  // host: fills kLaneLutEntries uint16
 
 }  // namespace strgpu

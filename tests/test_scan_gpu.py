@@ -64,21 +64,14 @@ def test_reads_with_N(gpu):
 
 
 def test_iupac_codes_stay_out_of_the_N_gate(gpu):
-    # utils.nim:238 counts the literal 'N' only: a read with > 20 IUPAC ambiguity codes (R, Y, M, ...) and <= 20 N is still
-    # scanned by the reference (the codes scan as 'A' and never match in read.count), one with > 20 N is not
+    # utils.nim:238 counts the literal 'N' only: a read with > 20 non-ACGT bases of which <= 20 are 'N' is still scanned by
+    # the reference (IUPAC codes scan as 'A' and never match in read.count), one with > 20 'N' is not
     reads, cls, lclip, rclip = synth.make_reads(40_000, seed=12, n_frac=0.3, iupac_frac=0.4, mix=(0.3, 0.1, 0.2, 0.4))
     seq2, masks, stride = synth.pack_matrix(reads)
     assert isinstance(masks, sb.Masks)
     segs, _ = synth.segments_for(reads, lclip, rclip, stride)
     res = check(gpu, reads, segs, stride, seq2, masks)
-    n_iupac = ((reads != ord("N")) & ~np.isin(reads, np.frombuffer(b"ACGT", dtype=np.uint8))).sum(axis=1)
-    n_n = (reads == ord("N")).sum(axis=1)
-    gate_cases = np.nonzero((n_iupac + n_n > 20) & (n_n <= 20))[0]          # the old single-plane gate would have dropped these
-    assert len(gate_cases) > 1000 and (res["repeat_count"][gate_cases] > 0).sum() > 50
-    # without the second plane every flagged base counts as N (documented meaning of xmask == NULL): differs from the oracle
-    res1 = gpu.scan(seq2, reads.shape[0] * stride, masks[0], segs)
-    assert (res1["repeat_count"][gate_cases] > 0).sum() == 0
-    # the same reads through the uniform-read entry point and the hand-built pack_reads planes
+    # the same reads through the uniform-read entry point
     out = np.zeros(len(segs), dtype=sb.REPEAT_DTYPE)
     seq2_4, masks_4, stride_4 = synth.pack_matrix(reads, align_bases=4)
     segs_4, _ = synth.segments_for(reads, lclip, rclip, stride_4)
@@ -87,6 +80,31 @@ def test_iupac_codes_stay_out_of_the_N_gate(gpu):
     t = gpu.scan_reads_submit(seq2_4, n, 150, stride_4, 0, masks_4, extra, int(extra["len"].max()), out)
     gpu.scan_wait(t)
     assert np.array_equal(out, res)
+    # crafted: a block of non-ACGT bases (some N, some IUPAC) in front of a clean repeat -- the gate decides the result
+    rng = np.random.default_rng(3)
+    crafted, expect_unit = [], []
+    for unit in ("CAG", "AC", "AAAG", "T", "ACGATC", "TTTCA"):
+        for n_n in (0, 5, 19, 20, 21, 25):
+            for n_x in (0, 1, 2, 10, 16):
+                if n_n + n_x > 28:
+                    continue
+                block = list("N" * n_n + "".join(rng.choice(list("RYMKSWHBVD"), size=n_x)))
+                rng.shuffle(block)
+                body = (unit * 160)[: 150 - len(block)]
+                crafted.append("".join(block) + body)
+                expect_unit.append(n_n <= 20)
+    assert sum(("N" in r and r.count("N") <= 20 and sum(c not in "ACGT" for c in r) > 20) for r in crafted) >= 12
+    seq2c, masks_c, segs_c, n_bases = sb.pack_reads(crafted, 0)
+    got = gpu.scan(seq2c, n_bases, masks_c, segs_c)
+    for r, g, want in zip(crafted, got, expect_unit):
+        exp = orc.get_repeat(r, P[0])
+        assert (bytes(g["unit"]).rstrip(b"\0"), int(g["repeat_count"])) == exp, (r, g, exp)
+        assert want or exp[1] == 0, (r, exp)       # more than 20 literal N: gated away
+    assert sum(int(g["repeat_count"]) > 0 for g, want in zip(got, expect_unit) if want) > 0.9 * sum(expect_unit)
+    # xmask == NULL means "every flagged base is N" (include/strgpu.h): then those reads are gated away, unlike the reference
+    got1 = gpu.scan(seq2c, n_bases, masks_c[0], segs_c)
+    differ = [r for r, g, g1 in zip(crafted, got, got1) if g["repeat_count"] != g1["repeat_count"]]
+    assert len(differ) >= 12 and all(r.count("N") <= 20 < sum(c not in "ACGT" for c in r) for r in differ)
 
 
 def test_all_p_classes_and_unaligned_segments(gpu):
