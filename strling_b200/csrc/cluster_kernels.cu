@@ -3,17 +3,21 @@
 //
 //   K2  stable LSD radix sort of 16-byte (tid, unit, position, index) records: one warp owns one contiguous
 //       chunk, ranks 32 records at a time with match.any, so equal keys keep `.bin` order exactly like the
-//       reference's bucket append + stable sort by position (call.nim:124-130).  Digits whose bits do not vary
-//       are skipped.
+//       reference's bucket append + stable sort by position (call.nim:124-130).  The bits that vary across the
+//       batch (position span, unit span, tid span) are concatenated into one virtual key on the DEVICE (sort_plan), so
+//       only ceil(varying bits / 8) passes do work and the host never reads anything back: every kernel of the
+//       cluster path takes its sizes from device memory and the whole path is enqueued without a synchronisation.
 //   K3  next(i) = first read NOT absorbed by a cluster started at read i (trcluster, cluster.nim:323-362) is a
 //       pure function of i: <= 8 explicit steps while the median-of-first-9 still moves, then one binary search.
 //       Bucket heads then chase next() to mark cluster starts; the chase is cut into 256-record pieces (exit tables per
-//       piece, a piece-to-piece hop per bucket, a marking sweep per piece) so it stays parallel for huge buckets.
+//       piece, a piece-to-piece hop per bucket, a marking sweep per piece) so it stays parallel for huge buckets.  A piece
+//       is handled by one warp with its next[] slice in shared memory: exits and marks by pointer doubling (8 rounds).
 //   K4  one thread per chained cluster: trim, left/right_most, min_support + anchor test, split_cluster, bounds,
 //       filters, has_per_sample_reads.  CountTable.largest ties follow Nim's slot order (hashWangYi1 + linear
 //       probing + growth), emulated in a per-cluster scratch region.
 #include "cluster_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 namespace strgpu {
@@ -56,7 +60,19 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_block_sums(const uint32_t *in, uint32_t n, uint32_t *block_sums) {
+// Exclusive scan of n uint32 in two launches.  n comes from device memory (*d_n, capped at n_max); `gate` (may be null)
+// names a device flag: when it is zero both kernels return at once (an inactive radix pass).
+//   scan_block_sums : per-tile totals; the LAST block to finish (ticket) scans the totals in place and writes the grand total
+//   scan_apply      : rescans each tile with its offset
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums(const uint32_t *in, const uint32_t *d_n, uint32_t n_max, uint32_t *block_sums,
+                                                                uint32_t *ticket, uint32_t *total_out, const uint32_t *gate) {
+  if (gate && *gate == 0u) return;
+  const uint32_t n = min(*d_n, n_max);
+  const uint32_t n_blocks = (n + kScanTile - 1) / kScanTile;
+  if (blockIdx.x >= n_blocks) {
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
+    return;
+  }
   const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   uint32_t s = 0;
 #pragma unroll
@@ -64,25 +80,36 @@ __global__ void __launch_bounds__(kScanThreads) scan_block_sums(const uint32_t *
     if (base + j < n) s += in[base + j];
   uint32_t total;
   block_exclusive_scan(s, &total);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_single_block(uint32_t *data, uint32_t n, uint32_t *total_out) {
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < n; base += kScanThreads) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < n ? data[i] : 0;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan(v, &total);
-    if (i < n) data[i] = carry + ex;
-    carry += total;
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    block_sums[blockIdx.x] = total;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == n_blocks - 1u;
   }
-  if (threadIdx.x == 0 && total_out) *total_out = carry;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  uint32_t carry = 0;
+  for (uint32_t b0 = 0; b0 < n_blocks; b0 += kScanThreads) {
+    const uint32_t i = b0 + threadIdx.x;
+    const uint32_t v = i < n_blocks ? reinterpret_cast<volatile uint32_t *>(block_sums)[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan(v, &tot);
+    if (i < n_blocks) block_sums[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    if (total_out) *total_out = carry;
+    *ticket = 0;   // ready for the next scan on this stream
+  }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t *in, uint32_t n, const uint32_t *block_offsets,
-                                                           uint32_t *out) {
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t *in, const uint32_t *d_n, uint32_t n_max, const uint32_t *block_offsets,
+                                                           uint32_t *out, const uint32_t *gate) {
+  if (gate && *gate == 0u) return;
+  const uint32_t n = min(*d_n, n_max);
   const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  if (blockIdx.x * kScanTile >= n) return;
   uint32_t v[kScanItems];
   uint32_t s = 0;
 #pragma unroll
@@ -149,16 +176,77 @@ __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint3
   if (threadIdx.x < 3 && blk[threadIdx.x]) atomicOr(&varbits[threadIdx.x], blk[threadIdx.x]);
 }
 
-__device__ __forceinline__ uint32_t digit_of(const SortRec &r, int field, int shift) {
-  const uint32_t v = field == 0 ? r.pos : (field == 1 ? r.mid : r.hi);
-  return (v >> shift) & 0xffu;
+// ---- device-side sort plan.  Small device words (d_small), all uint32:
+//   [0..2] bits that vary across the batch in pos / unit / tid (make_sort_records)      [3] clusters chained (K3)
+//   [5] records entering K3 (n, or what assign_reads_locus left)    [6] scan ticket     [7] scratch bump pointer (K4)
+//   [8] 2 * clusters (length of the K4 compaction scan)   [9] length of the radix count matrix   [15] which ping-pong buffer holds the sorted records
+//   [16 + p] radix pass p does work     [32 + p] its source buffer
+//   [48 + f], [51 + f], [54 + f] lowest varying bit / width / offset in the virtual key of field f (0 pos, 1 unit, 2 tid)
+constexpr int kSmallWords = 64;
+constexpr int kMaxPasses = 12;   // 32 + 18 + 32 varying bits at most, 8 per pass
+enum { SM_VAR = 0, SM_NCLUSTERS = 3, SM_NCUR = 5, SM_TICKET = 6, SM_BUMP = 7, SM_N2 = 8, SM_COUNTLEN = 9, SM_FINAL = 15, SM_ACTIVE = 16, SM_SRC = 32,
+       SM_LO = 48, SM_WIDTH = 51, SM_OFF = 54 };
+
+__global__ void sort_plan(uint32_t *small, uint32_t n, uint32_t count_len) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  small[SM_COUNTLEN] = count_len;
+  uint32_t off = 0;
+  for (int f = 0; f < 3; f++) {
+    const uint32_t var = small[SM_VAR + f];
+    const uint32_t lo = var ? (uint32_t)(__ffs(var) - 1) : 0u;
+    const uint32_t width = var ? (uint32_t)(32 - __clz(var)) - lo : 0u;
+    small[SM_LO + f] = lo;
+    small[SM_WIDTH + f] = width;
+    small[SM_OFF + f] = off;
+    off += width;
+  }
+  uint32_t src = 0;
+  for (int p = 0; p < kMaxPasses; p++) {
+    const uint32_t active = (uint32_t)(8 * p) < off ? 1u : 0u;
+    small[SM_ACTIVE + p] = active;
+    small[SM_SRC + p] = src;
+    src ^= active;
+  }
+  small[SM_FINAL] = src;
+  small[SM_NCUR] = n;
+}
+
+// the pass's 8-bit digit of the virtual key: the varying spans of pos, unit and tid, concatenated (pos least significant)
+struct DigitPlan {
+  uint32_t lo[3], mask[3];
+  int rel[3];   // bit offset of the field's span relative to the digit's bit 0
+};
+__device__ __forceinline__ DigitPlan load_digit_plan(const uint32_t *small, int pass) {
+  DigitPlan d;
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    const uint32_t w = small[SM_WIDTH + f];
+    d.lo[f] = small[SM_LO + f];
+    d.mask[f] = w >= 32u ? 0xffffffffu : ((1u << w) - 1u);
+    d.rel[f] = (int)small[SM_OFF + f] - 8 * pass;
+  }
+  return d;
+}
+__device__ __forceinline__ uint32_t digit_of(const SortRec &r, const DigitPlan &d) {
+  uint32_t out = 0;
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    const uint32_t v = ((f == 0 ? r.pos : (f == 1 ? r.mid : r.hi)) >> d.lo[f]) & d.mask[f];
+    const int rel = d.rel[f];
+    if (rel >= 0) out |= rel < 8 ? (v << rel) : 0u;
+    else out |= rel > -32 ? (v >> (-rel)) : 0u;
+  }
+  return out & 0xffu;
 }
 
 constexpr int kSortWarps = 8;
 
-__global__ void __launch_bounds__(kSortWarps * 32) radix_histogram(const SortRec *__restrict__ in, uint32_t n, uint32_t chunk,
-                                                                   uint32_t n_chunks, int field, int shift,
+__global__ void __launch_bounds__(kSortWarps * 32) radix_histogram(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, uint32_t n,
+                                                                   uint32_t chunk, uint32_t n_chunks, const uint32_t *__restrict__ small, int pass,
                                                                    uint32_t *__restrict__ counts) {
+  if (small[SM_ACTIVE + pass] == 0u) return;
+  const SortRec *in = small[SM_SRC + pass] ? buf1 : buf0;
+  const DigitPlan dp = load_digit_plan(small, pass);
   __shared__ uint32_t hist[kSortWarps][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t w = blockIdx.x * kSortWarps + warp;
@@ -167,15 +255,20 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_histogram(const SortRec
   if (w < n_chunks) {
     const uint32_t beg = w * chunk;
     const uint32_t end = min(n, beg + chunk);
-    for (uint32_t i = beg + lane; i < end; i += 32) atomicAdd(&hist[warp][digit_of(in[i], field, shift)], 1u);
+    for (uint32_t i = beg + lane; i < end; i += 32) atomicAdd(&hist[warp][digit_of(in[i], dp)], 1u);
     __syncwarp();
     for (int d = lane; d < 256; d += 32) counts[(size_t)d * n_chunks + w] = hist[warp][d];
   }
 }
 
-__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(const SortRec *__restrict__ in, SortRec *__restrict__ out,
-                                                                 uint32_t n, uint32_t chunk, uint32_t n_chunks, int field,
-                                                                 int shift, const uint32_t *__restrict__ offsets) {
+__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(SortRec *__restrict__ buf0, SortRec *__restrict__ buf1, uint32_t n, uint32_t chunk,
+                                                                 uint32_t n_chunks, const uint32_t *__restrict__ small, int pass,
+                                                                 const uint32_t *__restrict__ offsets) {
+  if (small[SM_ACTIVE + pass] == 0u) return;
+  const bool flip = small[SM_SRC + pass] != 0u;
+  const SortRec *in = flip ? buf1 : buf0;
+  SortRec *out = flip ? buf0 : buf1;
+  const DigitPlan dp = load_digit_plan(small, pass);
   __shared__ uint32_t off[kSortWarps][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t w = blockIdx.x * kSortWarps + warp;
@@ -190,7 +283,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(const SortRec *
     const bool valid = i < end;
     SortRec r{0, 0, 0, 0};
     if (valid) r = in[i];
-    const uint32_t d = valid ? digit_of(r, field, shift) : (0x100u + (uint32_t)lane);
+    const uint32_t d = valid ? digit_of(r, dp) : (0x100u + (uint32_t)lane);
     const uint32_t grp = __match_any_sync(kFull, d);
     uint32_t dst = 0;
     if (valid) dst = off[warp][d] + __popc(grp & lane_lt);  // lane order == input order: stable
@@ -201,10 +294,22 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(const SortRec *
   }
 }
 
-__global__ void gather_treads(const strgpu_tread *__restrict__ treads, const SortRec *__restrict__ recs, uint32_t n,
-                              strgpu_tread *__restrict__ sorted) {
+// after assign_reads_locus: the records kept (left in SM_NCLUSTERS by the compaction scan) are what K3 works on
+__global__ void set_ncur(uint32_t *small) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  small[SM_NCUR] = small[SM_NCLUSTERS];
+  small[SM_NCLUSTERS] = 0;
+}
+
+__device__ __forceinline__ const SortRec *sorted_recs(const SortRec *buf0, const SortRec *buf1, const uint32_t *small) {
+  return small[SM_FINAL] ? buf1 : buf0;
+}
+
+__global__ void gather_treads(const strgpu_tread *__restrict__ treads, const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1,
+                              const uint32_t *__restrict__ small, uint32_t n, strgpu_tread *__restrict__ sorted) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const SortRec *recs = sorted_recs(buf0, buf1, small);
   const unsigned long long *src = reinterpret_cast<const unsigned long long *>(treads + recs[i].idx);
   unsigned long long *dst = reinterpret_cast<unsigned long long *>(sorted + i);
   dst[0] = src[0];
@@ -215,11 +320,13 @@ __global__ void gather_treads(const strgpu_tread *__restrict__ treads, const Sor
 // ------------------------------------------------------------------------------------------- C10 assign_reads_locus
 // One thread per chain (= the loci of one bucket, in file order): callclusters.nim:14-50 on the sorted records with
 // removal expressed as marks.  Earlier loci change what later loci of the same bucket see, hence the serial chain.
-__global__ void assign_loci(const SortRec *__restrict__ recs, const strgpu_tread *__restrict__ sorted, uint32_t n,
+__global__ void assign_loci(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, const uint32_t *__restrict__ small,
+                            const strgpu_tread *__restrict__ sorted, uint32_t n,
                             const DevLocus *__restrict__ loci, const uint32_t *__restrict__ chain_start, uint32_t n_chains,
                             uint32_t *__restrict__ removed, uint16_t *__restrict__ counts) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_chains) return;
+  const SortRec *recs = sorted_recs(buf0, buf1, small);
   const DevLocus first = loci[chain_start[c]];
   // bucket [bs, be): records whose (hi, mid) equals the key
   uint32_t lo = 0, hi = n;
@@ -268,11 +375,14 @@ __global__ void invert_flags(const uint32_t *__restrict__ removed, uint32_t n, u
   if (i < n) keep[i] = removed[i] ? 0u : 1u;
 }
 
-__global__ void compact_sorted(const SortRec *__restrict__ recs, const strgpu_tread *__restrict__ sorted, const uint32_t *__restrict__ keep,
-                               const uint32_t *__restrict__ dst, uint32_t n, SortRec *__restrict__ recs_out,
-                               strgpu_tread *__restrict__ sorted_out) {
+__global__ void compact_sorted(SortRec *__restrict__ buf0, SortRec *__restrict__ buf1, const uint32_t *__restrict__ small,
+                               const strgpu_tread *__restrict__ sorted, const uint32_t *__restrict__ keep,
+                               const uint32_t *__restrict__ dst, uint32_t n, strgpu_tread *__restrict__ sorted_out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !keep[i]) return;
+  const bool fin = small[SM_FINAL] != 0u;
+  const SortRec *recs = fin ? buf1 : buf0;
+  SortRec *recs_out = fin ? buf0 : buf1;   // the kept records land in the other ping-pong buffer
   const uint32_t d = dst[i];
   recs_out[d] = recs[i];
   const unsigned long long *src = reinterpret_cast<const unsigned long long *>(sorted + i);
@@ -283,11 +393,20 @@ __global__ void compact_sorted(const SortRec *__restrict__ recs, const strgpu_tr
 // ------------------------------------------------------------------------------------------- K3 chain
 __device__ __forceinline__ bool same_bucket(const SortRec &a, const SortRec &b) { return a.hi == b.hi && a.mid == b.mid; }
 
-__global__ void cluster_next(const SortRec *__restrict__ recs, uint32_t n, uint32_t max_dist, uint32_t *__restrict__ next,
-                             uint32_t *__restrict__ bucket_end, uint32_t *__restrict__ head) {
+// recs of K3: the sorted buffer, or the other one when assign_reads_locus compacted into it (flip == 1)
+__device__ __forceinline__ const SortRec *k3_recs(const SortRec *buf0, const SortRec *buf1, const uint32_t *small, int flip) {
+  return ((small[SM_FINAL] != 0u) != (flip != 0)) ? buf1 : buf0;
+}
+
+__global__ void cluster_next(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, const uint32_t *__restrict__ small, int flip,
+                             uint32_t max_dist, uint32_t *__restrict__ next, uint32_t *__restrict__ bucket_end, uint32_t *__restrict__ head,
+                             uint32_t *__restrict__ entry_flag) {
+  const uint32_t n = small[SM_NCUR];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const SortRec *recs = k3_recs(buf0, buf1, small, flip);
   head[i] = 0;
+  entry_flag[i] = 0;
   const SortRec me = recs[i];
   // end of my (tid, unit) bucket: first index whose bucket key differs (records are sorted)
   uint32_t lo = i + 1, hi = n;
@@ -321,60 +440,118 @@ __global__ void cluster_next(const SortRec *__restrict__ recs, uint32_t n, uint3
 }
 
 // Cluster starts = the chain bucket_start -> next -> next ... of every bucket.  The walk is cut into pieces of kSeg records
-// so that no thread takes more than kSeg steps (a bucket can hold 10^5 reads):
-//   seg_exits : for every record i of a piece, exit[i] = the first index >= the piece's end that the chain through i reaches
-//               (a reverse sweep of the piece; next[i] > i always)
-//   seg_entry : one thread per bucket hops piece to piece (entry -> exit[entry]) and records each piece's entry point
-//   seg_mark  : one thread per entered piece marks the cluster starts inside it
+// so that no thread takes more than a few steps (a bucket can hold 10^5 reads):
+//   piece_exits : for every record i of a piece, exit[i] = the first index >= the piece's end that the chain through i reaches
+//                 (or the index at which the chain leaves its bucket)
+//   bucket_entry: one thread per bucket hops piece to piece (entry -> exit[entry]) and flags each piece's entry point
+//   piece_mark  : marks the cluster starts inside every piece, from its flagged entry points
+// A piece is one warp's job with its slice of next[] in shared memory; both sweeps are pointer doubling (8 rounds of 8
+// records per lane) instead of a serial walk at L2 latency.
 constexpr uint32_t kSeg = 256;
+constexpr int kPieceWarps = 8;
+constexpr uint32_t kTerm = 0x80000000u;   // "this value is final" (record counts stay below 2^31)
 
-__global__ void seg_exits(const uint32_t *__restrict__ next, const uint32_t *__restrict__ bucket_end, uint32_t n,
-                          uint32_t *__restrict__ exit_of) {
-  const uint32_t sgi = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lo = sgi * kSeg;
+__global__ void __launch_bounds__(kPieceWarps * 32) piece_exits(const uint32_t *__restrict__ next, const uint32_t *__restrict__ bucket_end,
+                                                                const uint32_t *__restrict__ small, uint32_t *__restrict__ exit_of) {
+  __shared__ uint32_t ex[kPieceWarps][kSeg];
+  const uint32_t n = small[SM_NCUR];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lo = (blockIdx.x * kPieceWarps + warp) * kSeg;
   if (lo >= n) return;
   const uint32_t hi = min(n, lo + kSeg);
-  for (uint32_t i = hi; i-- > lo;) {
-    const uint32_t nx = next[i];
-    // a chain never leaves its bucket: next[i] <= bucket_end[i]; stop at the piece end or the bucket end
-    exit_of[i] = (nx >= hi || nx >= bucket_end[i]) ? nx : exit_of[nx];
+  uint32_t *e = ex[warp];
+  // a chain never leaves its bucket: next[i] <= bucket_end[i]; it is final when it reaches the piece end or the bucket end
+  for (uint32_t t = lane; t < kSeg; t += 32) {
+    const uint32_t i = lo + t;
+    uint32_t v = kTerm;
+    if (i < hi) {
+      const uint32_t nx = next[i];
+      v = (nx >= hi || nx >= bucket_end[i]) ? (nx | kTerm) : nx;
+    }
+    e[t] = v;
   }
+  __syncwarp();
+  for (int round = 0; round < 8; round++) {   // path lengths double every round: 2^8 = kSeg
+    uint32_t nv[kSeg / 32];
+#pragma unroll
+    for (int q = 0; q < (int)(kSeg / 32); q++) {
+      const uint32_t v = e[q * 32 + lane];
+      nv[q] = (v & kTerm) ? v : e[v - lo];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < (int)(kSeg / 32); q++) e[q * 32 + lane] = nv[q];
+    __syncwarp();
+  }
+  for (uint32_t t = lane; t < kSeg; t += 32)
+    if (lo + t < hi) exit_of[lo + t] = e[t] & ~kTerm;
 }
 
-__global__ void seg_entry(const SortRec *__restrict__ recs, uint32_t n, const uint32_t *__restrict__ bucket_end,
-                          const uint32_t *__restrict__ exit_of, uint32_t *__restrict__ entry_of_seg) {
+__global__ void bucket_entry(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, const uint32_t *__restrict__ small, int flip,
+                             const uint32_t *__restrict__ bucket_end, const uint32_t *__restrict__ exit_of, uint32_t *__restrict__ entry_flag) {
+  const uint32_t n = small[SM_NCUR];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const SortRec *recs = k3_recs(buf0, buf1, small, flip);
   if (i > 0 && same_bucket(recs[i - 1], recs[i])) return;  // bucket starts only
   const uint32_t be = bucket_end[i];
   uint32_t h = i;
   while (h < be) {
-    // several buckets can start inside one piece: keep the piece's entries as a linked list through the records
-    entry_of_seg[h] = 1;   // h is a cluster start and the point where the chain enters (or re-enters) its piece
+    entry_flag[h] = 1;   // h is a cluster start and the point where the chain enters (or re-enters) a piece
     h = exit_of[h];
   }
 }
 
-__global__ void seg_mark(const uint32_t *__restrict__ next, const uint32_t *__restrict__ bucket_end, uint32_t n,
-                         const uint32_t *__restrict__ entry_flag, uint32_t *__restrict__ head) {
-  const uint32_t sgi = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lo = sgi * kSeg;
+__global__ void __launch_bounds__(kPieceWarps * 32) piece_mark(const uint32_t *__restrict__ next, const uint32_t *__restrict__ bucket_end,
+                                                               const uint32_t *__restrict__ small, const uint32_t *__restrict__ entry_flag,
+                                                               uint32_t *__restrict__ head) {
+  __shared__ uint32_t jump[kPieceWarps][kSeg];
+  __shared__ uint32_t mark[kPieceWarps][kSeg];
+  const uint32_t n = small[SM_NCUR];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lo = (blockIdx.x * kPieceWarps + warp) * kSeg;
   if (lo >= n) return;
   const uint32_t hi = min(n, lo + kSeg);
-  for (uint32_t e = lo; e < hi; e++) {
-    if (!entry_flag[e]) continue;          // chains enter the piece here (one per bucket that touches the piece)
-    const uint32_t be = bucket_end[e];
-    uint32_t h = e;
-    while (h < hi && h < be) {
-      head[h] = 1;
-      h = next[h];
+  uint32_t *jp = jump[warp], *mk = mark[warp];
+  uint32_t any = 0;
+  for (uint32_t t = lane; t < kSeg; t += 32) {
+    const uint32_t i = lo + t;
+    uint32_t j = kTerm, m = 0;
+    if (i < hi) {
+      const uint32_t nx = next[i];
+      j = (nx >= hi || nx >= bucket_end[i]) ? kTerm : nx - lo;   // successor inside the piece and the bucket, else none
+      m = entry_flag[i];
     }
+    jp[t] = j;
+    mk[t] = m;
+    any |= m;
   }
+  if (__ballot_sync(kFull, any != 0u) == 0u) return;   // no chain enters this piece (warp-uniform)
+  __syncwarp();
+  for (int round = 0; round < 8; round++) {
+    // every marked record marks its 2^round-th successor; then the jump distance doubles
+    uint32_t nj[kSeg / 32];
+#pragma unroll
+    for (int q = 0; q < (int)(kSeg / 32); q++) {
+      const uint32_t t = q * 32 + lane;
+      const uint32_t j = jp[t];
+      if (mk[t] && !(j & kTerm)) mk[j] = 1;     // concurrent writers all store 1
+      nj[q] = (j & kTerm) ? j : jp[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < (int)(kSeg / 32); q++) jp[q * 32 + lane] = nj[q];
+    __syncwarp();
+  }
+  for (uint32_t t = lane; t < kSeg; t += 32)
+    if (lo + t < hi && mk[t]) head[lo + t] = 1;
 }
 
 __global__ void cluster_fill(const uint32_t *__restrict__ head, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ next,
-                             uint32_t n, uint32_t *__restrict__ cl_start, uint32_t *__restrict__ cl_end) {
+                             uint32_t *__restrict__ small, uint32_t *__restrict__ cl_start, uint32_t *__restrict__ cl_end) {
+  const uint32_t n = small[SM_NCUR];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) small[SM_N2] = 2u * small[SM_NCLUSTERS];
   if (i >= n || !head[i]) return;
   cl_start[cid[i]] = i;
   cl_end[cid[i]] = next[i];
@@ -544,13 +721,15 @@ __device__ bool bounds_of(const strgpu_tread *__restrict__ reads, uint32_t a, ui
 }
 
 __global__ void cluster_bounds(const strgpu_tread *__restrict__ reads, const uint32_t *__restrict__ cl_start,
-                               const uint32_t *__restrict__ cl_end, uint32_t n_clusters, strgpu_cluster_params p,
-                               Slot *__restrict__ scratch_all, strgpu_bounds *__restrict__ out2, uint32_t *__restrict__ valid2) {
+                               const uint32_t *__restrict__ cl_end, uint32_t *__restrict__ small, strgpu_cluster_params p,
+                               Slot *__restrict__ scratch_all, uint32_t scratch_slots, strgpu_bounds *__restrict__ out2,
+                               uint32_t *__restrict__ valid2) {
+  const uint32_t n_clusters = small[SM_NCLUSTERS];
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_clusters) return;
   uint32_t a = cl_start[c];
   const uint32_t b = cl_end[c];
-  Slot *scratch = scratch_all + ((size_t)32 * c + (size_t)8 * a);
+  Slot *scratch = nullptr;   // claimed below, only by clusters that get past the min_support / anchor tests
   valid2[2 * c] = 0;
   valid2[2 * c + 1] = 0;
   const strgpu_tread first = reads[a];
@@ -583,6 +762,14 @@ __global__ void cluster_bounds(const strgpu_tread *__restrict__ reads, const uin
   bool anchor = false;
   for (uint32_t i = a; i < b && !anchor; i++) anchor = reads[i].split == SOFT_NONE;
   if (!anchor) return;
+  {
+    // scratch for the CountTable replay (16 + 4 * reads slots, twice) and the per-sample counter (<= 4 * reads + 16): bump-allocated,
+    // so its size follows the clusters that need it (at most reads / max(1, min_support) of them) instead of the worst case
+    const uint32_t need = 32u + 8u * (b - a);
+    const uint32_t off = atomicAdd(small + SM_BUMP, need);
+    if (off + need > scratch_slots) return;   // cannot happen: the pool is sized for every cluster that can get here (run_cluster)
+    scratch = scratch_all + off;
+  }
   // split_cluster (cluster.nim:283-320)
   uint32_t sub_a[2] = {a, 0}, sub_b[2] = {b, 0}, sub_lm[2] = {cl_left_most, 0}, sub_rm[2] = {cl_right_most, 0};
   int n_sub = 1;
@@ -611,7 +798,9 @@ __global__ void cluster_bounds(const strgpu_tread *__restrict__ reads, const uin
 }
 
 __global__ void compact_bounds(const strgpu_bounds *__restrict__ out2, const uint32_t *__restrict__ valid2,
-                               const uint32_t *__restrict__ dst_idx, uint32_t n2, strgpu_bounds *__restrict__ out, uint32_t cap) {
+                               const uint32_t *__restrict__ dst_idx, const uint32_t *__restrict__ small, strgpu_bounds *__restrict__ out,
+                               uint32_t cap) {
+  const uint32_t n2 = small[SM_N2];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n2 || !valid2[i]) return;
   const uint32_t d = dst_idx[i];
@@ -620,7 +809,8 @@ __global__ void compact_bounds(const strgpu_bounds *__restrict__ out2, const uin
 
 // ------------------------------------------------------------------------------------------- host driver
 enum { WS_RECS_A, WS_RECS_B, WS_COUNTS, WS_BLOCKSUMS, WS_SORTED, WS_NEXT, WS_BEND, WS_HEAD, WS_CID, WS_CLSTART, WS_CLEND,
-       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL, WS_SORTED_B };
+       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL, WS_SORTED_B, WS_ENTRY, WS_COUNT_ };
+static_assert(WS_COUNT_ <= (int)(sizeof(ClusterWorkspace::buf) / sizeof(void *)), "workspace slots");
 
 cudaError_t ws_ensure(ClusterWorkspace &ws, int which, size_t bytes) {
   if (bytes <= ws.cap[which]) return cudaSuccess;
@@ -639,16 +829,16 @@ cudaError_t ws_ensure(ClusterWorkspace &ws, int which, size_t bytes) {
     if (e_ != cudaSuccess) return e_;      \
   } while (0)
 
-// exclusive scan of n uint32 (in -> out, may alias), total to *d_total (device)
-cudaError_t exclusive_scan(ClusterWorkspace &ws, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *d_total,
-                           cudaStream_t st, uint64_t *launches) {
-  const uint32_t blocks = (n + kScanTile - 1) / kScanTile;
-  CK(ws_ensure(ws, WS_BLOCKSUMS, (size_t)(blocks + 1) * 4));
+// exclusive scan of *d_n (<= n_max) uint32 (in -> out, may alias), total to *d_total (device); see scan_block_sums
+cudaError_t exclusive_scan(ClusterWorkspace &ws, const uint32_t *in, uint32_t *out, const uint32_t *d_n, uint32_t n_max, uint32_t *d_total,
+                           const uint32_t *gate, cudaStream_t st, uint64_t *launches) {
+  if (n_max == 0) return cudaSuccess;
+  const uint32_t blocks = (n_max + kScanTile - 1) / kScanTile;
   uint32_t *bs = (uint32_t *)ws.buf[WS_BLOCKSUMS];
-  scan_block_sums<<<blocks, kScanThreads, 0, st>>>(in, n, bs);
-  scan_single_block<<<1, kScanThreads, 0, st>>>(bs, blocks, d_total);
-  scan_apply<<<blocks, kScanThreads, 0, st>>>(in, n, bs, out);
-  *launches += 3;
+  uint32_t *small = (uint32_t *)ws.buf[WS_SMALL];
+  scan_block_sums<<<blocks, kScanThreads, 0, st>>>(in, d_n, n_max, bs, small + SM_TICKET, d_total, gate);
+  scan_apply<<<blocks, kScanThreads, 0, st>>>(in, d_n, n_max, bs, out, gate);
+  *launches += 2;
   return cudaGetLastError();
 }
 
@@ -672,7 +862,7 @@ uint32_t unit_rank_host(const char repeat[6]) {
 }
 
 void free_workspace(ClusterWorkspace &ws) {
-  for (int i = 0; i < 17; i++) {
+  for (int i = 0; i < 20; i++) {
     if (ws.buf[i]) cudaFree(ws.buf[i]);
     ws.buf[i] = nullptr;
     ws.cap[i] = 0;
@@ -682,111 +872,99 @@ void free_workspace(ClusterWorkspace &ws) {
 cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
                         strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t st, uint64_t *launches,
                         const LociArgs *loci) {
+  // Everything below is enqueued on `st` and nothing is read back: sizes the host does not know (how many digits vary, how
+  // many records assign_reads_locus leaves, how many clusters were chained) stay in device memory (d_small) and the
+  // kernels that depend on them are launched for the worst case n.
   if (n == 0) return cudaMemsetAsync(d_n_out, 0, 4, st);
+  if (n >= 0x80000000u) return cudaErrorInvalidValue;
   const int T = 256;
   const uint32_t nb = (n + T - 1) / T;
-  CK(ws_ensure(ws, WS_RECS_A, (size_t)n * sizeof(SortRec)));
-  CK(ws_ensure(ws, WS_RECS_B, (size_t)n * sizeof(SortRec)));
-  CK(ws_ensure(ws, WS_SMALL, 64));
-  uint32_t *d_small = (uint32_t *)ws.buf[WS_SMALL];  // [0..2] varying bits, [3] n_clusters, [4] n_out
-  CK(cudaMemsetAsync(d_small, 0, 64, st));
-  SortRec *ra = (SortRec *)ws.buf[WS_RECS_A], *rb = (SortRec *)ws.buf[WS_RECS_B];
-  make_sort_records<<<nb, T, 0, st>>>(d_treads, n, ra, d_small);
-  ++*launches;
-  uint32_t var[3];
-  CK(cudaMemcpyAsync(var, d_small, 12, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-
-  // ---- K2: LSD radix sort, least significant field first: position, unit, tid
   uint32_t chunk = 1024;
   while ((n + chunk - 1) / chunk > 8192) chunk *= 2;
   const uint32_t n_chunks = (n + chunk - 1) / chunk;
   const uint32_t sort_blocks = (n_chunks + kSortWarps - 1) / kSortWarps;
+  const bool with_loci = loci && loci->n_chains;
+  // K4 scratch pool: 32 + 8 * reads slots per cluster that passes the min_support test (at most n / max(1, min_support) of them)
+  const size_t scratch_slots = (size_t)8 * n + (size_t)32 * (n / (uint32_t)(p.min_support > 1 ? p.min_support : 1)) + 64;
+  const uint32_t scan_max = std::max<uint32_t>(2u * n, 256u * n_chunks);
+  CK(ws_ensure(ws, WS_RECS_A, (size_t)n * sizeof(SortRec)));
+  CK(ws_ensure(ws, WS_RECS_B, (size_t)n * sizeof(SortRec)));
+  CK(ws_ensure(ws, WS_SMALL, kSmallWords * 4));
   CK(ws_ensure(ws, WS_COUNTS, (size_t)256 * n_chunks * 4));
-  uint32_t *counts = (uint32_t *)ws.buf[WS_COUNTS];
-  for (int field = 0; field < 3; field++)
-    for (int shift = 0; shift < 32; shift += 8) {
-      if (((var[field] >> shift) & 0xffu) == 0) continue;  // this digit is the same everywhere
-      radix_histogram<<<sort_blocks, kSortWarps * 32, 0, st>>>(ra, n, chunk, n_chunks, field, shift, counts);
-      ++*launches;
-      CK(exclusive_scan(ws, counts, counts, 256 * n_chunks, nullptr, st, launches));
-      radix_scatter<<<sort_blocks, kSortWarps * 32, 0, st>>>(ra, rb, n, chunk, n_chunks, field, shift, counts);
-      ++*launches;
-      SortRec *t = ra; ra = rb; rb = t;
-    }
+  CK(ws_ensure(ws, WS_BLOCKSUMS, ((size_t)(scan_max + kScanTile - 1) / kScanTile + 1) * 4));
   CK(ws_ensure(ws, WS_SORTED, (size_t)n * sizeof(strgpu_tread)));
-  strgpu_tread *sorted = (strgpu_tread *)ws.buf[WS_SORTED];
-  gather_treads<<<nb, T, 0, st>>>(d_treads, ra, n, sorted);
-  ++*launches;
-
-  // ---- C10: loci take their reads out of the sorted buckets before clustering
-  if (loci && loci->n_chains) {
-    CK(ws_ensure(ws, WS_HEAD, (size_t)n * 4));
-    CK(ws_ensure(ws, WS_NEXT, (size_t)n * 4));
-    CK(ws_ensure(ws, WS_CID, (size_t)n * 4));
-    CK(ws_ensure(ws, WS_SORTED_B, (size_t)n * sizeof(strgpu_tread)));
-    uint32_t *removed = (uint32_t *)ws.buf[WS_HEAD], *keep = (uint32_t *)ws.buf[WS_NEXT], *dst = (uint32_t *)ws.buf[WS_CID];
-    CK(cudaMemsetAsync(removed, 0, (size_t)n * 4, st));
-    assign_loci<<<(loci->n_chains + 63) / 64, 64, 0, st>>>(ra, sorted, n, loci->d_loci, loci->d_chain_start, loci->n_chains, removed,
-                                                            loci->d_counts);
-    invert_flags<<<nb, T, 0, st>>>(removed, n, keep);
-    *launches += 2;
-    CK(exclusive_scan(ws, keep, dst, n, d_small + 5, st, launches));
-    strgpu_tread *sorted_b = (strgpu_tread *)ws.buf[WS_SORTED_B];
-    compact_sorted<<<nb, T, 0, st>>>(ra, sorted, keep, dst, n, rb, sorted_b);
-    ++*launches;
-    uint32_t n_kept = 0;
-    CK(cudaMemcpyAsync(&n_kept, d_small + 5, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    SortRec *t = ra; ra = rb; rb = t;
-    sorted = sorted_b;
-    n = n_kept;
-    if (n == 0) return cudaMemsetAsync(d_n_out, 0, 4, st);
-  }
-  const uint32_t nb2 = (n + T - 1) / T;
-
-  // ---- K3: next(i), bucket heads, cluster ids
   CK(ws_ensure(ws, WS_NEXT, (size_t)n * 4));
   CK(ws_ensure(ws, WS_BEND, (size_t)n * 4));
   CK(ws_ensure(ws, WS_HEAD, (size_t)n * 4));
   CK(ws_ensure(ws, WS_CID, (size_t)n * 4));
-  uint32_t *next = (uint32_t *)ws.buf[WS_NEXT], *bend = (uint32_t *)ws.buf[WS_BEND], *head = (uint32_t *)ws.buf[WS_HEAD],
-           *cid = (uint32_t *)ws.buf[WS_CID];
-  cluster_next<<<nb2, T, 0, st>>>(ra, n, p.window, next, bend, head);
-  {
-    // chain walk in pieces of kSeg records (see seg_exits): cid doubles as exit_of, the scatter buffer rb as entry flags
-    uint32_t *exit_of = cid;
-    uint32_t *entry_flag = reinterpret_cast<uint32_t *>(rb);
-    const uint32_t n_seg = (n + kSeg - 1) / kSeg;
-    CK(cudaMemsetAsync(entry_flag, 0, (size_t)n * 4, st));
-    seg_exits<<<(n_seg + 63) / 64, 64, 0, st>>>(next, bend, n, exit_of);
-    seg_entry<<<nb2, T, 0, st>>>(ra, n, bend, exit_of, entry_flag);
-    seg_mark<<<(n_seg + 63) / 64, 64, 0, st>>>(next, bend, n, entry_flag, head);
+  CK(ws_ensure(ws, WS_ENTRY, (size_t)n * 4));
+  CK(ws_ensure(ws, WS_CLSTART, (size_t)n * 4));
+  CK(ws_ensure(ws, WS_CLEND, (size_t)n * 4));
+  CK(ws_ensure(ws, WS_SCRATCH, scratch_slots * sizeof(Slot)));
+  CK(ws_ensure(ws, WS_OUT2, (size_t)2 * n * sizeof(strgpu_bounds)));
+  CK(ws_ensure(ws, WS_VALID2, (size_t)2 * n * 4));
+  CK(ws_ensure(ws, WS_DST2, (size_t)2 * n * 4));
+  if (with_loci) CK(ws_ensure(ws, WS_SORTED_B, (size_t)n * sizeof(strgpu_tread)));
+  uint32_t *d_small = (uint32_t *)ws.buf[WS_SMALL];
+  CK(cudaMemsetAsync(d_small, 0, kSmallWords * 4, st));
+  SortRec *ra = (SortRec *)ws.buf[WS_RECS_A], *rb = (SortRec *)ws.buf[WS_RECS_B];
+  make_sort_records<<<nb, T, 0, st>>>(d_treads, n, ra, d_small + SM_VAR);
+  sort_plan<<<1, 32, 0, st>>>(d_small, n, 256u * n_chunks);
+  *launches += 2;
+
+  // ---- K2: LSD radix sort over the virtual key (varying bits of position, unit, tid); passes past its width return at once
+  uint32_t *counts = (uint32_t *)ws.buf[WS_COUNTS];
+  for (int pass = 0; pass < kMaxPasses; pass++) {
+    radix_histogram<<<sort_blocks, kSortWarps * 32, 0, st>>>(ra, rb, n, chunk, n_chunks, d_small, pass, counts);
+    ++*launches;
+    CK(exclusive_scan(ws, counts, counts, d_small + SM_COUNTLEN, 256 * n_chunks, nullptr, d_small + SM_ACTIVE + pass, st, launches));
+    radix_scatter<<<sort_blocks, kSortWarps * 32, 0, st>>>(ra, rb, n, chunk, n_chunks, d_small, pass, counts);
+    ++*launches;
   }
-  *launches += 4;
-  CK(exclusive_scan(ws, head, cid, n, d_small + 3, st, launches));
-  uint32_t n_clusters = 0;
-  CK(cudaMemcpyAsync(&n_clusters, d_small + 3, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (n_clusters == 0) return cudaMemsetAsync(d_n_out, 0, 4, st);
-  CK(ws_ensure(ws, WS_CLSTART, (size_t)n_clusters * 4));
-  CK(ws_ensure(ws, WS_CLEND, (size_t)n_clusters * 4));
-  uint32_t *cl_start = (uint32_t *)ws.buf[WS_CLSTART], *cl_end = (uint32_t *)ws.buf[WS_CLEND];
-  cluster_fill<<<nb2, T, 0, st>>>(head, cid, next, n, cl_start, cl_end);
+  strgpu_tread *sorted = (strgpu_tread *)ws.buf[WS_SORTED];
+  gather_treads<<<nb, T, 0, st>>>(d_treads, ra, rb, d_small, n, sorted);
   ++*launches;
 
-  // ---- K4: bounds per cluster, then ordered compaction
-  CK(ws_ensure(ws, WS_SCRATCH, ((size_t)32 * n_clusters + (size_t)8 * n + 64) * sizeof(Slot)));
-  CK(ws_ensure(ws, WS_OUT2, (size_t)2 * n_clusters * sizeof(strgpu_bounds)));
-  CK(ws_ensure(ws, WS_VALID2, (size_t)2 * n_clusters * 4));
-  CK(ws_ensure(ws, WS_DST2, (size_t)2 * n_clusters * 4));
+  // ---- C10: loci take their reads out of the sorted buckets before clustering
+  int flip = 0;
+  if (with_loci) {
+    uint32_t *removed = (uint32_t *)ws.buf[WS_HEAD], *keep = (uint32_t *)ws.buf[WS_NEXT], *dst = (uint32_t *)ws.buf[WS_CID];
+    CK(cudaMemsetAsync(removed, 0, (size_t)n * 4, st));
+    assign_loci<<<(loci->n_chains + 63) / 64, 64, 0, st>>>(ra, rb, d_small, sorted, n, loci->d_loci, loci->d_chain_start, loci->n_chains,
+                                                            removed, loci->d_counts);
+    invert_flags<<<nb, T, 0, st>>>(removed, n, keep);
+    *launches += 2;
+    CK(exclusive_scan(ws, keep, dst, d_small + SM_NCUR, n, d_small + SM_NCLUSTERS /* temporary: records kept */, nullptr, st, launches));
+    strgpu_tread *sorted_b = (strgpu_tread *)ws.buf[WS_SORTED_B];
+    compact_sorted<<<nb, T, 0, st>>>(ra, rb, d_small, sorted, keep, dst, n, sorted_b);
+    set_ncur<<<1, 32, 0, st>>>(d_small);
+    *launches += 2;
+    sorted = sorted_b;
+    flip = 1;
+  }
+
+  // ---- K3: next(i), bucket heads, cluster ids (n = d_small[SM_NCUR] from here on)
+  uint32_t *next = (uint32_t *)ws.buf[WS_NEXT], *bend = (uint32_t *)ws.buf[WS_BEND], *head = (uint32_t *)ws.buf[WS_HEAD],
+           *cid = (uint32_t *)ws.buf[WS_CID], *entry_flag = (uint32_t *)ws.buf[WS_ENTRY];
+  const uint32_t piece_blocks = ((n + kSeg - 1) / kSeg + kPieceWarps - 1) / kPieceWarps;
+  cluster_next<<<nb, T, 0, st>>>(ra, rb, d_small, flip, p.window, next, bend, head, entry_flag);
+  uint32_t *exit_of = cid;   // cid doubles as exit_of until the scan below
+  piece_exits<<<piece_blocks, kPieceWarps * 32, 0, st>>>(next, bend, d_small, exit_of);
+  bucket_entry<<<nb, T, 0, st>>>(ra, rb, d_small, flip, bend, exit_of, entry_flag);
+  piece_mark<<<piece_blocks, kPieceWarps * 32, 0, st>>>(next, bend, d_small, entry_flag, head);
+  *launches += 4;
+  CK(exclusive_scan(ws, head, cid, d_small + SM_NCUR, n, d_small + SM_NCLUSTERS, nullptr, st, launches));
+  uint32_t *cl_start = (uint32_t *)ws.buf[WS_CLSTART], *cl_end = (uint32_t *)ws.buf[WS_CLEND];
+  cluster_fill<<<nb, T, 0, st>>>(head, cid, next, d_small, cl_start, cl_end);
+  ++*launches;
+
+  // ---- K4: bounds per cluster (launched for n clusters, the worst case), then ordered compaction
   strgpu_bounds *out2 = (strgpu_bounds *)ws.buf[WS_OUT2];
   uint32_t *valid2 = (uint32_t *)ws.buf[WS_VALID2], *dst2 = (uint32_t *)ws.buf[WS_DST2];
-  const uint32_t cb = (n_clusters + 127) / 128;
-  cluster_bounds<<<cb, 128, 0, st>>>(sorted, cl_start, cl_end, n_clusters, p, (Slot *)ws.buf[WS_SCRATCH], out2, valid2);
+  cluster_bounds<<<(n + 127) / 128, 128, 0, st>>>(sorted, cl_start, cl_end, d_small, p, (Slot *)ws.buf[WS_SCRATCH], (uint32_t)std::min<size_t>(scratch_slots, 0xffffffffu), out2, valid2);
   ++*launches;
-  CK(exclusive_scan(ws, valid2, dst2, 2 * n_clusters, d_n_out, st, launches));
-  compact_bounds<<<(2 * n_clusters + T - 1) / T, T, 0, st>>>(out2, valid2, dst2, 2 * n_clusters, d_out, cap);
+  CK(exclusive_scan(ws, valid2, dst2, d_small + SM_N2, 2 * n, d_n_out, nullptr, st, launches));
+  compact_bounds<<<(2 * n + T - 1) / T, T, 0, st>>>(out2, valid2, dst2, d_small, d_out, cap);
   ++*launches;
   return cudaGetLastError();
 }

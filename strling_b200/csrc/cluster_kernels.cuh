@@ -16,8 +16,8 @@ struct SortRec {  // 16-byte radix-sort record: key fields + the tread's index i
 
 // Growable device workspace owned by the ctx; every pointer is device memory.
 struct ClusterWorkspace {
-  void *buf[17] = {nullptr};
-  size_t cap[17] = {0};
+  void *buf[20] = {nullptr};
+  size_t cap[20] = {0};
 };
 
 // Loci for assign_reads_locus, already grouped on the host: loci of one bucket are consecutive ("chain") and keep
@@ -35,9 +35,10 @@ struct LociArgs {
 };
 uint32_t unit_rank_host(const char repeat[6]);
 
-// Runs the whole cluster path for n treads already in device memory.  Synchronises `stream` internally
-// (key-range probe, cluster count).  Returns cudaSuccess or the failing call's error; *launches is
-// incremented per kernel launch.  d_n_out receives the number of records produced (may exceed cap).
+// Enqueues the whole cluster path for n treads already in device memory on `stream`; nothing is read back and nothing
+// synchronises (sizes only the device knows stay in device memory).  Returns cudaSuccess or the failing call's error;
+// *launches is incremented per kernel launch.  d_n_out receives the number of records produced (may exceed cap).
+// n must be below 2^31.
 cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
                         strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t stream, uint64_t *launches,
                         const LociArgs *loci = nullptr);

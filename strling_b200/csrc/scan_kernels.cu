@@ -1505,7 +1505,10 @@ cudaError_t launch_repeat_scan(const uint32_t *d_seq_words, const uint32_t *d_nm
     static const bool no_tma = getenv("STRGPU_NO_TMA") != nullptr;   // A/B: per-lane loads for uniform reads too
     static const int stages = getenv("STRGPU_STAGES") ? atoi(getenv("STRGPU_STAGES")) : 4;   // A/B: staging depth
     const uint32_t groups = (n_seg + 31) / 32;
-    uint32_t pre_grid = (uint32_t)sm_count * 4u;   // 4 resident CTAs of 8 warps per SM, grid-stride over groups of 32
+    // resident pre-filter CTAs per SM (8 warps, 64 registers each: 4 fill the register file).  With 3 the ladder kernels of the
+    // previous call (other stream) find room next to them and run in the issue slots the pre-filter leaves idle.
+    static const int pre_ctas = getenv("STRGPU_PRE_CTAS") ? std::max(1, std::min(4, atoi(getenv("STRGPU_PRE_CTAS")))) : 4;
+    uint32_t pre_grid = (uint32_t)sm_count * (uint32_t)pre_ctas;   // grid-stride over groups of 32
     const uint32_t pre_need = (groups + kPreWarps - 1) / kPreWarps;
     if (pre_grid > pre_need) pre_grid = pre_need;
     auto pre = variant == 7 ? (stages == 2 ? repeat_prefilter<12, 2> : repeat_prefilter<12, 4>)
