@@ -206,7 +206,7 @@ int strgpu_cluster_loci(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n,
 /* Device-resident variant: d_treads / d_out are device pointers, *d_n_out a device uint32.  The whole path (sort, chain,
  * bounds, compaction) is enqueued on `cuda_stream` and the call returns without synchronising or reading anything back;
  * every size only the device knows stays in device memory.  d_out needs room for `cap` records; records past cap are
- * dropped and counted in *d_n_out.  n must be below 2^31. */
+ * dropped and counted in *d_n_out.  n must be below 2^29. */
 int strgpu_cluster_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, const strgpu_cluster_params *params,
                           void *d_out, uint32_t cap, void *d_n_out, void *cuda_stream);
 

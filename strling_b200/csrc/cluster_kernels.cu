@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <mutex>
 
 namespace strgpu {
 
@@ -137,6 +138,18 @@ __device__ __forceinline__ uint32_t unit_rank(char c) {
   }
 }
 
+// The top three bits of SortRec::idx carry the tread's split (Soft, cluster.nim:14-20), so that the chain and bounds kernels work
+// on the sorted 16-byte records alone (position, split) and never gather the 24-byte treads; n stays below 2^29.
+constexpr int kIdxBits = 29;
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+struct Reads {
+  const SortRec *recs;
+  const strgpu_tread *treads;   // input order, for the few fields read once per cluster (tid, repeat) or on demand (sample)
+  __device__ __forceinline__ uint32_t pos(uint32_t i) const { return recs[i].pos; }
+  __device__ __forceinline__ int split(uint32_t i) const { return (int)(recs[i].idx >> kIdxBits); }
+  __device__ __forceinline__ const strgpu_tread &tread(uint32_t i) const { return treads[recs[i].idx & kIdxMask]; }
+};
+
 __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint32_t n, SortRec *__restrict__ recs,
                                   uint32_t *__restrict__ varbits) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,7 +163,7 @@ __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint3
     for (int j = 0; j < 6; j++) m = (m << 3) | unit_rank(t.repeat[j]);
     r.mid = m;
     r.pos = t.position;
-    r.idx = i;
+    r.idx = i | ((uint32_t)(t.split < 8 ? t.split : 7) << kIdxBits);   // K3 / K4 read the split from the sort record
     recs[i] = r;
     const strgpu_tread f = treads[0];
     uint32_t fm = 0;
@@ -239,60 +252,88 @@ __device__ __forceinline__ uint32_t digit_of(const SortRec &r, const DigitPlan &
   return out & 0xffu;
 }
 
+// One CTA owns one tile of kTile consecutive records.  The scatter first sorts the tile by digit in shared memory (warp w
+// ranks its 512 records 32 at a time with match.any, so equal digits keep their order; a per-warp / per-digit prefix makes
+// the ranks tile-wide), then copies the tile out position by position: records of one digit leave for consecutive
+// addresses, so a pass writes whole sectors instead of one 16-byte record per sector.
 constexpr int kSortWarps = 8;
+constexpr uint32_t kTile = 4096;
+constexpr uint32_t kWarpSpan = kTile / kSortWarps;   // 512 records per warp
 
 __global__ void __launch_bounds__(kSortWarps * 32) radix_histogram(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, uint32_t n,
-                                                                   uint32_t chunk, uint32_t n_chunks, const uint32_t *__restrict__ small, int pass,
+                                                                   uint32_t n_tiles, const uint32_t *__restrict__ small, int pass,
                                                                    uint32_t *__restrict__ counts) {
   if (small[SM_ACTIVE + pass] == 0u) return;
   const SortRec *in = small[SM_SRC + pass] ? buf1 : buf0;
   const DigitPlan dp = load_digit_plan(small, pass);
-  __shared__ uint32_t hist[kSortWarps][256];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t w = blockIdx.x * kSortWarps + warp;
-  for (int d = lane; d < 256; d += 32) hist[warp][d] = 0;
-  __syncwarp();
-  if (w < n_chunks) {
-    const uint32_t beg = w * chunk;
-    const uint32_t end = min(n, beg + chunk);
-    for (uint32_t i = beg + lane; i < end; i += 32) atomicAdd(&hist[warp][digit_of(in[i], dp)], 1u);
-    __syncwarp();
-    for (int d = lane; d < 256; d += 32) counts[(size_t)d * n_chunks + w] = hist[warp][d];
-  }
+  __shared__ uint32_t hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t beg = blockIdx.x * kTile, end = min(n, beg + kTile);
+  for (uint32_t i = beg + threadIdx.x; i < end; i += kSortWarps * 32) atomicAdd(&hist[digit_of(in[i], dp)], 1u);
+  __syncthreads();
+  counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(SortRec *__restrict__ buf0, SortRec *__restrict__ buf1, uint32_t n, uint32_t chunk,
-                                                                 uint32_t n_chunks, const uint32_t *__restrict__ small, int pass,
+__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(SortRec *__restrict__ buf0, SortRec *__restrict__ buf1, uint32_t n,
+                                                                 uint32_t n_tiles, const uint32_t *__restrict__ small, int pass,
                                                                  const uint32_t *__restrict__ offsets) {
   if (small[SM_ACTIVE + pass] == 0u) return;
   const bool flip = small[SM_SRC + pass] != 0u;
   const SortRec *in = flip ? buf1 : buf0;
   SortRec *out = flip ? buf0 : buf1;
   const DigitPlan dp = load_digit_plan(small, pass);
-  __shared__ uint32_t off[kSortWarps][256];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t w = blockIdx.x * kSortWarps + warp;
-  if (w >= n_chunks) return;
-  for (int d = lane; d < 256; d += 32) off[warp][d] = offsets[(size_t)d * n_chunks + w];
-  __syncwarp();
-  const uint32_t beg = w * chunk;
-  const uint32_t end = min(n, beg + chunk);
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  SortRec *stage = reinterpret_cast<SortRec *>(sort_smem);                                 // kTile records
+  uint32_t(*whist)[256] = reinterpret_cast<uint32_t(*)[256]>(sort_smem + kTile * sizeof(SortRec));   // [warp][digit]
+  uint32_t *dbase = reinterpret_cast<uint32_t *>(whist + kSortWarps);                      // tile-local first position of a digit
+  uint32_t *gbase = dbase + 256;                                                           // its first position in the output
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t beg = blockIdx.x * kTile, end = min(n, beg + kTile);
+  const uint32_t wbeg = beg + warp * kWarpSpan, wend = min(end, wbeg + kWarpSpan);
+  for (int w = 0; w < kSortWarps; w++) whist[w][tid] = 0;
+  __syncthreads();
+  // pass A: digit counts per warp
+  for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&whist[warp][digit_of(in[i], dp)], 1u);
+  __syncthreads();
+  {
+    // digit tid: exclusive prefix over the warps, tile-wide total, then the exclusive scan of the totals
+    uint32_t run = 0;
+    for (int w = 0; w < kSortWarps; w++) {
+      const uint32_t c = whist[w][tid];
+      whist[w][tid] = run;
+      run += c;
+    }
+    const uint32_t ex = block_exclusive_scan(run, nullptr);
+    dbase[tid] = ex;
+    gbase[tid] = offsets[(size_t)tid * n_tiles + blockIdx.x];
+    for (int w = 0; w < kSortWarps; w++) whist[w][tid] += ex;
+  }
+  __syncthreads();
+  // pass B: stable ranks, records to their tile-local position
   const uint32_t lane_lt = (1u << lane) - 1u;
-  for (uint32_t base = beg; base < end; base += 32) {
+  for (uint32_t base = wbeg; base < wend; base += 32) {
     const uint32_t i = base + lane;
-    const bool valid = i < end;
+    const bool valid = i < wend;
     SortRec r{0, 0, 0, 0};
     if (valid) r = in[i];
     const uint32_t d = valid ? digit_of(r, dp) : (0x100u + (uint32_t)lane);
     const uint32_t grp = __match_any_sync(kFull, d);
-    uint32_t dst = 0;
-    if (valid) dst = off[warp][d] + __popc(grp & lane_lt);  // lane order == input order: stable
+    uint32_t local = 0;
+    if (valid) local = whist[warp][d] + __popc(grp & lane_lt);  // lane order == input order: stable
     __syncwarp();
-    if (valid && lane == 31 - __clz(grp)) off[warp][d] += __popc(grp);
+    if (valid && lane == 31 - __clz(grp)) whist[warp][d] += __popc(grp);
     __syncwarp();
-    if (valid) out[dst] = r;
+    if (valid) stage[local] = r;
+  }
+  __syncthreads();
+  for (uint32_t j = tid; j < end - beg; j += kSortWarps * 32) {
+    const SortRec r = stage[j];
+    const uint32_t d = digit_of(r, dp);
+    out[gbase[d] + (j - dbase[d])] = r;
   }
 }
+constexpr int kScatterSmem = kTile * sizeof(SortRec) + kSortWarps * 256 * 4 + 2 * 256 * 4;
 
 // after assign_reads_locus: the records kept (left in SM_NCLUSTERS by the compaction scan) are what K3 works on
 __global__ void set_ncur(uint32_t *small) {
@@ -305,23 +346,11 @@ __device__ __forceinline__ const SortRec *sorted_recs(const SortRec *buf0, const
   return small[SM_FINAL] ? buf1 : buf0;
 }
 
-__global__ void gather_treads(const strgpu_tread *__restrict__ treads, const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1,
-                              const uint32_t *__restrict__ small, uint32_t n, strgpu_tread *__restrict__ sorted) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const SortRec *recs = sorted_recs(buf0, buf1, small);
-  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(treads + recs[i].idx);
-  unsigned long long *dst = reinterpret_cast<unsigned long long *>(sorted + i);
-  dst[0] = src[0];
-  dst[1] = src[1];
-  dst[2] = src[2];
-}
-
 // ------------------------------------------------------------------------------------------- C10 assign_reads_locus
 // One thread per chain (= the loci of one bucket, in file order): callclusters.nim:14-50 on the sorted records with
 // removal expressed as marks.  Earlier loci change what later loci of the same bucket see, hence the serial chain.
 __global__ void assign_loci(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, const uint32_t *__restrict__ small,
-                            const strgpu_tread *__restrict__ sorted, uint32_t n,
+                            uint32_t n,
                             const DevLocus *__restrict__ loci, const uint32_t *__restrict__ chain_start, uint32_t n_chains,
                             uint32_t *__restrict__ removed, uint16_t *__restrict__ counts) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,7 +387,7 @@ __global__ void assign_loci(const SortRec *__restrict__ buf0, const SortRec *__r
         if (removed[i]) continue;
         removed[i] = 1;
         n_total++;
-        const uint8_t sp = sorted[i].split;
+        const int sp = (int)(recs[i].idx >> kIdxBits);
         if (sp == SOFT_RIGHT) n_right++; else if (sp == SOFT_LEFT) n_left++;
       }
       for (uint32_t i = ri; i < be; i++)  // the element at `ri` of the shrunken bucket is dropped too (callclusters.nim:35-36)
@@ -376,21 +405,15 @@ __global__ void invert_flags(const uint32_t *__restrict__ removed, uint32_t n, u
 }
 
 __global__ void compact_sorted(SortRec *__restrict__ buf0, SortRec *__restrict__ buf1, const uint32_t *__restrict__ small,
-                               const strgpu_tread *__restrict__ sorted, const uint32_t *__restrict__ keep,
-                               const uint32_t *__restrict__ dst, uint32_t n, strgpu_tread *__restrict__ sorted_out) {
+                               const uint32_t *__restrict__ keep, const uint32_t *__restrict__ dst, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !keep[i]) return;
   const bool fin = small[SM_FINAL] != 0u;
   const SortRec *recs = fin ? buf1 : buf0;
   SortRec *recs_out = fin ? buf0 : buf1;   // the kept records land in the other ping-pong buffer
-  const uint32_t d = dst[i];
-  recs_out[d] = recs[i];
-  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(sorted + i);
-  unsigned long long *o = reinterpret_cast<unsigned long long *>(sorted_out + d);
-  o[0] = src[0]; o[1] = src[1]; o[2] = src[2];
+  recs_out[dst[i]] = recs[i];
 }
 
-// ------------------------------------------------------------------------------------------- K3 chain
 __device__ __forceinline__ bool same_bucket(const SortRec &a, const SortRec &b) { return a.hi == b.hi && a.mid == b.mid; }
 
 // recs of K3: the sorted buffer, or the other one when assign_reads_locus compacted into it (flip == 1)
@@ -408,8 +431,14 @@ __global__ void cluster_next(const SortRec *__restrict__ buf0, const SortRec *__
   head[i] = 0;
   entry_flag[i] = 0;
   const SortRec me = recs[i];
-  // end of my (tid, unit) bucket: first index whose bucket key differs (records are sorted)
+  // end of my (tid, unit) bucket: first index whose bucket key differs (records are sorted).  Galloping first: most buckets
+  // are short, so the search costs log(bucket) probes instead of log(n)
   uint32_t lo = i + 1, hi = n;
+  for (uint32_t step = 1; lo < n; step *= 2) {
+    const uint32_t probe = min(n - 1u, i + step);
+    if (same_bucket(recs[probe], me)) { lo = probe + 1; if (probe == n - 1u) break; }
+    else { hi = probe; break; }
+  }
   while (lo < hi) {
     const uint32_t mid = lo + ((hi - lo) >> 1);
     if (same_bucket(recs[mid], me)) lo = mid + 1; else hi = mid;
@@ -427,6 +456,11 @@ __global__ void cluster_next(const SortRec *__restrict__ buf0, const SortRec *__
     const uint32_t thr = recs[i + ((mm - 1u) >> 1)].pos + max_dist + 100u;  // posmed + max_dist + 100, uint32 wrap
     if (m >= 9u) {  // the median of the first 9 no longer moves: first position > thr ends the cluster
       uint32_t a = j, b = be;
+      for (uint32_t step = 1; a < be; step *= 2) {   // galloping: clusters are short
+        const uint32_t probe = min(be - 1u, j + step - 1u);
+        if (recs[probe].pos <= thr) { a = probe + 1; if (probe == be - 1u) break; }
+        else { b = probe; break; }
+      }
       while (a < b) {
         const uint32_t mid = a + ((b - a) >> 1);
         if (recs[mid].pos <= thr) a = mid + 1; else b = mid;
@@ -572,14 +606,14 @@ struct Slot {
 
 enum ClipMode { kSplitLeft, kSplitRight, kBoundsLeft, kBoundsRight };
 
-__device__ __forceinline__ bool clip_selected(const strgpu_tread &r, ClipMode mode, uint32_t cm, uint32_t mcd) {
+__device__ __forceinline__ bool clip_selected(int split, uint32_t position, ClipMode mode, uint32_t cm, uint32_t mcd) {
   // bounds(): cluster.nim:193,197 (int32 casts and adds wrap); the elif makes "right" exclude nothing extra
   // because a read has a single split value.
   switch (mode) {
-    case kSplitLeft: return r.split == SOFT_LEFT;
-    case kSplitRight: return r.split == SOFT_RIGHT;
-    case kBoundsLeft: return r.split == SOFT_LEFT && (int32_t)r.position < (int32_t)(cm + mcd);
-    default: return r.split == SOFT_RIGHT && (int32_t)r.position > (int32_t)(cm - mcd);
+    case kSplitLeft: return split == SOFT_LEFT;
+    case kSplitRight: return split == SOFT_RIGHT;
+    case kBoundsLeft: return split == SOFT_LEFT && (int32_t)position < (int32_t)(cm + mcd);
+    default: return split == SOFT_RIGHT && (int32_t)position > (int32_t)(cm - mcd);
   }
 }
 
@@ -592,21 +626,22 @@ struct Largest {
 
 // CountTable over the selected reads' positions in [a, b) + `largest`.  Positions ascend, so equal keys are
 // consecutive among the selected reads and first-insertion order is ascending key order.
-__device__ Largest count_largest(const strgpu_tread *__restrict__ reads, uint32_t a, uint32_t b, ClipMode mode, uint32_t cm,
+__device__ Largest count_largest(const Reads &reads, uint32_t a, uint32_t b, ClipMode mode, uint32_t cm,
                                  uint32_t mcd, Slot *scratch) {
   Largest res{0, 0, 0, 0};
   uint32_t cur_key = 0, cur_val = 0, n_at_max = 0;
   for (uint32_t i = a; i < b; i++) {
-    const strgpu_tread r = reads[i];
-    if (!clip_selected(r, mode, cm, mcd)) continue;
+    const SortRec rr = reads.recs[i];
+    const uint32_t r_position = rr.pos;
+    if (!clip_selected((int)(rr.idx >> kIdxBits), r_position, mode, cm, mcd)) continue;
     res.n_selected++;
-    if (cur_val && r.position == cur_key) { cur_val++; }
+    if (cur_val && r_position == cur_key) { cur_val++; }
     else {
       if (cur_val) {
         if (cur_val > res.val) { res.val = cur_val; res.key = cur_key; n_at_max = 1; }
         else if (cur_val == res.val) n_at_max++;
       }
-      cur_key = r.position; cur_val = 1; res.n_distinct++;
+      cur_key = r_position; cur_val = 1; res.n_distinct++;
     }
   }
   if (cur_val) {
@@ -639,12 +674,13 @@ __device__ Largest count_largest(const strgpu_tread *__restrict__ reads, uint32_
   };
   cur_val = 0;
   for (uint32_t i = a; i < b; i++) {
-    const strgpu_tread r = reads[i];
-    if (!clip_selected(r, mode, cm, mcd)) continue;
-    if (cur_val && r.position == cur_key) { cur_val++; }
+    const SortRec rr = reads.recs[i];
+    const uint32_t r_position = rr.pos;
+    if (!clip_selected((int)(rr.idx >> kIdxBits), r_position, mode, cm, mcd)) continue;
+    if (cur_val && r_position == cur_key) { cur_val++; }
     else {
       if (cur_val) insert(cur_key, cur_val);
-      cur_key = r.position; cur_val = 1;
+      cur_key = r_position; cur_val = 1;
     }
   }
   if (cur_val) insert(cur_key, cur_val);
@@ -656,14 +692,14 @@ __device__ Largest count_largest(const strgpu_tread *__restrict__ reads, uint32_
   return res;
 }
 
-__device__ __forceinline__ uint32_t posmed(const strgpu_tread *__restrict__ reads, uint32_t a, uint32_t b) {
+__device__ __forceinline__ uint32_t posmed(const Reads &reads, uint32_t a, uint32_t b) {
   const uint32_t n = b - a;  // cluster.nim:59-62 : reads[int(min(9, n)/2 - 0.5)]
   const uint32_t m = n < 9u ? n : 9u;
-  return reads[a + ((m - 1u) >> 1)].position;
+  return reads.pos(a + ((m - 1u) >> 1));
 }
 
 // merge.nim:18-25 : does any sample own >= supporting reads of [a, b)?  (scratch as an open-addressing counter)
-__device__ bool per_sample_support(const strgpu_tread *__restrict__ reads, uint32_t a, uint32_t b, int supporting, Slot *scratch) {
+__device__ bool per_sample_support(const Reads &reads, uint32_t a, uint32_t b, int supporting, Slot *scratch) {
   if (supporting <= 0) return true;
   const uint32_t n = b - a;
   if (n < (uint32_t)supporting) return false;
@@ -671,7 +707,7 @@ __device__ bool per_sample_support(const strgpu_tread *__restrict__ reads, uint3
   while (cap < 2 * n) cap <<= 1;
   for (uint32_t s = 0; s < cap; s++) scratch[s] = Slot{0, 0};
   for (uint32_t i = a; i < b; i++) {
-    const uint32_t key = (uint32_t)reads[i].sample;
+    const uint32_t key = (uint32_t)reads.tread(i).sample;
     uint32_t h = (key * 2654435761u) & (cap - 1);
     while (scratch[h].val != 0 && scratch[h].key != key) h = (h + 1) & (cap - 1);
     scratch[h].key = key;
@@ -681,15 +717,15 @@ __device__ bool per_sample_support(const strgpu_tread *__restrict__ reads, uint3
 }
 
 // cluster.nim:175-250 + callclusters.nim:52-66.  Returns false when the cluster is dropped.
-__device__ bool bounds_of(const strgpu_tread *__restrict__ reads, uint32_t a, uint32_t b, uint32_t cl_left_most,
+__device__ bool bounds_of(const Reads &reads, uint32_t a, uint32_t b, uint32_t cl_left_most,
                           uint32_t cl_right_most, const strgpu_cluster_params &p, Slot *scratch, strgpu_bounds &out) {
   const uint32_t n = b - a;
   if (n >= 65535u) return false;  // callclusters.nim:53-55
-  const strgpu_tread first = reads[a];
+  const strgpu_tread first = reads.tread(a);
   out.tid = first.tid;
 #pragma unroll
   for (int j = 0; j < 6; j++) out.repeat[j] = first.repeat[j];
-  const uint32_t cm = reads[a + (n >> 1)].position;
+  const uint32_t cm = reads.pos(a + (n >> 1));
   out.center_mass = cm;
   const uint32_t mcd = p.max_clip_dist;
   const Largest ll = count_largest(reads, a, b, kBoundsLeft, cm, mcd, scratch);
@@ -707,8 +743,8 @@ __device__ bool bounds_of(const strgpu_tread *__restrict__ reads, uint32_t a, ui
     else left = right - 1;
   }
   // positions ascend, so posns.min()/max() are the first / last read
-  uint32_t lm = cl_left_most > 0 ? cl_left_most : first.position;
-  uint32_t rm = cl_right_most > 0 ? cl_right_most : reads[b - 1].position;
+  uint32_t lm = cl_left_most > 0 ? cl_left_most : reads.pos(a);
+  uint32_t rm = cl_right_most > 0 ? cl_right_most : reads.pos(b - 1);
   if (lm > left) lm = left;
   if (rm < right) rm = right;
   out.left = left; out.right = right; out.left_most = lm; out.right_most = rm;
@@ -720,7 +756,8 @@ __device__ bool bounds_of(const strgpu_tread *__restrict__ reads, uint32_t a, ui
   return true;
 }
 
-__global__ void cluster_bounds(const strgpu_tread *__restrict__ reads, const uint32_t *__restrict__ cl_start,
+__global__ void cluster_bounds(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, int flip,
+                               const strgpu_tread *__restrict__ treads, const uint32_t *__restrict__ cl_start,
                                const uint32_t *__restrict__ cl_end, uint32_t *__restrict__ small, strgpu_cluster_params p,
                                Slot *__restrict__ scratch_all, uint32_t scratch_slots, strgpu_bounds *__restrict__ out2,
                                uint32_t *__restrict__ valid2) {
@@ -732,8 +769,9 @@ __global__ void cluster_bounds(const strgpu_tread *__restrict__ reads, const uin
   Slot *scratch = nullptr;   // claimed below, only by clusters that get past the min_support / anchor tests
   valid2[2 * c] = 0;
   valid2[2 * c + 1] = 0;
-  const strgpu_tread first = reads[a];
-  if (first.tid < 0) {  // unplaced bucket: call.nim:226-228 records len per unit; merge.nim:175-176 skips
+  const Reads reads{k3_recs(buf0, buf1, small, flip), treads};
+  if ((int32_t)(reads.recs[a].hi ^ 0x80000000u) < 0) {  // unplaced bucket: call.nim:226-228 records len per unit; merge.nim:175-176 skips
+    const strgpu_tread first = reads.tread(a);
     if (!p.merge_mode) {
       strgpu_bounds u;
       u.tid = -1; u.left = u.left_most = u.right = u.right_most = u.center_mass = 0;
@@ -751,16 +789,16 @@ __global__ void cluster_bounds(const strgpu_tread *__restrict__ reads, const uin
   {
     const long long lo_l = (long long)posmed(reads, a, b) - (long long)(max_dist + 100u);
     const uint32_t lo = lo_l > 0 ? (uint32_t)lo_l : 0u;
-    while (b - a > 1 && reads[a].position < lo) a++;
+    while (b - a > 1 && reads.pos(a) < lo) a++;
   }
   const uint32_t pm = posmed(reads, a, b);
-  const uint32_t last = reads[b - 1].position, firstp = reads[a].position;
+  const uint32_t last = reads.pos(b - 1), firstp = reads.pos(a);
   const uint32_t hi_edge = pm + max_dist, lo_edge = pm - max_dist;  // uint32 wrap (cluster.nim:343-344)
   const uint32_t cl_right_most = last > hi_edge ? last : hi_edge;
   const uint32_t cl_left_most = firstp < lo_edge ? firstp : lo_edge;
   if ((long long)(b - a) < (long long)p.min_support) return;
   bool anchor = false;
-  for (uint32_t i = a; i < b && !anchor; i++) anchor = reads[i].split == SOFT_NONE;
+  for (uint32_t i = a; i < b && !anchor; i++) anchor = reads.split(i) == SOFT_NONE;
   if (!anchor) return;
   {
     // scratch for the CountTable replay (16 + 4 * reads slots, twice) and the per-sample counter (<= 4 * reads + 16): bump-allocated,
@@ -781,7 +819,7 @@ __global__ void cluster_bounds(const strgpu_tread *__restrict__ reads, const uin
         (double)rl.val / (double)rl.n_distinct > 0.5) {
       const uint32_t mid = (uint32_t)(0.5 + ((double)rl.key + (double)ll.key) / 2.0);
       uint32_t m = a;
-      while (m < b && reads[m].position < mid) m++;
+      while (m < b && reads.pos(m) < mid) m++;
       sub_a[0] = a; sub_b[0] = m; sub_lm[0] = 0; sub_rm[0] = mid - 1;
       sub_a[1] = m; sub_b[1] = b; sub_lm[1] = mid; sub_rm[1] = 0;
       n_sub = 2;
@@ -876,13 +914,16 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   // many records assign_reads_locus leaves, how many clusters were chained) stay in device memory (d_small) and the
   // kernels that depend on them are launched for the worst case n.
   if (n == 0) return cudaMemsetAsync(d_n_out, 0, 4, st);
-  if (n >= 0x80000000u) return cudaErrorInvalidValue;
+  if (n > kIdxMask) return cudaErrorInvalidValue;   // 2^29 records: the split shares SortRec::idx with the index
   const int T = 256;
   const uint32_t nb = (n + T - 1) / T;
-  uint32_t chunk = 1024;
-  while ((n + chunk - 1) / chunk > 8192) chunk *= 2;
-  const uint32_t n_chunks = (n + chunk - 1) / chunk;
-  const uint32_t sort_blocks = (n_chunks + kSortWarps - 1) / kSortWarps;
+  const uint32_t n_chunks = (n + kTile - 1) / kTile;   // one CTA per tile
+  static std::once_flag attr_once[64];
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    std::call_once(attr_once[dev], []() { cudaFuncSetAttribute(radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem); });
+  }
   const bool with_loci = loci && loci->n_chains;
   // K4 scratch pool: 32 + 8 * reads slots per cluster that passes the min_support test (at most n / max(1, min_support) of them)
   const size_t scratch_slots = (size_t)8 * n + (size_t)32 * (n / (uint32_t)(p.min_support > 1 ? p.min_support : 1)) + 64;
@@ -892,7 +933,6 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   CK(ws_ensure(ws, WS_SMALL, kSmallWords * 4));
   CK(ws_ensure(ws, WS_COUNTS, (size_t)256 * n_chunks * 4));
   CK(ws_ensure(ws, WS_BLOCKSUMS, ((size_t)(scan_max + kScanTile - 1) / kScanTile + 1) * 4));
-  CK(ws_ensure(ws, WS_SORTED, (size_t)n * sizeof(strgpu_tread)));
   CK(ws_ensure(ws, WS_NEXT, (size_t)n * 4));
   CK(ws_ensure(ws, WS_BEND, (size_t)n * 4));
   CK(ws_ensure(ws, WS_HEAD, (size_t)n * 4));
@@ -904,7 +944,6 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   CK(ws_ensure(ws, WS_OUT2, (size_t)2 * n * sizeof(strgpu_bounds)));
   CK(ws_ensure(ws, WS_VALID2, (size_t)2 * n * 4));
   CK(ws_ensure(ws, WS_DST2, (size_t)2 * n * 4));
-  if (with_loci) CK(ws_ensure(ws, WS_SORTED_B, (size_t)n * sizeof(strgpu_tread)));
   uint32_t *d_small = (uint32_t *)ws.buf[WS_SMALL];
   CK(cudaMemsetAsync(d_small, 0, kSmallWords * 4, st));
   SortRec *ra = (SortRec *)ws.buf[WS_RECS_A], *rb = (SortRec *)ws.buf[WS_RECS_B];
@@ -915,31 +954,26 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   // ---- K2: LSD radix sort over the virtual key (varying bits of position, unit, tid); passes past its width return at once
   uint32_t *counts = (uint32_t *)ws.buf[WS_COUNTS];
   for (int pass = 0; pass < kMaxPasses; pass++) {
-    radix_histogram<<<sort_blocks, kSortWarps * 32, 0, st>>>(ra, rb, n, chunk, n_chunks, d_small, pass, counts);
+    radix_histogram<<<n_chunks, kSortWarps * 32, 0, st>>>(ra, rb, n, n_chunks, d_small, pass, counts);
     ++*launches;
     CK(exclusive_scan(ws, counts, counts, d_small + SM_COUNTLEN, 256 * n_chunks, nullptr, d_small + SM_ACTIVE + pass, st, launches));
-    radix_scatter<<<sort_blocks, kSortWarps * 32, 0, st>>>(ra, rb, n, chunk, n_chunks, d_small, pass, counts);
+    radix_scatter<<<n_chunks, kSortWarps * 32, kScatterSmem, st>>>(ra, rb, n, n_chunks, d_small, pass, counts);
     ++*launches;
   }
-  strgpu_tread *sorted = (strgpu_tread *)ws.buf[WS_SORTED];
-  gather_treads<<<nb, T, 0, st>>>(d_treads, ra, rb, d_small, n, sorted);
-  ++*launches;
 
   // ---- C10: loci take their reads out of the sorted buckets before clustering
   int flip = 0;
   if (with_loci) {
     uint32_t *removed = (uint32_t *)ws.buf[WS_HEAD], *keep = (uint32_t *)ws.buf[WS_NEXT], *dst = (uint32_t *)ws.buf[WS_CID];
     CK(cudaMemsetAsync(removed, 0, (size_t)n * 4, st));
-    assign_loci<<<(loci->n_chains + 63) / 64, 64, 0, st>>>(ra, rb, d_small, sorted, n, loci->d_loci, loci->d_chain_start, loci->n_chains,
+    assign_loci<<<(loci->n_chains + 63) / 64, 64, 0, st>>>(ra, rb, d_small, n, loci->d_loci, loci->d_chain_start, loci->n_chains,
                                                             removed, loci->d_counts);
     invert_flags<<<nb, T, 0, st>>>(removed, n, keep);
     *launches += 2;
     CK(exclusive_scan(ws, keep, dst, d_small + SM_NCUR, n, d_small + SM_NCLUSTERS /* temporary: records kept */, nullptr, st, launches));
-    strgpu_tread *sorted_b = (strgpu_tread *)ws.buf[WS_SORTED_B];
-    compact_sorted<<<nb, T, 0, st>>>(ra, rb, d_small, sorted, keep, dst, n, sorted_b);
+    compact_sorted<<<nb, T, 0, st>>>(ra, rb, d_small, keep, dst, n);
     set_ncur<<<1, 32, 0, st>>>(d_small);
     *launches += 2;
-    sorted = sorted_b;
     flip = 1;
   }
 
@@ -961,7 +995,7 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   // ---- K4: bounds per cluster (launched for n clusters, the worst case), then ordered compaction
   strgpu_bounds *out2 = (strgpu_bounds *)ws.buf[WS_OUT2];
   uint32_t *valid2 = (uint32_t *)ws.buf[WS_VALID2], *dst2 = (uint32_t *)ws.buf[WS_DST2];
-  cluster_bounds<<<(n + 127) / 128, 128, 0, st>>>(sorted, cl_start, cl_end, d_small, p, (Slot *)ws.buf[WS_SCRATCH], (uint32_t)std::min<size_t>(scratch_slots, 0xffffffffu), out2, valid2);
+  cluster_bounds<<<(n + 127) / 128, 128, 0, st>>>(ra, rb, flip, d_treads, cl_start, cl_end, d_small, p, (Slot *)ws.buf[WS_SCRATCH], (uint32_t)std::min<size_t>(scratch_slots, 0xffffffffu), out2, valid2);
   ++*launches;
   CK(exclusive_scan(ws, valid2, dst2, d_small + SM_N2, 2 * n, d_n_out, nullptr, st, launches));
   compact_bounds<<<(2 * n + T - 1) / T, T, 0, st>>>(out2, valid2, dst2, d_small, d_out, cap);

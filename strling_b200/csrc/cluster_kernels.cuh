@@ -38,7 +38,7 @@ uint32_t unit_rank_host(const char repeat[6]);
 // Enqueues the whole cluster path for n treads already in device memory on `stream`; nothing is read back and nothing
 // synchronises (sizes only the device knows stay in device memory).  Returns cudaSuccess or the failing call's error;
 // *launches is incremented per kernel launch.  d_n_out receives the number of records produced (may exceed cap).
-// n must be below 2^31.
+// n must be below 2^29.
 cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
                         strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t stream, uint64_t *launches,
                         const LociArgs *loci = nullptr);
