@@ -486,7 +486,7 @@ int strgpu_cluster_loci(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n,
     hl.resize(n_loci);
     std::vector<strgpu::DevLocus> key(n_loci);
     for (uint32_t i = 0; i < n_loci; i++) {
-      key[i].hi = (uint32_t)loci[i].tid ^ 0x80000000u;
+      key[i].hi = strgpu::tid_key_host(loci[i].tid);
       key[i].mid = strgpu::unit_rank_host(loci[i].repeat);
       key[i].left_most = loci[i].left_most;
       key[i].right_most = loci[i].right_most;

@@ -127,6 +127,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t *in, c
 }
 
 // ------------------------------------------------------------------------------------------- K2 sort
+// Sort keys are kept NARROW because the radix sort only walks the bits that vary: tid + 1 (unplaced reads, tid -1, sort first
+// as 0; a BAM has no other negative tid -- one would sort last) and the unit as a base-6 number of its six characters
+// (0 < A < C < G < T < anything else: memcmp order of the zero-padded array[6, char] for units over ACGT, 16 bits).
+__host__ __device__ __forceinline__ uint32_t tid_key(int32_t tid) { return (uint32_t)tid + 1u; }
+__device__ __forceinline__ bool key_unplaced(uint32_t hi) { return (int32_t)(hi - 1u) < 0; }
 __device__ __forceinline__ uint32_t unit_rank(char c) {
   switch (c) {
     case 0: return 0;
@@ -157,10 +162,10 @@ __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint3
   uint32_t d0 = 0, d1 = 0, d2 = 0;
   if (i < n) {
     const strgpu_tread t = treads[i];
-    r.hi = (uint32_t)t.tid ^ 0x80000000u;
+    r.hi = tid_key(t.tid);
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 6; j++) m = (m << 3) | unit_rank(t.repeat[j]);
+    for (int j = 0; j < 6; j++) m = m * 6u + unit_rank(t.repeat[j]);
     r.mid = m;
     r.pos = t.position;
     r.idx = i | ((uint32_t)(t.split < 8 ? t.split : 7) << kIdxBits);   // K3 / K4 read the split from the sort record
@@ -168,10 +173,10 @@ __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint3
     const strgpu_tread f = treads[0];
     uint32_t fm = 0;
 #pragma unroll
-    for (int j = 0; j < 6; j++) fm = (fm << 3) | unit_rank(f.repeat[j]);
+    for (int j = 0; j < 6; j++) fm = fm * 6u + unit_rank(f.repeat[j]);
     d0 = r.pos ^ f.position;
     d1 = r.mid ^ fm;
-    d2 = r.hi ^ ((uint32_t)f.tid ^ 0x80000000u);
+    d2 = r.hi ^ tid_key(f.tid);
   }
   // OR-reduce over the block, then one atomic per block and field
   __shared__ uint32_t blk[3];
@@ -192,12 +197,12 @@ __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint3
 // ---- device-side sort plan.  Small device words (d_small), all uint32:
 //   [0..2] bits that vary across the batch in pos / unit / tid (make_sort_records)      [3] clusters chained (K3)
 //   [5] records entering K3 (n, or what assign_reads_locus left)    [6] scan ticket     [7] scratch bump pointer (K4)
-//   [8] 2 * clusters (length of the K4 compaction scan)   [9] length of the radix count matrix   [15] which ping-pong buffer holds the sorted records
+//   [8] 2 * clusters (length of the K4 compaction scan)   [9] length of the radix count matrix   [10] clusters listed for cluster_bounds   [15] which ping-pong buffer holds the sorted records
 //   [16 + p] radix pass p does work     [32 + p] its source buffer
 //   [48 + f], [51 + f], [54 + f] lowest varying bit / width / offset in the virtual key of field f (0 pos, 1 unit, 2 tid)
 constexpr int kSmallWords = 64;
 constexpr int kMaxPasses = 12;   // 32 + 18 + 32 varying bits at most, 8 per pass
-enum { SM_VAR = 0, SM_NCLUSTERS = 3, SM_NCUR = 5, SM_TICKET = 6, SM_BUMP = 7, SM_N2 = 8, SM_COUNTLEN = 9, SM_FINAL = 15, SM_ACTIVE = 16, SM_SRC = 32,
+enum { SM_VAR = 0, SM_NCLUSTERS = 3, SM_NCUR = 5, SM_TICKET = 6, SM_BUMP = 7, SM_N2 = 8, SM_COUNTLEN = 9, SM_HEAVY = 10, SM_FINAL = 15, SM_ACTIVE = 16, SM_SRC = 32,
        SM_LO = 48, SM_WIDTH = 51, SM_OFF = 54 };
 
 __global__ void sort_plan(uint32_t *small, uint32_t n, uint32_t count_len) {
@@ -445,7 +450,7 @@ __global__ void cluster_next(const SortRec *__restrict__ buf0, const SortRec *__
   }
   const uint32_t be = lo;
   bucket_end[i] = be;
-  if ((int32_t)(me.hi ^ 0x80000000u) < 0) {  // unplaced: the whole bucket is one Cluster (cluster.nim:369-371)
+  if (key_unplaced(me.hi)) {  // unplaced: the whole bucket is one Cluster (cluster.nim:369-371)
     next[i] = be;
     return;
   }
@@ -756,23 +761,30 @@ __device__ bool bounds_of(const Reads &reads, uint32_t a, uint32_t b, uint32_t c
   return true;
 }
 
-__global__ void cluster_bounds(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, int flip,
+// K4 in two kernels.  cluster_screen (one thread per chained cluster): the cheap part every cluster goes through -- unplaced
+// buckets, trim, min_support, has_anchor -- after which most clusters are done (a lone noise read is a cluster too); the
+// ones that go on are appended to a dense list.  cluster_bounds (one thread per listed cluster): split_cluster,
+// has_per_sample_reads, bounds and the filters.  With the list, the 32 threads of a warp all hold a real cluster instead of
+// one of them walking 30 reads while 31 wait.
+struct Heavy {
+  uint32_t c, a, b;   // cluster id, reads [a, b) after trim
+};
+
+__global__ void cluster_screen(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, int flip,
                                const strgpu_tread *__restrict__ treads, const uint32_t *__restrict__ cl_start,
                                const uint32_t *__restrict__ cl_end, uint32_t *__restrict__ small, strgpu_cluster_params p,
-                               Slot *__restrict__ scratch_all, uint32_t scratch_slots, strgpu_bounds *__restrict__ out2,
-                               uint32_t *__restrict__ valid2) {
+                               strgpu_bounds *__restrict__ out2, uint32_t *__restrict__ valid2, Heavy *__restrict__ heavy) {
   const uint32_t n_clusters = small[SM_NCLUSTERS];
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_clusters) return;
   uint32_t a = cl_start[c];
   const uint32_t b = cl_end[c];
-  Slot *scratch = nullptr;   // claimed below, only by clusters that get past the min_support / anchor tests
   valid2[2 * c] = 0;
   valid2[2 * c + 1] = 0;
   const Reads reads{k3_recs(buf0, buf1, small, flip), treads};
-  if ((int32_t)(reads.recs[a].hi ^ 0x80000000u) < 0) {  // unplaced bucket: call.nim:226-228 records len per unit; merge.nim:175-176 skips
-    const strgpu_tread first = reads.tread(a);
+  if (key_unplaced(reads.recs[a].hi)) {  // unplaced bucket: call.nim:226-228 records len per unit; merge.nim:175-176 skips
     if (!p.merge_mode) {
+      const strgpu_tread first = reads.tread(a);
       strgpu_bounds u;
       u.tid = -1; u.left = u.left_most = u.right = u.right_most = u.center_mass = 0;
       u.n_left = u.n_right = u.n_total = 0;
@@ -784,22 +796,35 @@ __global__ void cluster_bounds(const SortRec *__restrict__ buf0, const SortRec *
     }
     return;
   }
-  const uint32_t max_dist = p.window;
   // trim (cluster.nim:252-257): lo is computed once from the untrimmed cluster
-  {
-    const long long lo_l = (long long)posmed(reads, a, b) - (long long)(max_dist + 100u);
+  if (b - a > 1) {
+    const long long lo_l = (long long)posmed(reads, a, b) - (long long)(p.window + 100u);
     const uint32_t lo = lo_l > 0 ? (uint32_t)lo_l : 0u;
     while (b - a > 1 && reads.pos(a) < lo) a++;
   }
+  if ((long long)(b - a) < (long long)p.min_support) return;
+  bool anchor = false;
+  for (uint32_t i = a; i < b && !anchor; i++) anchor = reads.split(i) == SOFT_NONE;
+  if (!anchor) return;
+  heavy[atomicAdd(small + SM_HEAVY, 1u)] = Heavy{c, a, b};
+}
+
+__global__ void cluster_bounds(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, int flip,
+                               const strgpu_tread *__restrict__ treads, uint32_t *__restrict__ small, strgpu_cluster_params p,
+                               const Heavy *__restrict__ heavy, Slot *__restrict__ scratch_all, uint32_t scratch_slots,
+                               strgpu_bounds *__restrict__ out2, uint32_t *__restrict__ valid2) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= small[SM_HEAVY]) return;
+  const Heavy h = heavy[t];
+  const uint32_t c = h.c, a = h.a, b = h.b;
+  const Reads reads{k3_recs(buf0, buf1, small, flip), treads};
+  const uint32_t max_dist = p.window;
   const uint32_t pm = posmed(reads, a, b);
   const uint32_t last = reads.pos(b - 1), firstp = reads.pos(a);
   const uint32_t hi_edge = pm + max_dist, lo_edge = pm - max_dist;  // uint32 wrap (cluster.nim:343-344)
   const uint32_t cl_right_most = last > hi_edge ? last : hi_edge;
   const uint32_t cl_left_most = firstp < lo_edge ? firstp : lo_edge;
-  if ((long long)(b - a) < (long long)p.min_support) return;
-  bool anchor = false;
-  for (uint32_t i = a; i < b && !anchor; i++) anchor = reads.split(i) == SOFT_NONE;
-  if (!anchor) return;
+  Slot *scratch;
   {
     // scratch for the CountTable replay (16 + 4 * reads slots, twice) and the per-sample counter (<= 4 * reads + 16): bump-allocated,
     // so its size follows the clusters that need it (at most reads / max(1, min_support) of them) instead of the worst case
@@ -847,7 +872,7 @@ __global__ void compact_bounds(const strgpu_bounds *__restrict__ out2, const uin
 
 // ------------------------------------------------------------------------------------------- host driver
 enum { WS_RECS_A, WS_RECS_B, WS_COUNTS, WS_BLOCKSUMS, WS_SORTED, WS_NEXT, WS_BEND, WS_HEAD, WS_CID, WS_CLSTART, WS_CLEND,
-       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL, WS_SORTED_B, WS_ENTRY, WS_COUNT_ };
+       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL, WS_SORTED_B, WS_ENTRY, WS_HEAVY, WS_COUNT_ };
 static_assert(WS_COUNT_ <= (int)(sizeof(ClusterWorkspace::buf) / sizeof(void *)), "workspace slots");
 
 cudaError_t ws_ensure(ClusterWorkspace &ws, int which, size_t bytes) {
@@ -882,6 +907,8 @@ cudaError_t exclusive_scan(ClusterWorkspace &ws, const uint32_t *in, uint32_t *o
 
 }  // namespace
 
+uint32_t tid_key_host(int32_t tid) { return tid_key(tid); }
+
 uint32_t unit_rank_host(const char repeat[6]) {
   uint32_t m = 0;
   for (int j = 0; j < 6; j++) {
@@ -894,7 +921,7 @@ uint32_t unit_rank_host(const char repeat[6]) {
       case 'T': r = 4; break;
       default: r = 5;
     }
-    m = (m << 3) | r;
+    m = m * 6u + r;
   }
   return m;
 }
@@ -995,8 +1022,14 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   // ---- K4: bounds per cluster (launched for n clusters, the worst case), then ordered compaction
   strgpu_bounds *out2 = (strgpu_bounds *)ws.buf[WS_OUT2];
   uint32_t *valid2 = (uint32_t *)ws.buf[WS_VALID2], *dst2 = (uint32_t *)ws.buf[WS_DST2];
-  cluster_bounds<<<(n + 127) / 128, 128, 0, st>>>(ra, rb, flip, d_treads, cl_start, cl_end, d_small, p, (Slot *)ws.buf[WS_SCRATCH], (uint32_t)std::min<size_t>(scratch_slots, 0xffffffffu), out2, valid2);
-  ++*launches;
+  // clusters that reach cluster_bounds hold >= min_support reads each
+  const uint32_t heavy_max = p.min_support > 1 ? n / (uint32_t)p.min_support + 1u : n;
+  CK(ws_ensure(ws, WS_HEAVY, (size_t)heavy_max * sizeof(Heavy)));
+  Heavy *heavy = (Heavy *)ws.buf[WS_HEAVY];
+  cluster_screen<<<(n + 127) / 128, 128, 0, st>>>(ra, rb, flip, d_treads, cl_start, cl_end, d_small, p, out2, valid2, heavy);
+  cluster_bounds<<<(heavy_max + 63) / 64, 64, 0, st>>>(ra, rb, flip, d_treads, d_small, p, heavy, (Slot *)ws.buf[WS_SCRATCH],
+                                                       (uint32_t)std::min<size_t>(scratch_slots, 0xffffffffu), out2, valid2);
+  *launches += 2;
   CK(exclusive_scan(ws, valid2, dst2, d_small + SM_N2, 2 * n, d_n_out, nullptr, st, launches));
   compact_bounds<<<(2 * n + T - 1) / T, T, 0, st>>>(out2, valid2, dst2, d_small, d_out, cap);
   ++*launches;

@@ -8,8 +8,8 @@
 namespace strgpu {
 
 struct SortRec {  // 16-byte radix-sort record: key fields + the tread's index in input order
-  uint32_t hi;    // tid with the sign bit flipped (signed order)
-  uint32_t mid;   // repeat unit, 3 bits per char, memcmp order (0 < A < C < G < T)
+  uint32_t hi;    // tid + 1 (unplaced reads first)
+  uint32_t mid;   // repeat unit as a base-6 number of its chars, memcmp order (0 < A < C < G < T)
   uint32_t pos;
   uint32_t idx;
 };
@@ -34,6 +34,7 @@ struct LociArgs {
   uint16_t *d_counts = nullptr;  // [orig][3] = n_left, n_right, n_total
 };
 uint32_t unit_rank_host(const char repeat[6]);
+uint32_t tid_key_host(int32_t tid);
 
 // Enqueues the whole cluster path for n treads already in device memory on `stream`; nothing is read back and nothing
 // synchronises (sizes only the device knows stay in device memory).  Returns cudaSuccess or the failing call's error;
