@@ -182,7 +182,7 @@ typedef struct {
 
 /* treads: n records in `.bin` / concatenation order (host memory).  Writes up to `cap` records to `out`
  * in ascending (tid, repeat bytes, position) order -- the reference visits buckets in Nim Table hash order,
- * which only permutes output lines.  Unplaced buckets (tid < 0) come first as tid == -1 records when
+ * which only permutes output lines.  Unplaced buckets (tid == -1) come first as tid == -1 records when
  * merge_mode == 0.  STRGPU_ERR_OVERFLOW if more than `cap` records were produced (*n_out = needed). */
 int strgpu_cluster(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,
                    strgpu_bounds *out, uint32_t cap, uint32_t *n_out);
@@ -209,6 +209,41 @@ int strgpu_cluster_loci(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n,
  * dropped and counted in *d_n_out.  n must be below 2^29. */
 int strgpu_cluster_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, const strgpu_cluster_params *params,
                           void *d_out, uint32_t cap, void *d_n_out, void *cuda_stream);
+
+
+/* ---- sharded clustering: one process per GPU, NCCL over NVLink / NVSwitch ----------------------------------------
+ * The reference's only parallelism for this stage is one `strling merge --chromosome C` process per chromosome
+ * (merge.nim:52,89; pipelines/strling-joint.groovy:7-12): buckets (tid, repeat) never interact (call.nim:124-125,
+ * merge.nim:125).  Here every bucket has an owner rank: each rank hands over its shard's treads, the records travel to
+ * their owners, every rank runs the cluster kernels on the buckets it owns, the 48-byte cluster records are all-gathered.
+ * The result on EVERY rank equals strgpu_cluster over the concatenation (rank 0's treads, then rank 1's, ...) of all shards,
+ * in the same order; `first_read` indexes the owner rank's sorted records.
+ * NCCL (libnccl.so.2) is loaded with dlopen by strgpu_comm_unique_id / strgpu_comm_init; nothing else in the library needs it. */
+#define STRGPU_COMM_ID_BYTES 128
+/* rank 0 creates the id and hands it to the other ranks by whatever means the host program has (a file, MPI, a socket) */
+int  strgpu_comm_unique_id(void *id_out /* STRGPU_COMM_ID_BYTES */);
+/* collective: every rank of the job calls it with the same id.  One communicator per ctx; ctx's device is the rank's GPU. */
+int  strgpu_comm_init(strgpu_ctx *ctx, int rank, int world, const void *id);
+int  strgpu_comm_info(const strgpu_ctx *ctx, int *rank, int *world);
+void strgpu_comm_destroy(strgpu_ctx *ctx);   /* also done by strgpu_destroy */
+
+/* Collective, device-resident, enqueued on `cuda_stream` without any host synchronisation (partition by owner, record
+ * exchange, per-rank clustering with a device-side record count, all-gather, final order).
+ *   n             treads of this rank's shard (d_treads, `.bin` / concatenation order)
+ *   max_n         an upper bound of n that is THE SAME on every rank (it sizes the exchange slots)
+ *   pair_capacity treads one rank may send to one owner; 0 = max_n / world * 1.25 + 1024 (a hash partition is that even);
+ *                 max_n always fits.  Must be the same on every rank.
+ *   d_out, cap    room for the cluster records of ALL ranks; one rank may contribute at most cap / world of them
+ *   d_n_out       device uint32: records produced by all ranks together
+ * A slot that was too small is reported by strgpu_comm_status (STRGPU_ERR_OVERFLOW): the output is then incomplete. */
+int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, uint32_t max_n, uint32_t pair_capacity,
+                                  const strgpu_cluster_params *params, void *d_out, uint32_t cap, void *d_n_out, void *cuda_stream);
+/* synchronises `cuda_stream` and reports the sticky overflow flags of the last sharded call */
+int strgpu_comm_status(strgpu_ctx *ctx, void *cuda_stream);
+/* Host-buffer variant (collective): copies the shard in, uses the always-sufficient pair capacity max_n, copies all ranks'
+ * cluster records out. */
+int strgpu_cluster_sharded(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, uint32_t max_n, const strgpu_cluster_params *params,
+                           strgpu_bounds *out, uint32_t cap, uint32_t *n_out);
 
 #ifdef __cplusplus
 }

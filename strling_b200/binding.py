@@ -32,6 +32,7 @@ assert SEGMENT_DTYPE.itemsize == 8 and REPEAT_DTYPE.itemsize == 8
 assert TREAD_DTYPE.itemsize == 24 and BOUNDS_DTYPE.itemsize == 48 and CLUSTER_PARAMS_DTYPE.itemsize == 16 and LOCUS_DTYPE.itemsize == 24
 SEG_HAS_N = 1
 MAX_SEGMENT_LEN = 510
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -82,6 +83,14 @@ def load_library():
     L.strgpu_cluster.argtypes = [vp, vp, u32, vp, vp, u32, C.POINTER(u32)]
     L.strgpu_cluster_loci.argtypes = [vp, vp, u32, vp, vp, u32, vp, u32, C.POINTER(u32)]
     L.strgpu_cluster_device.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp]
+    L.strgpu_comm_unique_id.argtypes = [vp]
+    L.strgpu_comm_init.argtypes = [vp, i32, i32, vp]
+    L.strgpu_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.strgpu_comm_destroy.argtypes = [vp]
+    L.strgpu_comm_destroy.restype = None
+    L.strgpu_cluster_sharded_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, vp, vp]
+    L.strgpu_comm_status.argtypes = [vp, vp]
+    L.strgpu_cluster_sharded.argtypes = [vp, vp, u32, u32, vp, vp, u32, C.POINTER(u32)]
     _lib = L
     return L
 
@@ -268,6 +277,53 @@ class StrGpu:
         out = out[: n_out.value]
         unplaced = {bytes(r["repeat"]).rstrip(b"\0"): int(r["n_reads"]) for r in out[out["tid"] < 0]}
         return loci, out[out["tid"] >= 0].copy(), unplaced
+
+    # ---- sharded clustering (one process per GPU, NCCL inside the library) ------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load_library().strgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise StrGpuError(rc, "strgpu_comm_unique_id (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, uid: bytes):
+        assert len(uid) == COMM_ID_BYTES
+        self._check(self.L.strgpu_comm_init(self.h, rank, world, uid))
+
+    def comm_init_torch(self):
+        """Communicator over the ranks of an initialised torch.distributed job (the id travels through its store / broadcast)."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        torch.cuda.synchronize()
+        self.comm_init(rank, world, box[0])
+
+    def cluster_sharded_device(self, d_treads: int, n: int, max_n: int, params: np.ndarray, d_out: int, cap: int, d_n_out: int,
+                               stream: int = 0, pair_capacity: int = 0):
+        self._check(self.L.strgpu_cluster_sharded_device(self.h, d_treads, n, max_n, pair_capacity, params.ctypes.data, d_out, cap,
+                                                         d_n_out, stream or None))
+
+    def comm_status(self, stream: int = 0):
+        self._check(self.L.strgpu_comm_status(self.h, stream or None))
+
+    def cluster_sharded(self, treads: np.ndarray, max_n: int, window: int, min_support: int, min_clip: int = 0, min_clip_total: int = 0,
+                        max_clip_dist: int = 200, merge_mode: bool = False, cap: int | None = None):
+        """Collective: this rank's shard in, the cluster records of the whole job out (same result and order on every rank as
+        `cluster` over the concatenated shards).  Returns (bounds with tid >= 0, {unit: count} of unplaced buckets)."""
+        treads = np.ascontiguousarray(treads, dtype=TREAD_DTYPE)
+        p = self.cluster_params(window, min_support, min_clip, min_clip_total, max_clip_dist, merge_mode)
+        cap = cap or max(1024, 2 * max_n)
+        out = np.zeros(cap, dtype=BOUNDS_DTYPE)
+        n_out = C.c_uint32(0)
+        self._check(self.L.strgpu_cluster_sharded(self.h, treads.ctypes.data, len(treads), max_n, p.ctypes.data, out.ctypes.data, cap,
+                                                  C.byref(n_out)))
+        out = out[: n_out.value]
+        unplaced = {bytes(r["repeat"]).rstrip(b"\0"): int(r["n_reads"]) for r in out[out["tid"] < 0]}
+        return out[out["tid"] >= 0].copy(), unplaced
 
     def cluster_device(self, d_treads: int, n: int, params: np.ndarray, d_out: int, cap: int, d_n_out: int, stream: int = 0):
         self._check(self.L.strgpu_cluster_device(self.h, d_treads, n, params.ctypes.data, d_out, cap, d_n_out, stream or None))

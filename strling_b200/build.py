@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstrgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_SOURCES = ["api.cu", "scan_kernels.cu", "cluster_kernels.cu"]
+CUDA_SOURCES = ["api.cu", "scan_kernels.cu", "cluster_kernels.cu", "comm.cu"]
 CXX_SOURCES = ["pack.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -53,7 +53,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

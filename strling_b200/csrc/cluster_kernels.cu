@@ -155,8 +155,27 @@ struct Reads {
   __device__ __forceinline__ const strgpu_tread &tread(uint32_t i) const { return treads[recs[i].idx & kIdxMask]; }
 };
 
-__global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint32_t n, SortRec *__restrict__ recs,
+// ---- device-side sort plan.  Small device words (d_small), all uint32:
+//   [0..2] bits that vary across the batch in pos / unit / tid (make_sort_records)      [3] clusters chained (K3)
+//   [5] records entering K3 (n, or what assign_reads_locus left)    [6] scan ticket     [7] scratch bump pointer (K4)
+//   [8] 2 * clusters (length of the K4 compaction scan)   [9] length of the radix count matrix   [10] clusters listed for cluster_bounds   [15] which ping-pong buffer holds the sorted records
+//   [16 + p] radix pass p does work     [32 + p] its source buffer
+//   [48 + f], [51 + f], [54 + f] lowest varying bit / width / offset in the virtual key of field f (0 pos, 1 unit, 2 tid)
+constexpr int kSmallWords = 64;
+constexpr int kMaxPasses = 10;   // 32 + 16 + 32 varying bits at most, 8 per pass
+enum { SM_VAR = 0, SM_NCLUSTERS = 3, SM_NCUR = 5, SM_TICKET = 6, SM_BUMP = 7, SM_N2 = 8, SM_COUNTLEN = 9, SM_HEAVY = 10, SM_FINAL = 15, SM_ACTIVE = 16, SM_SRC = 32,
+       SM_LO = 48, SM_WIDTH = 51, SM_OFF = 54 };
+
+// the record count of this run: the host's n, or -- sharded clustering, where only the device knows how many records a rank
+// received -- the device value (never more than the host's n, which sizes the grids and the workspace)
+__global__ void init_small(uint32_t *small, uint32_t n_host, const uint32_t *d_n_in) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  small[SM_NCUR] = d_n_in ? min(*d_n_in, n_host) : n_host;
+}
+
+__global__ void make_sort_records(const strgpu_tread *__restrict__ treads, const uint32_t *__restrict__ small, SortRec *__restrict__ recs,
                                   uint32_t *__restrict__ varbits) {
+  const uint32_t n = small[SM_NCUR];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   SortRec r{0, 0, 0, 0};
   uint32_t d0 = 0, d1 = 0, d2 = 0;
@@ -194,18 +213,7 @@ __global__ void make_sort_records(const strgpu_tread *__restrict__ treads, uint3
   if (threadIdx.x < 3 && blk[threadIdx.x]) atomicOr(&varbits[threadIdx.x], blk[threadIdx.x]);
 }
 
-// ---- device-side sort plan.  Small device words (d_small), all uint32:
-//   [0..2] bits that vary across the batch in pos / unit / tid (make_sort_records)      [3] clusters chained (K3)
-//   [5] records entering K3 (n, or what assign_reads_locus left)    [6] scan ticket     [7] scratch bump pointer (K4)
-//   [8] 2 * clusters (length of the K4 compaction scan)   [9] length of the radix count matrix   [10] clusters listed for cluster_bounds   [15] which ping-pong buffer holds the sorted records
-//   [16 + p] radix pass p does work     [32 + p] its source buffer
-//   [48 + f], [51 + f], [54 + f] lowest varying bit / width / offset in the virtual key of field f (0 pos, 1 unit, 2 tid)
-constexpr int kSmallWords = 64;
-constexpr int kMaxPasses = 12;   // 32 + 18 + 32 varying bits at most, 8 per pass
-enum { SM_VAR = 0, SM_NCLUSTERS = 3, SM_NCUR = 5, SM_TICKET = 6, SM_BUMP = 7, SM_N2 = 8, SM_COUNTLEN = 9, SM_HEAVY = 10, SM_FINAL = 15, SM_ACTIVE = 16, SM_SRC = 32,
-       SM_LO = 48, SM_WIDTH = 51, SM_OFF = 54 };
-
-__global__ void sort_plan(uint32_t *small, uint32_t n, uint32_t count_len) {
+__global__ void sort_plan(uint32_t *small, uint32_t count_len) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   small[SM_COUNTLEN] = count_len;
   uint32_t off = 0;
@@ -226,7 +234,6 @@ __global__ void sort_plan(uint32_t *small, uint32_t n, uint32_t count_len) {
     src ^= active;
   }
   small[SM_FINAL] = src;
-  small[SM_NCUR] = n;
 }
 
 // the pass's 8-bit digit of the virtual key: the varying spans of pos, unit and tid, concatenated (pos least significant)
@@ -265,7 +272,7 @@ constexpr int kSortWarps = 8;
 constexpr uint32_t kTile = 4096;
 constexpr uint32_t kWarpSpan = kTile / kSortWarps;   // 512 records per warp
 
-__global__ void __launch_bounds__(kSortWarps * 32) radix_histogram(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1, uint32_t n,
+__global__ void __launch_bounds__(kSortWarps * 32) radix_histogram(const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1,
                                                                    uint32_t n_tiles, const uint32_t *__restrict__ small, int pass,
                                                                    uint32_t *__restrict__ counts) {
   if (small[SM_ACTIVE + pass] == 0u) return;
@@ -274,13 +281,14 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_histogram(const SortRec
   __shared__ uint32_t hist[256];
   hist[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t beg = blockIdx.x * kTile, end = min(n, beg + kTile);
+  const uint32_t n = small[SM_NCUR];
+  const uint32_t beg = min(n, blockIdx.x * kTile), end = min(n, beg + kTile);
   for (uint32_t i = beg + threadIdx.x; i < end; i += kSortWarps * 32) atomicAdd(&hist[digit_of(in[i], dp)], 1u);
   __syncthreads();
   counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(SortRec *__restrict__ buf0, SortRec *__restrict__ buf1, uint32_t n,
+__global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(SortRec *__restrict__ buf0, SortRec *__restrict__ buf1,
                                                                  uint32_t n_tiles, const uint32_t *__restrict__ small, int pass,
                                                                  const uint32_t *__restrict__ offsets) {
   if (small[SM_ACTIVE + pass] == 0u) return;
@@ -294,8 +302,10 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_scatter(SortRec *__rest
   uint32_t *dbase = reinterpret_cast<uint32_t *>(whist + kSortWarps);                      // tile-local first position of a digit
   uint32_t *gbase = dbase + 256;                                                           // its first position in the output
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t beg = blockIdx.x * kTile, end = min(n, beg + kTile);
-  const uint32_t wbeg = beg + warp * kWarpSpan, wend = min(end, wbeg + kWarpSpan);
+  const uint32_t n = small[SM_NCUR];
+  const uint32_t beg = min(n, blockIdx.x * kTile), end = min(n, beg + kTile);
+  if (beg >= end) return;   // a tile past the device-side record count
+  const uint32_t wbeg = min(end, beg + warp * kWarpSpan), wend = min(end, wbeg + kWarpSpan);
   for (int w = 0; w < kSortWarps; w++) whist[w][tid] = 0;
   __syncthreads();
   // pass A: digit counts per warp
@@ -872,7 +882,7 @@ __global__ void compact_bounds(const strgpu_bounds *__restrict__ out2, const uin
 
 // ------------------------------------------------------------------------------------------- host driver
 enum { WS_RECS_A, WS_RECS_B, WS_COUNTS, WS_BLOCKSUMS, WS_SORTED, WS_NEXT, WS_BEND, WS_HEAD, WS_CID, WS_CLSTART, WS_CLEND,
-       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL, WS_SORTED_B, WS_ENTRY, WS_HEAVY, WS_COUNT_ };
+       WS_SCRATCH, WS_OUT2, WS_VALID2, WS_DST2, WS_SMALL, WS_SORTED_B, WS_ENTRY, WS_HEAVY, WS_SCANAUX, WS_COUNT_ };
 static_assert(WS_COUNT_ <= (int)(sizeof(ClusterWorkspace::buf) / sizeof(void *)), "workspace slots");
 
 cudaError_t ws_ensure(ClusterWorkspace &ws, int which, size_t bytes) {
@@ -934,9 +944,107 @@ void free_workspace(ClusterWorkspace &ws) {
   }
 }
 
+namespace {
+__global__ void set_words(uint32_t *dst, uint32_t a, uint32_t b) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { dst[0] = a; dst[1] = b; }
+}
+
+__global__ void bounds_sort_records(const strgpu_bounds *__restrict__ in, const uint32_t *small, SortRec *__restrict__ recs, uint32_t *varbits) {
+  const uint32_t n = small[SM_NCUR];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t d1 = 0, d2 = 0;
+  if (i < n) {
+    auto key_of = [&](const strgpu_bounds &b, uint32_t &hi, uint32_t &mid) {
+      hi = tid_key(b.tid);
+      mid = 0;
+#pragma unroll
+      for (int j = 0; j < 6; j++) mid = mid * 6u + unit_rank(b.repeat[j]);
+    };
+    SortRec r;
+    key_of(in[i], r.hi, r.mid);
+    r.pos = 0;
+    r.idx = i;
+    recs[i] = r;
+    uint32_t fh, fm;
+    key_of(in[0], fh, fm);
+    d1 = r.mid ^ fm;
+    d2 = r.hi ^ fh;
+  }
+  d1 = __reduce_or_sync(kFull, d1);
+  d2 = __reduce_or_sync(kFull, d2);
+  if ((threadIdx.x & 31) == 0) {
+    if (d1) atomicOr(&varbits[1], d1);
+    if (d2) atomicOr(&varbits[2], d2);
+  }
+}
+
+__global__ void bounds_gather(const strgpu_bounds *__restrict__ in, const SortRec *__restrict__ buf0, const SortRec *__restrict__ buf1,
+                              const uint32_t *__restrict__ small, strgpu_bounds *__restrict__ out, uint32_t cap, uint32_t *__restrict__ n_out) {
+  const uint32_t n = small[SM_NCUR];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *n_out = n;
+  if (i >= n || i >= cap) return;
+  out[i] = in[sorted_recs(buf0, buf1, small)[i].idx];
+}
+}  // namespace
+
+// exclusive scan of n (host-known) uint32 on `st`, for the callers outside this file (the owner partition of comm.cu)
+cudaError_t scan_u32(ClusterWorkspace &ws, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *d_total, cudaStream_t st,
+                     uint64_t *launches) {
+  if (n == 0) return cudaSuccess;
+  CK(ws_ensure(ws, WS_BLOCKSUMS, ((size_t)(n + kScanTile - 1) / kScanTile + 1) * 4));
+  CK(ws_ensure(ws, WS_SCANAUX, 64));
+  uint32_t *aux = (uint32_t *)ws.buf[WS_SCANAUX];   // [0] n, [1] ticket
+  set_words<<<1, 32, 0, st>>>(aux, n, 0u);
+  const uint32_t blocks = (n + kScanTile - 1) / kScanTile;
+  uint32_t *bs = (uint32_t *)ws.buf[WS_BLOCKSUMS];
+  scan_block_sums<<<blocks, kScanThreads, 0, st>>>(in, aux, n, bs, aux + 1, d_total, nullptr);
+  scan_apply<<<blocks, kScanThreads, 0, st>>>(in, aux, n, bs, out, nullptr);
+  *launches += 3;
+  return cudaGetLastError();
+}
+
+// Stable sort of *d_n (<= n_max) cluster records by (tid, unit): the last step of sharded clustering (a bucket lives on one
+// rank, so inside a bucket the rank-major concatenation is already in position order).  Writes min(*d_n, cap) records, *d_n_out = *d_n.
+cudaError_t sort_bounds_device(ClusterWorkspace &ws, const strgpu_bounds *d_in, uint32_t n_max, const uint32_t *d_n, strgpu_bounds *d_out,
+                               uint32_t cap, uint32_t *d_n_out, cudaStream_t st, uint64_t *launches) {
+  if (n_max == 0) return cudaMemsetAsync(d_n_out, 0, 4, st);
+  const int T = 256;
+  const uint32_t nb = (n_max + T - 1) / T;
+  const uint32_t n_chunks = (n_max + kTile - 1) / kTile;
+  CK(ws_ensure(ws, WS_RECS_A, (size_t)n_max * sizeof(SortRec)));
+  CK(ws_ensure(ws, WS_RECS_B, (size_t)n_max * sizeof(SortRec)));
+  CK(ws_ensure(ws, WS_SMALL, kSmallWords * 4));
+  CK(ws_ensure(ws, WS_COUNTS, (size_t)256 * n_chunks * 4));
+  CK(ws_ensure(ws, WS_BLOCKSUMS, ((size_t)(256 * n_chunks + kScanTile - 1) / kScanTile + 1) * 4));
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    static std::once_flag attr_once[64];
+    std::call_once(attr_once[dev], []() { cudaFuncSetAttribute(radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem); });
+  }
+  uint32_t *d_small = (uint32_t *)ws.buf[WS_SMALL];
+  CK(cudaMemsetAsync(d_small, 0, kSmallWords * 4, st));
+  SortRec *ra = (SortRec *)ws.buf[WS_RECS_A], *rb = (SortRec *)ws.buf[WS_RECS_B];
+  init_small<<<1, 32, 0, st>>>(d_small, n_max, d_n);
+  bounds_sort_records<<<nb, T, 0, st>>>(d_in, d_small, ra, d_small + SM_VAR);
+  sort_plan<<<1, 32, 0, st>>>(d_small, 256u * n_chunks);
+  *launches += 3;
+  uint32_t *counts = (uint32_t *)ws.buf[WS_COUNTS];
+  for (int pass = 0; pass < 6; pass++) {   // 16 + 32 key bits at most
+    radix_histogram<<<n_chunks, kSortWarps * 32, 0, st>>>(ra, rb, n_chunks, d_small, pass, counts);
+    CK(exclusive_scan(ws, counts, counts, d_small + SM_COUNTLEN, 256 * n_chunks, nullptr, d_small + SM_ACTIVE + pass, st, launches));
+    radix_scatter<<<n_chunks, kSortWarps * 32, kScatterSmem, st>>>(ra, rb, n_chunks, d_small, pass, counts);
+    *launches += 2;
+  }
+  bounds_gather<<<nb, T, 0, st>>>(d_in, ra, rb, d_small, d_out, cap, d_n_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
                         strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t st, uint64_t *launches,
-                        const LociArgs *loci) {
+                        const LociArgs *loci, const uint32_t *d_n_in) {
   // Everything below is enqueued on `st` and nothing is read back: sizes the host does not know (how many digits vary, how
   // many records assign_reads_locus leaves, how many clusters were chained) stay in device memory (d_small) and the
   // kernels that depend on them are launched for the worst case n.
@@ -974,17 +1082,18 @@ cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint
   uint32_t *d_small = (uint32_t *)ws.buf[WS_SMALL];
   CK(cudaMemsetAsync(d_small, 0, kSmallWords * 4, st));
   SortRec *ra = (SortRec *)ws.buf[WS_RECS_A], *rb = (SortRec *)ws.buf[WS_RECS_B];
-  make_sort_records<<<nb, T, 0, st>>>(d_treads, n, ra, d_small + SM_VAR);
-  sort_plan<<<1, 32, 0, st>>>(d_small, n, 256u * n_chunks);
-  *launches += 2;
+  init_small<<<1, 32, 0, st>>>(d_small, n, d_n_in);
+  make_sort_records<<<nb, T, 0, st>>>(d_treads, d_small, ra, d_small + SM_VAR);
+  sort_plan<<<1, 32, 0, st>>>(d_small, 256u * n_chunks);
+  *launches += 3;
 
   // ---- K2: LSD radix sort over the virtual key (varying bits of position, unit, tid); passes past its width return at once
   uint32_t *counts = (uint32_t *)ws.buf[WS_COUNTS];
   for (int pass = 0; pass < kMaxPasses; pass++) {
-    radix_histogram<<<n_chunks, kSortWarps * 32, 0, st>>>(ra, rb, n, n_chunks, d_small, pass, counts);
+    radix_histogram<<<n_chunks, kSortWarps * 32, 0, st>>>(ra, rb, n_chunks, d_small, pass, counts);
     ++*launches;
     CK(exclusive_scan(ws, counts, counts, d_small + SM_COUNTLEN, 256 * n_chunks, nullptr, d_small + SM_ACTIVE + pass, st, launches));
-    radix_scatter<<<n_chunks, kSortWarps * 32, kScatterSmem, st>>>(ra, rb, n, n_chunks, d_small, pass, counts);
+    radix_scatter<<<n_chunks, kSortWarps * 32, kScatterSmem, st>>>(ra, rb, n_chunks, d_small, pass, counts);
     ++*launches;
   }
 

@@ -42,7 +42,15 @@ uint32_t tid_key_host(int32_t tid);
 // n must be below 2^29.
 cudaError_t run_cluster(ClusterWorkspace &ws, const strgpu_tread *d_treads, uint32_t n, const strgpu_cluster_params &p,
                         strgpu_bounds *d_out, uint32_t cap, uint32_t *d_n_out, cudaStream_t stream, uint64_t *launches,
-                        const LociArgs *loci = nullptr);
+                        const LociArgs *loci = nullptr, const uint32_t *d_n_in = nullptr);
+// d_n_in (optional, device): the actual record count when only the device knows it; n is then the upper bound that sizes
+// grids and workspace (sharded clustering: the records a rank receives from its peers)
+
+// helpers of the sharded path (comm.cu)
+cudaError_t scan_u32(ClusterWorkspace &ws, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *d_total, cudaStream_t st,
+                     uint64_t *launches);
+cudaError_t sort_bounds_device(ClusterWorkspace &ws, const strgpu_bounds *d_in, uint32_t n_max, const uint32_t *d_n, strgpu_bounds *d_out,
+                               uint32_t cap, uint32_t *d_n_out, cudaStream_t st, uint64_t *launches);
 
 void free_workspace(ClusterWorkspace &ws);
 
