@@ -233,6 +233,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     g = sb.StrGpu(local)
     g.set_proportions(P_CLASSES)
+    if world > 1:
+        g.comm_init_torch()   # the library's own NCCL communicator (strgpu_comm_init): the id travels through torch's store
 
     # ---- workload: one seeded shard per rank, replicated to the per-GPU read count
     shard_reads = min(args.shard_reads, args.reads_per_gpu)
@@ -264,17 +266,22 @@ def run_ours(args):
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
 
-    # ---- cluster leg (configs[2]): the STR reads of this shard (~1 % of the reads) -> candidate loci, then the
-    # all-gather of per-shard cluster records, the only collective on the path
-    from strling_b200 import parallel
-
+    # ---- cluster leg (configs[2]): the STR reads of this shard (~1 % of the reads) -> candidate loci.  N > 1: the library's
+    # sharded path (strgpu_cluster_sharded_device: owner partition, NCCL exchange, per-rank clustering, all-gather of the
+    # cluster records, final order), enqueued without a host synchronisation
     n_treads = max(1000, reads_per_gpu // 100)
     t0 = time.time()
     treads = synth.make_treads(max(10, n_treads // 120), seed=40 + rank, noise_reads=n_treads - (n_treads // 120) * 26, unplaced=n_treads // 200)
     n_treads = len(treads)
     h_treads = torch.from_numpy(treads.view(np.uint8).reshape(-1).copy()).pin_memory()
     d_treads = h_treads.to(dev)
-    cap_bounds = max(1024, n_treads // 2)
+    max_treads = n_treads
+    if world > 1:
+        mt = torch.tensor([n_treads], dtype=torch.int64, device=dev)
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        max_treads = int(mt.item())
+    cap_bounds = max(1024, n_treads // 2) * world
+    pair_capacity = max_treads // world + max_treads // (2 * world) + 4096   # 50 % slack over an even split (few, large buckets here)
     d_bounds = torch.zeros(cap_bounds * 48, dtype=torch.uint8, device=dev)
     d_nb = torch.zeros(1, dtype=torch.int32, device=dev)
     cparams = sb.StrGpu.cluster_params(window=480, min_support=5, max_clip_dist=190)
@@ -284,32 +291,25 @@ def run_ours(args):
     cl_events = []
     cl_stats = {}
 
-    def cluster_owned(owned):
-        g.cluster_device(owned.data_ptr(), owned.shape[0], cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(), stream)
-        n_local = int(d_nb.item())
-        if n_local > cap_bounds:
-            raise SystemExit("bench.py: bounds capacity too small")
-        return d_bounds, n_local
-
     def cluster_device_leg():
-        # N > 1: every (tid, repeat) bucket has an owner rank; the STR-read records go to their owner (all-to-all over
-        # NVLink), every rank clusters the buckets it owns, the 48-byte cluster records are all-gathered
-        e0, ex, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        owned = parallel.exchange_by_owner(t32)
-        ex.record()
-        _, n_local = cluster_owned(owned)
+        if world > 1:
+            g.cluster_sharded_device(d_treads.data_ptr(), n_treads, max_treads, cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(),
+                                     stream, pair_capacity=pair_capacity)
+        else:
+            g.cluster_device(d_treads.data_ptr(), n_treads, cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(), stream)
         e1.record()
-        allb, counts = parallel.allgather_records(d_bounds, n_local)
-        e2.record()
-        cl_events.append((e0, ex, e1, e2))
-        cl_stats["bounds_local"] = n_local
-        cl_stats["bounds_all"] = int(sum(counts))
-        cl_stats["treads_owned"] = int(owned.shape[0])
-        cl_stats["gathered"] = allb
+        cl_events.append((e0, e1))
 
     n_extra = n_seg - shard_reads           # soft-clip segments: the only ones that carry descriptors
     extra_max = int(segs["len"][shard_reads:].max()) if n_extra else 0
+    n_extra_dev, extra_max_dev = n_extra, extra_max
+    n_treads_strong = max(1000, n_treads // world)   # a 1 / world slice of the STR reads for the strong-scaling pass
+
+    def cluster_strong():
+        g.cluster_sharded_device(d_treads.data_ptr(), n_treads_strong, n_treads_strong, cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(),
+                                 stream, pair_capacity=n_treads_strong // world + n_treads_strong // (2 * world) + 4096)
 
     # --streams 2: library calls alternate between two contexts on two streams, so that call i's scan kernel (ALU + shared-memory
     # bound, low issue rate) runs next to call i + 1's pre-filter (ALU + popcount bound) on the same SMs (STRGPU_SHARE_SM geometry)
@@ -355,10 +355,16 @@ def run_ours(args):
             inflight.append(g.scan_reads_submit(seq_np, shard_reads, READ_LEN, stride_e, 0, None, extra_np, extra_max, out_np[b % 3]))
         for t in inflight:
             g.scan_wait(t)
-        # cluster through the host API: H2D of the tread PODs, kernels, D2H of the bounds records
+        # cluster through the host API: H2D of the tread PODs, kernels (N > 1: + the NCCL exchange / all-gather inside the
+        # library), D2H of the bounds records
         n_out = ctypes.c_uint32(0)
-        g._check(g.L.strgpu_cluster(g.h, h_treads.data_ptr(), n_treads, cparams.ctypes.data, h_bounds.ctypes.data, cap_bounds,
-                                    ctypes.byref(n_out)))
+        if world > 1:
+            g._check(g.L.strgpu_cluster_sharded(g.h, h_treads.data_ptr(), n_treads, max_treads, cparams.ctypes.data, h_bounds.ctypes.data,
+                                                cap_bounds, ctypes.byref(n_out)))
+        else:
+            g._check(g.L.strgpu_cluster(g.h, h_treads.data_ptr(), n_treads, cparams.ctypes.data, h_bounds.ctypes.data, cap_bounds,
+                                        ctypes.byref(n_out)))
+        cl_stats["bounds_e2e"] = int(n_out.value)
 
     def barrier():
         torch.cuda.synchronize()
@@ -398,9 +404,13 @@ def run_ours(args):
     g.device_status(stream)
     torch.cuda.synchronize()
     timed_ev = cl_events[-args.steps:]
-    exchange_ms = float(np.mean([a.elapsed_time(x) for a, x, b, c in timed_ev]))
-    cluster_ms = float(np.mean([a.elapsed_time(b) for a, x, b, c in timed_ev]))   # exchange + sort + chain + bounds kernels
-    gather_ms = float(np.mean([b.elapsed_time(c) for a, x, b, c in timed_ev]))
+    cluster_ms = float(np.mean([a.elapsed_time(b) for a, b in timed_ev]))   # whole cluster leg incl. the collectives (device time)
+    if world > 1:
+        g.comm_status(stream)          # raises if an exchange / gather slot overflowed
+    n_bounds_all = int(d_nb.item())
+    if n_bounds_all > cap_bounds:
+        raise SystemExit("bench.py: bounds capacity too small")
+    cl_stats["bounds_all"] = n_bounds_all
     # N > 1, outside the timing: the sharded result equals ONE GPU clustering the concatenation of every rank's records
     sharded_ok = None
     if world > 1:
@@ -415,10 +425,11 @@ def run_ours(args):
             cat = torch.cat([everyone[r * n_max: r * n_max + int(n_all[r])] for r in range(world)]).contiguous()
             cap1 = max(1024, cat.shape[0] // 2)
             d_b1 = torch.zeros(cap1 * 48, dtype=torch.uint8, device=dev)
-            g.cluster_device(cat.data_ptr(), cat.shape[0], cparams, d_b1.data_ptr(), cap1, d_nb.data_ptr(), stream)
-            n1 = int(d_nb.item())
-            one = parallel.sort_bounds(parallel.bounds_from_bytes(d_b1[: n1 * 48]))
-            many = parallel.sort_bounds(parallel.bounds_from_bytes(cl_stats["gathered"]))
+            d_n1 = torch.zeros(1, dtype=torch.int32, device=dev)
+            g.cluster_device(cat.data_ptr(), cat.shape[0], cparams, d_b1.data_ptr(), cap1, d_n1.data_ptr(), stream)
+            n1 = int(d_n1.item())
+            one = d_b1[: n1 * 48].cpu().numpy().view(sb.BOUNDS_DTYPE)
+            many = d_bounds[: n_bounds_all * 48].cpu().numpy().view(sb.BOUNDS_DTYPE)
             fields = ("tid", "left", "left_most", "right", "right_most", "center_mass", "n_left", "n_right", "n_total", "repeat", "n_reads")
             sharded_ok = len(one) == len(many) and all(np.array_equal(one[f], many[f]) for f in fields)
             if not sharded_ok:
@@ -431,6 +442,51 @@ def run_ours(args):
     last = d_out[(n_sub - 1) * n_seg * 8:].cpu().numpy().view(sb.REPEAT_DTYPE)
     if not np.array_equal(last, out_np[(n_sub - 1) % 3]):
         raise SystemExit("bench.py: device-resident and host-API results differ")
+
+    # parity at bench scale, outside the timing: a random sample of the TIMED shard's device results against the oracle
+    parity = None
+    if rank == 0 and args.parity_sample > 0:
+        from oracle import oracle as orc   # the checker; never on the measured path
+
+        orc.build()
+        rng = np.random.default_rng(12345)
+        pick = np.sort(rng.choice(n_seg, size=min(args.parity_sample, n_seg), replace=False))
+        flat, off, lens = synth.segment_ascii(reads, segs[pick], stride)
+        units, counts = orc.get_repeat_batch(flat, off, lens, np.asarray(P_CLASSES)[segs["pclass"][pick]])
+        bad = int(((last["unit"][pick] != units) | (last["repeat_count"][pick] != counts)).sum())
+        parity = {"n": int(len(pick)), "mismatches": bad, "found": int((counts > 0).sum()),
+                  "what": "random segments of the last timed sub-batch (device results) vs the oracle's get_repeat"}
+        if bad:
+            raise SystemExit(f"bench.py: {bad} of {len(pick)} sampled segments differ from the oracle")
+
+    # strong scaling (configs[2] as written: the SAME 6e8-read job split over the GPUs): reads_per_gpu / world reads per rank
+    strong = None
+    if world > 1 and not args.no_strong:
+        n_sub_strong = max(1, n_sub // world)
+
+        def step_strong():
+            main = torch.cuda.current_stream()
+            for gx, st in lanes[1:]:
+                st.wait_stream(main)
+            for b in range(n_sub_strong):
+                gx, st = lanes[b % len(lanes)]
+                gx.scan_reads_device(d_seq.data_ptr() + b * seq_bytes, shard_reads, READ_LEN, stride, 0, None,
+                                     d_segs.data_ptr() + (b * n_seg + shard_reads) * 8, n_extra_dev, extra_max_dev,
+                                     d_out.data_ptr() + b * n_seg * 8, st.cuda_stream)
+            for gx, st in lanes[1:]:
+                main.wait_stream(st)
+            cluster_strong()
+
+        sec_strong, _, _ = timed(step_strong, True)
+        g.comm_status(stream)
+        strong = {"reads_total": n_sub_strong * shard_reads * world, "reads_per_gpu": n_sub_strong * shard_reads,
+                  "treads_per_gpu": n_treads_strong, "ms_per_step": 1e3 * sec_strong / args.steps,
+                  "value": n_sub_strong * shard_reads * world * args.steps / sec_strong, "unit": "reads/s",
+                  "note": "configs[2] as written: the one-GPU job (reads_per_gpu reads) split over the ranks; compare with the N = 1 line's value"}
+
+    joint = None
+    if world > 1 and not args.no_joint:
+        joint = joint_leg(g, rank, world, local, dev)
 
     total_reads = reads_per_gpu * world
     value = total_reads * args.steps / sec_dev
@@ -448,7 +504,7 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # dominant kernels = the scan (pre-filter + ladder kernel per library call): average time per call = (step time - cluster leg) / calls
-    launch_s = (sec_dev - args.steps * (cluster_ms + gather_ms) / 1e3) / max(1, scan_launches)
+    launch_s = (sec_dev - args.steps * cluster_ms / 1e3) / max(1, scan_launches)
     achieved = ALGO_BYTES_PER_READ * shard_reads / launch_s / 1e9
     traffic = None
     try:
@@ -476,31 +532,80 @@ def run_ours(args):
                    "reads_per_gpu": reads_per_gpu, "segments_per_gpu": n_seg * n_sub, "read_len": READ_LEN,
                    "sub_batches_per_step": n_sub, "reads_per_launch": shard_reads,
                    "l2": f"each launch streams {(seq_bytes + 16 * n_seg) / 1e6:.0f} MB of its own HBM region (> 126 MB L2); {n_sub} distinct regions per step",
-                   "streams": f"{len(lanes)} library contexts on {len(lanes)} CUDA streams, calls alternate (call i's ladder kernel overlaps call i+1's pre-filter)",
+                   "streams": f"{len(lanes)} library contexts on {len(lanes)} CUDA streams, calls alternate (call i's ladder kernels overlap call i+1's pre-filter)",
                    "parallelism": f"read batches sharded over {world} GPU(s), no data-path collective",
                    "numa": f"rank pinned to the {numa_cpus} CPUs local to its GPU" if numa_cpus else "unbound"},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(n_sub * (seq_bytes_e + len(extra_np) * 8) + n_treads * 24),
-                "api": "strgpu_scan_reads_submit/wait (3 slots in flight) + strgpu_cluster, pinned host buffers",
-                "d2h_bytes_per_step": int(n_sub * n_seg * 8 + cl_stats.get("bounds_local", 0) * 48), "ms_per_step": 1e3 * sec_e2e / args.steps,
+                "api": "strgpu_scan_reads_submit/wait (3 slots in flight) + " + ("strgpu_cluster_sharded" if world > 1 else "strgpu_cluster") + ", pinned host buffers",
+                "d2h_bytes_per_step": int(n_sub * n_seg * 8 + cl_stats.get("bounds_e2e", 0) * 48), "ms_per_step": 1e3 * sec_e2e / args.steps,
                 "h2d_gb_per_s_per_gpu": (n_sub * (seq_bytes_e + len(extra_np) * 8) + n_treads * 24) / (sec_e2e / args.steps) / 1e9,
                 "bound": "PCIe host-to-device copy of the 2-bit reads (38 B per 150-bp read); kernels and the device-to-host copy of the results overlap it"},
-        "cluster": {"treads_per_gpu": n_treads, "ms_per_step": cluster_ms, "treads_per_s": n_treads / (cluster_ms / 1e3),
-                    "bounds_per_gpu": cl_stats.get("bounds_local"), "bounds_gathered": cl_stats.get("bounds_all"),
-                    "allgather_ms": gather_ms, "exchange_ms": exchange_ms, "treads_owned": cl_stats.get("treads_owned"),
-                    "collective": "all_to_all of 24-byte STR-read records by bucket owner + all_gather of 48-byte bounds records (NCCL)" if world > 1 else "none (1 GPU)",
+        "cluster": {"treads_per_gpu": n_treads, "ms_per_step": cluster_ms, "treads_per_s": n_treads * world / (cluster_ms / 1e3),
+                    "bounds": cl_stats.get("bounds_all"),
+                    "api": "strgpu_cluster_sharded_device (owner partition, NCCL exchange of 24-byte STR-read records, per-rank K2-K4, NCCL all-gather of 48-byte cluster records, final order; no host synchronisation)" if world > 1 else "strgpu_cluster_device (enqueued without host synchronisation)",
                     "sharded_equals_single_gpu": sharded_ok},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "repeat_prefilter + repeat_scan_lane (one library call)",
-                     "note": "achieved = 62 B x reads per call / measured time of the call's two kernels; integer-pipe bound, not HBM bound: see DESIGN.md"},
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "repeat_prefilter + ladder_stage<2> + ladder_stage<4> (one library call)",
+                     "note": "achieved = 62 B x reads per call / measured time of the call's kernels (CUDA events over the timed region, cluster leg subtracted); integer-pipe bound, not HBM bound: see DESIGN.md"},
         "clocks": clocks,
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if parity:
+        line["parity_sample"] = parity
+    if strong:
+        line["strong"] = strong
+    if joint:
+        line["joint"] = joint
     emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def joint_leg(g, rank, world, local, dev, n_samples: int = 10, n_pairs: int = 12000):
+    """configs[4] in miniature, outside the timing: 10 synthetic samples -> `strling extract` each (this rank's GPU, CLI) ->
+    joint merge over all ranks through the library's sharded clustering == `strling merge` on one GPU, line for line."""
+    import subprocess as sp
+    import tempfile
+
+    import torch.distributed as dist
+
+    from strling_b200 import bamio, joint
+    from strling_b200 import build as sb_build
+
+    box = [tempfile.mkdtemp(prefix="bench_joint_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    d = box[0]
+    cli = sb_build.build_cli()
+    targets = [(f"chr{i + 1}", 1_500_000) for i in range(6)]
+    loci = [(i % 6, 100_000 + 61_000 * i, 100_000 + 61_000 * i + 30 + 7 * (i % 9), u)
+            for i, u in enumerate(["CAG", "AAAG", "AC", "CCG", "ATTCT", "A", "AAGGG", "CTG", "AAAAT", "GGC", "AT", "CAGG"] * 2)]
+    hdr = bamio.sam_header(targets)
+    bins = [os.path.join(d, f"s{s}.bin") for s in range(n_samples)]
+    t0 = time.time()
+    for s in range(rank, n_samples, world):     # every rank prepares its share of the samples
+        recs = bamio.simulate_alignments(900 + s, n_pairs, targets, loci, str_pair_frac=0.3, unmapped_pairs=50)
+        bam = os.path.join(d, f"s{s}.bam")
+        bamio.write_bam(bam, hdr, targets, recs)
+        sp.run([cli, "extract", "--device", str(local), bam, bins[s]], check=True, capture_output=True)
+    dist.barrier()
+    t1 = time.time()
+    lines, counts = joint.joint_merge(bins, None, dev, min_support=5, lib=g)
+    t2 = time.time()
+    out = None
+    if rank == 0:
+        sp.run([cli, "merge", "-m", "5", "-o", os.path.join(d, "one"), *bins], check=True, capture_output=True)
+        one = open(os.path.join(d, "one-bounds.txt")).read().splitlines()[1:]
+        same = one == lines
+        out = {"samples": n_samples, "pairs_per_sample": n_pairs, "gpus": world, "bounds_lines": len(lines), "equals_single_gpu_merge": same,
+               "prepare_s": round(t1 - t0, 2), "joint_merge_s": round(t2 - t1, 3),
+               "api": "python -m strling_b200.joint semantics in-process: per-rank .bin blocks -> strgpu_cluster_sharded (merge mode) -> bounds lines"}
+        if not same:
+            raise SystemExit("bench.py: joint merge over the GPUs differs from `strling merge` on one GPU")
+    dist.barrier()
+    return out
 
 
 _REAL_STDOUT = None
@@ -532,7 +637,10 @@ def main():
     ap.add_argument("--reads-per-gpu", type=int, default=600_000_000)
     ap.add_argument("--shard-reads", type=int, default=12_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--no-joint", action="store_true", help="skip the config-5 joint-merge leg of multi-GPU runs")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling pass (configs[2] as written) of multi-GPU runs")
+    ap.add_argument("--parity-sample", type=int, default=200_000, help="segments of the timed shard checked against the oracle outside the timing")
     ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     quiet_stdout()

@@ -4,12 +4,13 @@
 
 One process per GPU.  The input files are split into contiguous blocks, one per rank (so that rank-major order is file order,
 the concatenation order of merge.nim:95-125); every rank parses its files, the fragment-length histograms are summed with an
-all-reduce (merge.nim:112-115: window = the 0.98 quantile of the sum), the STR-read records travel to the owner of their
-(tid, repeat) bucket, every rank clusters what it owns in merge mode (has_per_sample_reads, merge.nim:18-25) on its GPU, the
-48-byte cluster records are all-gathered and rank 0 writes `<prefix>-bounds.txt` -- the same lines, in the same order, as
+all-reduce (merge.nim:112-115: window = the 0.98 quantile of the sum); then libstrgpu.so's sharded clustering
+(strgpu_cluster_sharded: the STR-read records travel to the owner of their (tid, repeat) bucket over NCCL, every rank clusters
+what it owns in merge mode (has_per_sample_reads, merge.nim:18-25) on its GPU, the 48-byte cluster records are all-gathered)
+and rank 0 writes `<prefix>-bounds.txt` -- the same lines, in the same order, as
 `strling merge` on one GPU.  `-l` loci and `--chromosome` are the single-GPU command's business (strling_b200/bin/strling merge).
 The record parsing below reads the `.bin` layout of extract.nim:331-348 / cluster.nim:38-50; it contains no clustering logic:
-that is the CUDA library's (strgpu_cluster_device)."""
+that is the CUDA library's (strgpu_cluster_sharded)."""
 from __future__ import annotations
 
 import argparse
@@ -89,8 +90,11 @@ def files_of_rank(n_files: int, rank: int, world: int):
     return list(range(rank * per, min(n_files, (rank + 1) * per)))
 
 
-def joint_merge(paths, cluster_fn, device, window=-1, min_support=5, min_clip=0, min_clip_total=0):
-    """cluster_fn(int32 [m, 6] records on `device`, params dict) -> (uint8 tensor of 48-byte records, count).
+def joint_merge(paths, cluster_fn, device, window=-1, min_support=5, min_clip=0, min_clip_total=0, lib=None):
+    """lib: a StrGpu context whose communicator spans the job (comm_init): the exchange, the per-rank clustering and the
+    all-gather then all happen inside libstrgpu.so (strgpu_cluster_sharded) -- the GPU path.  Without it (CPU tests of the
+    host logic over gloo) cluster_fn(int32 [m, 6] records on `device`, params dict) -> (uint8 tensor of 48-byte records, count)
+    is called on what torch.distributed delivered.
     Returns (bounds lines, or None on ranks other than 0; per-rank record counts)."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -120,31 +124,24 @@ def joint_merge(paths, cluster_fn, device, window=-1, min_support=5, min_clip=0,
     params = dict(window=window, min_support=min_support, min_clip=min_clip, min_clip_total=min_clip_total,
                   max_clip_dist=int(0.5 * float(frag_median(frag, 0.5))) & 0xFFFF, merge_mode=True)
     mine = np.concatenate(parts) if parts else np.zeros(0, dtype=TREAD_DTYPE)
+    if lib is not None:
+        max_n = len(mine)
+        if world > 1:
+            m = torch.tensor([max_n], dtype=torch.int64, device=device)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            max_n = int(m.item())
+        if world > 1:
+            res, _ = lib.cluster_sharded(mine, max(max_n, 1), **params)
+        else:
+            res, _ = lib.cluster(mine, **params)
+        if rank != 0:
+            return None, [len(res)]
+        return [bounds_line(b, targets) for b in res if b["tid"] >= 0], [len(res)]
     t32 = torch.from_numpy(mine.view(np.uint8).reshape(-1).view(np.int32).reshape(-1, 6).copy()).to(device)
     res, counts = parallel.cluster_sharded(lambda owned: cluster_fn(owned, params), t32)
     if rank != 0:
         return None, counts
     return [bounds_line(b, targets) for b in res if b["tid"] >= 0], counts
-
-
-def gpu_cluster_fn(g):
-    """The CUDA path: strgpu_cluster_device on the rank's GPU."""
-    def fn(owned: torch.Tensor, params: dict):
-        dev = owned.device
-        n = int(owned.shape[0])
-        cap = max(1024, n // 2)
-        d_bounds = torch.zeros(cap * BOUNDS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-        d_n = torch.zeros(1, dtype=torch.int32, device=dev)
-        p = g.cluster_params(params["window"], params["min_support"], params["min_clip"], params["min_clip_total"], params["max_clip_dist"],
-                             params["merge_mode"])
-        owned = owned.contiguous()
-        g.cluster_device(owned.data_ptr() if n else d_bounds.data_ptr(), n, p, d_bounds.data_ptr(), cap, d_n.data_ptr(),
-                         torch.cuda.current_stream(dev).cuda_stream)
-        produced = int(d_n.item())
-        if produced > cap:
-            raise SystemExit("[strling] joint merge: bounds capacity too small")
-        return d_bounds, produced
-    return fn
 
 
 def main(argv=None):
@@ -167,7 +164,9 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     with sb.StrGpu(local) as g:
-        lines, counts = joint_merge(a.bins, gpu_cluster_fn(g), dev, a.window, a.min_support, a.min_clip, a.min_clip_total)
+        if world > 1:
+            g.comm_init_torch()
+        lines, counts = joint_merge(a.bins, None, dev, a.window, a.min_support, a.min_clip, a.min_clip_total, lib=g)
     if lines is not None:
         with open(a.output_prefix + "-bounds.txt", "w") as fh:
             fh.write(BOUNDS_HEADER + "\n" + "".join(l + "\n" for l in lines))
