@@ -280,7 +280,7 @@ def run_ours(args):
         mt = torch.tensor([n_treads], dtype=torch.int64, device=dev)
         dist.all_reduce(mt, op=dist.ReduceOp.MAX)
         max_treads = int(mt.item())
-    cap_bounds = max(1024, n_treads // 2) * world
+    cap_bounds = max(4096, n_treads // 32) * world   # ~1 cluster record per 110 STR reads here; a rank may fill cap / world of it
     pair_capacity = max_treads // world + max_treads // (2 * world) + 4096   # 50 % slack over an even split (few, large buckets here)
     d_bounds = torch.zeros(cap_bounds * 48, dtype=torch.uint8, device=dev)
     d_nb = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -115,7 +115,7 @@ def _revcomp(s: str) -> str:
 
 
 def simulate_alignments(seed: int, n_pairs: int, targets, loci, read_len: int = 150, insert_mean: float = 400, insert_sd: float = 60,
-                        str_pair_frac: float = 0.3, unmapped_pairs: int = 0, n_frac: float = 0.0):
+                        str_pair_frac: float = 0.3, unmapped_pairs: int = 0, n_frac: float = 0.0, name_prefix: str = ""):
     """Synthetic stand-in for `bwa mem` output around STR loci.
     loci: [(tid, start, stop, unit)].  Returns a coordinate-sorted list of Aln (unplaced pairs last).
     Pair kinds: background (both mates random sequence, 150M, proper pair), spanning-clip (one mate soft-clipped
@@ -148,7 +148,7 @@ def simulate_alignments(seed: int, n_pairs: int, targets, loci, read_len: int = 
                 isize = (hi - lo) if me["pos"] <= mate["pos"] else -(hi - lo)
                 if me["pos"] == mate["pos"]:
                     isize = (hi - lo) if first else -(hi - lo)
-            out.append(Aln(name, flag, me["tid"], me["pos"], me["mapq"], me["cigar"], mate["tid"], mate["pos"], isize, me["seq"]))
+            out.append(Aln(name_prefix + name, flag, me["tid"], me["pos"], me["mapq"], me["cigar"], mate["tid"], mate["pos"], isize, me["seq"]))
 
     def frag():
         return int(np.clip(rng.normal(insert_mean, insert_sd), L + 10, 4000))

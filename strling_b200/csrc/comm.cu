@@ -19,7 +19,10 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "ctx.cuh"
 
@@ -71,7 +74,13 @@ static NcclApi *nccl_api() {
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
-  DevBuf send, recv, own, counts, gath, cat, small;
+  DevBuf send, recv, own, counts, gath, cat, small, peer_tab;
+  // peer-to-peer exchange: every rank's receive buffer is mapped into every other rank (cudaIpc over NVLink / NVSwitch), so the
+  // partition kernel stores each record straight into its owner's memory -- partition and exchange are ONE kernel, only the
+  // records themselves cross the links (no padded slots), and the count all-gather that follows is the barrier
+  int tab_flip = 0;
+  void *peer_recv[256] = {nullptr};   // [rank] -> that rank's recv buffer in this process's address space (own entry: recv.p)
+  bool p2p = false;
   // small (uint32 words): [0 .. W) send counts, [W .. W + W*W) count matrix [src][dst], then: records owned, local bounds,
   // W gathered bound counts, total bounds, overflow flags (bit 0 exchange slot, bit 1 gather slot)
 };
@@ -85,8 +94,11 @@ struct Comm {
 void comm_release(strgpu_ctx *ctx) {
   if (!ctx || !ctx->comm) return;
   Comm *c = ctx->comm;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; r++)
+    if (c->p2p && r != c->rank && c->peer_recv[r]) cudaIpcCloseMemHandle(c->peer_recv[r]);
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
-  for (DevBuf *b : {&c->send, &c->recv, &c->own, &c->counts, &c->gath, &c->cat, &c->small})
+  for (DevBuf *b : {&c->send, &c->recv, &c->own, &c->counts, &c->gath, &c->cat, &c->small, &c->peer_tab})
     if (b->p) cudaFree(b->p);
   delete c;
   ctx->comm = nullptr;
@@ -120,13 +132,23 @@ __global__ void __launch_bounds__(kPartWarps * 32) part_histogram(const strgpu_t
   if (threadIdx.x < world) counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];
 }
 
-// offsets = exclusive scan of counts in (owner, tile) order.  Send slot of a record = owner * pair_cap + its rank among the
-// records of that owner (input order: stable).  sendcnt[owner] is written by the last tile.
+// offsets = exclusive scan of counts in (owner, tile) order.  Slot of a record = its rank among the records this shard has for
+// that owner (input order: stable).  The tile is first sorted by owner in shared memory, then copied out run by run, so the
+// stores to one owner are consecutive 24-byte records: dst_tab[owner] + slot.  dst_tab points either into the local send
+// buffer (NCCL exchange) or -- peer-to-peer -- straight into the owner's receive buffer on another GPU.
+// sendcnt[owner] is written by the last tile.
+constexpr int kPartSmem = kPartTile * sizeof(strgpu_tread) + kPartTile + kPartWarps * kMaxWorld * 4 + 2 * kMaxWorld * 4;
+
 __global__ void __launch_bounds__(kPartWarps * 32) part_scatter(const strgpu_tread *__restrict__ treads, uint32_t n, uint32_t world,
                                                                 uint32_t n_tiles, const uint32_t *__restrict__ offsets, uint32_t pair_cap,
-                                                                strgpu_tread *__restrict__ send, uint32_t *__restrict__ sendcnt,
+                                                                strgpu_tread *const *__restrict__ dst_tab, uint32_t *__restrict__ sendcnt,
                                                                 uint32_t *__restrict__ flags) {
-  __shared__ uint32_t whist[kPartWarps][kMaxWorld];
+  extern __shared__ __align__(16) unsigned char part_smem[];
+  unsigned long long *stage = reinterpret_cast<unsigned long long *>(part_smem);                     // kPartTile records, 3 words each
+  unsigned char *own_of = part_smem + kPartTile * sizeof(strgpu_tread);                               // owner of the record at a tile position
+  uint32_t(*whist)[kMaxWorld] = reinterpret_cast<uint32_t(*)[kMaxWorld]>(own_of + kPartTile);        // [warp][owner]
+  uint32_t *lbase = reinterpret_cast<uint32_t *>(whist + kPartWarps);                                 // tile-local first position of an owner
+  uint32_t *gbase = lbase + kMaxWorld;                                                                // its first slot in the owner's segment
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t beg = blockIdx.x * kPartTile, end = min(n, beg + kPartTile);
   const uint32_t wbeg = min(end, beg + warp * kPartSpan), wend = min(end, wbeg + kPartSpan);
@@ -134,37 +156,73 @@ __global__ void __launch_bounds__(kPartWarps * 32) part_scatter(const strgpu_tre
   __syncthreads();
   for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&whist[warp][bucket_owner(treads[i], world)], 1u);
   __syncthreads();
-  if ((uint32_t)tid < world) {
-    // first slot of this tile's records inside the owner's segment, then the prefix over the warps
-    uint32_t run = offsets[(size_t)tid * n_tiles + blockIdx.x] - offsets[(size_t)tid * n_tiles];
+  {
+    uint32_t run = 0;
     for (int w = 0; w < kPartWarps; w++) {
       const uint32_t c = whist[w][tid];
       whist[w][tid] = run;
       run += c;
     }
-    if (blockIdx.x == n_tiles - 1) {
-      sendcnt[tid] = run;   // records for this owner in the whole shard
-      if (run > pair_cap) atomicOr(flags, 1u);
+    // exclusive scan of the owners' tile totals (256 threads: one warp-shuffle scan + warp totals through lbase)
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
     }
+    if (lane == 31) gbase[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < warp; w++) before += gbase[w];
+    __syncthreads();
+    const uint32_t ex = before + inc - run;
+    lbase[tid] = ex;
+    for (int w = 0; w < kPartWarps; w++) whist[w][tid] += ex;
+    uint32_t first = 0;
+    if ((uint32_t)tid < world) {
+      first = offsets[(size_t)tid * n_tiles + blockIdx.x] - offsets[(size_t)tid * n_tiles];
+      if (blockIdx.x == n_tiles - 1) {
+        sendcnt[tid] = first + run;   // records for this owner in the whole shard
+        if (first + run > pair_cap) atomicOr(flags, 1u);
+      }
+    }
+    gbase[tid] = first;
   }
   __syncthreads();
   const uint32_t lane_lt = (1u << lane) - 1u;
   for (uint32_t base = wbeg; base < wend; base += 32) {
     const uint32_t i = base + lane;
     const bool valid = i < wend;
-    strgpu_tread t;
+    unsigned long long w0 = 0, w1 = 0, w2 = 0;
     uint32_t o = 0x10000u + (uint32_t)lane;
     if (valid) {
-      t = treads[i];
+      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(treads + i);
+      w0 = src[0]; w1 = src[1]; w2 = src[2];
+      strgpu_tread t;
+      reinterpret_cast<unsigned long long *>(&t)[0] = w0;
+      reinterpret_cast<unsigned long long *>(&t)[1] = w1;
+      reinterpret_cast<unsigned long long *>(&t)[2] = w2;
       o = bucket_owner(t, world);
     }
     const uint32_t grp = __match_any_sync(kFull, o);
-    uint32_t slot = 0;
-    if (valid) slot = whist[warp][o] + __popc(grp & lane_lt);   // lane order == input order: stable
+    uint32_t local = 0;
+    if (valid) local = whist[warp][o] + __popc(grp & lane_lt);   // lane order == input order: stable
     __syncwarp();
     if (valid && lane == 31 - __clz(grp)) whist[warp][o] += __popc(grp);
     __syncwarp();
-    if (valid && slot < pair_cap) send[(size_t)o * pair_cap + slot] = t;
+    if (valid) {
+      stage[3 * local] = w0; stage[3 * local + 1] = w1; stage[3 * local + 2] = w2;
+      own_of[local] = (unsigned char)o;
+    }
+  }
+  __syncthreads();
+  for (uint32_t j = tid; j < end - beg; j += kPartWarps * 32) {
+    const uint32_t o = own_of[j];
+    const uint32_t slot = gbase[o] + (j - lbase[o]);
+    if (slot < pair_cap) {
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(dst_tab[o] + slot);
+      dst[0] = stage[3 * j]; dst[1] = stage[3 * j + 1]; dst[2] = stage[3 * j + 2];
+    }
   }
 }
 
@@ -253,6 +311,76 @@ int strgpu_comm_info(const strgpu_ctx *ctx, int *rank, int *world) {
 
 void strgpu_comm_destroy(strgpu_ctx *ctx) { comm_release(ctx); }
 
+namespace strgpu_internal {
+namespace {
+// (Re)allocates the receive buffer and maps every rank's buffer into every other rank.  Collective and synchronising: it runs
+// when a call needs a larger buffer than the last one, which every rank decides identically from the call's arguments.
+int setup_recv(strgpu_ctx *ctx, Comm *c, size_t bytes, cudaStream_t st) {
+  NcclApi *api = nccl_api();
+  const int W = c->world;
+  CU(ctx, cudaStreamSynchronize(st));
+  for (int r = 0; r < W; r++)
+    if (c->p2p && r != c->rank && c->peer_recv[r]) cudaIpcCloseMemHandle(c->peer_recv[r]);
+  for (int r = 0; r < W; r++) c->peer_recv[r] = nullptr;
+  c->p2p = false;
+  // nobody may free a buffer a peer still has mapped: a collective round trip first
+  int rc;
+  if ((rc = ensure(ctx, c->small, 4096))) return rc;
+  NC(ctx, api->AllGather(c->small.p, (char *)c->small.p + 1024, 4, ncclUint8, c->comm, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  if ((rc = ensure(ctx, c->recv, bytes))) return rc;
+  if ((rc = ensure(ctx, c->peer_tab, (size_t)2 * kMaxWorld * sizeof(void *)))) return rc;
+  static const bool no_p2p = getenv("STRGPU_NO_P2P") != nullptr;
+  // exchange the IPC handles (64 bytes each) through the communicator
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  static_assert(sizeof(Msg) == 80, "handle message");
+  Msg mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.ok = (!no_p2p && cudaIpcGetMemHandle(&mine.h, c->recv.p) == cudaSuccess) ? 1 : 0;
+  if (!mine.ok) cudaGetLastError();
+  char *dbuf = nullptr;
+  CU(ctx, cudaMalloc(&dbuf, sizeof(Msg) * (size_t)(W + 1)));
+  CU(ctx, cudaMemcpyAsync(dbuf, &mine, sizeof(Msg), cudaMemcpyHostToDevice, st));
+  NC(ctx, api->AllGather(dbuf, dbuf + sizeof(Msg), sizeof(Msg), ncclUint8, c->comm, st));
+  std::vector<Msg> all((size_t)W);
+  CU(ctx, cudaMemcpyAsync(all.data(), dbuf + sizeof(Msg), sizeof(Msg) * (size_t)W, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  bool ok = true;
+  for (int r = 0; r < W; r++) ok = ok && all[(size_t)r].ok;
+  int opened = 1;
+  if (ok) {
+    for (int r = 0; r < W && opened; r++) {
+      if (r == c->rank) { c->peer_recv[r] = c->recv.p; continue; }
+      if (cudaIpcOpenMemHandle(&c->peer_recv[r], all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        c->peer_recv[r] = nullptr;
+        opened = 0;
+      }
+    }
+  } else {
+    opened = 0;
+  }
+  // every rank must have every mapping, or all fall back to the NCCL exchange
+  CU(ctx, cudaMemcpyAsync(dbuf, &opened, 4, cudaMemcpyHostToDevice, st));
+  NC(ctx, api->AllGather(dbuf, dbuf + sizeof(Msg), 4, ncclUint8, c->comm, st));
+  std::vector<int> flags((size_t)W);
+  CU(ctx, cudaMemcpyAsync(flags.data(), dbuf + sizeof(Msg), 4 * (size_t)W, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  cudaFree(dbuf);
+  bool all_open = true;
+  for (int r = 0; r < W; r++) all_open = all_open && flags[(size_t)r] == 1;
+  if (!all_open) {
+    for (int r = 0; r < W; r++) {
+      if (r != c->rank && c->peer_recv[r]) cudaIpcCloseMemHandle(c->peer_recv[r]);
+      c->peer_recv[r] = nullptr;
+    }
+  }
+  c->p2p = all_open;
+  return STRGPU_OK;
+}
+}  // namespace
+}  // namespace strgpu_internal
+
 int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, uint32_t max_n, uint32_t pair_capacity,
                                   const strgpu_cluster_params *params, void *d_out, uint32_t cap, void *d_n_out, void *cuda_stream) {
   if (!ctx || !params || !d_n_out || (n && !d_treads) || (cap && !d_out)) return fail(ctx, STRGPU_ERR_INVALID, "cluster_sharded: null argument");
@@ -274,8 +402,8 @@ int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_
   const uint32_t rank_cap = std::max<uint32_t>(1u, cap / W);   // bounds a rank may contribute to the gather
   const uint32_t n_tiles = std::max<uint32_t>(1u, (n + kPartTile - 1) / kPartTile);
   int rc;
-  if ((rc = ensure(ctx, c->send, (size_t)own_max * sizeof(strgpu_tread)))) return rc;
-  if ((rc = ensure(ctx, c->recv, (size_t)own_max * sizeof(strgpu_tread)))) return rc;
+  if ((size_t)own_max * sizeof(strgpu_tread) > c->recv.cap && (rc = setup_recv(ctx, c, (size_t)own_max * sizeof(strgpu_tread), st))) return rc;
+  if (!c->p2p && (rc = ensure(ctx, c->send, (size_t)own_max * sizeof(strgpu_tread)))) return rc;
   if ((rc = ensure(ctx, c->own, (size_t)own_max * sizeof(strgpu_tread) + 64))) return rc;
   if ((rc = ensure(ctx, c->counts, (size_t)W * n_tiles * 4 + 64))) return rc;
   if ((rc = ensure(ctx, c->gath, (size_t)W * rank_cap * sizeof(strgpu_bounds)))) return rc;
@@ -288,36 +416,64 @@ int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_
   CU(ctx, cudaMemsetAsync(small, 0, small_words * 4, st));
   strgpu_tread *send = (strgpu_tread *)c->send.p, *recv = (strgpu_tread *)c->recv.p, *own = (strgpu_tread *)c->own.p;
   uint64_t launches = 0;
+  // STRGPU_COMM_TIMING=1 (profiling only): per-phase device times on stderr; the call then synchronises
+  static const bool timing = getenv("STRGPU_COMM_TIMING") != nullptr;
+  cudaEvent_t ev[6] = {nullptr};
+  auto mark = [&](int i) {
+    if (!timing) return;
+    cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[i], st);
+  };
+  mark(0);
 
-  // 1. stable partition by owner into the send slots
-  uint32_t *counts = (uint32_t *)c->counts.p;
-  part_histogram<<<n_tiles, kPartWarps * 32, 0, st>>>((const strgpu_tread *)d_treads, n, W, n_tiles, counts);
-  CU(ctx, strgpu::scan_u32(ctx->cluster_ws, counts, counts, W * n_tiles, nullptr, st, &launches));
-  part_scatter<<<n_tiles, kPartWarps * 32, 0, st>>>((const strgpu_tread *)d_treads, n, W, n_tiles, counts, pair_cap, send, sendcnt, flags);
-  launches += 2;
-  CU(ctx, cudaGetLastError());
-
-  // 2. counts (all-gather of the W send counts -> [src][dst] matrix) and records (fixed-capacity slots) to their owners
-  NC(ctx, api->AllGather(sendcnt, cntmat, W, ncclUint32, c->comm, st));
-  NC(ctx, api->GroupStart());
-  for (uint32_t peer = 0; peer < W; peer++) {
-    if (peer == me) continue;
-    NC(ctx, api->Send(send + (size_t)peer * pair_cap, (size_t)pair_cap * sizeof(strgpu_tread), ncclUint8, (int)peer, c->comm, st));
-    NC(ctx, api->Recv(recv + (size_t)peer * pair_cap, (size_t)pair_cap * sizeof(strgpu_tread), ncclUint8, (int)peer, c->comm, st));
+  // 1. stable partition by owner: into the owners' receive buffers (peer-to-peer stores over NVLink) or the local send slots
+  {
+    strgpu_tread *tab[kMaxWorld];
+    for (uint32_t r = 0; r < W; r++)
+      tab[r] = c->p2p ? (strgpu_tread *)c->peer_recv[r] + (size_t)me * pair_cap : send + (size_t)r * pair_cap;
+    static std::once_flag attr_once[64];
+    std::call_once(attr_once[ctx->device & 63], []() { cudaFuncSetAttribute(part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kPartSmem); });
+    if ((rc = ensure(ctx, c->peer_tab, (size_t)2 * kMaxWorld * sizeof(void *)))) return rc;
+    // two alternating halves so that a table still in use by the previous call's kernel is never overwritten
+    c->tab_flip ^= 1;
+    strgpu_tread **d_tab = (strgpu_tread **)c->peer_tab.p + (size_t)c->tab_flip * kMaxWorld;
+    CU(ctx, cudaMemcpyAsync(d_tab, tab, W * sizeof(void *), cudaMemcpyHostToDevice, st));
+    uint32_t *counts = (uint32_t *)c->counts.p;
+    part_histogram<<<n_tiles, kPartWarps * 32, 0, st>>>((const strgpu_tread *)d_treads, n, W, n_tiles, counts);
+    CU(ctx, strgpu::scan_u32(ctx->cluster_ws, counts, counts, W * n_tiles, nullptr, st, &launches));
+    part_scatter<<<n_tiles, kPartWarps * 32, kPartSmem, st>>>((const strgpu_tread *)d_treads, n, W, n_tiles, counts, pair_cap, d_tab, sendcnt, flags);
+    launches += 2;
+    CU(ctx, cudaGetLastError());
   }
-  NC(ctx, api->GroupEnd());
-  CU(ctx, cudaMemcpyAsync(recv + (size_t)me * pair_cap, send + (size_t)me * pair_cap, (size_t)pair_cap * sizeof(strgpu_tread),
-                          cudaMemcpyDeviceToDevice, st));
+
+  mark(1);
+  // 2. counts (all-gather of the W send counts -> [src][dst] matrix) and records (fixed-capacity slots) to their owners
+  // (peer-to-peer: the records are already in place; a rank's counts arrive after its partition kernel has finished, so this
+  // all-gather is also the barrier that makes every peer's stores into recv visible)
+  NC(ctx, api->AllGather(sendcnt, cntmat, W, ncclUint32, c->comm, st));
+  if (!c->p2p) {
+    NC(ctx, api->GroupStart());
+    for (uint32_t peer = 0; peer < W; peer++) {
+      if (peer == me) continue;
+      NC(ctx, api->Send(send + (size_t)peer * pair_cap, (size_t)pair_cap * sizeof(strgpu_tread), ncclUint8, (int)peer, c->comm, st));
+      NC(ctx, api->Recv(recv + (size_t)peer * pair_cap, (size_t)pair_cap * sizeof(strgpu_tread), ncclUint8, (int)peer, c->comm, st));
+    }
+    NC(ctx, api->GroupEnd());
+    CU(ctx, cudaMemcpyAsync(recv + (size_t)me * pair_cap, send + (size_t)me * pair_cap, (size_t)pair_cap * sizeof(strgpu_tread),
+                            cudaMemcpyDeviceToDevice, st));
+  }
   {
     dim3 grid((pair_cap + 255) / 256, W);
     compact_received<<<grid, 256, 0, st>>>(recv, cntmat, W, me, pair_cap, own, n_own);
     launches++;
   }
 
+  mark(2);
   // 3. cluster what this rank owns (record count known to the device only)
   strgpu_bounds *local = (strgpu_bounds *)c->cat.p + (size_t)W * rank_cap;   // the slot after the concatenation buffer
   CU(ctx, strgpu::run_cluster(ctx->cluster_ws, own, own_max, *params, local, rank_cap, n_loc, st, &launches, nullptr, n_own));
 
+  mark(3);
   // 4. all-gather of the cluster records, then single-GPU order
   NC(ctx, api->AllGather(n_loc, gcnt, 1, ncclUint32, c->comm, st));
   NC(ctx, api->AllGather(local, c->gath.p, (size_t)rank_cap * sizeof(strgpu_bounds), ncclUint8, c->comm, st));
@@ -326,8 +482,18 @@ int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_
     compact_gathered<<<grid, 256, 0, st>>>((const strgpu_bounds *)c->gath.p, gcnt, W, rank_cap, (strgpu_bounds *)c->cat.p, n_total, flags);
     launches++;
   }
+  mark(4);
   CU(ctx, strgpu::sort_bounds_device(ctx->cluster_ws, (const strgpu_bounds *)c->cat.p, W * rank_cap, n_total, (strgpu_bounds *)d_out, cap,
                                      (uint32_t *)d_n_out, st, &launches));
+  mark(5);
+  if (timing) {
+    cudaStreamSynchronize(st);
+    float t[5];
+    for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+    fprintf(stderr, "[strgpu rank %u] sharded cluster: partition %.3f ms, exchange %.3f, cluster %.3f, gather %.3f, order %.3f (pair_cap %u, own_max %u, rank_cap %u, %s)\n",
+            me, t[0], t[1], t[2], t[3], t[4], pair_cap, own_max, rank_cap, c->p2p ? "peer-to-peer stores" : "NCCL send/recv");
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->launches += launches;
   return STRGPU_OK;

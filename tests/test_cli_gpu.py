@@ -161,6 +161,53 @@ def test_call_and_merge_outputs_identical(cli, tmp_path):
     assert got == [l for l in all_lines if l.split("\t")[0] == targets[2][0]] and len(got) > 0
 
 
+def _simulate_chunk(args):
+    seed, n_pairs, targets, loci, frac, unmapped = args
+    return bamio.simulate_alignments(seed, n_pairs, targets, loci, str_pair_frac=frac, unmapped_pairs=unmapped, name_prefix=f"c{seed}_")
+
+
+def test_config3_30x_depth_extract_then_call(cli, tmp_path):
+    # BASELINE.json configs[3] at real depth: the sim/ disease loci (tests/golden/disease_loci.json) on contigs sized so that
+    # 10^6 read pairs of 150 bp are 30x coverage (sim/sim_shared.groovy:6,65), through `strling extract` -> `strling call`;
+    # .bin byte-identical, bounds / unplaced / genotype lines equal to the oracle's.  STRLING_CONFIG3_PAIRS scales it.
+    import multiprocessing as mp
+
+    n_pairs = int(os.environ.get("STRLING_CONFIG3_PAIRS", "1000000"))
+    loci_json = json.load(open(os.path.join(HERE, "golden", "disease_loci.json")))
+    chroms = sorted({l["chrom"] for l in loci_json}, key=lambda c: (len(c), c))
+    contig = max(100_000, n_pairs * 300 // 30 // len(chroms))
+    targets = [(f"chr{c}", contig) for c in chroms]
+    loci = []
+    for l in loci_json:
+        start = 20_000 + l["start"] % (contig - 40_000)
+        loci.append((chroms.index(l["chrom"]), start, start + max(20, min(200, l["stop"] - l["start"])), l["unit"]))
+    n_chunks = 16
+    jobs = [(100 + c, n_pairs // n_chunks, targets, loci, 0.03, 40) for c in range(n_chunks)]
+    with mp.get_context("fork").Pool(min(n_chunks, os.cpu_count() or 1)) as pool:
+        parts = pool.map(_simulate_chunk, jobs)
+    placed = [a for part in parts for a in part if a.tid >= 0]
+    unplaced = [a for part in parts for a in part if a.tid < 0]
+    placed.sort(key=lambda a: (a.tid, a.pos))
+    recs = placed + unplaced
+    assert len(recs) >= 2 * (n_pairs // n_chunks) * n_chunks
+    hdr = bamio.sam_header(targets)
+    bam, out = str(tmp_path / "c3.bam"), str(tmp_path / "c3.bin")
+    bamio.write_bam(bam, hdr, targets, recs)
+    run(cli, "extract", bam, out)
+    exp, cache, _ = eo.extract(recs, targets, hdr)
+    assert open(out, "rb").read() == exp and len(cache) > n_pairs // 100
+    prefix = str(tmp_path / "c3")
+    run(cli, "call", "-o", prefix, bam, out)
+    exp_gt, exp_lines, exp_unplaced, _ = co.call(recs, exp)
+    got = open(prefix + "-bounds.txt").read().splitlines()
+    assert got[0] == eo.BOUNDS_HEADER + "\tdepth" and len(exp_lines) >= len(loci) // 2
+    assert sorted(got[1:]) == sorted(exp_lines)
+    got_un = dict(l.split("\t") for l in open(prefix + "-unplaced.txt").read().splitlines())
+    assert {k.encode(): int(v) for k, v in got_un.items()} == exp_unplaced
+    got_gt = open(prefix + "-genotype.txt").read().splitlines()
+    assert got_gt[0] == co.GT_HEADER and sorted(got_gt[1:]) == sorted(exp_gt)
+
+
 def _random_genome(seed, targets):
     rng = np.random.default_rng(seed)
 

@@ -143,3 +143,41 @@ def test_assign_reads_locus_then_cluster(gpu):
             assert len(gb) == len(eb) and gu == eu
             for f in FIELDS:
                 assert np.array_equal(gb[f], eb[f]), f
+
+
+def test_sharded_entry_points_with_a_one_rank_communicator(gpu):
+    # strgpu_comm_init + strgpu_cluster_sharded(_device) on a communicator of ONE rank (what a single-GPU box can run; 2 and 8
+    # ranks: tools/sharded_check.py and bench.py --gpus N): owner partition through the peer table, device-side record count,
+    # gather, final order -- the result must be strgpu_cluster's, in call and in merge mode
+    import torch
+
+    g = sb.StrGpu(0)
+    try:
+        g.comm_init(0, 1, sb.StrGpu.comm_unique_id())
+        treads = synth.make_treads(1500, seed=77, n_samples=4, noise_reads=30_000, unplaced=300)
+        for merge_mode in (False, True):
+            kw = dict(window=480, min_support=4, max_clip_dist=190, merge_mode=merge_mode)
+            one_b, one_u = gpu.cluster(treads, **kw)
+            many_b, many_u = g.cluster_sharded(treads, len(treads) + 5, **kw)
+            assert len(one_b) == len(many_b) > 100 and one_u == many_u
+            for f in FIELDS:
+                assert np.array_equal(one_b[f], many_b[f]), f
+            dev = torch.device("cuda", 0)
+            d_t = torch.from_numpy(treads.view(np.uint8).reshape(-1).copy()).to(dev)
+            cap = 2 * len(treads)
+            d_out = torch.zeros(cap * 48, dtype=torch.uint8, device=dev)
+            d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+            st = torch.cuda.current_stream().cuda_stream
+            g.cluster_sharded_device(d_t.data_ptr(), len(treads), len(treads), g.cluster_params(**kw), d_out.data_ptr(), cap, d_n.data_ptr(), st)
+            g.comm_status(st)
+            got = d_out[: int(d_n.item()) * 48].cpu().numpy().view(sb.BOUNDS_DTYPE)
+            got = got[got["tid"] >= 0]
+            assert len(got) == len(one_b) and all(np.array_equal(one_b[f], got[f]) for f in FIELDS)
+        # a pair capacity that is too small is reported, not silently truncated
+        g.cluster_sharded_device(d_t.data_ptr(), len(treads), len(treads), g.cluster_params(**kw), d_out.data_ptr(), cap, d_n.data_ptr(), st,
+                                 pair_capacity=100)
+        with pytest.raises(sb.StrGpuError) as e:
+            g.comm_status(st)
+        assert e.value.status == -7
+    finally:
+        g.close()
