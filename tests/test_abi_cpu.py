@@ -29,6 +29,27 @@ def test_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), f"libstrgpu.so does not export {n}"
 
 
+def test_nim_shim_declares_every_entry_point_with_the_headers_arity():
+    # strling_b200/nim/strgpu.nim cannot be compiled here (no nim): at least keep it in step with include/strgpu.h -- every
+    # entry point declared, with as many parameters as the C prototype has
+    hdr = open(os.path.join(ROOT, "include", "strgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    nim = open(os.path.join(ROOT, "strling_b200", "nim", "strgpu.nim")).read()
+    protos = dict(re.findall(r"\b(strgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S))
+    assert len(protos) >= 30
+    for name, args in protos.items():
+        n_c = 0 if args.strip() in ("", "void") else args.count(",") + 1
+        m = re.search(r"proc " + name + r"\*\((.*?)\)(?::|\s*$)", nim, flags=re.S | re.M)
+        assert m, f"strgpu.nim does not declare {name}"
+        params = m.group(1)
+        n_nim = 0
+        for group in [g for g in params.split(";")] if ";" in params else [params]:
+            for decl in re.split(r",(?![^\[]*\])", group):
+                if decl.strip():
+                    n_nim += 1
+        assert n_nim == n_c, f"{name}: {n_c} parameters in strgpu.h, {n_nim} in strgpu.nim"
+
+
 def test_struct_layouts():
     assert sb.SEGMENT_DTYPE.itemsize == 8 and sb.REPEAT_DTYPE.itemsize == 8
     assert sb.SEGMENT_DTYPE.fields["len"][1] == 4 and sb.REPEAT_DTYPE.fields["repeat_count"][1] == 6

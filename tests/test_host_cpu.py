@@ -140,3 +140,99 @@ def test_cli_fails_loudly_without_gpu(cli, sim, tmp_path):
     r = subprocess.run([cli, "extract", bam, str(tmp_path / "x.bin")], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
     assert not os.path.exists(tmp_path / "x.bin")
+
+
+def test_bam_decode_against_an_independent_encoder(cli, tmp_path):
+    """host/bam.hpp against a BAM laid out HERE from the SAM/BAM specification (SAMv1 section 4.2) with nothing shared with
+    strling_b200/bamio.py: records span BGZF block boundaries, blocks have uneven sizes and different deflate settings
+    (stored, fixed and dynamic Huffman), the gzip extra field carries a second subfield, tags and qualities follow the SEQ,
+    one CIGAR has every operator and one read has no CIGAR / SEQ at all."""
+    import struct
+    import zlib
+
+    nib = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    ops = {c: i for i, c in enumerate("MIDNSHP=X")}
+
+    def record(qname, flag, tid, pos, mapq, cigar, mtid, mpos, tlen, seq, tags=b""):
+        name = qname.encode() + b"\0"
+        cig = b"".join(struct.pack("<I", (n << 4) | ops[o]) for n, o in cigar)
+        sq = bytearray((len(seq) + 1) // 2)
+        for i, ch in enumerate(seq):
+            sq[i // 2] |= nib[ch] << (4 if i % 2 == 0 else 0)
+        qual = bytes([0xFF] * len(seq))
+        ref_span = sum(n for n, o in cigar if o in "MDN=X")
+        end = pos + (ref_span if ref_span else 1)
+        # reg2bin (SAMv1 section 5.3)
+        b, e = max(pos, 0), max(end, 1) - 1
+        bin_ = next((((1 << s) - 1) // 7 + (b >> sh) for s, sh in ((15, 14), (12, 17), (9, 20), (6, 23), (3, 26)) if b >> sh == e >> sh), 0)
+        core = struct.pack("<iiBBHHHIiii", tid, pos, len(name), mapq, bin_, len(cigar), flag, len(seq), mtid, mpos, tlen)
+        body = core + name + cig + bytes(sq) + qual + tags
+        return struct.pack("<i", len(body)) + body
+
+    targets = [("chrA", 100_000), ("chrB_random", 5_000)]
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in targets) + "@PG\tID:hand\n"
+    hdr = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(targets))
+    for n, l in targets:
+        hdr += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    rng = np.random.default_rng(99)
+    expect, body = [], b""
+    every_op = [(5, "S"), (10, "M"), (2, "I"), (3, "D"), (7, "N"), (4, "="), (1, "X"), (6, "M"), (2, "P"), (3, "H")]
+    for i in range(400):
+        kind = i % 5
+        seq = "".join(rng.choice(list("ACGTN" if i % 7 else "ACGTRYKMSWBDHVN="), size=int(rng.integers(30, 260))))
+        cigar = [(len(seq), "M")]
+        if kind == 1:
+            cigar = [(20, "S"), (len(seq) - 20, "M")]
+        elif kind == 2:
+            seq = seq[:38]
+            cigar = every_op   # query-consuming ops: 5+10+2+4+1+6 = 28 ... make SEQ match below
+            seq = (seq * 2)[: sum(n for n, o in every_op if o in "MIS=X")]
+        elif kind == 3:
+            cigar = [(len(seq) - 17, "M"), (17, "S")]
+        tid, pos = (0, 100 + 37 * i) if i < 390 else (-1, -1)
+        if tid < 0:
+            cigar = []
+        flag = [99, 147, 83, 163, 77, 141, 1, 2113, 355][i % 9] if tid >= 0 else 77
+        tags = struct.pack("<2sci", b"NM", b"i", i) + b"RGZgrp" + bytes([0])
+        if i == 123:
+            seq, cigar = "", []     # no SEQ: l_seq = 0
+        body += record(f"q{i}:{'x' * (i % 40)}", flag, tid, pos, i % 61, cigar, 1 if i % 11 == 0 else tid, pos + 300 if tid >= 0 else -1,
+                       (350 if i % 2 == 0 else -350) if tid >= 0 else 0, seq, tags)
+        cig_s = "".join(f"{n}{o}" for n, o in cigar) or "*"
+        span = sum(n for n, o in cigar if o in "MDN=X")
+        expect.append((f"q{i}:{'x' * (i % 40)}", flag, tid, pos, i % 61, cig_s, 1 if i % 11 == 0 else tid, pos + 300 if tid >= 0 else -1,
+                       ((350 if i % 2 == 0 else -350) if tid >= 0 else 0), seq, span))
+    payload = hdr + body
+
+    def bgzf(data, level, strategy, extra_sub):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+        comp = co.compress(data) + co.flush()
+        xlen = 6 + len(extra_sub)
+        bsize = 12 + xlen + len(comp) + 8 - 1
+        assert bsize < 65536
+        return (struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, xlen) + extra_sub + struct.pack("<BBHH", 66, 67, 2, bsize) + comp
+                + struct.pack("<II", zlib.crc32(data), len(data)))
+
+    out, off, k = b"", 0, 0
+    sizes = [7, 60_000, 113, 1, 4096, 30_000, 65_280]
+    while off < len(payload):
+        n = min(sizes[k % len(sizes)], len(payload) - off)
+        level, strategy = [(0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_HUFFMAN_ONLY)][k % 4]
+        extra = struct.pack("<BBH3s", 88, 89, 3, b"abc") if k % 3 == 1 else b""   # an unrelated subfield BEFORE the BC one
+        out += bgzf(payload[off: off + n], level, strategy, extra)
+        off += n
+        k += 1
+    out += bgzf(b"", 6, zlib.Z_DEFAULT_STRATEGY, b"")    # EOF marker block
+    bam = str(tmp_path / "hand.bam")
+    open(bam, "wb").write(out)
+    lines = run(cli, "debug", "bam", bam).splitlines()
+    assert lines[0] == "@targets 2" and lines[1] == "@target\tchrA\t100000" and lines[2] == "@target\tchrB_random\t5000"
+    assert lines[3] == f"@text_bytes {len(text)}"
+    recs = [l.split("\t") for l in lines[4:]]
+    assert len(recs) == len(expect)
+    for f, e in zip(recs, expect):
+        qname, flag, tid, pos, mapq, cig, mtid, mpos, tlen, seq, span = e
+        assert f[:10] == [qname, str(flag), str(tid), str(pos), str(mapq), cig, str(mtid), str(mpos), str(tlen), seq], (f, e)
+        # hts-nim `stop` = htslib bam_endpos: pos + reference span of the CIGAR; pos + 1 for a read flagged unmapped or without
+        # a reference-consuming CIGAR
+        assert int(f[10]) == (pos + span if span and not flag & 4 else pos + 1), (f, e)
