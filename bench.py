@@ -280,7 +280,9 @@ def run_ours(args):
         mt = torch.tensor([n_treads], dtype=torch.int64, device=dev)
         dist.all_reduce(mt, op=dist.ReduceOp.MAX)
         max_treads = int(mt.item())
-    cap_bounds = max(4096, n_treads // 32) * world   # ~1 cluster record per 110 STR reads here; a rank may fill cap / world of it
+    # ~1 cluster record per 110 STR reads here; a rank may fill cap / world of it.  The sharded call is a collective: max_n,
+    # pair_capacity and cap must be THE SAME on every rank (they size the exchange and gather slots), hence max_treads
+    cap_bounds = max(4096, max_treads // 32) * world
     pair_capacity = max_treads // world + max_treads // (2 * world) + 4096   # 50 % slack over an even split (few, large buckets here)
     d_bounds = torch.zeros(cap_bounds * 48, dtype=torch.uint8, device=dev)
     d_nb = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -306,10 +308,11 @@ def run_ours(args):
     extra_max = int(segs["len"][shard_reads:].max()) if n_extra else 0
     n_extra_dev, extra_max_dev = n_extra, extra_max
     n_treads_strong = max(1000, n_treads // world)   # a 1 / world slice of the STR reads for the strong-scaling pass
+    max_strong = max(1000, max_treads // world)      # the same on every rank
 
     def cluster_strong():
-        g.cluster_sharded_device(d_treads.data_ptr(), n_treads_strong, n_treads_strong, cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(),
-                                 stream, pair_capacity=n_treads_strong // world + n_treads_strong // (2 * world) + 4096)
+        g.cluster_sharded_device(d_treads.data_ptr(), n_treads_strong, max_strong, cparams, d_bounds.data_ptr(), cap_bounds, d_nb.data_ptr(),
+                                 stream, pair_capacity=max_strong // world + max_strong // (2 * world) + 4096)
 
     # --streams 2: library calls alternate between two contexts on two streams, so that call i's scan kernel (ALU + shared-memory
     # bound, low issue rate) runs next to call i + 1's pre-filter (ALU + popcount bound) on the same SMs (STRGPU_SHARE_SM geometry)

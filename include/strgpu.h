@@ -233,7 +233,8 @@ void strgpu_comm_destroy(strgpu_ctx *ctx);   /* also done by strgpu_destroy */
  *   max_n         an upper bound of n that is THE SAME on every rank (it sizes the exchange slots)
  *   pair_capacity treads one rank may send to one owner; 0 = max_n / world * 1.25 + 1024 (a hash partition is that even);
  *                 max_n always fits.  Must be the same on every rank.
- *   d_out, cap    room for the cluster records of ALL ranks; one rank may contribute at most cap / world of them
+ *   d_out, cap    room for the cluster records of ALL ranks; one rank may contribute at most cap / world of them.
+ *                 Must be the same on every rank (like max_n and pair_capacity: they size the collectives' slots).
  *   d_n_out       device uint32: records produced by all ranks together
  * A slot that was too small is reported by strgpu_comm_status (STRGPU_ERR_OVERFLOW): the output is then incomplete. */
 int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, uint32_t max_n, uint32_t pair_capacity,
