@@ -216,13 +216,13 @@ __global__ void __launch_bounds__(kPartWarps * 32) part_scatter(const strgpu_tre
     }
   }
   __syncthreads();
-  for (uint32_t j = tid; j < end - beg; j += kPartWarps * 32) {
+  // copy-out, 8 bytes per thread and consecutive threads on consecutive words: inside an owner's run the stores of a warp are
+  // one contiguous 256-byte span (what NVLink wants when the destination is a peer's memory)
+  for (uint32_t w = tid; w < 3u * (end - beg); w += kPartWarps * 32) {
+    const uint32_t j = w / 3u, part = w - 3u * j;
     const uint32_t o = own_of[j];
     const uint32_t slot = gbase[o] + (j - lbase[o]);
-    if (slot < pair_cap) {
-      unsigned long long *dst = reinterpret_cast<unsigned long long *>(dst_tab[o] + slot);
-      dst[0] = stage[3 * j]; dst[1] = stage[3 * j + 1]; dst[2] = stage[3 * j + 2];
-    }
+    if (slot < pair_cap) reinterpret_cast<unsigned long long *>(dst_tab[o] + slot)[part] = stage[w];
   }
 }
 

@@ -1,9 +1,11 @@
 // `strling merge` (merge.nim:47-187) and the cluster loop of `strling call` (call.nim:50-130,223-235,280-281), with
 // grouping, sorting, clustering and bounds on the GPU (strgpu_cluster).  Host work: `.bin` decoding, the fragment
 // distribution medians that parameterise the kernels, and writing `-bounds.txt` / `-unplaced.txt`.
-// `-l` / `-b` loci take their reads first (assign_reads_locus, callclusters.nim:14-50; also on the GPU).
-// Not part of this build: spanning reads + genotypes (collect.nim, genotyper.nim), so `call` writes no
-// `-genotype.txt` and its bounds lines lack the trailing median-depth column (call.nim:255).
+// `-l` / `-b` loci take their reads first (assign_reads_locus, callclusters.nim:14-50; `merge -l` on the GPU through
+// strgpu_cluster_loci, `call -l / -b` on the host because its genotyper needs the reads themselves).
+// `call` then gathers the spanning-read / spanning-pair / depth evidence and genotypes every locus on the host
+// (genotype.hpp: collect.nim, spanning.nim, genotyper.nim, call.nim:158-281) and writes `-bounds.txt` with the trailing
+// median-depth column (call.nim:255), `-unplaced.txt` and `-genotype.txt`.
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
