@@ -567,7 +567,9 @@ int debug_genotype(int argc, char **argv) {
 int extract_main(int argc, char **argv) {
   static const char *usage =
       "strling extract [-f fasta] [-g genome-repeats] [-p proportion-repeat=0.8] [-q min-mapq=40] [-v] [--device N] [--threads N]\n"
-      "                [--batch-reads N] <bam> <bin>\n";
+      "                [--batch-reads N] <bam> <bin>\n"
+      "  <bam> must be coordinate-sorted with the no-coordinate reads at the end (as `samtools sort` writes it).  Reads longer\n"
+      "  than 510 bases are refused: beyond that the reference's uint8 k-mer count tables wrap (utils.nim:113-117).\n";
   Args a = parse(argc, argv, {{"-f", "--fasta", true}, {"-g", "--genome-repeats", true}, {"-p", "--proportion-repeat", true}, {"-q", "--min-mapq", true},
                               {"-v", "--verbose", false}, {"", "--device", true}, {"", "--threads", true}, {"", "--batch-reads", true}},
                  usage);

@@ -218,6 +218,7 @@ struct GLocus {
   std::unordered_map<std::string, size_t> exp_idx;
   std::vector<double> exp_vals;      // insertion order (the reference sums a Table's values: order unpinned)
   bool dead = false;                 // > 20000 read names in the window: the reference gives up on the locus (collect.nim:166-169)
+  bool finished = false;             // the stream has passed the window: evidence reduced to support / median depth / expectation
   // results
   int median_depth_v = 0;
   float expected = 0.0f;
@@ -225,6 +226,7 @@ struct GLocus {
 
 inline void locus_add_record(GLocus &L, const BamRecord &a, int stop, const std::vector<float> &cd, uint8_t min_mapq, int max_size = 5000) {
   if (L.dead) return;
+  if (L.depths.empty()) L.depths.assign((size_t)(L.wr - L.wl), 0);   // allocated when the first record of the window arrives
   if (a.flag & (0x100 | 0x800 | 0x400)) return;
   if (a.mapq < min_mapq) return;
   const int left = (int)L.left, right = (int)L.right;
@@ -264,12 +266,18 @@ inline void locus_add_record(GLocus &L, const BamRecord &a, int stop, const std:
 }
 
 inline void locus_finish(GLocus &L, const std::array<uint32_t, 4096> &frag) {
+  if (L.finished) return;
+  L.finished = true;
   if (L.dead) {
     L.median_depth_v = -1;
     L.expected = 0.0f;
     L.support.clear();
+    std::unordered_map<std::string, std::vector<GLocus::PairRec>>().swap(L.pairs);
+    std::unordered_map<std::string, size_t>().swap(L.exp_idx);
+    std::vector<int>().swap(L.depths);
     return;
   }
+  if (L.depths.empty()) L.depths.assign((size_t)(L.wr - L.wl), 0);   // no record at all: depth 0 everywhere
   float e = 0.0f;
   for (double v : L.exp_vals) e += (float)v;
   L.expected = e;
@@ -289,11 +297,17 @@ inline void locus_finish(GLocus &L, const std::array<uint32_t, 4096> &frag) {
   long run = 0;
   for (auto &d : L.depths) { run += d; d = (int)run; }
   L.median_depth_v = median_depth(L.depths);
-  L.pairs.clear();
-  L.exp_idx.clear();
+  // the window's working set (read names, per-base depth) is released as soon as the locus is done: a 30x `call` with 10^5 loci
+  // would otherwise hold every window of the genome until the end of the BAM
+  std::unordered_map<std::string, std::vector<GLocus::PairRec>>().swap(L.pairs);
+  std::unordered_map<std::string, size_t>().swap(L.exp_idx);
+  std::vector<double>().swap(L.exp_vals);
+  std::vector<int>().swap(L.depths);
 }
 
-// One pass over the BAM for every locus at once.
+// One pass over the BAM for every locus at once.  The reference queries an index per locus (collect.nim:130-146), which only
+// works on a coordinate-sorted BAM; this pass needs the same order (it is what lets a locus be finished, and its memory
+// released, as soon as the stream has passed its window) and says so when the file is not sorted.
 inline void collect_evidence(const std::string &bam, std::vector<GLocus> &loci, int window, const std::array<uint32_t, 4096> &frag, uint8_t min_mapq) {
   const std::vector<float> cd = cumulative(frag);
   int n_tid = 0;
@@ -301,7 +315,6 @@ inline void collect_evidence(const std::string &bam, std::vector<GLocus> &loci, 
     L.wl = (int)L.left - window;
     L.wr = (int)L.right + window;
     L.qbeg = std::max(0, L.wl);
-    L.depths.assign((size_t)(L.wr - L.wl), 0);
     n_tid = std::max(n_tid, L.tid + 1);
   }
   std::vector<std::vector<uint32_t>> by_tid((size_t)n_tid);
@@ -312,19 +325,35 @@ inline void collect_evidence(const std::string &bam, std::vector<GLocus> &loci, 
     std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return loci[a].qbeg < loci[b].qbeg; });
     for (uint32_t i : v) max_span[(size_t)t] = std::max(max_span[(size_t)t], loci[i].wr - loci[i].qbeg);
   }
+  std::vector<size_t> first_active((size_t)n_tid, 0);   // loci before this index (in qbeg order) are finished
+  auto finish_upto = [&](int tid, int pos) {            // every window of `tid` that ends at or before pos
+    auto &v = by_tid[(size_t)tid];
+    size_t &f = first_active[(size_t)tid];
+    while (f < v.size() && (loci[v[f]].finished || loci[v[f]].wr <= pos)) locus_finish(loci[v[f++]], frag);
+  };
   BamReader rd(bam);
   BamRecord a;
+  int last_tid = -1, last_pos = -1;
   while (rd.next(a)) {
-    if (a.tid < 0 || a.tid >= n_tid) continue;
+    if (a.tid < 0) continue;
+    if (a.tid < last_tid || (a.tid == last_tid && a.pos < last_pos))
+      throw std::runtime_error("[strling] call: " + bam + " is not coordinate-sorted (record " + std::string(a.qname, a.l_qname) +
+                               "); the reference needs a sorted, indexed BAM here too");
+    if (a.tid != last_tid)
+      for (int t = std::max(0, last_tid); t < std::min(a.tid, n_tid); t++) finish_upto(t, INT32_MAX);
+    last_tid = a.tid;
+    last_pos = a.pos;
+    if (a.tid >= n_tid) continue;
     const auto &v = by_tid[(size_t)a.tid];
     if (v.empty()) continue;
+    finish_upto(a.tid, a.pos);
     const int stop = a.stop();
     // candidates: qbeg < stop and wr > pos  =>  qbeg > pos - max_span
     const int lo_key = a.pos - max_span[(size_t)a.tid];
     auto it = std::upper_bound(v.begin(), v.end(), lo_key, [&](int key, uint32_t i) { return key < loci[i].qbeg; });
     for (; it != v.end() && loci[*it].qbeg < stop; ++it) {
       GLocus &L = loci[*it];
-      if (a.pos < L.wr && stop > L.qbeg) locus_add_record(L, a, stop, cd, min_mapq);
+      if (!L.finished && a.pos < L.wr && stop > L.qbeg) locus_add_record(L, a, stop, cd, min_mapq);
     }
   }
   for (auto &L : loci) locus_finish(L, frag);

@@ -233,3 +233,21 @@ def test_high_depth_loci_are_skipped_like_the_reference(cli, tmp_path):
     assert any(abs(p - 50_000) < 500 for p in pos)                                   # the ordinary locus is reported
     assert not any(abs(p - 150_000) < 500 for p in pos) and not any(abs(p - 300_000) < 500 for p in pos)   # the deep ones are not
     assert len(got_bounds) < len(b)
+
+
+def test_unsorted_bam_is_refused(cli, tmp_path):
+    # `call` gathers the evidence in one streaming pass that relies on coordinate order (the reference's indexed queries need a
+    # sorted BAM as well): an unsorted file must fail loudly, not produce evidence with records missing
+    targets = [("chr1", 300_000)]
+    loci = [(0, 50_000, 50_060, "CAG")]
+    recs = bamio.simulate_alignments(5, 800, targets, loci, str_pair_frac=0.3)
+    placed = [a for a in recs if a.tid >= 0]
+    placed[10], placed[400] = placed[400], placed[10]
+    hdr = bamio.sam_header(targets)
+    bam, binp, cl = str(tmp_path / "u.bam"), str(tmp_path / "u.bin"), str(tmp_path / "cl.tsv")
+    bamio.write_bam(bam, hdr, targets, placed)
+    data, _, _ = eo.extract(sorted(placed, key=lambda a: (a.tid, a.pos)), targets, hdr)
+    open(binp, "wb").write(data)
+    open(cl, "w").write("0 50000 50060 CAG 49500 50500 50030 3 3 12 0 12\n")
+    r = subprocess.run([cli, "debug", "genotype", bam, binp, cl, str(tmp_path / "o"), "500", "3", "40"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not coordinate-sorted" in r.stderr
