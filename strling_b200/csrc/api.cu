@@ -108,6 +108,7 @@ void strgpu_destroy(strgpu_ctx *ctx) {
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  if (ctx->cluster_graph.exec) cudaGraphExecDestroy(ctx->cluster_graph.exec);
   strgpu::free_workspace(ctx->cluster_ws);
   if (ctx->cl_in.p) cudaFree(ctx->cl_in.p);
   if (ctx->cl_out.p) cudaFree(ctx->cl_out.p);
@@ -385,9 +386,18 @@ int strgpu_cluster_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, con
   if (((uintptr_t)d_treads & 7) || ((uintptr_t)d_out & 7) || ((uintptr_t)d_n_out & 3))
     return fail(ctx, STRGPU_ERR_INVALID, "cluster_device: misaligned device pointer");
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, strgpu::run_cluster(ctx->cluster_ws, (const strgpu_tread *)d_treads, n, *params, (strgpu_bounds *)d_out, cap,
-                              (uint32_t *)d_n_out, (cudaStream_t)cuda_stream, &ctx->launches));
-  return STRGPU_OK;
+  const strgpu_cluster_params p = *params;
+  uint64_t key = hash_bytes(&d_treads, sizeof(d_treads));
+  key = hash_bytes(&n, sizeof(n), key);
+  key = hash_bytes(&p, sizeof(p), key);          // 16 bytes, no padding
+  key = hash_bytes(&d_out, sizeof(d_out), key);
+  key = hash_bytes(&cap, sizeof(cap), key);
+  key = hash_bytes(&d_n_out, sizeof(d_n_out), key);
+  return run_graphed(ctx, ctx->cluster_graph, key, (cudaStream_t)cuda_stream, [&](cudaStream_t st, uint64_t *launches, bool) -> int {
+    CU(ctx, strgpu::run_cluster(ctx->cluster_ws, (const strgpu_tread *)d_treads, n, p, (strgpu_bounds *)d_out, cap, (uint32_t *)d_n_out, st,
+                                launches));
+    return STRGPU_OK;
+  });
 }
 
 int strgpu_cluster(strgpu_ctx *ctx, const strgpu_tread *treads, uint32_t n, const strgpu_cluster_params *params,

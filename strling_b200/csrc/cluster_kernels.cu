@@ -887,6 +887,7 @@ static_assert(WS_COUNT_ <= (int)(sizeof(ClusterWorkspace::buf) / sizeof(void *))
 
 cudaError_t ws_ensure(ClusterWorkspace &ws, int which, size_t bytes) {
   if (bytes <= ws.cap[which]) return cudaSuccess;
+  ws.gen++;
   if (ws.buf[which]) cudaFree(ws.buf[which]);
   ws.buf[which] = nullptr;
   ws.cap[which] = 0;

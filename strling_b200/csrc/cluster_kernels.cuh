@@ -18,6 +18,7 @@ struct SortRec {  // 16-byte radix-sort record: key fields + the tread's index i
 struct ClusterWorkspace {
   void *buf[20] = {nullptr};
   size_t cap[20] = {0};
+  uint64_t gen = 0;   // bumped whenever a buffer is reallocated: captured CUDA graphs that hold the old pointers are stale
 };
 
 // Loci for assign_reads_locus, already grouped on the host: loci of one bucket are consecutive ("chain") and keep

@@ -79,6 +79,8 @@ struct Comm {
   // partition kernel stores each record straight into its owner's memory -- partition and exchange are ONE kernel, only the
   // records themselves cross the links (no padded slots), and the count all-gather that follows is the barrier
   int tab_flip = 0;
+  void *h_tab = nullptr;     // pinned copy of the destination table for captured graphs
+  GraphSlot graph;
   void *peer_recv[256] = {nullptr};   // [rank] -> that rank's recv buffer in this process's address space (own entry: recv.p)
   bool p2p = false;
   // small (uint32 words): [0 .. W) send counts, [W .. W + W*W) count matrix [src][dst], then: records owned, local bounds,
@@ -95,6 +97,8 @@ void comm_release(strgpu_ctx *ctx) {
   if (!ctx || !ctx->comm) return;
   Comm *c = ctx->comm;
   cudaDeviceSynchronize();
+  if (c->graph.exec) cudaGraphExecDestroy(c->graph.exec);
+  if (c->h_tab) cudaFreeHost(c->h_tab);
   for (int r = 0; r < c->world; r++)
     if (c->p2p && r != c->rank && c->peer_recv[r]) cudaIpcCloseMemHandle(c->peer_recv[r]);
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
@@ -381,16 +385,12 @@ int setup_recv(strgpu_ctx *ctx, Comm *c, size_t bytes, cudaStream_t st) {
 }  // namespace
 }  // namespace strgpu_internal
 
-int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, uint32_t max_n, uint32_t pair_capacity,
-                                  const strgpu_cluster_params *params, void *d_out, uint32_t cap, void *d_n_out, void *cuda_stream) {
-  if (!ctx || !params || !d_n_out || (n && !d_treads) || (cap && !d_out)) return fail(ctx, STRGPU_ERR_INVALID, "cluster_sharded: null argument");
-  if (!ctx->comm) return fail(ctx, STRGPU_ERR_INVALID, "cluster_sharded: strgpu_comm_init has not been called");
-  if (n > max_n) return fail(ctx, STRGPU_ERR_INVALID, "cluster_sharded: n %u > max_n %u", n, max_n);
+static int sharded_enqueue(strgpu_ctx *ctx, const void *d_treads, uint32_t n, uint32_t max_n, uint32_t pair_capacity,
+                           const strgpu_cluster_params *params, void *d_out, uint32_t cap, void *d_n_out, cudaStream_t st,
+                           uint64_t *launches_out, bool capturing) {
   Comm *c = ctx->comm;
   NcclApi *api = nccl_api();
   const uint32_t W = (uint32_t)c->world, me = (uint32_t)c->rank;
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  CU(ctx, cudaSetDevice(ctx->device));
   // slot per (source, destination) pair: a hash partition gives every owner ~ n / W of a shard; 25 % + 1024 of slack
   uint64_t pair_cap64 = pair_capacity ? pair_capacity : (uint64_t)max_n / W + (uint64_t)max_n / (4 * W) + 1024;
   if (pair_cap64 > max_n) pair_cap64 = max_n;
@@ -402,7 +402,11 @@ int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_
   const uint32_t rank_cap = std::max<uint32_t>(1u, cap / W);   // bounds a rank may contribute to the gather
   const uint32_t n_tiles = std::max<uint32_t>(1u, (n + kPartTile - 1) / kPartTile);
   int rc;
-  if ((size_t)own_max * sizeof(strgpu_tread) > c->recv.cap && (rc = setup_recv(ctx, c, (size_t)own_max * sizeof(strgpu_tread), st))) return rc;
+  if ((size_t)own_max * sizeof(strgpu_tread) > c->recv.cap) {
+    if (capturing) return fail(ctx, STRGPU_ERR_CUDA, "cluster_sharded: buffer growth during graph capture");
+    if ((rc = setup_recv(ctx, c, (size_t)own_max * sizeof(strgpu_tread), st))) return rc;
+    ctx->cluster_ws.gen++;   // captured graphs hold the old receive buffers
+  }
   if (!c->p2p && (rc = ensure(ctx, c->send, (size_t)own_max * sizeof(strgpu_tread)))) return rc;
   if ((rc = ensure(ctx, c->own, (size_t)own_max * sizeof(strgpu_tread) + 64))) return rc;
   if ((rc = ensure(ctx, c->counts, (size_t)W * n_tiles * 4 + 64))) return rc;
@@ -417,7 +421,8 @@ int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_
   strgpu_tread *send = (strgpu_tread *)c->send.p, *recv = (strgpu_tread *)c->recv.p, *own = (strgpu_tread *)c->own.p;
   uint64_t launches = 0;
   // STRGPU_COMM_TIMING=1 (profiling only): per-phase device times on stderr; the call then synchronises
-  static const bool timing = getenv("STRGPU_COMM_TIMING") != nullptr;
+  static const bool timing_env = getenv("STRGPU_COMM_TIMING") != nullptr;
+  const bool timing = timing_env && !capturing;
   cudaEvent_t ev[6] = {nullptr};
   auto mark = [&](int i) {
     if (!timing) return;
@@ -437,7 +442,14 @@ int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_
     // two alternating halves so that a table still in use by the previous call's kernel is never overwritten
     c->tab_flip ^= 1;
     strgpu_tread **d_tab = (strgpu_tread **)c->peer_tab.p + (size_t)c->tab_flip * kMaxWorld;
-    CU(ctx, cudaMemcpyAsync(d_tab, tab, W * sizeof(void *), cudaMemcpyHostToDevice, st));
+    if (capturing) {
+      // a captured copy re-reads its source at every replay: a pinned table that lives as long as the graph
+      if (!c->h_tab && cudaMallocHost(&c->h_tab, kMaxWorld * sizeof(void *)) != cudaSuccess) return fail(ctx, STRGPU_ERR_CUDA, "cudaMallocHost");
+      std::memcpy(c->h_tab, tab, W * sizeof(void *));
+      CU(ctx, cudaMemcpyAsync(d_tab, c->h_tab, W * sizeof(void *), cudaMemcpyHostToDevice, st));
+    } else {
+      CU(ctx, cudaMemcpyAsync(d_tab, tab, W * sizeof(void *), cudaMemcpyHostToDevice, st));
+    }
     uint32_t *counts = (uint32_t *)c->counts.p;
     part_histogram<<<n_tiles, kPartWarps * 32, 0, st>>>((const strgpu_tread *)d_treads, n, W, n_tiles, counts);
     CU(ctx, strgpu::scan_u32(ctx->cluster_ws, counts, counts, W * n_tiles, nullptr, st, &launches));
@@ -494,9 +506,40 @@ int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_
             me, t[0], t[1], t[2], t[3], t[4], pair_cap, own_max, rank_cap, c->p2p ? "peer-to-peer stores" : "NCCL send/recv");
     for (auto &e : ev) cudaEventDestroy(e);
   }
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->launches += launches;
+  *launches_out += launches;
   return STRGPU_OK;
+}
+
+int strgpu_cluster_sharded_device(strgpu_ctx *ctx, const void *d_treads, uint32_t n, uint32_t max_n, uint32_t pair_capacity,
+                                  const strgpu_cluster_params *params, void *d_out, uint32_t cap, void *d_n_out, void *cuda_stream) {
+  if (!ctx || !params || !d_n_out || (n && !d_treads) || (cap && !d_out)) return fail(ctx, STRGPU_ERR_INVALID, "cluster_sharded: null argument");
+  if (!ctx->comm) return fail(ctx, STRGPU_ERR_INVALID, "cluster_sharded: strgpu_comm_init has not been called");
+  if (n > max_n) return fail(ctx, STRGPU_ERR_INVALID, "cluster_sharded: n %u > max_n %u", n, max_n);
+  CU(ctx, cudaSetDevice(ctx->device));
+  const strgpu_cluster_params p = *params;
+  // Repeated calls with unchanged arguments are replayed as one CUDA graph (kernels, the small table upload and the NCCL
+  // all-gathers; see GraphSlot).  Every rank of a job that repeats its call sees the same direct / capture / replay sequence.
+  // STRGPU_SHARDED_GRAPH=0 keeps the sharded path on direct launches.
+  static const bool graph_ok = !(getenv("STRGPU_SHARDED_GRAPH") && atoi(getenv("STRGPU_SHARDED_GRAPH")) == 0) && !getenv("STRGPU_COMM_TIMING");
+  uint64_t key = hash_bytes(&d_treads, sizeof(d_treads));
+  key = hash_bytes(&n, sizeof(n), key);
+  key = hash_bytes(&max_n, sizeof(max_n), key);
+  key = hash_bytes(&pair_capacity, sizeof(pair_capacity), key);
+  key = hash_bytes(&p, sizeof(p), key);
+  key = hash_bytes(&d_out, sizeof(d_out), key);
+  key = hash_bytes(&cap, sizeof(cap), key);
+  key = hash_bytes(&d_n_out, sizeof(d_n_out), key);
+  cudaStream_t user = (cudaStream_t)cuda_stream;
+  if (!graph_ok) {
+    uint64_t l = 0;
+    const int rc = sharded_enqueue(ctx, d_treads, n, max_n, pair_capacity, &p, d_out, cap, d_n_out, user, &l, false);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->launches += l;
+    return rc;
+  }
+  return run_graphed(ctx, ctx->comm->graph, key, user, [&](cudaStream_t st, uint64_t *launches, bool capturing) -> int {
+    return sharded_enqueue(ctx, d_treads, n, max_n, pair_capacity, &p, d_out, cap, d_n_out, st, launches, capturing);
+  });
 }
 
 int strgpu_comm_status(strgpu_ctx *ctx, void *cuda_stream) {

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "cluster_kernels.cuh"
@@ -30,6 +31,17 @@ struct Slot {
 
 struct Comm;  // comm.cu: the NCCL communicator of a sharded job and its exchange buffers
 
+// The cluster path is ~100 short kernels; a caller that repeats a call with the same arguments (a pipeline clustering batch
+// after batch into the same buffers) gets it replayed as ONE CUDA graph launch: first call direct (it sizes the workspace),
+// second call captured, from then on replayed until an argument or a workspace buffer changes.  STRGPU_NO_GRAPH=1 disables it.
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  uint64_t key = 0, ws_gen = 0;          // what the captured graph was built for
+  uint64_t sized_key = 0, sized_gen = 0; // arguments of the last direct run
+  uint64_t launches = 0;
+  bool broken = false;                   // capture failed once: stay on direct launches
+};
+
 }  // namespace strgpu_internal
 
 struct strgpu_ctx {
@@ -54,6 +66,7 @@ struct strgpu_ctx {
   std::mutex mu;
   std::mutex err_mu;
   strgpu_internal::Comm *comm = nullptr;
+  strgpu_internal::GraphSlot cluster_graph;
 };
 
 namespace strgpu_internal {
@@ -87,5 +100,69 @@ inline int ensure(strgpu_ctx *ctx, DevBuf &b, size_t bytes) {
 }
 
 void comm_release(strgpu_ctx *ctx);   // comm.cu
+
+inline uint64_t hash_bytes(const void *p, size_t n, uint64_t h = 0xcbf29ce484222325ull) {
+  const unsigned char *b = static_cast<const unsigned char *>(p);
+  for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 0x100000001b3ull;
+  return h ? h : 1;
+}
+
+// enqueue(stream, &launches, capturing) -> strgpu_status enqueues the work on a stream; see GraphSlot
+template <typename F>
+int run_graphed(strgpu_ctx *ctx, GraphSlot &g, uint64_t key, cudaStream_t user, F enqueue) {
+  static const bool no_graph = getenv("STRGPU_NO_GRAPH") != nullptr;
+  uint64_t l = 0;
+  if (no_graph || g.broken) {
+    const int rc = enqueue(user, &l, false);
+    ctx->launches += l;
+    return rc;
+  }
+  if (g.exec && g.key == key && g.ws_gen == ctx->cluster_ws.gen) {
+    CU(ctx, cudaGraphLaunch(g.exec, user));
+    ctx->launches += g.launches;
+    return STRGPU_OK;
+  }
+  if (g.exec) {   // stale: other arguments, or a workspace buffer moved
+    CU(ctx, cudaStreamSynchronize(user));
+    cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+  if (g.sized_key != key || g.sized_gen != ctx->cluster_ws.gen) {   // first call with these arguments: direct
+    const int rc = enqueue(user, &l, false);
+    ctx->launches += l;
+    g.sized_key = key;
+    g.sized_gen = ctx->cluster_ws.gen;
+    return rc;
+  }
+  // second call: capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
+  cudaStream_t cs = ctx->cluster_stream;
+  if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    g.broken = true;
+    const int rc = enqueue(user, &l, false);
+    ctx->launches += l;
+    return rc;
+  }
+  const int rc = enqueue(cs, &l, true);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  if (rc != STRGPU_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g.exec = nullptr;
+    g.broken = true;
+    uint64_t l2 = 0;
+    const int rc2 = enqueue(user, &l2, false);
+    ctx->launches += l2;
+    return rc2;
+  }
+  cudaGraphDestroy(graph);
+  g.key = key;
+  g.ws_gen = ctx->cluster_ws.gen;
+  g.launches = l;
+  CU(ctx, cudaGraphLaunch(g.exec, user));
+  ctx->launches += l;
+  return STRGPU_OK;
+}
 
 }  // namespace strgpu_internal

@@ -181,3 +181,49 @@ def test_sharded_entry_points_with_a_one_rank_communicator(gpu):
         assert e.value.status == -7
     finally:
         g.close()
+
+
+def test_repeated_device_calls_replay_a_cuda_graph_with_the_same_result(gpu):
+    # strgpu_cluster_device with unchanged arguments: first call direct, second captured into a CUDA graph, then replayed;
+    # new input in the same buffers must give the new result, changed arguments must leave the graph
+    import torch
+
+    dev = torch.device("cuda", 0)
+    g = sb.StrGpu(0)
+    try:
+        kw = dict(window=480, min_support=4, max_clip_dist=190)
+        p = g.cluster_params(**kw)
+        a = synth.make_treads(900, seed=5, noise_reads=20_000, unplaced=200)
+        b = synth.make_treads(900, seed=6, noise_reads=20_000, unplaced=200)[: len(a)]
+        assert len(b) == len(a)
+        d_t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev)
+        cap = len(a)
+        d_out = torch.zeros(cap * 48, dtype=torch.uint8, device=dev)
+        d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = torch.cuda.Stream(device=dev)
+
+        def run(treads):
+            d_t.copy_(torch.from_numpy(treads.view(np.uint8).reshape(-1).copy()))
+            torch.cuda.synchronize()
+            g.cluster_device(d_t.data_ptr(), len(treads), p, d_out.data_ptr(), cap, d_n.data_ptr(), st.cuda_stream)
+            st.synchronize()
+            return d_out[: int(d_n.item()) * 48].cpu().numpy().view(sb.BOUNDS_DTYPE).copy()
+
+        exp_a, _ = gpu.cluster(a, **kw)
+        exp_b, _ = gpu.cluster(b, **kw)
+        for rep, (treads, exp) in enumerate([(a, exp_a), (a, exp_a), (a, exp_a), (b, exp_b), (a, exp_a), (b, exp_b)]):
+            got = run(treads)
+            got = got[got["tid"] >= 0]
+            assert len(got) == len(exp) > 50, rep
+            for f in FIELDS:
+                assert np.array_equal(got[f], exp[f]), (rep, f)
+        # other arguments (min_support): a different result, and back
+        p2 = g.cluster_params(window=480, min_support=9, max_clip_dist=190)
+        g.cluster_device(d_t.data_ptr(), len(b), p2, d_out.data_ptr(), cap, d_n.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        exp2, _ = gpu.cluster(b, window=480, min_support=9, max_clip_dist=190)
+        got2 = d_out[: int(d_n.item()) * 48].cpu().numpy().view(sb.BOUNDS_DTYPE)
+        got2 = got2[got2["tid"] >= 0]
+        assert len(got2) == len(exp2) and all(np.array_equal(got2[f], exp2[f]) for f in FIELDS)
+    finally:
+        g.close()
