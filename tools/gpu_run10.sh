@@ -5,6 +5,4 @@ import json; d=json.load(open('gpurun_out/bench_n8.json'))
 for k in ('value','ms_per_step','cluster','strong','joint','parity_sample'): print(k, d.get(k))
 print('e2e', d['e2e']['value'], d['e2e'].get('h2d_gb_per_s_per_gpu'), 'frac', d['roofline']['frac'])
 "
-grep -i "nvls\|error" gpurun_out/bench_n8.err | head -5
-nvidia-smi topo -m 2>/dev/null | head -14
-lscpu | grep -E "Model name|Socket|NUMA|^CPU\(s\)" | head
+tail -2 gpurun_out/bench_n8.err | cut -c1-300
