@@ -579,7 +579,7 @@ def _simulate_chunk(job):
     return bamio.simulate_alignments(seed, n_pairs, targets, loci, str_pair_frac=0.03, unmapped_pairs=n_pairs // 100, name_prefix=f"c{seed}_")
 
 
-def cli_leg(local: int, n_pairs: int = 320_000):
+def cli_leg(local: int, n_pairs: int = 500_000):
     """What a user runs: `strling extract` (BGZF inflate + BAM decode + staging on the host cores, scan on the GPU, mate pairing
     replay, .bin) on a synthetic coordinate-sorted BAM, best of three runs, with the binary's own stage report."""
     import re
