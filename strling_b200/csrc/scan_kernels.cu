@@ -808,8 +808,8 @@ __device__ __forceinline__ void prefilter_masks(int L, uint32_t (&V)[5]) {
 // the other seven follow from the margins of the 4 x 4 table:
 //   f[3]    = (L - 1) - f[0] - f[1] - f[2]                        c[3][b] = f[b] - c[0][b] - c[1][b] - c[2][b]     (exact)
 //   row sum n[a] = occurrences of a at positions 0 .. L - 2 = f[a] + [base 0 == a] - [base L-1 == a], so with
-//   n+[a] = f[a] + [base 0 == a] >= n[a] >= n+[a] - 1:            c[a][3] <= n+[a] - (c[a][0] + c[a][1] + c[a][2])
-//                                                                 c[3][3] <= f[3] - sum_a (n+[a] - 1 - (c[a][0] + c[a][1] + c[a][2]))
+//   n+[a] = f[a] + [base 0 == a] = n[a] + [base L-1 == a]:        c[a][3] <= d[a] = n+[a] - (c[a][0] + c[a][1] + c[a][2])   (over by [base L-1 == a])
+//                                                                 c[3][3] <= f[3] - (d[0] + d[1] + d[2]) + 1             (over by 1 - [base L-1 < 3])
 // -- the last four are over-estimates by at most one, which keeps the filter sound (a segment it finishes really has the
 // empty result; at worst a borderline segment more reaches the ladder kernels, which are exact).  12 popcount streams
 // instead of 16 and 45 + 15 + 3 mask LOP3 instead of 60 + 20: this kernel is bound by the ALU / popcount pipes.
@@ -880,11 +880,11 @@ __device__ __forceinline__ void prefilter_top2(const uint32_t (&w)[10], const ui
     // [base 0 == a]: position 0 is bit 31 of plane 0
     const uint32_t e0 = a == 0 ? (V[0] & ~Dh[0] & ~Dl[0]) : (a == 1 ? (V[0] & ~Dh[0] & Dl[0]) : (V[0] & Dh[0] & ~Dl[0]));
     const int nplus = (int)__umulhi(e0, 2u) * one + f[a];
-    const int d = row * (-one) + nplus;     // >= c[a][3] >= d - 1
+    const int d = row * (-one) + nplus;     // = c[a][3] + [base L-1 == a]
     c[a][3] = d;
-    rest = (d * (-one) + rest) * one + one;
+    rest = d * (-one) + rest;
   }
-  c[3][3] = rest;
+  c[3][3] = rest * one + one;   // = c[3][3] + 1 - [base L-1 is one of the three counted bases] <= c[3][3] + 1
   // top two of the sixteen: pack cell i with cell i + 8 (all values are in 0 .. 161), select on both halves at once
   const int k16 = one << 16;
   uint32_t P[8];

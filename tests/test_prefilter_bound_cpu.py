@@ -55,3 +55,59 @@ def test_bound_holds_on_adversarial_repeats(unit, copies, pad, phase, p, noise):
     unit_found, count = orc.get_repeat(s, p)
     if count > 0:
         assert survives(s, p), (s, p, unit_found, count)
+
+
+# ---- round 2: the kernel counts only nine of the sixteen 2-mer cells and three column sums and derives the rest from the margins
+# of the 4 x 4 table (csrc/scan_kernels.cu, prefilter_top2).  A numpy model of exactly those formulas: the derived cells are the
+# true counts where the kernel claims exactness and over-estimate by at most one elsewhere, so the filter stays sound.
+_CODE = {"C": 0, "A": 1, "T": 2, "G": 3}
+
+
+def derived_cells(s: str):
+    L = len(s)
+    b = [_CODE[ch] for ch in s]
+    true = np.zeros((4, 4), dtype=int)
+    for i in range(L - 1):
+        true[b[i], b[i + 1]] += 1
+    c = np.zeros((4, 4), dtype=int)
+    c[:3, :3] = true[:3, :3]                                   # the nine counted cells
+    f = [sum(1 for i in range(L - 1) if b[i + 1] == x) for x in range(3)]   # counted column sums: successor is x
+    f.append(max(L - 1, 0) - sum(f))
+    rest = f[3]
+    for x in range(3):
+        c[3, x] = f[x] - c[:3, x].sum()                        # exact
+    for a in range(3):
+        row = c[a, :3].sum()
+        nplus = f[a] + (1 if L >= 2 and b[0] == a else 0)      # >= occurrences of a at positions 0 .. L-2
+        d = nplus - row                                        # = true count + [last base == a]
+        c[a, 3] = d
+        rest = rest - d
+    c[3, 3] = rest + 1                                         # = true count + 1 - [last base is one of the three counted]
+    return true, c
+
+
+@settings(max_examples=600, deadline=None)
+@given(s=st.text(alphabet="ACGT", min_size=0, max_size=160))
+def test_derived_cells_bound_the_true_counts(s):
+    true, c = derived_cells(s)
+    assert (c >= true).all() and (c <= true + 1).all(), (s, true, c)
+    assert (c[:3, :3] == true[:3, :3]).all() and (c[3, :3] == true[3, :3]).all()    # exact where the kernel says so
+
+
+def test_filter_with_derived_cells_keeps_every_segment_the_oracle_gives_a_unit():
+    reads, cls, lclip, rclip = synth.make_reads(30_000, seed=5, mix=(0.4, 0.1, 0.25, 0.25), noise=0.03)
+    segs, _ = synth.segments_for(reads, lclip, rclip, 160)
+    flat, off, lens = synth.segment_ascii(reads, segs, 160)
+    P = np.asarray([0.8, 0.73, 0.6])
+    units, counts = orc.get_repeat_batch(flat, off, lens, P[segs["pclass"]])
+    extra = 0
+    for i in range(len(segs)):
+        s = bytes(flat[int(off[i]): int(off[i]) + int(lens[i])]).decode()
+        p = float(P[segs["pclass"][i]])
+        _, c = derived_cells(s)
+        v = np.sort(c.reshape(-1))[::-1]
+        keep = any(v[0] + (k - 2) * v[1] >= (int(float(len(s)) * p / float(k)) + 1) * (k - 1) for k in range(2, 7))
+        if counts[i] > 0:
+            assert keep, (s, units[i], counts[i])
+        extra += keep and not survives(s, p)
+    assert extra < 0.002 * len(segs)     # the over-estimates let almost nothing more through than the exact counts do
