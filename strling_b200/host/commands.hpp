@@ -15,6 +15,10 @@ struct ExtractArgs {
   int device = 0;
   int threads = 0;
   uint32_t batch_reads = 1u << 18;
+  // `strling debug extract` only (CPU-side checks of the staging and replay logic; never set by `strling extract`):
+  // dump: write every staged segment ("pclass<TAB>bases", submission order) instead of scanning it, no .bin is written;
+  // results: read the scan results (8-byte strgpu_repeat records in that same order) from a file instead of the GPU
+  std::string debug_dump_segments, debug_scan_results;
 };
 int extract_run(const ExtractArgs &a);
 std::array<uint32_t, 4096> fragment_length_distribution(const std::string &bam, int threads);

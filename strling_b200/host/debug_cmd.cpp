@@ -45,6 +45,25 @@ int debug_main(int argc, char **argv) {
   if (argc < 1) return 1;
   const std::string what = argv[0];
   if (what == "genotype") return debug_genotype(argc - 1, argv + 1);
+  if (what == "extract" && argc >= 5) {
+    // strling debug extract {dump <segments.tsv> | replay <results.bin>} <bam> <bin> [p] [min_mapq] [batch_reads] [genome-repeats.bed]
+    // The staging and the order-dependent replay of `strling extract` WITHOUT the scan: `dump` writes every staged segment, `replay`
+    // takes the scan results from a file (the CPU tests compute them with the oracle).  It is a test hook, not a CPU path: the
+    // results never come from this program.
+    ExtractArgs e;
+    const std::string mode = argv[1];
+    if (mode == "dump") e.debug_dump_segments = argv[2];
+    else if (mode == "replay") e.debug_scan_results = argv[2];
+    else return 1;
+    e.bam = argv[3];
+    e.bin = argv[4];
+    if (argc >= 6) e.proportion_repeat = std::atof(argv[5]);
+    if (argc >= 7) e.min_mapq = std::atoi(argv[6]);
+    if (argc >= 8) e.batch_reads = (uint32_t)std::atol(argv[7]);
+    if (argc >= 9) e.genome_repeats = argv[8];
+    e.threads = 2;
+    return extract_run(e);
+  }
   if (what == "bam" && argc >= 2) {
     BamReader rd(argv[1]);
     std::printf("@targets %zu\n", rd.targets().size());
@@ -130,7 +149,7 @@ int debug_main(int argc, char **argv) {
     }
     return 0;
   }
-  std::fprintf(stderr, "strling debug {bam <bam> | fragdist <bam> | bin <bin> [out.bin] | logic}\n");
+  std::fprintf(stderr, "strling debug {bam <bam> | fragdist <bam> | bin <bin> [out.bin] | logic | extract {dump|replay} <file> <bam> <bin> ...}\n");
   return 1;
 }
 

@@ -117,6 +117,9 @@ struct Extractor {
   double t_wait = 0, t_replay = 0, t_submit = 0, t_decode = 0, t_stage = 0;  // host stage timers (seconds)
   bool verbose = false;
   int threads = 1;
+  // `strling debug extract`: the scan is replaced by a segment dump / by results read from a file (commands.hpp); no GPU then
+  FILE *dump = nullptr, *results = nullptr;
+  bool debug_mode() const { return dump != nullptr || results != nullptr; }
 
   void gpu_check(int rc, const char *what) {
     if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + what + ": " + strgpu_last_error(gpu));
@@ -126,17 +129,26 @@ struct Extractor {
     b.cap_bases = cap_bases;
     b.cap_seg = cap_seg;
     void *p1, *p2, *p3, *p4, *p5;
-    gpu_check(strgpu_host_alloc(&p1, strgpu_seq2_bytes(cap_bases)), "host_alloc");
-    gpu_check(strgpu_host_alloc(&p2, strgpu_nmask_bytes(cap_bases)), "host_alloc");
-    gpu_check(strgpu_host_alloc(&p3, (size_t)cap_seg * sizeof(strgpu_segment)), "host_alloc");
-    gpu_check(strgpu_host_alloc(&p4, (size_t)cap_seg * sizeof(strgpu_repeat)), "host_alloc");
-    gpu_check(strgpu_host_alloc(&p5, strgpu_nmask_bytes(cap_bases)), "host_alloc");
+    auto get = [&](void **p, size_t bytes) {
+      if (debug_mode()) {   // no CUDA runtime on the machines the CPU-side checks run on: plain memory
+        *p = std::malloc(bytes ? bytes : 1);
+        if (!*p) throw std::runtime_error("[strling] out of memory");
+      } else {
+        gpu_check(strgpu_host_alloc(p, bytes), "host_alloc");
+      }
+    };
+    get(&p1, strgpu_seq2_bytes(cap_bases));
+    get(&p2, strgpu_nmask_bytes(cap_bases));
+    get(&p3, (size_t)cap_seg * sizeof(strgpu_segment));
+    get(&p4, (size_t)cap_seg * sizeof(strgpu_repeat));
+    get(&p5, strgpu_nmask_bytes(cap_bases));
     b.seq2 = (uint8_t *)p1; b.nmask = (uint32_t *)p2; b.segs = (strgpu_segment *)p3; b.out = (strgpu_repeat *)p4;
     b.xmask = (uint32_t *)p5;
     std::memset(b.nmask, 0, strgpu_nmask_bytes(cap_bases));
     std::memset(b.xmask, 0, strgpu_nmask_bytes(cap_bases));
   }
   void free_batch(Batch &b) {
+    if (debug_mode()) { std::free(b.seq2); std::free(b.nmask); std::free(b.xmask); std::free(b.segs); std::free(b.out); return; }
     strgpu_host_free(b.seq2); strgpu_host_free(b.nmask); strgpu_host_free(b.xmask); strgpu_host_free(b.segs); strgpu_host_free(b.out);
   }
   void grow_batch(Batch &b, uint64_t need_bases, uint32_t need_seg) {
@@ -263,11 +275,37 @@ struct Extractor {
 
   void submit(Batch &b) {
     n_scanned += b.n_seg;
+    if (dump) {   // one line per staged segment, in the order the results are consumed in
+      std::string line;
+      for (uint32_t i = 0; i < b.n_seg; i++) {
+        const strgpu_segment &sg = b.segs[i];
+        line.assign(std::to_string((int)sg.pclass));
+        line.push_back('\t');
+        for (uint32_t k = 0; k < sg.len; k++) {
+          const uint64_t base = (uint64_t)sg.base_off + k;
+          char c = "CATG"[(b.seq2[base >> 2] >> (6 - 2 * (base & 3))) & 3];
+          if (b.any_n && ((b.nmask[base >> 5] >> (base & 31)) & 1u)) c = ((b.xmask[base >> 5] >> (base & 31)) & 1u) ? 'R' : 'N';
+          line.push_back(c);
+        }
+        line.push_back('\n');
+        std::fputs(line.c_str(), dump);
+      }
+      std::memset(b.out, 0, (size_t)b.n_seg * sizeof(strgpu_repeat));
+      return;
+    }
+    if (results) {
+      if (b.n_seg && std::fread(b.out, sizeof(strgpu_repeat), b.n_seg, results) != b.n_seg)
+        throw std::runtime_error("[strling] debug extract: the scan-results file is shorter than the staged segments");
+      return;
+    }
     gpu_check(strgpu_scan_submit(gpu, b.seq2, b.n_bases, b.any_n ? b.nmask : nullptr, b.any_n ? b.xmask : nullptr, b.segs, b.n_seg,
                                  b.max_len, b.out, &b.ticket),
               "scan_submit");
   }
-  void wait(Batch &b) { gpu_check(strgpu_scan_wait(gpu, b.ticket), "scan_wait"); }
+  void wait(Batch &b) {
+    if (debug_mode()) return;
+    gpu_check(strgpu_scan_wait(gpu, b.ticket), "scan_wait");
+  }
   void recycle(Batch &b) {
     if (b.any_n) {
       std::memset(b.nmask, 0, (size_t)((b.n_bases + 31) / 32) * 4 + 8);
@@ -437,6 +475,8 @@ int extract_run(const ExtractArgs &a) {
     std::fprintf(stderr, "[strling] using existing file %s for genome repeats\n", a.genome_repeats.c_str());
     genome_str = read_bed(a.genome_repeats);
   } else if (!a.fasta.empty()) {
+    if (!a.debug_dump_segments.empty() || !a.debug_scan_results.empty())
+      throw std::runtime_error("[strling] debug extract: building the genome-repeats index needs the GPU; pass an existing -g file");
     const std::vector<std::string> lines = genome_repeat_lines(a.fasta, a.proportion_repeat, a.device);
     std::fprintf(stderr, "[strling] found %zu STR-like regions in the genome\n", lines.size());
     std::string path = a.genome_repeats;
@@ -461,10 +501,18 @@ int extract_run(const ExtractArgs &a) {
     if (it != genome_str.end()) ex.genome_str_by_tid[t] = &it->second;
   }
 
-  int rc = strgpu_create(&ex.gpu, a.device);
-  if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + strgpu_error_string(rc));
-  const double classes[3] = {a.proportion_repeat, a.proportion_repeat - 0.07, std::min(a.proportion_repeat, 0.6)};
-  ex.gpu_check(strgpu_set_proportions(ex.gpu, classes, 3), "set_proportions");
+  if (!a.debug_dump_segments.empty()) {
+    ex.dump = std::fopen(a.debug_dump_segments.c_str(), "w");
+    if (!ex.dump) throw std::runtime_error("[strling] debug extract: cannot write " + a.debug_dump_segments);
+  } else if (!a.debug_scan_results.empty()) {
+    ex.results = std::fopen(a.debug_scan_results.c_str(), "rb");
+    if (!ex.results) throw std::runtime_error("[strling] debug extract: cannot read " + a.debug_scan_results);
+  } else {
+    int rc = strgpu_create(&ex.gpu, a.device);
+    if (rc != STRGPU_OK) throw std::runtime_error(std::string("[strling] gpu: ") + strgpu_error_string(rc));
+    const double classes[3] = {a.proportion_repeat, a.proportion_repeat - 0.07, std::min(a.proportion_repeat, 0.6)};
+    ex.gpu_check(strgpu_set_proportions(ex.gpu, classes, 3), "set_proportions");
+  }
 
   ex.threads = a.threads > 0 ? a.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   const uint64_t first_voffset = rd.tell();
@@ -656,6 +704,12 @@ int extract_run(const ExtractArgs &a) {
   if (!consumer_error.empty()) throw std::runtime_error(consumer_error);
   const double dt = std::chrono::duration<double>(clk::now() - t0).count();
 
+  if (ex.dump) {   // segments only: the replay ran on empty results, there is nothing to write
+    std::fclose(ex.dump);
+    for (auto &b : batches) ex.free_batch(b);
+    return 0;
+  }
+  if (ex.results) std::fclose(ex.results);
   std::fprintf(stderr, "[strling] writing binary file:%s\n", a.bin.c_str());
   BinFile bf;
   bf.proportion_repeat = (float)a.proportion_repeat;
@@ -670,10 +724,10 @@ int extract_run(const ExtractArgs &a) {
     std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"threads\": %d, \"inflate_s\": %.3f, \"stage_s\": %.3f, \"submit_s\": %.3f, \"gpu_wait_s\": %.3f, \"replay_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
                  (unsigned long long)ex.n_reads, (unsigned long long)ex.n_scanned, bf.reads.size(), dt, ex.threads, ex.t_decode, ex.t_stage, ex.t_submit,
                  ex.t_wait, ex.t_replay, ex.n_reads / std::max(dt, 1e-9), total,
-                 (unsigned long long)strgpu_launch_count(ex.gpu));
+                 (unsigned long long)(ex.gpu ? strgpu_launch_count(ex.gpu) : 0));
   }
   for (auto &b : batches) ex.free_batch(b);
-  strgpu_destroy(ex.gpu);
+  if (ex.gpu) strgpu_destroy(ex.gpu);
   return 0;
 }
 

@@ -236,3 +236,40 @@ def test_bam_decode_against_an_independent_encoder(cli, tmp_path):
         # hts-nim `stop` = htslib bam_endpos: pos + reference span of the CIGAR; pos + 1 for a read flagged unmapped or without
         # a reference-consuming CIGAR
         assert int(f[10]) == (pos + span if span and not flag & 4 else pos + 1), (f, e)
+
+
+@pytest.mark.parametrize("p,q,use_bed,batch", [(0.8, 40, False, 262144), (0.8, 40, True, 1500), (0.7, 20, True, 700), (0.9, 0, False, 333)])
+def test_extract_staging_and_replay_without_the_scan(cli, tmp_path, p, q, use_bed, batch):
+    """The host half of `strling extract` on the CPU: BAM decode -> which segments a record contributes (genome-STR filter,
+    soft clips under both proportion classes, extract.nim:20-40,93-114) -> replay of Cache.add in file order (extract.nim:192-248)
+    -> .bin.  `strling debug extract dump` writes the staged segments, the ORACLE scans them here in the test, and
+    `strling debug extract replay` consumes those results: the .bin must be the oracle pipeline's, byte for byte, also with
+    batches so small that mates land in different batches."""
+    targets = [("chr1", 400_000), ("chr2", 300_000)]
+    loci = [(0, 100_000, 100_150, "CAG"), (0, 250_000, 250_090, "AAAG"), (1, 120_000, 120_060, "ATTCT"), (1, 200_000, 200_040, "A")]
+    recs = bamio.simulate_alignments(31, 4000, targets, loci, unmapped_pairs=60, n_frac=0.03)
+    hdr = bamio.sam_header(targets)
+    bam, segs_path, res_path, out = (str(tmp_path / n) for n in ("x.bam", "segs.tsv", "res.bin", "x.bin"))
+    bamio.write_bam(bam, hdr, targets, recs)
+    extra, genome_str = [], None
+    if use_bed:
+        bed = str(tmp_path / "ref.str")
+        with open(bed, "w") as fh:
+            for tid, s, e, u in loci:
+                fh.write(f"{targets[tid][0]}\t{s}\t{e}\t{u}\n")
+        extra = [bed]
+        genome_str = eo.read_bed(bed)
+    run(cli, "debug", "extract", "dump", segs_path, bam, out, repr(p), str(q), str(batch), *extra)
+    classes = [p, p - 0.07, min(p, 0.6)]
+    lines = open(segs_path).read().splitlines()
+    assert len(lines) > 1000
+    res = np.zeros(len(lines), dtype=[("unit", "S6"), ("repeat_count", "<u2")])
+    for i, l in enumerate(lines):
+        cls, _, seq = l.partition("\t")
+        unit, count = orc.get_repeat(seq, classes[int(cls)])
+        res["unit"][i], res["repeat_count"][i] = unit, count
+    res.tofile(res_path)
+    run(cli, "debug", "extract", "replay", res_path, bam, out, repr(p), str(q), str(batch), *extra)
+    exp, cache, _ = eo.extract(recs, targets, hdr, p, q, genome_str)
+    assert len(cache) > 500
+    assert open(out, "rb").read() == exp
