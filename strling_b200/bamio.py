@@ -59,7 +59,8 @@ def encode_record(a: Aln) -> bytes:
     if l_seq & 1:
         nib.append(0)
     seq = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
-    qual = b"\xff" * l_seq
+    qual = a.extra.get("qual", b"\xff" * l_seq)   # tests plant byte patterns here
+    assert len(qual) == l_seq
     body = struct.pack("<iiBBHHHiiii", a.tid, a.pos, len(name), a.mapq, binv, len(a.cigar), a.flag, l_seq, a.mate_tid,
                        a.mate_pos, a.isize) + name + cig + seq + qual
     return struct.pack("<i", len(body)) + body

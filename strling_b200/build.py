@@ -71,7 +71,7 @@ def build_cli(force: bool = False) -> str:
     if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
         return CLI
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
-    cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", *srcs, "-I", os.path.join(ROOT, "include"), "-I", HOST,
+    cmd = [CXX, "-O3", "-std=c++17", "-Wall", "-Wextra", "-pthread", *srcs, "-I", os.path.join(ROOT, "include"), "-I", HOST,
            "-L", HERE, "-lstrgpu", "-lz", "-Wl,-rpath,$ORIGIN/..", "-o", CLI]
     subprocess.check_call(cmd)
     return CLI

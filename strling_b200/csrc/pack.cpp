@@ -4,6 +4,9 @@
 // ambiguity code, '=') is flagged in the second plane too, because the reference's N > 20 gate counts 'N' only (utils.nim:238).
 #include <cstdint>
 #include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "strgpu.h"
 
@@ -53,6 +56,30 @@ inline void flag(uint32_t *nmask, uint32_t *xmask, uint64_t b, bool literal_n) {
   if (xmask && !literal_n) set_n(xmask, b);
 }
 
+#if defined(__x86_64__)
+// Sixteen bases (eight BAM bytes) per step: nibble -> code is two OR-shifts (bit 0 = A | G, bit 1 = G | T with A=1 C=2 G=4
+// T=8), the 2-bit codes are gathered with PEXT and the two nibbles of every output byte swapped (BAM puts the first base of
+// a byte in the high nibble, PEXT gathers from the low end).  Stops at the first group that holds anything but A, C, G, T
+// and returns the number of bases done; the table loop takes over from there.
+__attribute__((target("bmi2"))) uint32_t pack_bam4_bmi2(const uint8_t *bam_seq, uint32_t len, uint8_t *dst) {
+  uint32_t i = 0;
+  for (; i + 16 <= len; i += 16) {
+    uint64_t w;
+    std::memcpy(&w, bam_seq + (i >> 1), 8);
+    const uint64_t pairs = (w & 0x5555555555555555ull) + ((w >> 1) & 0x5555555555555555ull);
+    const uint64_t pop = (pairs & 0x3333333333333333ull) + ((pairs >> 2) & 0x3333333333333333ull);
+    if (pop != 0x1111111111111111ull) break;  // a nibble that is not one-hot: '=', N or an IUPAC code
+    const uint64_t lo = (w | (w >> 2)) & 0x1111111111111111ull;
+    const uint64_t hi = ((w >> 2) | (w >> 3)) & 0x1111111111111111ull;
+    const uint32_t x = (uint32_t)_pext_u64(lo | (hi << 1), 0x3333333333333333ull);
+    const uint32_t y = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
+    std::memcpy(dst + (i >> 2), &y, 4);
+  }
+  return i;
+}
+const bool kHaveBmi2 = __builtin_cpu_supports("bmi2");
+#endif
+
 }  // namespace
 
 extern "C" {
@@ -92,6 +119,9 @@ int strgpu_pack_bam4(const uint8_t *bam_seq, uint32_t len, uint8_t *seq2, uint32
   uint8_t *dst = seq2 + (base_off >> 2);
   int n_other = 0;
   uint32_t i = 0;  // base index
+#if defined(__x86_64__)
+  if (kHaveBmi2) i = pack_bam4_bmi2(bam_seq, len, dst);
+#endif
   for (; i + 4 <= len; i += 4) {
     const uint8_t b0 = bam_seq[i >> 1], b1 = bam_seq[(i >> 1) + 1];
     dst[i >> 2] = (uint8_t)((kBam4.pair_code[b0] << 4) | kBam4.pair_code[b1]);

@@ -1,5 +1,6 @@
 // BGZF + BAM reader for the host side of `strling extract` / `strling call` (stands in for htslib, which the
-// reference reaches through hts-nim: extract.nim:275-329).  Blocks are inflated in parallel batches (zlib).
+// reference reaches through hts-nim: extract.nim:275-329).  Blocks are inflated in parallel batches with the repo's own
+// whole-block DEFLATE decoder (inflate_fast.hpp; STRLING_ZLIB=1 switches back to zlib's inflate for A/B runs).
 #pragma once
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -9,6 +10,10 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <memory>
+
+#include "inflate_fast.hpp"
+#include "pool.hpp"
 
 #include <cstdint>
 #include <cstdio>
@@ -57,6 +62,29 @@ struct BamRecord {
     return (int32_t)(pos + rl);
   }
 };
+
+// one BGZF block: `in` is followed by the block's 8-byte footer (the decoder may read into it)
+inline void inflate_bgzf_block(const uint8_t *in, uint32_t csize, uint8_t *out, uint32_t isize) {
+  static const bool use_zlib = std::getenv("STRLING_ZLIB") != nullptr;
+  if (isize == 0) return;
+  if (!use_zlib) {
+    static thread_local std::unique_ptr<infl::Tables> tables;
+    if (!tables) { tables.reset(new infl::Tables); tables->fixed_built = false; }
+    const int rc = infl::inflate_block(*tables, in, csize, out, isize);
+    if (rc != infl::kOk) throw std::runtime_error("BGZF: inflate failed (" + std::to_string(rc) + ")");
+    return;
+  }
+  z_stream zs;
+  std::memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("BGZF: inflateInit2");
+  zs.next_in = const_cast<uint8_t *>(in);
+  zs.avail_in = csize;
+  zs.next_out = out;
+  zs.avail_out = isize;
+  const int rc = inflate(&zs, Z_FINISH);
+  inflateEnd(&zs);
+  if (rc != Z_STREAM_END || zs.avail_out != 0) throw std::runtime_error("BGZF: inflate failed");
+}
 
 class BamReader {
  public:
@@ -217,18 +245,10 @@ class BamReader {
     }
     if (spans_.empty()) spans_.push_back(Span{base, blks[0].fpos});
     auto work = [&](size_t from, size_t to, std::string *err) {
-      z_stream zs;
-      for (size_t i = from; i < to; i++) {
-        if (blks[i].isize == 0) continue;
-        std::memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { *err = "inflateInit2"; return; }
-        zs.next_in = comp_.data() + blks[i].coff;
-        zs.avail_in = blks[i].csize;
-        zs.next_out = data_.data() + outoff[i];
-        zs.avail_out = blks[i].isize;
-        const int rc = inflate(&zs, Z_FINISH);
-        inflateEnd(&zs);
-        if (rc != Z_STREAM_END || zs.avail_out != 0) { *err = "inflate failed"; return; }
+      try {
+        for (size_t i = from; i < to; i++) inflate_bgzf_block(comp_.data() + blks[i].coff, blks[i].csize, data_.data() + outoff[i], blks[i].isize);
+      } catch (const std::exception &e) {
+        *err = e.what();
       }
     };
     const int nt = (int)std::min<size_t>((size_t)threads_, (blks.size() + 15) / 16);
@@ -246,7 +266,7 @@ class BamReader {
       for (auto &x : th) x.join();
     }
     for (auto &e : errs)
-      if (!e.empty()) throw std::runtime_error("BGZF: " + e);
+      if (!e.empty()) throw std::runtime_error(e);
   }
 
   void read_raw(void *dst, size_t n) {
@@ -366,7 +386,9 @@ struct BamChunk {
 
 class BamChunkReader {
  public:
-  BamChunkReader(const std::string &path, uint64_t start_voffset, int threads) {
+  // `pool`: the threads that inflate and walk (nullptr: a private pool of `threads`); `n_ref`: number of reference
+  // sequences in the header (only sharpens the record-start guesses of the parallel walk; any value is correct)
+  BamChunkReader(const std::string &path, uint64_t start_voffset, int threads, Pool *pool = nullptr, int32_t n_ref = INT32_MAX) : n_ref_(n_ref) {
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0) throw std::runtime_error("couldn't open bam");
     struct stat st;
@@ -377,7 +399,12 @@ class BamChunkReader {
       if (map_ == MAP_FAILED) throw std::runtime_error("couldn't mmap bam");
       ::madvise(const_cast<uint8_t *>(map_), file_size_, MADV_SEQUENTIAL);
     }
-    threads_ = threads > 0 ? threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (pool) {
+      pool_ = pool;
+    } else {
+      own_pool_.reset(new Pool(threads > 0 ? threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()))));
+      pool_ = own_pool_.get();
+    }
     fpos_ = start_voffset >> 16;
     first_skip_ = (uint32_t)(start_voffset & 0xffff);
   }
@@ -389,6 +416,7 @@ class BamChunkReader {
   BamChunkReader &operator=(const BamChunkReader &) = delete;
 
   double t_read = 0, t_alloc = 0, t_inflate = 0, t_walk = 0;  // seconds spent per phase (diagnostics)
+  size_t n_rewalked = 0;                                      // parts of the parallel walk whose guessed start was wrong
 
   // Fills `c` with the next whole records (about max_blocks BGZF blocks); false at EOF.
   bool next(BamChunk &c, size_t max_blocks) {
@@ -447,37 +475,7 @@ class BamChunkReader {
     }
     const auto q2 = clk::now();
     uint8_t *out = c.data.data();
-    auto work = [&](size_t from, size_t to, std::string *err) {
-      z_stream zs;
-      for (size_t i = from; i < to; i++) {
-        if (blks[i].isize == 0) continue;
-        std::memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { *err = "inflateInit2"; return; }
-        zs.next_in = const_cast<uint8_t *>(map_ + blks[i].in_off);
-        zs.avail_in = blks[i].csize;
-        zs.next_out = out + outoff[i];
-        zs.avail_out = blks[i].isize;
-        const int rc = inflate(&zs, Z_FINISH);
-        inflateEnd(&zs);
-        if (rc != Z_STREAM_END || zs.avail_out != 0) { *err = "inflate failed"; return; }
-      }
-    };
-    const int nt = (int)std::min<size_t>((size_t)threads_, (blks.size() + 7) / 8);
-    std::vector<std::string> errs((size_t)std::max(nt, 1));
-    if (nt <= 1) {
-      work(0, blks.size(), &errs[0]);
-    } else {
-      std::vector<std::thread> th;
-      const size_t per = (blks.size() + (size_t)nt - 1) / (size_t)nt;
-      for (int t = 0; t < nt; t++) {
-        const size_t a = (size_t)t * per, b = std::min(blks.size(), a + per);
-        if (a >= b) break;
-        th.emplace_back(work, a, b, &errs[(size_t)t]);
-      }
-      for (auto &x : th) x.join();
-    }
-    for (auto &e : errs)
-      if (!e.empty()) throw std::runtime_error("BGZF: " + e);
+    pool_->run(blks.size(), [&](size_t i) { inflate_bgzf_block(map_ + blks[i].in_off, blks[i].csize, out + outoff[i], blks[i].isize); });
     const auto q3 = clk::now();
     for (size_t i = 0; i < blks.size(); i++)
       if (blks[i].isize) c.spans.push_back(BamChunk::Span{(uint32_t)outoff[i], blks[i].fpos, 0});
@@ -496,19 +494,7 @@ class BamChunkReader {
       }
       first_skip_ = 0;
     }
-    // walk the records; keep the incomplete tail for the next call
-    size_t pos = 0;
-    c.rec_off.reserve(n / 200 + 16);
-    while (pos + 4 <= n) {
-      int32_t block_size;
-      std::memcpy(&block_size, out + pos, 4);
-      if (block_size < 32) throw std::runtime_error("corrupt BAM record");
-      if (pos + 4 + (size_t)block_size > n) break;
-      c.rec_off.push_back((uint32_t)pos);
-      pos += 4 + (size_t)block_size;
-      __builtin_prefetch(out + pos + 512);
-    }
-    c.rec_off.push_back((uint32_t)pos);
+    const size_t pos = walk_records(out, n, c.rec_off);
     if (pos < n) {
       if (eof && blks.empty()) throw std::runtime_error("truncated BAM record at end of file");
       carry_.assign(out + pos, out + n);
@@ -531,11 +517,120 @@ class BamChunkReader {
     return c.n_records() > 0 || !eof || !carry_.empty();
   }
 
+  // ---- record boundaries.  A BAM record only says where the NEXT one starts, so the walk is a chain through memory the
+  // inflate threads have just written.  It is cut into parts: every part but the first GUESSES its first record start
+  // (the first offset at or after the part's beginning from which kChain records in a row look like BAM records) and walks
+  // from there; afterwards the parts are checked in order -- part p is accepted only if it started exactly where the
+  // (already verified) chain through part p-1 arrived, otherwise it is walked again from that position.  data[0] is a
+  // record start by construction, so by induction the result is the one chain from data[0]: exact, whatever the guesses were.
+  struct WalkPart {
+    size_t start = 0, landing = 0;     // first record walked / first record start at or after the part's end (or the incomplete tail)
+    bool ok = false;
+    std::vector<uint32_t> offs;
+  };
+  static constexpr int kChain = 4;
+
+  bool plausible(const uint8_t *d, size_t n, size_t c, size_t *next) const {
+    if (c + 36 > n) return false;
+    int32_t bs, tid, pos, l_seq, mtid, mpos;
+    uint16_t n_cig;
+    std::memcpy(&bs, d + c, 4);
+    std::memcpy(&tid, d + c + 4, 4);
+    std::memcpy(&pos, d + c + 8, 4);
+    const uint32_t l_name = d[c + 12];
+    std::memcpy(&n_cig, d + c + 16, 2);
+    std::memcpy(&l_seq, d + c + 20, 4);
+    std::memcpy(&mtid, d + c + 24, 4);
+    std::memcpy(&mpos, d + c + 28, 4);
+    if (bs < 32 || bs > (1 << 24)) return false;
+    if (tid < -1 || tid >= n_ref_ || mtid < -1 || mtid >= n_ref_ || pos < -1 || mpos < -1 || l_name < 1 || l_seq < 0) return false;
+    const uint64_t need = 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
+    if (need > (uint64_t)bs) return false;
+    const size_t nul = c + 36 + l_name - 1;
+    if (nul < n && d[nul] != 0) return false;
+    *next = c + 4 + (size_t)bs;
+    return true;
+  }
+
+  // appends the complete records that start in [pos, limit); returns the first record start >= limit, or the position of the
+  // incomplete tail / of the first implausible length (then *bad is set, when bad is given; otherwise that is an error)
+  static size_t walk_range(const uint8_t *d, size_t n, size_t pos, size_t limit, std::vector<uint32_t> &offs, bool *bad) {
+    while (pos < limit && pos + 4 <= n) {
+      int32_t block_size;
+      std::memcpy(&block_size, d + pos, 4);
+      if (block_size < 32) {
+        if (bad) { *bad = true; return pos; }
+        throw std::runtime_error("corrupt BAM record");
+      }
+      if (pos + 4 + (size_t)block_size > n) break;
+      offs.push_back((uint32_t)pos);
+      pos += 4 + (size_t)block_size;
+      __builtin_prefetch(d + pos + 1024);
+    }
+    return pos;
+  }
+
+  // fills rec_off (n_records + 1 entries) and returns the end of the last complete record
+  size_t walk_records(const uint8_t *d, size_t n, std::vector<uint32_t> &rec_off) {
+    size_t parts = (size_t)pool_->size() * 2;
+    if (n < (1u << 22) || parts < 2) parts = 1;
+    std::vector<WalkPart> wp(parts);
+    const size_t per = (n + parts - 1) / parts;
+    pool_->run(parts, [&](size_t p) {
+      WalkPart &w = wp[p];
+      const size_t begin = p * per, limit = std::min(n, begin + per);
+      w.offs.reserve(per / 160 + 16);
+      if (p == 0) {
+        w.start = 0;
+        w.landing = walk_range(d, n, 0, limit, w.offs, nullptr);
+        w.ok = true;
+        return;
+      }
+      for (size_t c = begin; c < limit; c++) {
+        size_t q = c, nx = 0;
+        int k = 0;
+        while (k < kChain && plausible(d, n, q, &nx)) { q = nx; k++; }
+        if (k < kChain && !(k > 0 && q + 36 > n)) continue;  // a chain that runs into the end of the data counts as well
+        bool bad = false;
+        w.start = c;
+        w.landing = walk_range(d, n, c, limit, w.offs, &bad);
+        w.ok = !bad;
+        return;
+      }
+      w.ok = false;
+    });
+    // verification in chain order (serial, one comparison per part; a wrong guess costs one re-walk of that part)
+    size_t at = wp[0].landing;
+    for (size_t p = 1; p < parts; p++) {
+      WalkPart &w = wp[p];
+      const size_t begin = p * per, limit = std::min(n, begin + per);
+      (void)begin;
+      if (at >= limit) { w.offs.clear(); w.landing = at; continue; }   // the chain jumps over this part entirely
+      if (!(w.ok && w.start == at)) {
+        n_rewalked++;
+        w.offs.clear();
+        w.landing = walk_range(d, n, at, limit, w.offs, nullptr);
+      }
+      at = w.landing;
+    }
+    size_t total = 0;
+    std::vector<size_t> first(parts);
+    for (size_t p = 0; p < parts; p++) { first[p] = total; total += wp[p].offs.size(); }
+    rec_off.resize(total + 1);
+    pool_->run(parts, [&](size_t p) {
+      if (!wp[p].offs.empty()) std::memcpy(rec_off.data() + first[p], wp[p].offs.data(), wp[p].offs.size() * sizeof(uint32_t));
+    });
+    rec_off[total] = (uint32_t)at;
+    return at;
+  }
+
  private:
   int fd_ = -1;
   const uint8_t *map_ = nullptr;
   size_t file_size_ = 0;
-  int threads_ = 1;
+  Pool *pool_ = nullptr;
+  std::unique_ptr<Pool> own_pool_;
+  int32_t n_ref_ = INT32_MAX;
   uint64_t fpos_ = 0;
   uint32_t first_skip_ = 0;
   std::vector<uint8_t> carry_;

@@ -14,7 +14,8 @@ struct ExtractArgs {
   bool verbose = false;
   int device = 0;
   int threads = 0;
-  uint32_t batch_reads = 1u << 18;
+  uint32_t batch_reads = 1u << 19;
+  int replay_shards = 0;          // 0: a quarter of the threads
   // `strling debug extract` only (CPU-side checks of the staging and replay logic; never set by `strling extract`):
   // dump: write every staged segment ("pclass<TAB>bases", submission order) instead of scanning it, no .bin is written;
   // results: read the scan results (8-byte strgpu_repeat records in that same order) from a file instead of the GPU
@@ -29,6 +30,7 @@ int call_main(int argc, char **argv);
 int debug_main(int argc, char **argv);
 int debug_genotype(int argc, char **argv);
 int index_main(int argc, char **argv);
+int synth_bam(const std::string &path, uint64_t n_pairs, uint64_t seed, int level, int threads);
 std::vector<std::string> genome_repeat_lines(const std::string &fasta, double proportion_repeat, int device);
 
 }  // namespace strling

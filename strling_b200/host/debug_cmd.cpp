@@ -6,6 +6,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <vector>
 
 #include "bam.hpp"
 #include "commands.hpp"
@@ -62,7 +63,74 @@ int debug_main(int argc, char **argv) {
     if (argc >= 8) e.batch_reads = (uint32_t)std::atol(argv[7]);
     if (argc >= 9) e.genome_repeats = argv[8];
     e.threads = 2;
+    if (const char *t = std::getenv("STRLING_DEBUG_THREADS")) { e.threads = std::atoi(t); e.verbose = true; }
+    if (const char *t = std::getenv("STRLING_DEBUG_SHARDS")) e.replay_shards = std::atoi(t);  // stage timings of the host side
     return extract_run(e);
+  }
+  if (what == "synth-bam" && argc >= 3)  // strling debug synth-bam <out.bam> <n_pairs> [seed] [deflate level] [threads]
+    return synth_bam(argv[1], (uint64_t)std::atoll(argv[2]), argc >= 4 ? (uint64_t)std::atoll(argv[3]) : 2, argc >= 5 ? std::atoi(argv[4]) : 1,
+                     argc >= 6 ? std::atoi(argv[5]) : 0);
+  if (what == "inflate-selftest") {
+    // the repo's DEFLATE decoder against zlib's encoder: every deflate level and strategy (stored, fixed and dynamic Huffman
+    // blocks, long sub-table codes, every match distance / length class) over several kinds of data and all small sizes
+    const uint64_t seed = argc >= 2 ? (uint64_t)std::atoll(argv[1]) : 1;
+    const int rounds = argc >= 3 ? std::atoi(argv[2]) : 200;
+    uint64_t st = seed * 0x9e3779b97f4a7c15ull + 1;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    infl::Tables *T = new infl::Tables;
+    T->fixed_built = false;
+    size_t cases = 0, bytes = 0;
+    for (int r = 0; r < rounds; r++) {
+      const size_t n = r < 64 ? (size_t)r : (size_t)(rnd() % 65281);
+      std::vector<uint8_t> raw(n);
+      const int kind = (int)(rnd() % 6);
+      for (size_t i = 0; i < n; i++) {
+        switch (kind) {
+          case 0: raw[i] = (uint8_t)rnd(); break;                                         // incompressible
+          case 1: raw[i] = (uint8_t)"ACGT"[rnd() & 3]; break;                             // 2 bits of entropy per byte
+          case 2: raw[i] = (uint8_t)(i % (1 + seed % 7 + (size_t)r % 300)); break;        // periodic: every short distance
+          case 3: raw[i] = (uint8_t)((rnd() % 100) < 3 ? rnd() : 'F'); break;             // long runs (distance 1)
+          case 4: raw[i] = (uint8_t)(i > 4000 && (rnd() % 8) ? raw[i - 1 - (size_t)(rnd() % 4000)] : rnd()); break;  // far matches
+          default: raw[i] = (uint8_t)(rnd() % (2 + (size_t)r % 250)); break;              // skewed alphabets: long codes
+        }
+      }
+      for (int level = 0; level <= 9; level += (level < 2 ? 1 : 4)) {
+        for (int strategy : {Z_DEFAULT_STRATEGY, Z_FIXED, Z_HUFFMAN_ONLY, Z_RLE}) {
+          std::vector<uint8_t> comp(n + n / 8 + 1024);
+          z_stream zs;
+          std::memset(&zs, 0, sizeof(zs));
+          if (deflateInit2(&zs, level, Z_DEFLATED, -15, 1 + (r % 9), strategy) != Z_OK) return 2;
+          zs.next_in = raw.data();
+          zs.avail_in = (uInt)n;
+          zs.next_out = comp.data();
+          zs.avail_out = (uInt)comp.size() - 8;
+          // a flush in the middle makes multi-block streams (and empty stored blocks)
+          if (n > 100 && (r & 1)) { zs.avail_in = (uInt)(n / 2); deflate(&zs, Z_FULL_FLUSH); zs.avail_in = (uInt)(n - n / 2); }
+          if (deflate(&zs, Z_FINISH) != Z_STREAM_END) return 2;
+          const size_t clen = comp.size() - 8 - zs.avail_out;
+          deflateEnd(&zs);
+          std::vector<uint8_t> got(n + 64, 0xAB);
+          const int rc = infl::inflate_block(*T, comp.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
+          bool ok = rc == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
+          for (int g = 0; g < 32; g++) ok = ok && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;  // nothing outside [out, out + n)
+          if (!ok) { std::printf("FAIL round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc); return 1; }
+          // a truncated or corrupted stream must be refused or at least stay inside the output buffer
+          if (clen > 4) {
+            std::vector<uint8_t> bad(comp);
+            bad[(size_t)(rnd() % clen)] ^= (uint8_t)(1u << (rnd() % 8));
+            std::fill(got.begin(), got.end(), 0xAB);
+            (void)infl::inflate_block(*T, bad.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
+            for (int g = 0; g < 32; g++)
+              if (got[(size_t)g] != 0xAB || got[32 + n + (size_t)g] != 0xAB) { std::printf("FAIL overrun on corrupt input, round %d\n", r); return 1; }
+          }
+          cases++;
+          bytes += n;
+        }
+      }
+    }
+    delete T;
+    std::printf("ok\t%zu cases\t%zu bytes\n", cases, bytes);
+    return 0;
   }
   if (what == "bam" && argc >= 2) {
     BamReader rd(argv[1]);
@@ -84,14 +152,27 @@ int debug_main(int argc, char **argv) {
     BamReader hdr(argv[1]);
     const int threads = argc >= 3 ? std::atoi(argv[2]) : 0;
     const size_t blocks = argc >= 4 ? (size_t)std::atol(argv[3]) : 4096;
-    BamChunkReader rd(argv[1], hdr.tell(), threads);
+    BamChunkReader rd(argv[1], hdr.tell(), threads, nullptr, (int32_t)hdr.targets().size());
     BamChunk c;
     size_t n = 0, chunks = 0;
+    uint64_t digest = 1469598103934665603ull;  // FNV-1a over (tid, pos, flag, l_seq, qname) of every record, in order
+    auto mix = [&](const void *p, size_t len) {
+      const uint8_t *b = static_cast<const uint8_t *>(p);
+      for (size_t i = 0; i < len; i++) digest = (digest ^ b[i]) * 1099511628211ull;
+    };
     const auto t0 = std::chrono::steady_clock::now();
-    while (rd.next(c, blocks)) { n += c.n_records(); chunks++; }
+    while (rd.next(c, blocks)) {
+      n += c.n_records();
+      chunks++;
+      if (argc >= 5)
+        for (size_t i = 0; i < c.n_records(); i++) {
+          const BamRecord r = BamChunk::view(c.data.data() + c.rec_off[i]);
+          mix(&r.tid, 4); mix(&r.pos, 4); mix(&r.flag, 2); mix(&r.l_seq, 4); mix(r.qname, r.l_qname);
+        }
+    }
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    std::printf("records\t%zu\tchunks\t%zu\tseconds\t%.3f\tread\t%.3f\talloc\t%.3f\tinflate\t%.3f\twalk\t%.3f\n", n, chunks, dt, rd.t_read, rd.t_alloc,
-                rd.t_inflate, rd.t_walk);
+    std::printf("records\t%zu\tchunks\t%zu\tseconds\t%.3f\tread\t%.3f\talloc\t%.3f\tinflate\t%.3f\twalk\t%.3f\trewalked\t%zu\tdigest\t%016llx\n", n, chunks, dt, rd.t_read,
+                rd.t_alloc, rd.t_inflate, rd.t_walk, rd.n_rewalked, (unsigned long long)digest);
     return 0;
   }
   if (what == "fragdist" && argc >= 2) {

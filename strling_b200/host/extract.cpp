@@ -9,6 +9,7 @@
 // travels with the batch, so qnames are never copied); a consumer thread waits for the GPU and replays batch n-1 while
 // the producer stages batch n+1.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -25,6 +26,7 @@
 
 #include "bam.hpp"
 #include "commands.hpp"
+#include "pool.hpp"
 #include "strgpu.h"
 #include "tread.hpp"
 
@@ -72,6 +74,8 @@ std::unordered_map<std::string, Intervals> read_bed(const std::string &path) {
 }
 
 constexpr int kClsRead = 0, kClsFirstSeen = 1, kClsSecondSeen = 2;
+constexpr uint8_t kNoOwner = 255;   // a record the replay does not look at (secondary / supplementary, placed records in the tail pass)
+constexpr int kMaxShards = 16;
 
 struct Pending {  // what the replay needs from one BAM record (qname stays in the batch's decode buffer)
   int32_t tid, pos, stop, mate_tid, mate_pos;
@@ -85,14 +89,57 @@ struct Pending {  // what the replay needs from one BAM record (qname stays in t
   const char *qname;
   uint32_t qname_len;
   uint32_t aligned_bases;  // bases reserved in seq2 (0: the record's SEQ is not needed)
+  uint64_t hash;           // of the qname: picks the replay shard and the slot in its mate table
   bool skip, clip_l, clip_r, primary;
+};
+
+inline uint64_t hash_name(const char *s, size_t n) {  // 8 bytes at a time, multiply-xorshift mixing
+  uint64_t h = 0x9e3779b97f4a7c15ull ^ (n * 0xff51afd7ed558ccdull);
+  while (n >= 8) {
+    uint64_t w;
+    std::memcpy(&w, s, 8);
+    h = (h ^ w) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+    s += 8;
+    n -= 8;
+  }
+  uint64_t w = 0;
+  std::memcpy(&w, s, n);
+  h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+  h ^= h >> 29;
+  h *= 0xff51afd7ed558ccdull;
+  h ^= h >> 32;
+  return h;
+}
+
+template <typename T>
+struct PodVec {  // uninitialised growable array (std::vector would value-initialise ~50 MB per batch on one thread)
+  T *p = nullptr;
+  size_t n = 0, cap = 0;
+  PodVec() = default;
+  PodVec(const PodVec &) = delete;
+  PodVec &operator=(const PodVec &) = delete;
+  ~PodVec() { std::free(p); }
+  void resize(size_t m) {
+    if (m > cap) {
+      std::free(p);
+      cap = m + m / 8 + 64;
+      p = static_cast<T *>(std::malloc(cap * sizeof(T)));
+      if (!p) throw std::runtime_error("[strling] out of memory");
+    }
+    n = m;
+  }
+  size_t size() const { return n; }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
 };
 
 struct Batch {
   BamChunk chunk;                // owns the decoded records (qname / SEQ are used in place)
-  std::vector<Pending> recs;     // one per record of the chunk, file order
-  std::vector<uint64_t> base_off;
-  std::vector<uint32_t> seg_off;
+  PodVec<Pending> recs;          // one per record of the chunk, file order
+  PodVec<uint8_t> owner;         // replay shard of every record, kNoOwner: not replayed
+  std::vector<std::pair<uint32_t, int32_t>> tid_changes;  // (record, tid) wherever the reference id changes (progress messages)
+  uint64_t n_replayed = 0;
   uint8_t *seq2 = nullptr;       // pinned
   uint32_t *nmask = nullptr;     // pinned
   uint32_t *xmask = nullptr;     // pinned: non-ACGT bases other than the literal N (stay out of the N > 20 gate, utils.nim:238)
@@ -105,18 +152,108 @@ struct Batch {
   int ticket = -1;
 };
 
+// Cache.tbl (extract.nim:89-91): qname -> the first-seen mate.  Open addressing over indices into an entry pool
+// (linear probing, backward-shift deletion); names of up to 54 bytes live inside the entry, so the common insert / take
+// pair allocates nothing.
+class MateTable {
+ public:
+  struct Entry {
+    uint64_t hash;
+    TreadCore t;
+    uint32_t name_len;
+    char name[54];
+    std::string long_name;
+    const char *name_ptr() const { return name_len <= sizeof(name) ? name : long_name.data(); }
+  };
+  MateTable() { slots_.assign(1024, 0); }
+  size_t size() const { return live_; }
+  // slot of the key or SIZE_MAX
+  size_t find(const char *name, uint32_t len, uint64_t h) const {
+    const size_t mask = slots_.size() - 1;
+    for (size_t s = (size_t)h & mask;; s = (s + 1) & mask) {
+      const uint32_t e = slots_[s];
+      if (!e) return SIZE_MAX;
+      const Entry &en = pool_[e - 1];
+      if (en.hash == h && en.name_len == len && std::memcmp(en.name_ptr(), name, len) == 0) return s;
+    }
+  }
+  Entry &at(size_t slot) { return pool_[slots_[slot] - 1]; }
+  void insert(const char *name, uint32_t len, uint64_t h, const TreadCore &t) {  // the key must be absent
+    if ((live_ + 1) * 2 > slots_.size()) grow();
+    uint32_t idx;
+    if (!free_.empty()) { idx = free_.back(); free_.pop_back(); }
+    else { pool_.emplace_back(); idx = (uint32_t)pool_.size() - 1; }
+    Entry &en = pool_[idx];
+    en.hash = h;
+    en.t = t;
+    en.name_len = len;
+    if (len <= sizeof(en.name)) std::memcpy(en.name, name, len);
+    else en.long_name.assign(name, len);
+    place(idx);
+    live_++;
+  }
+  void erase(size_t slot) {
+    const size_t mask = slots_.size() - 1;
+    const uint32_t idx = slots_[slot] - 1;
+    pool_[idx].long_name.clear();
+    free_.push_back(idx);
+    live_--;
+    // backward shift: pull later members of the probe run into the hole while that shortens their probe distance
+    size_t hole = slot;
+    for (size_t s = (slot + 1) & mask;; s = (s + 1) & mask) {
+      const uint32_t e = slots_[s];
+      if (!e) break;
+      const size_t home = (size_t)pool_[e - 1].hash & mask;
+      if (((s - home) & mask) >= ((s - hole) & mask)) { slots_[hole] = e; hole = s; }
+    }
+    slots_[hole] = 0;
+  }
+
+ private:
+  void place(uint32_t idx) {
+    const size_t mask = slots_.size() - 1;
+    size_t s = (size_t)pool_[idx].hash & mask;
+    while (slots_[s]) s = (s + 1) & mask;
+    slots_[s] = idx + 1;
+  }
+  void grow() {
+    std::vector<uint32_t> old;
+    old.swap(slots_);
+    slots_.assign(old.size() * 2, 0);
+    for (uint32_t e : old)
+      if (e) place(e - 1);
+  }
+  std::vector<uint32_t> slots_;
+  std::vector<Entry> pool_;
+  std::vector<uint32_t> free_;
+  size_t live_ = 0;
+};
+
+// One replay shard: the reads whose qname hashes to it, in file order.  Everything add() (extract.nim:192-248) does is keyed
+// by the qname, so shards never interact; what they append to cache.cache is tagged with (record, ordinal within the record)
+// and merged back into file order once per batch.
+struct Shard {
+  MateTable tbl;
+  std::vector<std::pair<uint64_t, Tread>> out;
+  uint64_t tag = 0;
+};
+
 struct Extractor {
   strgpu_ctx *gpu = nullptr;
   Options opts;
   double p = 0.8;
   const std::vector<Target> *targets = nullptr;
   std::vector<const Intervals *> genome_str_by_tid;  // nullptr: chrom not in genome_str
-  std::unordered_map<std::string, Tread> tbl;        // Cache.tbl (extract.nim:89-91)
+  Shard shards[kMaxShards];                          // Cache.tbl, split by qname hash
+  int n_shards = 1;
   std::vector<Tread> cache;                          // Cache.cache
-  uint64_t n_reads = 0, n_scanned = 0, n_warned = 0;
+  uint64_t n_reads = 0, n_scanned = 0;
+  std::atomic<uint64_t> n_warned{0};
   double t_wait = 0, t_replay = 0, t_submit = 0, t_decode = 0, t_stage = 0;  // host stage timers (seconds)
+  double t_stage_parse = 0, t_stage_grow = 0, t_stage_pack = 0, t_replay_shards = 0;
   bool verbose = false;
   int threads = 1;
+  Pool *pool = nullptr;
   // `strling debug extract`: the scan is replaced by a segment dump / by results read from a file (commands.hpp); no GPU then
   FILE *dump = nullptr, *results = nullptr;
   bool debug_mode() const { return dump != nullptr || results != nullptr; }
@@ -157,39 +294,31 @@ struct Extractor {
     alloc_batch(b, std::max<uint64_t>(need_bases + need_bases / 8, b.cap_bases), std::max<uint32_t>(need_seg + need_seg / 8, b.cap_seg));
   }
 
-  template <typename F>
-  void parallel_for(size_t n, F f) {  // f(begin, end, thread)
-    const int nt = (int)std::min<size_t>((size_t)threads, (n + 4095) / 4096);
-    if (nt <= 1) { f((size_t)0, n, 0); return; }
-    std::vector<std::thread> th;
-    std::vector<std::string> errs((size_t)nt);
-    const size_t per = (n + (size_t)nt - 1) / (size_t)nt;
-    for (int t = 0; t < nt; t++) {
-      const size_t a = (size_t)t * per, e = std::min(n, a + per);
-      if (a >= e) break;
-      th.emplace_back([&, a, e, t]() {
-        try { f(a, e, t); } catch (const std::exception &ex) { errs[(size_t)t] = ex.what(); }
-      });
-    }
-    for (auto &x : th) x.join();
-    for (auto &e : errs)
-      if (!e.empty()) throw std::runtime_error(e);
-  }
-
-  // Decode every record of the chunk and lay the batch out: phase 1 (parallel) parses the fields and decides which
-  // segments a record contributes; a prefix sum fixes every record's place in seq2 / segs; phase 2 (parallel) packs the
-  // SEQ fields and writes the descriptors.
-  void stage(Batch &b) {
+  // Decode every record of the chunk and lay the batch out: phase 1 (parallel) parses the fields, hashes the qname and
+  // decides which segments a record contributes; a prefix sum over the parts fixes every part's place in seq2 / segs; phase 2
+  // (parallel, same parts) packs the SEQ fields and writes the descriptors.
+  void stage(Batch &b, bool pass1) {
     const size_t n = b.chunk.n_records();
+    const auto s0 = std::chrono::steady_clock::now();
     b.recs.resize(n);
-    b.base_off.resize(n + 1);
-    b.seg_off.resize(n + 1);
+    b.owner.resize(n);
+    b.tid_changes.clear();
     const uint8_t *data = b.chunk.data.data();  // RawBuffer
-    parallel_for(n, [&](size_t lo, size_t hi, int) {
+    const size_t parts = std::max<size_t>(1, std::min<size_t>((size_t)pool->size() * 4, (n + 2047) / 2048));
+    struct PartSum { uint64_t bases = 0; uint32_t segs = 0; uint64_t replayed = 0; std::vector<std::pair<uint32_t, int32_t>> tids; };
+    std::vector<PartSum> sums(parts);
+    const uint32_t n_sh = (uint32_t)n_shards;
+    pool->ranges(n, parts, [&](size_t lo, size_t hi, size_t part) {
+      PartSum ps;
+      int32_t last_tid = INT32_MIN;
       for (size_t i = lo; i < hi; i++) {
+        if (i + 6 < hi) {
+          __builtin_prefetch(data + b.chunk.rec_off[i + 6]);
+          __builtin_prefetch(data + b.chunk.rec_off[i + 6] + 64);
+        }
         const BamRecord r = BamChunk::view(data + b.chunk.rec_off[i]);
         Pending &pr = b.recs[i];
-        pr.tid = r.tid; pr.pos = r.pos; pr.stop = r.stop(); pr.mate_tid = r.mate_tid; pr.mate_pos = r.mate_pos;
+        pr.tid = r.tid; pr.pos = r.pos; pr.mate_tid = r.mate_tid; pr.mate_pos = r.mate_pos;
         pr.flag = r.flag; pr.n_cigar = r.n_cigar; pr.mapq = r.mapq; pr.l_seq = r.l_seq;
         pr.first_cig = r.n_cigar ? r.cigar_at(0) : 0;
         pr.last_cig = r.n_cigar ? r.cigar_at(r.n_cigar - 1) : 0;
@@ -202,9 +331,18 @@ struct Extractor {
         pr.skip = pr.clip_l = pr.clip_r = false;
         pr.n_seg = 0;
         pr.aligned_bases = 0;
+        pr.stop = 0;
+        pr.hash = 0;
+        b.owner[i] = kNoOwner;
+        if (r.tid != last_tid) { ps.tids.emplace_back((uint32_t)i, r.tid); last_tid = r.tid; }
         if (!pr.primary) continue;
+        if (!pass1 && r.tid >= 0) continue;   // ibam.query("*") returns no-coordinate records only (extract.nim:326-329)
         if (r.l_seq > STRGPU_MAX_SEGMENT_LEN)
           throw std::runtime_error("[strling] read longer than " + std::to_string(STRGPU_MAX_SEGMENT_LEN) + " bp: " + std::string(r.qname));
+        pr.stop = r.stop();
+        pr.hash = hash_name(r.qname, r.l_qname);
+        b.owner[i] = (uint8_t)((pr.hash >> 40) % n_sh);
+        ps.replayed++;
         // extract.nim:30-34 : exact single-M match outside every genome STR region -> no scan
         if (r.n_cigar == 1 && BamRecord::op(pr.first_cig) == 0 && r.tid >= 0 && (size_t)r.tid < genome_str_by_tid.size() &&
             genome_str_by_tid[(size_t)r.tid] != nullptr && !genome_str_by_tid[(size_t)r.tid]->find(r.pos, pr.stop)) {
@@ -218,37 +356,54 @@ struct Extractor {
         }
         pr.n_seg = (uint8_t)((pr.skip ? 0 : 1) + (pr.clip_l ? 2 : 0) + (pr.clip_r ? 2 : 0));
         if (pr.n_seg) pr.aligned_bases = ((uint32_t)r.l_seq + 31u) & ~31u;  // 32-base alignment: no two records share an nmask word
+        ps.bases += pr.aligned_bases;
+        ps.segs += pr.n_seg;
       }
-    });
+      sums[part] = std::move(ps);
+    }, 1);
+    const auto s1 = std::chrono::steady_clock::now();
     uint64_t nb = 0;
     uint32_t ns = 0;
-    for (size_t i = 0; i < n; i++) {
-      b.base_off[i] = nb;
-      b.seg_off[i] = ns;
-      nb += b.recs[i].aligned_bases;
-      ns += b.recs[i].n_seg;
+    uint64_t n_rep = 0;
+    std::vector<uint64_t> part_base(parts);
+    std::vector<uint32_t> part_seg(parts);
+    int32_t last_tid = INT32_MIN;
+    for (size_t q = 0; q < parts; q++) {
+      part_base[q] = nb;
+      part_seg[q] = ns;
+      nb += sums[q].bases;
+      if ((uint64_t)ns + sums[q].segs > 0xfffffff0ull) throw std::runtime_error("[strling] batch too large: lower --batch-reads");
+      ns += sums[q].segs;
+      n_rep += sums[q].replayed;
+      for (const auto &tc : sums[q].tids)
+        if (tc.second != last_tid) { b.tid_changes.push_back(tc); last_tid = tc.second; }
     }
-    b.base_off[n] = nb;
-    b.seg_off[n] = ns;
     if (nb > 0xffffff00ull) throw std::runtime_error("[strling] batch too large: lower --batch-reads");
     grow_batch(b, nb + 64, ns + 8);
     b.n_bases = nb;
     b.n_seg = ns;
-    std::vector<uint32_t> tmax((size_t)threads + 1, 0);
-    std::vector<uint8_t> tany((size_t)threads + 1, 0);
-    parallel_for(n, [&](size_t lo, size_t hi, int t) {
+    b.n_replayed = n_rep;
+    const auto s2 = std::chrono::steady_clock::now();
+    std::vector<uint32_t> tmax(parts, 0);
+    std::vector<uint8_t> tany(parts, 0);
+    pool->ranges(n, parts, [&](size_t lo, size_t hi, size_t part) {
       uint32_t mx = 0;
       bool any = false;
+      uint64_t base = part_base[part];
+      uint32_t si = part_seg[part];
       for (size_t i = lo; i < hi; i++) {
+        if (i + 6 < hi) {
+          __builtin_prefetch(data + b.chunk.rec_off[i + 6]);
+          __builtin_prefetch(data + b.chunk.rec_off[i + 6] + 64);
+          __builtin_prefetch(data + b.chunk.rec_off[i + 6] + 128);
+        }
         Pending &pr = b.recs[i];
         if (!pr.n_seg) continue;
         const BamRecord r = BamChunk::view(data + b.chunk.rec_off[i]);
-        const uint64_t base = b.base_off[i];
         const int n_other = strgpu_pack_bam4(r.seq, (uint32_t)r.l_seq, b.seq2, b.nmask, b.xmask, base);
         if (n_other < 0) throw std::runtime_error("[strling] pack_bam4 failed");
         const bool has_n = n_other > 0;
         any = any || has_n;
-        uint32_t si = b.seg_off[i];
         auto put = [&](uint64_t off, uint32_t len, int cls) {
           b.segs[si] = strgpu_segment{(uint32_t)off, (uint16_t)len, (uint8_t)cls, (uint8_t)(has_n ? STRGPU_SEG_HAS_N : 0)};
           mx = std::max(mx, len);
@@ -265,12 +420,17 @@ struct Extractor {
           pr.seg_clip[1][0] = put(base + (uint64_t)r.l_seq - len, len, kClsFirstSeen);
           pr.seg_clip[1][1] = put(base + (uint64_t)r.l_seq - len, len, kClsSecondSeen);
         }
+        base += pr.aligned_bases;
       }
-      tmax[(size_t)t] = mx;
-      tany[(size_t)t] = any;
-    });
+      tmax[part] = mx;
+      tany[part] = any;
+    }, 1);
     b.max_len = *std::max_element(tmax.begin(), tmax.end());
     b.any_n = std::any_of(tany.begin(), tany.end(), [](uint8_t v) { return v != 0; });
+    const auto s3 = std::chrono::steady_clock::now();
+    t_stage_parse += std::chrono::duration<double>(s1 - s0).count();
+    t_stage_grow += std::chrono::duration<double>(s2 - s1).count();
+    t_stage_pack += std::chrono::duration<double>(s3 - s2).count();
   }
 
   void submit(Batch &b) {
@@ -314,15 +474,15 @@ struct Extractor {
     b.n_bases = 0; b.n_seg = 0; b.max_len = 0; b.any_n = false; b.ticket = -1;
   }
 
-  // ---- replay: extract.nim:63-132,192-248 with scan results looked up instead of computed
-  Tread to_tread(const Batch &b, const Pending &r) {
-    Tread t;
+  // ---- replay: extract.nim:63-132,192-248 with scan results looked up instead of computed.  The pair arithmetic runs on
+  // records without the qname (every read of a pair carries the same one); emit() attaches it.
+  TreadCore to_tread(const Batch &b, const Pending &r) {
+    TreadCore t;
     t.tid = r.tid;
     t.position = (uint32_t)std::max(0, r.pos);
     t.flag = r.flag;
     t.split = kNone;
     t.mapping_quality = r.mapq;
-    t.qname.assign(r.qname, r.qname_len);
     int align_length = r.m_len, repeat_count = 0;
     if (r.seg_full >= 0) {
       const strgpu_repeat &res = b.out[r.seg_full];
@@ -330,7 +490,8 @@ struct Extractor {
       repeat_count = res.repeat_count;
       align_length = r.l_seq;
     }
-    if (repeat_count >= 256) throw std::runtime_error("[strling] repeat_count >= 256 for read " + t.qname);  // doAssert, extract.nim:72
+    if (repeat_count >= 256)  // doAssert, extract.nim:72
+      throw std::runtime_error("[strling] repeat_count >= 256 for read " + std::string(r.qname, r.qname_len));
     t.repeat_count = (uint8_t)repeat_count;
     t.align_length = (uint8_t)align_length;
     if (r.n_cigar > 1 && BamRecord::op(r.first_cig) == 4 && BamRecord::oplen(r.first_cig) > 16) t.split = kNoneLeft;
@@ -338,7 +499,9 @@ struct Extractor {
     return t;
   }
 
-  void add_soft(const Batch &b, const Pending &r, int cls_idx, const std::array<char, 6> &read_repeat, const std::string &qname) {
+  static void emit(Shard &sh, const TreadCore &t, const Pending &r) { sh.out.emplace_back(sh.tag++, Tread(t, r.qname, r.qname_len)); }
+
+  void add_soft(Shard &sh, const Batch &b, const Pending &r, int cls_idx, const std::array<char, 6> &read_repeat) {
     if (r.mapq < opts.min_mapq) return;
     if (r.n_cigar == 0 || (BamRecord::op(r.first_cig) != 4 && BamRecord::op(r.last_cig) != 4)) return;
     const int idxs[2] = {0, (int)r.n_cigar - 1};
@@ -352,7 +515,7 @@ struct Extractor {
       if (si < 0) continue;
       const strgpu_repeat &res = b.out[si];
       if (res.repeat_count == 0) continue;
-      Tread tr;
+      TreadCore tr;
       tr.tid = r.tid;
       tr.position = (uint32_t)(is_left ? std::max(0, r.pos) : std::max(0, r.stop));
       tr.flag = r.flag;
@@ -361,27 +524,27 @@ struct Extractor {
       tr.align_length = (uint8_t)std::min<uint32_t>(clen, (uint32_t)r.l_seq);
       tr.split = is_left ? kLeft : kRight;
       tr.mapping_quality = r.mapq;
-      tr.qname = qname;
       if (p_repeat(tr) < 0.9) continue;
-      cache.push_back(std::move(tr));
+      emit(sh, tr, r);
     }
   }
 
-  void add(const Batch &b, const Pending &r) {
-    std::string qname(r.qname, r.qname_len);
-    auto it = tbl.end();
+  void add(Shard &sh, const Batch &b, const Pending &r) {
+    MateTable &tbl = sh.tbl;
+    size_t slot = SIZE_MAX;
+    bool looked = false;
     bool after_mate = r.tid > r.mate_tid;
     if (!after_mate && r.tid == r.mate_tid) {
       if (r.pos > r.mate_pos) after_mate = true;
-      else if (r.pos == r.mate_pos) { it = tbl.find(qname); after_mate = it != tbl.end(); }
+      else if (r.pos == r.mate_pos) { slot = tbl.find(r.qname, r.qname_len, r.hash); looked = true; after_mate = slot != SIZE_MAX; }
     }
     if (after_mate) {
-      if (it == tbl.end()) it = tbl.find(qname);
-      if (it == tbl.end()) return;
-      Tread mate = std::move(it->second);
-      tbl.erase(it);
-      Tread self = to_tread(b, r);
-      add_soft(b, r, 1, self.repeat, qname);  // opts.proportion_repeat = min(p, 0.6)
+      if (!looked) slot = tbl.find(r.qname, r.qname_len, r.hash);
+      if (slot == SIZE_MAX) return;
+      TreadCore mate = tbl.at(slot).t;
+      tbl.erase(slot);
+      TreadCore self = to_tread(b, r);
+      add_soft(sh, b, r, 1, self.repeat);  // opts.proportion_repeat = min(p, 0.6)
       if (mate.repeat_count == 0 && self.repeat_count == 0) return;
       if (unplaced_pair(self, mate, opts)) {
         if (self.repeat[0] == 0 || mate.repeat[0] == 0) return;
@@ -391,28 +554,66 @@ struct Extractor {
         mate.repeat = canonical_repeat(mate.repeat);
         mate.position = 0;
         mate.tid = -1;
-        cache.push_back(std::move(self));
-        cache.push_back(std::move(mate));
+        emit(sh, self, r);
+        emit(sh, mate, r);
         return;
       }
       const uint32_t mp = mate.position;
-      if (adjust_by(mate, self, opts, self.position)) cache.push_back(mate);
-      if (adjust_by(self, mate, opts, mp)) cache.push_back(std::move(self));
+      if (adjust_by(mate, self, opts, self.position)) emit(sh, mate, r);
+      if (adjust_by(self, mate, opts, mp)) emit(sh, self, r);
     } else {
-      Tread tr = to_tread(b, r);
-      add_soft(b, r, 0, tr.repeat, qname);  // opts.proportion_repeat = p - 0.07
-      auto ins = tbl.emplace(qname, std::move(tr));
-      if (!ins.second) {  // hasKeyOrPut found the key: warn and drop it (extract.nim:245-248)
-        if (n_warned++ < 20)
-          std::fprintf(stderr, "[strling] warning. bad read (this happens with bwa-kit alignments):%s already in table\n", qname.c_str());
-        tbl.erase(ins.first);
+      const TreadCore tr = to_tread(b, r);
+      add_soft(sh, b, r, 0, tr.repeat);  // opts.proportion_repeat = p - 0.07
+      if (!looked) slot = tbl.find(r.qname, r.qname_len, r.hash);
+      if (slot != SIZE_MAX) {  // hasKeyOrPut found the key: warn and drop it (extract.nim:245-248)
+        if (n_warned.fetch_add(1) < 20)
+          std::fprintf(stderr, "[strling] warning. bad read (this happens with bwa-kit alignments):%.*s already in table\n", (int)r.qname_len, r.qname);
+        tbl.erase(slot);
+      } else {
+        tbl.insert(r.qname, r.qname_len, r.hash, tr);
       }
     }
   }
 
+  // One batch: every shard walks the batch's records in file order and handles its own; what they emitted is merged into
+  // cache.cache by (record, ordinal) -- the order a single add() loop would have appended in.
   void replay(const Batch &b) {
-    for (const Pending &r : b.recs)
-      if (r.primary) add(b, r);
+    const size_t n = b.recs.size();
+    const uint8_t *own = b.owner.p;
+    auto shard_work = [&](size_t s) {
+      Shard &sh = shards[s];
+      sh.out.clear();
+      for (size_t i = 0; i < n; i++) {
+        if (own[i] != (uint8_t)s) continue;
+        sh.tag = (uint64_t)i << 4;
+        add(sh, b, b.recs[i]);
+      }
+    };
+    const auto r0 = std::chrono::steady_clock::now();
+    if (n_shards == 1) shard_work(0);
+    else pool->run((size_t)n_shards, shard_work, 2);
+    t_replay_shards += std::chrono::duration<double>(std::chrono::steady_clock::now() - r0).count();
+    size_t total = 0;
+    for (int s = 0; s < n_shards; s++) total += shards[s].out.size();
+    if (n_shards == 1) {
+      for (auto &e : shards[0].out) cache.push_back(std::move(e.second));
+      return;
+    }
+    cache.reserve(cache.size() + total);
+    size_t head[kMaxShards] = {0};
+    for (size_t k = 0; k < total; k++) {
+      int best = -1;
+      uint64_t best_tag = UINT64_MAX;
+      for (int s = 0; s < n_shards; s++)
+        if (head[s] < shards[s].out.size() && shards[s].out[head[s]].first < best_tag) { best_tag = shards[s].out[head[s]].first; best = s; }
+      cache.push_back(std::move(shards[best].out[head[best]++].second));
+    }
+  }
+
+  size_t table_size() const {
+    size_t n = 0;
+    for (int s = 0; s < n_shards; s++) n += shards[s].tbl.size();
+    return n;
   }
 };
 
@@ -514,7 +715,11 @@ int extract_run(const ExtractArgs &a) {
     ex.gpu_check(strgpu_set_proportions(ex.gpu, classes, 3), "set_proportions");
   }
 
-  ex.threads = a.threads > 0 ? a.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  ex.threads = a.threads > 0 ? a.threads : (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  Pool pool(ex.threads);
+  ex.pool = &pool;
+  // replay shards (by qname hash): the mate-table work of one batch spread over a quarter of the threads
+  ex.n_shards = std::max(1, std::min(kMaxShards, a.replay_shards > 0 ? a.replay_shards : ex.threads / 4));
   const uint64_t first_voffset = rd.tell();
   constexpr int kBatches = STRGPU_SLOTS + 1;  // one being inflated, one being staged, up to two on the GPU / in replay
   Batch batches[kBatches];
@@ -555,22 +760,20 @@ int extract_run(const ExtractArgs &a) {
         }
         cv.notify_all();
         const auto w1 = clk::now();
-        for (const Pending &r : b.recs) {
-          if (!r.primary) continue;
-          if (!first_pass && r.tid >= 0) continue;   // ibam.query("*") returns no-coordinate records only
-          if (first_pass && r.tid != tid_seen && r.tid >= 0) {
-            if (rd.targets()[(size_t)r.tid].length > 2000000u)
-              std::fprintf(stderr, "[strling] extracting chromosome:%s\n", rd.targets()[(size_t)r.tid].name.c_str());
-            tid_seen = r.tid;
-          }
-          ex.n_reads++;
-          if (ex.verbose && ex.n_reads % 10000000 == 0) {
-            const double dt = std::chrono::duration<double>(clk::now() - t0).count();
-            std::fprintf(stderr, "%llu %.1f reads/sec tbl len: %zu cache len: %zu\n", (unsigned long long)ex.n_reads, ex.n_reads / dt,
-                         ex.tbl.size(), ex.cache.size());
-          }
-          ex.add(b, r);
+        if (first_pass)
+          for (const auto &tc : b.tid_changes)
+            if (tc.second != tid_seen && tc.second >= 0) {
+              if (rd.targets()[(size_t)tc.second].length > 2000000u)
+                std::fprintf(stderr, "[strling] extracting chromosome:%s\n", rd.targets()[(size_t)tc.second].name.c_str());
+              tid_seen = tc.second;
+            }
+        ex.replay(b);
+        if (ex.verbose && (ex.n_reads + b.n_replayed) / 10000000 != ex.n_reads / 10000000) {
+          const double dt = std::chrono::duration<double>(clk::now() - t0).count();
+          std::fprintf(stderr, "%llu %.1f reads/sec tbl len: %zu cache len: %zu\n", (unsigned long long)(ex.n_reads + b.n_replayed),
+                       (ex.n_reads + b.n_replayed) / dt, ex.table_size(), ex.cache.size());
         }
+        ex.n_reads += b.n_replayed;
         ex.recycle(b);
         ex.t_wait += std::chrono::duration<double>(w1 - w0).count();
         ex.t_replay += std::chrono::duration<double>(clk::now() - w1).count();
@@ -609,7 +812,7 @@ int extract_run(const ExtractArgs &a) {
     std::string reader_error;
     std::thread reader_thread([&]() {
       try {
-        BamChunkReader reader(a.bam, voffset, ex.threads);
+        BamChunkReader reader(a.bam, voffset, ex.threads, &pool, (int32_t)rd.targets().size());
         while (true) {
           const int bi = acquire_free();
           if (bi < 0) break;
@@ -649,10 +852,10 @@ int extract_run(const ExtractArgs &a) {
       }
       try {
         const auto d1 = clk::now();
-        ex.stage(b);
+        ex.stage(b, pass1);
         if (pass1 && !have_tail)
-          for (size_t i = 0; i < b.recs.size(); i++)
-            if (b.recs[i].tid < 0) { have_tail = true; tail_voffset = b.chunk.voffset_of(i); break; }
+          for (const auto &tc : b.tid_changes)
+            if (tc.second < 0) { have_tail = true; tail_voffset = b.chunk.voffset_of(tc.first); break; }
         const auto d2 = clk::now();
         ex.t_stage += std::chrono::duration<double>(d2 - d1).count();
         {
@@ -721,9 +924,9 @@ int extract_run(const ExtractArgs &a) {
   std::fprintf(stderr, "[strling] finished extraction\n");
   if (a.verbose) {
     const double total = std::chrono::duration<double>(clk::now() - t_start).count();
-    std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"threads\": %d, \"inflate_s\": %.3f, \"stage_s\": %.3f, \"submit_s\": %.3f, \"gpu_wait_s\": %.3f, \"replay_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
+    std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"threads\": %d, \"inflate_s\": %.3f, \"stage_s\": %.3f, \"submit_s\": %.3f, \"gpu_wait_s\": %.3f, \"replay_s\": %.3f, \"stage_parse_s\": %.3f, \"stage_grow_s\": %.3f, \"stage_pack_s\": %.3f, \"replay_shards\": %d, \"replay_shard_phase_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
                  (unsigned long long)ex.n_reads, (unsigned long long)ex.n_scanned, bf.reads.size(), dt, ex.threads, ex.t_decode, ex.t_stage, ex.t_submit,
-                 ex.t_wait, ex.t_replay, ex.n_reads / std::max(dt, 1e-9), total,
+                 ex.t_wait, ex.t_replay, ex.t_stage_parse, ex.t_stage_grow, ex.t_stage_pack, ex.n_shards, ex.t_replay_shards, ex.n_reads / std::max(dt, 1e-9), total,
                  (unsigned long long)(ex.gpu ? strgpu_launch_count(ex.gpu) : 0));
   }
   for (auto &b : batches) ex.free_batch(b);

@@ -15,7 +15,7 @@ namespace strling {
 
 enum Soft : uint8_t { kLeft = 0, kRight = 1, kBoth = 2, kNone = 3, kNoneRight = 4, kNoneLeft = 5 };  // cluster.nim:14-20
 
-struct Tread {  // cluster.nim:23-32
+struct TreadCore {  // cluster.nim:23-32 without the qname: what the pair arithmetic works on (20 bytes, trivially copyable)
   int32_t tid = 0;
   uint32_t position = 0;
   std::array<char, 6> repeat{{0, 0, 0, 0, 0, 0}};
@@ -24,7 +24,11 @@ struct Tread {  // cluster.nim:23-32
   uint8_t mapping_quality = 0;
   uint8_t repeat_count = 0;
   uint8_t align_length = 0;
+};
+struct Tread : TreadCore {
   std::string qname;
+  Tread() = default;
+  Tread(const TreadCore &c, const char *name, size_t len) : TreadCore(c), qname(name, len) {}
 };
 
 struct Options {  // utils.nim:119-127 (fields used on this path)
@@ -40,7 +44,7 @@ inline int unit_length(const std::array<char, 6> &u) {
 }
 
 // extract.nim:56-58 : the uint8 product wraps (checks are off in the release build)
-inline double p_repeat(const Tread &t) {
+inline double p_repeat(const TreadCore &t) {
   const uint8_t prod = (uint8_t)(t.repeat_count * (uint8_t)unit_length(t.repeat));
   return (double)prod / (double)std::max<uint8_t>(1, t.align_length);
 }
@@ -90,10 +94,10 @@ inline std::array<char, 6> canonical_repeat(const std::array<char, 6> &u) {
   return u;
 }
 
-inline uint32_t half_length(const Tread &t) { return (uint32_t)((double)t.align_length / 2.0 + 0.5); }
+inline uint32_t half_length(const TreadCore &t) { return (uint32_t)((double)t.align_length / 2.0 + 0.5); }
 
 // extract.nim:141-179
-inline bool adjust_by(Tread &A, const Tread &B, const Options &o, uint32_t B_position) {
+inline bool adjust_by(TreadCore &A, const TreadCore &B, const Options &o, uint32_t B_position) {
   if (A.repeat_count == 0) return false;
   const bool a_proper = (A.flag & 0x2) != 0;
   if (B.mapping_quality > o.min_mapq &&
@@ -119,7 +123,7 @@ inline bool adjust_by(Tread &A, const Tread &B, const Options &o, uint32_t B_pos
 }
 
 // extract.nim:182-190
-inline bool unplaced_pair(const Tread &A, const Tread &B, const Options &o) {
+inline bool unplaced_pair(const TreadCore &A, const TreadCore &B, const Options &o) {
   const double pa = p_repeat(A), pb = p_repeat(B);
   if (pa > o.proportion_repeat && pb > o.proportion_repeat) return true;
   if (pa > o.proportion_repeat && B.mapping_quality < o.min_mapq) return true;

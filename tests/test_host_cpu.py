@@ -2,6 +2,7 @@
 distribution, `.bin` codec (also cross-checked with python msgpack), and the per-pair arithmetic
 (adjust_by / unplaced_pair / canonical_repeat, extract.nim:134-190, utils.nim:61-83,304-310)."""
 import os
+import struct
 import subprocess
 
 import numpy as np
@@ -30,8 +31,8 @@ def sim(tmp_path_factory):
     return recs, bam, d
 
 
-def run(cli, *args, stdin=None):
-    r = subprocess.run([cli, *args], input=stdin, capture_output=True, text=True)
+def run(cli, *args, stdin=None, env=None):
+    r = subprocess.run([cli, *args], input=stdin, capture_output=True, text=True, env=dict(os.environ, **env) if env else None)
     assert r.returncode == 0, r.stderr
     return r.stdout
 
@@ -238,8 +239,38 @@ def test_bam_decode_against_an_independent_encoder(cli, tmp_path):
         assert int(f[10]) == (pos + span if span and not flag & 4 else pos + 1), (f, e)
 
 
-@pytest.mark.parametrize("p,q,use_bed,batch", [(0.8, 40, False, 262144), (0.8, 40, True, 1500), (0.7, 20, True, 700), (0.9, 0, False, 333)])
-def test_extract_staging_and_replay_without_the_scan(cli, tmp_path, p, q, use_bed, batch):
+def _awkward_pairs(targets, rng):
+    """Records that exercise the order-dependent corners of Cache.add (extract.nim:60-61,192-248): mates at the SAME position
+    (after_mate then depends on the table), a qname that occurs three and four times (hasKeyOrPut's 'bad read' branch drops the
+    table entry), and second-seen reads whose first-seen mate is missing."""
+    out = []
+    unit = "CAG" * 50
+    for k in range(40):
+        tid, pos = k % 2, 5_000 + 7_000 * k
+        name = f"same{k}"
+        seqs = [unit if k % 3 == 0 else "".join(rng.choice("ACGT") for _ in range(150)), unit if k % 3 == 1 else "".join(rng.choice("ACGT") for _ in range(150))]
+        mapq = [60, 0 if k % 4 == 0 else 60]
+        out.append(bamio.Aln(name, 0x1 | 0x40 | 0x20, tid, pos, mapq[0], [("M", 150)], tid, pos, 0, seqs[0]))
+        out.append(bamio.Aln(name, 0x1 | 0x80 | 0x10, tid, pos, mapq[1], [("S", 40), ("M", 110)] if k % 5 == 0 else [("M", 150)], tid, pos, 0, seqs[1]))
+    for k in range(12):
+        tid, pos = 0, 290_000 + 500 * k
+        name = f"dup{k}"
+        for j in range(3 + k % 2):  # 3 or 4 records of one name, all "first-seen" by position
+            out.append(bamio.Aln(name, 0x1 | 0x40, tid, pos + j, 60, [("M", 150)], tid, pos + 300, 300, unit if j == 1 else "".join(rng.choice("ACGT") for _ in range(150))))
+        out.append(bamio.Aln(name, 0x1 | 0x80 | 0x10, tid, pos + 300, 60, [("M", 100), ("S", 50)], tid, pos, -300, "".join(rng.choice("ACGT") for _ in range(100)) + unit[:50]))
+    for k in range(10):  # the mate never shows up / shows up as a secondary record only
+        out.append(bamio.Aln(f"orphan{k}", 0x1 | 0x80 | 0x10, 1, 150_000 + 10 * k, 60, [("M", 150)], 0, 1_000, 0, unit))
+    return out
+
+
+@pytest.mark.parametrize("p,q,use_bed,batch,env", [
+    (0.8, 40, False, 262144, None), (0.8, 40, True, 1500, None), (0.7, 20, True, 700, None), (0.9, 0, False, 333, None),
+    # the same through the thread pool: parallel inflate / walk / staging and the replay split over qname-hash shards
+    (0.8, 40, True, 1500, {"STRLING_DEBUG_THREADS": "8", "STRLING_DEBUG_SHARDS": "5"}),
+    (0.7, 20, False, 333, {"STRLING_DEBUG_THREADS": "3", "STRLING_DEBUG_SHARDS": "16"}),
+    (0.8, 40, False, 262144, {"STRLING_DEBUG_THREADS": "8", "STRLING_DEBUG_SHARDS": "2"}),
+])
+def test_extract_staging_and_replay_without_the_scan(cli, tmp_path, p, q, use_bed, batch, env):
     """The host half of `strling extract` on the CPU: BAM decode -> which segments a record contributes (genome-STR filter,
     soft clips under both proportion classes, extract.nim:20-40,93-114) -> replay of Cache.add in file order (extract.nim:192-248)
     -> .bin.  `strling debug extract dump` writes the staged segments, the ORACLE scans them here in the test, and
@@ -248,6 +279,10 @@ def test_extract_staging_and_replay_without_the_scan(cli, tmp_path, p, q, use_be
     targets = [("chr1", 400_000), ("chr2", 300_000)]
     loci = [(0, 100_000, 100_150, "CAG"), (0, 250_000, 250_090, "AAAG"), (1, 120_000, 120_060, "ATTCT"), (1, 200_000, 200_040, "A")]
     recs = bamio.simulate_alignments(31, 4000, targets, loci, unmapped_pairs=60, n_frac=0.03)
+    import random
+    extra_recs = _awkward_pairs(targets, random.Random(5))
+    placed = sorted([a for a in recs if a.tid >= 0] + extra_recs, key=lambda a: (a.tid, a.pos))  # stable: equal positions keep their order
+    recs = placed + [a for a in recs if a.tid < 0]
     hdr = bamio.sam_header(targets)
     bam, segs_path, res_path, out = (str(tmp_path / n) for n in ("x.bam", "segs.tsv", "res.bin", "x.bin"))
     bamio.write_bam(bam, hdr, targets, recs)
@@ -259,7 +294,7 @@ def test_extract_staging_and_replay_without_the_scan(cli, tmp_path, p, q, use_be
                 fh.write(f"{targets[tid][0]}\t{s}\t{e}\t{u}\n")
         extra = [bed]
         genome_str = eo.read_bed(bed)
-    run(cli, "debug", "extract", "dump", segs_path, bam, out, repr(p), str(q), str(batch), *extra)
+    run(cli, "debug", "extract", "dump", segs_path, bam, out, repr(p), str(q), str(batch), *extra, env=env)
     classes = [p, p - 0.07, min(p, 0.6)]
     lines = open(segs_path).read().splitlines()
     assert len(lines) > 1000
@@ -269,7 +304,72 @@ def test_extract_staging_and_replay_without_the_scan(cli, tmp_path, p, q, use_be
         unit, count = orc.get_repeat(seq, classes[int(cls)])
         res["unit"][i], res["repeat_count"][i] = unit, count
     res.tofile(res_path)
-    run(cli, "debug", "extract", "replay", res_path, bam, out, repr(p), str(q), str(batch), *extra)
+    run(cli, "debug", "extract", "replay", res_path, bam, out, repr(p), str(q), str(batch), *extra, env=env)
     exp, cache, _ = eo.extract(recs, targets, hdr, p, q, genome_str)
     assert len(cache) > 500
     assert open(out, "rb").read() == exp
+
+
+def test_inflate_decoder_against_zlib(cli):
+    """The repo's whole-block DEFLATE decoder (host/inflate_fast.hpp) against zlib's encoder inside the binary: every level and
+    strategy (stored / fixed / dynamic blocks, multi-block streams, sub-table codes), six kinds of data, all sizes below 64
+    and random sizes up to a BGZF block; output must match byte for byte, nothing outside the output buffer may be touched,
+    and a stream with a flipped bit must never write outside it either."""
+    for seed in (1, 2):
+        out = run(cli, "debug", "inflate-selftest", str(seed), "160")
+        assert out.startswith("ok\t"), out
+
+
+def _decoy_chain(n_fake: int) -> bytes:
+    """n_fake byte strings that each look like a complete, minimal BAM record (block_size 34, refID 0, pos 0, a 2-byte name,
+    no CIGAR, no SEQ) and chain into each other -- planted inside QUAL fields to mislead a record-start guesser."""
+    one = struct.pack("<iiiBBHHHiiii", 34, 0, 0, 2, 0, 4680, 0, 0, 0, -1, -1, 0) + b"A\0"
+    assert len(one) == 38
+    return one * n_fake
+
+
+def test_parallel_record_walk_is_exact_despite_decoys(cli, tmp_path):
+    """BamChunkReader cuts the record walk of a chunk into parts that GUESS their first record start and are then verified
+    against the chain from the chunk's first byte (host/bam.hpp).  Here most QUAL fields hold chains of well-formed fake
+    records, so the guesses of many parts are wrong: the reader must notice (rewalked > 0) and still deliver exactly the
+    records the single-threaded walk delivers (same count, same digest over tid / pos / flag / l_seq / qname)."""
+    import random
+    rng = random.Random(11)
+    targets = [("chr1", 5_000_000)]
+    recs = []
+    for i in range(40_000):
+        l_seq = 380 if i % 3 else 150
+        qual = _decoy_chain(10) if l_seq == 380 else bytes(rng.randrange(0, 94) for _ in range(150))
+        a = bamio.Aln(f"r{i:07d}", 0x1 | 0x40, 0, 100 + 50 * i, 60, [("M", l_seq)], 0, 400 + 50 * i, 450, "".join(rng.choice("ACGT") for _ in range(l_seq)))
+        a.extra["qual"] = qual
+        recs.append(a)
+    bam = str(tmp_path / "decoy.bam")
+    bamio.write_bam(bam, bamio.sam_header(targets), targets, recs)
+    serial = run(cli, "debug", "chunks", bam, "1", "300", "digest").split("\t")
+    par = run(cli, "debug", "chunks", bam, "8", "300", "digest").split("\t")
+    f = lambda row, key: row[row.index(key) + 1].strip()
+    assert f(serial, "records") == f(par, "records") == "40000"
+    assert f(serial, "digest") == f(par, "digest")
+    assert f(serial, "rewalked") == "0" and int(f(par, "rewalked")) > 0
+    # and the record-at-a-time reader (the one `debug bam` uses) agrees on the count
+    assert sum(1 for l in run(cli, "debug", "bam", bam).splitlines() if not l.startswith("@")) == 40000
+
+
+def test_synth_bam_is_a_valid_sorted_bam(cli, tmp_path):
+    """`strling debug synth-bam` (the measurement input of bench.py's cli leg): coordinate-sorted, mates consistent, the
+    no-coordinate pairs at the end, and readable by both readers."""
+    bam = str(tmp_path / "s.bam")
+    run(cli, "debug", "synth-bam", bam, "5000", "9")
+    rows = [l.split("\t") for l in run(cli, "debug", "bam", bam).splitlines() if not l.startswith("@")]
+    assert len(rows) == 10000
+    keys = [(int(r[2]) if int(r[2]) >= 0 else 1 << 30, int(r[3])) for r in rows]
+    assert keys == sorted(keys)
+    by_name = {}
+    for r in rows:
+        by_name.setdefault(r[0], []).append(r)
+    assert all(len(v) == 2 for v in by_name.values())
+    for a, b in by_name.values():
+        assert (a[2], a[3]) == (b[6], b[7]) and (b[2], b[3]) == (a[6], a[7])
+    assert sum(1 for r in rows if int(r[2]) < 0) == 100
+    par = run(cli, "debug", "chunks", bam, "4", "64").split("\t")
+    assert par[par.index("records") + 1] == "10000"
