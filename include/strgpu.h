@@ -30,7 +30,8 @@ typedef enum {
   STRGPU_ERR_TOO_LONG = -4,      /* a segment is longer than STRGPU_MAX_SEGMENT_LEN (or than max_len passed) */
   STRGPU_ERR_BUSY = -5,          /* no free submit slot: wait on an earlier ticket first */
   STRGPU_ERR_TICKET = -6,        /* unknown / already consumed ticket */
-  STRGPU_ERR_OVERFLOW = -7       /* an output capacity was too small */
+  STRGPU_ERR_OVERFLOW = -7,      /* an output capacity was too small */
+  STRGPU_ERR_DATA = -8           /* malformed input data (a BGZF block that does not inflate to its stated size) */
 } strgpu_status;
 
 /* The reference counts k-mers in uint8 tables with overflow checks off (utils.nim:9,113-117,192-195);
@@ -83,6 +84,23 @@ uint64_t strgpu_launch_count(const strgpu_ctx *ctx);
 /* Pinned host memory for submit buffers (optional but needed for copy/compute overlap). */
 int  strgpu_host_alloc(void **ptr, size_t bytes);
 void strgpu_host_free(void *ptr);
+
+/* ---- BGZF inflate (optional front end of the scan) ----------------------------------------------
+ * Stands in for the htslib inflate behind hts-nim's record iterator (`for aln in ibam`, extract.nim:308,326): a batch of
+ * BGZF blocks (SAM specification 4.1) is copied to the device compressed, inflated there -- one block per warp -- and the
+ * inflated bytes are copied back, so the host cores only walk and stage records.  Record boundaries, field extraction and
+ * mate pairing stay with the caller.  Synchronous; runs on its own stream beside scans in flight on the same ctx. */
+typedef struct {
+  uint64_t in_off;     /* offset in `comp` of the block's raw DEFLATE payload (after the gzip header + extra field) */
+  uint32_t csize;      /* payload bytes (BSIZE + 1 - XLEN - 20) */
+  uint32_t isize;      /* inflated size from the block footer; 0: nothing to do */
+  uint64_t out_off;    /* where in `out` the block's isize bytes go; blocks must not overlap */
+} strgpu_bgzf_block;   /* 24 bytes */
+/* comp / out: host buffers (pinned memory from strgpu_host_alloc makes the copies asynchronous DMA).  Only
+ * [min out_off, max out_off + isize) of `out` is written.  STRGPU_ERR_DATA: a block is not a valid DEFLATE stream of
+ * exactly isize bytes (strgpu_last_error names it). */
+int strgpu_inflate_bgzf(strgpu_ctx *ctx, const uint8_t *comp, size_t comp_bytes, const strgpu_bgzf_block *blocks, uint32_t n_blocks,
+                        uint8_t *out, size_t out_bytes);
 
 /* ---- scan: get_repeat(read, counts, repeat_count, opts) -- utils.nim:236, called from
  * extract.nim:40 (whole read), extract.nim:114 (soft clip), genome_strs.nim:74 (reference window) ---- */

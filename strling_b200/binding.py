@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libstrgpu.so")
 
 SEGMENT_DTYPE = np.dtype([("base_off", "<u4"), ("len", "<u2"), ("pclass", "u1"), ("flags", "u1")])
 REPEAT_DTYPE = np.dtype([("unit", "S6"), ("repeat_count", "<u2")])
+BGZF_BLOCK_DTYPE = np.dtype([("in_off", "<u8"), ("csize", "<u4"), ("isize", "<u4"), ("out_off", "<u8")])
 TREAD_DTYPE = np.dtype(
     [("tid", "<i4"), ("position", "<u4"), ("repeat", "S6"), ("flag", "<u2"), ("split", "u1"),
      ("mapq", "u1"), ("repeat_count", "u1"), ("align_length", "u1"), ("sample", "<i4")]
@@ -91,6 +92,8 @@ def load_library():
     L.strgpu_cluster_sharded_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, vp, vp]
     L.strgpu_comm_status.argtypes = [vp, vp]
     L.strgpu_cluster_sharded.argtypes = [vp, vp, u32, u32, vp, vp, u32, C.POINTER(u32)]
+    L.strgpu_inflate_bgzf.argtypes = [vp, vp, C.c_size_t, vp, u32, vp, C.c_size_t]
+    L.strgpu_inflate_bgzf.restype = i32
     _lib = L
     return L
 
@@ -185,6 +188,16 @@ class StrGpu:
     def set_proportions(self, ps):
         arr = (C.c_double * len(ps))(*ps)
         self._check(self.L.strgpu_set_proportions(self.h, arr, len(ps)))
+
+    # ---- BGZF inflate -------------------------------------------------------------------------
+    def inflate_bgzf(self, comp: np.ndarray, blocks: np.ndarray, out_bytes: int) -> np.ndarray:
+        """Inflates BGZF block payloads on the device (strgpu_inflate_bgzf).  comp: uint8 array holding the raw DEFLATE payloads,
+        blocks: BGZF_BLOCK_DTYPE array (in_off, csize, isize, out_off); returns the uint8 output buffer of out_bytes bytes."""
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        blocks = np.ascontiguousarray(blocks, dtype=BGZF_BLOCK_DTYPE)
+        out = np.zeros(out_bytes, dtype=np.uint8)
+        self._check(self.L.strgpu_inflate_bgzf(self.h, comp.ctypes.data, comp.nbytes, blocks.ctypes.data, len(blocks), out.ctypes.data, out.nbytes))
+        return out
 
     # ---- scan ---------------------------------------------------------------------------------
     def scan(self, seq2: np.ndarray, n_bases: int, nmask, segs: np.ndarray, max_len: int | None = None) -> np.ndarray:

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstrgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_SOURCES = ["api.cu", "scan_kernels.cu", "cluster_kernels.cu", "comm.cu"]
+CUDA_SOURCES = ["api.cu", "scan_kernels.cu", "cluster_kernels.cu", "comm.cu", "decode_kernels.cu"]
 CXX_SOURCES = ["pack.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -30,6 +30,7 @@ def _stale() -> bool:
     t = os.path.getmtime(LIB)
     deps = _sources() + [os.path.join(ROOT, "include", "strgpu.h")]
     deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
+    deps += [os.path.join(HERE, "host", "inflate_fast.hpp")]   # compiled into decode_kernels.cu as the device-side decoder
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -42,6 +42,7 @@ const char *strgpu_error_string(int status) {
     case STRGPU_ERR_BUSY: return "no free submit slot";
     case STRGPU_ERR_TICKET: return "bad ticket";
     case STRGPU_ERR_OVERFLOW: return "output capacity too small";
+    case STRGPU_ERR_DATA: return "malformed input data";
     default: return "unknown status";
   }
 }
@@ -109,6 +110,7 @@ void strgpu_destroy(strgpu_ctx *ctx) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   if (ctx->cluster_graph.exec) cudaGraphExecDestroy(ctx->cluster_graph.exec);
+  decode_release(ctx);
   strgpu::free_workspace(ctx->cluster_ws);
   if (ctx->cl_in.p) cudaFree(ctx->cl_in.p);
   if (ctx->cl_out.p) cudaFree(ctx->cl_out.p);

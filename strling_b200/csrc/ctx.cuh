@@ -30,6 +30,7 @@ struct Slot {
 };
 
 struct Comm;  // comm.cu: the NCCL communicator of a sharded job and its exchange buffers
+struct Decode;  // decode_kernels.cu: stream and buffers of strgpu_inflate_bgzf
 
 // The cluster path is ~100 short kernels; a caller that repeats a call with the same arguments (a pipeline clustering batch
 // after batch into the same buffers) gets it replayed as ONE CUDA graph launch: first call direct (it sizes the workspace),
@@ -66,6 +67,7 @@ struct strgpu_ctx {
   std::mutex mu;
   std::mutex err_mu;
   strgpu_internal::Comm *comm = nullptr;
+  strgpu_internal::Decode *decode = nullptr;
   strgpu_internal::GraphSlot cluster_graph;
 };
 
@@ -100,6 +102,7 @@ inline int ensure(strgpu_ctx *ctx, DevBuf &b, size_t bytes) {
 }
 
 void comm_release(strgpu_ctx *ctx);   // comm.cu
+void decode_release(strgpu_ctx *ctx); // decode_kernels.cu
 
 inline uint64_t hash_bytes(const void *p, size_t n, uint64_t h = 0xcbf29ce484222325ull) {
   const unsigned char *b = static_cast<const unsigned char *>(p);

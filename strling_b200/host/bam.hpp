@@ -10,6 +10,7 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 
 #include "inflate_fast.hpp"
@@ -147,6 +148,7 @@ class BamReader {
     spans_.clear();
     cur_ = 0;
     eof_ = false;
+    fill_blocks_ = 16;
     if (std::fseek(fh_, (long)(voffset >> 16), SEEK_SET) != 0) throw std::runtime_error("seek failed");
     fpos_ = voffset >> 16;
     fill();
@@ -198,7 +200,8 @@ class BamReader {
     std::vector<Blk> blks;
     comp_.clear();
     size_t total_out = 0;
-    constexpr size_t kBatch = 1024;
+    const size_t kBatch = fill_blocks_;   // small at first (the header is usually all a caller wants), then up to 1024
+    fill_blocks_ = std::min<size_t>(fill_blocks_ * 4, 1024);
     while (blks.size() < kBatch) {
       uint8_t hdr[18];
       const size_t got = std::fread(hdr, 1, 18, fh_);
@@ -309,6 +312,7 @@ class BamReader {
   uint64_t fpos_ = 0;
   bool eof_ = false;
   std::vector<uint8_t> data_, comp_;
+  size_t fill_blocks_ = 16;
   std::vector<Span> spans_;
   size_t cur_ = 0;
   std::string header_text_;
@@ -324,20 +328,25 @@ class BamReader {
 struct RawBuffer {  // uninitialised, growable byte buffer (std::vector would zero-fill hundreds of MB per chunk)
   uint8_t *p = nullptr;
   size_t size = 0, cap = 0;
+  // optional allocator (pinned host memory when the GPU inflates into the buffer); contents are NOT kept across a growth
+  void *(*alloc_fn)(size_t) = nullptr;
+  void (*free_fn)(void *) = nullptr;
   RawBuffer() = default;
   RawBuffer(const RawBuffer &) = delete;
   RawBuffer &operator=(const RawBuffer &) = delete;
-  RawBuffer(RawBuffer &&o) noexcept : p(o.p), size(o.size), cap(o.cap) { o.p = nullptr; o.size = o.cap = 0; }
-  RawBuffer &operator=(RawBuffer &&o) noexcept {
-    if (this != &o) { std::free(p); p = o.p; size = o.size; cap = o.cap; o.p = nullptr; o.size = o.cap = 0; }
-    return *this;
+  ~RawBuffer() { release(); }
+  void release() {
+    if (p) { if (free_fn) free_fn(p); else std::free(p); }
+    p = nullptr;
+    size = cap = 0;
   }
-  ~RawBuffer() { std::free(p); }
+  void set_allocator(void *(*a)(size_t), void (*f)(void *)) { release(); alloc_fn = a; free_fn = f; }
   void resize(size_t n) {
     if (n > cap) {
       const size_t nc = n + n / 8 + 4096;
-      uint8_t *q = static_cast<uint8_t *>(std::realloc(p, nc));
+      uint8_t *q = static_cast<uint8_t *>(alloc_fn ? alloc_fn(nc) : std::malloc(nc));
       if (!q) throw std::runtime_error("out of memory");
+      if (p) { if (free_fn) free_fn(p); else std::free(p); }
       p = q;
       cap = nc;
     }
@@ -345,6 +354,13 @@ struct RawBuffer {  // uninitialised, growable byte buffer (std::vector would ze
   }
   uint8_t *data() { return p; }
   const uint8_t *data() const { return p; }
+};
+
+// a BGZF block of a chunk: the same 24-byte layout as strgpu_bgzf_block (include/strgpu.h)
+struct BgzfBlockRef {
+  uint64_t in_off;   // offset of the raw DEFLATE payload in the file
+  uint32_t csize, isize;
+  uint64_t out_off;  // offset of the inflated bytes in the chunk's buffer
 };
 
 struct BamChunk {
@@ -415,6 +431,10 @@ class BamChunkReader {
   BamChunkReader(const BamChunkReader &) = delete;
   BamChunkReader &operator=(const BamChunkReader &) = delete;
 
+  // When set, inflates the blocks of a chunk instead of the host threads (`strling extract --gpu-inflate`): file = the
+  // mapped BAM, every block's isize bytes go to out + out_off; must throw on failure.
+  std::function<void(const uint8_t *file, size_t file_size, const BgzfBlockRef *blocks, size_t n_blocks, uint8_t *out, size_t out_bytes)> inflate_hook;
+
   double t_read = 0, t_alloc = 0, t_inflate = 0, t_walk = 0;  // seconds spent per phase (diagnostics)
   size_t n_rewalked = 0;                                      // parts of the parallel walk whose guessed start was wrong
 
@@ -475,7 +495,13 @@ class BamChunkReader {
     }
     const auto q2 = clk::now();
     uint8_t *out = c.data.data();
-    pool_->run(blks.size(), [&](size_t i) { inflate_bgzf_block(map_ + blks[i].in_off, blks[i].csize, out + outoff[i], blks[i].isize); });
+    if (inflate_hook && !blks.empty()) {
+      std::vector<BgzfBlockRef> refs(blks.size());
+      for (size_t i = 0; i < blks.size(); i++) refs[i] = BgzfBlockRef{blks[i].in_off, blks[i].csize, blks[i].isize, (uint64_t)outoff[i]};
+      inflate_hook(map_, file_size_, refs.data(), refs.size(), out, c.data.size);
+    } else {
+      pool_->run(blks.size(), [&](size_t i) { inflate_bgzf_block(map_ + blks[i].in_off, blks[i].csize, out + outoff[i], blks[i].isize); });
+    }
     const auto q3 = clk::now();
     for (size_t i = 0; i < blks.size(); i++)
       if (blks[i].isize) c.spans.push_back(BamChunk::Span{(uint32_t)outoff[i], blks[i].fpos, 0});

@@ -567,11 +567,12 @@ int debug_genotype(int argc, char **argv) {
 int extract_main(int argc, char **argv) {
   static const char *usage =
       "strling extract [-f fasta] [-g genome-repeats] [-p proportion-repeat=0.8] [-q min-mapq=40] [-v] [--device N] [--threads N]\n"
-      "                [--batch-reads N] [--replay-shards N] <bam> <bin>\n"
+      "                [--batch-reads N] [--replay-shards N] [--gpu-inflate] <bam> <bin>\n"
+      "  --gpu-inflate: the BGZF blocks are inflated on the GPU instead of the host threads (same .bin)\n"
       "  <bam> must be coordinate-sorted with the no-coordinate reads at the end (as `samtools sort` writes it).  Reads longer\n"
       "  than 510 bases are refused: beyond that the reference's uint8 k-mer count tables wrap (utils.nim:113-117).\n";
   Args a = parse(argc, argv, {{"-f", "--fasta", true}, {"-g", "--genome-repeats", true}, {"-p", "--proportion-repeat", true}, {"-q", "--min-mapq", true},
-                              {"-v", "--verbose", false}, {"", "--device", true}, {"", "--threads", true}, {"", "--batch-reads", true}, {"", "--replay-shards", true}},
+                              {"-v", "--verbose", false}, {"", "--device", true}, {"", "--threads", true}, {"", "--batch-reads", true}, {"", "--replay-shards", true}, {"", "--gpu-inflate", false}},
                  usage);
   if (a.pos.size() != 2) { std::fputs(usage, stdout); return a.pos.empty() ? 0 : 1; }
   ExtractArgs e;
@@ -584,6 +585,7 @@ int extract_main(int argc, char **argv) {
   e.threads = std::stoi(a.get("--threads", "0"));
   e.batch_reads = (uint32_t)std::stoul(a.get("--batch-reads", "524288"));
   e.replay_shards = std::stoi(a.get("--replay-shards", "0"));
+  e.gpu_inflate = a.has("--gpu-inflate");
   e.bam = a.pos[0];
   e.bin = a.pos[1];
   return extract_run(e);

@@ -16,6 +16,7 @@ struct ExtractArgs {
   int threads = 0;
   uint32_t batch_reads = 1u << 19;
   int replay_shards = 0;          // 0: a quarter of the threads
+  bool gpu_inflate = false;       // BGZF blocks are inflated on the GPU (strgpu_inflate_bgzf) instead of the host threads
   // `strling debug extract` only (CPU-side checks of the staging and replay logic; never set by `strling extract`):
   // dump: write every staged segment ("pclass<TAB>bases", submission order) instead of scanning it, no .bin is written;
   // results: read the scan results (8-byte strgpu_repeat records in that same order) from a file instead of the GPU

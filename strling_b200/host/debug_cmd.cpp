@@ -64,7 +64,10 @@ int debug_main(int argc, char **argv) {
     if (argc >= 9) e.genome_repeats = argv[8];
     e.threads = 2;
     if (const char *t = std::getenv("STRLING_DEBUG_THREADS")) { e.threads = std::atoi(t); e.verbose = true; }
-    if (const char *t = std::getenv("STRLING_DEBUG_SHARDS")) e.replay_shards = std::atoi(t);  // stage timings of the host side
+    if (const char *t = std::getenv("STRLING_DEBUG_SHARDS")) e.replay_shards = std::atoi(t);
+    // the --gpu-inflate plumbing (compressed bytes staged contiguously, rebased block descriptors) with the blocks decoded on the
+    // host from that staging buffer: everything but the CUDA calls of strgpu_inflate_bgzf
+    if (std::getenv("STRLING_DEBUG_STAGED_INFLATE")) e.gpu_inflate = true;  // stage timings of the host side
     return extract_run(e);
   }
   if (what == "synth-bam" && argc >= 3)  // strling debug synth-bam <out.bam> <n_pairs> [seed] [deflate level] [threads]

@@ -238,6 +238,50 @@ struct Shard {
   uint64_t tag = 0;
 };
 
+// `--gpu-inflate`: the compressed bytes of a chunk's blocks (one contiguous stretch of the file) are copied into a pinned
+// staging buffer, the block descriptors rebased to it, and strgpu_inflate_bgzf inflates them on the device into the chunk's
+// (pinned) buffer.  gpu == nullptr (`strling debug extract` with STRLING_DEBUG_STAGED_INFLATE): the same staging and
+// descriptors, decoded by the host threads -- the CPU check of this plumbing.
+struct StagedInflater {
+  strgpu_ctx *gpu = nullptr;
+  Pool *pool = nullptr;
+  uint8_t *staging = nullptr;
+  size_t cap = 0;
+  ~StagedInflater() { release(); }
+  void release() {
+    if (staging) { if (gpu) strgpu_host_free(staging); else std::free(staging); }
+    staging = nullptr;
+    cap = 0;
+  }
+  void operator()(const uint8_t *file, size_t file_size, const BgzfBlockRef *blocks, size_t n, uint8_t *out, size_t out_bytes) {
+    const uint64_t lo = blocks[0].in_off;
+    const uint64_t hi = std::min<uint64_t>(file_size, blocks[n - 1].in_off + blocks[n - 1].csize + 8);  // + the last block's footer
+    const size_t bytes = (size_t)(hi - lo);
+    if (bytes + 16 > cap) {
+      release();
+      cap = bytes + bytes / 4 + 4096;
+      if (gpu) {
+        void *p = nullptr;
+        if (strgpu_host_alloc(&p, cap) != STRGPU_OK) throw std::runtime_error("[strling] gpu: host_alloc failed");
+        staging = static_cast<uint8_t *>(p);
+      } else {
+        staging = static_cast<uint8_t *>(std::malloc(cap));
+        if (!staging) throw std::runtime_error("[strling] out of memory");
+      }
+    }
+    pool->ranges(bytes, (bytes + (1u << 20) - 1) >> 20, [&](size_t a, size_t e, size_t) { std::memcpy(staging + a, file + lo + a, e - a); });
+    std::memset(staging + bytes, 0, 16);
+    std::vector<strgpu_bgzf_block> d(n);
+    for (size_t i = 0; i < n; i++) d[i] = strgpu_bgzf_block{blocks[i].in_off - lo, blocks[i].csize, blocks[i].isize, blocks[i].out_off};
+    if (gpu) {
+      if (strgpu_inflate_bgzf(gpu, staging, bytes, d.data(), (uint32_t)n, out, out_bytes) != STRGPU_OK)
+        throw std::runtime_error(std::string("[strling] gpu: inflate_bgzf: ") + strgpu_last_error(gpu));
+    } else {
+      pool->run(n, [&](size_t i) { inflate_bgzf_block(staging + d[i].in_off, d[i].csize, out + d[i].out_off, d[i].isize); });
+    }
+  }
+};
+
 struct Extractor {
   strgpu_ctx *gpu = nullptr;
   Options opts;
@@ -622,25 +666,45 @@ struct Extractor {
 // utils.nim:86-111 with n_reads = 2_000_000, skip_reads = 100_000 (extract.nim:273, call.nim:76)
 std::array<uint32_t, 4096> fragment_length_distribution(const std::string &bam, int threads) {
   std::array<uint32_t, 4096> frag{};
-  BamReader rd(bam, threads);
-  BamRecord r;
+  uint64_t first;
+  int32_t n_ref;
+  {
+    BamReader hdr(bam, 1);
+    first = hdr.tell();
+    n_ref = (int32_t)hdr.targets().size();
+  }
+  BamChunkReader rd(bam, first, threads, nullptr, n_ref);  // blocks inflated in parallel; the records are looked at in file order
+  BamChunk c;
   int64_t i = -1, counted = 0;
   std::vector<int32_t> skipped;
-  while (rd.next(r)) {
-    i++;
-    if (!(r.flag & 0x2)) continue;
-    if (r.flag & (0x800 | 0x100)) continue;
-    if (r.isize < 0 || r.isize > 4095) continue;
-    if (i < 100000) { skipped.push_back(r.isize); continue; }
-    skipped.clear();
-    frag[(size_t)r.isize]++;
-    if (++counted > 2000000) break;
+  bool done = false;
+  size_t blocks = 64;
+  while (!done && rd.next(c, blocks)) {
+    blocks = std::min<size_t>(blocks * 4, 2048);
+    const uint8_t *data = c.data.data();
+    const size_t n = c.n_records();
+    for (size_t k = 0; k < n; k++) {
+      if (k + 8 < n) __builtin_prefetch(data + c.rec_off[k + 8]);
+      const uint8_t *p = data + c.rec_off[k] + 4;
+      uint16_t flag;
+      int32_t isize;
+      std::memcpy(&flag, p + 14, 2);
+      std::memcpy(&isize, p + 28, 4);
+      i++;
+      if (!(flag & 0x2)) continue;
+      if (flag & (0x800 | 0x100)) continue;
+      if (isize < 0 || isize > 4095) continue;
+      if (i < 100000) { skipped.push_back(isize); continue; }
+      skipped.clear();
+      frag[(size_t)isize]++;
+      if (++counted > 2000000) { done = true; break; }
+    }
   }
   uint64_t sum = 0;
-  for (uint32_t c : frag) sum += c;
+  for (uint32_t v : frag) sum += v;
   if (sum == 0) {
     std::fprintf(stderr, "using first reads in fragment_length_distribution calculation as there were not enough\n");
-    for (int32_t s : skipped) frag[(size_t)s]++;
+    for (int32_t v : skipped) frag[(size_t)v]++;
   }
   return frag;
 }
@@ -723,8 +787,17 @@ int extract_run(const ExtractArgs &a) {
   const uint64_t first_voffset = rd.tell();
   constexpr int kBatches = STRGPU_SLOTS + 1;  // one being inflated, one being staged, up to two on the GPU / in replay
   Batch batches[kBatches];
-  for (auto &b : batches) ex.alloc_batch(b, (uint64_t)a.batch_reads * 160 + 4096, (uint32_t)std::min<uint64_t>((uint64_t)a.batch_reads * 2 + 64, 0xfffffff0u));
-  const size_t blocks_per_chunk = std::max<size_t>(16, (size_t)a.batch_reads / 200);  // ~64 KiB blocks of ~300-byte records
+  StagedInflater staged;
+  staged.gpu = ex.gpu;
+  staged.pool = &pool;
+  if (a.gpu_inflate && ex.gpu)  // the device copies the inflated records straight into the chunk buffers: pinned memory
+    for (auto &b : batches)
+      b.chunk.data.set_allocator([](size_t n) -> void * { void *p = nullptr; return strgpu_host_alloc(&p, n) == STRGPU_OK ? p : nullptr; },
+                                 [](void *p) { strgpu_host_free(p); });
+  // a chunk is a number of ~64 KiB BGZF blocks (~220 records of a 150-bp library each); the pinned buffers start out with
+  // room for a quarter more than that and grow should a file pack more reads into its blocks
+  const size_t blocks_per_chunk = std::max<size_t>(16, (size_t)a.batch_reads / 220);
+  for (auto &b : batches) ex.alloc_batch(b, (uint64_t)a.batch_reads * 200 + 4096, (uint32_t)std::min<uint64_t>((uint64_t)a.batch_reads * 2 + 64, 0xfffffff0u));
 
   std::fprintf(stderr, "[strling] collecting str-like reads\n");
   const auto t0 = clk::now();
@@ -813,6 +886,10 @@ int extract_run(const ExtractArgs &a) {
     std::thread reader_thread([&]() {
       try {
         BamChunkReader reader(a.bam, voffset, ex.threads, &pool, (int32_t)rd.targets().size());
+        if (a.gpu_inflate)
+          reader.inflate_hook = [&](const uint8_t *file, size_t file_size, const BgzfBlockRef *blocks, size_t n, uint8_t *out, size_t out_bytes) {
+            staged(file, file_size, blocks, n, out, out_bytes);
+          };
         while (true) {
           const int bi = acquire_free();
           if (bi < 0) break;
@@ -924,8 +1001,8 @@ int extract_run(const ExtractArgs &a) {
   std::fprintf(stderr, "[strling] finished extraction\n");
   if (a.verbose) {
     const double total = std::chrono::duration<double>(clk::now() - t_start).count();
-    std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"threads\": %d, \"inflate_s\": %.3f, \"stage_s\": %.3f, \"submit_s\": %.3f, \"gpu_wait_s\": %.3f, \"replay_s\": %.3f, \"stage_parse_s\": %.3f, \"stage_grow_s\": %.3f, \"stage_pack_s\": %.3f, \"replay_shards\": %d, \"replay_shard_phase_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
-                 (unsigned long long)ex.n_reads, (unsigned long long)ex.n_scanned, bf.reads.size(), dt, ex.threads, ex.t_decode, ex.t_stage, ex.t_submit,
+    std::fprintf(stderr, "[strling] perf: {\"reads\": %llu, \"segments_scanned\": %llu, \"str_reads\": %zu, \"scan_pass_s\": %.3f, \"threads\": %d, \"gpu_inflate\": %s, \"inflate_s\": %.3f, \"stage_s\": %.3f, \"submit_s\": %.3f, \"gpu_wait_s\": %.3f, \"replay_s\": %.3f, \"stage_parse_s\": %.3f, \"stage_grow_s\": %.3f, \"stage_pack_s\": %.3f, \"replay_shards\": %d, \"replay_shard_phase_s\": %.3f, \"reads_per_s\": %.1f, \"total_s\": %.3f, \"gpu_launches\": %llu}\n",
+                 (unsigned long long)ex.n_reads, (unsigned long long)ex.n_scanned, bf.reads.size(), dt, ex.threads, a.gpu_inflate ? "true" : "false", ex.t_decode, ex.t_stage, ex.t_submit,
                  ex.t_wait, ex.t_replay, ex.t_stage_parse, ex.t_stage_grow, ex.t_stage_pack, ex.n_shards, ex.t_replay_shards, ex.n_reads / std::max(dt, 1e-9), total,
                  (unsigned long long)(ex.gpu ? strgpu_launch_count(ex.gpu) : 0));
   }

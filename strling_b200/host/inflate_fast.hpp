@@ -13,6 +13,7 @@
 
 #if defined(__CUDACC__)
 #define STRLING_HD __host__ __device__
+#define STRLING_INFLATE_NO_PAIRS 1   // the device build keeps its tables small (shared memory): no literal-pair entries
 #else
 #define STRLING_HD
 #endif
@@ -34,7 +35,9 @@ struct Tables {
   uint8_t lens[320];       // litlen + distance code lengths of the current dynamic block
   uint16_t sorted[288];    // scratch of build()
   uint8_t sub_bits[1 << kLitBits];
+#if !defined(STRLING_INFLATE_NO_PAIRS)
   uint32_t single[1 << kLitBits];  // scratch of build(): the main table before literal pairs are merged
+#endif
   bool fixed_built;
 };
 
@@ -130,7 +133,7 @@ STRLING_HD inline bool build(Tables &T, uint32_t *table, int table_bits, int cap
   }
   }
   (void)n_codes;
-#if !defined(__CUDA_ARCH__)
+#if !defined(STRLING_INFLATE_NO_PAIRS)
   if (kind == 0) {  // literal pairs: when the bits behind a short literal code decode to another literal inside the same index
     for (int i = 0; i < main_size; i++) T.single[i] = table[i];
     for (int i = 0; i < main_size; i++) {

@@ -23,6 +23,11 @@ type
     unit*: array[6, char]
     repeat_count*: uint16
 
+  StrGpuBgzfBlock* {.bycopy.} = object ## strgpu_bgzf_block: one BGZF block of a batch handed to strgpu_inflate_bgzf
+    in_off*: uint64
+    csize*, isize*: uint32
+    out_off*: uint64
+
   StrGpuTread* {.bycopy.} = object     ## strgpu_tread == cluster.tread with qname -> sample
     tid*: int32
     position*: uint32
@@ -103,6 +108,8 @@ proc strgpu_cluster_sharded_device*(ctx: StrGpuCtx, d_treads: pointer, n, max_n,
 proc strgpu_comm_status*(ctx: StrGpuCtx, cuda_stream: pointer): cint
 proc strgpu_cluster_sharded*(ctx: StrGpuCtx, treads: ptr StrGpuTread, n, max_n: uint32, params: ptr StrGpuClusterParams,
                              res: ptr StrGpuBounds, cap: uint32, n_out: ptr uint32): cint
+proc strgpu_inflate_bgzf*(ctx: StrGpuCtx, comp: ptr uint8, comp_bytes: csize_t, blocks: ptr StrGpuBgzfBlock, n_blocks: uint32,
+                          res: ptr uint8, out_bytes: csize_t): cint
 {.pop.}
 
 template check*(ctx: StrGpuCtx, rc: cint) =

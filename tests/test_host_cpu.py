@@ -269,6 +269,9 @@ def _awkward_pairs(targets, rng):
     (0.8, 40, True, 1500, {"STRLING_DEBUG_THREADS": "8", "STRLING_DEBUG_SHARDS": "5"}),
     (0.7, 20, False, 333, {"STRLING_DEBUG_THREADS": "3", "STRLING_DEBUG_SHARDS": "16"}),
     (0.8, 40, False, 262144, {"STRLING_DEBUG_THREADS": "8", "STRLING_DEBUG_SHARDS": "2"}),
+    # the --gpu-inflate plumbing (compressed bytes staged contiguously, rebased descriptors, inflate hook of the chunk reader) with
+    # the blocks decoded on the host from the staging buffer
+    (0.8, 40, True, 1500, {"STRLING_DEBUG_THREADS": "4", "STRLING_DEBUG_STAGED_INFLATE": "1"}),
 ])
 def test_extract_staging_and_replay_without_the_scan(cli, tmp_path, p, q, use_bed, batch, env):
     """The host half of `strling extract` on the CPU: BAM decode -> which segments a record contributes (genome-STR filter,
