@@ -602,6 +602,25 @@ def cli_leg(local: int, n_pairs: int = 3_000_000):
                       if k in best},
            "command": "strling extract -v <bam> <bin> (best of 3)",
            "bound": "host: BGZF inflate (the repo's own decoder) + BAM decode + staging + sharded mate-pairing replay on the CPU cores; the GPU waits"}
+    # the opt-in variant that inflates the BGZF blocks on the GPU: must write the same .bin; reported beside the default, never instead
+    # of it (a failure here is recorded, it does not fail the bench line)
+    try:
+        ref_bytes = open(out, "rb").read()
+        out2 = os.path.join(d, "bench_gpu_inflate.bin")
+        r = sp.run([cli, "extract", "-v", "--gpu-inflate", "--device", str(local), bam, out2], capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:
+            res["gpu_inflate"] = {"ok": False, "error": r.stderr[-300:]}
+        else:
+            perf = json.loads(re.search(r"perf: (\{.*\})", r.stderr).group(1))
+            res["gpu_inflate"] = {"ok": True, "bin_identical": open(out2, "rb").read() == ref_bytes, "reads_per_s": perf["reads_per_s"],
+                                  "inflate_s": perf["inflate_s"], "scan_pass_s": perf["scan_pass_s"],
+                                  "command": "strling extract -v --gpu-inflate <bam> <bin> (one run)"}
+        try:
+            os.remove(out2)
+        except OSError:
+            pass
+    except Exception as e:  # noqa: BLE001
+        res["gpu_inflate"] = {"ok": False, "error": repr(e)[:300]}
     for f in (bam, out):
         try:
             os.remove(f)

@@ -11,11 +11,14 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <mutex>
 
 #include "../host/inflate_fast.hpp"
 #include "ctx.cuh"
 
 static_assert(sizeof(strgpu_bgzf_block) == 24, "strgpu_bgzf_block layout");
+constexpr int kDefaultInflateKernel = 1;
 
 namespace strgpu_internal {
 
@@ -38,6 +41,71 @@ __global__ void __launch_bounds__(32) inflate_bgzf_blocks(const uint8_t *__restr
   tables.fixed_built = false;
   const int rc = strling::infl::inflate_block(tables, comp + blk.in_off, blk.csize, out + (blk.out_off - out_base), blk.isize);
   if (rc != strling::infl::kOk && atomicCAS(&status[0], 0, (int)b + 1) == 0) status[1] = rc;
+}
+
+// v2: the block's whole output (<= 64 KiB) is assembled in shared memory and the copies are done by the warp.  Lane 0 runs the
+// decoder as a command stream (infl::Stream: literals go straight into the window, a match or a stored block comes back as a
+// command), the command is broadcast, and the 32 lanes copy its bytes -- a match reads what the warp wrote a moment ago, which
+// in v1 is a dependent round trip to L2 per BYTE on a single lane and here is a shared-memory access per 32 bytes.  The finished
+// window leaves for global memory in whole sectors.  64 KiB + 15 KiB of tables per CTA: two blocks per SM, 296 in flight.
+// kStageInput (kernel 3): the compressed block is first copied into shared memory by the whole warp (coalesced), when it fits
+// kStagedInputBytes -- measured with kernel 2, the decoder otherwise spends most of its time waiting for the eight single-byte
+// global loads of every bit-buffer refill, a latency nothing hides with one active lane per SM sub-partition.  64 KiB window +
+// 15 KiB tables + 32 KiB input = 111 KiB per CTA: still two blocks per SM.  A block whose payload is larger (nearly
+// incompressible data) is read from global memory as in kernel 2.
+constexpr uint32_t kWindowBytes = 65536;
+constexpr uint32_t kStagedInputBytes = 32768;
+constexpr size_t kV2Smem = kWindowBytes + sizeof(strling::infl::Tables);
+constexpr size_t kV3Smem = kV2Smem + 16 + kStagedInputBytes;
+
+template <bool kStageInput>
+__global__ void __launch_bounds__(32) inflate_bgzf_blocks_v2(const uint8_t *__restrict__ comp, const strgpu_bgzf_block *__restrict__ blocks, uint32_t n_blocks,
+                                                             uint8_t *__restrict__ out, uint64_t out_base, int *status) {
+  using namespace strling::infl;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t *window = smem;
+  Tables &tables = *reinterpret_cast<Tables *>(smem + kWindowBytes);
+  const uint32_t lane = threadIdx.x;
+  const uint32_t b = blockIdx.x;
+  if (b >= n_blocks) return;
+  const strgpu_bgzf_block blk = blocks[b];
+  if (blk.isize == 0) return;                 // the same for every lane
+  const uint8_t *in = comp + blk.in_off;
+  if (kStageInput && blk.csize + 8u <= kStagedInputBytes) {
+    uint8_t *staged = smem + ((kV2Smem + 15) & ~(size_t)15);
+    const uint32_t n_in = blk.csize + 8u;   // the decoder may read 8 bytes past the stream (the buffer behind comp is padded)
+    for (uint32_t i = lane; i < n_in; i += 32) staged[i] = in[i];
+    __syncwarp();
+    in = staged;
+  }
+  Stream s;
+  if (lane == 0) {
+    tables.fixed_built = false;
+    s.init(in, blk.csize, blk.isize);
+  }
+  int rc = 0;
+  while (true) {
+    Command c{0, 0, 0, 0};
+    if (lane == 0) c = s.next(tables, window);
+    c.type = __shfl_sync(0xffffffffu, c.type, 0);
+    c.o = __shfl_sync(0xffffffffu, c.o, 0);
+    c.a = __shfl_sync(0xffffffffu, c.a, 0);
+    c.b = __shfl_sync(0xffffffffu, c.b, 0);
+    __syncwarp();                             // lane 0's literal stores are visible to the lanes that copy from them
+    if (c.type <= 0) { rc = c.type; break; }
+    if (c.type == kCmdMatch) {
+      for (uint32_t i = lane; i < c.b; i += 32) window[c.o + i] = window[match_source(c, i)];
+    } else {
+      for (uint32_t i = lane; i < c.b; i += 32) window[c.o + i] = in[c.a + i];
+    }
+    __syncwarp();                             // ... and the copied bytes to lane 0 and to the next command
+  }
+  if (rc != 0) {
+    if (lane == 0 && atomicCAS(&status[0], 0, (int)b + 1) == 0) status[1] = rc;
+    return;
+  }
+  uint8_t *dst = out + (blk.out_off - out_base);
+  for (uint32_t i = lane; i < blk.isize; i += 32) dst[i] = window[i];
 }
 
 void decode_release(strgpu_ctx *ctx) {
@@ -96,8 +164,25 @@ extern "C" int strgpu_inflate_bgzf(strgpu_ctx *ctx, const uint8_t *comp, size_t 
   CU(ctx, cudaMemsetAsync(static_cast<uint8_t *>(d->comp.p) + comp_bytes, 0, 64, st));  // the decoder may read 8 bytes past a stream
   CU(ctx, cudaMemcpyAsync(d->comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
   CU(ctx, cudaMemcpyAsync(d->blocks.p, blocks, (size_t)n_blocks * sizeof(strgpu_bgzf_block), cudaMemcpyHostToDevice, st));
-  inflate_bgzf_blocks<<<n_blocks, 32, 0, st>>>(static_cast<const uint8_t *>(d->comp.p), static_cast<const strgpu_bgzf_block *>(d->blocks.p), n_blocks,
-                                               static_cast<uint8_t *>(d->out.p), lo, d->d_status);
+  // STRGPU_INFLATE_KERNEL=1: one lane per block writing to global memory (the first version); 2: window in shared memory,
+  // warp-cooperative copies; 3: 2 + the compressed block staged in shared memory
+  static const int kernel = getenv("STRGPU_INFLATE_KERNEL") ? atoi(getenv("STRGPU_INFLATE_KERNEL")) : kDefaultInflateKernel;
+  if (kernel == 3) {
+    static std::once_flag attr_once[64];
+    std::call_once(attr_once[ctx->device & 63],
+                   []() { cudaFuncSetAttribute(inflate_bgzf_blocks_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV3Smem); });
+    inflate_bgzf_blocks_v2<true><<<n_blocks, 32, kV3Smem, st>>>(static_cast<const uint8_t *>(d->comp.p), static_cast<const strgpu_bgzf_block *>(d->blocks.p),
+                                                                n_blocks, static_cast<uint8_t *>(d->out.p), lo, d->d_status);
+  } else if (kernel == 2) {
+    static std::once_flag attr_once[64];
+    std::call_once(attr_once[ctx->device & 63],
+                   []() { cudaFuncSetAttribute(inflate_bgzf_blocks_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV2Smem); });
+    inflate_bgzf_blocks_v2<false><<<n_blocks, 32, kV2Smem, st>>>(static_cast<const uint8_t *>(d->comp.p), static_cast<const strgpu_bgzf_block *>(d->blocks.p),
+                                                                 n_blocks, static_cast<uint8_t *>(d->out.p), lo, d->d_status);
+  } else {
+    inflate_bgzf_blocks<<<n_blocks, 32, 0, st>>>(static_cast<const uint8_t *>(d->comp.p), static_cast<const strgpu_bgzf_block *>(d->blocks.p), n_blocks,
+                                                 static_cast<uint8_t *>(d->out.p), lo, d->d_status);
+  }
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(out + lo, d->out.p, (size_t)(hi - lo), cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaMemcpyAsync(d->h_status, d->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -117,14 +117,30 @@ int debug_main(int argc, char **argv) {
           bool ok = rc == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
           for (int g = 0; g < 32; g++) ok = ok && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;  // nothing outside [out, out + n)
           if (!ok) { std::printf("FAIL round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc); return 1; }
+          // the command-stream form of the decoder (what the CUDA kernel runs), commands executed serially
+          std::fill(got.begin(), got.end(), 0xAB);
+          const int rc2 = infl::inflate_block_stream(*T, comp.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
+          bool ok2 = rc2 == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
+          for (int g = 0; g < 32; g++) ok2 = ok2 && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;
+          if (!ok2) { std::printf("FAIL (stream) round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc2); return 1; }
           // a truncated or corrupted stream must be refused or at least stay inside the output buffer
           if (clen > 4) {
             std::vector<uint8_t> bad(comp);
             bad[(size_t)(rnd() % clen)] ^= (uint8_t)(1u << (rnd() % 8));
             std::fill(got.begin(), got.end(), 0xAB);
-            (void)infl::inflate_block(*T, bad.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
+            const int rb1 = infl::inflate_block(*T, bad.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
             for (int g = 0; g < 32; g++)
               if (got[(size_t)g] != 0xAB || got[32 + n + (size_t)g] != 0xAB) { std::printf("FAIL overrun on corrupt input, round %d\n", r); return 1; }
+            std::vector<uint8_t> first(got.begin() + 32, got.begin() + 32 + (long)n);
+            std::fill(got.begin(), got.end(), 0xAB);
+            const int rb2 = infl::inflate_block_stream(*T, bad.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
+            for (int g = 0; g < 32; g++)
+              if (got[(size_t)g] != 0xAB || got[32 + n + (size_t)g] != 0xAB) { std::printf("FAIL (stream) overrun on corrupt input, round %d\n", r); return 1; }
+            // both forms must agree on whether the damaged stream is acceptable, and on its bytes when it is
+            if ((rb1 == infl::kOk) != (rb2 == infl::kOk) || (rb1 == infl::kOk && std::memcmp(first.data(), got.data() + 32, n) != 0)) {
+              std::printf("FAIL the two decoders disagree on a corrupt stream, round %d: %d vs %d\n", r, rb1, rb2);
+              return 1;
+            }
           }
           cases++;
           bytes += n;

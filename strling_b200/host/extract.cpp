@@ -518,6 +518,22 @@ struct Extractor {
     b.n_bases = 0; b.n_seg = 0; b.max_len = 0; b.any_n = false; b.ticket = -1;
   }
 
+  // `--gpu-inflate` only: the submit slots get their device buffers (and the scan kernels are loaded) before the pipeline starts.
+  // cudaMalloc waits for every kernel in flight, so a first-use allocation inside strgpu_scan_submit would otherwise stall the
+  // staging thread behind a running inflate kernel, once per slot and buffer.  Empty segments: nothing is scanned.
+  void warm_up(Batch *bs, int n) {
+    if (debug_mode()) return;
+    int tickets[STRGPU_SLOTS];
+    const int m = std::min(n, (int)STRGPU_SLOTS);
+    for (int i = 0; i < m; i++) {
+      Batch &b = bs[i];
+      const uint32_t n_seg = b.cap_seg > 16 ? b.cap_seg - 16 : 0;
+      std::memset(b.segs, 0, (size_t)n_seg * sizeof(strgpu_segment));
+      gpu_check(strgpu_scan_submit(gpu, b.seq2, b.cap_bases > 64 ? b.cap_bases - 64 : 0, nullptr, nullptr, b.segs, n_seg, 160, b.out, &tickets[i]), "scan_submit (warm-up)");
+    }
+    for (int i = 0; i < m; i++) gpu_check(strgpu_scan_wait(gpu, tickets[i]), "scan_wait (warm-up)");
+  }
+
   // ---- replay: extract.nim:63-132,192-248 with scan results looked up instead of computed.  The pair arithmetic runs on
   // records without the qname (every read of a pair carries the same one); emit() attaches it.
   TreadCore to_tread(const Batch &b, const Pending &r) {
@@ -799,6 +815,7 @@ int extract_run(const ExtractArgs &a) {
   const size_t blocks_per_chunk = std::max<size_t>(16, (size_t)a.batch_reads / 220);
   for (auto &b : batches) ex.alloc_batch(b, (uint64_t)a.batch_reads * 200 + 4096, (uint32_t)std::min<uint64_t>((uint64_t)a.batch_reads * 2 + 64, 0xfffffff0u));
 
+  if (a.gpu_inflate) ex.warm_up(batches, kBatches);
   std::fprintf(stderr, "[strling] collecting str-like reads\n");
   const auto t0 = clk::now();
   // producer (this thread): inflate + decode + stage (all parallel) + submit.  consumer: wait for the GPU, replay in

@@ -404,5 +404,182 @@ STRLING_HD inline int inflate_block(Tables &T, const uint8_t *in, uint32_t in_le
   return kOk;
 }
 
+// ---- The same decoder as a pull-style state machine: next() decodes up to the next COPY (a match or a stored block), writing the
+// literals on the way straight into the output window, and returns that copy as a command.  This is the form the
+// warp-per-block CUDA kernel (csrc/decode_kernels.cu, kernel v2) runs: lane 0 calls next(), the command is broadcast and all 32
+// lanes execute the copy.  inflate_block_stream() below executes the commands serially -- the CPU check of this decoder
+// (`strling debug inflate-selftest` runs it beside inflate_block on every case).
+enum CommandType { kCmdEnd = 0, kCmdMatch = 1, kCmdStored = 2 };   // negative: a Status
+struct Command {
+  int type;
+  uint32_t o;   // where the copy starts in the output
+  uint32_t a;   // match: distance; stored: offset of the bytes in the input
+  uint32_t b;   // length
+};
+
+struct Stream {
+  Bits b;
+  const uint8_t *in0;
+  uint32_t o, o_end;
+  bool last, in_block;
+
+  STRLING_HD void init(const uint8_t *in, uint32_t in_len, uint32_t out_len) {
+    b.in = in;
+    b.in_end = in + in_len;
+    b.buf = 0;
+    b.cnt = 0;
+    in0 = in;
+    o = 0;
+    o_end = out_len;
+    last = false;
+    in_block = false;
+  }
+
+  STRLING_HD static Command status(int st) { return Command{st, 0, 0, 0}; }
+
+  // block header of a fixed / dynamic block (the 3 header bits are consumed already): builds T.lit / T.dist
+  STRLING_HD int read_tables(Tables &T, uint32_t type) {
+    if (type == 1) {
+      if (!T.fixed_built) {
+        for (int i = 0; i < 144; i++) T.lens[i] = 8;
+        for (int i = 144; i < 256; i++) T.lens[i] = 9;
+        for (int i = 256; i < 280; i++) T.lens[i] = 7;
+        for (int i = 280; i < 288; i++) T.lens[i] = 8;
+        for (int i = 0; i < 32; i++) T.lens[288 + i] = 5;
+        if (!build(T, T.lit, kLitBits, kLitCap, T.lens, 288, 0) || !build(T, T.dist, kDistBits, kDistCap, T.lens + 288, 32, 1)) return kBadCode;
+        T.fixed_built = true;
+      }
+      return kOk;
+    }
+    T.fixed_built = false;
+    const uint32_t hlit = b.peek(5) + 257, hdist = (b.peek(10) >> 5) + 1, hclen = (b.peek(14) >> 10) + 4;
+    b.consume(14);
+    if (hlit > 286 || hdist > 30) return kBadCode;
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint8_t pl[19];
+    for (int i = 0; i < 19; i++) pl[i] = 0;
+    for (uint32_t i = 0; i < hclen; i++) {
+      if ((i & 7) == 0 && !b.refill()) return kInputOverrun;
+      pl[order[i]] = (uint8_t)b.peek(3);
+      b.consume(3);
+    }
+    if (!build(T, T.pre, kPreBits, kPreCap, pl, 19, 2)) return kBadCode;
+    uint32_t n = 0;
+    while (n < hlit + hdist) {
+      if (!b.refill()) return kInputOverrun;
+      const uint32_t e = T.pre[b.peek(kPreBits)];
+      if (!(e & kLiteral)) return kBadCode;
+      b.consume(e & 0xff);
+      const uint32_t sym = e >> 16;
+      if (sym < 16) { T.lens[n++] = (uint8_t)sym; continue; }
+      uint32_t rep, val = 0;
+      if (sym == 16) {
+        if (n == 0) return kBadCode;
+        val = T.lens[n - 1];
+        rep = 3 + b.peek(2);
+        b.consume(2);
+      } else if (sym == 17) {
+        rep = 3 + b.peek(3);
+        b.consume(3);
+      } else {
+        rep = 11 + b.peek(7);
+        b.consume(7);
+      }
+      if (n + rep > hlit + hdist) return kBadCode;
+      for (uint32_t i = 0; i < rep; i++) T.lens[n++] = (uint8_t)val;
+    }
+    if (T.lens[256] == 0) return kBadCode;
+    uint8_t dl[32];
+    for (uint32_t i = 0; i < 32; i++) dl[i] = i < hdist ? T.lens[hlit + i] : 0;
+    for (uint32_t i = hlit; i < 288; i++) T.lens[i] = 0;
+    if (!build(T, T.lit, kLitBits, kLitCap, T.lens, 288, 0) || !build(T, T.dist, kDistBits, kDistCap, dl, 32, 1)) return kBadCode;
+    return kOk;
+  }
+
+  STRLING_HD Command next(Tables &T, uint8_t *window) {
+    while (true) {
+      if (!in_block) {
+        if (last) {
+          if (o != o_end) return status(kOutputShort);
+          if (b.in - (b.cnt >> 3) > b.in_end) return status(kInputOverrun);
+          return Command{kCmdEnd, o, 0, 0};
+        }
+        if (!b.refill()) return status(kInputOverrun);
+        last = b.peek(1) != 0;
+        const uint32_t type = b.peek(3) >> 1;
+        b.consume(3);
+        if (type == 0) {
+          b.consume(b.cnt & 7);
+          const uint8_t *p = b.in - (b.cnt >> 3);
+          b.buf = 0;
+          b.cnt = 0;
+          if (p + 4 > b.in_end) return status(kBadStored);
+          const uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8), nlen = (uint32_t)p[2] | ((uint32_t)p[3] << 8);
+          if ((len ^ nlen) != 0xffffu) return status(kBadStored);
+          p += 4;
+          if (p + len > b.in_end) return status(kInputOverrun);
+          if (len > o_end - o) return status(kOutputOverrun);
+          b.in = p + len;
+          if (len == 0) continue;
+          const Command c{kCmdStored, o, (uint32_t)(p - in0), len};
+          o += len;
+          return c;
+        }
+        if (type == 3) return status(kBadBlockType);
+        const int rc = read_tables(T, type);
+        if (rc != kOk) return status(rc);
+        in_block = true;
+      }
+      // a symbol takes at most 15 + 5 + 15 + 13 = 48 bits: the bit buffer is topped up only when it holds fewer
+      if (b.cnt < 48 && !b.refill()) return status(kInputOverrun);
+      uint32_t e = T.lit[b.peek(kLitBits)];
+      if (e & kSubtable) { b.consume(kLitBits); e = T.lit[(e >> 16) + b.peek((e >> 8) & 0x1f)]; }
+      if (e & kLiteral) {
+        const uint32_t n_lit = 1 + ((e >> 12) & 1);
+        if (o_end - o < n_lit) return status(kOutputOverrun);
+        b.consume(e & 0xff);
+        window[o++] = (uint8_t)(e >> 16);
+        if (n_lit == 2) window[o++] = (uint8_t)(e >> 24);
+        continue;
+      }
+      if (e & kEndOfBlock) { b.consume(e & 0xff); in_block = false; continue; }
+      const uint32_t total = e & 0xff, cw = (e >> 8) & 0x1f;
+      if (total == 0) return status(kBadCode);
+      const uint32_t len = (e >> 16) + (b.peek(total) >> cw);
+      b.consume(total);
+      uint32_t d = T.dist[b.peek(kDistBits)];
+      if (d & kSubtable) { b.consume(kDistBits); d = T.dist[(d >> 16) + b.peek((d >> 8) & 0x1f)]; }
+      const uint32_t dtotal = d & 0xff, dcw = (d >> 8) & 0x1f;
+      if (dtotal == 0) return status(kBadCode);
+      const uint32_t dist = (d >> 16) + (b.peek(dtotal) >> dcw);
+      b.consume(dtotal);
+      if (dist > o) return status(kBadDistance);
+      if (len > o_end - o) return status(kOutputOverrun);
+      const Command c{kCmdMatch, o, dist, len};
+      o += len;
+      return c;
+    }
+  }
+};
+
+// byte i of a match copy, for an executor that copies the bytes of one command in any order (the source of byte i lies
+// before the command's first output byte even when the match overlaps itself)
+STRLING_HD inline uint32_t match_source(const Command &c, uint32_t i) { return c.o - c.a + (i < c.a ? i : i % c.a); }
+
+STRLING_HD inline int inflate_block_stream(Tables &T, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len) {
+  Stream s;
+  s.init(in, in_len, out_len);
+  while (true) {
+    const Command c = s.next(T, out);
+    if (c.type == kCmdEnd) return kOk;
+    if (c.type < 0) return c.type;
+    if (c.type == kCmdMatch) {
+      for (uint32_t i = c.b; i-- > 0;) out[c.o + i] = out[match_source(c, i)];   // back to front: any order must do
+    } else {
+      for (uint32_t i = 0; i < c.b; i++) out[c.o + i] = in[c.a + i];
+    }
+  }
+}
+
 }  // namespace infl
 }  // namespace strling

@@ -1,11 +1,10 @@
 """BGZF inflate on the GPU (strgpu_inflate_bgzf, `strling extract --gpu-inflate`).  Run with -m gpu.
 
 The decoder's arithmetic is host/inflate_fast.hpp compiled as a device function and is covered on the CPU
-(tests/test_host_cpu.py::test_inflate_decoder_against_zlib, ::test_extract_staging_and_replay_without_the_scan with
-STRLING_DEBUG_STAGED_INFLATE); what these tests add is the CUDA side (csrc/decode_kernels.cu).  That kernel was written after the
-round's GPU budget was spent and HAS NOT RUN ON HARDWARE yet, so each test runs it in a child process with a timeout and is
-marked xfail(strict=False): a failure here reads as "the opt-in GPU inflate does not work yet", never as a regression of the
-default path (`strling extract` without --gpu-inflate inflates on the host threads and is covered by tests/test_cli_gpu.py)."""
+(tests/test_host_cpu.py::test_inflate_decoder_against_zlib -- both the direct form kernel 1 runs and the command-stream form
+kernels 2 and 3 run --, ::test_extract_staging_and_replay_without_the_scan with STRLING_DEBUG_STAGED_INFLATE); what these tests add
+is the CUDA side (csrc/decode_kernels.cu), for each of its three kernels (STRGPU_INFLATE_KERNEL).  Every case runs in a child
+process with a timeout, so a device fault cannot take the test session's CUDA context with it."""
 import os
 import subprocess
 import sys
@@ -17,7 +16,7 @@ from oracle import extract_oracle as eo
 from strling_b200 import bamio
 from strling_b200 import build as sb_build
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="csrc/decode_kernels.cu has not run on hardware yet (opt-in path)")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 DIRECT = textwrap.dedent("""
@@ -67,12 +66,18 @@ DIRECT = textwrap.dedent("""
 """)
 
 
-def test_gpu_inflate_matches_zlib():
-    r = subprocess.run([sys.executable, "-c", DIRECT % ROOT], capture_output=True, text=True, timeout=240)
+@pytest.mark.parametrize("kernel", ["1", "2", "3"])
+def test_gpu_inflate_matches_zlib(kernel):
+    """400 blocks through strgpu_inflate_bgzf: stored / fixed / dynamic DEFLATE blocks of every zlib level and strategy, sizes 0..65280,
+    incompressible data (payload larger than kernel 3's staging buffer) -- byte-identical to the input of zlib's encoder, nothing
+    written outside [first out_off, last out_off + isize), and a damaged block is refused (STRGPU_ERR_DATA) or at least decodes
+    to something else without touching memory outside its range."""
+    r = subprocess.run([sys.executable, "-c", DIRECT % ROOT], capture_output=True, text=True, timeout=240, env=dict(os.environ, STRGPU_INFLATE_KERNEL=kernel))
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_extract_with_gpu_inflate_writes_the_same_bin(tmp_path):
+    """`strling extract --gpu-inflate` (all three kernels) == `strling extract` == the oracle's .bin, byte for byte."""
     cli = sb_build.build_cli()
     targets = [("chr1", 3_000_000), ("chr2", 2_000_000)]
     loci = [(0, 400_000, 400_150, "CAG"), (0, 900_000, 900_090, "AAAG"), (1, 300_000, 300_060, "ATTCT")]
@@ -81,12 +86,13 @@ def test_extract_with_gpu_inflate_writes_the_same_bin(tmp_path):
     bam = str(tmp_path / "g.bam")
     bamio.write_bam(bam, hdr, targets, recs)
     outs = []
-    for extra in ([], ["--gpu-inflate"]):
-        out = str(tmp_path / ("a.bin" if not extra else "b.bin"))
-        r = subprocess.run([cli, "extract", "--batch-reads", "8192", *extra, bam, out], capture_output=True, text=True, timeout=240)
+    for k, extra in enumerate(([], ["--gpu-inflate"], ["--gpu-inflate"], ["--gpu-inflate"])):
+        out = str(tmp_path / f"x{k}.bin")
+        r = subprocess.run([cli, "extract", "--batch-reads", "8192", *extra, bam, out], capture_output=True, text=True, timeout=240,
+                           env=dict(os.environ, STRGPU_INFLATE_KERNEL=str(max(k, 1))))
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(open(out, "rb").read())
     exp, cache, _ = eo.extract(recs, targets, hdr)
     assert len(cache) > 500
-    assert outs[0] == exp
-    assert outs[1] == exp
+    for got in outs:
+        assert got == exp

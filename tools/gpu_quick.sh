@@ -1,20 +1,20 @@
 #!/bin/bash
-# One short GPU-box check of the extract command line: host inflate vs --gpu-inflate on synthetic BAMs (same .bin?), with the
-# binary's stage reports.  Everything is written to gpurun_out/ step by step so that a cut-off call still leaves results.
+# One short GPU-box check of the extract command line: host inflate vs --gpu-inflate (STRGPU_INFLATE_KERNEL=1|2|3) on a
+# synthetic BAM of 6x10^6 reads -- same .bin? -- with the binary's stage reports.  Everything is written to gpurun_out/ step
+# by step so that a cut-off call still leaves results.
 set +e
 mkdir -p gpurun_out
 B=strling_b200/bin/strling
-{ nproc; lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket"; } > gpurun_out/q_host.txt 2>&1
-$B debug synth-bam /tmp/q.bam 400000 > gpurun_out/q_synth.txt 2>&1
-timeout 60 $B extract -v /tmp/q.bam /tmp/a.bin 2> gpurun_out/q_small_host.txt; echo "rc $?" >> gpurun_out/q_small_host.txt
-timeout 60 $B extract -v --gpu-inflate /tmp/q.bam /tmp/b.bin 2> gpurun_out/q_small_gpuinflate.txt; echo "rc $?" >> gpurun_out/q_small_gpuinflate.txt
-cmp /tmp/a.bin /tmp/b.bin > gpurun_out/q_small_cmp.txt 2>&1; echo "cmp rc $?" >> gpurun_out/q_small_cmp.txt
-$B debug synth-bam /tmp/big.bam 3000000 >> gpurun_out/q_synth.txt 2>&1
-for i in 1 2; do
-timeout 90 $B extract -v /tmp/big.bam /tmp/c.bin 2>&1 | grep perf >> gpurun_out/q_big_host.txt
-timeout 90 $B extract -v --gpu-inflate /tmp/big.bam /tmp/d.bin 2>&1 | grep -E "perf|gpu:" >> gpurun_out/q_big_gpuinflate.txt
-done
-cmp /tmp/c.bin /tmp/d.bin > gpurun_out/q_big_cmp.txt 2>&1; echo "cmp rc $?" >> gpurun_out/q_big_cmp.txt
-timeout 100 python -m pytest tests/test_cli_gpu.py tests/test_decode_gpu.py -x -q -k "config1 or config4 or inflate" > gpurun_out/q_pytest.txt 2>&1
-tail -3 gpurun_out/q_pytest.txt
-cat gpurun_out/q_small_cmp.txt gpurun_out/q_big_cmp.txt gpurun_out/q_big_host.txt gpurun_out/q_big_gpuinflate.txt
+O=gpurun_out/q3
+$B debug synth-bam /tmp/big.bam 3000000 > ${O}_synth.txt 2>&1
+perf() { grep -E "perf|gpu:|rror" | sed 's/.*perf: //'; }
+echo "host" > ${O}_runs.txt;          timeout 30 $B extract -v /tmp/big.bam /tmp/c.bin 2>&1 | perf >> ${O}_runs.txt
+echo "k3" >> ${O}_runs.txt;           STRGPU_INFLATE_KERNEL=3 timeout 30 $B extract -v --gpu-inflate /tmp/big.bam /tmp/d3.bin 2>&1 | perf >> ${O}_runs.txt
+cmp /tmp/c.bin /tmp/d3.bin > /dev/null 2>&1; echo "cmp c.bin d3.bin rc $?" >> ${O}_cmp.txt
+echo "k3 shards8" >> ${O}_runs.txt;   STRGPU_INFLATE_KERNEL=3 timeout 30 $B extract -v --gpu-inflate --replay-shards 8 /tmp/big.bam /tmp/d3b.bin 2>&1 | perf >> ${O}_runs.txt
+cmp /tmp/c.bin /tmp/d3b.bin > /dev/null 2>&1; echo "cmp c.bin d3b.bin rc $?" >> ${O}_cmp.txt
+STRGPU_INFLATE_KERNEL=3 timeout 40 python -m pytest tests/test_decode_gpu.py -x -q -k zlib > ${O}_pytest_k3.txt 2>&1
+echo "k3 shards8 batch1M" >> ${O}_runs.txt; STRGPU_INFLATE_KERNEL=3 timeout 30 $B extract -v --gpu-inflate --replay-shards 8 --batch-reads 1048576 /tmp/big.bam /tmp/d3c.bin 2>&1 | perf >> ${O}_runs.txt
+cmp /tmp/c.bin /tmp/d3c.bin > /dev/null 2>&1; echo "cmp c.bin d3c.bin rc $?" >> ${O}_cmp.txt
+tail -2 ${O}_pytest_k3.txt
+cat ${O}_cmp.txt ${O}_runs.txt
