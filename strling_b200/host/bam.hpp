@@ -64,6 +64,9 @@ struct BamRecord {
   }
 };
 
+// inflate_host.cpp: the decoder compiled for the best ISA level this CPU has
+int inflate_block_host(infl::Tables &T, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len);
+
 // one BGZF block: `in` is followed by the block's 8-byte footer (the decoder may read into it)
 inline void inflate_bgzf_block(const uint8_t *in, uint32_t csize, uint8_t *out, uint32_t isize) {
   static const bool use_zlib = std::getenv("STRLING_ZLIB") != nullptr;
@@ -71,7 +74,7 @@ inline void inflate_bgzf_block(const uint8_t *in, uint32_t csize, uint8_t *out, 
   if (!use_zlib) {
     static thread_local std::unique_ptr<infl::Tables> tables;
     if (!tables) { tables.reset(new infl::Tables); tables->fixed_built = false; }
-    const int rc = infl::inflate_block(*tables, in, csize, out, isize);
+    const int rc = inflate_block_host(*tables, in, csize, out, isize);
     if (rc != infl::kOk) throw std::runtime_error("BGZF: inflate failed (" + std::to_string(rc) + ")");
     return;
   }

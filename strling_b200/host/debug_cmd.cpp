@@ -117,6 +117,12 @@ int debug_main(int argc, char **argv) {
           bool ok = rc == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
           for (int g = 0; g < 32; g++) ok = ok && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;  // nothing outside [out, out + n)
           if (!ok) { std::printf("FAIL round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc); return 1; }
+          // the instance the BAM readers call (compiled for BMI2 where the CPU has it)
+          std::fill(got.begin(), got.end(), 0xAB);
+          const int rc1 = inflate_block_host(*T, comp.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
+          bool ok1 = rc1 == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
+          for (int g = 0; g < 32; g++) ok1 = ok1 && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;
+          if (!ok1) { std::printf("FAIL (dispatched) round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc1); return 1; }
           // the command-stream form of the decoder (what the CUDA kernel runs), commands executed serially
           std::fill(got.begin(), got.end(), 0xAB);
           const int rc2 = infl::inflate_block_stream(*T, comp.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);

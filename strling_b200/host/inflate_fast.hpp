@@ -14,8 +14,11 @@
 #if defined(__CUDACC__)
 #define STRLING_HD __host__ __device__
 #define STRLING_INFLATE_NO_PAIRS 1   // the device build keeps its tables small (shared memory): no literal-pair entries
+#define STRLING_INFLATE_INLINE inline
 #else
 #define STRLING_HD
+// on the host the decoder is instantiated per ISA level (inflate_host.cpp): it has to be inlined into those instances
+#define STRLING_INFLATE_INLINE inline __attribute__((always_inline))
 #endif
 
 namespace strling {
@@ -183,7 +186,7 @@ struct Bits {
   STRLING_HD inline uint32_t peek(uint32_t n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
 };
 
-STRLING_HD inline void copy_match(uint8_t *dst, uint32_t dist, uint32_t len, bool room) {
+STRLING_HD STRLING_INFLATE_INLINE void copy_match(uint8_t *dst, uint32_t dist, uint32_t len, bool room) {
   const uint8_t *src = dst - dist;
 #if !defined(__CUDA_ARCH__)
   if (room) {  // at least 16 bytes may be written past dst + len
@@ -215,7 +218,7 @@ STRLING_HD inline void copy_match(uint8_t *dst, uint32_t dist, uint32_t len, boo
 }
 
 // Decodes one complete deflate stream.  Returns kOk when exactly out_len bytes were produced by a stream that ends inside `in`.
-STRLING_HD inline int inflate_block(Tables &T, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len) {
+STRLING_HD STRLING_INFLATE_INLINE int inflate_block(Tables &T, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len) {
   Bits b{in, in + in_len, 0, 0};
   uint8_t *o = out;
   uint8_t *const o_end = out + out_len;
