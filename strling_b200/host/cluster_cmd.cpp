@@ -583,7 +583,7 @@ int extract_main(int argc, char **argv) {
   e.verbose = a.has("--verbose");
   e.device = std::stoi(a.get("--device", "0"));
   e.threads = std::stoi(a.get("--threads", "0"));
-  e.batch_reads = (uint32_t)std::stoul(a.get("--batch-reads", "524288"));
+  e.batch_reads = (uint32_t)std::stoul(a.get("--batch-reads", "262144"));
   e.replay_shards = std::stoi(a.get("--replay-shards", "0"));
   e.gpu_inflate = a.has("--gpu-inflate");
   e.bam = a.pos[0];

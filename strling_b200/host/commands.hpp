@@ -14,7 +14,7 @@ struct ExtractArgs {
   bool verbose = false;
   int device = 0;
   int threads = 0;
-  uint32_t batch_reads = 1u << 19;
+  uint32_t batch_reads = 1u << 18;
   int replay_shards = 0;          // 0: a quarter of the threads
   bool gpu_inflate = false;       // BGZF blocks are inflated on the GPU (strgpu_inflate_bgzf) instead of the host threads
   // `strling debug extract` only (CPU-side checks of the staging and replay logic; never set by `strling extract`):

@@ -80,6 +80,7 @@ int debug_main(int argc, char **argv) {
     const int rounds = argc >= 3 ? std::atoi(argv[2]) : 200;
     uint64_t st = seed * 0x9e3779b97f4a7c15ull + 1;
     auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    auto same_bytes = [](const uint8_t *a, const uint8_t *b, size_t len) { return len == 0 || std::memcmp(a, b, len) == 0; };
     infl::Tables *T = new infl::Tables;
     T->fixed_built = false;
     size_t cases = 0, bytes = 0;
@@ -114,19 +115,19 @@ int debug_main(int argc, char **argv) {
           deflateEnd(&zs);
           std::vector<uint8_t> got(n + 64, 0xAB);
           const int rc = infl::inflate_block(*T, comp.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
-          bool ok = rc == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
+          bool ok = rc == infl::kOk && same_bytes(got.data() + 32, raw.data(), n);
           for (int g = 0; g < 32; g++) ok = ok && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;  // nothing outside [out, out + n)
           if (!ok) { std::printf("FAIL round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc); return 1; }
           // the instance the BAM readers call (compiled for BMI2 where the CPU has it)
           std::fill(got.begin(), got.end(), 0xAB);
           const int rc1 = inflate_block_host(*T, comp.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
-          bool ok1 = rc1 == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
+          bool ok1 = rc1 == infl::kOk && same_bytes(got.data() + 32, raw.data(), n);
           for (int g = 0; g < 32; g++) ok1 = ok1 && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;
           if (!ok1) { std::printf("FAIL (dispatched) round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc1); return 1; }
           // the command-stream form of the decoder (what the CUDA kernel runs), commands executed serially
           std::fill(got.begin(), got.end(), 0xAB);
           const int rc2 = infl::inflate_block_stream(*T, comp.data(), (uint32_t)clen, got.data() + 32, (uint32_t)n);
-          bool ok2 = rc2 == infl::kOk && std::memcmp(got.data() + 32, raw.data(), n) == 0;
+          bool ok2 = rc2 == infl::kOk && same_bytes(got.data() + 32, raw.data(), n);
           for (int g = 0; g < 32; g++) ok2 = ok2 && got[(size_t)g] == 0xAB && got[32 + n + (size_t)g] == 0xAB;
           if (!ok2) { std::printf("FAIL (stream) round %d kind %d level %d strategy %d n %zu rc %d\n", r, kind, level, strategy, n, rc2); return 1; }
           // a truncated or corrupted stream must be refused or at least stay inside the output buffer
@@ -143,7 +144,7 @@ int debug_main(int argc, char **argv) {
             for (int g = 0; g < 32; g++)
               if (got[(size_t)g] != 0xAB || got[32 + n + (size_t)g] != 0xAB) { std::printf("FAIL (stream) overrun on corrupt input, round %d\n", r); return 1; }
             // both forms must agree on whether the damaged stream is acceptable, and on its bytes when it is
-            if ((rb1 == infl::kOk) != (rb2 == infl::kOk) || (rb1 == infl::kOk && std::memcmp(first.data(), got.data() + 32, n) != 0)) {
+            if ((rb1 == infl::kOk) != (rb2 == infl::kOk) || (rb1 == infl::kOk && !same_bytes(first.data(), got.data() + 32, n))) {
               std::printf("FAIL the two decoders disagree on a corrupt stream, round %d: %d vs %d\n", r, rb1, rb2);
               return 1;
             }
