@@ -6,10 +6,12 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "bam.hpp"
 #include "commands.hpp"
+#include "mate_table.hpp"
 #include "tread.hpp"
 
 namespace strling {
@@ -73,6 +75,54 @@ int debug_main(int argc, char **argv) {
   if (what == "synth-bam" && argc >= 3)  // strling debug synth-bam <out.bam> <n_pairs> [seed] [deflate level] [threads]
     return synth_bam(argv[1], (uint64_t)std::atoll(argv[2]), argc >= 4 ? (uint64_t)std::atoll(argv[3]) : 2, argc >= 5 ? std::atoi(argv[4]) : 1,
                      argc >= 6 ? std::atoi(argv[5]) : 0);
+  if (what == "matetable-selftest") {
+    // MateTable (the mate table of extract's replay) against std::unordered_map under random insert / find / take traffic: names of
+    // 1..120 bytes (inline and heap storage), growth from 1024 slots to hundreds of thousands of live entries, and -- with a degraded
+    // hash that keeps only a few bits -- long probe runs, which is where backward-shift deletion goes wrong if it is wrong
+    const uint64_t seed = argc >= 2 ? (uint64_t)std::atoll(argv[1]) : 1;
+    const long n_ops = argc >= 3 ? std::atol(argv[2]) : 2000000;
+    uint64_t st = seed * 0x9e3779b97f4a7c15ull + 7;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    for (int mode = 0; mode < 3; mode++) {
+      const uint64_t hash_mask = mode == 0 ? ~0ull : mode == 1 ? 0xfffull : 0x3full;   // full hash, 4096 classes, 64 classes
+      const size_t n_names = mode == 0 ? 400000 : mode == 1 ? 20000 : 2000;   // degraded hashes: probe runs as long as the table is full
+      MateTable tbl;
+      std::unordered_map<std::string, uint32_t> ref;
+      std::vector<std::string> names(n_names);
+      for (size_t i = 0; i < n_names; i++) {
+        const size_t len = 1 + (size_t)(rnd() % (i % 50 == 0 ? 120 : 40));
+        names[i].resize(len);
+        for (auto &c : names[i]) c = (char)('!' + rnd() % 90);
+        names[i] += std::to_string(i);  // unique
+      }
+      for (long op = 0; op < n_ops / (mode == 0 ? 1 : 10); op++) {
+        const std::string &nm = names[(size_t)(rnd() % n_names)];
+        const uint64_t h = hash_name(nm.data(), nm.size()) & hash_mask;
+        const size_t slot = tbl.find(nm.data(), (uint32_t)nm.size(), h);
+        auto it = ref.find(nm);
+        if ((slot != SIZE_MAX) != (it != ref.end())) { std::printf("FAIL presence mode %d op %ld\n", mode, op); return 1; }
+        if (slot != SIZE_MAX) {
+          if (tbl.at(slot).t.position != it->second) { std::printf("FAIL value mode %d op %ld\n", mode, op); return 1; }
+          if (rnd() % 3) { tbl.erase(slot); ref.erase(it); }
+        } else if (rnd() % 4) {
+          TreadCore t;
+          t.position = (uint32_t)rnd();
+          tbl.insert(nm.data(), (uint32_t)nm.size(), h, t);
+          ref.emplace(nm, t.position);
+        }
+        if (tbl.size() != ref.size()) { std::printf("FAIL size mode %d op %ld\n", mode, op); return 1; }
+      }
+      // everything that should be there is there
+      for (const auto &kv : ref) {
+        const uint64_t h = hash_name(kv.first.data(), kv.first.size()) & hash_mask;
+        const size_t slot = tbl.find(kv.first.data(), (uint32_t)kv.first.size(), h);
+        if (slot == SIZE_MAX || tbl.at(slot).t.position != kv.second) { std::printf("FAIL final mode %d\n", mode); return 1; }
+      }
+      std::printf("mode %d ok\tlive %zu\n", mode, ref.size());
+      std::fflush(stdout);
+    }
+    return 0;
+  }
   if (what == "inflate-selftest") {
     // the repo's DEFLATE decoder against zlib's encoder: every deflate level and strategy (stored, fixed and dynamic Huffman
     // blocks, long sub-table codes, every match distance / length class) over several kinds of data and all small sizes

@@ -376,3 +376,11 @@ def test_synth_bam_is_a_valid_sorted_bam(cli, tmp_path):
     assert sum(1 for r in rows if int(r[2]) < 0) == 100
     par = run(cli, "debug", "chunks", bam, "4", "64").split("\t")
     assert par[par.index("records") + 1] == "10000"
+
+
+def test_mate_table_against_unordered_map(cli):
+    """The replay's mate table (host/mate_table.hpp: open addressing over a pooled entry array, backward-shift deletion, names inline
+    up to 54 bytes) under random insert / find / take traffic against std::unordered_map -- growth to >10^5 live entries, and
+    degraded hashes (4096 and 64 classes) that force long probe runs."""
+    out = run(cli, "debug", "matetable-selftest", "3", "600000")
+    assert [l.split("\t")[0] for l in out.splitlines()] == ["mode 0 ok", "mode 1 ok", "mode 2 ok"], out
