@@ -8,6 +8,7 @@
 // median-depth column (call.nim:255), `-unplaced.txt` and `-genotype.txt`.
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -423,7 +424,11 @@ void write_call_outputs(const std::vector<strgpu_bounds> &bounds, const std::vec
     gl_bound.push_back(i);
     gl_locus.push_back(0);
   }
+  const auto ev0 = std::chrono::steady_clock::now();
   collect_evidence(bam, gl, (int)p.window, frag, min_mapq);
+  if (std::getenv("STRLING_CALL_TIMING"))
+    std::fprintf(stderr, "[strling] call: evidence pass over the BAM for %zu loci: %.3f s\n", gl.size(),
+                 std::chrono::duration<double>(std::chrono::steady_clock::now() - ev0).count());
   GenotypeOpts go;
   go.min_clip = p.min_clip; go.min_clip_total = p.min_clip_total; go.min_support = p.min_support; go.median_fragment_length = frag_median(frag);
   std::vector<Call> calls;

@@ -12,12 +12,15 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include "bam.hpp"
+#include "pool.hpp"
 #include "tread.hpp"
 
 namespace strling {
@@ -308,7 +311,14 @@ inline void locus_finish(GLocus &L, const std::array<uint32_t, 4096> &frag) {
 // One pass over the BAM for every locus at once.  The reference queries an index per locus (collect.nim:130-146), which only
 // works on a coordinate-sorted BAM; this pass needs the same order (it is what lets a locus be finished, and its memory
 // released, as soon as the stream has passed its window) and says so when the file is not sorted.
-inline void collect_evidence(const std::string &bam, std::vector<GLocus> &loci, int window, const std::array<uint32_t, 4096> &frag, uint8_t min_mapq) {
+// The pass is chunked and parallel (round 2): a chunk of BGZF blocks is inflated and walked on the thread pool
+// (BamChunkReader), one parallel sweep takes (tid, pos, stop) of every record and checks the order, and then every locus whose
+// window meets the chunk takes ITS records -- a binary search on the sorted positions gives the range -- in file order.  Loci
+// only ever touch their own state, so they are worked off in parallel; a locus sees exactly the records, in exactly the
+// order, the record-at-a-time loop gave it.  (A chunk in which a placed record follows a no-coordinate record is not sorted by
+// the SAM specification's rule but was tolerated by that loop: such a chunk goes through the loop's logic record by record.)
+inline void collect_evidence(const std::string &bam, std::vector<GLocus> &loci, int window, const std::array<uint32_t, 4096> &frag, uint8_t min_mapq,
+                             int threads = 0) {
   const std::vector<float> cd = cumulative(frag);
   int n_tid = 0;
   for (auto &L : loci) {
@@ -325,38 +335,148 @@ inline void collect_evidence(const std::string &bam, std::vector<GLocus> &loci, 
     std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return loci[a].qbeg < loci[b].qbeg; });
     for (uint32_t i : v) max_span[(size_t)t] = std::max(max_span[(size_t)t], loci[i].wr - loci[i].qbeg);
   }
+  Pool pool(threads > 0 ? threads : (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency())));
   std::vector<size_t> first_active((size_t)n_tid, 0);   // loci before this index (in qbeg order) are finished
+  std::vector<uint32_t> to_finish;
   auto finish_upto = [&](int tid, int pos) {            // every window of `tid` that ends at or before pos
     auto &v = by_tid[(size_t)tid];
     size_t &f = first_active[(size_t)tid];
-    while (f < v.size() && (loci[v[f]].finished || loci[v[f]].wr <= pos)) locus_finish(loci[v[f++]], frag);
+    while (f < v.size() && (loci[v[f]].finished || loci[v[f]].wr <= pos)) to_finish.push_back(v[f++]);
   };
-  BamReader rd(bam);
-  BamRecord a;
-  int last_tid = -1, last_pos = -1;
-  while (rd.next(a)) {
-    if (a.tid < 0) continue;
-    if (a.tid < last_tid || (a.tid == last_tid && a.pos < last_pos))
-      throw std::runtime_error("[strling] call: " + bam + " is not coordinate-sorted (record " + std::string(a.qname, a.l_qname) +
-                               "); the reference needs a sorted, indexed BAM here too");
-    if (a.tid != last_tid)
-      for (int t = std::max(0, last_tid); t < std::min(a.tid, n_tid); t++) finish_upto(t, INT32_MAX);
-    last_tid = a.tid;
-    last_pos = a.pos;
-    if (a.tid >= n_tid) continue;
-    const auto &v = by_tid[(size_t)a.tid];
-    if (v.empty()) continue;
-    finish_upto(a.tid, a.pos);
-    const int stop = a.stop();
-    // candidates: qbeg < stop and wr > pos  =>  qbeg > pos - max_span
-    const int lo_key = a.pos - max_span[(size_t)a.tid];
-    auto it = std::upper_bound(v.begin(), v.end(), lo_key, [&](int key, uint32_t i) { return key < loci[i].qbeg; });
-    for (; it != v.end() && loci[*it].qbeg < stop; ++it) {
-      GLocus &L = loci[*it];
-      if (!L.finished && a.pos < L.wr && stop > L.qbeg) locus_add_record(L, a, stop, cd, min_mapq);
-    }
+  auto run_finish = [&]() {
+    pool.run(to_finish.size(), [&](size_t k) { locus_finish(loci[to_finish[k]], frag); });
+    to_finish.clear();
+  };
+  uint64_t first_voffset;
+  int32_t n_ref;
+  {
+    BamReader hdr(bam, 1);
+    first_voffset = hdr.tell();
+    n_ref = (int32_t)hdr.targets().size();
   }
-  for (auto &L : loci) locus_finish(L, frag);
+  BamChunkReader rd(bam, first_voffset, pool.size(), &pool, n_ref);
+  BamChunk c;
+  std::vector<int32_t> tid, pos, stop;
+  int last_tid = -1, last_pos = -1;
+  auto unsorted = [&](const uint8_t *rec) {
+    const BamRecord a = BamChunk::view(rec);
+    return std::runtime_error("[strling] call: " + bam + " is not coordinate-sorted (record " + std::string(a.qname, a.l_qname) +
+                              "); the reference needs a sorted, indexed BAM here too");
+  };
+  // test hooks: STRLING_CALL_BLOCKS = BGZF blocks per chunk (many small chunks), STRLING_CALL_SERIAL = every chunk through the
+  // record-by-record logic
+  static const size_t env_blocks = std::getenv("STRLING_CALL_BLOCKS") ? (size_t)std::atol(std::getenv("STRLING_CALL_BLOCKS")) : 0;
+  static const bool force_serial = std::getenv("STRLING_CALL_SERIAL") != nullptr;
+  size_t blocks = env_blocks ? env_blocks : 256;
+  while (rd.next(c, blocks)) {
+    blocks = env_blocks ? env_blocks : 1024;
+    const size_t n = c.n_records();
+    if (n == 0) continue;
+    const uint8_t *data = c.data.data();
+    tid.resize(n); pos.resize(n); stop.resize(n);
+    const size_t parts = std::max<size_t>(1, std::min<size_t>((size_t)pool.size() * 4, (n + 4095) / 4096));
+    struct PartInfo { int64_t bad = -1; bool placed_after_unplaced = false; bool any_unplaced = false; int32_t first_tid = -2, first_pos = 0, last_tid = -2, last_pos = 0; int max_len = 0; };
+    std::vector<PartInfo> info(parts);
+    pool.ranges(n, parts, [&](size_t lo, size_t hi, size_t part) {
+      PartInfo pi;
+      for (size_t i = lo; i < hi; i++) {
+        if (i + 6 < hi) __builtin_prefetch(data + c.rec_off[i + 6]);
+        const BamRecord a = BamChunk::view(data + c.rec_off[i]);
+        tid[i] = a.tid;
+        pos[i] = a.pos;
+        if (a.tid < 0) { stop[i] = a.pos; pi.any_unplaced = true; continue; }
+        stop[i] = a.stop();
+        pi.max_len = std::max(pi.max_len, stop[i] - a.pos);
+        if (pi.any_unplaced) pi.placed_after_unplaced = true;
+        if (pi.first_tid == -2) { pi.first_tid = a.tid; pi.first_pos = a.pos; }
+        else if (pi.bad < 0 && (a.tid < pi.last_tid || (a.tid == pi.last_tid && a.pos < pi.last_pos))) pi.bad = (int64_t)i;
+        pi.last_tid = a.tid;
+        pi.last_pos = a.pos;
+      }
+      info[part] = pi;
+    });
+    // order across the parts and against the previous chunk; the earliest offending record is the one reported
+    bool mixed = force_serial, seen_unplaced = false;
+    int max_len = 0;
+    int ct = last_tid, cp = last_pos;
+    const size_t per = (n + parts - 1) / parts;
+    for (size_t q = 0; q < parts; q++) {
+      const PartInfo &pi = info[q];
+      max_len = std::max(max_len, pi.max_len);
+      if (pi.first_tid != -2) {
+        if (seen_unplaced) mixed = true;
+        if (pi.first_tid < ct || (pi.first_tid == ct && pi.first_pos < cp)) {
+          size_t i = q * per;   // the part's first placed record
+          while (tid[i] < 0) i++;
+          throw unsorted(data + c.rec_off[i]);
+        }
+        if (pi.bad >= 0) throw unsorted(data + c.rec_off[(size_t)pi.bad]);
+        ct = pi.last_tid;
+        cp = pi.last_pos;
+      }
+      if (pi.placed_after_unplaced) mixed = true;
+      if (pi.any_unplaced) seen_unplaced = true;
+    }
+    if (mixed) {   // record by record, as before
+      for (size_t i = 0; i < n; i++) {
+        if (tid[i] < 0) continue;
+        const BamRecord a = BamChunk::view(data + c.rec_off[i]);
+        if (a.tid != last_tid)
+          for (int t = std::max(0, last_tid); t < std::min(a.tid, n_tid); t++) finish_upto(t, INT32_MAX);
+        last_tid = a.tid;
+        last_pos = a.pos;
+        if (a.tid >= n_tid) continue;
+        const auto &v = by_tid[(size_t)a.tid];
+        if (v.empty()) continue;
+        finish_upto(a.tid, a.pos);
+        run_finish();
+        const int lo_key = a.pos - max_span[(size_t)a.tid];
+        auto it = std::upper_bound(v.begin(), v.end(), lo_key, [&](int key, uint32_t k) { return key < loci[k].qbeg; });
+        for (; it != v.end() && loci[*it].qbeg < stop[i]; ++it) {
+          GLocus &L = loci[*it];
+          if (!L.finished && a.pos < L.wr && stop[i] > L.qbeg) locus_add_record(L, a, stop[i], cd, min_mapq);
+        }
+      }
+      run_finish();
+      continue;
+    }
+    size_t n_placed = n;
+    while (n_placed > 0 && tid[n_placed - 1] < 0) n_placed--;   // no-coordinate records only ever trail here
+    if (n_placed == 0) continue;
+    // one stretch of records per reference sequence
+    size_t a0 = 0;
+    while (a0 < n_placed) {
+      const int t = tid[a0];
+      const size_t a1 = (size_t)(std::upper_bound(tid.begin() + (long)a0, tid.begin() + (long)n_placed, t) - tid.begin());
+      if (t != last_tid)
+        for (int u = std::max(0, last_tid); u < std::min(t, n_tid); u++) finish_upto(u, INT32_MAX);
+      last_tid = t;
+      last_pos = pos[a1 - 1];
+      if (t < n_tid && !by_tid[(size_t)t].empty()) {
+        const auto &v = by_tid[(size_t)t];
+        finish_upto(t, pos[a0]);   // windows that ended before this stretch began
+        // loci whose window can meet a record of the stretch: qbeg < (largest stop) and wr > first pos
+        const int reach = pos[a1 - 1] + max_len;
+        std::vector<uint32_t> todo;
+        for (size_t k = first_active[(size_t)t]; k < v.size() && loci[v[k]].qbeg < reach; k++)
+          if (!loci[v[k]].finished && loci[v[k]].wr > pos[a0]) todo.push_back(v[k]);
+        pool.run(todo.size(), [&](size_t k) {
+          GLocus &L = loci[todo[k]];
+          // records with pos < wr and stop > qbeg; stop - pos <= max_len bounds the search from below
+          const auto lo_it = std::upper_bound(pos.begin() + (long)a0, pos.begin() + (long)a1, L.qbeg - max_len - 1);
+          const auto hi_it = std::lower_bound(pos.begin() + (long)a0, pos.begin() + (long)a1, L.wr);
+          for (size_t i = (size_t)(lo_it - pos.begin()); i < (size_t)(hi_it - pos.begin()); i++)
+            if (stop[i] > L.qbeg) locus_add_record(L, BamChunk::view(data + c.rec_off[i]), stop[i], cd, min_mapq);
+        });
+        finish_upto(t, pos[a1 - 1]);
+      }
+      a0 = a1;
+    }
+    run_finish();
+  }
+  to_finish.clear();
+  for (uint32_t i = 0; i < loci.size(); i++) to_finish.push_back(i);
+  run_finish();   // locus_finish is a no-op for the ones already done
 }
 
 // ---- genotyper.nim

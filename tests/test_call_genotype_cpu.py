@@ -121,6 +121,15 @@ def test_host_genotyping_matches_oracle(cli, tmp_path, seed, min_support, min_ma
     assert got_gt[0] == co.GT_HEADER and got_bounds[0] == eo.BOUNDS_HEADER + "\tdepth"
     assert len(exp_gt) >= 8 and sorted(got_gt[1:]) == sorted(exp_gt)
     assert got_bounds[1:] == exp_bounds
+    # the evidence pass is chunked and parallel over loci (genotype.hpp collect_evidence): the same files with chunks of two BGZF
+    # blocks (windows straddle many chunk boundaries), on one thread's worth of parts, and through the record-by-record logic
+    for k, env in enumerate(({"STRLING_CALL_BLOCKS": "2"}, {"STRLING_CALL_SERIAL": "1"}, {"STRLING_CALL_BLOCKS": "1", "STRLING_CALL_SERIAL": "1"})):
+        alt = str(tmp_path / f"alt{k}")
+        r = subprocess.run([cli, "debug", "genotype", bam, binp, cl, alt, str(window), str(min_support), str(min_mapq)], capture_output=True, text=True,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        for suffix in ("-genotype.txt", "-bounds.txt", "-unplaced.txt"):
+            assert open(alt + suffix).read() == open(prefix + suffix).read(), (env, suffix)
     # the evidence is not trivial: spanning reads, spanning pairs and non-zero indel alleles occur
     cols = [l.split("\t") for l in exp_gt]
     assert any(int(c[7]) > 0 for c in cols) and any(int(c[8]) > 0 for c in cols) and any(c[4] not in ("0.00", "nan") for c in cols)
