@@ -384,3 +384,123 @@ def test_mate_table_against_unordered_map(cli):
     degraded hashes (4096 and 64 classes) that force long probe runs."""
     out = run(cli, "debug", "matetable-selftest", "3", "600000")
     assert [l.split("\t")[0] for l in out.splitlines()] == ["mode 0 ok", "mode 1 ok", "mode 2 ok"], out
+
+
+def _fuzz_records(rng, n, targets):
+    """Random BAM records far from what an aligner writes: every flag combination, empty / clip-only / hard-clipped / spliced
+    CIGARs, names of 1..250 bytes that repeat up to four times, mates that point anywhere (same position, other contig, nowhere),
+    mapq around the threshold, reads of 0..300 bases made of repeats, noise, N and IUPAC codes."""
+    pool = []
+    for k in range(max(4, n // 2)):
+        ln = rng.choice([1, 2, 7, 15, 16, 31, 40, 54, 55, 56, 90, 250]) if rng.random() < 0.3 else rng.randrange(8, 40)
+        pool.append(("%x" % rng.getrandbits(4 * ln)).rjust(ln, "q")[:ln - len(str(k))] + str(k) if ln > len(str(k)) else str(k))
+    units = ["A", "C", "AC", "AG", "CAG", "AAG", "AAAG", "ATTCT", "AAGGG", "CACGAT", "CCCCGG"]
+
+    def seq_of(L, kind):
+        if kind == 0:
+            return "".join(rng.choice("ACGT") for _ in range(L))
+        u = rng.choice(units)
+        if len(u) == 1 and L > 250:   # a homopolymer of 256+ bases trips the reference's doAssert repeat_count < 256 (extract.nim:72)
+            u = "AC"
+        s = (u * (L // len(u) + 2))[rng.randrange(len(u)):][:L]
+        if kind == 2:   # half repeat, half noise (either order): what a clipped STR read looks like
+            h = L // 2
+            s = s[:h] + "".join(rng.choice("ACGT") for _ in range(L - h)) if rng.random() < 0.5 else "".join(rng.choice("ACGT") for _ in range(h)) + s[h:]
+        s = list(s)
+        for i in range(L):
+            r = rng.random()
+            if r < 0.01:
+                s[i] = rng.choice("ACGT")
+            elif kind == 3 and r < 0.08:
+                s[i] = rng.choice("NNNRYKM")
+        return "".join(s)
+
+    recs = []
+    for i in range(n):
+        placed = rng.random() < 0.92
+        tid = rng.randrange(len(targets)) if placed else -1
+        pos = rng.randrange(0, targets[tid][1] - 2000) if placed else -1
+        flag = 0
+        for bit, p in ((0x1, 0.95), (0x2, 0.7), (0x4, 0.03), (0x8, 0.05), (0x10, 0.5), (0x20, 0.5), (0x100, 0.03), (0x800, 0.03), (0x400, 0.02)):
+            if rng.random() < p:
+                flag |= bit
+        flag |= rng.choice([0x40, 0x80])
+        if not placed:
+            flag |= 0x4
+        r = rng.random()
+        if not placed or r < 0.1:
+            mtid, mpos = -1, -1
+        elif r < 0.25:
+            mtid, mpos = tid, pos                      # same position: after_mate asks the table
+        elif r < 0.4:
+            mtid, mpos = rng.randrange(len(targets)), rng.randrange(0, 100000)
+        else:
+            mtid, mpos = tid, max(0, pos + rng.randrange(-600, 600))
+        L = rng.choice([0, 1, 30, 100, 150, 150, 150, 151, 250, 300])
+        t = rng.randrange(9)
+        if not placed or t == 0 or L == 0:
+            cigar = []
+        elif t == 1:
+            cigar = [("M", L)]
+        elif t == 2:
+            a = min(L - 1, rng.choice([5, 16, 17, 40, 100])) if L > 1 else 0
+            cigar = [("S", a), ("M", L - a)] if a else [("M", L)]
+        elif t == 3:
+            a = min(L - 1, rng.choice([5, 16, 17, 40, 100])) if L > 1 else 0
+            cigar = [("M", L - a), ("S", a)] if a else [("M", L)]
+        elif t == 4 and L >= 60:
+            a, c = rng.choice([10, 17, 25]), rng.choice([16, 17, 30])
+            cigar = [("S", a), ("M", L - a - c), ("S", c)]
+        elif t == 5:
+            cigar = [("S", L)]                         # one op: add_soft takes it as "left" twice
+        elif t == 6 and L >= 120:
+            cigar = [("H", 5), ("S", 20), ("M", 30), ("I", 3), ("M", 20), ("D", 4), ("N", 50), ("M", L - 20 - 30 - 3 - 20 - 18), ("S", 18), ("H", 3)]
+        elif t == 7 and L >= 30:
+            cigar = [("=", 10), ("X", 1), ("=", L - 11)]
+        else:
+            cigar = [("M", L)]
+        seq = seq_of(L, rng.choice([0, 0, 1, 1, 2, 2, 3]))
+        isize = rng.choice([0, 300, 350, 400, 450, 4095, 4096, -400, 10000])
+        recs.append(bamio.Aln(rng.choice(pool), flag, tid, pos, rng.choice([0, 10, 19, 20, 39, 40, 41, 60]), cigar, mtid, mpos, isize, seq))
+    placed = sorted((a for a in recs if a.tid >= 0), key=lambda a: (a.tid, a.pos))
+    return placed + [a for a in recs if a.tid < 0]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_extract_host_logic_on_random_records(cli, tmp_path, seed):
+    """Fuzz of the host half of `strling extract` against the oracle's restatement of extract.nim:20-248: records no aligner would
+    write (see _fuzz_records), a genome-STR bed on odd seeds, p / min_mapq varied, small batches and several replay shards; the
+    .bin must equal the oracle's byte for byte."""
+    import random
+    rng = random.Random(1000 + seed)
+    targets = [("chr1", 200_000), ("chr2", 150_000), ("chrM", 20_000)]
+    recs = _fuzz_records(rng, 2500, targets)
+    hdr = bamio.sam_header(targets)
+    bam, segs_path, res_path, out = (str(tmp_path / n) for n in ("f.bam", "segs.tsv", "res.bin", "f.bin"))
+    bamio.write_bam(bam, hdr, targets, recs)
+    p, q = [(0.8, 40), (0.7, 20), (0.9, 0), (0.85, 41)][seed % 4]
+    extra, genome_str = [], None
+    if seed % 2:
+        bed = str(tmp_path / "ref.str")
+        with open(bed, "w") as fh:
+            for k in range(60):
+                t = rng.randrange(len(targets))
+                s = rng.randrange(0, targets[t][1] - 3000)
+                fh.write(f"{targets[t][0]}\t{s}\t{s + rng.randrange(1, 2500)}\tCAG\n")
+        extra = [bed]
+        genome_str = eo.read_bed(bed)
+    env = {"STRLING_DEBUG_THREADS": str(1 + seed % 5), "STRLING_DEBUG_SHARDS": str(1 + seed % 4)}
+    batch = str([100000, 64, 257][seed % 3])
+    run(cli, "debug", "extract", "dump", segs_path, bam, out, repr(p), str(q), batch, *extra, env=env)
+    classes = [p, p - 0.07, min(p, 0.6)]
+    lines = open(segs_path).read().splitlines()
+    res = np.zeros(len(lines), dtype=[("unit", "S6"), ("repeat_count", "<u2")])
+    for i, l in enumerate(lines):
+        cls, _, seq = l.partition("\t")
+        unit, count = orc.get_repeat(seq, classes[int(cls)])
+        res["unit"][i], res["repeat_count"][i] = unit, count
+    res.tofile(res_path)
+    run(cli, "debug", "extract", "replay", res_path, bam, out, repr(p), str(q), batch, *extra, env=env)
+    exp, cache, _ = eo.extract(recs, targets, hdr, p, q, genome_str)
+    assert len(cache) > 20
+    assert open(out, "rb").read() == exp
