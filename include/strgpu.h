@@ -8,7 +8,8 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * strgpu_status; nothing aborts or exits (the reference `quit`s / doAsserts -- the shim maps a non-zero
  * status to `quit`).  One ctx per GPU; a ctx may be shared by ONE submitting and ONE waiting host thread (slot
- * bookkeeping is locked inside the library), every other use is one thread at a time.  All structs are little-endian PODs with the
+ * bookkeeping is locked inside the library) and, beside them, ONE thread calling strgpu_inflate_bgzf (own stream, own
+ * buffers, own lock); every other use is one thread at a time.  All structs are little-endian PODs with the
  * exact layouts below (static_asserted in the implementation).
  */
 #ifndef STRGPU_H
