@@ -572,6 +572,10 @@ def run_ours(args):
     return 0
 
 
+# (n_pairs, seed) of `strling debug synth-bam` -> md5 of the .bin the oracle pipeline writes for it (tools/cli_oracle_md5.py)
+CLI_BIN_MD5_ORACLE = {(3_000_000, 2): "ab5b3864dcff18faea27cd62b6b20932"}
+
+
 def cli_leg(local: int, n_pairs: int = 3_000_000):
     """What a user runs: `strling extract` (BGZF inflate + BAM decode + staging on the host cores, scan on the GPU, mate pairing
     replay, .bin) on a synthetic coordinate-sorted BAM in the shape of configs[1] (6x10^6 150-bp reads, `strling debug synth-bam`:
@@ -609,6 +613,16 @@ def cli_leg(local: int, n_pairs: int = 3_000_000):
     # `--gpu-inflate` uses by default; kernel 4 (warp-cooperative copies at kernel 1's occupancy) was written after the round's GPU
     # time was spent and has not run on hardware before this line: whatever it does is recorded here.
     ref_bytes = open(out, "rb").read()
+    # parity of the whole command line at this size: the md5 of the .bin against the one the ORACLE pipeline gives for the same
+    # synthetic BAM (tools/cli_oracle_md5.py: staged segments scanned by oracle/liboracle.so, replayed by `strling debug extract`;
+    # computed in the build container, no GPU involved; the records do not depend on the deflate level)
+    import hashlib
+
+    res["bin_md5"] = hashlib.md5(ref_bytes).hexdigest()
+    expected = CLI_BIN_MD5_ORACLE.get((n_pairs, 2))
+    if expected:
+        res["bin_md5_oracle"] = expected
+        res["bin_equals_oracle"] = res["bin_md5"] == expected
     for key, kernel, extra in (("gpu_inflate", "1", []), ("gpu_inflate_kernel4_untested", "4", ["--batch-reads", "524288"])):
         try:
             out2 = os.path.join(d, f"bench_{key}.bin")
