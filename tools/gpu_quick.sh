@@ -10,6 +10,8 @@ O=gpurun_out/q
 $B debug synth-bam /tmp/big.bam 3000000 > ${O}_synth.txt 2>&1
 perf() { grep -E "perf|gpu:|rror" | sed 's/.*perf: //'; }
 echo "host" > ${O}_runs.txt; timeout 60 $B extract -v /tmp/big.bam /tmp/c.bin 2>&1 | perf >> ${O}_runs.txt
+# the oracle pipeline's .bin for this BAM (tools/cli_oracle_md5.py 3000000 2): md5 ab5b3864dcff18faea27cd62b6b20932
+md5sum /tmp/c.bin > ${O}_cmp.txt
 for k in 1 2 3; do
   echo "gpu-inflate kernel $k" >> ${O}_runs.txt
   STRGPU_INFLATE_KERNEL=$k timeout 60 $B extract -v --gpu-inflate /tmp/big.bam /tmp/d$k.bin 2>&1 | perf >> ${O}_runs.txt
