@@ -1,17 +1,20 @@
 // `strling debug ...`: CPU-only introspection of the host side (BAM decode, `.bin` codec, pair arithmetic) so that
 // tests can compare it with the oracle without a GPU.  Not part of the reference CLI.
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include "bam.hpp"
 #include "commands.hpp"
 #include "mate_table.hpp"
+#include "pool.hpp"
 #include "tread.hpp"
 
 namespace strling {
@@ -75,6 +78,42 @@ int debug_main(int argc, char **argv) {
   if (what == "synth-bam" && argc >= 3)  // strling debug synth-bam <out.bam> <n_pairs> [seed] [deflate level] [threads]
     return synth_bam(argv[1], (uint64_t)std::atoll(argv[2]), argc >= 4 ? (uint64_t)std::atoll(argv[3]) : 2, argc >= 5 ? std::atoi(argv[4]) : 1,
                      argc >= 6 ? std::atoi(argv[5]) : 0);
+  if (what == "pool-selftest") {
+    // pool.hpp: three threads submit jobs of different priorities at the same time (as the reader, stager and consumer of extract
+    // do); every task must run exactly once, run() must not return before its job is done, and a throwing task must surface in
+    // the caller of that job only
+    const int threads = argc >= 2 ? std::atoi(argv[1]) : 6;
+    Pool pool(threads);
+    std::atomic<long> bad{0};
+    auto submitter = [&](int prio, int rounds, size_t n) {
+      for (int r = 0; r < rounds; r++) {
+        std::vector<std::atomic<int>> hit(n);
+        for (auto &h : hit) h = 0;
+        bool threw = false;
+        const bool want_throw = (r % 7) == 3;
+        try {
+          pool.run(n, [&](size_t i) {
+            hit[i]++;
+            if (want_throw && i == n / 2) throw std::runtime_error("task failed");
+            volatile uint64_t x = 0;
+            for (int k = 0; k < 200 + (int)(i % 50) * 20; k++) x += (uint64_t)k * i;
+          }, prio);
+        } catch (const std::exception &) {
+          threw = true;
+        }
+        if (threw != want_throw) bad++;
+        for (auto &h : hit)
+          if (h != 1) bad++;
+      }
+    };
+    std::thread a(submitter, 0, 300, (size_t)997), b(submitter, 1, 400, (size_t)64), c(submitter, 2, 500, (size_t)5);
+    a.join(); b.join(); c.join();
+    size_t covered = 0;
+    pool.ranges(1000003, 37, [&](size_t lo, size_t hi, size_t) { __atomic_fetch_add(&covered, hi - lo, __ATOMIC_RELAXED); });
+    if (covered != 1000003) bad++;
+    std::printf(bad == 0 ? "ok\n" : "FAIL %ld\n", bad.load());
+    return bad == 0 ? 0 : 1;
+  }
   if (what == "matetable-selftest") {
     // MateTable (the mate table of extract's replay) against std::unordered_map under random insert / find / take traffic: names of
     // 1..120 bytes (inline and heap storage), growth from 1024 slots to hundreds of thousands of live entries, and -- with a degraded

@@ -39,8 +39,16 @@ class Pool {
   // priority first: the later a stage sits in the pipeline the higher its priority, so that batches drain.
   void run(size_t n, const std::function<void(size_t)> &f, int priority = 0) {
     if (n == 0) return;
-    if (n == 1 || n_ == 1) {
-      for (size_t i = 0; i < n; i++) f(i);
+    if (n == 1 || n_ == 1) {   // inline, with the same contract: every task runs, the first exception is rethrown at the end
+      std::string err;
+      for (size_t i = 0; i < n; i++) {
+        try {
+          f(i);
+        } catch (const std::exception &e) {
+          if (err.empty()) err = e.what();
+        }
+      }
+      if (!err.empty()) throw std::runtime_error(err);
       return;
     }
     auto job = std::make_shared<Job>();

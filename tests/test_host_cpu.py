@@ -504,3 +504,9 @@ def test_extract_host_logic_on_random_records(cli, tmp_path, seed):
     exp, cache, _ = eo.extract(recs, targets, hdr, p, q, genome_str)
     assert len(cache) > 20
     assert open(out, "rb").read() == exp
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_thread_pool_contract(cli, threads):
+    """host/pool.hpp: concurrent submitters with different priorities, every task exactly once, exceptions surface in their own job."""
+    assert run(cli, "debug", "pool-selftest", threads).strip() == "ok"
