@@ -66,7 +66,11 @@ DIRECT = textwrap.dedent("""
 """)
 
 
-@pytest.mark.parametrize("kernel", ["1", "2", "3"])
+# kernel 4 was written after the round's GPU time was spent and has not run on hardware: it may fail without failing the suite
+KERNEL4 = pytest.param("4", marks=pytest.mark.xfail(strict=False, reason="inflate kernel 4 has not run on hardware yet (env-selected, experimental)"))
+
+
+@pytest.mark.parametrize("kernel", ["1", "2", "3", KERNEL4])
 def test_gpu_inflate_matches_zlib(kernel):
     """400 blocks through strgpu_inflate_bgzf: stored / fixed / dynamic DEFLATE blocks of every zlib level and strategy, sizes 0..65280,
     incompressible data (payload larger than kernel 3's staging buffer) -- byte-identical to the input of zlib's encoder, nothing
