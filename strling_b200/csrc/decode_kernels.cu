@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(32) inflate_bgzf_blocks_v2(const uint8_t *__re
   for (uint32_t i = lane; i < blk.isize; i += 32) dst[i] = window[i];
 }
 
-// Kernel 4 (written after the round's GPU time was spent: NOT run on hardware yet, selectable with STRGPU_INFLATE_KERNEL=4 only, not
-// covered by the -m gpu tests; bench.py's cli leg tries it in a child process and records what happened).  What the measurements of
+// Kernel 4 (written after the round's GPU time was spent: NOT run on hardware yet, selectable with STRGPU_INFLATE_KERNEL=4 only; in the
+// -m gpu tests as an xfail(strict=False) case, and bench.py's cli leg tries it in a child process and records what happened).  What the measurements of
 // kernels 1-3 say is wanted: kernel 1's occupancy (tables only in shared memory, ~2200 blocks in flight) with kernel 2's copies (a
 // match is ONE round trip to L2 for the warp instead of one per byte on a single lane).  So: the command-stream decoder of kernel 2 on
 // lane 0, but the window is the block's place in the global output buffer itself; literals are plain stores, the 32 lanes copy a
